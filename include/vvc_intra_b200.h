@@ -1,0 +1,158 @@
+/*
+ * vvc_intra_b200 -- C ABI of the B200 intra cost-evaluation engine.
+ *
+ * Drop-in boundary for the per-CTU intra cost evaluation behind EncCu::xCompressCU of the VTM 6.1
+ * fork llsurreal919/Reduce-Complexity-for-intra-coding-of-VVC.  The reference has no FFI for this
+ * path; each entry point below names the reference call it replaces.  Abbreviations:
+ * EL/ = VVC_project/source/Lib/EncoderLib/, CL/ = VVC_project/source/Lib/CommonLib/.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no C++ types; every function returns VVCB_OK (0) or a negative
+ *     error code, vvcb_last_error() gives the text (the reference throws Exception, CL/TypeDef.h:1322;
+ *     a host shim turns a non-zero status back into CHECK/THROW).
+ *   - sample planes are int16_t (Pel, CL/TypeDef.h:488), row-major, stride in samples (CL/Buffer.h:99).
+ *   - all calls are synchronous from the caller's view; one context per host thread / frame in flight.
+ *   - there is no CPU fallback: without a CUDA device every call fails with VVCB_ERR_CUDA.
+ */
+#ifndef VVC_INTRA_B200_H
+#define VVC_INTRA_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VVCB_OK            0
+#define VVCB_ERR_ARG      -1
+#define VVCB_ERR_CUDA     -2
+#define VVCB_ERR_STATE    -3
+
+/* ---- evaluation slots of one RMD visit -------------------------------------------------------
+ * slot 0..66     regular mode m, reference line 0            (EL/IntraSearch.cpp:489-532, 577-623)
+ * slot 67..71    MPM[1..5] on reference line 1               (EL/IntraSearch.cpp:635-681)
+ * slot 72..76    MPM[1..5] on reference line 3
+ * slot 77..111   MIP mode 0..34                              (EL/IntraSearch.cpp:704-743)          */
+#define VVCB_NUM_LUMA_MODE   67
+#define VVCB_SLOT_MRL1       67
+#define VVCB_SLOT_MRL3       72
+#define VVCB_SLOT_MIP        77
+#define VVCB_NUM_SLOTS       112
+#define VVCB_MAX_LIST        16
+#define VVCB_SAT_NONE        0xFFFFFFFFu   /* slot not evaluated for this visit */
+
+/* Fractional-bit prices (SCALE_BITS = 15 fixed point, CL/CommonDef.h:354) of the context-coded bins
+ * that xFracModeBitsIntra (EL/IntraSearch.cpp:4263) can touch, read from the CABAC estimator's
+ * context snapshot at visit entry (EL/IntraSearch.cpp:301-309).  Bypass bins cost 1<<15.           */
+typedef struct vvcb_rates {
+  uint32_t mip_flag[2];     /* Ctx::MipFlag(DeriveCtx::CtxMipFlag(cu)), bin 0/1   EL/CABACWriter.cpp:4741 */
+  uint32_t mrl_bin0[2];     /* Ctx::MultiRefLineIdx(0)                            EL/CABACWriter.cpp:1566 */
+  uint32_t mrl_bin1[2];     /* Ctx::MultiRefLineIdx(1)                                                    */
+  uint32_t isp_bin0_0;      /* Ctx::ISPMode(0), bin 0 (ispMode == 0 during RMD)   EL/CABACWriter.cpp:3944 */
+  uint32_t mpm_flag[2];     /* Ctx::IntraLumaMpmFlag()                            EL/CABACWriter.cpp:1762 */
+  uint32_t planar_flag[2];  /* Ctx::IntraLumaPlanarFlag(1)                                                */
+} vvcb_rates;
+
+/* One call of the SATD rough-mode-decision part of IntraSearch::estIntraPredLumaQT
+ * (EL/IntraSearch.cpp:430-802) for one luma CU.                                                   */
+typedef struct vvcb_rmd_visit {
+  int16_t  x, y;              /* luma position in the picture                                          */
+  uint8_t  log2w, log2h;      /* 2..6                                                                  */
+  /* reference-sample availability in units of 4 samples, as counted by is*Available()
+   * (CL/IntraPrediction.cpp:1524-1662): prefix lengths, because constrained intra pred is off.       */
+  uint8_t  avail_al;          /* 0/1                                                                   */
+  uint8_t  n_above;           /* 0..w/4                                                                */
+  uint8_t  n_above_right;     /* 0..w/4                                                                */
+  uint8_t  n_left;            /* 0..h/4                                                                */
+  uint8_t  n_below_left;      /* 0..h/4                                                                */
+  uint8_t  flags;             /* VVCB_VISIT_*                                                          */
+  uint8_t  mpm[6];            /* PU::getIntraMPMs (CL/UnitTools.cpp:507)                               */
+  uint8_t  num_mpm_cand;      /* its return value (1 or 2): MPMs appended to the RD list (:777-802)    */
+  uint8_t  pad[3];
+  vvcb_rates rates;
+  double   sqrt_lambda;       /* RdCost::getMotionLambda() * FRAC_BITS_SCALE (EL/IntraSearch.cpp:297)  */
+} vvcb_rmd_visit;
+
+#define VVCB_VISIT_NO_MRL   1u   /* skip the multi-reference-line pass (derived from y & (ctu-1) if 0)  */
+#define VVCB_VISIT_NO_MIP   2u   /* sps.getUseMIP() == false                                            */
+
+typedef struct vvcb_mode {
+  uint8_t mip;                /* ModeInfo::mipFlg (EL/IntraSearch.h:190)                               */
+  uint8_t mrl;                /* ModeInfo::mRefId: 0, 1 or 3                                           */
+  uint8_t mode;               /* ModeInfo::modeId                                                      */
+  uint8_t pad;
+} vvcb_mode;
+
+typedef struct vvcb_rmd_result {
+  uint32_t  sad [VVCB_NUM_SLOTS];   /* RdCost::xGetSAD  (CL/RdCost.cpp:449);  VVCB_SAT_NONE if skipped  */
+  uint32_t  satd[VVCB_NUM_SLOTS];   /* RdCost::xGetHADs (CL/RdCost.cpp:2746)                            */
+  /* uiRdModeList / CandCostList after the MIP pass and reduceHadCandList (EL/IntraSearch.cpp:747),
+   * i.e. what the reference saves at :753-762; costs are IEEE doubles computed in reference order.   */
+  int32_t   n_rd;
+  vvcb_mode rd_mode[VVCB_MAX_LIST];
+  double    rd_cost[VVCB_MAX_LIST];
+  /* uiHadModeList / CandHadList (PBINTRA list, :531, :738)                                           */
+  int32_t   n_had;
+  vvcb_mode had_mode[VVCB_MAX_LIST];
+  double    had_cost[VVCB_MAX_LIST];
+  /* regular-only list as it stood before the MIP pass (what :686-701 saves for small blocks)         */
+  int32_t   n_reg;
+  vvcb_mode reg_mode[VVCB_MAX_LIST];
+  double    reg_cost[VVCB_MAX_LIST];
+  int32_t   n_reg_had;
+  vvcb_mode reg_had_mode[VVCB_MAX_LIST];
+  double    reg_had_cost[VVCB_MAX_LIST];
+  /* final full-RD candidate list: rd list + missing MPMs (:777-802)                                  */
+  int32_t   n_final;
+  vvcb_mode final_mode[VVCB_MAX_LIST];
+} vvcb_rmd_result;
+
+typedef struct vvcb_ctx vvcb_ctx;
+
+/* ---- life cycle (replaces IntraPrediction::init CL/IntraPrediction.cpp:177, RdCost::init
+ *      CL/RdCost.cpp:92, initROM CL/Rom.cpp:263 for this path) ---------------------------------- */
+int  vvcb_create (vvcb_ctx** out, int device, int bit_depth, int ctu_size);
+void vvcb_destroy(vvcb_ctx* ctx);
+const char* vvcb_last_error(const vvcb_ctx* ctx);   /* ctx may be NULL: error of the last failed create */
+int  vvcb_device_count(void);
+
+/* ---- picture planes -------------------------------------------------------------------------
+ * frame_begin uploads the (LMCS-mapped) original luma, which is constant during the CTU loop
+ * (EL/EncGOP.cpp:1692), and clears the reconstruction plane.  reco_update pushes the rectangle the
+ * host has just decided (EncCu::xCompressCU copies the winner into the picture, EL/EncCu.cpp:1581;
+ * xRecurIntraCodingLumaQT per tested mode, EL/IntraSearch.cpp:3761).                               */
+int vvcb_frame_begin(vvcb_ctx* ctx, const int16_t* orig, int stride, int width, int height);
+int vvcb_reco_update(vvcb_ctx* ctx, const int16_t* reco, int stride, int x, int y, int w, int h);
+
+/* ---- rough mode decision: intra prediction + SAD/SATD + mode cost + candidate lists ---------
+ * Replaces the RMD block of IntraSearch::estIntraPredLumaQT (EL/IntraSearch.cpp:430-802) for a
+ * batch of independent visits: initIntraPatternChType (CL/IntraPrediction.cpp:1064), predIntraAng
+ * (:316), initIntraMip/predIntraMip (:2152/:2177), RdCost::xGetSAD/xGetHADs, xFracModeBitsIntra,
+ * updateCandList (CL/UnitTools.h:261) and reduceHadCandList (EL/IntraSearch.cpp:4333).
+ * visits/results are HOST arrays; copies in both directions happen inside the call.             */
+int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results);
+
+/* Same work with visits/results already resident on the device (device pointers from
+ * vvcb_dev_alloc); used to time the kernels without the PCIe copies.                            */
+int vvcb_rmd_eval_device(vvcb_ctx* ctx, const void* d_visits, int n, void* d_results);
+
+/* Prediction samples of one evaluation slot (debug / parity): writes w*h samples.               */
+int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t* pred);
+
+/* ---- raw device memory for resident benchmarking --------------------------------------------- */
+int vvcb_dev_alloc(vvcb_ctx* ctx, size_t bytes, void** out);
+int vvcb_dev_free (vvcb_ctx* ctx, void* p);
+int vvcb_dev_upload  (vvcb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int vvcb_dev_download(vvcb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int vvcb_sync(vvcb_ctx* ctx);
+/* CUDA-event timing on the context's own stream (torch.cuda.Event cannot see it).               */
+int vvcb_timer_start(vvcb_ctx* ctx);
+int vvcb_timer_stop (vvcb_ctx* ctx, float* ms);
+/* kernel launches issued by this context since creation (bench.py reports the delta).           */
+uint64_t vvcb_launch_count(const vvcb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

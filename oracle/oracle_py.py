@@ -1,0 +1,185 @@
+"""ctypes binding of the plain-C oracle (oracle/libvvc_oracle.so).
+
+TEST INFRASTRUCTURE: import only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+
+NUM_SLOTS, MAX_LIST = 112, 16
+SLOT_MRL1, SLOT_MRL3, SLOT_MIP = 67, 72, 77
+SAT_NONE = 0xFFFFFFFF
+
+
+class Rates(C.Structure):
+    _fields_ = [('mip_flag', C.c_uint32 * 2), ('mrl_bin0', C.c_uint32 * 2), ('mrl_bin1', C.c_uint32 * 2),
+                ('isp_bin0_0', C.c_uint32), ('mpm_flag', C.c_uint32 * 2), ('planar_flag', C.c_uint32 * 2)]
+
+
+class RmdVisit(C.Structure):
+    _fields_ = [('x', C.c_int16), ('y', C.c_int16), ('log2w', C.c_uint8), ('log2h', C.c_uint8),
+                ('avail_al', C.c_uint8), ('n_above', C.c_uint8), ('n_above_right', C.c_uint8),
+                ('n_left', C.c_uint8), ('n_below_left', C.c_uint8), ('flags', C.c_uint8),
+                ('mpm', C.c_uint8 * 6), ('num_mpm_cand', C.c_uint8), ('pad', C.c_uint8 * 3),
+                ('rates', Rates), ('sqrt_lambda', C.c_double)]
+
+
+class Mode(C.Structure):
+    _fields_ = [('mip', C.c_uint8), ('mrl', C.c_uint8), ('mode', C.c_uint8), ('pad', C.c_uint8)]
+
+
+class RmdResult(C.Structure):
+    _fields_ = [('sad', C.c_uint32 * NUM_SLOTS), ('satd', C.c_uint32 * NUM_SLOTS),
+                ('n_rd', C.c_int32), ('rd_mode', Mode * MAX_LIST), ('rd_cost', C.c_double * MAX_LIST),
+                ('n_had', C.c_int32), ('had_mode', Mode * MAX_LIST), ('had_cost', C.c_double * MAX_LIST),
+                ('n_reg', C.c_int32), ('reg_mode', Mode * MAX_LIST), ('reg_cost', C.c_double * MAX_LIST),
+                ('n_reg_had', C.c_int32), ('reg_had_mode', Mode * MAX_LIST), ('reg_had_cost', C.c_double * MAX_LIST),
+                ('n_final', C.c_int32), ('final_mode', Mode * MAX_LIST)]
+
+
+class Ipa(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ('is_ver', 'mrl', 'ref_filter', 'interp', 'pdpc', 'angle', 'inv_angle', 'ang_scale')]
+
+
+VISIT_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('log2w', 'u1'), ('log2h', 'u1'), ('avail_al', 'u1'),
+                        ('n_above', 'u1'), ('n_above_right', 'u1'), ('n_left', 'u1'), ('n_below_left', 'u1'),
+                        ('flags', 'u1'), ('mpm', 'u1', 6), ('num_mpm_cand', 'u1'), ('pad', 'u1', 3),
+                        ('rates', '<u4', 11), ('sqrt_lambda', '<f8')], align=True)
+MODE_DTYPE = np.dtype([('mip', 'u1'), ('mrl', 'u1'), ('mode', 'u1'), ('pad', 'u1')])
+
+
+def _list(prefix, cost=True):
+    f = [('n_' + prefix, '<i4'), (prefix + '_mode', MODE_DTYPE, MAX_LIST)]
+    if cost:
+        f.append((prefix + '_cost', '<f8', MAX_LIST))
+    return f
+
+
+RESULT_DTYPE = np.dtype([('sad', '<u4', NUM_SLOTS), ('satd', '<u4', NUM_SLOTS)] + _list('rd') + _list('had') +
+                        _list('reg') + _list('reg_had') + _list('final', cost=False), align=True)
+assert VISIT_DTYPE.itemsize == C.sizeof(RmdVisit), (VISIT_DTYPE.itemsize, C.sizeof(RmdVisit))
+assert RESULT_DTYPE.itemsize == C.sizeof(RmdResult), (RESULT_DTYPE.itemsize, C.sizeof(RmdResult))
+
+_lib = None
+_p16 = C.POINTER(C.c_int16)
+
+
+def build():
+    subprocess.check_call(['make', '-s', '-f', 'oracle/Makefile'], cwd=_ROOT)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, 'libvvc_oracle.so')
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_sad.restype = C.c_uint64
+        L.orc_satd.restype = C.c_uint64
+        L.orc_mode_bits.restype = C.c_uint64
+        L.orc_fnv1a.restype = C.c_uint64
+        _lib = L
+    return _lib
+
+
+def _a16(a):
+    a = np.ascontiguousarray(a, dtype=np.int16)
+    return a, a.ctypes.data_as(_p16)
+
+
+def ref_fill(reco, x, y, w, h, mrl, bd, avail_al, n_above, n_above_right, n_left, n_below_left):
+    reco, pr = _a16(reco)
+    top = np.zeros(2 * w + 1 + mrl, np.int16)
+    left = np.zeros(2 * h + 1 + mrl, np.int16)
+    lib().orc_ref_fill(pr, reco.shape[1], x, y, w, h, mrl, bd, avail_al, n_above, n_above_right, n_left, n_below_left,
+                       top.ctypes.data_as(_p16), left.ctypes.data_as(_p16))
+    return top, left
+
+
+def ref_filter(top, left, w, h, mrl):
+    top, pt = _a16(top)
+    left, pl = _a16(left)
+    ft, fl = np.zeros_like(top), np.zeros_like(left)
+    lib().orc_ref_filter(pt, pl, w, h, mrl, ft.ctypes.data_as(_p16), fl.ctypes.data_as(_p16))
+    return ft, fl
+
+
+def ipa_init(w, h, mode, mrl, is_mip=0):
+    p = Ipa()
+    lib().orc_ipa_init(w, h, mode, mrl, is_mip, C.byref(p))
+    return p
+
+
+def pred_regular(top, left, w, h, bd, mode, ipa):
+    top, pt = _a16(top)
+    left, pl = _a16(left)
+    pred = np.zeros((h, w), np.int16)
+    lib().orc_pred_regular(pt, pl, w, h, bd, mode, C.byref(ipa), pred.ctypes.data_as(_p16))
+    return pred
+
+
+def pred_mip(top, left, w, h, bd, mode):
+    top, pt = _a16(top)
+    left, pl = _a16(left)
+    pred = np.zeros((h, w), np.int16)
+    lib().orc_pred_mip(pt, pl, w, h, bd, mode, pred.ctypes.data_as(_p16))
+    return pred
+
+
+def sad(org, cur):
+    org, po = _a16(org)
+    cur, pc = _a16(cur)
+    h, w = org.shape
+    return lib().orc_sad(po, w, pc, w, w, h)
+
+
+def satd(org, cur):
+    org, po = _a16(org)
+    cur, pc = _a16(cur)
+    h, w = org.shape
+    return lib().orc_satd(po, w, pc, w, w, h)
+
+
+def fnv1a(a):
+    a, p = _a16(a)
+    return lib().orc_fnv1a(p, a.size)
+
+
+def mode_bits(rates11, mpm, w, h, mrl_allowed, mip_enabled, is_mip, mrl, mode):
+    r = Rates.from_buffer_copy(np.asarray(rates11, '<u4').tobytes())
+    m = (C.c_uint8 * 6)(*[int(v) for v in mpm])
+    return lib().orc_mode_bits(C.byref(r), m, w, h, int(mrl_allowed), int(mip_enabled), int(is_mip), mrl, mode)
+
+
+def intra_mpms(left_dir, above_dir):
+    m = (C.c_uint8 * 6)()
+    n = C.c_int()
+    lib().orc_intra_mpms(left_dir, above_dir, m, C.byref(n))
+    return list(m), n.value
+
+
+def rmd_batch(orig, reco, bd, ctu_size, visits, want_pred=False):
+    """visits: numpy array of VISIT_DTYPE.  Returns numpy array of RESULT_DTYPE (and preds list)."""
+    orig, po = _a16(orig)
+    reco, pr = _a16(reco)
+    visits = np.ascontiguousarray(visits, dtype=VISIT_DTYPE)
+    out = np.zeros(len(visits), RESULT_DTYPE)
+    if not want_pred:
+        lib().orc_rmd_batch(po, orig.shape[1], pr, reco.shape[1], bd, ctu_size,
+                            visits.ctypes.data_as(C.c_void_p), len(visits), out.ctypes.data_as(C.c_void_p))
+        return out
+    preds = []
+    for i in range(len(visits)):
+        w, h = 1 << int(visits[i]['log2w']), 1 << int(visits[i]['log2h'])
+        p = np.zeros((NUM_SLOTS, h, w), np.int16)
+        lib().orc_rmd_visit(po, orig.shape[1], pr, reco.shape[1], bd, ctu_size,
+                            C.c_void_p(visits[i:i + 1].ctypes.data), C.c_void_p(out[i:i + 1].ctypes.data),
+                            p.ctypes.data_as(_p16))
+        preds.append(p)
+    return out, preds

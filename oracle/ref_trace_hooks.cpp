@@ -83,7 +83,8 @@ int    g_visitStride = 1;     // keep every Nth RMD visit per shape ...
 int    g_visitFirst  = 4;     // ... after always keeping the first K of each shape
 int    g_tuStride    = 64;    // keep every Nth transform call per shape
 int    g_tuFirst     = 2;
-int    g_fullPred    = 0;     // 1: store prediction samples, 0: only their hash
+int    g_fullPred    = 0;     // store prediction samples (not only their hash) for the first N visits of each shape
+bool   g_curFull     = false;
 int    g_maxVisits   = 1 << 30;
 
 IntraSearch* g_is      = nullptr;
@@ -205,6 +206,7 @@ bool __wrap__ZN11IntraSearch18estIntraPredLumaQTER10CodingUnitR11Partitionerdbii
   {
     int& n = g_shapeCount[w * 256 + h];
     keep   = n < g_visitFirst || ( n % g_visitStride ) == 0;
+    g_curFull = n < g_fullPred;
     n++;
   }
   g_is = is;
@@ -338,8 +340,8 @@ static void emitPred( IntraPrediction* ip, const PelBuf& pred, const PredictionU
   r.u64( refDist( org, pred, bd, true ) );
   std::vector<int16_t> v = flat( pred );
   r.u64( fnv1a( v.data(), v.size() ) );
-  r.i32( g_fullPred );
-  if( g_fullPred ) for( int16_t s : v ) r.i16( s );
+  r.i32( g_curFull );
+  if( g_curFull ) for( int16_t s : v ) r.i16( s );
   r.emit( 'P' );
 }
 

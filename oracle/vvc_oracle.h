@@ -1,0 +1,57 @@
+/*
+ * TEST INFRASTRUCTURE -- CPU restatement ("oracle") of the reference's intra cost-evaluation path.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library; the
+ * product (libvvc_intra_b200.so) never links or calls it.
+ *
+ * Parity status: PINNED.  Every function here is checked against records captured from the
+ * unmodified reference encoder (oracle/ref_trace_hooks.cpp -> tests/golden/ fixtures) by
+ * tests/test_oracle_golden.py.
+ */
+#ifndef VVC_ORACLE_H
+#define VVC_ORACLE_H
+#include <stdint.h>
+#include "../include/vvc_intra_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* IntraPrediction::m_ipaParam as derived by initPredIntraParams (CL/IntraPrediction.cpp:487-618) */
+typedef struct orc_ipa {
+  int is_ver, mrl, ref_filter, interp, pdpc, angle, inv_angle, ang_scale;
+} orc_ipa;
+
+/* a1/a2: reference lines.  top has 2w+1+mrl samples, left has 2h+1+mrl; top[0] == left[0]. */
+void orc_ref_fill(const int16_t* reco, int stride, int x, int y, int w, int h, int mrl, int bd,
+                  int avail_al, int n_above, int n_above_right, int n_left, int n_below_left,
+                  int16_t* top, int16_t* left);
+/* a3 */
+void orc_ref_filter(const int16_t* top, const int16_t* left, int w, int h, int mrl, int16_t* ftop, int16_t* fleft);
+/* a4 */
+void orc_ipa_init(int w, int h, int mode, int mrl, int is_mip, orc_ipa* p);
+/* a5: regular prediction from the lines selected by the caller (filtered iff p->ref_filter) */
+void orc_pred_regular(const int16_t* top, const int16_t* left, int w, int h, int bd, int mode,
+                      const orc_ipa* p, int16_t* pred);
+/* a6: MIP prediction from unfiltered line-0 references */
+int  orc_mip_num_modes(int w, int h);
+void orc_pred_mip(const int16_t* top, const int16_t* left, int w, int h, int bd, int mode, int16_t* pred);
+/* a7/a8 */
+uint64_t orc_sad (const int16_t* org, int org_stride, const int16_t* cur, int cur_stride, int w, int h);
+uint64_t orc_satd(const int16_t* org, int org_stride, const int16_t* cur, int cur_stride, int w, int h);
+/* a10 */
+uint64_t orc_mode_bits(const vvcb_rates* r, const uint8_t mpm[6], int w, int h, int mrl_allowed,
+                       int mip_enabled, int is_mip, int mrl, int mode);
+void orc_intra_mpms(int left_dir, int above_dir, uint8_t mpm[6], int* num_cand);
+/* a9: the whole RMD of one visit, references fetched from the reco plane.
+ * pred_out (optional) receives VVCB_NUM_SLOTS blocks of w*h samples. */
+void orc_rmd_visit(const int16_t* orig, int orig_stride, const int16_t* reco, int reco_stride,
+                   int bd, int ctu_size, const vvcb_rmd_visit* v, vvcb_rmd_result* out, int16_t* pred_out);
+/* batch with an OpenMP-free pthread pool is overkill for a checker: plain loop */
+void orc_rmd_batch(const int16_t* orig, int orig_stride, const int16_t* reco, int reco_stride,
+                   int bd, int ctu_size, const vvcb_rmd_visit* v, int n, vvcb_rmd_result* out);
+uint64_t orc_fnv1a(const int16_t* p, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
