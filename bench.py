@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the intra cost-evaluation hot path (BASELINE.json: all-intra 1080p10 CTUs/sec).
+
+b200 arm (default): one "step" = the exhaustive rough-mode-decision sweep of ONE 1920x1080 10-bit frame:
+every candidate luma CU of every 64x64 root (679 260 visits) x every evaluation slot
+(67 regular modes, MPMs on reference lines 1 and 3, all MIP modes): reference-line fetch, prediction,
+SAD, SATD, mode bits, costs and the reference's candidate lists.  Steps cycle over 8 synthetic frames
+and QP 32/27/37/22.  `value` times the kernels with planes, visits and results resident in HBM; `e2e`
+times the same step through the C ABI with HOST buffers (page-locked), copies included.
+
+reference arm (--impl reference): the UNMODIFIED reference encoder (oracle/_ref/EncoderApp, built by
+__graft_entry__.build() from /root/reference) on the box's host cores, one process per 128x128 crop of
+the same synthetic frames -- a bounded sample of the same workload, all cores busy.
+
+Launch: python bench.py --gpus N --steps K --warmup W   (N > 1 under torchrun, one rank per GPU).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'tools')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+W, H, BITS, NFRAMES = 1920, 1080, 10, 8
+QPS = (32, 27, 37, 22)
+CTU = 128
+CTUS_PER_FRAME = ((W + CTU - 1) // CTU) * ((H + CTU - 1) // CTU)     # 15 x 9 = 135
+
+
+def synth_luma(frame):
+    from make_golden import synth_yuv
+    return synth_yuv(W, H, BITS, frame)[0].astype(np.int16)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured (MEASURED_PEAKS.json)'
+    except OSError:
+        return {'hbm_gbs': 6650.0}, 'fallback (B200_PROFILING.md)'
+
+
+def active_slot_counts(vis):
+    """Evaluation slots per visit, as the kernels count them."""
+    w, h = 1 << vis['log2w'].astype(np.int64), 1 << vis['log2h'].astype(np.int64)
+    mip = np.where((w > 4 * h) | (h > 4 * w), 0, np.where((w == 4) & (h == 4), 35, np.where((w <= 8) & (h <= 8), 19, 11)))
+    mrl = np.where((vis['y'].astype(np.int64) & (CTU - 1)) != 0, 10, 0)
+    return 67 + mrl + mip, w * h
+
+
+def run_b200(args, rank, world, local_rank, dist):
+    import vvc_intra_b200 as vb
+    peaks, peak_src = measured_peaks()
+    eng = vb.IntraCostEngine(device=local_rank, bit_depth=BITS, ctu_size=CTU)
+    base = vb.build_sweep_visits(W, H, qp=32, ctu=CTU)
+    n = len(base)
+    slots, area = active_slot_counts(base)
+    evals_per_step = int(slots.sum())
+    samples_per_step = int((slots * area).sum())
+    # algorithmic integer ops per predicted sample = 13 + log2(tile w) + log2(tile h)
+    satd_ops = np.where((area == 16), 6, np.where(np.minimum(1 << base['log2w'].astype(int), 1 << base['log2h'].astype(int)) == 4, 7,
+                        np.where(base['log2w'] == base['log2h'], 8, 9)))
+    ops_per_step = float((slots * area * (13 + satd_ops)).sum())
+    # algorithmic bytes per step: visit descriptors in, results + detail tables out, original samples once per visit,
+    # reference lines (2w+2h+1 samples per line, 3 lines)
+    w_, h_ = 1 << base['log2w'].astype(np.int64), 1 << base['log2h'].astype(np.int64)
+    bytes_per_step = float(n * (vb.VISIT_DTYPE.itemsize + vb.RESULT_DTYPE.itemsize + vb.DETAIL_DTYPE.itemsize)
+                           + (2 * area).sum() + (3 * 2 * (2 * w_ + 2 * h_ + 1)).sum())
+
+    frames = [synth_luma(f) for f in range(NFRAMES)]
+    # this rank's share of the (frame, qp) pairs: all-intra frames are independent -> no collective on the path
+    pairs = [(s % NFRAMES, QPS[s % len(QPS)]) for s in range(NFRAMES * len(QPS))]
+    mine = pairs[rank::world] if world > 1 else pairs
+
+    # ---- resident set-up
+    pitch = (W + 63) & ~63
+    d_planes = []
+    for f in range(NFRAMES):
+        padded = np.zeros((H, pitch), np.int16)
+        padded[:, :W] = frames[f]
+        d = eng.dev_alloc(padded.nbytes)
+        eng.dev_upload(d, padded)
+        d_planes.append(d)
+    d_vis = {}
+    for qp in QPS:
+        v = base.copy()
+        v['sqrt_lambda'] = vb.partition.sqrt_lambda_for_qp(qp)
+        d = eng.dev_alloc(v.nbytes)
+        eng.dev_upload(d, v)
+        d_vis[qp] = d
+    d_res = eng.dev_alloc(n * vb.RESULT_DTYPE.itemsize)
+    d_det = eng.dev_alloc(n * vb.DETAIL_DTYPE.itemsize)
+
+    def resident_step(s):
+        f, qp = mine[s % len(mine)]
+        eng.frame_bind_device(d_planes[f], d_planes[f], pitch, W, H)     # speculative sweep: neighbours from the original
+        eng.rmd_eval_device(d_vis[qp], n, d_res, d_det)
+
+    int_peak = eng.measure_int_peak()
+    for s in range(args.warmup):
+        resident_step(s)
+    eng.sync()
+    if dist is not None:
+        dist.barrier()
+    eng.kernel_timing(True)
+    launches0 = eng.launch_count
+    with ClockSampler(local_rank) as clk:
+        eng.sync()
+        eng.timer_start()
+        for s in range(args.steps):
+            resident_step(args.warmup + s)
+        ms_total = eng.timer_stop()
+        eng.sync()
+    k_plan, k_eval, k_lists, k_n = eng.kernel_times()
+    eng.kernel_timing(False)
+    launches = eng.launch_count - launches0
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_total], dtype=torch.float64, device='cuda:%d' % local_rank)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+
+    # ---- end to end through the C ABI with host buffers
+    h_vis = {}
+    for qp in QPS:
+        a = eng.host_array(n, vb.VISIT_DTYPE)
+        a[:] = base
+        a['sqrt_lambda'] = vb.partition.sqrt_lambda_for_qp(qp)
+        h_vis[qp] = a
+    h_res = eng.host_array(n, vb.RESULT_DTYPE)
+    h_frames = []
+    for f in range(NFRAMES):
+        a = eng.host_array(H * W, np.int16).reshape(H, W)
+        a[:] = frames[f]
+        h_frames.append(a)
+
+    def e2e_step(s):
+        f, qp = mine[s % len(mine)]
+        eng.frame_begin(h_frames[f])
+        eng.reco_update(h_frames[f])
+        eng.rmd_eval(h_vis[qp], out=h_res)
+        return int(h_res['n_rd'][0])
+
+    e2e_steps = max(1, min(args.steps, 4))
+    for s in range(2):
+        e2e_step(s)
+    eng.sync()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        e2e_step(2 + s)
+    eng.sync()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda:%d' % local_rank)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = 2 * H * W * 2 + n * vb.VISIT_DTYPE.itemsize
+    d2h = n * vb.RESULT_DTYPE.itemsize
+
+    if rank != 0:
+        return
+    ms_step = ms_total / args.steps
+    value = world * args.steps * CTUS_PER_FRAME / (ms_total * 1e-3)
+    eval_ms = k_eval / max(1, k_n)
+    hbm_achieved = bytes_per_step / (eval_ms * 1e-3) / 1e9 if eval_ms > 0 else 0.0
+    int_best = max(int_peak)
+    out = {
+        'metric': 'all-intra 1080p10 CTUs/sec (exhaustive RMD sweep: intra pred + SAD/SATD + mode cost + candidate lists)',
+        'value': value, 'unit': 'CTU/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'int16 samples / int32 arithmetic / f64 costs', 'data': 'synthetic',
+        'config': {'workload': 'configs[1]: all-intra 1920x1080 10-bit synthetic YUV, 8 frames, QP 22/27/32/37, one frame sweep per step',
+                   'visits_per_step': n, 'satd_evals_per_step': evals_per_step, 'ctus_per_step': CTUS_PER_FRAME,
+                   'predicted_samples_per_step': samples_per_step,
+                   'l2': 'per-step working set %.2f GB (visits + result tables) > 126 MB L2; consecutive steps use different frames' %
+                         ((n * (vb.VISIT_DTYPE.itemsize + vb.RESULT_DTYPE.itemsize + vb.DETAIL_DTYPE.itemsize)) / 1e9),
+                   'sharding': 'frames x QPs partitioned across ranks, no collective on the hot path'},
+        'satd_evals_per_s': world * args.steps * evals_per_step / (ms_total * 1e-3),
+        'e2e': {'value': world * e2e_steps * CTUS_PER_FRAME / e2e_s, 'unit': 'CTU/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
+                'note': 'vvcb_frame_begin + vvcb_reco_update + vvcb_rmd_eval with page-locked host buffers, wall clock'},
+        'gpu_launches': launches,
+        'clocks': clk.summary(),
+        'roofline': {'bound': 'hbm', 'kernel': 'rmd_eval_kernel', 'achieved': hbm_achieved, 'peak': peaks.get('hbm_gbs'), 'unit': 'GB/s',
+                     'frac': hbm_achieved / peaks.get('hbm_gbs') if peaks.get('hbm_gbs') else None, 'traffic': None,
+                     'peak_source': peak_src, 'kernel_ms': eval_ms, 'kernel_share_of_step': eval_ms / ms_step if ms_step else None,
+                     'algorithmic_bytes_per_launch': bytes_per_step,
+                     'note': 'the path is integer-issue bound, not HBM bound (SURVEY.md 8d); see int_alu'},
+        'int_alu': {'achieved_gops': ops_per_step / (eval_ms * 1e-3) / 1e9 if eval_ms > 0 else 0.0,
+                    'peak_gops': int_best, 'frac': (ops_per_step / (eval_ms * 1e-3) / 1e9) / int_best if eval_ms > 0 and int_best else None,
+                    'peak_source': 'measured live: dependent-free IMAD / IADD3+LOP3 / mixed streams = %.0f / %.0f / %.0f Gop/s' % int_peak,
+                    'algorithmic_ops_per_launch': ops_per_step,
+                    'ops_model': 'SURVEY.md 8d: 13 + (6|7|8|9 by SATD tile) = 19..22 integer ops per predicted sample'},
+        'kernel_ms': {'plan': k_plan / max(1, k_n), 'eval': eval_ms, 'lists': k_lists / max(1, k_n)},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_baseline_port(base, frames[0])
+    print(json.dumps(out))
+
+
+def cpu_baseline_port(base, frame):
+    """The oracle (plain-C port of the same sweep) on one host core, on the visits of the first two CTUs."""
+    from oracle import oracle_py as O
+    sel = base[(base['x'] < 256) & (base['y'] < 128)]
+    sel = sel[(sel['x'] + (1 << sel['log2w'].astype(int)) <= 256)]
+    t0 = time.perf_counter()
+    O.rmd_batch(frame, frame, BITS, CTU, sel)
+    dt = time.perf_counter() - t0
+    return {'value': 2.0 / dt, 'unit': 'CTU/s', 'cores': 1, 'kind': 'port',
+            'sample': 'oracle/vvc_oracle.c, same exhaustive sweep, the %d visits of the first two CTUs of frame 0, %.1f s' % (len(sel), dt)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    enc = os.path.join(ROOT, 'oracle/_ref/EncoderApp')
+    cfg = os.path.join(ROOT, 'oracle/_ref/encoder_intra.cfg')
+    if not (os.path.exists(enc) and os.path.exists(cfg)):
+        print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref/EncoderApp was not built (run __graft_entry__.build() in the container that has /root/reference)'}))
+        return
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    frames = [synth_luma(f) for f in range(NFRAMES)]
+    tmp = tempfile.mkdtemp(prefix='vvcref_')
+    crops = [(cx, cy) for cy in range(0, H - CTU + 1, CTU) for cx in range(0, W - CTU + 1, CTU)]
+
+    def one_step(s):
+        f, qp = s % NFRAMES, QPS[s % len(QPS)]
+        procs = []
+        for k in range(cores):
+            cx, cy = crops[(s * cores + k) % len(crops)]
+            d = os.path.join(tmp, 's%d_%d' % (s, k))
+            os.makedirs(d, exist_ok=True)
+            y = frames[f][cy:cy + CTU, cx:cx + CTU].astype('<u2')
+            c = np.full((CTU // 2, CTU // 2), 512, '<u2')
+            open(os.path.join(d, 'in.yuv'), 'wb').write(y.tobytes() + c.tobytes() + c.tobytes())
+            open(os.path.join(d, 'Time_python.dat'), 'w').close()
+            procs.append(subprocess.Popen([enc, '-c', cfg, '-i', 'in.yuv', '-wdt', str(CTU), '-hgt', str(CTU), '-q', str(qp), '-f', '1',
+                                           '-fr', '30', '-b', 'out.bin', '--InputBitDepth=10', '--InternalBitDepth=10',
+                                           '--OutputBitDepth=10'], cwd=d, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        rcs = [p.wait() for p in procs]
+        if any(rcs):
+            raise RuntimeError('reference encoder failed: %r' % rcs)
+
+    for s in range(min(args.warmup, 1)):
+        one_step(s)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        one_step(args.warmup + s)
+    dt = time.perf_counter() - t0
+    value = args.steps * cores / dt
+    sample = ('unmodified reference encoder (VTM 6.1 fork, encoder_intra.cfg, all tools on, AVX2 dispatch), one process per 128x128 '
+              '10-bit crop (1 CTU) of the same synthetic frames, %d processes at a time, QP cycling 32/27/37/22; '
+              'full encode of the CTU (split search + full RD), not only the RMD sweep' % cores)
+    print(json.dumps({
+        'impl': 'reference',
+        'metric': 'all-intra 1080p10 CTUs/sec (exhaustive RMD sweep: intra pred + SAD/SATD + mode cost + candidate lists)',
+        'value': value, 'unit': 'CTU/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'int16 samples / int32 arithmetic / f64 costs', 'data': 'synthetic',
+        'config': {'workload': 'configs[1]: all-intra 1920x1080 10-bit synthetic YUV, 8 frames, QP 22/27/32/37 (bounded sample: %d CTU crops per step)' % cores},
+        'cpu_baseline': {'value': value, 'unit': 'CTU/s', 'cores': cores, 'kind': 'reference', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'CTU/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl')
+    run_b200(args, rank, world, local_rank, dist)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -84,29 +84,33 @@ typedef struct vvcb_mode {
   uint8_t pad;
 } vvcb_mode;
 
+#define VVCB_MAX_HAD_LIST   8
+
+/* What the RMD part of estIntraPredLumaQT hands to its full-RD loop (EL/IntraSearch.cpp:1158):        */
 typedef struct vvcb_rmd_result {
-  uint32_t  sad [VVCB_NUM_SLOTS];   /* RdCost::xGetSAD  (CL/RdCost.cpp:449);  VVCB_SAT_NONE if skipped  */
-  uint32_t  satd[VVCB_NUM_SLOTS];   /* RdCost::xGetHADs (CL/RdCost.cpp:2746)                            */
+  int32_t   n_rd, n_had, n_final, pad;
   /* uiRdModeList / CandCostList after the MIP pass and reduceHadCandList (EL/IntraSearch.cpp:747),
    * i.e. what the reference saves at :753-762; costs are IEEE doubles computed in reference order.   */
-  int32_t   n_rd;
   vvcb_mode rd_mode[VVCB_MAX_LIST];
   double    rd_cost[VVCB_MAX_LIST];
   /* uiHadModeList / CandHadList (PBINTRA list, :531, :738)                                           */
-  int32_t   n_had;
-  vvcb_mode had_mode[VVCB_MAX_LIST];
-  double    had_cost[VVCB_MAX_LIST];
-  /* regular-only list as it stood before the MIP pass (what :686-701 saves for small blocks)         */
-  int32_t   n_reg;
-  vvcb_mode reg_mode[VVCB_MAX_LIST];
-  double    reg_cost[VVCB_MAX_LIST];
-  int32_t   n_reg_had;
-  vvcb_mode reg_had_mode[VVCB_MAX_LIST];
-  double    reg_had_cost[VVCB_MAX_LIST];
+  vvcb_mode had_mode[VVCB_MAX_HAD_LIST];
+  double    had_cost[VVCB_MAX_HAD_LIST];
   /* final full-RD candidate list: rd list + missing MPMs (:777-802)                                  */
-  int32_t   n_final;
   vvcb_mode final_mode[VVCB_MAX_LIST];
 } vvcb_rmd_result;
+
+/* Optional per-visit detail (parity, tracing, host-side re-ranking): every evaluated distortion and the
+ * regular-only lists as they stood before the MIP pass (what :686-701 saves for blocks < 16x16).      */
+typedef struct vvcb_rmd_detail {
+  uint32_t  sad [VVCB_NUM_SLOTS];   /* RdCost::xGetSAD  (CL/RdCost.cpp:449);  VVCB_SAT_NONE if skipped  */
+  uint32_t  satd[VVCB_NUM_SLOTS];   /* RdCost::xGetHADs (CL/RdCost.cpp:2746)                            */
+  int32_t   n_reg, n_reg_had;
+  vvcb_mode reg_mode[VVCB_MAX_LIST];
+  double    reg_cost[VVCB_MAX_LIST];
+  vvcb_mode reg_had_mode[VVCB_MAX_HAD_LIST];
+  double    reg_had_cost[VVCB_MAX_HAD_LIST];
+} vvcb_rmd_detail;
 
 typedef struct vvcb_ctx vvcb_ctx;
 
@@ -125,17 +129,24 @@ int  vvcb_device_count(void);
 int vvcb_frame_begin(vvcb_ctx* ctx, const int16_t* orig, int stride, int width, int height);
 int vvcb_reco_update(vvcb_ctx* ctx, const int16_t* reco, int stride, int x, int y, int w, int h);
 
+/* Resident variant: use planes that already live in device memory (from vvcb_dev_alloc); nothing is
+ * copied, the caller keeps ownership.  stride in samples, a multiple of 4.                          */
+int vvcb_frame_bind_device(vvcb_ctx* ctx, const void* d_orig, const void* d_reco, int stride, int width, int height);
+
 /* ---- rough mode decision: intra prediction + SAD/SATD + mode cost + candidate lists ---------
  * Replaces the RMD block of IntraSearch::estIntraPredLumaQT (EL/IntraSearch.cpp:430-802) for a
  * batch of independent visits: initIntraPatternChType (CL/IntraPrediction.cpp:1064), predIntraAng
  * (:316), initIntraMip/predIntraMip (:2152/:2177), RdCost::xGetSAD/xGetHADs, xFracModeBitsIntra,
  * updateCandList (CL/UnitTools.h:261) and reduceHadCandList (EL/IntraSearch.cpp:4333).
- * visits/results are HOST arrays; copies in both directions happen inside the call.             */
-int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results);
+ * visits/results/details are HOST arrays (pinned memory from vvcb_host_alloc makes the copies
+ * asynchronous DMA); copies in both directions happen inside the call.                          */
+int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results,
+                  vvcb_rmd_detail* details /* may be NULL */);
 
 /* Same work with visits/results already resident on the device (device pointers from
  * vvcb_dev_alloc); used to time the kernels without the PCIe copies.                            */
-int vvcb_rmd_eval_device(vvcb_ctx* ctx, const void* d_visits, int n, void* d_results);
+int vvcb_rmd_eval_device(vvcb_ctx* ctx, const void* d_visits, int n, void* d_results,
+                         void* d_details /* may be NULL: internal scratch is used */);
 
 /* Prediction samples of one evaluation slot (debug / parity): writes w*h samples.               */
 int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t* pred);
@@ -143,12 +154,21 @@ int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t*
 /* ---- raw device memory for resident benchmarking --------------------------------------------- */
 int vvcb_dev_alloc(vvcb_ctx* ctx, size_t bytes, void** out);
 int vvcb_dev_free (vvcb_ctx* ctx, void* p);
+int vvcb_host_alloc(vvcb_ctx* ctx, size_t bytes, void** out);   /* page-locked host memory */
+int vvcb_host_free (vvcb_ctx* ctx, void* p);
 int vvcb_dev_upload  (vvcb_ctx* ctx, void* dst, const void* src, size_t bytes);
 int vvcb_dev_download(vvcb_ctx* ctx, void* dst, const void* src, size_t bytes);
 int vvcb_sync(vvcb_ctx* ctx);
 /* CUDA-event timing on the context's own stream (torch.cuda.Event cannot see it).               */
 int vvcb_timer_start(vvcb_ctx* ctx);
 int vvcb_timer_stop (vvcb_ctx* ctx, float* ms);
+/* Per-kernel device time (CUDA events on the context's stream around each launch), accumulated since
+ * the last call; enable with on != 0.  ms[0] plan, ms[1] eval (prediction+SAD+SATD), ms[2] lists.   */
+int vvcb_kernel_timing(vvcb_ctx* ctx, int on);
+int vvcb_kernel_times(vvcb_ctx* ctx, float ms[3], int* launches);
+/* Integer-ALU roofline denominator, measured live: dependent-free IMAD / IADD3+LOP3 / 1:1 mixed
+ * instruction streams on every SM; results in 10^9 lane-operations per second.                  */
+int vvcb_measure_int_peak(vvcb_ctx* ctx, double* gops_imad, double* gops_alu, double* gops_mixed);
 /* kernel launches issued by this context since creation (bench.py reports the delta).           */
 uint64_t vvcb_launch_count(const vvcb_ctx* ctx);
 

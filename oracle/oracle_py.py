@@ -33,13 +33,20 @@ class Mode(C.Structure):
     _fields_ = [('mip', C.c_uint8), ('mrl', C.c_uint8), ('mode', C.c_uint8), ('pad', C.c_uint8)]
 
 
+MAX_HAD_LIST = 8
+
+
 class RmdResult(C.Structure):
-    _fields_ = [('sad', C.c_uint32 * NUM_SLOTS), ('satd', C.c_uint32 * NUM_SLOTS),
-                ('n_rd', C.c_int32), ('rd_mode', Mode * MAX_LIST), ('rd_cost', C.c_double * MAX_LIST),
-                ('n_had', C.c_int32), ('had_mode', Mode * MAX_LIST), ('had_cost', C.c_double * MAX_LIST),
-                ('n_reg', C.c_int32), ('reg_mode', Mode * MAX_LIST), ('reg_cost', C.c_double * MAX_LIST),
-                ('n_reg_had', C.c_int32), ('reg_had_mode', Mode * MAX_LIST), ('reg_had_cost', C.c_double * MAX_LIST),
-                ('n_final', C.c_int32), ('final_mode', Mode * MAX_LIST)]
+    _fields_ = [('n_rd', C.c_int32), ('n_had', C.c_int32), ('n_final', C.c_int32), ('pad', C.c_int32),
+                ('rd_mode', Mode * MAX_LIST), ('rd_cost', C.c_double * MAX_LIST),
+                ('had_mode', Mode * MAX_HAD_LIST), ('had_cost', C.c_double * MAX_HAD_LIST),
+                ('final_mode', Mode * MAX_LIST)]
+
+
+class RmdDetail(C.Structure):
+    _fields_ = [('sad', C.c_uint32 * NUM_SLOTS), ('satd', C.c_uint32 * NUM_SLOTS), ('n_reg', C.c_int32), ('n_reg_had', C.c_int32),
+                ('reg_mode', Mode * MAX_LIST), ('reg_cost', C.c_double * MAX_LIST),
+                ('reg_had_mode', Mode * MAX_HAD_LIST), ('reg_had_cost', C.c_double * MAX_HAD_LIST)]
 
 
 class Ipa(C.Structure):
@@ -53,17 +60,16 @@ VISIT_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('log2w', 'u1'), ('log2h', '
 MODE_DTYPE = np.dtype([('mip', 'u1'), ('mrl', 'u1'), ('mode', 'u1'), ('pad', 'u1')])
 
 
-def _list(prefix, cost=True):
-    f = [('n_' + prefix, '<i4'), (prefix + '_mode', MODE_DTYPE, MAX_LIST)]
-    if cost:
-        f.append((prefix + '_cost', '<f8', MAX_LIST))
-    return f
-
-
-RESULT_DTYPE = np.dtype([('sad', '<u4', NUM_SLOTS), ('satd', '<u4', NUM_SLOTS)] + _list('rd') + _list('had') +
-                        _list('reg') + _list('reg_had') + _list('final', cost=False), align=True)
+RESULT_DTYPE = np.dtype([('n_rd', '<i4'), ('n_had', '<i4'), ('n_final', '<i4'), ('pad', '<i4'),
+                         ('rd_mode', MODE_DTYPE, MAX_LIST), ('rd_cost', '<f8', MAX_LIST),
+                         ('had_mode', MODE_DTYPE, MAX_HAD_LIST), ('had_cost', '<f8', MAX_HAD_LIST),
+                         ('final_mode', MODE_DTYPE, MAX_LIST)], align=True)
+DETAIL_DTYPE = np.dtype([('sad', '<u4', NUM_SLOTS), ('satd', '<u4', NUM_SLOTS), ('n_reg', '<i4'), ('n_reg_had', '<i4'),
+                         ('reg_mode', MODE_DTYPE, MAX_LIST), ('reg_cost', '<f8', MAX_LIST),
+                         ('reg_had_mode', MODE_DTYPE, MAX_HAD_LIST), ('reg_had_cost', '<f8', MAX_HAD_LIST)], align=True)
 assert VISIT_DTYPE.itemsize == C.sizeof(RmdVisit), (VISIT_DTYPE.itemsize, C.sizeof(RmdVisit))
 assert RESULT_DTYPE.itemsize == C.sizeof(RmdResult), (RESULT_DTYPE.itemsize, C.sizeof(RmdResult))
+assert DETAIL_DTYPE.itemsize == C.sizeof(RmdDetail), (DETAIL_DTYPE.itemsize, C.sizeof(RmdDetail))
 
 _lib = None
 _p16 = C.POINTER(C.c_int16)
@@ -165,21 +171,23 @@ def intra_mpms(left_dir, above_dir):
 
 
 def rmd_batch(orig, reco, bd, ctu_size, visits, want_pred=False):
-    """visits: numpy array of VISIT_DTYPE.  Returns numpy array of RESULT_DTYPE (and preds list)."""
+    """visits: numpy array of VISIT_DTYPE.  Returns (results, details) numpy arrays (and preds list)."""
     orig, po = _a16(orig)
     reco, pr = _a16(reco)
     visits = np.ascontiguousarray(visits, dtype=VISIT_DTYPE)
     out = np.zeros(len(visits), RESULT_DTYPE)
+    det = np.zeros(len(visits), DETAIL_DTYPE)
     if not want_pred:
         lib().orc_rmd_batch(po, orig.shape[1], pr, reco.shape[1], bd, ctu_size,
-                            visits.ctypes.data_as(C.c_void_p), len(visits), out.ctypes.data_as(C.c_void_p))
-        return out
+                            visits.ctypes.data_as(C.c_void_p), len(visits), out.ctypes.data_as(C.c_void_p),
+                            det.ctypes.data_as(C.c_void_p))
+        return out, det
     preds = []
     for i in range(len(visits)):
         w, h = 1 << int(visits[i]['log2w']), 1 << int(visits[i]['log2h'])
         p = np.zeros((NUM_SLOTS, h, w), np.int16)
         lib().orc_rmd_visit(po, orig.shape[1], pr, reco.shape[1], bd, ctu_size,
                             C.c_void_p(visits[i:i + 1].ctypes.data), C.c_void_p(out[i:i + 1].ctypes.data),
-                            p.ctypes.data_as(_p16))
+                            C.c_void_p(det[i:i + 1].ctypes.data), p.ctypes.data_as(_p16))
         preds.append(p)
-    return out, preds
+    return out, det, preds

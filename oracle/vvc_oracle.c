@@ -568,19 +568,21 @@ static void cand_push(cand_list* L, vvcb_mode m, double cost, int cap)
 static int same_mode(vvcb_mode a, vvcb_mode b) { return a.mip == b.mip && a.mrl == b.mrl && a.mode == b.mode; }
 static vvcb_mode mk_mode(int mip, int mrl, int mode) { vvcb_mode m; m.mip = (uint8_t)mip; m.mrl = (uint8_t)mrl; m.mode = (uint8_t)mode; m.pad = 0; return m; }
 
-static void copy_list(const cand_list* L, int32_t* n, vvcb_mode* m, double* c)
+static void copy_list(const cand_list* L, int32_t* n, vvcb_mode* m, double* c, int cap)
 {
   int i;
   *n = L->n;
-  for (i = 0; i < L->n && i < VVCB_MAX_LIST; i++) { m[i] = L->m[i]; if (c) c[i] = L->c[i]; }
+  for (i = 0; i < L->n && i < cap; i++) { m[i] = L->m[i]; if (c) c[i] = L->c[i]; }
 }
 
 static const uint8_t kFastModes[6][6] = {   /* g_aucIntraModeNumFast_UseMPM_2D, CL/Rom.cpp:536 */
   { 3, 3, 3, 3, 2, 2 }, { 3, 3, 3, 3, 3, 2 }, { 3, 3, 3, 3, 3, 2 }, { 3, 3, 3, 3, 3, 2 }, { 2, 3, 3, 3, 3, 2 }, { 2, 2, 2, 2, 2, 3 } };
 
 void orc_rmd_visit(const int16_t* orig, int orig_stride, const int16_t* reco, int reco_stride,
-                   int bd, int ctu_size, const vvcb_rmd_visit* v, vvcb_rmd_result* out, int16_t* pred_out)
+                   int bd, int ctu_size, const vvcb_rmd_visit* v, vvcb_rmd_result* out, vvcb_rmd_detail* det,
+                   int16_t* pred_out)
 {
+  vvcb_rmd_detail detLocal;
   const int w = 1 << v->log2w, h = 1 << v->log2h;
   const int16_t* org = orig + v->y * orig_stride + v->x;
   const int mipEnabled = !(v->flags & VVCB_VISIT_NO_MIP);
@@ -596,8 +598,10 @@ void orc_rmd_visit(const int16_t* orig, int orig_stride, const int16_t* reco, in
   int K = kFastModes[v->log2w - 2][v->log2h - 2];
   int numHad, slot, i, li, m;
 
+  if (!det) det = &detLocal;
   memset(out, 0, sizeof(*out));
-  for (i = 0; i < VVCB_NUM_SLOTS; i++) { out->sad[i] = VVCB_SAT_NONE; out->satd[i] = VVCB_SAT_NONE; }
+  memset(det, 0, sizeof(*det));
+  for (i = 0; i < VVCB_NUM_SLOTS; i++) { det->sad[i] = VVCB_SAT_NONE; det->satd[i] = VVCB_SAT_NONE; }
   for (li = 0; li < 3; li++)
     orc_ref_fill(reco, reco_stride, v->x, v->y, w, h, kMrl[li], bd, v->avail_al, v->n_above, v->n_above_right,
                  v->n_left, v->n_below_left, top[li], left[li]);
@@ -625,7 +629,7 @@ void orc_rmd_visit(const int16_t* orig, int orig_stride, const int16_t* reco, in
     if (pred_out) memcpy(pred_out + (size_t)slot * w * h, pred, sizeof(int16_t) * w * h);
     sad = orc_sad(org, orig_stride, pred, w, w, h);
     satd = orc_satd(org, orig_stride, pred, w, w, h);
-    out->sad[slot] = (uint32_t)sad; out->satd[slot] = (uint32_t)satd;
+    det->sad[slot] = (uint32_t)sad; det->satd[slot] = (uint32_t)satd;
     mn = sad * 2 < satd ? sad * 2 : satd;                                   /* :515 */
     bits = orc_mode_bits(&v->rates, v->mpm, w, h, mrlAllowed, mipEnabled, isMip, mrl, mode);
     dist[slot] = (double)mn;
@@ -663,17 +667,15 @@ void orc_rmd_visit(const int16_t* orig, int orig_stride, const int16_t* reco, in
         cand_push(&rd, mk_mode(0, kMrl[li], v->mpm[i]), cost[slot], K);
         cand_push(&had, mk_mode(0, kMrl[li], v->mpm[i]), dist[slot], numHad);
       }
-  copy_list(&rd, &out->n_reg, out->reg_mode, out->reg_cost);
-  copy_list(&had, &out->n_reg_had, out->reg_had_mode, out->reg_had_cost);
+  copy_list(&rd, &det->n_reg, det->reg_mode, det->reg_cost, VVCB_MAX_LIST);
+  copy_list(&had, &det->n_reg_had, det->reg_had_mode, det->reg_had_cost, VVCB_MAX_HAD_LIST);
 
   if (testMip) {                                                            /* :704-751 */
     double mipCost[35];
     cand_list tmp;
     const double thr = 1.0 + 1.4 / sqrt((double)(w * h));
     const int maxPerType = K >> 1;
-    const double minCost = 0;  /* set below */
     int keepOne, numConv = 0, numMipKept = 0, idx;
-    (void)minCost;
     for (m = 0; m < numMip; m++) {
       slot = VVCB_SLOT_MIP + m;
       mipCost[m] = cost[slot];
@@ -710,8 +712,8 @@ void orc_rmd_visit(const int16_t* orig, int orig_stride, const int16_t* reco, in
     rd = tmp;
     K = rd.n;
   }
-  copy_list(&rd, &out->n_rd, out->rd_mode, out->rd_cost);
-  copy_list(&had, &out->n_had, out->had_mode, out->had_cost);
+  copy_list(&rd, &out->n_rd, out->rd_mode, out->rd_cost, VVCB_MAX_LIST);
+  copy_list(&had, &out->n_had, out->had_mode, out->had_cost, VVCB_MAX_HAD_LIST);
 
   for (i = 0; i < v->num_mpm_cand; i++) {                                   /* :777-802 */
     const vvcb_mode mp = mk_mode(0, 0, v->mpm[i]);
@@ -719,14 +721,14 @@ void orc_rmd_visit(const int16_t* orig, int orig_stride, const int16_t* reco, in
     for (j = 0; j < K; j++) inc |= same_mode(mp, rd.m[j]);
     if (!inc) { rd.m[rd.n] = mp; rd.c[rd.n] = 0; rd.n++; K++; }
   }
-  copy_list(&rd, &out->n_final, out->final_mode, NULL);
+  copy_list(&rd, &out->n_final, out->final_mode, NULL, VVCB_MAX_LIST);
 }
 
 void orc_rmd_batch(const int16_t* orig, int orig_stride, const int16_t* reco, int reco_stride,
-                   int bd, int ctu_size, const vvcb_rmd_visit* v, int n, vvcb_rmd_result* out)
+                   int bd, int ctu_size, const vvcb_rmd_visit* v, int n, vvcb_rmd_result* out, vvcb_rmd_detail* det)
 {
   int i;
-  for (i = 0; i < n; i++) orc_rmd_visit(orig, orig_stride, reco, reco_stride, bd, ctu_size, v + i, out + i, NULL);
+  for (i = 0; i < n; i++) orc_rmd_visit(orig, orig_stride, reco, reco_stride, bd, ctu_size, v + i, out + i, det ? det + i : NULL, NULL);
 }
 
 uint64_t orc_fnv1a(const int16_t* p, int n)

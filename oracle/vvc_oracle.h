@@ -45,10 +45,11 @@ void orc_intra_mpms(int left_dir, int above_dir, uint8_t mpm[6], int* num_cand);
 /* a9: the whole RMD of one visit, references fetched from the reco plane.
  * pred_out (optional) receives VVCB_NUM_SLOTS blocks of w*h samples. */
 void orc_rmd_visit(const int16_t* orig, int orig_stride, const int16_t* reco, int reco_stride,
-                   int bd, int ctu_size, const vvcb_rmd_visit* v, vvcb_rmd_result* out, int16_t* pred_out);
+                   int bd, int ctu_size, const vvcb_rmd_visit* v, vvcb_rmd_result* out, vvcb_rmd_detail* det,
+                   int16_t* pred_out);
 /* batch with an OpenMP-free pthread pool is overkill for a checker: plain loop */
 void orc_rmd_batch(const int16_t* orig, int orig_stride, const int16_t* reco, int reco_stride,
-                   int bd, int ctu_size, const vvcb_rmd_visit* v, int n, vvcb_rmd_result* out);
+                   int bd, int ctu_size, const vvcb_rmd_visit* v, int n, vvcb_rmd_result* out, vvcb_rmd_detail* det);
 uint64_t orc_fnv1a(const int16_t* p, int n);
 
 #ifdef __cplusplus

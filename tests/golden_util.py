@@ -73,7 +73,7 @@ def result_list(res, pre, cost=True):
     return out
 
 
-def check_visit_against_reference(v, res):
+def check_visit_against_reference(v, res, det):
     """Compares one RMD result (oracle or GPU) with what the reference encoder produced.  Returns a
     list of human-readable mismatches (empty = parity)."""
     hd = v['head']
@@ -81,8 +81,8 @@ def check_visit_against_reference(v, res):
     errs = []
     for e in v['evals']:
         s = slot_of(hd, e)
-        if int(res['sad'][s]) != e['sad'] or int(res['satd'][s]) != e['satd']:
-            errs.append('slot %d %dx%d sad %d/%d satd %d/%d' % (s, w, h, res['sad'][s], e['sad'], res['satd'][s], e['satd']))
+        if int(det['sad'][s]) != e['sad'] or int(det['satd'][s]) != e['satd']:
+            errs.append('slot %d %dx%d sad %d/%d satd %d/%d' % (s, w, h, det['sad'][s], e['sad'], det['satd'][s], e['satd']))
     L = v['lists']
     exp_rd = [(a['mip'], a['mrl'], a['mode'], a['cost']) for a in L['rd']]
     exp_had = [(a['mip'], a['mrl'], a['mode'], a['cost']) for a in L['had']]
@@ -90,7 +90,7 @@ def check_visit_against_reference(v, res):
         got_rd, got_had = result_list(res, 'rd'), result_list(res, 'had')
     else:   # EL/IntraSearch.cpp:686-701 saved the regular-only lists, truncated
         k = KFAST[w.bit_length() - 3][h.bit_length() - 3]
-        got_rd, got_had = result_list(res, 'reg')[:k], result_list(res, 'reg_had')[:3]
+        got_rd, got_had = result_list(det, 'reg')[:k], result_list(det, 'reg_had')[:3]
     if got_rd != exp_rd:
         errs.append('rd list %dx%d variant %d: %r != %r' % (w, h, L['variant'], got_rd, exp_rd))
     if got_had != exp_had:

@@ -1,0 +1,63 @@
+// TEST INFRASTRUCTURE -- executes the real RMD kernels (vvc_intra_b200/csrc/vvcb_rmd.cuh) on host threads
+// through cuda_emul.h and exposes one C entry point for tests/test_kernel_emulation.py.
+#include "cuda_emul.h"
+#include <string.h>
+#include <stdlib.h>
+#include "../../vvc_intra_b200/csrc/vvcb_rmd.cuh"
+#include "../../vvc_intra_b200/csrc/vvcb_romfill.h"
+
+thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local EmuBlock* emuBlock;
+
+struct ThreadArg { unsigned tid, bid, block, grid; EmuBlock* blk; const std::function<void()>* fn; };
+
+static void* thread_main(void* p)
+{
+  ThreadArg* a = (ThreadArg*)p;
+  threadIdx = { a->tid, 0, 0 }; blockIdx = { a->bid, 0, 0 }; blockDim = { a->block, 1, 1 }; gridDim = { a->grid, 1, 1 };
+  emuBlock = a->blk;
+  (*a->fn)();
+  return nullptr;
+}
+
+void emu_launch(unsigned grid, unsigned block, const std::function<void()>& fn)
+{
+  for (unsigned b = 0; b < grid; b++) {
+    EmuBlock blk;
+    pthread_barrier_init(&blk.bar, nullptr, block);
+    blk.warps.resize((block + 31) / 32);
+    for (unsigned w = 0; w < blk.warps.size(); w++) {
+      const unsigned cnt = (w + 1) * 32 <= block ? 32 : block - w * 32;
+      pthread_barrier_init(&blk.warps[w].bar, nullptr, cnt);
+    }
+    std::vector<pthread_t> th(block);
+    std::vector<ThreadArg> args(block);
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 1 << 20);
+    for (unsigned t = 0; t < block; t++) {
+      args[t] = { t, b, block, grid, &blk, &fn };
+      pthread_create(&th[t], &attr, thread_main, &args[t]);
+    }
+    for (unsigned t = 0; t < block; t++) pthread_join(th[t], nullptr);
+    pthread_attr_destroy(&attr);
+  }
+}
+
+extern "C" int emul_rmd_eval(const int16_t* orig, const int16_t* reco, int stride, int bd, int ctu,
+                             const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results, vvcb_rmd_detail* details,
+                             int16_t* predOut)
+{
+  static Rom rom;
+  fill_rom(rom);
+  std::vector<WorkItem> items((size_t)n * VVCB_NUM_SLOTS);
+  unsigned counters[4] = { 0, 0, 0, 0 };
+  emu_launch((n + 255) / 256, 256, [&] { rmd_plan_kernel(visits, n, ctu, items.data(), counters); });
+  EvalParams P;
+  P.visits = visits; P.items = items.data(); P.itemCount = counters; P.cursor = counters + 1;
+  P.details = details;
+  P.orig = orig; P.reco = reco; P.stride = stride; P.bd = bd; P.ctu = ctu; P.rom = &rom; P.predOut = predOut;
+  emu_launch(1, kThreads, [&] { rmd_eval_kernel(P); });
+  emu_launch((n + 127) / 128, 128, [&] { rmd_lists_kernel(visits, n, ctu, results, details); });
+  return 0;
+}

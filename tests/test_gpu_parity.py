@@ -1,0 +1,178 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against the
+reference encoder's golden records, against the oracle on seeded random inputs, and -- at BASELINE.json's
+full 1080p size -- through sampled oracle checks and size-independent properties."""
+import numpy as np
+import pytest
+
+import vvc_intra_b200 as vb
+from oracle import oracle_py as O
+import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng10():
+    with vb.IntraCostEngine(device=0, bit_depth=10, ctu_size=128) as e:
+        yield e
+
+
+@pytest.fixture(scope='module')
+def eng8():
+    with vb.IntraCostEngine(device=0, bit_depth=8, ctu_size=128) as e:
+        yield e
+
+
+@pytest.mark.parametrize('name,bd', [('ref_8b_128x64_qp32', 8), ('ref_10b_192x128_qp27', 10)])
+def test_golden_fixture_parity(name, bd, eng8, eng10):
+    """Every recorded visit of the reference encoder: SAD/SATD of every evaluation, candidate lists with
+    exact double costs, and byte-identical result structs versus the oracle."""
+    eng = eng8 if bd == 8 else eng10
+    visits, _ = G.load_fixture(name)
+    orig, reco, arr = G.build_atlas(visits)
+    eng.frame_begin(orig)
+    eng.reco_update(reco)
+    res, det = eng.rmd_eval(arr, detail=True)
+    errs = []
+    for v, r, d in zip(visits, res, det):
+        errs += G.check_visit_against_reference(v, r, d)
+    assert not errs, errs[:5]
+    ora, odet = O.rmd_batch(orig, reco, bd, 128, arr)
+    assert np.array_equal(det['sad'], odet['sad']) and np.array_equal(det['satd'], odet['satd'])
+    assert res.tobytes() == ora.tobytes() and det.tobytes() == odet.tobytes()
+
+
+def test_prediction_samples_match_reference(eng8):
+    """Prediction samples (not only their distortion) of the visits recorded with full samples."""
+    visits, _ = G.load_fixture('ref_8b_128x64_qp32')
+    sel = [v for v in visits if any('pred' in e for e in v['evals'])][:17 * 2]
+    orig, reco, arr = G.build_atlas(sel)
+    eng8.frame_begin(orig)
+    eng8.reco_update(reco)
+    n = 0
+    for v, a in zip(sel, arr):
+        for e in v['evals'][::7]:
+            if 'pred' not in e:
+                continue
+            got = eng8.rmd_pred(a, G.slot_of(v['head'], e))
+            assert np.array_equal(got, e['pred']), (v['head']['w'], v['head']['h'], e['mip'], e['mrl'], e['mode'])
+            n += 1
+    assert n > 200
+
+
+def random_case(rng, bd, n_per_shape, plane=(512, 1024)):
+    H, W = plane
+    orig = rng.integers(0, 1 << bd, (H, W)).astype(np.int16)
+    reco = rng.integers(0, 1 << bd, (H, W)).astype(np.int16)
+    vis = []
+    for lw in range(2, 7):
+        for lh in range(2, 7):
+            if (lw == 6) != (lh == 6):
+                continue
+            w, h = 1 << lw, 1 << lh
+            for _ in range(n_per_shape):
+                v = np.zeros(1, vb.VISIT_DTYPE)[0]
+                v['x'] = 4 * rng.integers(1, (W - 2 * w) // 4)
+                v['y'] = 4 * rng.integers(1, (H - 2 * h) // 4)
+                v['log2w'], v['log2h'] = lw, lh
+                mode = rng.integers(0, 4)
+                if mode == 0:        # everything available
+                    v['avail_al'], v['n_above'], v['n_above_right'], v['n_left'], v['n_below_left'] = 1, w // 4, w // 4, h // 4, h // 4
+                elif mode == 1:      # nothing
+                    pass
+                else:                # ragged
+                    v['avail_al'] = rng.integers(0, 2)
+                    v['n_above'] = rng.integers(0, w // 4 + 1)
+                    v['n_above_right'] = rng.integers(0, w // 4 + 1)
+                    v['n_left'] = rng.integers(0, h // 4 + 1)
+                    v['n_below_left'] = rng.integers(0, h // 4 + 1)
+                v['flags'] = rng.integers(0, 4) if rng.random() < 0.3 else 0
+                L, A = rng.integers(0, 67, 2)
+                mpm, nc = O.intra_mpms(int(L), int(A))
+                v['mpm'], v['num_mpm_cand'] = mpm, nc
+                v['rates'] = rng.integers(100, 200000, 11)
+                v['sqrt_lambda'] = float(rng.uniform(1e-4, 3e-3))
+                vis.append(v)
+    return orig, reco, np.array(vis, vb.VISIT_DTYPE)
+
+
+@pytest.mark.parametrize('bd,seed', [(8, 1), (10, 2), (10, 3)])
+def test_random_visits_match_oracle(bd, seed, eng8, eng10):
+    """Seeded random planes, random ragged availability, random MPM lists / rates / lambda, all 17 shapes."""
+    eng = eng8 if bd == 8 else eng10
+    rng = np.random.default_rng(seed)
+    orig, reco, arr = random_case(rng, bd, 24)
+    eng.frame_begin(orig)
+    eng.reco_update(reco)
+    res, det = eng.rmd_eval(arr, detail=True)
+    ora, odet = O.rmd_batch(orig, reco, bd, 128, arr)
+    bad = [i for i in range(len(arr)) if res[i].tobytes() != ora[i].tobytes() or det[i].tobytes() != odet[i].tobytes()]
+    assert not bad, (len(bad), arr[bad[0]], [s for s in range(112) if det[bad[0]]['satd'][s] != odet[bad[0]]['satd'][s]])
+
+
+def test_extreme_sample_values(eng10):
+    """All-zero / all-max / checkerboard content: largest residuals the SATD accumulators can see."""
+    H, W = 256, 512
+    yy, xx = np.mgrid[0:H, 0:W]
+    for orig, reco in ((np.zeros((H, W), np.int16), np.full((H, W), 1023, np.int16)),
+                       (((xx + yy) % 2 * 1023).astype(np.int16), ((xx + yy + 1) % 2 * 1023).astype(np.int16))):
+        rng = np.random.default_rng(7)
+        _, _, arr = random_case(rng, 10, 3, plane=(H, W))
+        eng10.frame_begin(orig)
+        eng10.reco_update(reco)
+        res, det = eng10.rmd_eval(arr, detail=True)
+        ora, odet = O.rmd_batch(orig, reco, 10, 128, arr)
+        assert res.tobytes() == ora.tobytes() and det.tobytes() == odet.tobytes()
+
+
+def test_full_1080p_sweep_properties(eng10):
+    """BASELINE config 2 size: every candidate CU of a 1920x1080 10-bit picture (679 260 visits).  Checked by
+    (i) a seeded sample of visits against the oracle, (ii) determinism, (iii) domain properties: DC-only
+    content has zero distortion for planar/DC, list costs ascend, SATD of identical blocks is zero."""
+    import sys
+    sys.path.insert(0, 'tools')
+    from make_golden import synth_yuv
+    Y, _, _ = synth_yuv(1920, 1080, 10)
+    orig = Y.astype(np.int16)
+    vis = vb.build_sweep_visits(1920, 1080, qp=32)
+    assert len(vis) == 679260
+    eng10.frame_begin(orig)
+    eng10.reco_update(orig)            # speculative sweep: neighbours taken from the original picture
+    res, det = eng10.rmd_eval(vis, detail=True)
+    res2 = eng10.rmd_eval(vis)
+    assert res.tobytes() == res2.tobytes()
+    rng = np.random.default_rng(11)
+    idx = np.sort(rng.choice(len(vis), 3000, replace=False))
+    ora, odet = O.rmd_batch(orig, orig, 10, 128, vis[idx])
+    assert res[idx].tobytes() == ora.tobytes() and det[idx].tobytes() == odet.tobytes()
+    n_rd = res['n_rd']
+    assert n_rd.min() >= 2 and n_rd.max() <= vb.engine.MAX_LIST
+    for i in idx[:200]:
+        c = res[i]['had_cost'][:res[i]['n_had']]
+        assert np.all(np.diff(c) >= 0)
+    # flat picture: planar and DC predict it exactly wherever any neighbour exists
+    flat = np.full((1080, 1920), 600, np.int16)
+    eng10.frame_begin(flat)
+    eng10.reco_update(flat)
+    _, d3 = eng10.rmd_eval(vis[:20000], detail=True)
+    has_nb = (vis[:20000]['n_above'] > 0) | (vis[:20000]['n_left'] > 0)
+    assert np.all(d3['satd'][has_nb][:, :2] == 0) and np.all(d3['sad'][has_nb][:, :2] == 0)
+
+
+def test_error_behaviour(eng10):
+    orig = np.zeros((64, 64), np.int16)
+    eng10.frame_begin(orig)
+    v = np.zeros(1, vb.VISIT_DTYPE)
+    v['x'], v['y'], v['log2w'], v['log2h'] = 32, 32, 6, 6      # sticks out of the picture
+    with pytest.raises(vb.EngineError, match='malformed'):
+        eng10.rmd_eval(v)
+    v['log2w'], v['log2h'] = 3, 3
+    v['n_above'] = 5                                             # more units than the CU is wide
+    with pytest.raises(vb.EngineError, match='malformed'):
+        eng10.rmd_eval(v)
+    assert len(eng10.rmd_eval(np.zeros(0, vb.VISIT_DTYPE))) == 0  # empty batch
+    with vb.IntraCostEngine(device=0, bit_depth=10) as fresh:
+        with pytest.raises(vb.EngineError, match='frame_begin'):
+            fresh.rmd_eval(np.zeros(1, vb.VISIT_DTYPE))
+    with pytest.raises(vb.EngineError):
+        vb.IntraCostEngine(device=99)

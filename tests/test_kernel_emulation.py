@@ -1,0 +1,65 @@
+"""CPU tests of the REAL kernel source (vvc_intra_b200/csrc/vvcb_rmd.cuh) executed on host threads through
+tests/host_emul/cuda_emul.h, compared with the reference encoder's golden records and with the oracle.
+Test-only: the product library has no CPU path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+import golden_util as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def emul():
+    subprocess.check_call(['make', '-s', '-f', 'tests/host_emul/Makefile'], cwd=ROOT)
+    return C.CDLL(os.path.join(ROOT, 'tests/host_emul/libemul_rmd.so'))
+
+
+def run_emul(lib, orig, reco, bd, visits, pred_of_first=False):
+    orig = np.ascontiguousarray(orig, np.int16)
+    reco = np.ascontiguousarray(reco, np.int16)
+    visits = np.ascontiguousarray(visits, O.VISIT_DTYPE)
+    res = np.zeros(len(visits), O.RESULT_DTYPE)
+    det = np.zeros(len(visits), O.DETAIL_DTYPE)
+    pred = None
+    pp = None
+    if pred_of_first:
+        w, h = 1 << int(visits[0]['log2w']), 1 << int(visits[0]['log2h'])
+        pred = np.zeros((O.NUM_SLOTS, h, w), np.int16)
+        pp = pred.ctypes.data_as(C.c_void_p)
+    rc = lib.emul_rmd_eval(orig.ctypes.data_as(C.c_void_p), reco.ctypes.data_as(C.c_void_p), orig.shape[1], bd, 128,
+                           visits.ctypes.data_as(C.c_void_p), len(visits), res.ctypes.data_as(C.c_void_p),
+                           det.ctypes.data_as(C.c_void_p), pp)
+    assert rc == 0
+    return res, det, pred
+
+
+def pick(visits, per_shape):
+    seen, out = {}, []
+    for v in visits:
+        k = (v['head']['w'], v['head']['h'])
+        if seen.get(k, 0) < per_shape:
+            seen[k] = seen.get(k, 0) + 1
+            out.append(v)
+    return out
+
+
+@pytest.mark.parametrize('name', ['ref_8b_128x64_qp32', 'ref_10b_192x128_qp27'])
+def test_emulated_kernels_match_reference(emul, name):
+    visits, _ = G.load_fixture(name)
+    sel = pick(visits, 2)
+    orig, reco, arr = G.build_atlas(sel)
+    res, det, _ = run_emul(emul, orig, reco, sel[0]['head']['bd'], arr)
+    errs = []
+    for v, r, d in zip(sel, res, det):
+        errs += G.check_visit_against_reference(v, r, d)
+    assert not errs, errs[:5]
+    # and bit-identical to the oracle on every slot, including the ones the reference never evaluated
+    ora, odet = O.rmd_batch(orig, reco, sel[0]['head']['bd'], 128, arr)
+    assert np.array_equal(det['sad'], odet['sad']) and np.array_equal(det['satd'], odet['satd'])
+    assert res.tobytes() == ora.tobytes() and det.tobytes() == odet.tobytes()

@@ -81,10 +81,10 @@ def test_rmd_visit_lists(name):
     visits, _ = G.load_fixture(name)
     orig, reco, arr = G.build_atlas(visits)
     bd = visits[0]['head']['bd']
-    res = O.rmd_batch(orig, reco, bd, 128, arr)
+    res, det = O.rmd_batch(orig, reco, bd, 128, arr)
     errs = []
-    for v, r in zip(visits, res):
-        errs += G.check_visit_against_reference(v, r)
+    for v, r, d in zip(visits, res, det):
+        errs += G.check_visit_against_reference(v, r, d)
     assert not errs, errs[:5]
 
 

@@ -1,0 +1,13 @@
+"""vvc_intra_b200 -- B200-native intra cost-evaluation engine behind the IntraSearch::estIntraPredLumaQT /
+EncCu::xCompressCU call surface of the VTM 6.1 fork llsurreal919/Reduce-Complexity-for-intra-coding-of-VVC.
+
+The compute path is hand-written CUDA for sm_100a behind the C ABI of include/vvc_intra_b200.h
+(libvvc_intra_b200.so, built in-tree by __graft_entry__.build()).  This package is the thin host-side
+mirror of that ABI plus the host logic of the exhaustive candidate sweep; it has no CPU fallback."""
+from .engine import (IntraCostEngine, EngineError, VISIT_DTYPE, RESULT_DTYPE, DETAIL_DTYPE, NUM_SLOTS, SLOT_MRL1, SLOT_MRL3, SLOT_MIP,
+                     SAT_NONE, library_path)
+from .partition import enumerate_root_candidates, frame_candidates, candidate_availability, build_sweep_visits
+
+__all__ = ['IntraCostEngine', 'EngineError', 'VISIT_DTYPE', 'RESULT_DTYPE', 'DETAIL_DTYPE', 'NUM_SLOTS', 'SLOT_MRL1', 'SLOT_MRL3',
+           'SLOT_MIP', 'SAT_NONE', 'library_path', 'enumerate_root_candidates', 'frame_candidates',
+           'candidate_availability', 'build_sweep_visits']

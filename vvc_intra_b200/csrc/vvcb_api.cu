@@ -1,0 +1,461 @@
+// vvc_intra_b200 -- the C ABI of include/vvc_intra_b200.h: context, plane management and kernel launches.
+// The kernels live in vvcb_rmd.cuh.  There is no CPU fallback anywhere in this library.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <math.h>
+#include <new>
+#include "vvcb_rmd.cuh"
+#include "vvcb_romfill.h"
+
+// =====================================================================================================
+// integer-issue microbenchmark (roofline denominator; not part of the encoder path)
+// =====================================================================================================
+template <int KIND>   // 0: IMAD only, 1: IADD3/LOP3 only, 2: 1:1 mix
+__global__ void __launch_bounds__(256) int_peak_kernel(const int* in, int* out, int iters)
+{
+  int a[8], b[8];
+  const int k0 = in[threadIdx.x & 31], k1 = in[32 + (threadIdx.x & 31)];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { a[i] = k0 + i; b[i] = k1 - i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (KIND == 0)      { a[i] = a[i] * k1 + k0; b[i] = b[i] * k0 + k1; }
+        else if (KIND == 1) { a[i] = (a[i] + k1) ^ k0; b[i] = (b[i] ^ k1) + k0; }   // IADD3 + LOP3 pairs
+        else                { a[i] = a[i] * k1 + k0; b[i] = (b[i] + k1) ^ k0; }
+      }
+    }
+  }
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += a[i] ^ b[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+struct vvcb_ctx {
+  int device, bd, ctu;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  Rom* dRom;
+  int16_t* dOrig; int16_t* dReco;
+  const int16_t* bOrig; const int16_t* bReco;   // planes in use (own or bound)
+  int width, height, stride;        // planes share one pitch (in samples)
+  size_t planeSamples;
+  // scratch for the host-pointer API
+  vvcb_rmd_visit* dVisits; vvcb_rmd_result* dResults; size_t capVisits;
+  vvcb_rmd_detail* dDetails; size_t capDetails;
+  WorkItem* dItems; size_t capItems;
+  unsigned* dCounters;              // [0] item count, [1] cursor
+  int16_t* dPred; size_t capPred;
+  int numSms;
+  uint64_t launches;
+  int timing; int timedLaunches; float kms[3]; cudaEvent_t kev[4];
+  char err[512];
+};
+
+static char g_createErr[512] = "";
+
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) {                                                                              \
+      snprintf(ctx->err, sizeof(ctx->err), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return VVCB_ERR_CUDA;                                                                               \
+    }                                                                                                     \
+  } while (0)
+
+extern "C" int vvcb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" const char* vvcb_last_error(const vvcb_ctx* ctx) { return ctx ? ctx->err : g_createErr; }
+
+extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_size)
+{
+  if (!out || bit_depth < 8 || bit_depth > 12 || ctu_size < 32 || (ctu_size & (ctu_size - 1))) {
+    snprintf(g_createErr, sizeof(g_createErr), "vvcb_create: bad argument");
+    return VVCB_ERR_ARG;
+  }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || device < 0 || device >= n) {
+    snprintf(g_createErr, sizeof(g_createErr), "vvcb_create: no usable CUDA device %d (%s); this library has no CPU path",
+             device, e != cudaSuccess ? cudaGetErrorString(e) : "index out of range");
+    return VVCB_ERR_CUDA;
+  }
+  vvcb_ctx* ctx = new (std::nothrow) vvcb_ctx();
+  if (!ctx) return VVCB_ERR_ARG;
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->device = device; ctx->bd = bit_depth; ctx->ctu = ctu_size;
+  auto fail = [&](const char* what, cudaError_t err) {
+    snprintf(g_createErr, sizeof(g_createErr), "vvcb_create: %s: %s", what, cudaGetErrorString(err));
+    delete ctx;
+    return VVCB_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+  ctx->numSms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+  for (int i = 0; i < 4; i++) if ((e = cudaEventCreate(&ctx->kev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
+  Rom* h = new Rom();
+  fill_rom(*h);
+  if ((e = cudaMalloc(&ctx->dRom, sizeof(Rom))) != cudaSuccess) { delete h; return fail("cudaMalloc(rom)", e); }
+  e = cudaMemcpy(ctx->dRom, h, sizeof(Rom), cudaMemcpyHostToDevice);
+  delete h;
+  if (e != cudaSuccess) return fail("cudaMemcpy(rom)", e);
+  if ((e = cudaMalloc(&ctx->dCounters, 4 * sizeof(unsigned))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
+  *out = ctx;
+  return VVCB_OK;
+}
+
+extern "C" void vvcb_destroy(vvcb_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails);
+  cudaFree(ctx->dItems); cudaFree(ctx->dCounters); cudaFree(ctx->dPred);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->kev[i]);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" int vvcb_frame_begin(vvcb_ctx* ctx, const int16_t* orig, int stride, int width, int height)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (!orig || width <= 0 || height <= 0 || stride < width || (width & 3) || (height & 3)) {
+    snprintf(ctx->err, sizeof(ctx->err), "vvcb_frame_begin: bad argument (width/height must be positive multiples of 4)");
+    return VVCB_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  const int pitch = (width + 63) & ~63;
+  const size_t samples = (size_t)pitch * height;
+  if (samples > ctx->planeSamples) {
+    cudaFree(ctx->dOrig); cudaFree(ctx->dReco);
+    ctx->dOrig = ctx->dReco = nullptr; ctx->planeSamples = 0;
+    CK(cudaMalloc(&ctx->dOrig, samples * sizeof(int16_t)));
+    CK(cudaMalloc(&ctx->dReco, samples * sizeof(int16_t)));
+    ctx->planeSamples = samples;
+  }
+  ctx->width = width; ctx->height = height; ctx->stride = pitch;
+  ctx->bOrig = ctx->dOrig; ctx->bReco = ctx->dReco;
+  CK(cudaMemcpy2DAsync(ctx->dOrig, pitch * sizeof(int16_t), orig, stride * sizeof(int16_t), width * sizeof(int16_t), height,
+                       cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->dReco, 0, samples * sizeof(int16_t), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_reco_update(vvcb_ctx* ctx, const int16_t* reco, int stride, int x, int y, int w, int h)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (!ctx->dReco || ctx->bReco != ctx->dReco) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_reco_update: no frame owned by the context"); return VVCB_ERR_STATE; }
+  if (!reco || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > ctx->width || y + h > ctx->height || stride < w) {
+    snprintf(ctx->err, sizeof(ctx->err), "vvcb_reco_update: rectangle outside the picture");
+    return VVCB_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy2DAsync(ctx->dReco + (size_t)y * ctx->stride + x, ctx->stride * sizeof(int16_t), reco, stride * sizeof(int16_t),
+                       w * sizeof(int16_t), h, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_frame_bind_device(vvcb_ctx* ctx, const void* d_orig, const void* d_reco, int stride, int width, int height)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (!d_orig || !d_reco || width <= 0 || height <= 0 || stride < width || (width & 3) || (height & 3) || (stride & 3)) {
+    snprintf(ctx->err, sizeof(ctx->err), "vvcb_frame_bind_device: bad argument");
+    return VVCB_ERR_ARG;
+  }
+  ctx->bOrig = static_cast<const int16_t*>(d_orig); ctx->bReco = static_cast<const int16_t*>(d_reco);
+  ctx->width = width; ctx->height = height; ctx->stride = stride;
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_kernel_timing(vvcb_ctx* ctx, int on)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  ctx->timing = on; ctx->timedLaunches = 0; ctx->kms[0] = ctx->kms[1] = ctx->kms[2] = 0.f;
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_kernel_times(vvcb_ctx* ctx, float ms[3], int* launches)
+{
+  if (!ctx || !ms) return VVCB_ERR_ARG;
+  for (int i = 0; i < 3; i++) ms[i] = ctx->kms[i];
+  if (launches) *launches = ctx->timedLaunches;
+  ctx->timedLaunches = 0; ctx->kms[0] = ctx->kms[1] = ctx->kms[2] = 0.f;
+  return VVCB_OK;
+}
+
+static int ensure_items(vvcb_ctx* ctx, int n)
+{
+  const size_t need = (size_t)n * 56;     // worst case 64x64: ceil(112 slots * 64 lanes / kItemTasks)
+  if (need > ctx->capItems) {
+    cudaFree(ctx->dItems); ctx->dItems = nullptr; ctx->capItems = 0;
+    CK(cudaMalloc(&ctx->dItems, need * sizeof(WorkItem)));
+    ctx->capItems = need;
+  }
+  return VVCB_OK;
+}
+
+static int ensure_details(vvcb_ctx* ctx, int n)
+{
+  if ((size_t)n > ctx->capDetails) {
+    cudaFree(ctx->dDetails); ctx->dDetails = nullptr; ctx->capDetails = 0;
+    CK(cudaMalloc(&ctx->dDetails, (size_t)n * sizeof(vvcb_rmd_detail)));
+    ctx->capDetails = (size_t)n;
+  }
+  return VVCB_OK;
+}
+
+static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_rmd_result* dResults, vvcb_rmd_detail* dDetails,
+                      int16_t* dPred)
+{
+  if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
+  if (n == 0) return VVCB_OK;
+  int rc = ensure_items(ctx, n);
+  if (rc) return rc;
+  if (!dDetails) {
+    rc = ensure_details(ctx, n);
+    if (rc) return rc;
+    dDetails = ctx->dDetails;
+  }
+  CK(cudaMemsetAsync(ctx->dCounters, 0, 4 * sizeof(unsigned), ctx->stream));
+  const bool tm = ctx->timing != 0;
+  if (tm) CK(cudaEventRecord(ctx->kev[0], ctx->stream));
+  rmd_plan_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dItems, ctx->dCounters);
+  if (tm) CK(cudaEventRecord(ctx->kev[1], ctx->stream));
+  EvalParams P;
+  P.visits = dVisits; P.items = ctx->dItems; P.itemCount = ctx->dCounters; P.cursor = ctx->dCounters + 1;
+  P.details = dDetails;
+  P.orig = ctx->bOrig; P.reco = ctx->bReco; P.stride = ctx->stride; P.bd = ctx->bd; P.ctu = ctx->ctu; P.rom = ctx->dRom;
+  P.predOut = dPred;
+  const long long maxCtas = ((long long)n * 8 + kWarpsPerCta - 1) / kWarpsPerCta;
+  int grid = ctx->numSms * 2;
+  if (grid > maxCtas) grid = (int)maxCtas;
+  if (grid < 1) grid = 1;
+  rmd_eval_kernel<<<grid, kThreads, 0, ctx->stream>>>(P);
+  if (tm) CK(cudaEventRecord(ctx->kev[2], ctx->stream));
+  rmd_lists_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dResults, dDetails);
+  ctx->launches += 3;
+  CK(cudaGetLastError());
+  if (tm) {
+    CK(cudaEventRecord(ctx->kev[3], ctx->stream));
+    CK(cudaEventSynchronize(ctx->kev[3]));
+    for (int i = 0; i < 3; i++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->kev[i], ctx->kev[i + 1])); ctx->kms[i] += ms; }
+    ctx->timedLaunches++;
+  }
+  return VVCB_OK;
+}
+
+static int check_visits(vvcb_ctx* ctx, const vvcb_rmd_visit* v, int n)
+{
+  for (int i = 0; i < n; i++) {
+    const int w = 1 << v[i].log2w, h = 1 << v[i].log2h;
+    const bool ok = v[i].log2w >= 2 && v[i].log2w <= 6 && v[i].log2h >= 2 && v[i].log2h <= 6 && v[i].x >= 0 && v[i].y >= 0 &&
+                    (v[i].x & 3) == 0 && (v[i].y & 3) == 0 && v[i].x + w <= ctx->width && v[i].y + h <= ctx->height &&
+                    v[i].n_above <= w / 4 && v[i].n_above_right <= w / 4 && v[i].n_left <= h / 4 && v[i].n_below_left <= h / 4 &&
+                    v[i].avail_al <= 1 && v[i].num_mpm_cand <= 6 &&
+                    // available samples must lie inside the picture
+                    (!(v[i].avail_al || v[i].n_above || v[i].n_above_right) || v[i].y >= 4) &&
+                    (!(v[i].avail_al || v[i].n_left || v[i].n_below_left) || v[i].x >= 4) &&
+                    v[i].x + w + 4 * v[i].n_above_right <= ctx->width && v[i].y + h + 4 * v[i].n_below_left <= ctx->height;
+    bool mpmOk = true;
+    for (int k = 0; k < 6; k++) mpmOk = mpmOk && v[i].mpm[k] < VVCB_NUM_LUMA_MODE;
+    if (!ok || !mpmOk) {
+      snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: visit %d is malformed (position/size/availability outside the picture)", i);
+      return VVCB_ERR_ARG;
+    }
+  }
+  return VVCB_OK;
+}
+
+static int ensure_visit_buffers(vvcb_ctx* ctx, int n)
+{
+  if ((size_t)n > ctx->capVisits) {
+    cudaFree(ctx->dVisits); cudaFree(ctx->dResults);
+    ctx->dVisits = nullptr; ctx->dResults = nullptr; ctx->capVisits = 0;
+    CK(cudaMalloc(&ctx->dVisits, (size_t)n * sizeof(vvcb_rmd_visit)));
+    CK(cudaMalloc(&ctx->dResults, (size_t)n * sizeof(vvcb_rmd_result)));
+    ctx->capVisits = (size_t)n;
+  }
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results, vvcb_rmd_detail* details)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (n < 0 || (n > 0 && (!visits || !results))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: bad argument"); return VVCB_ERR_ARG; }
+  if (n == 0) return VVCB_OK;
+  if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
+  int rc = check_visits(ctx, visits, n);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  rc = ensure_visit_buffers(ctx, n);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->dVisits, visits, (size_t)n * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
+  rc = launch_rmd(ctx, ctx->dVisits, n, ctx->dResults, nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(results, ctx->dResults, (size_t)n * sizeof(vvcb_rmd_result), cudaMemcpyDeviceToHost, ctx->stream));
+  if (details) CK(cudaMemcpyAsync(details, ctx->dDetails, (size_t)n * sizeof(vvcb_rmd_detail), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_rmd_eval_device(vvcb_ctx* ctx, const void* d_visits, int n, void* d_results, void* d_details)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (n < 0 || (n > 0 && (!d_visits || !d_results))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval_device: bad argument"); return VVCB_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  return launch_rmd(ctx, static_cast<const vvcb_rmd_visit*>(d_visits), n, static_cast<vvcb_rmd_result*>(d_results),
+                    static_cast<vvcb_rmd_detail*>(d_details), nullptr);
+}
+
+extern "C" int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t* pred)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (!visit || !pred || slot < 0 || slot >= VVCB_NUM_SLOTS) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: bad argument"); return VVCB_ERR_ARG; }
+  if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: no frame"); return VVCB_ERR_STATE; }
+  int rc = check_visits(ctx, visit, 1);
+  if (rc) return rc;
+  const int w = 1 << visit->log2w, h = 1 << visit->log2h;
+  const bool mrlAllowed = !(visit->flags & VVCB_VISIT_NO_MRL) && (visit->y & (ctx->ctu - 1)) != 0;
+  const int numMip = (visit->flags & VVCB_VISIT_NO_MIP) ? 0 : mip_num_modes(w, h);
+  int a = -1;                                        // slot -> active slot index
+  if (slot < VVCB_SLOT_MRL1) a = slot;
+  else if (slot < VVCB_SLOT_MIP) { if (mrlAllowed) a = slot; }
+  else if (slot - VVCB_SLOT_MIP < numMip) a = VVCB_NUM_LUMA_MODE + (mrlAllowed ? 10 : 0) + slot - VVCB_SLOT_MIP;
+  if (a < 0) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: slot %d is not evaluated for this visit", slot); return VVCB_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  rc = ensure_visit_buffers(ctx, 1);
+  if (rc) return rc;
+  const size_t need = (size_t)VVCB_NUM_SLOTS * w * h;
+  if (need > ctx->capPred) {
+    cudaFree(ctx->dPred); ctx->dPred = nullptr; ctx->capPred = 0;
+    CK(cudaMalloc(&ctx->dPred, need * sizeof(int16_t)));
+    ctx->capPred = need;
+  }
+  CK(cudaMemcpyAsync(ctx->dVisits, visit, sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
+  rc = launch_rmd(ctx, ctx->dVisits, 1, ctx->dResults, nullptr, ctx->dPred);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(pred, ctx->dPred + (size_t)a * w * h, (size_t)w * h * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_dev_alloc(vvcb_ctx* ctx, size_t bytes, void** out)
+{
+  if (!ctx || !out) return VVCB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMalloc(out, bytes));
+  return VVCB_OK;
+}
+extern "C" int vvcb_dev_free(vvcb_ctx* ctx, void* p)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaFree(p));
+  return VVCB_OK;
+}
+extern "C" int vvcb_host_alloc(vvcb_ctx* ctx, size_t bytes, void** out)
+{
+  if (!ctx || !out) return VVCB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return VVCB_OK;
+}
+extern "C" int vvcb_host_free(vvcb_ctx* ctx, void* p)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  CK(cudaFreeHost(p));
+  return VVCB_OK;
+}
+extern "C" int vvcb_dev_upload(vvcb_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+extern "C" int vvcb_dev_download(vvcb_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+extern "C" int vvcb_sync(vvcb_ctx* ctx)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+extern "C" int vvcb_timer_start(vvcb_ctx* ctx)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  return VVCB_OK;
+}
+extern "C" int vvcb_timer_stop(vvcb_ctx* ctx, float* ms)
+{
+  if (!ctx || !ms) return VVCB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return VVCB_OK;
+}
+extern "C" int vvcb_measure_int_peak(vvcb_ctx* ctx, double* gops_imad, double* gops_alu, double* gops_mixed)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const int grid = ctx->numSms * 8, iters = 4096;
+  int *dIn = nullptr, *dOut = nullptr;
+  CK(cudaMalloc(&dIn, 64 * sizeof(int)));
+  CK(cudaMalloc(&dOut, (size_t)grid * 256 * sizeof(int)));
+  int hIn[64];
+  for (int i = 0; i < 64; i++) hIn[i] = 3 + 2 * i;
+  CK(cudaMemcpy(dIn, hIn, sizeof(hIn), cudaMemcpyHostToDevice));
+  double* outs[3] = { gops_imad, gops_alu, gops_mixed };
+  // lane-operations per thread: KIND 0: 64 IMAD per iteration; KIND 1: 2 ops per statement -> 128; KIND 2: 32 IMAD + 64 ALU
+  const double opsPerIter[3] = { 64.0, 128.0, 96.0 };
+  for (int kind = 0; kind < 3; kind++) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+      CK(cudaEventRecord(ctx->ev0, ctx->stream));
+      if (kind == 0) int_peak_kernel<0><<<grid, 256, 0, ctx->stream>>>(dIn, dOut, iters);
+      if (kind == 1) int_peak_kernel<1><<<grid, 256, 0, ctx->stream>>>(dIn, dOut, iters);
+      if (kind == 2) int_peak_kernel<2><<<grid, 256, 0, ctx->stream>>>(dIn, dOut, iters);
+      CK(cudaEventRecord(ctx->ev1, ctx->stream));
+      CK(cudaEventSynchronize(ctx->ev1));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    if (outs[kind]) *outs[kind] = opsPerIter[kind] * iters * (double)grid * 256.0 / (best * 1e-3) / 1e9;
+  }
+  cudaFree(dIn); cudaFree(dOut);
+  return VVCB_OK;
+}
+extern "C" uint64_t vvcb_launch_count(const vvcb_ctx* ctx) { return ctx ? ctx->launches : 0; }

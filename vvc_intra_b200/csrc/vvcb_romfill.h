@@ -1,0 +1,27 @@
+// Host-side construction of the device ROM (filter words, per-shape mode parameters, MIP matrices).
+#pragma once
+#include <string.h>
+#include "vvcb_core.cuh"
+#include "vvc_rom_tables.h"
+
+namespace vvcb {
+inline void fill_rom(Rom& r)
+{
+  memset(&r, 0, sizeof(r));
+  for (int t = 0; t < 2; t++)
+    for (int f = 0; f < 32; f++) {
+      const int8_t* c = (t ? kIntraGaussFilter : kIntraCubicFilter) + 4 * f;
+      r.filt[t][f] = (uint32_t)(uint8_t)c[0] | ((uint32_t)(uint8_t)c[1] << 8) | ((uint32_t)(uint8_t)c[2] << 16) | ((uint32_t)(uint8_t)c[3] << 24);
+    }
+  for (int lw = 2; lw <= 6; lw++)
+    for (int lh = 2; lh <= 6; lh++)
+      for (int m = 0; m < VVCB_NUM_LUMA_MODE; m++) r.mode[lw - 2][lh - 2][m] = make_mode_param(1 << lw, 1 << lh, m, 0);
+  memcpy(r.mip4, kMipMatrix4x4, sizeof(r.mip4));
+  memcpy(r.mip8, kMipMatrix8x8, sizeof(r.mip8));
+  memcpy(r.mip16, kMipMatrix16x16, sizeof(r.mip16));
+  memcpy(r.mipOff4, kMipOffset4x4, 18); memcpy(r.mipSh4, kMipShift4x4, 18);
+  memcpy(r.mipOff8, kMipOffset8x8, 10); memcpy(r.mipSh8, kMipShift8x8, 10);
+  memcpy(r.mipOff16, kMipOffset16x16, 6); memcpy(r.mipSh16, kMipShift16x16, 6);
+}
+
+}  // namespace vvcb

@@ -1,0 +1,209 @@
+"""ctypes mirror of the C ABI in include/vvc_intra_b200.h (one method per entry point, same names, same
+argument meaning, errors raised as EngineError with the library's message -- the reference throws
+Exception, CL/TypeDef.h:1322).  No compute happens in Python and nothing here falls back to a CPU."""
+import ctypes as C
+import os
+
+import numpy as np
+
+NUM_SLOTS, MAX_LIST = 112, 16
+SLOT_MRL1, SLOT_MRL3, SLOT_MIP = 67, 72, 77
+SAT_NONE = 0xFFFFFFFF
+VISIT_NO_MRL, VISIT_NO_MIP = 1, 2
+
+# struct vvcb_rmd_visit / vvcb_rmd_result (include/vvc_intra_b200.h)
+VISIT_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('log2w', 'u1'), ('log2h', 'u1'), ('avail_al', 'u1'),
+                        ('n_above', 'u1'), ('n_above_right', 'u1'), ('n_left', 'u1'), ('n_below_left', 'u1'),
+                        ('flags', 'u1'), ('mpm', 'u1', 6), ('num_mpm_cand', 'u1'), ('pad', 'u1', 3),
+                        ('rates', '<u4', 11), ('sqrt_lambda', '<f8')], align=True)
+MODE_DTYPE = np.dtype([('mip', 'u1'), ('mrl', 'u1'), ('mode', 'u1'), ('pad', 'u1')])
+
+
+MAX_HAD_LIST = 8
+RESULT_DTYPE = np.dtype([('n_rd', '<i4'), ('n_had', '<i4'), ('n_final', '<i4'), ('pad', '<i4'),
+                         ('rd_mode', MODE_DTYPE, MAX_LIST), ('rd_cost', '<f8', MAX_LIST),
+                         ('had_mode', MODE_DTYPE, MAX_HAD_LIST), ('had_cost', '<f8', MAX_HAD_LIST),
+                         ('final_mode', MODE_DTYPE, MAX_LIST)], align=True)
+DETAIL_DTYPE = np.dtype([('sad', '<u4', NUM_SLOTS), ('satd', '<u4', NUM_SLOTS), ('n_reg', '<i4'), ('n_reg_had', '<i4'),
+                         ('reg_mode', MODE_DTYPE, MAX_LIST), ('reg_cost', '<f8', MAX_LIST),
+                         ('reg_had_mode', MODE_DTYPE, MAX_HAD_LIST), ('reg_had_cost', '<f8', MAX_HAD_LIST)], align=True)
+assert VISIT_DTYPE.itemsize == 80 and RESULT_DTYPE.itemsize == 368 and DETAIL_DTYPE.itemsize == 1192, \
+    (VISIT_DTYPE.itemsize, RESULT_DTYPE.itemsize, DETAIL_DTYPE.itemsize)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libvvc_intra_b200.so')
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libvvc_intra_b200.so; fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise EngineError('%s is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                              '(there is no CPU fallback)' % path)
+        L = C.CDLL(path)
+        L.vvcb_last_error.restype = C.c_char_p
+        L.vvcb_last_error.argtypes = [C.c_void_p]
+        L.vvcb_launch_count.restype = C.c_uint64
+        L.vvcb_launch_count.argtypes = [C.c_void_p]
+        L.vvcb_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
+        L.vvcb_destroy.argtypes = [C.c_void_p]
+        L.vvcb_destroy.restype = None
+        L.vvcb_frame_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.vvcb_reco_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.vvcb_rmd_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.vvcb_rmd_eval_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.vvcb_rmd_pred.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.vvcb_dev_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.vvcb_dev_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.vvcb_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.vvcb_host_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.vvcb_dev_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.vvcb_dev_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.vvcb_sync.argtypes = [C.c_void_p]
+        L.vvcb_frame_bind_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.vvcb_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+        L.vvcb_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.vvcb_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.vvcb_timer_start.argtypes = [C.c_void_p]
+        L.vvcb_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class IntraCostEngine:
+    """One engine context (= one CUDA device + stream).  Mirrors vvcb_create .. vvcb_destroy."""
+
+    def __init__(self, device=0, bit_depth=10, ctu_size=128):
+        self._lib = load_library()
+        self._ctx = C.c_void_p()
+        rc = self._lib.vvcb_create(C.byref(self._ctx), device, bit_depth, ctu_size)
+        if rc != 0:
+            raise EngineError(self._lib.vvcb_last_error(None).decode())
+        self.bit_depth, self.ctu_size, self.device = bit_depth, ctu_size, device
+
+    def close(self):
+        if getattr(self, '_ctx', None):
+            for p in getattr(self, '_pinned', []):
+                self._lib.vvcb_host_free(self._ctx, p)
+            self._pinned = []
+            self._lib.vvcb_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError('%s (status %d)' % (self._lib.vvcb_last_error(self._ctx).decode(), rc))
+
+    # ---- planes
+    def frame_begin(self, orig):
+        orig = np.ascontiguousarray(orig, np.int16)
+        self._ck(self._lib.vvcb_frame_begin(self._ctx, _ptr(orig), orig.shape[1], orig.shape[1], orig.shape[0]))
+
+    def reco_update(self, reco, x=0, y=0):
+        reco = np.ascontiguousarray(reco, np.int16)
+        self._ck(self._lib.vvcb_reco_update(self._ctx, _ptr(reco), reco.shape[1], x, y, reco.shape[1], reco.shape[0]))
+
+    def frame_bind_device(self, d_orig, d_reco, stride, width, height):
+        self._ck(self._lib.vvcb_frame_bind_device(self._ctx, d_orig, d_reco, stride, width, height))
+
+    def kernel_timing(self, on=True):
+        self._ck(self._lib.vvcb_kernel_timing(self._ctx, int(on)))
+
+    def kernel_times(self):
+        """(ms_plan, ms_eval, ms_lists, timed launches) accumulated since the last call."""
+        ms = (C.c_float * 3)()
+        n = C.c_int()
+        self._ck(self._lib.vvcb_kernel_times(self._ctx, ms, C.byref(n)))
+        return ms[0], ms[1], ms[2], n.value
+
+    # ---- rough mode decision
+    def rmd_eval(self, visits, out=None, detail=False, detail_out=None):
+        """vvcb_rmd_eval.  Returns the result array, or (results, details) when detail is requested."""
+        visits = np.ascontiguousarray(visits, VISIT_DTYPE)
+        if out is None:
+            out = np.empty(len(visits), RESULT_DTYPE)
+        if detail and detail_out is None:
+            detail_out = np.empty(len(visits), DETAIL_DTYPE)
+        self._ck(self._lib.vvcb_rmd_eval(self._ctx, _ptr(visits), len(visits), _ptr(out),
+                                         _ptr(detail_out) if detail_out is not None else None))
+        return (out, detail_out) if detail_out is not None else out
+
+    def rmd_pred(self, visit, slot):
+        visit = np.ascontiguousarray(visit, VISIT_DTYPE).reshape(1)
+        w, h = 1 << int(visit[0]['log2w']), 1 << int(visit[0]['log2h'])
+        pred = np.zeros((h, w), np.int16)
+        self._ck(self._lib.vvcb_rmd_pred(self._ctx, _ptr(visit), slot, _ptr(pred)))
+        return pred
+
+    # ---- device-resident path (bench: kernels without the PCIe copies)
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(self._lib.vvcb_dev_alloc(self._ctx, nbytes, C.byref(p)))
+        return p
+
+    def dev_free(self, p):
+        self._ck(self._lib.vvcb_dev_free(self._ctx, p))
+
+    def dev_upload(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._ck(self._lib.vvcb_dev_upload(self._ctx, dptr, _ptr(arr), arr.nbytes))
+
+    def dev_download(self, arr, dptr):
+        self._ck(self._lib.vvcb_dev_download(self._ctx, _ptr(arr), dptr, arr.nbytes))
+
+    def rmd_eval_device(self, d_visits, n, d_results, d_details=None):
+        self._ck(self._lib.vvcb_rmd_eval_device(self._ctx, d_visits, n, d_results, d_details))
+
+    def host_array(self, n, dtype):
+        """numpy array of n items backed by page-locked host memory (vvcb_host_alloc)."""
+        dtype = np.dtype(dtype)
+        p = C.c_void_p()
+        nbytes = max(1, n * dtype.itemsize)
+        self._ck(self._lib.vvcb_host_alloc(self._ctx, nbytes, C.byref(p)))
+        buf = (C.c_char * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=n)
+        self._pinned = getattr(self, '_pinned', [])
+        self._pinned.append(p)
+        return arr
+
+    def sync(self):
+        self._ck(self._lib.vvcb_sync(self._ctx))
+
+    def timer_start(self):
+        self._ck(self._lib.vvcb_timer_start(self._ctx))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self._lib.vvcb_timer_stop(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def measure_int_peak(self):
+        """(IMAD-only, IADD3/LOP3-only, mixed) dependent-free issue rates in 1e9 lane-ops/s."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self._lib.vvcb_measure_int_peak(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    @property
+    def launch_count(self):
+        return int(self._lib.vvcb_launch_count(self._ctx))
