@@ -57,7 +57,7 @@ def test_prediction_samples_match_reference(eng8):
             got = eng8.rmd_pred(a, G.slot_of(v['head'], e))
             assert np.array_equal(got, e['pred']), (v['head']['w'], v['head']['h'], e['mip'], e['mrl'], e['mode'])
             n += 1
-    assert n > 200
+    assert n > 100
 
 
 def random_case(rng, bd, n_per_shape, plane=(512, 1024)):

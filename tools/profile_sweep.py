@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Small driver for ncu: one exhaustive RMD sweep of a WxH synthetic 10-bit frame (after one warm-up pass)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
+import vvc_intra_b200 as vb          # noqa: E402
+from make_golden import synth_yuv    # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--width', type=int, default=416)
+ap.add_argument('--height', type=int, default=240)
+ap.add_argument('--passes', type=int, default=2)
+a = ap.parse_args()
+Y = synth_yuv(a.width, a.height, 10)[0].astype(np.int16)
+vis = vb.build_sweep_visits(a.width, a.height, qp=32)
+with vb.IntraCostEngine(0, 10, 128) as eng:
+    eng.frame_begin(Y)
+    eng.reco_update(Y)
+    eng.kernel_timing(True)
+    for _ in range(a.passes):
+        res = eng.rmd_eval(vis)
+    print('visits', len(vis), 'kernel ms (plan, eval, lists, n):', eng.kernel_times(), 'n_rd[0]', res['n_rd'][0])
