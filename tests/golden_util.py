@@ -101,3 +101,39 @@ def check_visit_against_reference(v, res, det):
         if got != exp:
             errs.append('final list %dx%d: %r != %r' % (w, h, got, exp))
     return errs
+
+
+def random_case(rng, bd, n_per_shape, plane=(512, 1024)):
+    H, W = plane
+    orig = rng.integers(0, 1 << bd, (H, W)).astype(np.int16)
+    reco = rng.integers(0, 1 << bd, (H, W)).astype(np.int16)
+    vis = []
+    for lw in range(2, 7):
+        for lh in range(2, 7):
+            if (lw == 6) != (lh == 6):
+                continue
+            w, h = 1 << lw, 1 << lh
+            for _ in range(n_per_shape):
+                v = np.zeros(1, O.VISIT_DTYPE)[0]
+                v['x'] = 4 * rng.integers(1, (W - 2 * w) // 4)
+                v['y'] = 4 * rng.integers(1, (H - 2 * h) // 4)
+                v['log2w'], v['log2h'] = lw, lh
+                mode = rng.integers(0, 4)
+                if mode == 0:        # everything available
+                    v['avail_al'], v['n_above'], v['n_above_right'], v['n_left'], v['n_below_left'] = 1, w // 4, w // 4, h // 4, h // 4
+                elif mode == 1:      # nothing
+                    pass
+                else:                # ragged
+                    v['avail_al'] = rng.integers(0, 2)
+                    v['n_above'] = rng.integers(0, w // 4 + 1)
+                    v['n_above_right'] = rng.integers(0, w // 4 + 1)
+                    v['n_left'] = rng.integers(0, h // 4 + 1)
+                    v['n_below_left'] = rng.integers(0, h // 4 + 1)
+                v['flags'] = rng.integers(0, 4) if rng.random() < 0.3 else 0
+                L, A = rng.integers(0, 67, 2)
+                mpm, nc = O.intra_mpms(int(L), int(A))
+                v['mpm'], v['num_mpm_cand'] = mpm, nc
+                v['rates'] = rng.integers(100, 200000, 11)
+                v['sqrt_lambda'] = float(rng.uniform(1e-4, 3e-3))
+                vis.append(v)
+    return orig, reco, np.array(vis, O.VISIT_DTYPE)

@@ -44,20 +44,31 @@ void emu_launch(unsigned grid, unsigned block, const std::function<void()>& fn)
   }
 }
 
+template <int TILE, int KIND> static void emul_eval_bucket(const EvalParams& P)
+{
+  emu_launch(1, kThreads, [&] { rmd_eval_kernel<TILE, KIND>(P); });
+}
+
 extern "C" int emul_rmd_eval(const int16_t* orig, const int16_t* reco, int stride, int bd, int ctu,
                              const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results, vvcb_rmd_detail* details,
                              int16_t* predOut)
 {
   static Rom rom;
   fill_rom(rom);
-  std::vector<WorkItem> items((size_t)n * VVCB_NUM_SLOTS);
-  unsigned counters[4] = { 0, 0, 0, 0 };
-  emu_launch((n + 255) / 256, 256, [&] { rmd_plan_kernel(visits, n, ctu, items.data(), counters); });
+  std::vector<WorkItem> items((size_t)n * 60 + 8);
+  PlanState plan;
+  memset(&plan, 0, sizeof(plan));
+  emu_launch((n + 255) / 256, 256, [&] { rmd_plan_count(visits, n, ctu, &plan); });
+  emu_launch(1, 32, [&] { rmd_plan_scan(&plan); });
+  emu_launch((n + 255) / 256, 256, [&] { rmd_plan_fill(visits, n, ctu, &plan, items.data()); });
   EvalParams P;
-  P.visits = visits; P.items = items.data(); P.itemCount = counters; P.cursor = counters + 1;
+  P.visits = visits; P.items = items.data(); P.plan = &plan;
   P.details = details;
   P.orig = orig; P.reco = reco; P.stride = stride; P.bd = bd; P.ctu = ctu; P.rom = &rom; P.predOut = predOut;
-  emu_launch(1, kThreads, [&] { rmd_eval_kernel(P); });
+  for (int b = 0; b < kNumBuckets; b++) {
+    if (!plan.count[b]) continue;
+    VVCB_FOR_BUCKET(b, emul_eval_bucket, P);
+  }
   emu_launch((n + 127) / 128, 128, [&] { rmd_lists_kernel(visits, n, ctu, results, details); });
   return 0;
 }

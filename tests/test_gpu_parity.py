@@ -60,48 +60,12 @@ def test_prediction_samples_match_reference(eng8):
     assert n > 100
 
 
-def random_case(rng, bd, n_per_shape, plane=(512, 1024)):
-    H, W = plane
-    orig = rng.integers(0, 1 << bd, (H, W)).astype(np.int16)
-    reco = rng.integers(0, 1 << bd, (H, W)).astype(np.int16)
-    vis = []
-    for lw in range(2, 7):
-        for lh in range(2, 7):
-            if (lw == 6) != (lh == 6):
-                continue
-            w, h = 1 << lw, 1 << lh
-            for _ in range(n_per_shape):
-                v = np.zeros(1, vb.VISIT_DTYPE)[0]
-                v['x'] = 4 * rng.integers(1, (W - 2 * w) // 4)
-                v['y'] = 4 * rng.integers(1, (H - 2 * h) // 4)
-                v['log2w'], v['log2h'] = lw, lh
-                mode = rng.integers(0, 4)
-                if mode == 0:        # everything available
-                    v['avail_al'], v['n_above'], v['n_above_right'], v['n_left'], v['n_below_left'] = 1, w // 4, w // 4, h // 4, h // 4
-                elif mode == 1:      # nothing
-                    pass
-                else:                # ragged
-                    v['avail_al'] = rng.integers(0, 2)
-                    v['n_above'] = rng.integers(0, w // 4 + 1)
-                    v['n_above_right'] = rng.integers(0, w // 4 + 1)
-                    v['n_left'] = rng.integers(0, h // 4 + 1)
-                    v['n_below_left'] = rng.integers(0, h // 4 + 1)
-                v['flags'] = rng.integers(0, 4) if rng.random() < 0.3 else 0
-                L, A = rng.integers(0, 67, 2)
-                mpm, nc = O.intra_mpms(int(L), int(A))
-                v['mpm'], v['num_mpm_cand'] = mpm, nc
-                v['rates'] = rng.integers(100, 200000, 11)
-                v['sqrt_lambda'] = float(rng.uniform(1e-4, 3e-3))
-                vis.append(v)
-    return orig, reco, np.array(vis, vb.VISIT_DTYPE)
-
-
 @pytest.mark.parametrize('bd,seed', [(8, 1), (10, 2), (10, 3)])
 def test_random_visits_match_oracle(bd, seed, eng8, eng10):
     """Seeded random planes, random ragged availability, random MPM lists / rates / lambda, all 17 shapes."""
     eng = eng8 if bd == 8 else eng10
     rng = np.random.default_rng(seed)
-    orig, reco, arr = random_case(rng, bd, 24)
+    orig, reco, arr = G.random_case(rng, bd, 24)
     eng.frame_begin(orig)
     eng.reco_update(reco)
     res, det = eng.rmd_eval(arr, detail=True)
@@ -117,7 +81,7 @@ def test_extreme_sample_values(eng10):
     for orig, reco in ((np.zeros((H, W), np.int16), np.full((H, W), 1023, np.int16)),
                        (((xx + yy) % 2 * 1023).astype(np.int16), ((xx + yy + 1) % 2 * 1023).astype(np.int16))):
         rng = np.random.default_rng(7)
-        _, _, arr = random_case(rng, 10, 3, plane=(H, W))
+        _, _, arr = G.random_case(rng, 10, 3, plane=(H, W))
         eng10.frame_begin(orig)
         eng10.reco_update(reco)
         res, det = eng10.rmd_eval(arr, detail=True)

@@ -63,3 +63,14 @@ def test_emulated_kernels_match_reference(emul, name):
     ora, odet = O.rmd_batch(orig, reco, sel[0]['head']['bd'], 128, arr)
     assert np.array_equal(det['sad'], odet['sad']) and np.array_equal(det['satd'], odet['satd'])
     assert res.tobytes() == ora.tobytes() and det.tobytes() == odet.tobytes()
+
+
+@pytest.mark.parametrize('bd,seed', [(8, 5), (10, 6)])
+def test_emulated_kernels_match_oracle_on_random_visits(emul, bd, seed):
+    """Ragged availability, NO_MRL / NO_MIP flags, random MPM lists (with and without DC), random rates."""
+    rng = np.random.default_rng(seed)
+    orig, reco, arr = G.random_case(rng, bd, 4, plane=(256, 512))
+    res, det, _ = run_emul(emul, orig, reco, bd, arr)
+    ora, odet = O.rmd_batch(orig, reco, bd, 128, arr)
+    bad = [i for i in range(len(arr)) if res[i].tobytes() != ora[i].tobytes() or det[i].tobytes() != odet[i].tobytes()]
+    assert not bad, (len(bad), arr[bad[0]])

@@ -52,7 +52,7 @@ struct vvcb_ctx {
   vvcb_rmd_visit* dVisits; vvcb_rmd_result* dResults; size_t capVisits;
   vvcb_rmd_detail* dDetails; size_t capDetails;
   WorkItem* dItems; size_t capItems;
-  unsigned* dCounters;              // [0] item count, [1] cursor
+  PlanState* dPlan;
   int16_t* dPred; size_t capPred;
   int numSms;
   uint64_t launches;
@@ -117,7 +117,7 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
   e = cudaMemcpy(ctx->dRom, h, sizeof(Rom), cudaMemcpyHostToDevice);
   delete h;
   if (e != cudaSuccess) return fail("cudaMemcpy(rom)", e);
-  if ((e = cudaMalloc(&ctx->dCounters, 4 * sizeof(unsigned))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
+  if ((e = cudaMalloc(&ctx->dPlan, sizeof(PlanState))) != cudaSuccess) return fail("cudaMalloc(plan)", e);
   *out = ctx;
   return VVCB_OK;
 }
@@ -128,7 +128,7 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails);
-  cudaFree(ctx->dItems); cudaFree(ctx->dCounters); cudaFree(ctx->dPred);
+  cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->kev[i]);
   cudaStreamDestroy(ctx->stream);
@@ -206,7 +206,7 @@ extern "C" int vvcb_kernel_times(vvcb_ctx* ctx, float ms[3], int* launches)
 
 static int ensure_items(vvcb_ctx* ctx, int n)
 {
-  const size_t need = (size_t)n * 56;     // worst case 64x64: ceil(112 slots * 64 lanes / kItemTasks)
+  const size_t need = (size_t)n * 60 + 8; // worst case 64x64: three kinds, ceil(slots * 64 lanes / kItemTasks) items each
   if (need > ctx->capItems) {
     cudaFree(ctx->dItems); ctx->dItems = nullptr; ctx->capItems = 0;
     CK(cudaMalloc(&ctx->dItems, need * sizeof(WorkItem)));
@@ -225,6 +225,11 @@ static int ensure_details(vvcb_ctx* ctx, int n)
   return VVCB_OK;
 }
 
+template <int TILE, int KIND> static void launch_eval_bucket(const EvalParams& P, int grid, cudaStream_t stream)
+{
+  rmd_eval_kernel<TILE, KIND><<<grid, kThreads, 0, stream>>>(P);
+}
+
 static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_rmd_result* dResults, vvcb_rmd_detail* dDetails,
                       int16_t* dPred)
 {
@@ -237,13 +242,15 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
     if (rc) return rc;
     dDetails = ctx->dDetails;
   }
-  CK(cudaMemsetAsync(ctx->dCounters, 0, 4 * sizeof(unsigned), ctx->stream));
+  CK(cudaMemsetAsync(ctx->dPlan, 0, sizeof(PlanState), ctx->stream));
   const bool tm = ctx->timing != 0;
   if (tm) CK(cudaEventRecord(ctx->kev[0], ctx->stream));
-  rmd_plan_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dItems, ctx->dCounters);
+  rmd_plan_count<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan);
+  rmd_plan_scan<<<1, 32, 0, ctx->stream>>>(ctx->dPlan);
+  rmd_plan_fill<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan, ctx->dItems);
   if (tm) CK(cudaEventRecord(ctx->kev[1], ctx->stream));
   EvalParams P;
-  P.visits = dVisits; P.items = ctx->dItems; P.itemCount = ctx->dCounters; P.cursor = ctx->dCounters + 1;
+  P.visits = dVisits; P.items = ctx->dItems; P.plan = ctx->dPlan;
   P.details = dDetails;
   P.orig = ctx->bOrig; P.reco = ctx->bReco; P.stride = ctx->stride; P.bd = ctx->bd; P.ctu = ctx->ctu; P.rom = ctx->dRom;
   P.predOut = dPred;
@@ -251,10 +258,10 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   int grid = ctx->numSms * 2;
   if (grid > maxCtas) grid = (int)maxCtas;
   if (grid < 1) grid = 1;
-  rmd_eval_kernel<<<grid, kThreads, 0, ctx->stream>>>(P);
+  for (int b = 0; b < kNumBuckets; b++) { VVCB_FOR_BUCKET(b, launch_eval_bucket, P, grid, ctx->stream); }
   if (tm) CK(cudaEventRecord(ctx->kev[2], ctx->stream));
   rmd_lists_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dResults, dDetails);
-  ctx->launches += 3;
+  ctx->launches += 3 + kNumBuckets + 1;
   CK(cudaGetLastError());
   if (tm) {
     CK(cudaEventRecord(ctx->kev[3], ctx->stream));
@@ -338,11 +345,8 @@ extern "C" int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slo
   const int w = 1 << visit->log2w, h = 1 << visit->log2h;
   const bool mrlAllowed = !(visit->flags & VVCB_VISIT_NO_MRL) && (visit->y & (ctx->ctu - 1)) != 0;
   const int numMip = (visit->flags & VVCB_VISIT_NO_MIP) ? 0 : mip_num_modes(w, h);
-  int a = -1;                                        // slot -> active slot index
-  if (slot < VVCB_SLOT_MRL1) a = slot;
-  else if (slot < VVCB_SLOT_MIP) { if (mrlAllowed) a = slot; }
-  else if (slot - VVCB_SLOT_MIP < numMip) a = VVCB_NUM_LUMA_MODE + (mrlAllowed ? 10 : 0) + slot - VVCB_SLOT_MIP;
-  if (a < 0) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: slot %d is not evaluated for this visit", slot); return VVCB_ERR_ARG; }
+  const bool evaluated = slot < VVCB_SLOT_MRL1 || (slot < VVCB_SLOT_MIP ? mrlAllowed : slot - VVCB_SLOT_MIP < numMip);
+  if (!evaluated) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: slot %d is not evaluated for this visit", slot); return VVCB_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   rc = ensure_visit_buffers(ctx, 1);
   if (rc) return rc;
@@ -355,7 +359,7 @@ extern "C" int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slo
   CK(cudaMemcpyAsync(ctx->dVisits, visit, sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
   rc = launch_rmd(ctx, ctx->dVisits, 1, ctx->dResults, nullptr, ctx->dPred);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(pred, ctx->dPred + (size_t)a * w * h, (size_t)w * h * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(pred, ctx->dPred + (size_t)slot * w * h, (size_t)w * h * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return VVCB_OK;
 }

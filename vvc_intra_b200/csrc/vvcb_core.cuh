@@ -25,7 +25,10 @@ namespace vvcb {
 // ---- geometry -------------------------------------------------------------------------------------
 constexpr int kLineMax   = 140;            // samples per reference line (2*64 + 1 + 3, padded)
 constexpr int kNumSets   = 4;              // 0: line 0 unfiltered, 1: line 0 filtered, 2: line 1, 3: line 3
-constexpr int kSlotLineWords = 1152;       // int16 per warp for the per-slot main lines in flight
+constexpr int kSlotLineWords = 1920;       // int16 per warp for per-slot scratch in flight (projected main lines, MIP planes)
+constexpr int kNumClasses = 6;             // SATD tile of the shape: 0 4x4, 1 8x4, 2 4x8, 3 8x8, 4 16x8, 5 8x16
+constexpr int kNumKinds   = 3;             // 0 angular, 1 planar/DC, 2 MIP
+constexpr int kNumBuckets = kNumClasses * kNumKinds;
 constexpr int kItemTasks = 128;            // lane-tasks per work item (4 warp iterations)
 
 VHD int vmin(int a, int b) { return a < b ? a : b; }
@@ -185,6 +188,7 @@ VHD void line_pos(const LineGeom& g, int i, bool& isLeft, int& k, int& dx, int& 
 struct Rom {
   uint32_t filt[2][32];                    // [0] cubic (CL/InterpolationFilter.cpp:100), [1] Gaussian (CL/IntraPrediction.cpp:76)
   ModeParam mode[6][6][VVCB_NUM_LUMA_MODE];  // [log2w-2][log2h-2][mode], reference line 0
+  uint8_t angOrder[6][6][65];              // angular modes 2..66 ordered by (hor/ver, PDPC class) so that the lanes of a warp agree
   uint8_t mip4[18 * 16 * 4], mip8[10 * 16 * 8], mip16[6 * 64 * 7];
   uint8_t mipOff4[18], mipSh4[18], mipOff8[10], mipSh8[10], mipOff16[6], mipSh16[6];
 };

@@ -2,10 +2,14 @@
 // CUDA-on-pthreads shim, by tests/host_emul/emul_rmd.cpp (test-only lane emulation of this very source).
 //
 // Pipeline of one vvcb_rmd_eval call (all on the context's stream):
-//   rmd_plan_kernel    one thread per visit: cuts the visit into work items of <= kItemTasks lane-tasks
-//   rmd_eval_kernel    persistent warps pull work items; a lane predicts one 8x8 (or 4x4) unit of one
-//                      evaluation slot, keeps the residual in registers, computes SAD and the Walsh-
-//                      Hadamard SATD there, and the slot's lanes reduce with warp shuffles
+//   rmd_plan_count / rmd_plan_scan / rmd_plan_fill
+//                      cut every visit into work items of <= kItemTasks lane-tasks and bucket them by
+//                      (SATD tile class of the shape) x (prediction kind: angular, planar/DC, MIP)
+//   rmd_eval_kernel<TILE, KIND>   one launch per bucket, persistent warps pull the bucket's items.  Every
+//                      warp of a launch runs the same straight-line code (profiles/r1a: a monolithic kernel
+//                      was instruction-fetch bound).  A lane predicts one 8x8 (or 4x4) unit of one evaluation
+//                      slot, keeps the residual in registers, computes SAD and the Walsh-Hadamard SATD there,
+//                      and the slot's lanes reduce with warp shuffles.
 //   rmd_lists_kernel   one thread per visit: mode bits, double-precision costs and the exact replay of
 //                      the reference's candidate-list insertions
 #pragma once
@@ -13,46 +17,37 @@
 
 using namespace vvcb;
 
-// =====================================================================================================
-// device helpers
-// =====================================================================================================
 namespace {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads     = kWarpsPerCta * 32;
+constexpr int KIND_ANG = 0, KIND_PDC = 1, KIND_MIP = 2;
 
 struct WarpSmem {
-  int16_t lines[kNumSets][2][kLineMax];   // [set][0 top / 1 left][index]
-  int16_t slotLines[kSlotLineWords];      // per-slot main lines / MIP reduced predictions in flight
+  int16_t lines[kNumSets][2][kLineMax];   // [set][0 top / 1 left][index], tails replicated for positive angles
+  int16_t slot[kSlotLineWords];           // per-slot scratch of the slots in flight
   int     mipBnd[8];                      // Haar-averaged boundary: [0..4) top, [4..8) left
+};
+
+struct PlanState {                        // device-resident, zeroed before every call
+  unsigned count[kNumBuckets];            // items per bucket
+  unsigned offset[kNumBuckets];           // first item of the bucket
+  unsigned fill[kNumBuckets];             // fill cursor (plan) ...
+  unsigned cursor[kNumBuckets];           // ... and consume cursor (eval)
 };
 
 struct EvalParams {
   const vvcb_rmd_visit* visits;
   const WorkItem*       items;
-  const unsigned*       itemCount;
-  unsigned*             cursor;
+  PlanState*            plan;
   vvcb_rmd_detail*      details;  // sad/satd tables, one per visit
   const int16_t*        orig;
   const int16_t*        reco;
   int                   stride;   // both planes
   int                   bd, ctu;
   const Rom*            rom;
-  int16_t*              predOut;  // optional: [active slot][h][w] of visit 0 (debug / parity)
+  int16_t*              predOut;  // optional: [slot][h][w] of visit 0 (debug / parity)
 };
-
-__device__ __forceinline__ int active_slot_to_slot(int a, bool mrlAllowed)
-{
-  if (a < VVCB_NUM_LUMA_MODE) return a;
-  a -= VVCB_NUM_LUMA_MODE;
-  if (mrlAllowed) { if (a < 10) return VVCB_SLOT_MRL1 + a; a -= 10; }
-  return VVCB_SLOT_MIP + a;
-}
-
-__device__ __forceinline__ int num_active_slots(bool mrlAllowed, int numMip)
-{
-  return VVCB_NUM_LUMA_MODE + (mrlAllowed ? 10 : 0) + numMip;
-}
 
 __device__ __forceinline__ bool visit_mrl_allowed(const vvcb_rmd_visit& v, int ctu)
 {
@@ -64,45 +59,146 @@ __device__ __forceinline__ int visit_num_mip(const vvcb_rmd_visit& v)
   return (v.flags & VVCB_VISIT_NO_MIP) ? 0 : mip_num_modes(1 << v.log2w, 1 << v.log2h);
 }
 
-// ---- reference lines of one visit into the warp's shared memory ---------------------------------------
+// position (1..5) of DC among MPM[1..5], 0 if absent: DC on reference lines 1/3 goes to the planar/DC kernel
+__device__ __forceinline__ int mpm_dc_pos(const vvcb_rmd_visit& v)
+{
+  int pos = 0;
+#pragma unroll
+  for (int i = 5; i >= 1; i--) if (v.mpm[i] == 1) pos = i;
+  return pos;
+}
+
+// slots of one kind for one visit
+__device__ __forceinline__ int kind_slot_count(const vvcb_rmd_visit& v, int kind, int ctu)
+{
+  const bool mrl = visit_mrl_allowed(v, ctu);
+  const int dc = mpm_dc_pos(v);
+  if (kind == KIND_ANG) return 65 + (mrl ? 2 * (5 - (dc ? 1 : 0)) : 0);
+  if (kind == KIND_PDC) return 2 + (mrl && dc ? 2 : 0);
+  return visit_num_mip(v);
+}
+
+// index inside the kind's slot list -> evaluation slot (include/vvc_intra_b200.h)
+__device__ __forceinline__ int kind_slot(const Rom& rom, const vvcb_rmd_visit& v, int kind, int idx)
+{
+  if (kind == KIND_MIP) return VVCB_SLOT_MIP + idx;
+  const int dc = mpm_dc_pos(v);
+  if (kind == KIND_PDC) {
+    if (idx < 2) return idx;
+    return (idx == 2 ? VVCB_SLOT_MRL1 : VVCB_SLOT_MRL3) + dc - 1;
+  }
+  if (idx < 65) return rom.angOrder[v.log2w - 2][v.log2h - 2][idx];
+  const int per = 5 - (dc ? 1 : 0);
+  const int j = idx - 65;
+  const int li = j >= per ? 1 : 0;
+  int i = 1 + (j - li * per);
+  if (dc && i >= dc) i++;
+  return (li ? VVCB_SLOT_MRL3 : VVCB_SLOT_MRL1) + i - 1;
+}
+
+// =====================================================================================================
+// planning
+// =====================================================================================================
+__device__ __forceinline__ int items_of(int nSlots, int lanes, int& perItem)
+{
+  perItem = lanes >= kItemTasks ? 1 : kItemTasks / lanes;
+  return (nSlots + perItem - 1) / perItem;
+}
+
+__global__ void rmd_plan_count(const vvcb_rmd_visit* visits, int n, int ctu, PlanState* plan)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const vvcb_rmd_visit v = visits[i];
+  const Shape sh = make_shape(v.log2w, v.log2h);
+  for (int kind = 0; kind < kNumKinds; kind++) {
+    int perItem;
+    const int nItems = items_of(kind_slot_count(v, kind, ctu), sh.lanes, perItem);
+    if (nItems) atomicAdd(&plan->count[sh.tile * kNumKinds + kind], (unsigned)nItems);
+  }
+}
+
+__global__ void rmd_plan_scan(PlanState* plan)
+{
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned acc = 0;
+    for (int b = 0; b < kNumBuckets; b++) { plan->offset[b] = acc; acc += plan->count[b]; plan->fill[b] = 0; plan->cursor[b] = 0; }
+  }
+}
+
+__global__ void rmd_plan_fill(const vvcb_rmd_visit* visits, int n, int ctu, PlanState* plan, WorkItem* items)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const vvcb_rmd_visit v = visits[i];
+  const Shape sh = make_shape(v.log2w, v.log2h);
+  for (int kind = 0; kind < kNumKinds; kind++) {
+    int perItem;
+    const int nSlots = kind_slot_count(v, kind, ctu);
+    const int nItems = items_of(nSlots, sh.lanes, perItem);
+    if (!nItems) continue;
+    const int b = sh.tile * kNumKinds + kind;
+    const unsigned base = plan->offset[b] + atomicAdd(&plan->fill[b], (unsigned)nItems);
+    for (int k = 0; k < nItems; k++) {
+      WorkItem w;
+      w.visit = (uint32_t)i;
+      w.slot_begin = (uint16_t)(k * perItem);
+      w.slot_count = (uint16_t)vmin(perItem, nSlots - k * perItem);
+      items[base + k] = w;
+    }
+  }
+}
+
+// =====================================================================================================
+// reference lines of one visit into the warp's shared memory
+// =====================================================================================================
 __device__ void build_line_set(WarpSmem& sm, int set, int mrl, const vvcb_rmd_visit& v, const Shape& sh,
                                const int16_t* reco, int stride, int bd, int lane)
 {
   const LineGeom g = make_line_geom(v, sh.w, sh.h, mrl);
   const int16_t* base = reco + (size_t)v.y * stride + v.x;
-  for (int i = lane; i < g.n; i += 32) {
-    const int src = line_source(g, i);
+  // tails: the main reference of positive angles is extended by replication (CL/IntraPrediction.cpp:717-726)
+  const int extTop = (mrl << vmax(0, sh.lw - sh.lh)) + 2, extLeft = (mrl << vmax(0, sh.lh - sh.lw)) + 2;
+  const int nTop = 2 * sh.w + 1 + mrl, nLeft = 2 * sh.h + 1 + mrl;
+  const int total = g.n + extTop + extLeft;
+  for (int i = lane; i < total; i += 32) {
+    const int pos = i < g.n ? i : (i < g.n + extTop ? g.n - 1 : 0);
+    const int src = line_source(g, pos);
     int val = 1 << (bd - 1);
     bool isLeft; int k, dx, dy;
     if (src >= 0) {
       line_pos(g, src, isLeft, k, dx, dy);
       val = base[dy * stride + dx];
     }
-    line_pos(g, i, isLeft, k, dx, dy);
-    if (isLeft) sm.lines[set][1][k] = (int16_t)val;
-    else {
-      sm.lines[set][0][k] = (int16_t)val;
-      if (k == 0) sm.lines[set][1][0] = (int16_t)val;
-    }
+    if (i < g.n) {
+      line_pos(g, i, isLeft, k, dx, dy);
+      if (isLeft) sm.lines[set][1][k] = (int16_t)val;
+      else {
+        sm.lines[set][0][k] = (int16_t)val;
+        if (k == 0) sm.lines[set][1][0] = (int16_t)val;
+      }
+    } else if (i < g.n + extTop) sm.lines[set][0][nTop + (i - g.n)] = (int16_t)val;
+    else sm.lines[set][1][nLeft + (i - g.n - extTop)] = (int16_t)val;
   }
 }
 
+// [1 2 1]/4 smoothing of set 0 into set 1 (CL/IntraPrediction.cpp:1470-1522), tails copied
 __device__ void build_filtered_set(WarpSmem& sm, const Shape& sh, int lane)
 {
   const int nTop = 2 * sh.w + 1, nLeft = 2 * sh.h + 1;
   const int16_t* top = sm.lines[0][0];
   const int16_t* left = sm.lines[0][1];
-  for (int i = lane; i < nTop; i += 32) {
+  for (int i = lane; i < nTop + 2; i += 32) {
     int v;
     if (i == 0) v = (left[1] + 2 * top[0] + top[1] + 2) >> 2;
-    else if (i == nTop - 1) v = top[i];
+    else if (i >= nTop - 1) v = top[i];
     else v = (top[i - 1] + 2 * top[i] + top[i + 1] + 2) >> 2;
     sm.lines[1][0][i] = (int16_t)v;
     if (i == 0) sm.lines[1][1][0] = (int16_t)v;
   }
-  for (int i = 1 + lane; i < nLeft; i += 32) {
+  for (int i = 1 + lane; i < nLeft + 2; i += 32) {
     int v;
-    if (i == nLeft - 1) v = left[i];
+    if (i >= nLeft - 1) v = left[i];
     else v = (left[i - 1] + 2 * left[i] + left[i + 1] + 2) >> 2;   // left[0] == top[0]
     sm.lines[1][1][i] = (int16_t)v;
   }
@@ -123,7 +219,9 @@ __device__ void build_mip_boundary(WarpSmem& sm, const Shape& sh, const MipGeom&
   }
 }
 
-// ---- per-slot set-up by the slot's lane group -----------------------------------------------------------
+// =====================================================================================================
+// per-slot pieces
+// =====================================================================================================
 __device__ __forceinline__ SlotInfo make_slot_info(const Rom& rom, const vvcb_rmd_visit& v, const Shape& sh, int slot)
 {
   SlotInfo s;
@@ -145,91 +243,41 @@ __device__ __forceinline__ SlotInfo make_slot_info(const Rom& rom, const vvcb_rm
   return s;
 }
 
-// main line of an angular slot: ml[t + off] = refMain0[t]  (CL/IntraPrediction.cpp:654-726)
-__device__ void build_slot_line(int16_t* ml, const WarpSmem& sm, const SlotInfo& s, const Shape& sh, int gl, int gsize)
+// Main reference of a negative-angle slot with its projected extension (CL/IntraPrediction.cpp:654-673):
+// buf[t + mh] = refMain0[t], t in [-mh, mw + 1 + mrl].  Positive angles read the visit's lines directly.
+__device__ void build_projected_line(int16_t* buf, const WarpSmem& sm, const SlotInfo& s, int mw, int mh, int gl, int gsize)
 {
   const int16_t* mainSrc = sm.lines[s.set][s.p.is_ver ? 0 : 1];
   const int16_t* sideSrc = sm.lines[s.set][s.p.is_ver ? 1 : 0];
-  const int mw = s.p.is_ver ? sh.w : sh.h, mh = s.p.is_ver ? sh.h : sh.w;
-  const int mrl = s.mrl;
-  if (s.p.angle < 0) {
-    const int n = mh + mw + 2 + mrl;                 // t in [-mh, mw + 1 + mrl]
-    const int inv = s.p.inv_angle;
-    for (int i = gl; i < n; i += gsize) {
-      const int t = i - mh;
-      ml[i] = t >= 0 ? mainSrc[t] : sideSrc[vmin((-t * inv + 256) >> 9, mh)];
-    }
-  } else {
-    const int mainLen = 2 * mw + mrl;
-    const int sft = vmax(0, vlog2(mw) - vlog2(mh));
-    const int n = mainLen + 1 + (mrl << sft) + 2;
-    for (int i = gl; i < n; i += gsize) ml[i] = mainSrc[vmin(i, mainLen)];
+  const int n = mh + mw + 2 + s.mrl;
+  const int inv = s.p.inv_angle;
+  for (int i = gl; i < n; i += gsize) {
+    const int t = i - mh;
+    buf[i] = t >= 0 ? mainSrc[t] : sideSrc[vmin((-t * inv + 256) >> 9, mh)];
   }
 }
 
-__device__ void build_mip_reduced(int16_t* red, const Rom& rom, const WarpSmem& sm, const MipGeom& mg, const Shape& sh,
-                                  int bd, int mode, int gl, int gsize)
-{
-  const int n = mg.redW * mg.redH;
-  for (int i = gl; i < n; i += gsize)
-    red[i] = (int16_t)mip_reduced_sample(rom, mg, sm.mipBnd, sh.w, sh.h, bd, mode, i % mg.redW, i / mg.redW);
-}
-
-// ---- one lane, one unit: prediction in block orientation ---------------------------------------------------
-template <int S>
-__device__ __forceinline__ void predict_unit(const WarpSmem& sm, const int16_t* slotLine, const SlotInfo& s, const Shape& sh,
-                                             const MipGeom& mg, const uint32_t* filt, int bd, int x0, int y0, int (&b)[S][S])
-{
-  const int maxv = (1 << bd) - 1;
-  if (s.kind == 2) {
-    const bool ver = s.p.is_ver;
-    const int mw = ver ? sh.w : sh.h, mh = ver ? sh.h : sh.w;
-    const int off = s.p.angle < 0 ? mh : 0;
-    int q[S][S];
-    pred_angular_unit<S>(slotLine + off, sm.lines[s.set][ver ? 1 : 0], s.p, s.mrl, mw, mh,
-                         ver ? x0 : y0, ver ? y0 : x0, filt, maxv, q);
-#pragma unroll
-    for (int i = 0; i < S; i++)
-#pragma unroll
-      for (int j = 0; j < S; j++) b[i][j] = ver ? q[i][j] : q[j][i];
-  } else if (s.kind < 2) {
-    const int16_t* top = sm.lines[s.set][0];
-    const int16_t* left = sm.lines[s.set][1];
-    int dc = 0;
-    if (s.kind == 1) {                                // CL/IntraPrediction.cpp:248-285
-      int sum = 0;
-      const int denom = sh.w == sh.h ? 2 * sh.w : vmax(sh.w, sh.h);
-      if (sh.w >= sh.h) for (int i = 0; i < sh.w; i++) sum += top[s.mrl + 1 + i];
-      if (sh.w <= sh.h) for (int i = 0; i < sh.h; i++) sum += left[s.mrl + 1 + i];
-      dc = (sum + (denom >> 1)) >> vlog2(denom);
-    }
-    pred_planar_dc_unit<S>(top, left, s.kind, s.p.pdpc, dc, sh.lw, sh.lh, x0, y0, b);
-  } else {
-    const int16_t* top = sm.lines[0][0];
-    const int16_t* left = sm.lines[0][1];
-    const bool up = mg.upH > 1 || mg.upV > 1;
-#pragma unroll
-    for (int i = 0; i < S; i++)
-#pragma unroll
-      for (int j = 0; j < S; j++)
-        b[i][j] = up ? mip_upsampled_sample(mg, slotLine, top, left, sh.w, sh.h, x0 + j, y0 + i)
-                     : slotLine[(y0 + i) * mg.redW + x0 + j];
-  }
-}
-
-template <int S>
-__device__ __forceinline__ void residual_unit(const int16_t* org, int stride, const int (&b)[S][S], int (&d)[S][S], int& sad)
+// residual of one unit against the original block, SAD accumulated.  TRANSPOSED: the prediction q is in the
+// main/side frame of a horizontal mode, i.e. q[i][j] predicts block sample (y0 + j, x0 + i); SAD and the sum of
+// absolute Hadamard coefficients are invariant under transposition, so the residual stays in that frame.
+template <int S, bool TRANSPOSED>
+__device__ __forceinline__ void residual_unit(const int16_t* org, int stride, const int (&q)[S][S], int (&d)[S][S], int& sad)
 {
 #pragma unroll
-  for (int i = 0; i < S; i++) {
-    const int16_t* row = org + i * stride;
+  for (int r = 0; r < S; r++) {
+    const int16_t* row = org + r * stride;
 #pragma unroll
-    for (int j = 0; j < S; j += 4) {
-      const uint2 v = *reinterpret_cast<const uint2*>(row + j);       // CU positions are multiples of 4 samples
-      d[i][j + 0] = (int)(int16_t)(v.x & 0xffff) - b[i][j + 0];
-      d[i][j + 1] = (int)(int16_t)(v.x >> 16)    - b[i][j + 1];
-      d[i][j + 2] = (int)(int16_t)(v.y & 0xffff) - b[i][j + 2];
-      d[i][j + 3] = (int)(int16_t)(v.y >> 16)    - b[i][j + 3];
+    for (int c = 0; c < S; c += 4) {
+      const uint2 v = *reinterpret_cast<const uint2*>(row + c);       // CU positions are multiples of 4 samples
+      const int o0 = (int)(int16_t)(v.x & 0xffff), o1 = (int)(int16_t)(v.x >> 16);
+      const int o2 = (int)(int16_t)(v.y & 0xffff), o3 = (int)(int16_t)(v.y >> 16);
+      if (TRANSPOSED) {
+        d[c + 0][r] = o0 - q[c + 0][r]; d[c + 1][r] = o1 - q[c + 1][r];
+        d[c + 2][r] = o2 - q[c + 2][r]; d[c + 3][r] = o3 - q[c + 3][r];
+      } else {
+        d[r][c + 0] = o0 - q[r][c + 0]; d[r][c + 1] = o1 - q[r][c + 1];
+        d[r][c + 2] = o2 - q[r][c + 2]; d[r][c + 3] = o3 - q[r][c + 3];
+      }
     }
   }
 #pragma unroll
@@ -239,38 +287,142 @@ __device__ __forceinline__ void residual_unit(const int16_t* org, int stride, co
 }
 
 template <int S>
-__device__ __forceinline__ void store_pred(int16_t* out, int w, int x0, int y0, const int (&b)[S][S])
+__device__ __forceinline__ void store_pred(int16_t* out, int w, int x0, int y0, bool transposed, const int (&q)[S][S])
 {
 #pragma unroll
   for (int i = 0; i < S; i++)
 #pragma unroll
-    for (int j = 0; j < S; j++) out[(y0 + i) * w + x0 + j] = (int16_t)b[i][j];
+    for (int j = 0; j < S; j++) {
+      if (transposed) out[(y0 + j) * w + x0 + i] = (int16_t)q[i][j];
+      else            out[(y0 + i) * w + x0 + j] = (int16_t)q[i][j];
+    }
+}
+
+// SATD contribution of this lane's unit(s) once the residual d is in registers (rows already transformed
+// for S == 8 by the caller).  TILE: 0 4x4, 1 8x4, 2 4x8 (handled by the S == 4 path), 3 8x8, 4 16x8, 5 8x16.
+template <int TILE>
+__device__ __forceinline__ int satd_unit8(int (&d)[8][8], int partnerMask, bool owner)
+{
+  wht_rows<8>(d);
+  if (TILE == 3) return (wht_cols_abs_sum<8>(d) + 2) >> 2;                    // CL/RdCost.cpp:2306
+  // 16x8 / 8x16: the partner lane holds the other 8x8 half; the last butterfly stage across the halves is
+  // folded into the absolute sum: |a+b| + |a-b| = 2 max(|a|, |b|)
+  wht_cols<8>(d);
+  int t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int mine = vabs(d[i][j]);
+      const int other = __shfl_xor_sync(0xffffffffu, mine, partnerMask);
+      t += vmax(mine, other);
+    }
+  return owner ? satd_norm_rect(2 * t, true) : 0;                             // CL/RdCost.cpp:2452, :2589
 }
 
 // =====================================================================================================
-// kernels
+// prediction of one unit per kind.  q is produced in the frame named by `transposed`.
 // =====================================================================================================
-__global__ void rmd_plan_kernel(const vvcb_rmd_visit* visits, int n, int ctu, WorkItem* items, unsigned* itemCount)
+template <int S>
+__device__ __forceinline__ void predict_angular(const WarpSmem& sm, const int16_t* projected, const SlotInfo& s, const Shape& sh,
+                                                const uint32_t* filt, int bd, int x0, int y0, int (&q)[S][S])
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const vvcb_rmd_visit v = visits[i];
-  const Shape sh = make_shape(v.log2w, v.log2h);
-  const int nAct = num_active_slots(visit_mrl_allowed(v, ctu), visit_num_mip(v));
-  const int perItem = sh.lanes >= kItemTasks ? 1 : kItemTasks / sh.lanes;
-  const int nItems = (nAct + perItem - 1) / perItem;
-  const unsigned base = atomicAdd(itemCount, (unsigned)nItems);
-  for (int k = 0; k < nItems; k++) {
-    WorkItem w;
-    w.visit = (uint32_t)i;
-    w.slot_begin = (uint16_t)(k * perItem);
-    w.slot_count = (uint16_t)vmin(perItem, nAct - k * perItem);
-    items[base + k] = w;
+  const bool ver = s.p.is_ver;
+  const int mw = ver ? sh.w : sh.h, mh = ver ? sh.h : sh.w;
+  const int16_t* ml = s.p.angle < 0 ? projected + mh : sm.lines[s.set][ver ? 0 : 1];
+  pred_angular_unit<S>(ml, sm.lines[s.set][ver ? 1 : 0], s.p, s.mrl, mw, mh, ver ? x0 : y0, ver ? y0 : x0, filt, (1 << bd) - 1, q);
+}
+
+// MIP: first interpolation pass of one slot into shared memory (CL/MatrixIntraPrediction.cpp:469-567,
+// shorter side first).  w >= h: plane[y * redW + rx] (vertical pass at the reduced columns);
+// h > w: plane[ry * w + x] (horizontal pass at the reduced rows).
+// When that first pass is the identity (no up-sampling along the shorter side) the plane IS the reduced prediction.
+__device__ __forceinline__ int mip_plane_offset(const MipGeom& mg, const Shape& sh)
+{
+  const bool identity = sh.h > sh.w ? mg.upH == 1 : mg.upV == 1;
+  return identity ? 0 : mg.redW * mg.redH;
+}
+
+__device__ void build_mip_planes(int16_t* red, int16_t* plane, const Rom& rom, const WarpSmem& sm, const MipGeom& mg, const Shape& sh,
+                                 int bd, int mode, int gl, int gsize)
+{
+  const int nRed = mg.redW * mg.redH;
+  for (int i = gl; i < nRed; i += gsize)
+    red[i] = (int16_t)mip_reduced_sample(rom, mg, sm.mipBnd, sh.w, sh.h, bd, mode, i % mg.redW, i / mg.redW);
+  __syncwarp();
+  if (plane == red) return;
+  const int16_t* top = sm.lines[0][0];
+  const int16_t* left = sm.lines[0][1];
+  if (sh.h > sh.w) {
+    const int lH = vlog2(mg.upH);
+    const int n = mg.redH * sh.w;
+    for (int i = gl; i < n; i += gsize) {
+      const int ry = i / sh.w, x = i - ry * sh.w;
+      const int rx = x >> lH, k = (x & (mg.upH - 1)) + 1;
+      const int row = mg.upV * (ry + 1) - 1;
+      const int before = rx == 0 ? left[1 + row] : red[ry * mg.redW + rx - 1];
+      const int behind = red[ry * mg.redW + rx];
+      plane[i] = (int16_t)(mg.upH == 1 ? behind : ((mg.upH - k) * before + k * behind + (mg.upH >> 1)) >> lH);
+    }
+  } else {
+    const int lV = vlog2(mg.upV);
+    const int n = sh.h * mg.redW;
+    for (int i = gl; i < n; i += gsize) {
+      const int y = i / mg.redW, rx = i - y * mg.redW;
+      const int ry = y >> lV, k = (y & (mg.upV - 1)) + 1;
+      const int col = mg.upH * (rx + 1) - 1;
+      const int before = ry == 0 ? top[1 + col] : red[(ry - 1) * mg.redW + rx];
+      const int behind = red[ry * mg.redW + rx];
+      plane[i] = (int16_t)(mg.upV == 1 ? behind : ((mg.upV - k) * before + k * behind + (mg.upV >> 1)) >> lV);
+    }
   }
 }
 
+template <int S>
+__device__ __forceinline__ void predict_mip(const WarpSmem& sm, const int16_t* plane, const MipGeom& mg, const Shape& sh,
+                                            int x0, int y0, int (&q)[S][S])
+{
+  const int16_t* top = sm.lines[0][0];
+  const int16_t* left = sm.lines[0][1];
+  if (sh.h > sh.w) {
+    const int lV = vlog2(mg.upV);
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+      const int y = y0 + i;
+      const int ry = y >> lV, k = (y & (mg.upV - 1)) + 1;
+#pragma unroll
+      for (int j = 0; j < S; j++) {
+        const int x = x0 + j;
+        const int before = ry == 0 ? top[1 + x] : plane[(ry - 1) * sh.w + x];
+        const int behind = plane[ry * sh.w + x];
+        q[i][j] = mg.upV == 1 ? behind : ((mg.upV - k) * before + k * behind + (mg.upV >> 1)) >> lV;
+      }
+    }
+  } else {
+    const int lH = vlog2(mg.upH);
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+      const int y = y0 + i;
+#pragma unroll
+      for (int j = 0; j < S; j++) {
+        const int x = x0 + j;
+        const int rx = x >> lH, k = (x & (mg.upH - 1)) + 1;
+        const int before = rx == 0 ? left[1 + y] : plane[y * mg.redW + rx - 1];
+        const int behind = plane[y * mg.redW + rx];
+        q[i][j] = mg.upH == 1 ? behind : ((mg.upH - k) * before + k * behind + (mg.upH >> 1)) >> lH;
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// the evaluation kernel, one instantiation per (SATD tile class, prediction kind)
+// =====================================================================================================
+template <int TILE, int KIND>
 __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
 {
+  constexpr int S = TILE < 3 ? 4 : 8;
+  constexpr int BUCKET = TILE * kNumKinds + KIND;
   __shared__ WarpSmem smem[kWarpsPerCta];
   __shared__ uint32_t sFilt[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -278,120 +430,123 @@ __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
   if (threadIdx.x < 64) sFilt[threadIdx.x] = (&P.rom->filt[0][0])[threadIdx.x];
   __syncthreads();
   const Rom& rom = *P.rom;
-  const unsigned nItems = *P.itemCount;
+  const unsigned nItems = P.plan->count[BUCKET];
+  const WorkItem* items = P.items + P.plan->offset[BUCKET];
 
   for (;;) {
     unsigned it = 0;
-    if (lane == 0) it = atomicAdd(P.cursor, 1u);
+    if (lane == 0) it = atomicAdd(&P.plan->cursor[BUCKET], 1u);
     it = __shfl_sync(0xffffffffu, it, 0);
     if (it >= nItems) break;
-    const WorkItem item = P.items[it];
+    const WorkItem item = items[it];
     const vvcb_rmd_visit v = P.visits[item.visit];
     const Shape sh = make_shape(v.log2w, v.log2h);
     const MipGeom mg = make_mip_geom(sh.w, sh.h);
-    const bool mrlAllowed = visit_mrl_allowed(v, P.ctu);
     uint32_t* sadOut  = P.details[item.visit].sad;
     uint32_t* satdOut = P.details[item.visit].satd;
     const int16_t* org = P.orig + (size_t)v.y * P.stride + v.x;
 
     // ---- reference lines needed by this item's slots
-    const int firstSlot = active_slot_to_slot(item.slot_begin, mrlAllowed);
-    const int lastSlot  = active_slot_to_slot(item.slot_begin + item.slot_count - 1, mrlAllowed);
     __syncwarp();
     build_line_set(sm, 0, 0, v, sh, P.reco, P.stride, P.bd, lane);
-    if (firstSlot < VVCB_SLOT_MRL3 && lastSlot >= VVCB_SLOT_MRL1) build_line_set(sm, 2, 1, v, sh, P.reco, P.stride, P.bd, lane);
-    if (firstSlot < VVCB_SLOT_MIP && lastSlot >= VVCB_SLOT_MRL3)  build_line_set(sm, 3, 3, v, sh, P.reco, P.stride, P.bd, lane);
+    if (KIND != KIND_MIP) {
+      const int lastSlot = kind_slot(rom, v, KIND, item.slot_begin + item.slot_count - 1);
+      if (lastSlot >= VVCB_SLOT_MRL1) {        // reference lines 1 and 3 (the MRL slots sit at the end of the kind's list)
+        build_line_set(sm, 2, 1, v, sh, P.reco, P.stride, P.bd, lane);
+        build_line_set(sm, 3, 3, v, sh, P.reco, P.stride, P.bd, lane);
+      }
+    }
     __syncwarp();
-    if (firstSlot < VVCB_SLOT_MRL1) build_filtered_set(sm, sh, lane);
-    if (lastSlot >= VVCB_SLOT_MIP)  build_mip_boundary(sm, sh, mg, lane);
+    if (KIND != KIND_MIP) build_filtered_set(sm, sh, lane);
+    else                  build_mip_boundary(sm, sh, mg, lane);
     __syncwarp();
 
     const int lanes = sh.lanes;                       // lanes per slot
     const int gsize = lanes > 32 ? 32 : lanes;        // lanes of one slot inside this warp iteration
     const int gidx  = lane / gsize, gl = lane % gsize;
-    const int lineStride = kSlotLineWords / (32 / gsize);
-    int16_t* slotLine = sm.slotLines + gidx * lineStride;
+    int16_t* scratch = sm.slot + gidx * (kSlotLineWords / (32 / gsize));
     const int nTasks = item.slot_count * lanes;
     int accSad = 0, accSatd = 0;
 
     for (int base = 0; base < nTasks; base += 32) {
       const int task = base + lane;
       const bool act = task < nTasks;
-      const int a = item.slot_begin + (act ? task : nTasks - 1) / lanes;
-      const int u = (act ? task : nTasks - 1) % lanes;
-      const int slot = active_slot_to_slot(a, mrlAllowed);
+      const int tk = act ? task : nTasks - 1;
+      const int u = tk % lanes;
+      const int slot = kind_slot(rom, v, KIND, item.slot_begin + tk / lanes);
       const SlotInfo s = make_slot_info(rom, v, sh, slot);
 
+      // ---- per-slot scratch built by the slot's lanes
       __syncwarp();
-      if (s.kind == 2) build_slot_line(slotLine, sm, s, sh, gl, gsize);
-      else if (s.kind == 3) build_mip_reduced(slotLine, rom, sm, mg, sh, P.bd, s.mode, gl, gsize);
+      int dc = 0;
+      if (KIND == KIND_ANG) {
+        if (s.p.angle < 0) build_projected_line(scratch, sm, s, s.p.is_ver ? sh.w : sh.h, s.p.is_ver ? sh.h : sh.w, gl, gsize);
+      } else if (KIND == KIND_MIP) {
+        build_mip_planes(scratch, scratch + mip_plane_offset(mg, sh), rom, sm, mg, sh, P.bd, s.mode, gl, gsize);
+      } else {
+        // DC value (CL/IntraPrediction.cpp:248-285), summed by the slot's lanes
+        int part = 0;
+        if (s.kind == 1) {
+          const int16_t* top = sm.lines[s.set][0] + s.mrl + 1;
+          const int16_t* left = sm.lines[s.set][1] + s.mrl + 1;
+          if (sh.w >= sh.h) for (int i = gl; i < sh.w; i += gsize) part += top[i];
+          if (sh.w <= sh.h) for (int i = gl; i < sh.h; i += gsize) part += left[i];
+        }
+        for (int o = gsize >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        const int denom = sh.w == sh.h ? 2 * sh.w : vmax(sh.w, sh.h);
+        dc = (part + (denom >> 1)) >> vlog2(denom);
+      }
       __syncwarp();
 
       int sad = 0, satd = 0;
-      if (sh.S == 8) {
+      const bool transposed = KIND == KIND_ANG && !s.p.is_ver;
+      if constexpr (S == 8) {
         const int ux = u % sh.unitsX, uy = u / sh.unitsX;
         const int x0 = ux * 8, y0 = uy * 8;
-        int b[8][8], d[8][8];
-        predict_unit<8>(sm, slotLine, s, sh, mg, sFilt, P.bd, x0, y0, b);
-        if (P.predOut && act) store_pred<8>(P.predOut + (size_t)a * sh.w * sh.h, sh.w, x0, y0, b);
-        residual_unit<8>(org + y0 * P.stride + x0, P.stride, b, d, sad);
-        wht_rows<8>(d);
-        if (sh.tile == 3) {
-          satd = (wht_cols_abs_sum<8>(d) + 2) >> 2;                       // CL/RdCost.cpp:2306
-        } else {
-          // 16x8 / 8x16: the partner lane holds the other 8x8 half; the last butterfly stage across the
-          // halves is folded into the absolute sum: |a+b| + |a-b| = 2 max(|a|, |b|)
-          wht_cols<8>(d);
-          const int pm = sh.tile == 4 ? 1 : sh.unitsX;
-          int t = 0;
-#pragma unroll
-          for (int i = 0; i < 8; i++)
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const int mine = vabs(d[i][j]);
-              const int other = __shfl_xor_sync(0xffffffffu, mine, pm);
-              t += vmax(mine, other);
-            }
-          const bool owner = sh.tile == 4 ? (ux & 1) == 0 : (uy & 1) == 0;
-          satd = owner ? satd_norm_rect(2 * t, true) : 0;                 // CL/RdCost.cpp:2452, :2589
-        }
+        int q[8][8], d[8][8];
+        if (KIND == KIND_ANG)      predict_angular<8>(sm, scratch, s, sh, sFilt, P.bd, x0, y0, q);
+        else if (KIND == KIND_MIP) predict_mip<8>(sm, scratch + mip_plane_offset(mg, sh), mg, sh, x0, y0, q);
+        else pred_planar_dc_unit<8>(sm.lines[s.set][0], sm.lines[s.set][1], s.kind, s.p.pdpc, dc, sh.lw, sh.lh, x0, y0, q);
+        if (P.predOut && act) store_pred<8>(P.predOut + (size_t)slot * sh.w * sh.h, sh.w, x0, y0, transposed, q);
+        if (transposed) residual_unit<8, true>(org + y0 * P.stride + x0, P.stride, q, d, sad);
+        else            residual_unit<8, false>(org + y0 * P.stride + x0, P.stride, q, d, sad);
+        satd = satd_unit8<TILE>(d, TILE == 4 ? 1 : sh.unitsX, TILE == 4 ? (ux & 1) == 0 : (uy & 1) == 0);
       } else {
         // 4xN / Nx4 shapes: a lane owns one SATD tile = one (4x4) or two (8x4, 4x8) 4x4 units
-        const int tilesX = sh.tile == 1 ? sh.w / 8 : sh.w / 4;
+        const int tilesX = TILE == 1 ? sh.w / 8 : sh.w / 4;
         const int tx = u % tilesX, ty = u / tilesX;
-        const int tw = sh.tile == 1 ? 8 : 4, th = sh.tile == 2 ? 8 : 4;
-        const int nUnits = sh.tile == 0 ? 1 : 2;
         int c0[4][4];
         int t = 0;
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-          if (k < nUnits) {
-            const int x0 = tx * tw + (sh.tile == 1 ? 4 * k : 0);
-            const int y0 = ty * th + (sh.tile == 2 ? 4 * k : 0);
-            int b[4][4], d[4][4];
-            predict_unit<4>(sm, slotLine, s, sh, mg, sFilt, P.bd, x0, y0, b);
-            if (P.predOut && act) store_pred<4>(P.predOut + (size_t)a * sh.w * sh.h, sh.w, x0, y0, b);
-            residual_unit<4>(org + y0 * P.stride + x0, P.stride, b, d, sad);
-            wht_rows<4>(d);
-            if (sh.tile == 0) {
-              satd = (wht_cols_abs_sum<4>(d) + 1) >> 1;                     // CL/RdCost.cpp:2209
+        for (int k = 0; k < (TILE == 0 ? 1 : 2); k++) {
+          const int x0 = tx * (TILE == 1 ? 8 : 4) + (TILE == 1 ? 4 * k : 0);
+          const int y0 = ty * (TILE == 2 ? 8 : 4) + (TILE == 2 ? 4 * k : 0);
+          int q[4][4], d[4][4];
+          if (KIND == KIND_ANG)      predict_angular<4>(sm, scratch, s, sh, sFilt, P.bd, x0, y0, q);
+          else if (KIND == KIND_MIP) predict_mip<4>(sm, scratch + mip_plane_offset(mg, sh), mg, sh, x0, y0, q);
+          else pred_planar_dc_unit<4>(sm.lines[s.set][0], sm.lines[s.set][1], s.kind, s.p.pdpc, dc, sh.lw, sh.lh, x0, y0, q);
+          if (P.predOut && act) store_pred<4>(P.predOut + (size_t)slot * sh.w * sh.h, sh.w, x0, y0, transposed, q);
+          if (transposed) residual_unit<4, true>(org + y0 * P.stride + x0, P.stride, q, d, sad);
+          else            residual_unit<4, false>(org + y0 * P.stride + x0, P.stride, q, d, sad);
+          wht_rows<4>(d);
+          if (TILE == 0) {
+            satd = (wht_cols_abs_sum<4>(d) + 1) >> 1;                       // CL/RdCost.cpp:2209
+          } else {
+            wht_cols<4>(d);
+            if (k == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) c0[i][j] = vabs(d[i][j]);
             } else {
-              wht_cols<4>(d);
-              if (k == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; i++)
+              for (int i = 0; i < 4; i++)
 #pragma unroll
-                  for (int j = 0; j < 4; j++) c0[i][j] = vabs(d[i][j]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                  for (int j = 0; j < 4; j++) t += vmax(c0[i][j], vabs(d[i][j]));
-              }
+                for (int j = 0; j < 4; j++) t += vmax(c0[i][j], vabs(d[i][j]));
             }
           }
         }
-        if (sh.tile != 0) satd = satd_norm_rect(2 * t, false);             // CL/RdCost.cpp:2662, :2741
+        if (TILE != 0) satd = satd_norm_rect(2 * t, false);                 // CL/RdCost.cpp:2662, :2741
       }
       if (!act) { sad = 0; satd = 0; }
 
@@ -417,6 +572,20 @@ __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
   }
 }
 
+// calls F<TILE, KIND>(args) for bucket b
+#define VVCB_FOR_BUCKET(b, F, ...)                                                                          \
+  switch (b) {                                                                                               \
+    case 0:  F<0, 0>(__VA_ARGS__); break;  case 1:  F<0, 1>(__VA_ARGS__); break;  case 2:  F<0, 2>(__VA_ARGS__); break; \
+    case 3:  F<1, 0>(__VA_ARGS__); break;  case 4:  F<1, 1>(__VA_ARGS__); break;  case 5:  F<1, 2>(__VA_ARGS__); break; \
+    case 6:  F<2, 0>(__VA_ARGS__); break;  case 7:  F<2, 1>(__VA_ARGS__); break;  case 8:  F<2, 2>(__VA_ARGS__); break; \
+    case 9:  F<3, 0>(__VA_ARGS__); break;  case 10: F<3, 1>(__VA_ARGS__); break;  case 11: F<3, 2>(__VA_ARGS__); break; \
+    case 12: F<4, 0>(__VA_ARGS__); break;  case 13: F<4, 1>(__VA_ARGS__); break;  case 14: F<4, 2>(__VA_ARGS__); break; \
+    case 15: F<5, 0>(__VA_ARGS__); break;  case 16: F<5, 1>(__VA_ARGS__); break;  case 17: F<5, 2>(__VA_ARGS__); break; \
+  }
+
+// =====================================================================================================
+// candidate lists
+// =====================================================================================================
 // g_aucIntraModeNumFast_UseMPM_2D, CL/Rom.cpp:536
 __constant__ uint8_t cFastModes[6][6] = {
   { 3, 3, 3, 3, 2, 2 }, { 3, 3, 3, 3, 3, 2 }, { 3, 3, 3, 3, 3, 2 }, { 3, 3, 3, 3, 3, 2 }, { 2, 3, 3, 3, 3, 2 }, { 2, 2, 2, 2, 2, 3 } };

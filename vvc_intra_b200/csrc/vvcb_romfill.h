@@ -16,6 +16,16 @@ inline void fill_rom(Rom& r)
   for (int lw = 2; lw <= 6; lw++)
     for (int lh = 2; lh <= 6; lh++)
       for (int m = 0; m < VVCB_NUM_LUMA_MODE; m++) r.mode[lw - 2][lh - 2][m] = make_mode_param(1 << lw, 1 << lh, m, 0);
+  for (int lw = 2; lw <= 6; lw++)
+    for (int lh = 2; lh <= 6; lh++) {
+      int n = 0;
+      for (int key = 0; key < 6; key++)          // key = is_ver * 3 + PDPC class (0 none, 1 angular, 2 pure hor/ver)
+        for (int m = 2; m < VVCB_NUM_LUMA_MODE; m++) {
+          const ModeParam& p = r.mode[lw - 2][lh - 2][m];
+          const int cls = !p.pdpc ? 0 : (p.angle == 0 ? 2 : 1);
+          if (p.is_ver * 3 + cls == key) r.angOrder[lw - 2][lh - 2][n++] = (uint8_t)m;
+        }
+    }
   memcpy(r.mip4, kMipMatrix4x4, sizeof(r.mip4));
   memcpy(r.mip8, kMipMatrix8x8, sizeof(r.mip8));
   memcpy(r.mip16, kMipMatrix16x16, sizeof(r.mip16));
