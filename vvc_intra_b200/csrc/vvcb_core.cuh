@@ -25,7 +25,7 @@ namespace vvcb {
 // ---- geometry -------------------------------------------------------------------------------------
 constexpr int kLineMax   = 140;            // samples per reference line (2*64 + 1 + 3, padded)
 constexpr int kNumSets   = 4;              // 0: line 0 unfiltered, 1: line 0 filtered, 2: line 1, 3: line 3
-constexpr int kSlotLineWords = 1920;       // int16 per warp for per-slot scratch in flight (projected main lines, MIP planes)
+constexpr int kSlotLineWords = 1888;       // int16 per warp for per-slot scratch in flight (projected main lines, MIP planes)
 constexpr int kNumClasses = 6;             // SATD tile of the shape: 0 4x4, 1 8x4, 2 4x8, 3 8x8, 4 16x8, 5 8x16
 constexpr int kNumKinds   = 3;             // 0 angular, 1 planar/DC, 2 MIP
 constexpr int kNumBuckets = kNumClasses * kNumKinds;
@@ -34,7 +34,23 @@ constexpr int kItemTasks = 128;            // lane-tasks per work item (4 warp i
 VHD int vmin(int a, int b) { return a < b ? a : b; }
 VHD int vmax(int a, int b) { return a > b ? a : b; }
 VHD int vabs(int a) { return a < 0 ? -a : a; }
-VHD int vlog2(int v) { int r = 0; while (v > 1) { v >>= 1; r++; } return r; }
+VHD int vlog2(int v)
+{
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz(v);
+#else
+  return 31 - __builtin_clz((unsigned)v);
+#endif
+}
+// |a - b| + c (one VABSDIFF on the device)
+VHD int vsad(int a, int b, int c)
+{
+#if defined(__CUDA_ARCH__)
+  return (int)__sad(a, b, (unsigned)c);
+#else
+  return c + (a < b ? b - a : a - b);
+#endif
+}
 
 // Per (shape, mode) prediction parameters, precomputed on the host at context creation.
 struct ModeParam {
@@ -114,6 +130,8 @@ struct Shape {
   int unitsX, unitsY; // units per row / column of the CU
   int lanes;          // lanes per evaluation slot (power of two, 1..64)
   int tile;           // SATD tile: 0 4x4, 1 8x4, 2 4x8, 3 8x8, 4 16x8, 5 8x16
+  int lgLanes;        // log2(lanes)
+  int lgTilesX;       // log2 of the lane grid width: units per row (S == 8) or SATD tiles per row (S == 4)
 };
 
 VHD Shape make_shape(int lw, int lh)
@@ -131,6 +149,8 @@ VHD Shape make_shape(int lw, int lh)
   s.unitsX = w / s.S; s.unitsY = h / s.S;
   // 8x4 / 4x8 tiles: one lane owns both 4x4 units of a tile
   s.lanes = (s.tile == 1 || s.tile == 2) ? (w * h) / 32 : s.unitsX * s.unitsY;
+  s.lgLanes  = vlog2(s.lanes);
+  s.lgTilesX = s.S == 8 ? lw - 3 : (s.tile == 1 ? lw - 3 : lw - 2);
   return s;
 }
 
@@ -263,7 +283,7 @@ struct SlotInfo {
   ModeParam p;
 };
 
-VHD int clip_bd(int v, int maxv) { return v < 0 ? 0 : (v > maxv ? maxv : v); }
+VHD int clip_bd(int v, int maxv) { return vmin(vmax(v, 0), maxv); }
 
 // Angular prediction of the unit whose origin is (c0, r0) in the main/side frame.  ml points at the
 // slot's main line so that ml[t] == refMain0[t] (may be indexed with negative t); side points at
@@ -358,6 +378,8 @@ template <int S> VHD void pred_planar_dc_unit(const int16_t* top, const int16_t*
 // ---- MIP --------------------------------------------------------------------------------------------
 struct MipGeom {
   int numModes, small, bsz, redW, redH, upH, upV, grid, cols;
+  int lgRedW, lgUpH, lgUpV;
+  int family;            // 0: 4x4 matrices (4 inputs), 1: 8x8 matrices (8 inputs), 2: 16x16 matrices (7 inputs, first column dropped)
 };
 
 VHD MipGeom make_mip_geom(int w, int h)
@@ -371,84 +393,57 @@ VHD MipGeom make_mip_geom(int w, int h)
   g.upH   = w / g.redW; g.upV = h / g.redH;
   g.grid  = g.small ? 4 : 8;
   g.cols  = (w == 4 && h == 4) ? 4 : (g.small ? 8 : 7);
+  g.lgRedW = vlog2(g.redW); g.lgUpH = vlog2(g.upH); g.lgUpV = vlog2(g.upV);
+  g.family = (w == 4 && h == 4) ? 0 : (g.small ? 1 : 2);
   return g;
 }
 
-// One sample of the reduced prediction (logical position (rx, ry)), CL/MatrixIntraPrediction.cpp:637-741.
-// bnd: the visit's Haar-averaged boundary, bnd[0..bsz) = top, bnd[4..4+bsz) = left.
-VHD int mip_reduced_sample(const Rom& rom, const MipGeom& g, const int* bnd, int w, int h, int bd, int mode, int rx, int ry)
+// Everything one MIP mode needs besides the visit's boundary (CL/MatrixIntraPrediction.cpp:211-254, 570-591)
+struct MipSlot {
+  const uint8_t* mat;
+  int shift, off, inOff;
+  bool transpose;
+  int in[8];             // rebased reduced boundary (zero padded); in[0] == 0 for the 16x16 family
+};
+
+// mipIn[t][i]: rebased input vector of orientation t (0 normal, 1 transposed); mipAux: {inOff[0], inOff[1], sum[0], sum[1]}
+VHD MipSlot make_mip_slot(const Rom& rom, const MipGeom& g, const int16_t (*mipIn)[8], const int* mipAux, int mode)
 {
-  const bool transpose = mode > g.numModes / 2;
-  const int widx = transpose ? mode - g.numModes / 2 : mode;
-  const uint8_t* mat; int shift, offs;
-  if (w == 4 && h == 4) { mat = rom.mip4 + widx * 64;   shift = rom.mipSh4[widx];  offs = rom.mipOff4[widx]; }
-  else if (g.small)     { mat = rom.mip8 + widx * 128;  shift = rom.mipSh8[widx];  offs = rom.mipOff8[widx]; }
-  else                  { mat = rom.mip16 + widx * 448; shift = rom.mipSh16[widx]; offs = rom.mipOff16[widx]; }
-  const int inSize = 2 * g.bsz;
-  int in[8];
+  MipSlot m;
+  m.transpose = mode > g.numModes / 2;
+  const int widx = m.transpose ? mode - g.numModes / 2 : mode;
+  int offs;
+  if (g.family == 0)      { m.mat = rom.mip4 + widx * 64;   m.shift = rom.mipSh4[widx];  offs = rom.mipOff4[widx]; }
+  else if (g.family == 1) { m.mat = rom.mip8 + widx * 128;  m.shift = rom.mipSh8[widx];  offs = rom.mipOff8[widx]; }
+  else                    { m.mat = rom.mip16 + widx * 448; m.shift = rom.mipSh16[widx]; offs = rom.mipOff16[widx]; }
+  const int t = m.transpose ? 1 : 0;
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    if (i < g.bsz) {
-      in[i]         = transpose ? bnd[4 + i] : bnd[i];
-      in[g.bsz + i] = transpose ? bnd[i] : bnd[4 + i];
-    }
-  }
-  const int inOff = in[0];
-  int sum = 0;
-  in[0] = g.small ? inOff - (1 << (bd - 1)) : 0;
-  for (int i = 1; i < inSize; i++) in[i] -= inOff;
-  for (int i = 0; i < inSize; i++) sum += in[i];
-  const int off = (1 << (shift - 1)) - offs * sum;
-  bool lho = (w == 4 && h >= 16), lvo = (h == 4 && w >= 16);
-  int xx = rx, yy = ry, iw = g.redW;
-  if (transpose) { const bool t = lho; lho = lvo; lvo = t; xx = ry; yy = rx; iw = g.redH; }
-  const int row = (lvo ? 2 * yy : yy) * (g.small ? iw : g.grid) + (lho ? 2 * xx : xx);
-  const uint8_t* wgt = mat + row * g.cols;
-  int acc = 0;
-  if (g.small) { for (int i = 0; i < inSize; i++) acc += in[i] * wgt[i]; }
-  else         { for (int i = 1; i < inSize; i++) acc += in[i] * wgt[i - 1]; }
-  return clip_bd(((acc + off) >> shift) + inOff, (1 << bd) - 1);
+  for (int i = 0; i < 8; i++) m.in[i] = mipIn[t][i];
+  m.inOff = mipAux[t];
+  m.off = (1 << (m.shift - 1)) - offs * mipAux[2 + t];
+  return m;
 }
 
-// Sample (x, y) of the up-sampled MIP prediction from the reduced prediction red[ry*redW+rx]
-// (CL/MatrixIntraPrediction.cpp:399-567): linear interpolation, shorter side first.
-VHD int mip_upsampled_sample(const MipGeom& g, const int16_t* red, const int16_t* top, const int16_t* left, int w, int h, int x, int y)
+// One sample of the reduced prediction at logical position (rx, ry), CL/MatrixIntraPrediction.cpp:637-741.
+VHD int mip_reduced_sample(const MipSlot& m, const MipGeom& g, int w, int h, int maxv, int rx, int ry)
 {
-  const int lH = vlog2(g.upH), lV = vlog2(g.upV);
-  const int rx = x >> lH, ry = y >> lV;
-  const int kx = (x & (g.upH - 1)) + 1, ky = (y & (g.upV - 1)) + 1;    // 1..up
-  if (h > w) {
-    // horizontal pass lives on rows yr = upV*(ry'+1)-1; then vertical between the row above (or top[]) and the row below
-    const int rowB = g.upV * (ry + 1) - 1;
-    const int a1 = rx == 0 ? left[1 + rowB] : red[ry * g.redW + rx - 1];
-    const int b1 = red[ry * g.redW + rx];
-    const int below = g.upH == 1 ? b1 : ((g.upH - kx) * a1 + kx * b1 + (g.upH >> 1)) >> lH;
-    if (g.upV == 1) return below;
-    int above;
-    if (ry == 0) above = top[1 + x];
-    else {
-      const int rowA = g.upV * ry - 1;
-      const int a0 = rx == 0 ? left[1 + rowA] : red[(ry - 1) * g.redW + rx - 1];
-      const int b0 = red[(ry - 1) * g.redW + rx];
-      above = g.upH == 1 ? b0 : ((g.upH - kx) * a0 + kx * b0 + (g.upH >> 1)) >> lH;
-    }
-    return ((g.upV - ky) * above + ky * below + (g.upV >> 1)) >> lV;
+  bool lho = (w == 4 && h >= 16), lvo = (h == 4 && w >= 16);
+  int xx = rx, yy = ry, iw = g.redW;
+  if (m.transpose) { const bool t = lho; lho = lvo; lvo = t; xx = ry; yy = rx; iw = g.redH; }
+  const int row = (lvo ? 2 * yy : yy) * (g.small ? iw : g.grid) + (lho ? 2 * xx : xx);
+  const uint8_t* wgt = m.mat + row * g.cols;
+  int acc = m.off;
+  if (g.family == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc += m.in[i] * wgt[i];
+  } else if (g.family == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc += m.in[i] * wgt[i];
   } else {
-    const int colB = g.upH * (rx + 1) - 1;
-    const int a1 = ry == 0 ? top[1 + colB] : red[(ry - 1) * g.redW + rx];
-    const int b1 = red[ry * g.redW + rx];
-    const int right = g.upV == 1 ? b1 : ((g.upV - ky) * a1 + ky * b1 + (g.upV >> 1)) >> lV;
-    if (g.upH == 1) return right;
-    int lft;
-    if (rx == 0) lft = left[1 + y];
-    else {
-      const int colA = g.upH * rx - 1;
-      const int a0 = ry == 0 ? top[1 + colA] : red[(ry - 1) * g.redW + rx - 1];
-      const int b0 = red[ry * g.redW + rx - 1];
-      lft = g.upV == 1 ? b0 : ((g.upV - ky) * a0 + ky * b0 + (g.upV >> 1)) >> lV;
-    }
-    return ((g.upH - kx) * lft + kx * right + (g.upH >> 1)) >> lH;
+#pragma unroll
+    for (int i = 1; i < 8; i++) acc += m.in[i] * wgt[i - 1];
   }
+  return clip_bd((acc >> m.shift) + m.inOff, maxv);
 }
 
 // ---- candidate lists (lists kernel) -----------------------------------------------------------------

@@ -26,7 +26,9 @@ constexpr int KIND_ANG = 0, KIND_PDC = 1, KIND_MIP = 2;
 struct WarpSmem {
   int16_t lines[kNumSets][2][kLineMax];   // [set][0 top / 1 left][index], tails replicated for positive angles
   int16_t slot[kSlotLineWords];           // per-slot scratch of the slots in flight
-  int     mipBnd[8];                      // Haar-averaged boundary: [0..4) top, [4..8) left
+  int16_t mipBnd[8];                      // Haar-averaged boundary: [0..4) top, [4..8) left
+  int16_t mipIn[2][8];                    // rebased MIP input vectors: [0] normal, [1] transposed orientation
+  int     mipAux[4];                      // first boundary sample of each orientation, sum of each input vector
 };
 
 struct PlanState {                        // device-resident, zeroed before every call
@@ -105,17 +107,24 @@ __device__ __forceinline__ int items_of(int nSlots, int lanes, int& perItem)
   return (nSlots + perItem - 1) / perItem;
 }
 
+// Both planning passes aggregate per block in shared memory first: one global atomic per bucket per block.
 __global__ void rmd_plan_count(const vvcb_rmd_visit* visits, int n, int ctu, PlanState* plan)
 {
+  __shared__ unsigned hist[kNumBuckets];
+  if (threadIdx.x < kNumBuckets) hist[threadIdx.x] = 0;
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const vvcb_rmd_visit v = visits[i];
-  const Shape sh = make_shape(v.log2w, v.log2h);
-  for (int kind = 0; kind < kNumKinds; kind++) {
-    int perItem;
-    const int nItems = items_of(kind_slot_count(v, kind, ctu), sh.lanes, perItem);
-    if (nItems) atomicAdd(&plan->count[sh.tile * kNumKinds + kind], (unsigned)nItems);
+  if (i < n) {
+    const vvcb_rmd_visit v = visits[i];
+    const Shape sh = make_shape(v.log2w, v.log2h);
+    for (int kind = 0; kind < kNumKinds; kind++) {
+      int perItem;
+      const int nItems = items_of(kind_slot_count(v, kind, ctu), sh.lanes, perItem);
+      if (nItems) atomicAdd(&hist[sh.tile * kNumKinds + kind], (unsigned)nItems);
+    }
   }
+  __syncthreads();
+  if (threadIdx.x < kNumBuckets && hist[threadIdx.x]) atomicAdd(&plan->count[threadIdx.x], hist[threadIdx.x]);
 }
 
 __global__ void rmd_plan_scan(PlanState* plan)
@@ -128,25 +137,38 @@ __global__ void rmd_plan_scan(PlanState* plan)
 
 __global__ void rmd_plan_fill(const vvcb_rmd_visit* visits, int n, int ctu, PlanState* plan, WorkItem* items)
 {
+  __shared__ unsigned hist[kNumBuckets], base[kNumBuckets];
+  if (threadIdx.x < kNumBuckets) hist[threadIdx.x] = 0;
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const vvcb_rmd_visit v = visits[i];
-  const Shape sh = make_shape(v.log2w, v.log2h);
-  for (int kind = 0; kind < kNumKinds; kind++) {
-    int perItem;
-    const int nSlots = kind_slot_count(v, kind, ctu);
-    const int nItems = items_of(nSlots, sh.lanes, perItem);
-    if (!nItems) continue;
-    const int b = sh.tile * kNumKinds + kind;
-    const unsigned base = plan->offset[b] + atomicAdd(&plan->fill[b], (unsigned)nItems);
-    for (int k = 0; k < nItems; k++) {
-      WorkItem w;
-      w.visit = (uint32_t)i;
-      w.slot_begin = (uint16_t)(k * perItem);
-      w.slot_count = (uint16_t)vmin(perItem, nSlots - k * perItem);
-      items[base + k] = w;
+  vvcb_rmd_visit v;
+  Shape sh = make_shape(2, 2);
+  unsigned local[kNumKinds] = { 0, 0, 0 };
+  int nItems[kNumKinds] = { 0, 0, 0 }, perItem[kNumKinds] = { 1, 1, 1 }, nSlots[kNumKinds] = { 0, 0, 0 };
+  if (i < n) {
+    v = visits[i];
+    sh = make_shape(v.log2w, v.log2h);
+    for (int kind = 0; kind < kNumKinds; kind++) {
+      nSlots[kind] = kind_slot_count(v, kind, ctu);
+      nItems[kind] = items_of(nSlots[kind], sh.lanes, perItem[kind]);
+      if (nItems[kind]) local[kind] = atomicAdd(&hist[sh.tile * kNumKinds + kind], (unsigned)nItems[kind]);
     }
   }
+  __syncthreads();
+  if (threadIdx.x < kNumBuckets && hist[threadIdx.x])
+    base[threadIdx.x] = plan->offset[threadIdx.x] + atomicAdd(&plan->fill[threadIdx.x], hist[threadIdx.x]);
+  __syncthreads();
+  if (i < n)
+    for (int kind = 0; kind < kNumKinds; kind++) {
+      const unsigned at = base[sh.tile * kNumKinds + kind] + local[kind];
+      for (int k = 0; k < nItems[kind]; k++) {
+        WorkItem w;
+        w.visit = (uint32_t)i;
+        w.slot_begin = (uint16_t)(k * perItem[kind]);
+        w.slot_count = (uint16_t)vmin(perItem[kind], nSlots[kind] - k * perItem[kind]);
+        items[at + k] = w;
+      }
+    }
 }
 
 // =====================================================================================================
@@ -204,7 +226,9 @@ __device__ void build_filtered_set(WarpSmem& sm, const Shape& sh, int lane)
   }
 }
 
-__device__ void build_mip_boundary(WarpSmem& sm, const Shape& sh, const MipGeom& mg, int lane)
+// MIP inputs of one visit (CL/MatrixIntraPrediction.cpp:71-124): Haar-averaged boundary, then the two rebased
+// input vectors (normal and transposed orientation) with their sums.
+__device__ void build_mip_inputs(WarpSmem& sm, const Shape& sh, const MipGeom& mg, int bd, int lane)
 {
   if (lane < 8) {
     const int side = lane >> 2, i = lane & 3;          // 0 top, 1 left
@@ -214,8 +238,26 @@ __device__ void build_mip_boundary(WarpSmem& sm, const Shape& sh, const MipGeom&
       const int16_t* src = sm.lines[0][side] + 1 + i * f;
       int s = 0;
       for (int k = 0; k < f; k++) s += src[k];
-      sm.mipBnd[side * 4 + i] = f == 1 ? s : (s + (f >> 1)) >> vlog2(f);
+      sm.mipBnd[side * 4 + i] = (int16_t)(f == 1 ? s : (s + (f >> 1)) >> vlog2(f));
     }
+  }
+  __syncwarp();
+  if (lane < 16) {
+    const int t = lane >> 3, i = lane & 7;
+    const int first = sm.mipBnd[t ? 4 : 0];
+    int val = 0;
+    if (i < 2 * mg.bsz) {
+      const int raw = i < mg.bsz ? sm.mipBnd[(t ? 4 : 0) + i] : sm.mipBnd[(t ? 0 : 4) + i - mg.bsz];
+      val = i == 0 ? (mg.small ? first - (1 << (bd - 1)) : 0) : raw - first;
+    }
+    sm.mipIn[t][i] = (int16_t)val;
+    if (i == 0) sm.mipAux[t] = first;
+  }
+  __syncwarp();
+  if (lane < 2) {
+    int sum = 0;
+    for (int i = 0; i < 8; i++) sum += sm.mipIn[lane][i];
+    sm.mipAux[2 + lane] = sum;
   }
 }
 
@@ -274,16 +316,16 @@ __device__ __forceinline__ void residual_unit(const int16_t* org, int stride, co
       if (TRANSPOSED) {
         d[c + 0][r] = o0 - q[c + 0][r]; d[c + 1][r] = o1 - q[c + 1][r];
         d[c + 2][r] = o2 - q[c + 2][r]; d[c + 3][r] = o3 - q[c + 3][r];
+        sad = vsad(o0, q[c + 0][r], sad); sad = vsad(o1, q[c + 1][r], sad);
+        sad = vsad(o2, q[c + 2][r], sad); sad = vsad(o3, q[c + 3][r], sad);
       } else {
         d[r][c + 0] = o0 - q[r][c + 0]; d[r][c + 1] = o1 - q[r][c + 1];
         d[r][c + 2] = o2 - q[r][c + 2]; d[r][c + 3] = o3 - q[r][c + 3];
+        sad = vsad(o0, q[r][c + 0], sad); sad = vsad(o1, q[r][c + 1], sad);
+        sad = vsad(o2, q[r][c + 2], sad); sad = vsad(o3, q[r][c + 3], sad);
       }
     }
   }
-#pragma unroll
-  for (int i = 0; i < S; i++)
-#pragma unroll
-    for (int j = 0; j < S; j++) sad += vabs(d[i][j]);
 }
 
 template <int S>
@@ -346,34 +388,33 @@ __device__ __forceinline__ int mip_plane_offset(const MipGeom& mg, const Shape& 
 __device__ void build_mip_planes(int16_t* red, int16_t* plane, const Rom& rom, const WarpSmem& sm, const MipGeom& mg, const Shape& sh,
                                  int bd, int mode, int gl, int gsize)
 {
-  const int nRed = mg.redW * mg.redH;
+  const MipSlot ms = make_mip_slot(rom, mg, sm.mipIn, sm.mipAux, mode);
+  const int nRed = mg.redW * mg.redH, maxv = (1 << bd) - 1;
   for (int i = gl; i < nRed; i += gsize)
-    red[i] = (int16_t)mip_reduced_sample(rom, mg, sm.mipBnd, sh.w, sh.h, bd, mode, i % mg.redW, i / mg.redW);
+    red[i] = (int16_t)mip_reduced_sample(ms, mg, sh.w, sh.h, maxv, i & (mg.redW - 1), i >> mg.lgRedW);
   __syncwarp();
   if (plane == red) return;
   const int16_t* top = sm.lines[0][0];
   const int16_t* left = sm.lines[0][1];
   if (sh.h > sh.w) {
-    const int lH = vlog2(mg.upH);
-    const int n = mg.redH * sh.w;
+    const int n = mg.redH << sh.lw;
     for (int i = gl; i < n; i += gsize) {
-      const int ry = i / sh.w, x = i - ry * sh.w;
-      const int rx = x >> lH, k = (x & (mg.upH - 1)) + 1;
+      const int ry = i >> sh.lw, x = i & (sh.w - 1);
+      const int rx = x >> mg.lgUpH, k = (x & (mg.upH - 1)) + 1;
       const int row = mg.upV * (ry + 1) - 1;
-      const int before = rx == 0 ? left[1 + row] : red[ry * mg.redW + rx - 1];
-      const int behind = red[ry * mg.redW + rx];
-      plane[i] = (int16_t)(mg.upH == 1 ? behind : ((mg.upH - k) * before + k * behind + (mg.upH >> 1)) >> lH);
+      const int before = rx == 0 ? left[1 + row] : red[(ry << mg.lgRedW) + rx - 1];
+      const int behind = red[(ry << mg.lgRedW) + rx];
+      plane[i] = (int16_t)(((mg.upH - k) * before + k * behind + (mg.upH >> 1)) >> mg.lgUpH);
     }
   } else {
-    const int lV = vlog2(mg.upV);
-    const int n = sh.h * mg.redW;
+    const int n = sh.h << mg.lgRedW;
     for (int i = gl; i < n; i += gsize) {
-      const int y = i / mg.redW, rx = i - y * mg.redW;
-      const int ry = y >> lV, k = (y & (mg.upV - 1)) + 1;
+      const int y = i >> mg.lgRedW, rx = i & (mg.redW - 1);
+      const int ry = y >> mg.lgUpV, k = (y & (mg.upV - 1)) + 1;
       const int col = mg.upH * (rx + 1) - 1;
-      const int before = ry == 0 ? top[1 + col] : red[(ry - 1) * mg.redW + rx];
-      const int behind = red[ry * mg.redW + rx];
-      plane[i] = (int16_t)(mg.upV == 1 ? behind : ((mg.upV - k) * before + k * behind + (mg.upV >> 1)) >> lV);
+      const int before = ry == 0 ? top[1 + col] : red[((ry - 1) << mg.lgRedW) + rx];
+      const int behind = red[(ry << mg.lgRedW) + rx];
+      plane[i] = (int16_t)(((mg.upV - k) * before + k * behind + (mg.upV >> 1)) >> mg.lgUpV);
     }
   }
 }
@@ -385,31 +426,30 @@ __device__ __forceinline__ void predict_mip(const WarpSmem& sm, const int16_t* p
   const int16_t* top = sm.lines[0][0];
   const int16_t* left = sm.lines[0][1];
   if (sh.h > sh.w) {
-    const int lV = vlog2(mg.upV);
+    // second pass vertical; plane[ry * w + x] holds the rows that carry reduced samples
 #pragma unroll
     for (int i = 0; i < S; i++) {
       const int y = y0 + i;
-      const int ry = y >> lV, k = (y & (mg.upV - 1)) + 1;
+      const int ry = y >> mg.lgUpV, k = (y & (mg.upV - 1)) + 1;
+      const int16_t* rowB = plane + (ry << sh.lw) + x0;
 #pragma unroll
       for (int j = 0; j < S; j++) {
-        const int x = x0 + j;
-        const int before = ry == 0 ? top[1 + x] : plane[(ry - 1) * sh.w + x];
-        const int behind = plane[ry * sh.w + x];
-        q[i][j] = mg.upV == 1 ? behind : ((mg.upV - k) * before + k * behind + (mg.upV >> 1)) >> lV;
+        const int before = ry == 0 ? top[1 + x0 + j] : rowB[j - sh.w];
+        q[i][j] = ((mg.upV - k) * before + k * rowB[j] + (mg.upV >> 1)) >> mg.lgUpV;
       }
     }
   } else {
-    const int lH = vlog2(mg.upH);
+    // second pass horizontal; plane[y * redW + rx] holds the columns that carry reduced samples
 #pragma unroll
     for (int i = 0; i < S; i++) {
       const int y = y0 + i;
+      const int16_t* rowP = plane + (y << mg.lgRedW);
 #pragma unroll
       for (int j = 0; j < S; j++) {
         const int x = x0 + j;
-        const int rx = x >> lH, k = (x & (mg.upH - 1)) + 1;
-        const int before = rx == 0 ? left[1 + y] : plane[y * mg.redW + rx - 1];
-        const int behind = plane[y * mg.redW + rx];
-        q[i][j] = mg.upH == 1 ? behind : ((mg.upH - k) * before + k * behind + (mg.upH >> 1)) >> lH;
+        const int rx = x >> mg.lgUpH, k = (x & (mg.upH - 1)) + 1;
+        const int before = rx == 0 ? left[1 + y] : rowP[rx - 1];
+        q[i][j] = ((mg.upH - k) * before + k * rowP[rx] + (mg.upH >> 1)) >> mg.lgUpH;
       }
     }
   }
@@ -458,13 +498,14 @@ __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
     }
     __syncwarp();
     if (KIND != KIND_MIP) build_filtered_set(sm, sh, lane);
-    else                  build_mip_boundary(sm, sh, mg, lane);
+    else                  build_mip_inputs(sm, sh, mg, P.bd, lane);
     __syncwarp();
 
     const int lanes = sh.lanes;                       // lanes per slot
     const int gsize = lanes > 32 ? 32 : lanes;        // lanes of one slot inside this warp iteration
-    const int gidx  = lane / gsize, gl = lane % gsize;
-    int16_t* scratch = sm.slot + gidx * (kSlotLineWords / (32 / gsize));
+    const int lgG   = lanes > 32 ? 5 : sh.lgLanes;
+    const int gidx  = lane >> lgG, gl = lane & (gsize - 1);
+    int16_t* scratch = sm.slot + gidx * ((kSlotLineWords / 32) << lgG);
     const int nTasks = item.slot_count * lanes;
     int accSad = 0, accSatd = 0;
 
@@ -472,8 +513,8 @@ __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
       const int task = base + lane;
       const bool act = task < nTasks;
       const int tk = act ? task : nTasks - 1;
-      const int u = tk % lanes;
-      const int slot = kind_slot(rom, v, KIND, item.slot_begin + tk / lanes);
+      const int u = tk & (lanes - 1);
+      const int slot = kind_slot(rom, v, KIND, item.slot_begin + (tk >> sh.lgLanes));
       const SlotInfo s = make_slot_info(rom, v, sh, slot);
 
       // ---- per-slot scratch built by the slot's lanes
@@ -501,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
       int sad = 0, satd = 0;
       const bool transposed = KIND == KIND_ANG && !s.p.is_ver;
       if constexpr (S == 8) {
-        const int ux = u % sh.unitsX, uy = u / sh.unitsX;
+        const int ux = u & (sh.unitsX - 1), uy = u >> sh.lgTilesX;
         const int x0 = ux * 8, y0 = uy * 8;
         int q[8][8], d[8][8];
         if (KIND == KIND_ANG)      predict_angular<8>(sm, scratch, s, sh, sFilt, P.bd, x0, y0, q);
@@ -513,8 +554,7 @@ __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
         satd = satd_unit8<TILE>(d, TILE == 4 ? 1 : sh.unitsX, TILE == 4 ? (ux & 1) == 0 : (uy & 1) == 0);
       } else {
         // 4xN / Nx4 shapes: a lane owns one SATD tile = one (4x4) or two (8x4, 4x8) 4x4 units
-        const int tilesX = TILE == 1 ? sh.w / 8 : sh.w / 4;
-        const int tx = u % tilesX, ty = u / tilesX;
+        const int tx = u & ((1 << sh.lgTilesX) - 1), ty = u >> sh.lgTilesX;
         int c0[4][4];
         int t = 0;
 #pragma unroll
