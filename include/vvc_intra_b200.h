@@ -146,7 +146,7 @@ int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_r
 /* Same work with visits/results already resident on the device (device pointers from
  * vvcb_dev_alloc); used to time the kernels without the PCIe copies.                            */
 int vvcb_rmd_eval_device(vvcb_ctx* ctx, const void* d_visits, int n, void* d_results,
-                         void* d_details /* may be NULL: internal scratch is used */);
+                         void* d_details /* may be NULL: no detail tables are written */);
 
 /* Prediction samples of one evaluation slot (debug / parity): writes w*h samples.               */
 int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t* pred);

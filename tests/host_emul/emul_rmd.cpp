@@ -63,12 +63,14 @@ extern "C" int emul_rmd_eval(const int16_t* orig, const int16_t* reco, int strid
   emu_launch((n + 255) / 256, 256, [&] { rmd_plan_fill(visits, n, ctu, &plan, items.data()); });
   EvalParams P;
   P.visits = visits; P.items = items.data(); P.plan = &plan;
-  P.details = details;
+  std::vector<uint32_t> sm((size_t)2 * VVCB_NUM_SLOTS * n);
+  P.sadSM = sm.data(); P.satdSM = sm.data() + (size_t)VVCB_NUM_SLOTS * n; P.nVisits = n;
   P.orig = orig; P.reco = reco; P.stride = stride; P.bd = bd; P.ctu = ctu; P.rom = &rom; P.predOut = predOut;
   for (int b = 0; b < kNumBuckets; b++) {
     if (!plan.count[b]) continue;
     VVCB_FOR_BUCKET(b, emul_eval_bucket, P);
   }
-  emu_launch((n + 127) / 128, 128, [&] { rmd_lists_kernel(visits, n, ctu, results, details); });
+  if (details) emu_launch((n + 31) / 32, 256, [&] { rmd_detail_kernel(visits, n, ctu, details, P.sadSM, P.satdSM); });
+  emu_launch((n + kListThreads - 1) / kListThreads, kListThreads, [&] { rmd_lists_kernel(visits, n, ctu, results, details, P.sadSM, P.satdSM); });
   return 0;
 }

@@ -51,6 +51,7 @@ struct vvcb_ctx {
   // scratch for the host-pointer API
   vvcb_rmd_visit* dVisits; vvcb_rmd_result* dResults; size_t capVisits;
   vvcb_rmd_detail* dDetails; size_t capDetails;
+  uint32_t* dSlotMajor; size_t capSlotMajor;   // [2][VVCB_NUM_SLOTS][n] SAD / SATD scratch
   WorkItem* dItems; size_t capItems;
   PlanState* dPlan;
   int16_t* dPred; size_t capPred;
@@ -127,7 +128,7 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails);
+  cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dSlotMajor);
   cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->kev[i]);
@@ -237,10 +238,10 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   if (n == 0) return VVCB_OK;
   int rc = ensure_items(ctx, n);
   if (rc) return rc;
-  if (!dDetails) {
-    rc = ensure_details(ctx, n);
-    if (rc) return rc;
-    dDetails = ctx->dDetails;
+  if ((size_t)n > ctx->capSlotMajor) {
+    cudaFree(ctx->dSlotMajor); ctx->dSlotMajor = nullptr; ctx->capSlotMajor = 0;
+    CK(cudaMalloc(&ctx->dSlotMajor, (size_t)n * 2 * VVCB_NUM_SLOTS * sizeof(uint32_t)));
+    ctx->capSlotMajor = (size_t)n;
   }
   CK(cudaMemsetAsync(ctx->dPlan, 0, sizeof(PlanState), ctx->stream));
   const bool tm = ctx->timing != 0;
@@ -251,7 +252,7 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   if (tm) CK(cudaEventRecord(ctx->kev[1], ctx->stream));
   EvalParams P;
   P.visits = dVisits; P.items = ctx->dItems; P.plan = ctx->dPlan;
-  P.details = dDetails;
+  P.sadSM = ctx->dSlotMajor; P.satdSM = ctx->dSlotMajor + (size_t)VVCB_NUM_SLOTS * n; P.nVisits = n;
   P.orig = ctx->bOrig; P.reco = ctx->bReco; P.stride = ctx->stride; P.bd = ctx->bd; P.ctu = ctx->ctu; P.rom = ctx->dRom;
   P.predOut = dPred;
   const long long maxCtas = ((long long)n * 8 + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -260,7 +261,8 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   if (grid < 1) grid = 1;
   for (int b = 0; b < kNumBuckets; b++) { VVCB_FOR_BUCKET(b, launch_eval_bucket, P, grid, ctx->stream); }
   if (tm) CK(cudaEventRecord(ctx->kev[2], ctx->stream));
-  rmd_lists_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dResults, dDetails);
+  if (dDetails) { rmd_detail_kernel<<<(n + 31) / 32, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dDetails, P.sadSM, P.satdSM); ctx->launches++; }
+  rmd_lists_kernel<<<(n + kListThreads - 1) / kListThreads, kListThreads, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dResults, dDetails, P.sadSM, P.satdSM);
   ctx->launches += 3 + kNumBuckets + 1;
   CK(cudaGetLastError());
   if (tm) {
@@ -318,7 +320,11 @@ extern "C" int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n,
   rc = ensure_visit_buffers(ctx, n);
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->dVisits, visits, (size_t)n * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
-  rc = launch_rmd(ctx, ctx->dVisits, n, ctx->dResults, nullptr, nullptr);
+  if (details) {
+    rc = ensure_details(ctx, n);
+    if (rc) return rc;
+  }
+  rc = launch_rmd(ctx, ctx->dVisits, n, ctx->dResults, details ? ctx->dDetails : nullptr, nullptr);
   if (rc) return rc;
   CK(cudaMemcpyAsync(results, ctx->dResults, (size_t)n * sizeof(vvcb_rmd_result), cudaMemcpyDeviceToHost, ctx->stream));
   if (details) CK(cudaMemcpyAsync(details, ctx->dDetails, (size_t)n * sizeof(vvcb_rmd_detail), cudaMemcpyDeviceToHost, ctx->stream));

@@ -42,7 +42,9 @@ struct EvalParams {
   const vvcb_rmd_visit* visits;
   const WorkItem*       items;
   PlanState*            plan;
-  vvcb_rmd_detail*      details;  // sad/satd tables, one per visit
+  uint32_t*             sadSM;    // slot-major scratch: sadSM[slot * nVisits + visit] (coalesced for the list kernel)
+  uint32_t*             satdSM;
+  int                   nVisits;
   const int16_t*        orig;
   const int16_t*        reco;
   int                   stride;   // both planes
@@ -482,8 +484,8 @@ __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
     const vvcb_rmd_visit v = P.visits[item.visit];
     const Shape sh = make_shape(v.log2w, v.log2h);
     const MipGeom mg = make_mip_geom(sh.w, sh.h);
-    uint32_t* sadOut  = P.details[item.visit].sad;
-    uint32_t* satdOut = P.details[item.visit].satd;
+    uint32_t* sadOut  = P.sadSM + item.visit;
+    uint32_t* satdOut = P.satdSM + item.visit;
     const int16_t* org = P.orig + (size_t)v.y * P.stride + v.x;
 
     // ---- reference lines needed by this item's slots
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
           sad  += __shfl_xor_sync(0xffffffffu, sad, o);
           satd += __shfl_xor_sync(0xffffffffu, satd, o);
         }
-        if (act && gl == 0) { sadOut[slot] = (uint32_t)sad; satdOut[slot] = (uint32_t)satd; }
+        if (act && gl == 0) { sadOut[(size_t)slot * P.nVisits] = (uint32_t)sad; satdOut[(size_t)slot * P.nVisits] = (uint32_t)satd; }
       } else {
         // 64 lanes per slot: two consecutive warp iterations belong to the same slot
         accSad += sad; accSatd += satd;
@@ -604,7 +606,7 @@ __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
             accSad  += __shfl_xor_sync(0xffffffffu, accSad, o);
             accSatd += __shfl_xor_sync(0xffffffffu, accSatd, o);
           }
-          if (lane == 0) { sadOut[slot] = (uint32_t)accSad; satdOut[slot] = (uint32_t)accSatd; }
+          if (lane == 0) { sadOut[(size_t)slot * P.nVisits] = (uint32_t)accSad; satdOut[(size_t)slot * P.nVisits] = (uint32_t)accSatd; }
           accSad = 0; accSatd = 0;
         }
       }
@@ -639,33 +641,61 @@ __device__ void store_list(const CandList& L, int32_t* n, vvcb_mode* m, double* 
   }
 }
 
-// One thread per visit: EL/IntraSearch.cpp:489-802 minus the predictions (already reduced to SAD/SATD).
-__global__ void rmd_lists_kernel(const vvcb_rmd_visit* visits, int n, int ctu, vvcb_rmd_result* results, vvcb_rmd_detail* details)
+constexpr int kListThreads = 128;
+
+// Slot-major scratch -> per-visit detail tables (only when the caller asked for details): a shared-memory tile
+// transpose so that both the reads (fixed slot, consecutive visits) and the writes (one visit's row) are coalesced.
+__global__ void __launch_bounds__(256) rmd_detail_kernel(const vvcb_rmd_visit* visits, int n, int ctu, vvcb_rmd_detail* details,
+                                                         const uint32_t* sadSM, const uint32_t* satdSM)
+{
+  __shared__ uint32_t tile[32][2 * VVCB_NUM_SLOTS + 1];
+  const int first = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int vi = first + lane;
+  if (vi < n) {
+    const vvcb_rmd_visit v = visits[vi];
+    const bool mrlAllowed = visit_mrl_allowed(v, ctu);
+    const int numMip = visit_num_mip(v);
+    for (int s = wrp; s < VVCB_NUM_SLOTS; s += 8) {
+      const bool evaluated = s < VVCB_SLOT_MRL1 || (s < VVCB_SLOT_MIP ? mrlAllowed : s - VVCB_SLOT_MIP < numMip);
+      tile[lane][s] = evaluated ? sadSM[(size_t)s * n + vi] : VVCB_SAT_NONE;
+      tile[lane][VVCB_NUM_SLOTS + s] = evaluated ? satdSM[(size_t)s * n + vi] : VVCB_SAT_NONE;
+    }
+  }
+  __syncthreads();
+  for (int r = wrp; r < 32 && first + r < n; r += 8) {
+    uint32_t* dst = details[first + r].sad;          // sad[112] and satd[112] are contiguous
+    for (int k = lane; k < 2 * VVCB_NUM_SLOTS; k += 32) dst[k] = tile[r][k];
+  }
+}
+
+// One thread per visit: EL/IntraSearch.cpp:489-802 minus the predictions (already reduced to SAD/SATD, read from
+// the slot-major scratch: coalesced across the visits of a warp whenever they look at the same slot).
+__global__ void __launch_bounds__(kListThreads) rmd_lists_kernel(const vvcb_rmd_visit* visits, int n, int ctu, vvcb_rmd_result* results,
+                                                                 vvcb_rmd_detail* details, const uint32_t* sadSM, const uint32_t* satdSM)
 {
   const int vi = blockIdx.x * blockDim.x + threadIdx.x;
   if (vi >= n) return;
   const vvcb_rmd_visit v = visits[vi];
   vvcb_rmd_result& R = results[vi];
-  vvcb_rmd_detail& D = details[vi];
-  R.pad = 0;
   const int w = 1 << v.log2w, h = 1 << v.log2h;
   const bool mipEnabled = !(v.flags & VVCB_VISIT_NO_MIP);
   const int numMip = visit_num_mip(v);
   const bool testMip = numMip > 0;
   const bool mrlAllowed = visit_mrl_allowed(v, ctu);
+  const uint32_t* mySad = sadSM + vi;
+  const uint32_t* mySatd = satdSM + vi;
+  R.pad = 0;
+  vvcb_rmd_detail* D = details ? details + vi : nullptr;
 
   auto dist_of = [&](int slot) -> double {
-    const uint64_t sad = D.sad[slot], satd = D.satd[slot];
+    const uint64_t sad = mySad[(size_t)slot * n], satd = mySatd[(size_t)slot * n];
     return (double)(sad * 2 < satd ? sad * 2 : satd);                        // :515
   };
   auto cost_of = [&](int slot, bool isMip, int mrl, int mode) -> double {
     const uint64_t bits = mode_bits(v.rates, v.mpm, w, h, mrlAllowed, mipEnabled, isMip, mrl, mode);
     return __dadd_rn(dist_of(slot), __dmul_rn((double)bits, v.sqrt_lambda)); // :526, no FMA contraction
   };
-
-  // slots that were not evaluated
-  if (!mrlAllowed) for (int s = VVCB_SLOT_MRL1; s < VVCB_SLOT_MIP; s++) { D.sad[s] = VVCB_SAT_NONE; D.satd[s] = VVCB_SAT_NONE; }
-  for (int s = VVCB_SLOT_MIP + numMip; s < VVCB_NUM_SLOTS; s++) { D.sad[s] = VVCB_SAT_NONE; D.satd[s] = VVCB_SAT_NONE; }
 
   int K = cFastModes[v.log2w - 2][v.log2h - 2];
   if (testMip) K += vmax(K, vlog2(vmin(w, h)) - 1);                          // :472
@@ -701,8 +731,10 @@ __global__ void rmd_lists_kernel(const vvcb_rmd_visit* visits, int n, int ctu, v
         cand_push(rd, mk_mode(0, mrl, v.mpm[i]), cost_of(slot, false, mrl, v.mpm[i]), K);
         cand_push(had, mk_mode(0, mrl, v.mpm[i]), dist_of(slot), numHad);
       }
-  store_list(rd, &D.n_reg, D.reg_mode, D.reg_cost, VVCB_MAX_LIST);
-  store_list(had, &D.n_reg_had, D.reg_had_mode, D.reg_had_cost, VVCB_MAX_HAD_LIST);
+  if (D) {
+    store_list(rd, &D->n_reg, D->reg_mode, D->reg_cost, VVCB_MAX_LIST);
+    store_list(had, &D->n_reg_had, D->reg_had_mode, D->reg_had_cost, VVCB_MAX_HAD_LIST);
+  }
 
   if (testMip) {                                                             // :704-751
     double c3[6];                                                            // costs of MIP modes 3,4,5 and their transposes
