@@ -151,6 +151,36 @@ int vvcb_rmd_eval_device(vvcb_ctx* ctx, const void* d_visits, int n, void* d_res
 /* Prediction samples of one evaluation slot (debug / parity): writes w*h samples.               */
 int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t* pred);
 
+/* ---- TU coding: forward transform, MTS pre-selection sums, scalar quantisation, inverse, reconstruction, SSE ----
+ * One job = one candidate transform of one luma TU, i.e. one pass of IntraSearch::xIntraCodingTUBlock
+ * (EL/IntraSearch.cpp:2694) after the prediction: TrQuant::transformNxN(trModes) (CL/TrQuant.cpp:1049) when
+ * VVCB_TU_QUANT is clear, transformNxN(quant) (:1127) + invTransformNxN (:561) + PelBuf::reconstruct + RdCost::xGetSSE
+ * (CL/RdCost.cpp:1739) when it is set.  Quantisation is the scalar Quant::quant (CL/Quant.cpp:994, intra rounding);
+ * dependent quantisation / RDOQ are not built yet.                                            */
+#define VVCB_TU_QUANT   1u
+typedef struct vvcb_tu_job {
+  int16_t  x, y;            /* luma position of the TU (the original block is read from the frame for the SSE)      */
+  uint8_t  log2w, log2h;    /* 2..6; 64-point sides keep their 32 low frequencies (CL/TrQuant.cpp:853)             */
+  uint8_t  mts_idx;         /* TransformUnit::mtsIdx: 0 DCT2xDCT2, 1 transform skip, 2..5 DST7/DCT8 pairs (:822-829) */
+  uint8_t  flags;           /* VVCB_TU_*                                                                            */
+  int16_t  qp_per, qp_rem;  /* QpParam::per / rem of this candidate (CL/Quant.h:71)                                 */
+  uint32_t offset;          /* first sample of this job's dense w*h block in resi/pred/coeff/level/reco            */
+} vvcb_tu_job;
+
+typedef struct vvcb_tu_result {
+  int32_t  abs_sum_coeff;   /* int(sum |coeff| * scaleSAD), the MTS pre-selection cost (CL/TrQuant.cpp:1090-1103)   */
+  int32_t  abs_sum_level;   /* uiAbsSum of Quant::quant (0 when VVCB_TU_QUANT is clear)                             */
+  uint64_t sse;             /* sum (org - reco)^2 (0 when VVCB_TU_QUANT is clear)                                    */
+} vvcb_tu_result;
+
+/* resi / pred: HOST int16 arrays of n_samples (residual = org - pred as the reference's cs.getResiBuf holds it);
+ * coeff / level (int32) and reco (int16): optional HOST outputs of n_samples; results: n entries.                  */
+int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred, size_t n_samples,
+                 int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results);
+/* TrQuant::transformNxN(trModes) candidate selection (CL/TrQuant.cpp:1112-1123) from the pre-selection sums of one
+ * TU's candidates in list order (DCT2 first, transform skip second if tested): pure host logic.                    */
+void vvcb_mts_preselect(const int32_t* sums, int n, int width, int height, int max_cand, uint8_t* selected);
+
 /* ---- raw device memory for resident benchmarking --------------------------------------------- */
 int vvcb_dev_alloc(vvcb_ctx* ctx, size_t bytes, void** out);
 int vvcb_dev_free (vvcb_ctx* ctx, void* p);

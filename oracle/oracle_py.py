@@ -191,3 +191,69 @@ def rmd_batch(orig, reco, bd, ctu_size, visits, want_pred=False):
                             C.c_void_p(det[i:i + 1].ctypes.data), p.ctypes.data_as(_p16))
         preds.append(p)
     return out, det, preds
+
+
+# ---- TU coding (oracle/vvc_oracle_tr.c) -------------------------------------------------------------------
+_p32 = C.POINTER(C.c_int32)
+
+
+def fwd_transform(resi, bd, mts_idx):
+    resi, pr = _a16(resi)
+    h, w = resi.shape
+    coeff = np.zeros((h, w), np.int32)
+    if mts_idx == 1:
+        lib().orc_transform_skip(pr, w, w, h, bd, coeff.ctypes.data_as(_p32))
+    else:
+        lib().orc_fwd_transform(pr, w, w, h, bd, mts_idx, coeff.ctypes.data_as(_p32))
+    return coeff
+
+
+def abs_sum_for_preselection(coeff, mts_idx):
+    coeff = np.ascontiguousarray(coeff, np.int32)
+    h, w = coeff.shape
+    return lib().orc_abs_sum_for_preselection(coeff.ctypes.data_as(_p32), w, h, mts_idx)
+
+
+def mts_preselect(sums, w, h, max_cand):
+    a = (C.c_int * len(sums))(*[int(x) for x in sums])
+    sel = (C.c_uint8 * len(sums))()
+    lib().orc_mts_preselect(a, len(sums), w, h, max_cand, sel)
+    return list(sel)
+
+
+def quant_scalar(coeff, bd, per, rem, is_ts):
+    coeff = np.ascontiguousarray(coeff, np.int32)
+    h, w = coeff.shape
+    level = np.zeros((h, w), np.int32)
+    s = lib().orc_quant_scalar(coeff.ctypes.data_as(_p32), w, h, bd, per, rem, int(is_ts), level.ctypes.data_as(_p32))
+    return level, s
+
+
+def dequant(level, bd, per, rem, is_ts):
+    level = np.ascontiguousarray(level, np.int32)
+    h, w = level.shape
+    coeff = np.zeros((h, w), np.int32)
+    lib().orc_dequant(level.ctypes.data_as(_p32), w, h, bd, per, rem, int(is_ts), coeff.ctypes.data_as(_p32))
+    return coeff
+
+
+def inv_transform(coeff, bd, mts_idx):
+    coeff = np.ascontiguousarray(coeff, np.int32)
+    h, w = coeff.shape
+    resi = np.zeros((h, w), np.int16)
+    if mts_idx == 1:
+        lib().orc_inv_transform_skip(coeff.ctypes.data_as(_p32), w, h, bd, resi.ctypes.data_as(_p16), w)
+    else:
+        lib().orc_inv_transform(coeff.ctypes.data_as(_p32), w, h, bd, mts_idx, resi.ctypes.data_as(_p16), w)
+    return resi
+
+
+def reconstruct_sse(org, pred, resi, bd):
+    org, po = _a16(org)
+    pred, pp = _a16(pred)
+    resi, pr = _a16(resi)
+    h, w = org.shape
+    reco = np.zeros((h, w), np.int16)
+    lib().orc_reconstruct_sse.restype = C.c_uint64
+    sse = lib().orc_reconstruct_sse(po, w, pp, pr, w, h, bd, reco.ctypes.data_as(_p16))
+    return reco, sse

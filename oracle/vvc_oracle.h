@@ -52,6 +52,18 @@ void orc_rmd_batch(const int16_t* orig, int orig_stride, const int16_t* reco, in
                    int bd, int ctu_size, const vvcb_rmd_visit* v, int n, vvcb_rmd_result* out, vvcb_rmd_detail* det);
 uint64_t orc_fnv1a(const int16_t* p, int n);
 
+/* ---- TU coding (vvc_oracle_tr.c) ---- */
+void orc_tr_types(int mts_idx, int* hor, int* ver);
+void orc_fwd_transform(const int16_t* resi, int stride, int w, int h, int bd, int mts_idx, int32_t* coeff);
+void orc_transform_skip(const int16_t* resi, int stride, int w, int h, int bd, int32_t* coeff);
+int  orc_abs_sum_for_preselection(const int32_t* coeff, int w, int h, int mts_idx);
+void orc_mts_preselect(const int* sums, int n, int w, int h, int max_cand, uint8_t* selected);
+int  orc_quant_scalar(const int32_t* coeff, int w, int h, int bd, int per, int rem, int is_ts, int32_t* level);
+void orc_dequant(const int32_t* level, int w, int h, int bd, int per, int rem, int is_ts, int32_t* coeff);
+void orc_inv_transform(const int32_t* coeff, int w, int h, int bd, int mts_idx, int16_t* resi, int stride);
+void orc_inv_transform_skip(const int32_t* coeff, int w, int h, int bd, int16_t* resi, int stride);
+uint64_t orc_reconstruct_sse(const int16_t* org, int org_stride, const int16_t* pred, const int16_t* resi, int w, int h, int bd, int16_t* reco);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,3 +137,138 @@ def random_case(rng, bd, n_per_shape, plane=(512, 1024)):
                 v['sqrt_lambda'] = float(rng.uniform(1e-4, 3e-3))
                 vis.append(v)
     return orig, reco, np.array(vis, O.VISIT_DTYPE)
+
+
+# ---- TU coding: batches built from the reference's 'S' / 'Q' / 'I' records ---------------------------------
+def _tu_types():
+    import vvc_intra_b200 as vb          # struct layouts only (no library call)
+    return vb.TU_JOB_DTYPE, vb.TU_QUANT
+
+
+def build_tu_batch(tus, bd, seed=0, max_jobs=None):
+    """One job per (S record, candidate) [transform + pre-selection sum] and per Q record of a run without dependent
+    quantisation [transform + Quant::quant + dequant + inverse + reconstruction + SSE].  The recorded residuals are
+    split into a synthetic prediction and original (orig = pred + resi) laid out on an atlas of 64x64 cells.
+    Returns (orig_plane, jobs, resi_flat, pred_flat, expect) where expect[i] holds what the reference produced."""
+    job_dt, TU_QUANT = _tu_types()
+    rng = np.random.default_rng(seed)
+    items = []
+    for r in tus:
+        if r['bd'] != bd:
+            continue
+        if r['tag'] == 'S':
+            for m in r['modes']:
+                items.append(dict(kind='S', rec=r, mts=m['mts'], coeff=m['coeff'], resi=r['resi']))
+        elif r['tag'] == 'Q' and r['dep_quant'] == 0 and r['lfnst'] == 0:
+            items.append(dict(kind='Q', rec=r, mts=r['mts'], coeff=r['coeff'], resi=r['resi'], level=r['level']))
+    if max_jobs:
+        items = items[:max_jobs]
+    n = len(items)
+    cols = 16
+    orig = np.zeros((64 * ((n + cols - 1) // cols + 1), 64 * cols), np.int16)
+    jobs = np.zeros(n, job_dt)
+    resi_flat, pred_flat, off = [], [], 0
+    mx = (1 << bd) - 1
+    for i, it in enumerate(items):
+        resi = it['resi']
+        h, w = resi.shape
+        # prediction chosen so that orig = pred + resi is a legal picture wherever possible (clipped otherwise: the
+        # residual handed to the kernel stays the recorded one, as in the reference where resi = org - pred)
+        pred = np.clip(rng.integers(0, mx + 1, (h, w)), np.maximum(0, -resi), np.minimum(mx, mx - resi)).astype(np.int16)
+        org = np.clip(pred.astype(np.int32) + resi, 0, mx).astype(np.int16)
+        cx, cy = 64 * (i % cols), 64 * (i // cols)
+        orig[cy:cy + h, cx:cx + w] = org
+        j = jobs[i]
+        j['x'], j['y'], j['log2w'], j['log2h'] = cx, cy, w.bit_length() - 1, h.bit_length() - 1
+        j['mts_idx'] = it['mts']
+        j['offset'] = off
+        if it['kind'] == 'Q':
+            j['flags'] = TU_QUANT
+            j['qp_per'], j['qp_rem'] = it['rec']['per'], it['rec']['rem']
+        it['pred'], it['org'], it['off'] = pred, org, off
+        resi_flat.append(resi.ravel())
+        pred_flat.append(pred.ravel())
+        off += w * h
+    return orig, jobs, np.concatenate(resi_flat), np.concatenate(pred_flat), items
+
+
+def check_tu_outputs(items, bd, out):
+    """out: dict(results, coeff, level, reco) from the kernel.  Compares with the reference records; the dequant + inverse +
+    reconstruction + SSE part with the oracle chain (pinned by the 'I' records in tests/test_oracle_tu.py)."""
+    errs = []
+    for i, it in enumerate(items):
+        h, w = it['resi'].shape
+        sl = slice(it['off'], it['off'] + w * h)
+        r = out['results'][i]
+        if not np.array_equal(out['coeff'][sl].reshape(h, w), it['coeff']):
+            errs.append('job %d %dx%d mts %d: coefficients differ' % (i, w, h, it['mts']))
+        exp_sum = O.abs_sum_for_preselection(it['coeff'], it['mts'])
+        if int(r['abs_sum_coeff']) != exp_sum:
+            errs.append('job %d: pre-selection sum %d != %d' % (i, r['abs_sum_coeff'], exp_sum))
+        if it['kind'] == 'Q':
+            rec = it['rec']
+            if not np.array_equal(out['level'][sl].reshape(h, w), it['level']):
+                errs.append('job %d %dx%d mts %d: levels differ' % (i, w, h, it['mts']))
+            if int(r['abs_sum_level']) != rec['abs_sum']:
+                errs.append('job %d: abs sum %d != %d' % (i, r['abs_sum_level'], rec['abs_sum']))
+            co = O.dequant(it['level'], bd, rec['per'], rec['rem'], it['mts'] == 1)
+            res = O.inv_transform(co, bd, it['mts'])
+            reco, sse = O.reconstruct_sse(it['org'], it['pred'], res, bd)
+            if not np.array_equal(out['reco'][sl].reshape(h, w), reco):
+                errs.append('job %d %dx%d mts %d: reconstruction differs' % (i, w, h, it['mts']))
+            if int(r['sse']) != int(sse):
+                errs.append('job %d: sse %d != %d' % (i, r['sse'], sse))
+    return errs
+
+
+def random_tu_case(rng, bd, n_per_kind, amp=None):
+    """Random residuals for every (shape, transform) the path allows (incl. 64-point sides), random QP."""
+    job_dt, TU_QUANT = _tu_types()
+    mx = (1 << bd) - 1
+    items = []
+    for lw in range(2, 7):
+        for lh in range(2, 7):
+            for mts in range(6):
+                if mts >= 1 and (lw > 5 or lh > 5):
+                    continue
+                for _ in range(n_per_kind):
+                    w, h = 1 << lw, 1 << lh
+                    a = amp if amp is not None else int(rng.choice([3, 30, 300, mx]))
+                    a = min(a, mx)
+                    pred = rng.integers(0, mx + 1, (h, w))
+                    org = np.clip(pred + rng.integers(-a, a + 1, (h, w)), 0, mx)
+                    qp = int(rng.integers(0, 64)) + 6 * (bd - 8)
+                    items.append(dict(pred=pred.astype(np.int16), org=org.astype(np.int16), resi=(org - pred).astype(np.int16), mts=mts,
+                                      per=qp // 6, rem=qp % 6))
+    n = len(items)
+    cols = 16
+    orig = np.zeros((64 * ((n + cols - 1) // cols + 1), 64 * cols), np.int16)
+    jobs = np.zeros(n, job_dt)
+    off = 0
+    for i, it in enumerate(items):
+        h, w = it['resi'].shape
+        cx, cy = 64 * (i % cols), 64 * (i // cols)
+        orig[cy:cy + h, cx:cx + w] = it['org']
+        j = jobs[i]
+        j['x'], j['y'], j['log2w'], j['log2h'], j['mts_idx'], j['flags'] = cx, cy, w.bit_length() - 1, h.bit_length() - 1, it['mts'], TU_QUANT
+        j['qp_per'], j['qp_rem'], j['offset'] = it['per'], it['rem'], off
+        it['off'] = off
+        off += w * h
+    return orig, jobs, np.concatenate([it['resi'].ravel() for it in items]), np.concatenate([it['pred'].ravel() for it in items]), items
+
+
+def oracle_tu_chain(items, bd):
+    """The oracle's whole TU chain for random_tu_case items -> dict like the kernel's outputs."""
+    import vvc_intra_b200 as vb
+    n = sum(it['resi'].size for it in items)
+    out = dict(results=np.zeros(len(items), vb.TU_RESULT_DTYPE), coeff=np.zeros(n, np.int32), level=np.zeros(n, np.int32), reco=np.zeros(n, np.int16))
+    for i, it in enumerate(items):
+        h, w = it['resi'].shape
+        sl = slice(it['off'], it['off'] + w * h)
+        co = O.fwd_transform(it['resi'], bd, it['mts'])
+        lvl, s = O.quant_scalar(co, bd, it['per'], it['rem'], it['mts'] == 1)
+        res = O.inv_transform(O.dequant(lvl, bd, it['per'], it['rem'], it['mts'] == 1), bd, it['mts'])
+        reco, sse = O.reconstruct_sse(it['org'], it['pred'], res, bd)
+        out['coeff'][sl], out['level'][sl], out['reco'][sl] = co.ravel(), lvl.ravel(), reco.ravel()
+        out['results'][i] = (O.abs_sum_for_preselection(co, it['mts']), s, sse)
+    return out

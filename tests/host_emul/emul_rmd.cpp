@@ -4,6 +4,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include "../../vvc_intra_b200/csrc/vvcb_rmd.cuh"
+#include "../../vvc_intra_b200/csrc/vvcb_tu.cuh"
 #include "../../vvc_intra_b200/csrc/vvcb_romfill.h"
 
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -72,5 +73,17 @@ extern "C" int emul_rmd_eval(const int16_t* orig, const int16_t* reco, int strid
   }
   if (details) emu_launch((n + 31) / 32, 256, [&] { rmd_detail_kernel(visits, n, ctu, details, P.sadSM, P.satdSM); });
   emu_launch((n + kListThreads - 1) / kListThreads, kListThreads, [&] { rmd_lists_kernel(visits, n, ctu, results, details, P.sadSM, P.satdSM); });
+  return 0;
+}
+
+extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred,
+                            int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results)
+{
+  static TrRom rom;
+  fill_tr_rom(rom);
+  TuParams P;
+  P.jobs = jobs; P.n = n; P.resi = resi; P.pred = pred; P.coeff = coeff; P.level = level; P.reco = reco; P.results = results;
+  P.orig = orig; P.stride = stride; P.bd = bd; P.rom = &rom;
+  emu_launch(2, kTuThreads, [&] { tu_eval_kernel(P); });
   return 0;
 }

@@ -140,3 +140,52 @@ def test_error_behaviour(eng10):
             fresh.rmd_eval(np.zeros(1, vb.VISIT_DTYPE))
     with pytest.raises(vb.EngineError):
         vb.IntraCostEngine(device=99)
+
+
+# ---- TU coding (vvcb_tu_eval) ---------------------------------------------------------------------------
+@pytest.mark.parametrize('name,bd', [('ref_8b_128x64_qp32', 8), ('ref_10b_192x128_qp27', 10), ('ref_10b_64x64_qp32_scalarq', 10)])
+def test_tu_golden_parity(name, bd, eng8, eng10):
+    """Forward DCT-II / DST-VII / DCT-VIII / transform-skip coefficients and pre-selection sums of the reference's
+    transformNxN(trModes) records; levels and uiAbsSum of its Quant::quant records; reconstruction + SSE versus the oracle."""
+    eng = eng8 if bd == 8 else eng10
+    _, tus = G.load_fixture(name)
+    orig, jobs, resi, pred, items = G.build_tu_batch(tus, bd)
+    eng.frame_begin(orig)
+    out = eng.tu_eval(jobs, resi, pred, want_coeff=True, want_level=True, want_reco=True)
+    errs = G.check_tu_outputs(items, bd, out)
+    assert not errs, errs[:5]
+    # the candidate selection of TrQuant::transformNxN(trModes) from the kernel's sums
+    k = 0
+    for r in [t for t in tus if t['tag'] == 'S' and t['bd'] == bd]:
+        m = len(r['modes'])
+        sel = eng.mts_preselect(out['results']['abs_sum_coeff'][k:k + m], r['w'], r['h'], r['max_cand'])
+        assert list(sel) == [x['selected'] for x in r['modes']]
+        k += m
+
+
+@pytest.mark.parametrize('bd,seed', [(8, 31), (10, 32), (10, 33)])
+def test_tu_random_blocks_match_oracle(bd, seed, eng8, eng10):
+    """Every (shape, transform) incl. 64-point sides with their zero-out, random QP, small to full-range residuals."""
+    eng = eng8 if bd == 8 else eng10
+    rng = np.random.default_rng(seed)
+    orig, jobs, resi, pred, items = G.random_tu_case(rng, bd, 3)
+    eng.frame_begin(orig)
+    out = eng.tu_eval(jobs, resi, pred, want_coeff=True, want_level=True, want_reco=True)
+    exp = G.oracle_tu_chain(items, bd)
+    for k in ('coeff', 'level', 'reco'):
+        assert np.array_equal(out[k], exp[k]), k
+    assert out['results'].tobytes() == exp['results'].tobytes()
+    # properties: a zero residual quantises to nothing and reconstructs the prediction
+    z = eng.tu_eval(jobs, np.zeros_like(resi), pred, want_level=True, want_reco=True)
+    assert not z['level'].any() and np.array_equal(z['reco'], pred) and not z['results']['abs_sum_coeff'].any()
+
+
+def test_tu_error_behaviour(eng10):
+    eng10.frame_begin(np.zeros((64, 64), np.int16))
+    j = np.zeros(1, vb.TU_JOB_DTYPE)
+    j['log2w'], j['log2h'], j['mts_idx'] = 6, 6, 2              # MTS is not allowed on 64-point sides
+    with pytest.raises(vb.EngineError, match='malformed'):
+        eng10.tu_eval(j, np.zeros(4096, np.int16))
+    j['mts_idx'], j['flags'] = 0, vb.TU_QUANT
+    with pytest.raises(vb.EngineError, match='prediction'):
+        eng10.tu_eval(j, np.zeros(4096, np.int16))

@@ -74,3 +74,37 @@ def test_emulated_kernels_match_oracle_on_random_visits(emul, bd, seed):
     ora, odet = O.rmd_batch(orig, reco, bd, 128, arr)
     bad = [i for i in range(len(arr)) if res[i].tobytes() != ora[i].tobytes() or det[i].tobytes() != odet[i].tobytes()]
     assert not bad, (len(bad), arr[bad[0]])
+
+
+# ---- TU coding kernel (vvcb_tu.cuh) ------------------------------------------------------------------------
+def run_emul_tu(lib, orig, bd, jobs, resi, pred):
+    import vvc_intra_b200 as vb
+    orig = np.ascontiguousarray(orig, np.int16)
+    out = dict(results=np.zeros(len(jobs), vb.TU_RESULT_DTYPE), coeff=np.zeros(resi.size, np.int32), level=np.zeros(resi.size, np.int32),
+               reco=np.zeros(resi.size, np.int16))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.emul_tu_eval(p(orig), orig.shape[1], bd, p(jobs), len(jobs), p(resi), p(pred), p(out['coeff']), p(out['level']), p(out['reco']),
+                          p(out['results']))
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize('name,bd', [('ref_8b_128x64_qp32', 8), ('ref_10b_192x128_qp27', 10), ('ref_10b_64x64_qp32_scalarq', 10)])
+def test_emulated_tu_kernel_matches_reference(emul, name, bd):
+    _, tus = G.load_fixture(name)
+    orig, jobs, resi, pred, items = G.build_tu_batch(tus, bd, max_jobs=160)
+    assert len(items) > 20
+    out = run_emul_tu(emul, orig, bd, jobs, resi, pred)
+    errs = G.check_tu_outputs(items, bd, out)
+    assert not errs, errs[:5]
+
+
+@pytest.mark.parametrize('bd,seed', [(8, 21), (10, 22)])
+def test_emulated_tu_kernel_matches_oracle_on_random_blocks(emul, bd, seed):
+    rng = np.random.default_rng(seed)
+    orig, jobs, resi, pred, items = G.random_tu_case(rng, bd, 1)
+    out = run_emul_tu(emul, orig, bd, jobs, resi, pred)
+    exp = G.oracle_tu_chain(items, bd)
+    for k in ('coeff', 'level', 'reco'):
+        assert np.array_equal(out[k], exp[k]), k
+    assert out['results'].tobytes() == exp['results'].tobytes()

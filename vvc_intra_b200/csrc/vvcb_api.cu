@@ -7,6 +7,7 @@
 #include <math.h>
 #include <new>
 #include "vvcb_rmd.cuh"
+#include "vvcb_tu.cuh"
 #include "vvcb_romfill.h"
 
 // =====================================================================================================
@@ -44,6 +45,8 @@ struct vvcb_ctx {
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
   Rom* dRom;
+  TrRom* dTrRom;
+  void* dTu[7]; size_t capTu[7];    // TU scratch: jobs, resi, pred, coeff, level, reco, results
   int16_t* dOrig; int16_t* dReco;
   const int16_t* bOrig; const int16_t* bReco;   // planes in use (own or bound)
   int width, height, stride;        // planes share one pitch (in samples)
@@ -119,6 +122,14 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
   delete h;
   if (e != cudaSuccess) return fail("cudaMemcpy(rom)", e);
   if ((e = cudaMalloc(&ctx->dPlan, sizeof(PlanState))) != cudaSuccess) return fail("cudaMalloc(plan)", e);
+  {
+    TrRom* t = new TrRom();
+    fill_tr_rom(*t);
+    if ((e = cudaMalloc(&ctx->dTrRom, sizeof(TrRom))) != cudaSuccess) { delete t; return fail("cudaMalloc(trrom)", e); }
+    e = cudaMemcpy(ctx->dTrRom, t, sizeof(TrRom), cudaMemcpyHostToDevice);
+    delete t;
+    if (e != cudaSuccess) return fail("cudaMemcpy(trrom)", e);
+  }
   *out = ctx;
   return VVCB_OK;
 }
@@ -129,7 +140,8 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dSlotMajor);
-  cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred);
+  cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred); cudaFree(ctx->dTrRom);
+  for (int i = 0; i < 7; i++) cudaFree(ctx->dTu[i]);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->kev[i]);
   cudaStreamDestroy(ctx->stream);
@@ -368,6 +380,85 @@ extern "C" int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slo
   CK(cudaMemcpyAsync(pred, ctx->dPred + (size_t)slot * w * h, (size_t)w * h * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return VVCB_OK;
+}
+
+static int tu_buf(vvcb_ctx* ctx, int i, size_t bytes)
+{
+  if (bytes > ctx->capTu[i]) {
+    cudaFree(ctx->dTu[i]); ctx->dTu[i] = nullptr; ctx->capTu[i] = 0;
+    CK(cudaMalloc(&ctx->dTu[i], bytes));
+    ctx->capTu[i] = bytes;
+  }
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred, size_t n_samples,
+                            int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (n < 0 || (n > 0 && (!jobs || !resi || !results))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: bad argument"); return VVCB_ERR_ARG; }
+  if (n == 0) return VVCB_OK;
+  bool anyQuant = false;
+  for (int i = 0; i < n; i++) {
+    const vvcb_tu_job& j = jobs[i];
+    const size_t sz = (size_t)1 << (j.log2w + j.log2h);
+    const bool q = (j.flags & VVCB_TU_QUANT) != 0;
+    anyQuant = anyQuant || q;
+    bool ok = j.log2w >= 2 && j.log2w <= 6 && j.log2h >= 2 && j.log2h <= 6 && j.mts_idx <= 5 && (size_t)j.offset + sz <= n_samples &&
+              j.qp_rem >= 0 && j.qp_rem < 6 && j.qp_per >= 0 && j.qp_per < 16;
+    if (j.mts_idx == 1) ok = ok && j.log2w <= 5 && j.log2h <= 5;                 // TU::isTSAllowed, CL/UnitTools.cpp:4524
+    if (j.mts_idx > 1)  ok = ok && j.log2w <= 5 && j.log2h <= 5;                 // TU::isMTSAllowed, :4549
+    if (q) ok = ok && ctx->bOrig && j.x >= 0 && j.y >= 0 && j.x + (1 << j.log2w) <= ctx->width && j.y + (1 << j.log2h) <= ctx->height;
+    if (!ok) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: job %d is malformed", i); return VVCB_ERR_ARG; }
+  }
+  if (anyQuant && !pred) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: VVCB_TU_QUANT needs the prediction samples"); return VVCB_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = tu_buf(ctx, 0, (size_t)n * sizeof(vvcb_tu_job)))) return rc;
+  if ((rc = tu_buf(ctx, 1, n_samples * sizeof(int16_t)))) return rc;
+  if ((rc = tu_buf(ctx, 2, n_samples * sizeof(int16_t)))) return rc;
+  if (coeff && (rc = tu_buf(ctx, 3, n_samples * sizeof(int32_t)))) return rc;
+  if (level && (rc = tu_buf(ctx, 4, n_samples * sizeof(int32_t)))) return rc;
+  if (reco && (rc = tu_buf(ctx, 5, n_samples * sizeof(int16_t)))) return rc;
+  if ((rc = tu_buf(ctx, 6, (size_t)n * sizeof(vvcb_tu_result)))) return rc;
+  CK(cudaMemcpyAsync(ctx->dTu[0], jobs, (size_t)n * sizeof(vvcb_tu_job), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dTu[1], resi, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (pred) CK(cudaMemcpyAsync(ctx->dTu[2], pred, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  TuParams P;
+  P.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); P.n = n;
+  P.resi = static_cast<const int16_t*>(ctx->dTu[1]); P.pred = static_cast<const int16_t*>(ctx->dTu[2]);
+  P.coeff = coeff ? static_cast<int32_t*>(ctx->dTu[3]) : nullptr;
+  P.level = level ? static_cast<int32_t*>(ctx->dTu[4]) : nullptr;
+  P.reco = reco ? static_cast<int16_t*>(ctx->dTu[5]) : nullptr;
+  P.results = static_cast<vvcb_tu_result*>(ctx->dTu[6]);
+  P.orig = ctx->bOrig; P.stride = ctx->stride; P.bd = ctx->bd; P.rom = ctx->dTrRom;
+  const int grid = n < ctx->numSms * 8 ? n : ctx->numSms * 8;
+  tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  if (coeff) CK(cudaMemcpyAsync(coeff, ctx->dTu[3], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (level) CK(cudaMemcpyAsync(level, ctx->dTu[4], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (reco) CK(cudaMemcpyAsync(reco, ctx->dTu[5], n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(results, ctx->dTu[6], (size_t)n * sizeof(vvcb_tu_result), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+
+// host logic: CL/TrQuant.cpp:1112-1123
+extern "C" void vvcb_mts_preselect(const int32_t* sums, int n, int width, int height, int max_cand, uint8_t* selected)
+{
+  static const double facBB[5] = { 1.2, 1.3, 1.3, 1.4, 1.5 };
+  if (n <= 0) return;
+  int lg = 0;
+  for (int m = width > height ? width : height; m > 1; m >>= 1) lg++;
+  const double fac = facBB[lg - 2];
+  const double thr = fac * sums[0], thrTS = sums[0];
+  int tests = 0;
+  for (int i = 0; i < n; i++) {
+    const bool t = sums[i] <= (i == 1 ? thrTS : thr) && tests <= max_cand;
+    selected[i] = t ? 1 : 0;
+    tests += t;
+  }
 }
 
 extern "C" int vvcb_dev_alloc(vvcb_ctx* ctx, size_t bytes, void** out)

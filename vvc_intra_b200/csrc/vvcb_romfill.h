@@ -35,3 +35,14 @@ inline void fill_rom(Rom& r)
 }
 
 }  // namespace vvcb
+
+// forward transform kernels and quantiser scales (vvcb_tu.cuh's TrRom); T has the TrRom layout
+template <class T> inline void fill_tr_rom(T& r)
+{
+  memset(&r, 0, sizeof(r));
+  memcpy(r.dct2, kDct2_4, 32); memcpy(r.dct2 + 16, kDct2_8, 128); memcpy(r.dct2 + 80, kDct2_16, 512);
+  memcpy(r.dct2 + 336, kDct2_32, 2048); memcpy(r.dct2 + 1360, kDct2_64, 8192);
+  memcpy(r.dct8, kDct8_4, 32); memcpy(r.dct8 + 16, kDct8_8, 128); memcpy(r.dct8 + 80, kDct8_16, 512); memcpy(r.dct8 + 336, kDct8_32, 2048);
+  memcpy(r.dst7, kDst7_4, 32); memcpy(r.dst7 + 16, kDst7_8, 128); memcpy(r.dst7 + 80, kDst7_16, 512); memcpy(r.dst7 + 336, kDst7_32, 2048);
+  for (int i = 0; i < 12; i++) { r.quantScales[i] = kQuantScales[i]; r.invQuantScales[i] = kInvQuantScales[i]; }
+}

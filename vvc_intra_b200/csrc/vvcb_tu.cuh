@@ -1,0 +1,189 @@
+// vvc_intra_b200 -- TU coding kernel (sm_100a): forward separable transform (DCT-II / DST-VII / DCT-VIII as exact
+// integer matrix products, or transform skip), pre-selection sum, scalar quantisation, dequantisation, inverse
+// transform with the reference's intermediate clipping, reconstruction and SSE.
+//
+// Reference behaviour: CL/TrQuant.cpp:835-915 (xT), :917-993 (xIT), :1394-1438 / :996-1041 (transform skip),
+// :1090-1103 (pre-selection sum), CL/Quant.cpp:994-1089 (quant), :423-540 (dequant), CL/RdCost.cpp:1739 (SSE).
+// The reference's partial butterflies (CL/TrQuant_EMT.cpp) are exact evaluations of the same products.
+// One CTA per job; the block lives in shared memory as int32, the second operand with a padded stride.
+#pragma once
+#include "vvcb_core.cuh"
+
+namespace {
+
+struct TrRom {                     // forward kernels M[k][n], int16, by type (0 DCT2, 1 DCT8, 2 DST7) and log2 size
+  int16_t dct2[16 + 64 + 256 + 1024 + 4096];
+  int16_t dct8[16 + 64 + 256 + 1024];
+  int16_t dst7[16 + 64 + 256 + 1024];
+  int32_t quantScales[12], invQuantScales[12];
+};
+
+__device__ __forceinline__ const int16_t* tr_kernel(const TrRom& rom, int type, int lg)
+{
+  const int off = lg == 2 ? 0 : lg == 3 ? 16 : lg == 4 ? 80 : lg == 5 ? 336 : 1360;
+  return (type == 0 ? rom.dct2 : type == 1 ? rom.dct8 : rom.dst7) + off;
+}
+
+constexpr int kTuThreads = 128;
+
+struct TuParams {
+  const vvcb_tu_job* jobs;
+  int n;
+  const int16_t* resi;
+  const int16_t* pred;
+  int32_t* coeff;      // optional
+  int32_t* level;      // optional
+  int16_t* reco;       // optional
+  vvcb_tu_result* results;
+  const int16_t* orig;
+  int stride, bd;
+  const TrRom* rom;
+};
+
+__device__ __forceinline__ int clip16(int v) { return vmin(vmax(v, -32768), 32767); }
+
+// block-wide sum of one int per thread (result valid in every thread)
+__device__ __forceinline__ long long block_sum(long long v, long long* red)
+{
+  for (int o = 16; o > 0; o >>= 1) {
+    const int lo = __shfl_xor_sync(0xffffffffu, (int)(v & 0xffffffffll), o);
+    const int hi = __shfl_xor_sync(0xffffffffu, (int)(v >> 32), o);
+    v += ((long long)hi << 32) | (unsigned)lo;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  long long t = 0;
+  for (int i = 0; i < kTuThreads / 32; i++) t += red[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
+{
+  __shared__ int A[64 * 64];
+  __shared__ int B[32 * 65];
+  __shared__ long long red[kTuThreads / 32];
+  const TrRom& rom = *P.rom;
+  for (int ji = blockIdx.x; ji < P.n; ji += gridDim.x) {
+    const vvcb_tu_job job = P.jobs[ji];
+    const int lw = job.log2w, lh = job.log2h, w = 1 << lw, h = 1 << lh, n = w * h;
+    const bool ts = job.mts_idx == 1;
+    const int hor = job.mts_idx > 1 ? (((job.mts_idx - 2) & 1) ? 1 : 2) : 0;
+    const int ver = job.mts_idx > 1 ? (((job.mts_idx - 2) >> 1) ? 1 : 2) : 0;
+    const int wKeep = w - ((hor != 0 && w == 32) ? 16 : (w > 32 ? w - 32 : 0));
+    const int hKeep = h - ((ver != 0 && h == 32) ? 16 : (h > 32 ? h - 32 : 0));
+    const int trShift = 15 - P.bd - ((lw + lh) >> 1);
+    const int16_t* mh = tr_kernel(rom, hor, lw);
+    const int16_t* mv = tr_kernel(rom, ver, lh);
+    const int16_t* resi = P.resi + job.offset;
+    const int hp = h + 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kTuThreads) A[i] = ts ? ((int)resi[i] << trShift) : (int)resi[i];
+    __syncthreads();
+    if (!ts) {
+      const int shift1 = lw + P.bd + 6 - 15, shift2 = lh + 6;
+      const int add1 = shift1 > 0 ? 1 << (shift1 - 1) : 0, add2 = 1 << (shift2 - 1);
+      for (int o = threadIdx.x; o < wKeep * h; o += kTuThreads) {          // rows: B[k][j]
+        const int k = o % wKeep, j = o / wKeep;
+        const int16_t* m = mh + k * w;
+        const int* a = A + j * w;
+        int acc = 0;
+        for (int t = 0; t < w; t++) acc += (int)m[t] * a[t];
+        B[k * hp + j] = (acc + add1) >> shift1;
+      }
+      __syncthreads();
+      for (int o = threadIdx.x; o < n; o += kTuThreads) {                 // columns: A[l][k]
+        const int k = o & (w - 1), l = o >> lw;
+        int v = 0;
+        if (k < wKeep && l < hKeep) {
+          const int16_t* m = mv + l * h;
+          const int* b = B + k * hp;
+          int acc = 0;
+          for (int t = 0; t < h; t++) acc += (int)m[t] * b[t];
+          v = (acc + add2) >> shift2;
+        }
+        A[o] = v;
+      }
+      __syncthreads();
+    }
+    long long part = 0;
+    for (int i = threadIdx.x; i < n; i += kTuThreads) {
+      part += vabs(A[i]);
+      if (P.coeff) P.coeff[job.offset + i] = A[i];
+    }
+    const long long sumAbs = block_sum(part, red);
+    int absLevel = 0;
+    unsigned long long sse = 0;
+    if (job.flags & VVCB_TU_QUANT) {
+      const bool sqrtAdj = !ts && ((lw + lh) & 1);
+      const int qScale = rom.quantScales[(sqrtAdj ? 6 : 0) + job.qp_rem];
+      const int iScale = rom.invQuantScales[(sqrtAdj ? 6 : 0) + job.qp_rem];
+      const int qbits = 14 + job.qp_per + trShift + (sqrtAdj ? -1 : 0);
+      const long long qadd = 171ll << (qbits - 9);
+      const int rightShift = 6 - (trShift + (sqrtAdj ? -1 : 0) + job.qp_per);
+      const int tgt = vmin(16, 32 + rightShift - 7);
+      const int inMin = -(1 << (tgt - 1)), inMax = (1 << (tgt - 1)) - 1;
+      long long lpart = 0;
+      for (int i = threadIdx.x; i < n; i += kTuThreads) {
+        const int c = A[i];
+        const long long t = (long long)vabs(c) * qScale;
+        const int mag = (int)((t + qadd) >> qbits);
+        const int q = clip16(c < 0 ? -mag : mag);
+        lpart += mag;
+        if (P.level) P.level[job.offset + i] = q;
+        const int qc = vmin(vmax(q, inMin), inMax);
+        int d;
+        if (rightShift > 0) d = (qc * iScale + (1 << (rightShift - 1))) >> rightShift;
+        else                d = (int)((unsigned)(qc * iScale) << (-rightShift));
+        A[i] = clip16(d);
+      }
+      absLevel = (int)block_sum(lpart, red);
+      const int16_t* pred = P.pred + job.offset;
+      const int16_t* org = P.orig + (size_t)job.y * P.stride + job.x;
+      const int maxv = (1 << P.bd) - 1;
+      long long spart = 0;
+      if (!ts) {
+        const int shift2 = 20 - P.bd;
+        for (int o = threadIdx.x; o < wKeep * h; o += kTuThreads) {        // columns first: B[j][y]
+          const int j = o % wKeep, y = o / wKeep;
+          int acc = 0;
+          for (int k = 0; k < hKeep; k++) acc += (int)mv[k * h + y] * A[k * w + j];
+          B[j * hp + y] = clip16((acc + 64) >> 7);
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < n; o += kTuThreads) {               // rows
+          const int x = o & (w - 1), y = o >> lw;
+          int acc = 0;
+          for (int k = 0; k < wKeep; k++) acc += (int)mh[k * w + x] * B[k * hp + y];
+          const int r = clip16((acc + (1 << (shift2 - 1))) >> shift2);
+          const int rec = vmin(vmax((int)pred[o] + (int)(int16_t)r, 0), maxv);
+          if (P.reco) P.reco[job.offset + o] = (int16_t)rec;
+          const int d = (int)org[y * P.stride + x] - rec;
+          spart += (long long)d * d;
+        }
+      } else {
+        const int off = trShift == 0 ? 0 : 1 << (trShift - 1);
+        for (int o = threadIdx.x; o < n; o += kTuThreads) {
+          const int x = o & (w - 1), y = o >> lw;
+          const int r = (int)(int16_t)((A[o] + off) >> trShift);
+          const int rec = vmin(vmax((int)pred[o] + r, 0), maxv);
+          if (P.reco) P.reco[job.offset + o] = (int16_t)rec;
+          const int d = (int)org[y * P.stride + x] - rec;
+          spart += (long long)d * d;
+        }
+      }
+      sse = (unsigned long long)block_sum(spart, red);
+    }
+    if (threadIdx.x == 0) {
+      double scale = 1.0;
+      if (ts && ((lw + lh) & 1)) scale = 1.0 / 1.414213562;               // CL/TrQuant.cpp:1098-1102
+      vvcb_tu_result r;
+      r.abs_sum_coeff = (int)__dmul_rn((double)(int)sumAbs, scale);
+      r.abs_sum_level = absLevel;
+      r.sse = sse;
+      P.results[ji] = r;
+    }
+  }
+}
+
+}  // namespace

@@ -31,6 +31,13 @@ assert VISIT_DTYPE.itemsize == 80 and RESULT_DTYPE.itemsize == 368 and DETAIL_DT
     (VISIT_DTYPE.itemsize, RESULT_DTYPE.itemsize, DETAIL_DTYPE.itemsize)
 
 
+TU_QUANT = 1
+TU_JOB_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('log2w', 'u1'), ('log2h', 'u1'), ('mts_idx', 'u1'), ('flags', 'u1'),
+                         ('qp_per', '<i2'), ('qp_rem', '<i2'), ('offset', '<u4')], align=True)
+TU_RESULT_DTYPE = np.dtype([('abs_sum_coeff', '<i4'), ('abs_sum_level', '<i4'), ('sse', '<u8')], align=True)
+assert TU_JOB_DTYPE.itemsize == 16 and TU_RESULT_DTYPE.itemsize == 16
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -70,6 +77,10 @@ def load_library():
         L.vvcb_dev_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.vvcb_dev_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.vvcb_sync.argtypes = [C.c_void_p]
+        L.vvcb_tu_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+        L.vvcb_mts_preselect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.vvcb_mts_preselect.restype = None
         L.vvcb_frame_bind_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.vvcb_kernel_timing.argtypes = [C.c_void_p, C.c_int]
         L.vvcb_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
@@ -155,6 +166,31 @@ class IntraCostEngine:
         pred = np.zeros((h, w), np.int16)
         self._ck(self._lib.vvcb_rmd_pred(self._ctx, _ptr(visit), slot, _ptr(pred)))
         return pred
+
+    # ---- TU coding
+    def tu_eval(self, jobs, resi, pred=None, want_coeff=False, want_level=False, want_reco=False):
+        """vvcb_tu_eval.  resi / pred: flat int16 arrays indexed by job['offset'].  Returns dict of outputs."""
+        jobs = np.ascontiguousarray(jobs, TU_JOB_DTYPE)
+        resi = np.ascontiguousarray(resi, np.int16).ravel()
+        pred = None if pred is None else np.ascontiguousarray(pred, np.int16).ravel()
+        ns = resi.size
+        out = dict(results=np.zeros(len(jobs), TU_RESULT_DTYPE))
+        if want_coeff:
+            out['coeff'] = np.zeros(ns, np.int32)
+        if want_level:
+            out['level'] = np.zeros(ns, np.int32)
+        if want_reco:
+            out['reco'] = np.zeros(ns, np.int16)
+        self._ck(self._lib.vvcb_tu_eval(self._ctx, _ptr(jobs), len(jobs), _ptr(resi), _ptr(pred) if pred is not None else None, ns,
+                                        _ptr(out['coeff']) if want_coeff else None, _ptr(out['level']) if want_level else None,
+                                        _ptr(out['reco']) if want_reco else None, _ptr(out['results'])))
+        return out
+
+    def mts_preselect(self, sums, width, height, max_cand):
+        sums = np.ascontiguousarray(sums, np.int32)
+        sel = np.zeros(len(sums), np.uint8)
+        self._lib.vvcb_mts_preselect(_ptr(sums), len(sums), width, height, max_cand, _ptr(sel))
+        return sel
 
     # ---- device-resident path (bench: kernels without the PCIe copies)
     def dev_alloc(self, nbytes):
