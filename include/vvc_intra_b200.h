@@ -181,6 +181,35 @@ int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* r
  * TU's candidates in list order (DCT2 first, transform skip second if tested): pure host logic.                    */
 void vvcb_mts_preselect(const int32_t* sums, int n, int width, int height, int max_cand, uint8_t* selected);
 
+/* ---- texture features (orig-only, trivially parallel) ------------------------------------------------------------
+ * vvcb_ctu_hads_islice: EncCu::updateCtuDataISlice (EL/EncCu.cpp:564-675) for every CTU of the frame, as
+ * EncSlice::calCostSliceI calls it (EL/EncSlice.cpp:1276-1298): sum over the complete 8x8 blocks of the CTU's
+ * original luma of (Hadamard AC sum + 2) >> 2.  out[ctuRsAddr], n_ctus = ceil(w/ctu)*ceil(h/ctu).                    */
+int vvcb_ctu_hads_islice(vvcb_ctx* ctx, int32_t* out, int n_ctus);
+
+/* vvcb_features_eval: the 27 classifier inputs of the fork's FAST_ALGORITHM block (EL/EncCu.cpp:72-164, 816-1138).
+ * The host walk owns the coding structure, so it ships the current CU and the neighbour CUs it found with
+ * tempCS->getCU (:857-933: left, left-down, up, right-up, left-up; only their area and depths are used); the engine
+ * computes every pixel-derived term from the frame's (LMCS-mapped) original luma, saturated to 8 bit as the
+ * reference's convertTo(CV_8U) does.                                                                                 */
+#define VVCB_NUM_FEATURES 27
+typedef struct vvcb_feat_cu {
+  int16_t x, y;             /* luma position                                                                        */
+  uint8_t w, h;             /* luma size, powers of two 4..128                                                      */
+  uint8_t qt_depth, mt_depth;
+} vvcb_feat_cu;
+typedef struct vvcb_feat_job {
+  vvcb_feat_cu cu;          /* currCsArea + partitioner.currQtDepth / currMtDepth                                   */
+  uint8_t n_neighbours;     /* valid_num (0..5); the reference evaluates the classifier only when it is >= 3        */
+  uint8_t pad[7];
+  vvcb_feat_cu nb[5];
+} vvcb_feat_job;
+typedef struct vvcb_feat_result {
+  int32_t f[VVCB_NUM_FEATURES];   /* features[0..26] (EL/EncCu.cpp:1098-1138); neighbour terms are 0 when n_neighbours == 0 */
+  int32_t valid;                  /* n_neighbours >= 3                                                              */
+} vvcb_feat_result;
+int vvcb_features_eval(vvcb_ctx* ctx, const vvcb_feat_job* jobs, int n, vvcb_feat_result* results);
+
 /* ---- raw device memory for resident benchmarking --------------------------------------------- */
 int vvcb_dev_alloc(vvcb_ctx* ctx, size_t bytes, void** out);
 int vvcb_dev_free (vvcb_ctx* ctx, void* p);

@@ -257,3 +257,26 @@ def reconstruct_sse(org, pred, resi, bd):
     lib().orc_reconstruct_sse.restype = C.c_uint64
     sse = lib().orc_reconstruct_sse(po, w, pp, pr, w, h, bd, reco.ctypes.data_as(_p16))
     return reco, sse
+
+
+# ---- texture measures (oracle/vvc_oracle_feat.c) ------------------------------------------------------------
+FEAT_CU_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('w', 'u1'), ('h', 'u1'), ('qt_depth', 'u1'), ('mt_depth', 'u1')])
+FEAT_JOB_DTYPE = np.dtype([('cu', FEAT_CU_DTYPE), ('n_neighbours', 'u1'), ('pad', 'u1', 7), ('nb', FEAT_CU_DTYPE, 5)])
+FEAT_RESULT_DTYPE = np.dtype([('f', '<i4', 27), ('valid', '<i4')])
+assert FEAT_JOB_DTYPE.itemsize == 56 and FEAT_RESULT_DTYPE.itemsize == 112
+
+
+def ctu_hads_islice(orig, ctu=128):
+    orig, po = _a16(orig)
+    h, w = orig.shape
+    out = np.zeros(((h + ctu - 1) // ctu) * ((w + ctu - 1) // ctu), np.int32)
+    lib().orc_ctu_hads_islice(po, w, w, h, ctu, out.ctypes.data_as(_p32))
+    return out
+
+
+def features_batch(orig, jobs):
+    orig, po = _a16(orig)
+    jobs = np.ascontiguousarray(jobs, FEAT_JOB_DTYPE)
+    out = np.zeros(len(jobs), FEAT_RESULT_DTYPE)
+    lib().orc_features_batch(po, orig.shape[1], C.c_void_p(jobs.ctypes.data), len(jobs), C.c_void_p(out.ctypes.data))
+    return out

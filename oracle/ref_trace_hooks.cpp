@@ -15,6 +15,7 @@
 //   CABACWriter::intra_luma_pred_mode          :4263 xFracModeBitsIntra   mode bits (a10)
 //   TrQuant::transformNxN (both overloads)     :2965,:2968                fwd transform / quant (a12,a13)
 //   TrQuant::invTransformNxN                   :3002                      dequant + inverse (a14)
+//   EncCu::updateCtuDataISlice                 EL/EncSlice.cpp:1291       per-CTU Hadamard texture sum (a16; needs --RateControl=1)
 //
 // Record stream: { u8 tag; u32 payload_bytes; payload }.  Layouts are parsed by
 // tools/make_golden.py (one struct format per tag, kept next to each emit()).
@@ -72,6 +73,7 @@
 #include "CommonLib/UnitPartitioner.h"
 #include "EncoderLib/CABACWriter.h"
 #include "EncoderLib/IntraSearch.h"
+#include "EncoderLib/EncCu.h"
 #undef private
 #undef protected
 
@@ -436,6 +438,20 @@ void __wrap__ZN7TrQuant15invTransformNxNER13TransformUnitRK11ComponentIDR7AreaBu
   for( int y = 0; y < (int) rect.height; y++ ) for( int x = 0; x < (int) rect.width; x++ ) r.i32( lv.at( x, y ) );
   putBlock( r, resi );
   r.emit( 'I' );
+}
+
+// 'H' (EncCu::updateCtuDataISlice): i32 w,h,result, org[w*h] i16
+int __real__ZN5EncCu19updateCtuDataISliceE7AreaBufIKsE( EncCu* cu, const CPelBuf buf );
+int __wrap__ZN5EncCu19updateCtuDataISliceE7AreaBufIKsE( EncCu* cu, const CPelBuf buf )
+{
+  const int res = __real__ZN5EncCu19updateCtuDataISliceE7AreaBufIKsE( cu, buf );
+  init();
+  if( !g_out ) return res;
+  Rec r;
+  r.i32( buf.width ); r.i32( buf.height ); r.i32( res );
+  for( int y = 0; y < (int) buf.height; y++ ) for( int x = 0; x < (int) buf.width; x++ ) r.i16( buf.at( x, y ) );
+  r.emit( 'H' );
+  return res;
 }
 
 } // extern "C"

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include "../../vvc_intra_b200/csrc/vvcb_rmd.cuh"
 #include "../../vvc_intra_b200/csrc/vvcb_tu.cuh"
+#include "../../vvc_intra_b200/csrc/vvcb_feat.cuh"
 #include "../../vvc_intra_b200/csrc/vvcb_romfill.h"
 
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -85,5 +86,21 @@ extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_
   P.jobs = jobs; P.n = n; P.resi = resi; P.pred = pred; P.coeff = coeff; P.level = level; P.reco = reco; P.results = results;
   P.orig = orig; P.stride = stride; P.bd = bd; P.rom = &rom;
   emu_launch(2, kTuThreads, [&] { tu_eval_kernel(P); });
+  return 0;
+}
+
+extern "C" int emul_features_eval(const int16_t* orig, int stride, const vvcb_feat_job* jobs, int n, vvcb_feat_result* results)
+{
+  FeatParams P;
+  P.jobs = jobs; P.n = n; P.results = results; P.orig = orig; P.stride = stride;
+  emu_launch(3, kFeatThreads, [&] { features_kernel(P); });
+  return 0;
+}
+
+extern "C" int emul_ctu_hads(const int16_t* orig, int stride, int width, int height, int ctu, int32_t* out)
+{
+  const int perRow = (width + ctu - 1) / ctu, rows = (height + ctu - 1) / ctu;
+  memset(out, 0, sizeof(int32_t) * perRow * rows);
+  emu_launch(2, 256, [&] { ctu_hads_kernel(orig, stride, width, height, ctu, perRow, out); });
   return 0;
 }

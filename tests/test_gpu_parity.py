@@ -156,7 +156,11 @@ def test_tu_golden_parity(name, bd, eng8, eng10):
     assert not errs, errs[:5]
     # the candidate selection of TrQuant::transformNxN(trModes) from the kernel's sums
     k = 0
-    for r in [t for t in tus if t['tag'] == 'S' and t['bd'] == bd]:
+    while k < len(items):
+        if items[k]['kind'] != 'S':
+            k += 1
+            continue
+        r = items[k]['rec']
         m = len(r['modes'])
         sel = eng.mts_preselect(out['results']['abs_sum_coeff'][k:k + m], r['w'], r['h'], r['max_cand'])
         assert list(sel) == [x['selected'] for x in r['modes']]
@@ -189,3 +193,67 @@ def test_tu_error_behaviour(eng10):
     j['mts_idx'], j['flags'] = 0, vb.TU_QUANT
     with pytest.raises(vb.EngineError, match='prediction'):
         eng10.tu_eval(j, np.zeros(4096, np.int16))
+
+
+# ---- texture measures (vvcb_ctu_hads_islice, vvcb_features_eval) ------------------------------------------
+def test_ctu_hads_islice_parity(eng10):
+    """EncCu::updateCtuDataISlice: the reference's own per-CTU sums (ragged 72-wide / 8-high CTUs), then a 1080p frame."""
+    _, recs = G.load_fixture('ref_10b_200x136_ctuhad')
+    hs = [r for r in recs if r['tag'] == 'H']
+    pic = np.zeros((136, 200), np.int16)
+    pic[:128, :128], pic[:128, 128:], pic[128:, :128], pic[128:, 128:] = [r['org'] for r in hs]
+    eng10.frame_begin(pic)
+    assert eng10.ctu_hads_islice(200, 136).tolist() == [r['result'] for r in hs]
+    from make_golden import synth_yuv
+    Y = synth_yuv(1920, 1080, 10)[0].astype(np.int16)
+    eng10.frame_begin(Y)
+    got = eng10.ctu_hads_islice(1920, 1080)
+    assert got.shape == (135,) and got.tolist() == O.ctu_hads_islice(Y, ctu=128).tolist()
+    eng10.frame_begin(np.full((64, 64), 513, np.int16))       # flat content has no AC energy
+    assert eng10.ctu_hads_islice(64, 64).tolist() == [0]
+    with pytest.raises(vb.EngineError, match='CTUs'):
+        eng10._ck(eng10._lib.vvcb_ctu_hads_islice(eng10._ctx, np.zeros(3, np.int32).ctypes.data, 3))
+
+
+@pytest.mark.parametrize('seed,mx', [(51, 256), (52, 1024), (53, 40)])
+def test_features_match_oracle(seed, mx, eng10):
+    """FAST_ALGORITHM features on random content (8-bit range, 10-bit range saturating to 255 as the reference does,
+    and a low-contrast picture with many rounding ties), random CU shapes and neighbour sets."""
+    from test_oracle_features import random_feature_jobs
+    rng = np.random.default_rng(seed)
+    H, W = 256, 512
+    pic = rng.integers(0, mx, (H, W)).astype(np.int16)
+    pic[:, 256:] = (pic[:, 256:] // 8) * 8 % 256
+    jobs = random_feature_jobs(rng, H, W, 3000)
+    eng10.frame_begin(pic)
+    got = eng10.features_eval(jobs)
+    exp = O.features_batch(pic, jobs)
+    bad = [i for i in range(len(jobs)) if got[i].tobytes() != exp[i].tobytes()]
+    assert not bad, (len(bad), jobs[bad[0]]['cu'], got[bad[0]]['f'].tolist(), exp[bad[0]]['f'].tolist())
+
+
+def test_features_on_a_partitioned_picture(eng10):
+    """Config 4 shape of use: every CU of a random QT/MTT partition of a 416x240 picture, neighbours picked by the
+    host logic (vvc_intra_b200.features), checked against the oracle; plus the error behaviour."""
+    from test_host_features import random_partition, cu_lookup
+    from make_golden import synth_yuv
+    Y = synth_yuv(416, 240, 8)[0].astype(np.int16)
+    rng = np.random.default_rng(5)
+    cus = random_partition(rng, 416, 240)
+    get_cu = cu_lookup(cus, 416, 240)
+    jobs = []
+    for c in cus:
+        if vb.feature_gate(c['x'], c['y'], c['w'], c['h'], c['mt_depth']):
+            jobs.append(vb.feature_job(c['x'], c['y'], c['w'], c['h'], c['qt_depth'], c['mt_depth'],
+                                       vb.select_feature_neighbours(get_cu, c['x'], c['y'], c['w'], c['h'])))
+    jobs = np.array(jobs, vb.FEAT_JOB_DTYPE)
+    assert len(jobs) > 100
+    eng10.frame_begin(Y)
+    got = eng10.features_eval(jobs)
+    assert got.tobytes() == O.features_batch(Y, jobs).tobytes()
+    assert got['valid'].sum() > 50
+    bad = jobs[:1].copy()
+    bad['cu']['w'] = 12
+    with pytest.raises(vb.EngineError, match='malformed'):
+        eng10.features_eval(bad)
+    assert len(eng10.features_eval(jobs[:0])) == 0

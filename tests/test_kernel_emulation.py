@@ -108,3 +108,34 @@ def test_emulated_tu_kernel_matches_oracle_on_random_blocks(emul, bd, seed):
     for k in ('coeff', 'level', 'reco'):
         assert np.array_equal(out[k], exp[k]), k
     assert out['results'].tobytes() == exp['results'].tobytes()
+
+
+# ---- texture-measure kernels (vvcb_feat.cuh) -----------------------------------------------------------------
+def test_emulated_ctu_hads_kernel_matches_reference_records(emul):
+    _, recs = G.load_fixture('ref_10b_200x136_ctuhad')
+    hs = [r for r in recs if r['tag'] == 'H']
+    pic = np.zeros((136, 256), np.int16)            # pitch 256 > width 200
+    pic[:128, :128], pic[:128, 128:200], pic[128:, :128], pic[128:, 128:200] = [r['org'] for r in hs]
+    out = np.zeros(4, np.int32)
+    emul.emul_ctu_hads(pic.ctypes.data_as(C.c_void_p), 256, 200, 136, 128, out.ctypes.data_as(C.c_void_p))
+    assert out.tolist() == [r['result'] for r in hs]
+    rng = np.random.default_rng(3)
+    pic = rng.integers(0, 1024, (72, 192)).astype(np.int16)
+    out = np.zeros(6, np.int32)
+    emul.emul_ctu_hads(pic.ctypes.data_as(C.c_void_p), 192, 192, 72, 64, out.ctypes.data_as(C.c_void_p))
+    assert out.tolist() == O.ctu_hads_islice(pic, ctu=64).tolist()
+
+
+@pytest.mark.parametrize('seed,mx', [(41, 256), (42, 1024), (43, 40)])
+def test_emulated_features_kernel_matches_oracle(emul, seed, mx):
+    from test_oracle_features import random_feature_jobs
+    rng = np.random.default_rng(seed)
+    H, W = 128, 256
+    pic = rng.integers(0, mx, (H, W)).astype(np.int16)
+    pic[:, 128:] = (pic[:, 128:] // 8) * 8 % 256          # smoother half: ties in the rounded gradient mean
+    jobs = random_feature_jobs(rng, H, W, 120)
+    out = np.zeros(len(jobs), O.FEAT_RESULT_DTYPE)
+    emul.emul_features_eval(pic.ctypes.data_as(C.c_void_p), W, jobs.ctypes.data_as(C.c_void_p), len(jobs), out.ctypes.data_as(C.c_void_p))
+    exp = O.features_batch(pic, jobs)
+    bad = [i for i in range(len(jobs)) if out[i].tobytes() != exp[i].tobytes()]
+    assert not bad, (jobs[bad[0]]['cu'], out[bad[0]]['f'].tolist(), exp[bad[0]]['f'].tolist())

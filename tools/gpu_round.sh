@@ -1,0 +1,22 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, bench, ncu launch list of the bench command, full captures of the dominant kernels.
+# usage: tools/gpu_round.sh <tag> [skip-ncu]
+tag=${1:-r1}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"
+tail -15 gpurun_out/pytest_gpu_$tag.log
+python bench.py --steps 8 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"
+cat gpurun_out/bench_$tag.json | head -c 3500
+[ "$2" = "skip-ncu" ] && exit 0
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv \
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_$tag.log 2>&1; echo "ncu list rc=$?"
+python tools/profile_sweep.py --width 1920 --height 1080 --passes 2 > gpurun_out/prof_plain_$tag.log 2>&1 || exit 1
+# second pass of the sweep: 18 eval launches per pass in bucket order (class*3 + kind); 8x8 angular = launch 9, 16x8 angular = 12
+for k in 27:eval8x8ang 30:eval16x8ang 18:eval4x4ang; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:rmd_eval_kernel -s ${k%%:*} -c 1 -o gpurun_out/prof_${k##*:}_$tag -f \
+    python tools/profile_sweep.py --width 1920 --height 1080 --passes 2 > gpurun_out/ncu_full_${k##*:}_$tag.log 2>&1; echo "ncu ${k##*:} rc=$?"
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rmd_lists_kernel -s 1 -c 1 -o gpurun_out/prof_lists_$tag -f \
+  python tools/profile_sweep.py --width 1920 --height 1080 --passes 2 > gpurun_out/ncu_full_lists_$tag.log 2>&1; echo "ncu lists rc=$?"
+ls -la gpurun_out

@@ -67,6 +67,8 @@ def run(name, w, h, bits, qp, env, extra=()):
 def main():
     os.makedirs(os.path.join(ROOT, 'tests/golden'), exist_ok=True)
     lines = []
+    if len(sys.argv) > 1 and sys.argv[1] == '--extra':
+        return extra_fixtures(sys.argv[2:])
     # RMD visits (reference lines, predictions, SAD/SATD, mode bits, candidate lists) + sampled TU records
     lines.append(run('ref_8b_128x64_qp32', 128, 64, 8, 32,
                      dict(VVC_TRACE_VISIT_FIRST=3, VVC_TRACE_VISIT_STRIDE=60, VVC_TRACE_FULL_PRED=1,
@@ -81,6 +83,20 @@ def main():
                      extra=['--DepQuant=0', '--RDOQ=0', '--RDOQTS=0', '--SignHideFlag=0']))
     open(os.path.join(ROOT, 'tests/golden/MANIFEST.txt'), 'w').write(
         'Golden fixtures captured from the unmodified reference encoder by tools/make_golden.py\n' + '\n'.join(lines) + '\n')
+
+
+def extra_fixtures(which):
+    """Fixtures added after the first set; each is generated on its own (python tools/make_golden.py --extra NAME...) and
+    appended to MANIFEST.txt so that the earlier files keep their bytes."""
+    todo = {
+        # a16: EncCu::updateCtuDataISlice runs only under rate control (EL/EncGOP.cpp:1565); ragged CTUs (72 wide, 8 high)
+        'ref_10b_200x136_ctuhad': lambda n: run(n, 200, 136, 10, 32, dict(VVC_TRACE_VISIT_FIRST=0, VVC_TRACE_VISIT_STRIDE=1000000,
+                                                                         VVC_TRACE_MAX_VISITS=0, VVC_TRACE_TU_FIRST=0, VVC_TRACE_TU_STRIDE=100000000),
+                                                    extra=['--RateControl=1', '--TargetBitrate=400000']),
+    }
+    with open(os.path.join(ROOT, 'tests/golden/MANIFEST.txt'), 'a') as f:
+        for n in which or sorted(todo):
+            f.write(todo[n](n) + '\n')
 
 
 if __name__ == '__main__':

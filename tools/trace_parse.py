@@ -128,6 +128,9 @@ def parse_record(tag, payload):
         n = r['w'] * r['h']
         r['level'] = c.i32(n).reshape(r['h'], r['w'])
         r['resi'] = c.i16(n).reshape(r['h'], r['w'])
+    elif tag == 'H':
+        r['w'], r['h'], r['result'] = c.i32(), c.i32(), c.i32()
+        r['org'] = c.i16(r['w'] * r['h']).reshape(r['h'], r['w'])
     else:
         raise ValueError('unknown tag %r' % tag)
     c.done()

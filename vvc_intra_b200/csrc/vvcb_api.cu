@@ -8,6 +8,7 @@
 #include <new>
 #include "vvcb_rmd.cuh"
 #include "vvcb_tu.cuh"
+#include "vvcb_feat.cuh"
 #include "vvcb_romfill.h"
 
 // =====================================================================================================
@@ -47,6 +48,7 @@ struct vvcb_ctx {
   Rom* dRom;
   TrRom* dTrRom;
   void* dTu[7]; size_t capTu[7];    // TU scratch: jobs, resi, pred, coeff, level, reco, results
+  void* dFeat[2]; size_t capFeat[2]; // feature scratch: jobs / per-CTU sums, results
   int16_t* dOrig; int16_t* dReco;
   const int16_t* bOrig; const int16_t* bReco;   // planes in use (own or bound)
   int width, height, stride;        // planes share one pitch (in samples)
@@ -142,6 +144,7 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dSlotMajor);
   cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred); cudaFree(ctx->dTrRom);
   for (int i = 0; i < 7; i++) cudaFree(ctx->dTu[i]);
+  for (int i = 0; i < 2; i++) cudaFree(ctx->dFeat[i]);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->kev[i]);
   cudaStreamDestroy(ctx->stream);
@@ -459,6 +462,72 @@ extern "C" void vvcb_mts_preselect(const int32_t* sums, int n, int width, int he
     selected[i] = t ? 1 : 0;
     tests += t;
   }
+}
+
+static int feat_buf(vvcb_ctx* ctx, int i, size_t bytes)
+{
+  if (bytes > ctx->capFeat[i]) {
+    cudaFree(ctx->dFeat[i]); ctx->dFeat[i] = nullptr; ctx->capFeat[i] = 0;
+    CK(cudaMalloc(&ctx->dFeat[i], bytes));
+    ctx->capFeat[i] = bytes;
+  }
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_ctu_hads_islice(vvcb_ctx* ctx, int32_t* out, int n_ctus)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_ctu_hads_islice: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
+  const int perRow = (ctx->width + ctx->ctu - 1) / ctx->ctu, rows = (ctx->height + ctx->ctu - 1) / ctx->ctu;
+  if (!out || n_ctus != perRow * rows) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_ctu_hads_islice: the frame has %d CTUs", perRow * rows); return VVCB_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = feat_buf(ctx, 0, (size_t)n_ctus * sizeof(int32_t)))) return rc;
+  int32_t* d = static_cast<int32_t*>(ctx->dFeat[0]);
+  CK(cudaMemsetAsync(d, 0, (size_t)n_ctus * sizeof(int32_t), ctx->stream));
+  const int blocks = (ctx->width >> 3) * (ctx->height >> 3);
+  if (blocks > 0) {
+    ctu_hads_kernel<<<(blocks + 255) / 256, 256, 0, ctx->stream>>>(ctx->bOrig, ctx->stride, ctx->width, ctx->height, ctx->ctu, perRow, d);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(out, d, (size_t)n_ctus * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+
+static bool feat_cu_ok(const vvcb_ctx* ctx, const vvcb_feat_cu& c)
+{
+  return c.w >= 4 && c.h >= 4 && c.w <= kFeatMaxSide && c.h <= kFeatMaxSide && !(c.w & (c.w - 1)) && !(c.h & (c.h - 1)) &&
+         c.x >= 0 && c.y >= 0 && c.x + c.w <= ctx->width && c.y + c.h <= ctx->height;
+}
+
+extern "C" int vvcb_features_eval(vvcb_ctx* ctx, const vvcb_feat_job* jobs, int n, vvcb_feat_result* results)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (n < 0 || (n > 0 && (!jobs || !results))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_features_eval: bad argument"); return VVCB_ERR_ARG; }
+  if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_features_eval: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
+  if (n == 0) return VVCB_OK;
+  for (int i = 0; i < n; i++) {
+    bool ok = feat_cu_ok(ctx, jobs[i].cu) && jobs[i].n_neighbours <= 5;
+    for (int k = 0; ok && k < jobs[i].n_neighbours; k++) ok = feat_cu_ok(ctx, jobs[i].nb[k]);
+    if (!ok) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_features_eval: job %d is malformed (sizes are powers of two in 4..64 inside the picture, <= 5 neighbours)", i); return VVCB_ERR_ARG; }
+  }
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = feat_buf(ctx, 0, (size_t)n * sizeof(vvcb_feat_job)))) return rc;
+  if ((rc = feat_buf(ctx, 1, (size_t)n * sizeof(vvcb_feat_result)))) return rc;
+  CK(cudaMemcpyAsync(ctx->dFeat[0], jobs, (size_t)n * sizeof(vvcb_feat_job), cudaMemcpyHostToDevice, ctx->stream));
+  FeatParams P;
+  P.jobs = static_cast<const vvcb_feat_job*>(ctx->dFeat[0]); P.n = n; P.results = static_cast<vvcb_feat_result*>(ctx->dFeat[1]);
+  P.orig = ctx->bOrig; P.stride = ctx->stride;
+  const int grid = n < ctx->numSms * 16 ? n : ctx->numSms * 16;
+  features_kernel<<<grid, kFeatThreads, 0, ctx->stream>>>(P);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(results, ctx->dFeat[1], (size_t)n * sizeof(vvcb_feat_result), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
 }
 
 extern "C" int vvcb_dev_alloc(vvcb_ctx* ctx, size_t bytes, void** out)

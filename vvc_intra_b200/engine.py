@@ -38,6 +38,12 @@ TU_RESULT_DTYPE = np.dtype([('abs_sum_coeff', '<i4'), ('abs_sum_level', '<i4'), 
 assert TU_JOB_DTYPE.itemsize == 16 and TU_RESULT_DTYPE.itemsize == 16
 
 
+FEAT_CU_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('w', 'u1'), ('h', 'u1'), ('qt_depth', 'u1'), ('mt_depth', 'u1')])
+FEAT_JOB_DTYPE = np.dtype([('cu', FEAT_CU_DTYPE), ('n_neighbours', 'u1'), ('pad', 'u1', 7), ('nb', FEAT_CU_DTYPE, 5)])
+FEAT_RESULT_DTYPE = np.dtype([('f', '<i4', 27), ('valid', '<i4')])
+assert FEAT_JOB_DTYPE.itemsize == 56 and FEAT_RESULT_DTYPE.itemsize == 112
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -81,6 +87,8 @@ def load_library():
                                    C.c_void_p, C.c_void_p]
         L.vvcb_mts_preselect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vvcb_mts_preselect.restype = None
+        L.vvcb_ctu_hads_islice.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.vvcb_features_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.vvcb_frame_bind_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.vvcb_kernel_timing.argtypes = [C.c_void_p, C.c_int]
         L.vvcb_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
@@ -191,6 +199,20 @@ class IntraCostEngine:
         sel = np.zeros(len(sums), np.uint8)
         self._lib.vvcb_mts_preselect(_ptr(sums), len(sums), width, height, max_cand, _ptr(sel))
         return sel
+
+    # ---- texture measures
+    def ctu_hads_islice(self, width, height):
+        """vvcb_ctu_hads_islice for the frame given to frame_begin (width, height = its luma size)."""
+        n = -(-width // self.ctu_size) * -(-height // self.ctu_size)
+        out = np.zeros(n, np.int32)
+        self._ck(self._lib.vvcb_ctu_hads_islice(self._ctx, _ptr(out), n))
+        return out
+
+    def features_eval(self, jobs):
+        jobs = np.ascontiguousarray(jobs, FEAT_JOB_DTYPE)
+        out = np.zeros(len(jobs), FEAT_RESULT_DTYPE)
+        self._ck(self._lib.vvcb_features_eval(self._ctx, _ptr(jobs), len(jobs), _ptr(out)))
+        return out
 
     # ---- device-resident path (bench: kernels without the PCIe copies)
     def dev_alloc(self, nbytes):

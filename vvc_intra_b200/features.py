@@ -1,0 +1,67 @@
+"""Host logic around the FAST_ALGORITHM feature kernel (vvcb_features_eval): what the reference decides on the host
+before and after the pixel work.  Restates EL/EncCu.cpp:821-933 (gate and neighbour selection) and :1172-1216 (how the
+classifier's answer is applied).  The classifier itself is a CPython call into a pickled model the repository does not
+ship (BIN/TEST.py:14-24); `classifier_decision` takes the predicted class from the caller."""
+import numpy as np
+
+from .engine import FEAT_JOB_DTYPE
+
+# hard-coded in the reference (EL/EncCu.cpp:832-833), whatever the real picture size
+VIDEO_WIDTH, VIDEO_HEIGHT = 416, 240
+# GetPartition result -> split tried exclusively (EL/EncCu.cpp:1172-1195)
+PARTITION_OF_CLASS = ('ETM_INTRA', 'ETM_SPLIT_QT', 'ETM_SPLIT_BT_H', 'ETM_SPLIT_BT_V', 'ETM_SPLIT_TT_H', 'ETM_SPLIT_TT_V')
+
+
+def feature_gate(x, y, w, h, mt_depth, is_luma=True):
+    """True when the reference computes features for this CU (EL/EncCu.cpp:821-845)."""
+    if not is_luma:
+        return False
+    if not (h < 128 and x + w <= VIDEO_WIDTH and y + h <= VIDEO_HEIGHT):
+        return False
+    if mt_depth == 3:
+        return False
+    return not (h == 4 and w == 4)
+
+
+def select_feature_neighbours(get_cu, x, y, w, h):
+    """Neighbour CUs in the order the reference collects them (EL/EncCu.cpp:852-933).
+
+    get_cu(px, py) -> None or a dict(x, y, w, h, qt_depth, mt_depth): the coding structure's CU covering luma
+    position (px, py) (tempCS->getCU).  Returns the list of accepted neighbours (valid_num = its length)."""
+    out = []
+    left = get_cu(x - 1, y)
+    up = get_cu(x, y - 1)
+    left_up = get_cu(x - 1, y - 1)
+    if left is not None:
+        out.append(left)
+        left_down = get_cu(x - 1, y + left['h'] + 1)             # offset(-1, cuLeft->lheight() + 1), :873
+        if left_down is not None and left_down['y'] <= y + h:    # :876
+            out.append(left_down)
+    if up is not None:
+        out.append(up)
+        right_up = get_cu(x + up['w'] + 1, y - 1)                # offset(cuUp->lwidth() + 1, -1), :894
+        if right_up is not None and right_up['x'] < x + w:       # :897
+            out.append(right_up)
+    if left_up is not None:
+        if not (left_up['y'] + left_up['h'] > y or left_up['x'] + left_up['w'] > x):   # :910
+            out.append(left_up)
+    return out
+
+
+def feature_job(x, y, w, h, qt_depth, mt_depth, neighbours):
+    j = np.zeros(1, FEAT_JOB_DTYPE)[0]
+    j['cu'] = (x, y, w, h, qt_depth, mt_depth)
+    j['n_neighbours'] = len(neighbours)
+    for i, c in enumerate(neighbours):
+        j['nb'][i] = (c['x'], c['y'], c['w'], c['h'], c['qt_depth'], c['mt_depth'])
+    return j
+
+
+def classifier_decision(features, predicted_class):
+    """What xCompressCU does with GetPartition's answer (EL/EncCu.cpp:1172-1216): returns the only test mode to keep,
+    or None when the normal search runs (classifier not applicable: f26 >= 1 and 'no split' predicted, :1197)."""
+    if predicted_class is None or not 0 <= predicted_class < len(PARTITION_OF_CLASS):
+        return None
+    if features[26] >= 1 and predicted_class == 0:
+        return None
+    return PARTITION_OF_CLASS[predicted_class]
