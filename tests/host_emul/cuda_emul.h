@@ -58,6 +58,7 @@ static inline int atomicMax(int* p, int v)
   while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
   return old;
 }
+static inline long long __double_as_longlong(double a) { long long r; __builtin_memcpy(&r, &a, 8); return r; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }

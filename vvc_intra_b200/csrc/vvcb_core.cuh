@@ -214,18 +214,36 @@ struct Rom {
 };
 
 // ---- register-resident Walsh-Hadamard pieces -------------------------------------------------------
-template <int N> VHD void wht_rows(int (&d)[N][N])
+// C-point transform of each of the R rows
+template <int R, int C> VHD void wht_rows_rc(int (&d)[R][C])
 {
 #pragma unroll
-  for (int y = 0; y < N; y++)
+  for (int y = 0; y < R; y++)
 #pragma unroll
-    for (int len = 1; len < N; len <<= 1)
+    for (int len = 1; len < C; len <<= 1)
 #pragma unroll
-      for (int i = 0; i < N; i += 2 * len)
+      for (int i = 0; i < C; i += 2 * len)
 #pragma unroll
         for (int x = i; x < i + len; x++) {
           const int a = d[y][x], b = d[y][x + len];
           d[y][x] = a + b; d[y][x + len] = a - b;
+        }
+}
+template <int N> VHD void wht_rows(int (&d)[N][N]) { wht_rows_rc<N, N>(d); }
+
+// R-point transform of each of the C columns (all stages)
+template <int R, int C> VHD void wht_cols_rc(int (&d)[R][C])
+{
+#pragma unroll
+  for (int x = 0; x < C; x++)
+#pragma unroll
+    for (int len = 1; len < R; len <<= 1)
+#pragma unroll
+      for (int i = 0; i < R; i += 2 * len)
+#pragma unroll
+        for (int y = i; y < i + len; y++) {
+          const int a = d[y][x], b = d[y + len][x];
+          d[y][x] = a + b; d[y + len][x] = a - b;
         }
 }
 
@@ -252,21 +270,7 @@ template <int N> VHD int wht_cols_abs_sum(int (&d)[N][N])
   return 2 * s;
 }
 
-// full transform (all stages), coefficients left in d (needed when two units form one tile)
-template <int N> VHD void wht_cols(int (&d)[N][N])
-{
-#pragma unroll
-  for (int x = 0; x < N; x++)
-#pragma unroll
-    for (int len = 1; len < N; len <<= 1)
-#pragma unroll
-      for (int i = 0; i < N; i += 2 * len)
-#pragma unroll
-        for (int y = i; y < i + len; y++) {
-          const int a = d[y][x], b = d[y + len][x];
-          d[y][x] = a + b; d[y + len][x] = a - b;
-        }
-}
+template <int N> VHD void wht_cols(int (&d)[N][N]) { wht_cols_rc<N, N>(d); }
 
 // (int)(s / sqrt(N) * 2) of CL/RdCost.cpp:2452,2589,2662,2741 as one multiply; exactness over the
 // reachable range of s is proven exhaustively in tests/test_oracle_golden.py.
@@ -288,13 +292,13 @@ VHD int clip_bd(int v, int maxv) { return vmin(vmax(v, 0), maxv); }
 // Angular prediction of the unit whose origin is (c0, r0) in the main/side frame.  ml points at the
 // slot's main line so that ml[t] == refMain0[t] (may be indexed with negative t); side points at
 // refSide0.  Output in the main/side frame: q[r][c].
-template <int S> VHD void pred_angular_unit(const int16_t* ml, const int16_t* side, const ModeParam& p, int mrl,
-                                            int mw, int mh, int c0, int r0, const uint32_t* filt, int maxv, int (&q)[S][S])
+template <int R, int C> VHD void pred_angular_unit(const int16_t* ml, const int16_t* side, const ModeParam& p, int mrl,
+                                                   int mw, int mh, int c0, int r0, const uint32_t* filt, int maxv, int (&q)[R][C])
 {
   const int angle = p.angle;
   const uint32_t* ftab = filt + (p.interp ? 32 : 0);
 #pragma unroll
-  for (int i = 0; i < S; i++) {
+  for (int i = 0; i < R; i++) {
     const int r   = r0 + i;
     const int pos = angle * (r + 1 + mrl);
     const int dInt = pos >> 5, dFrac = pos & 31;
@@ -302,11 +306,11 @@ template <int S> VHD void pred_angular_unit(const int16_t* ml, const int16_t* si
     const int f0 = (int)(int8_t)(fw & 0xff), f1 = (int)(int8_t)((fw >> 8) & 0xff);
     const int f2 = (int)(int8_t)((fw >> 16) & 0xff), f3 = (int)(int8_t)(fw >> 24);
     const int16_t* m = ml + mrl + dInt + c0;
-    int t[S + 3];
+    int t[C + 3];
 #pragma unroll
-    for (int j = 0; j < S + 3; j++) t[j] = m[j];
+    for (int j = 0; j < C + 3; j++) t[j] = m[j];
 #pragma unroll
-    for (int j = 0; j < S; j++)
+    for (int j = 0; j < C; j++)
       q[i][j] = clip_bd((f0 * t[j] + f1 * t[j + 1] + f2 * t[j + 2] + f3 * t[j + 3] + 32) >> 6, maxv);
   }
   if (p.pdpc) {
@@ -315,12 +319,12 @@ template <int S> VHD void pred_angular_unit(const int16_t* ml, const int16_t* si
       const int lim = vmin(3 << scale, mw);
       const int tl = ml[0];
 #pragma unroll
-      for (int j = 0; j < S; j++) {
+      for (int j = 0; j < C; j++) {
         const int c = c0 + j;
         if (c < lim) {
           const int wL = 32 >> ((2 * c) >> scale);
 #pragma unroll
-          for (int i = 0; i < S; i++)
+          for (int i = 0; i < R; i++)
             q[i][j] = clip_bd(q[i][j] + ((wL * (side[1 + r0 + i] - tl) + 32) >> 6), maxv);
         }
       }
@@ -328,13 +332,13 @@ template <int S> VHD void pred_angular_unit(const int16_t* ml, const int16_t* si
       const int scale = p.ang_scale;
       const int lim = vmin(3 << scale, mw);
 #pragma unroll
-      for (int j = 0; j < S; j++) {
+      for (int j = 0; j < C; j++) {
         const int c = c0 + j;
         if (c < lim) {
           const int wL  = 32 >> ((2 * c) >> scale);
           const int off = (256 + (c + 1) * (int)p.inv_angle) >> 9;
 #pragma unroll
-          for (int i = 0; i < S; i++) {
+          for (int i = 0; i < R; i++) {
             const int l = side[r0 + i + off + 1];
             q[i][j] = q[i][j] + ((wL * (l - q[i][j]) + 32) >> 6);
           }
@@ -345,19 +349,19 @@ template <int S> VHD void pred_angular_unit(const int16_t* ml, const int16_t* si
 }
 
 // Planar / DC (+PDPC) of the unit at block position (x0, y0); output in block orientation b[y][x].
-template <int S> VHD void pred_planar_dc_unit(const int16_t* top, const int16_t* left, int kind, bool pdpc, int dc,
-                                              int lw, int lh, int x0, int y0, int (&b)[S][S])
+template <int R, int C> VHD void pred_planar_dc_unit(const int16_t* top, const int16_t* left, int kind, bool pdpc, int dc,
+                                                     int lw, int lh, int x0, int y0, int (&b)[R][C])
 {
   const int w = 1 << lw, h = 1 << lh;
   const int tr = top[w + 1], bl = left[h + 1];
   const int scale = (lw + lh - 2) >> 2;
 #pragma unroll
-  for (int i = 0; i < S; i++) {
+  for (int i = 0; i < R; i++) {
     const int y = y0 + i;
     const int l = left[y + 1];
     const int wT = 32 >> vmin(31, (y << 1) >> scale);
 #pragma unroll
-    for (int j = 0; j < S; j++) {
+    for (int j = 0; j < C; j++) {
       const int x = x0 + j;
       const int t = top[x + 1];
       int v;
@@ -446,32 +450,7 @@ VHD int mip_reduced_sample(const MipSlot& m, const MipGeom& g, int w, int h, int
   return clip_bd((acc >> m.shift) + m.inOff, maxv);
 }
 
-// ---- candidate lists (lists kernel) -----------------------------------------------------------------
-struct CandList {
-  vvcb_mode m[VVCB_MAX_LIST + 2];
-  double    c[VVCB_MAX_LIST + 2];
-  int       n;
-};
-
-VHD vvcb_mode mk_mode(int mip, int mrl, int mode)
-{
-  vvcb_mode m; m.mip = (uint8_t)mip; m.mrl = (uint8_t)mrl; m.mode = (uint8_t)mode; m.pad = 0; return m;
-}
-VHD bool same_mode(vvcb_mode a, vvcb_mode b) { return a.mip == b.mip && a.mrl == b.mrl && a.mode == b.mode; }
-
-// updateCandList (CL/UnitTools.h:261-307): stable bounded insertion, strict '<'
-VHD void cand_push(CandList& L, vvcb_mode m, double cost, int cap)
-{
-  const int live = L.n < cap ? L.n : cap;
-  int pos = live;
-  while (pos > 0 && cost < L.c[pos - 1]) pos--;
-  int last;
-  if (L.n >= cap) { if (pos == live) return; last = live - 1; }
-  else            { last = L.n; L.n++; }
-  for (int i = last; i > pos; i--) { L.m[i] = L.m[i - 1]; L.c[i] = L.c[i - 1]; }
-  L.m[pos] = m; L.c[pos] = cost;
-}
-
+// ---- mode bits (lists kernel) -----------------------------------------------------------------------
 VHD int trunc_bin_len(int symbol, int numSymbols)
 {
   const int thresh = vlog2(numSymbols);

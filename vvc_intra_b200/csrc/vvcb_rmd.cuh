@@ -301,17 +301,19 @@ __device__ void build_projected_line(int16_t* buf, const WarpSmem& sm, const Slo
   }
 }
 
-// residual of one unit against the original block, SAD accumulated.  TRANSPOSED: the prediction q is in the
+// residual of one R x C piece against the original block, SAD accumulated.  TRANSPOSED: the prediction q is in the
 // main/side frame of a horizontal mode, i.e. q[i][j] predicts block sample (y0 + j, x0 + i); SAD and the sum of
 // absolute Hadamard coefficients are invariant under transposition, so the residual stays in that frame.
-template <int S, bool TRANSPOSED>
-__device__ __forceinline__ void residual_unit(const int16_t* org, int stride, const int (&q)[S][S], int (&d)[S][S], int& sad)
+// org points at block sample (y0, x0) of the piece.
+template <int R, int C, bool TRANSPOSED>
+__device__ __forceinline__ void residual_unit(const int16_t* org, int stride, const int (&q)[R][C], int (&d)[R][C], int& sad)
 {
+  constexpr int ROWS = TRANSPOSED ? C : R, COLS = TRANSPOSED ? R : C;   // extent of the piece in the picture
 #pragma unroll
-  for (int r = 0; r < S; r++) {
+  for (int r = 0; r < ROWS; r++) {
     const int16_t* row = org + r * stride;
 #pragma unroll
-    for (int c = 0; c < S; c += 4) {
+    for (int c = 0; c < COLS; c += 4) {
       const uint2 v = *reinterpret_cast<const uint2*>(row + c);       // CU positions are multiples of 4 samples
       const int o0 = (int)(int16_t)(v.x & 0xffff), o1 = (int)(int16_t)(v.x >> 16);
       const int o2 = (int)(int16_t)(v.y & 0xffff), o3 = (int)(int16_t)(v.y >> 16);
@@ -330,51 +332,32 @@ __device__ __forceinline__ void residual_unit(const int16_t* org, int stride, co
   }
 }
 
-template <int S>
-__device__ __forceinline__ void store_pred(int16_t* out, int w, int x0, int y0, bool transposed, const int (&q)[S][S])
+// q[i][j] is block sample (y0 + i, x0 + j), or (y0 + j, x0 + i) when transposed
+template <int R, int C>
+__device__ __forceinline__ void store_pred(int16_t* out, int w, int x0, int y0, bool transposed, const int (&q)[R][C])
 {
 #pragma unroll
-  for (int i = 0; i < S; i++)
+  for (int i = 0; i < R; i++)
 #pragma unroll
-    for (int j = 0; j < S; j++) {
+    for (int j = 0; j < C; j++) {
       if (transposed) out[(y0 + j) * w + x0 + i] = (int16_t)q[i][j];
       else            out[(y0 + i) * w + x0 + j] = (int16_t)q[i][j];
     }
 }
 
-// SATD contribution of this lane's unit(s) once the residual d is in registers (rows already transformed
-// for S == 8 by the caller).  TILE: 0 4x4, 1 8x4, 2 4x8 (handled by the S == 4 path), 3 8x8, 4 16x8, 5 8x16.
-template <int TILE>
-__device__ __forceinline__ int satd_unit8(int (&d)[8][8], int partnerMask, bool owner)
-{
-  wht_rows<8>(d);
-  if (TILE == 3) return (wht_cols_abs_sum<8>(d) + 2) >> 2;                    // CL/RdCost.cpp:2306
-  // 16x8 / 8x16: the partner lane holds the other 8x8 half; the last butterfly stage across the halves is
-  // folded into the absolute sum: |a+b| + |a-b| = 2 max(|a|, |b|)
-  wht_cols<8>(d);
-  int t = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++)
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int mine = vabs(d[i][j]);
-      const int other = __shfl_xor_sync(0xffffffffu, mine, partnerMask);
-      t += vmax(mine, other);
-    }
-  return owner ? satd_norm_rect(2 * t, true) : 0;                             // CL/RdCost.cpp:2452, :2589
-}
-
 // =====================================================================================================
 // prediction of one unit per kind.  q is produced in the frame named by `transposed`.
 // =====================================================================================================
-template <int S>
+// (x0, y0): block position of the lane's unit; rOff: first row of the piece inside the unit, counted along the side
+// direction of the prediction frame (block rows for vertical modes, block columns for horizontal ones)
+template <int R, int C>
 __device__ __forceinline__ void predict_angular(const WarpSmem& sm, const int16_t* projected, const SlotInfo& s, const Shape& sh,
-                                                const uint32_t* filt, int bd, int x0, int y0, int (&q)[S][S])
+                                                const uint32_t* filt, int bd, int x0, int y0, int rOff, int (&q)[R][C])
 {
   const bool ver = s.p.is_ver;
   const int mw = ver ? sh.w : sh.h, mh = ver ? sh.h : sh.w;
   const int16_t* ml = s.p.angle < 0 ? projected + mh : sm.lines[s.set][ver ? 0 : 1];
-  pred_angular_unit<S>(ml, sm.lines[s.set][ver ? 1 : 0], s.p, s.mrl, mw, mh, ver ? x0 : y0, ver ? y0 : x0, filt, (1 << bd) - 1, q);
+  pred_angular_unit<R, C>(ml, sm.lines[s.set][ver ? 1 : 0], s.p, s.mrl, mw, mh, ver ? x0 : y0, (ver ? y0 : x0) + rOff, filt, (1 << bd) - 1, q);
 }
 
 // MIP: first interpolation pass of one slot into shared memory (CL/MatrixIntraPrediction.cpp:469-567,
@@ -421,21 +404,21 @@ __device__ void build_mip_planes(int16_t* red, int16_t* plane, const Rom& rom, c
   }
 }
 
-template <int S>
+template <int R, int C>
 __device__ __forceinline__ void predict_mip(const WarpSmem& sm, const int16_t* plane, const MipGeom& mg, const Shape& sh,
-                                            int x0, int y0, int (&q)[S][S])
+                                            int x0, int y0, int (&q)[R][C])
 {
   const int16_t* top = sm.lines[0][0];
   const int16_t* left = sm.lines[0][1];
   if (sh.h > sh.w) {
     // second pass vertical; plane[ry * w + x] holds the rows that carry reduced samples
 #pragma unroll
-    for (int i = 0; i < S; i++) {
+    for (int i = 0; i < R; i++) {
       const int y = y0 + i;
       const int ry = y >> mg.lgUpV, k = (y & (mg.upV - 1)) + 1;
       const int16_t* rowB = plane + (ry << sh.lw) + x0;
 #pragma unroll
-      for (int j = 0; j < S; j++) {
+      for (int j = 0; j < C; j++) {
         const int before = ry == 0 ? top[1 + x0 + j] : rowB[j - sh.w];
         q[i][j] = ((mg.upV - k) * before + k * rowB[j] + (mg.upV >> 1)) >> mg.lgUpV;
       }
@@ -443,11 +426,11 @@ __device__ __forceinline__ void predict_mip(const WarpSmem& sm, const int16_t* p
   } else {
     // second pass horizontal; plane[y * redW + rx] holds the columns that carry reduced samples
 #pragma unroll
-    for (int i = 0; i < S; i++) {
+    for (int i = 0; i < R; i++) {
       const int y = y0 + i;
       const int16_t* rowP = plane + (y << mg.lgRedW);
 #pragma unroll
-      for (int j = 0; j < S; j++) {
+      for (int j = 0; j < C; j++) {
         const int x = x0 + j;
         const int rx = x >> mg.lgUpH, k = (x & (mg.upH - 1)) + 1;
         const int before = rx == 0 ? left[1 + y] : rowP[rx - 1];
@@ -544,16 +527,55 @@ __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
       int sad = 0, satd = 0;
       const bool transposed = KIND == KIND_ANG && !s.p.is_ver;
       if constexpr (S == 8) {
+        // An 8x8 unit is processed as two 4x8 halves by the same loop body (kept rolled: the fully unrolled unit was
+        // > 64 KB of code and instruction-fetch bound, profiles/r1e).  Rows and the first two column stages of the
+        // Hadamard run inside a half; the column stage across the halves is folded into the absolute sum,
+        // |a+b| + |a-b| = 2 max(|a|, |b|); for 16x8 / 8x16 tiles the stage across the two units of the tile is a real
+        // butterfly with the partner lane.
         const int ux = u & (sh.unitsX - 1), uy = u >> sh.lgTilesX;
         const int x0 = ux * 8, y0 = uy * 8;
-        int q[8][8], d[8][8];
-        if (KIND == KIND_ANG)      predict_angular<8>(sm, scratch, s, sh, sFilt, P.bd, x0, y0, q);
-        else if (KIND == KIND_MIP) predict_mip<8>(sm, scratch + mip_plane_offset(mg, sh), mg, sh, x0, y0, q);
-        else pred_planar_dc_unit<8>(sm.lines[s.set][0], sm.lines[s.set][1], s.kind, s.p.pdpc, dc, sh.lw, sh.lh, x0, y0, q);
-        if (P.predOut && act) store_pred<8>(P.predOut + (size_t)slot * sh.w * sh.h, sh.w, x0, y0, transposed, q);
-        if (transposed) residual_unit<8, true>(org + y0 * P.stride + x0, P.stride, q, d, sad);
-        else            residual_unit<8, false>(org + y0 * P.stride + x0, P.stride, q, d, sad);
-        satd = satd_unit8<TILE>(d, TILE == 4 ? 1 : sh.unitsX, TILE == 4 ? (ux & 1) == 0 : (uy & 1) == 0);
+        const int partnerMask = TILE == 4 ? 1 : sh.unitsX;
+        const bool owner = TILE == 4 ? (ux & 1) == 0 : (uy & 1) == 0;
+        int c0[4][8];
+        int t = 0;
+#pragma unroll 1
+        for (int k = 0; k < 2; k++) {
+          int q[4][8], d[4][8];
+          const int hx = transposed ? x0 + 4 * k : x0, hy = transposed ? y0 : y0 + 4 * k;   // picture origin of the half
+          if (KIND == KIND_ANG)      predict_angular<4, 8>(sm, scratch, s, sh, sFilt, P.bd, x0, y0, 4 * k, q);
+          else if (KIND == KIND_MIP) predict_mip<4, 8>(sm, scratch + mip_plane_offset(mg, sh), mg, sh, hx, hy, q);
+          else pred_planar_dc_unit<4, 8>(sm.lines[s.set][0], sm.lines[s.set][1], s.kind, s.p.pdpc, dc, sh.lw, sh.lh, hx, hy, q);
+          if (P.predOut && act) store_pred<4, 8>(P.predOut + (size_t)slot * sh.w * sh.h, sh.w, hx, hy, transposed, q);
+          if (transposed) residual_unit<4, 8, true>(org + hy * P.stride + hx, P.stride, q, d, sad);
+          else            residual_unit<4, 8, false>(org + hy * P.stride + hx, P.stride, q, d, sad);
+          wht_rows_rc<4, 8>(d);
+          wht_cols_rc<4, 8>(d);
+          if (TILE != 3) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const int other = __shfl_xor_sync(0xffffffffu, d[i][j], partnerMask);
+                d[i][j] = owner ? d[i][j] + other : d[i][j] - other;
+              }
+          }
+          if (k == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+              for (int j = 0; j < 8; j++) c0[i][j] = vabs(d[i][j]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+              for (int j = 0; j < 8; j++) t += vmax(c0[i][j], vabs(d[i][j]));
+          }
+        }
+        if (TILE == 3) satd = (2 * t + 2) >> 2;                                // CL/RdCost.cpp:2306
+        else {
+          t += __shfl_xor_sync(0xffffffffu, t, partnerMask);
+          satd = owner ? satd_norm_rect(2 * t, true) : 0;                      // CL/RdCost.cpp:2452, :2589
+        }
       } else {
         // 4xN / Nx4 shapes: a lane owns one SATD tile = one (4x4) or two (8x4, 4x8) 4x4 units
         const int tx = u & ((1 << sh.lgTilesX) - 1), ty = u >> sh.lgTilesX;
@@ -564,12 +586,12 @@ __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
           const int x0 = tx * (TILE == 1 ? 8 : 4) + (TILE == 1 ? 4 * k : 0);
           const int y0 = ty * (TILE == 2 ? 8 : 4) + (TILE == 2 ? 4 * k : 0);
           int q[4][4], d[4][4];
-          if (KIND == KIND_ANG)      predict_angular<4>(sm, scratch, s, sh, sFilt, P.bd, x0, y0, q);
-          else if (KIND == KIND_MIP) predict_mip<4>(sm, scratch + mip_plane_offset(mg, sh), mg, sh, x0, y0, q);
-          else pred_planar_dc_unit<4>(sm.lines[s.set][0], sm.lines[s.set][1], s.kind, s.p.pdpc, dc, sh.lw, sh.lh, x0, y0, q);
-          if (P.predOut && act) store_pred<4>(P.predOut + (size_t)slot * sh.w * sh.h, sh.w, x0, y0, transposed, q);
-          if (transposed) residual_unit<4, true>(org + y0 * P.stride + x0, P.stride, q, d, sad);
-          else            residual_unit<4, false>(org + y0 * P.stride + x0, P.stride, q, d, sad);
+          if (KIND == KIND_ANG)      predict_angular<4, 4>(sm, scratch, s, sh, sFilt, P.bd, x0, y0, 0, q);
+          else if (KIND == KIND_MIP) predict_mip<4, 4>(sm, scratch + mip_plane_offset(mg, sh), mg, sh, x0, y0, q);
+          else pred_planar_dc_unit<4, 4>(sm.lines[s.set][0], sm.lines[s.set][1], s.kind, s.p.pdpc, dc, sh.lw, sh.lh, x0, y0, q);
+          if (P.predOut && act) store_pred<4, 4>(P.predOut + (size_t)slot * sh.w * sh.h, sh.w, x0, y0, transposed, q);
+          if (transposed) residual_unit<4, 4, true>(org + y0 * P.stride + x0, P.stride, q, d, sad);
+          else            residual_unit<4, 4, false>(org + y0 * P.stride + x0, P.stride, q, d, sad);
           wht_rows<4>(d);
           if (TILE == 0) {
             satd = (wht_cols_abs_sum<4>(d) + 1) >> 1;                       // CL/RdCost.cpp:2209
@@ -632,15 +654,6 @@ __global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
 __constant__ uint8_t cFastModes[6][6] = {
   { 3, 3, 3, 3, 2, 2 }, { 3, 3, 3, 3, 3, 2 }, { 3, 3, 3, 3, 3, 2 }, { 3, 3, 3, 3, 3, 2 }, { 2, 3, 3, 3, 3, 2 }, { 2, 2, 2, 2, 2, 3 } };
 
-__device__ void store_list(const CandList& L, int32_t* n, vvcb_mode* m, double* c, int cap)
-{
-  *n = L.n;
-  for (int i = 0; i < cap; i++) {
-    if (i < L.n) { m[i] = L.m[i]; if (c) c[i] = L.c[i]; }
-    else         { m[i] = mk_mode(0, 0, 0); if (c) c[i] = 0.0; }
-  }
-}
-
 constexpr int kListThreads = 128;
 
 // Slot-major scratch -> per-visit detail tables (only when the caller asked for details): a shared-memory tile
@@ -669,129 +682,208 @@ __global__ void __launch_bounds__(256) rmd_detail_kernel(const vvcb_rmd_visit* v
   }
 }
 
+// ---- candidate lists in shared memory: entry i of thread t lives at [i * kListThreads + t] (conflict-free, and no
+// per-thread local-memory arrays: profiles/r1e showed the local-memory version waiting on the long scoreboard)
+constexpr int kRdCap = VVCB_MAX_LIST + 2, kHadCap = VVCB_MAX_HAD_LIST;
+
+struct SmList { uint32_t* m; double* c; int n; };
+
+// vvcb_mode {mip, mrl, mode, pad} as one little-endian word
+__device__ __forceinline__ uint32_t pack_mode(int mip, int mrl, int mode) { return (uint32_t)mip | ((uint32_t)mrl << 8) | ((uint32_t)mode << 16); }
+
+// updateCandList (CL/UnitTools.h:261-307): stable bounded insertion, strict '<'
+__device__ __forceinline__ void sm_push(SmList& L, uint32_t m, double cost, int cap)
+{
+  const int live = L.n < cap ? L.n : cap;
+  int pos = live;
+  while (pos > 0 && cost < L.c[(pos - 1) * kListThreads]) pos--;
+  int last;
+  if (L.n >= cap) { if (pos == live) return; last = live - 1; }
+  else            { last = L.n; L.n++; }
+  for (int i = last; i > pos; i--) { L.m[i * kListThreads] = L.m[(i - 1) * kListThreads]; L.c[i * kListThreads] = L.c[(i - 1) * kListThreads]; }
+  L.m[pos * kListThreads] = m; L.c[pos * kListThreads] = cost;
+}
+
+__device__ void store_list_detail(const SmList& L, int32_t* n, vvcb_mode* m, double* c, int cap)
+{
+  *n = L.n;
+  for (int i = 0; i < cap; i++) {
+    reinterpret_cast<uint32_t*>(m)[i] = i < L.n ? L.m[i * kListThreads] : 0u;
+    c[i] = i < L.n ? L.c[i * kListThreads] : 0.0;
+  }
+}
+
 // One thread per visit: EL/IntraSearch.cpp:489-802 minus the predictions (already reduced to SAD/SATD, read from
-// the slot-major scratch: coalesced across the visits of a warp whenever they look at the same slot).
+// the slot-major scratch: coalesced across the visits of a warp whenever they look at the same slot).  The result
+// structs are written by the whole warp, one visit after the other, so that every store is a full line.
 __global__ void __launch_bounds__(kListThreads) rmd_lists_kernel(const vvcb_rmd_visit* visits, int n, int ctu, vvcb_rmd_result* results,
                                                                  vvcb_rmd_detail* details, const uint32_t* sadSM, const uint32_t* satdSM)
 {
-  const int vi = blockIdx.x * blockDim.x + threadIdx.x;
-  if (vi >= n) return;
-  const vvcb_rmd_visit v = visits[vi];
-  vvcb_rmd_result& R = results[vi];
-  const int w = 1 << v.log2w, h = 1 << v.log2h;
-  const bool mipEnabled = !(v.flags & VVCB_VISIT_NO_MIP);
-  const int numMip = visit_num_mip(v);
-  const bool testMip = numMip > 0;
-  const bool mrlAllowed = visit_mrl_allowed(v, ctu);
-  const uint32_t* mySad = sadSM + vi;
-  const uint32_t* mySatd = satdSM + vi;
-  R.pad = 0;
-  vvcb_rmd_detail* D = details ? details + vi : nullptr;
+  __shared__ double   sRdC[kRdCap * kListThreads], sHadC[kHadCap * kListThreads];
+  __shared__ uint32_t sRdM[kRdCap * kListThreads], sHadM[kHadCap * kListThreads];
+  __shared__ int      sCount[3 * kListThreads];              // n_rd, n_had, n_final per thread
+  __shared__ uint8_t  sParent[8 * kListThreads];
+  const int tid = threadIdx.x;
+  const int vi = blockIdx.x * blockDim.x + tid;
+  const bool live = vi < n;
+  SmList rd, had;
+  rd.m = sRdM + tid; rd.c = sRdC + tid; rd.n = 0;
+  had.m = sHadM + tid; had.c = sHadC + tid; had.n = 0;
+  if (live) {
+    const vvcb_rmd_visit v = visits[vi];
+    const int w = 1 << v.log2w, h = 1 << v.log2h;
+    const bool mipEnabled = !(v.flags & VVCB_VISIT_NO_MIP);
+    const int numMip = visit_num_mip(v);
+    const bool testMip = numMip > 0;
+    const bool mrlAllowed = visit_mrl_allowed(v, ctu);
+    const uint32_t* mySad = sadSM + vi;
+    const uint32_t* mySatd = satdSM + vi;
+    vvcb_rmd_detail* D = details ? details + vi : nullptr;
 
-  auto dist_of = [&](int slot) -> double {
-    const uint64_t sad = mySad[(size_t)slot * n], satd = mySatd[(size_t)slot * n];
-    return (double)(sad * 2 < satd ? sad * 2 : satd);                        // :515
-  };
-  auto cost_of = [&](int slot, bool isMip, int mrl, int mode) -> double {
-    const uint64_t bits = mode_bits(v.rates, v.mpm, w, h, mrlAllowed, mipEnabled, isMip, mrl, mode);
-    return __dadd_rn(dist_of(slot), __dmul_rn((double)bits, v.sqrt_lambda)); // :526, no FMA contraction
-  };
+    auto dist_of = [&](int slot) -> double {
+      const uint64_t sad = mySad[(size_t)slot * n], satd = mySatd[(size_t)slot * n];
+      return (double)(sad * 2 < satd ? sad * 2 : satd);                        // :515
+    };
+    auto cost_of = [&](double dist, bool isMip, int mrl, int mode) -> double {
+      const uint64_t bits = mode_bits(v.rates, v.mpm, w, h, mrlAllowed, mipEnabled, isMip, mrl, mode);
+      return __dadd_rn(dist, __dmul_rn((double)bits, v.sqrt_lambda));          // :526, no FMA contraction
+    };
 
-  int K = cFastModes[v.log2w - 2][v.log2h - 2];
-  if (testMip) K += vmax(K, vlog2(vmin(w, h)) - 1);                          // :472
-  const int numHad = testMip ? 6 : 3;
-  CandList rd, had;
-  rd.n = 0; had.n = 0;
-  uint64_t checked0 = 0, checked1 = 0;                                       // bSatdChecked
-  for (int m = 0; m < VVCB_NUM_LUMA_MODE; m++) {                             // :489-532
-    if (m > 1 && (m & 1)) continue;
-    if (m < 64) checked0 |= 1ull << m; else checked1 |= 1ull << (m - 64);
-    cand_push(rd, mk_mode(0, 0, m), cost_of(m, false, 0, m), K);
-    cand_push(had, mk_mode(0, 0, m), dist_of(m), numHad);
-  }
-  uint8_t parent[VVCB_MAX_LIST];
-  for (int i = 0; i < K; i++) parent[i] = rd.m[i].mode;
-  for (int i = 0; i < K; i++) {                                              // :577-623
-    const int pm = parent[i];
-    if (pm > 2 && pm < 66)
-      for (int dlt = -1; dlt <= 1; dlt += 2) {
-        const int m = pm + dlt;
-        const bool done = m < 64 ? (checked0 >> m) & 1 : (checked1 >> (m - 64)) & 1;
-        if (done) continue;
-        cand_push(rd, mk_mode(0, 0, m), cost_of(m, false, 0, m), K);
-        cand_push(had, mk_mode(0, 0, m), dist_of(m), numHad);
-        if (m < 64) checked0 |= 1ull << m; else checked1 |= 1ull << (m - 64);
-      }
-  }
-  if (mrlAllowed)                                                            // :635-681
-    for (int li = 0; li < 2; li++)
-      for (int i = 1; i < 6; i++) {
-        const int slot = (li ? VVCB_SLOT_MRL3 : VVCB_SLOT_MRL1) + i - 1;
-        const int mrl = li ? 3 : 1;
-        cand_push(rd, mk_mode(0, mrl, v.mpm[i]), cost_of(slot, false, mrl, v.mpm[i]), K);
-        cand_push(had, mk_mode(0, mrl, v.mpm[i]), dist_of(slot), numHad);
-      }
-  if (D) {
-    store_list(rd, &D->n_reg, D->reg_mode, D->reg_cost, VVCB_MAX_LIST);
-    store_list(had, &D->n_reg_had, D->reg_had_mode, D->reg_had_cost, VVCB_MAX_HAD_LIST);
-  }
-
-  if (testMip) {                                                             // :704-751
-    double c3[6];                                                            // costs of MIP modes 3,4,5 and their transposes
-    const int off = numMip / 2;
-    for (int m = 0; m < numMip; m++) {
-      const int slot = VVCB_SLOT_MIP + m;
-      const double c = cost_of(slot, true, 0, m);
-      if (m >= 3 && m <= 5) c3[m - 3] = c;
-      if (m >= 3 + off && m <= 5 + off) c3[3 + m - 3 - off] = c;
-      cand_push(rd, mk_mode(1, 0, m), c, K + 1);
-      cand_push(had, mk_mode(1, 0, m), __dmul_rn(0.8, dist_of(slot)), numHad);
+    int K = cFastModes[v.log2w - 2][v.log2h - 2];
+    if (testMip) K += vmax(K, vlog2(vmin(w, h)) - 1);                          // :472
+    const int numHad = testMip ? 6 : 3;
+    uint64_t checked0 = 0, checked1 = 0;                                       // bSatdChecked
+    for (int m = 0; m < VVCB_NUM_LUMA_MODE; m++) {                             // :489-532
+      if (m > 1 && (m & 1)) continue;
+      if (m < 64) checked0 |= 1ull << m; else checked1 |= 1ull << (m - 64);
+      const double dist = dist_of(m);
+      sm_push(rd, pack_mode(0, 0, m), cost_of(dist, false, 0, m), K);
+      sm_push(had, pack_mode(0, 0, m), dist, numHad);
     }
-    // reduceHadCandList, :4333-4405
-    const double thr = __dadd_rn(1.0, __ddiv_rn(1.4, __dsqrt_rn((double)(w * h))));
-    const int maxPerType = K >> 1;
-    const double minCost = rd.c[0];
-    CandList tmp;
-    tmp.n = 0;
-    bool keepOne = rd.n > K;
-    int numConv = 0, numMipKept = 0;
-    for (int idx = 0; idx < rd.n - (keepOne ? 0 : 1); idx++) {
-      bool add;
-      if (!rd.m[idx].mip) { add = numConv < 3; numConv += add; }
-      else {
-        add = numMipKept < maxPerType || rd.c[idx] < __dmul_rn(thr, minCost) || keepOne;
-        keepOne = false;
-        numMipKept += add;
-      }
-      if (add) { tmp.m[tmp.n] = rd.m[idx]; tmp.c[tmp.n] = rd.c[idx]; tmp.n++; }
+    for (int i = 0; i < K; i++) sParent[i * kListThreads + tid] = (uint8_t)(rd.m[i * kListThreads] >> 16);
+    for (int i = 0; i < K; i++) {                                              // :577-623
+      const int pm = sParent[i * kListThreads + tid];
+      if (pm > 2 && pm < 66)
+        for (int dlt = -1; dlt <= 1; dlt += 2) {
+          const int m = pm + dlt;
+          const bool done = m < 64 ? (checked0 >> m) & 1 : (checked1 >> (m - 64)) & 1;
+          if (done) continue;
+          const double dist = dist_of(m);
+          sm_push(rd, pack_mode(0, 0, m), cost_of(dist, false, 0, m), K);
+          sm_push(had, pack_mode(0, 0, m), dist, numHad);
+          if (m < 64) checked0 |= 1ull << m; else checked1 |= 1ull << (m - 64);
+        }
     }
-    if (w > 8 && h > 8) {
-      CandList srt;
-      srt.n = 0;
-      for (int m = 3; m <= 5; m++) {
-        const bool tr = c3[3 + m - 3] < c3[m - 3];
-        cand_push(srt, mk_mode(1, 0, tr ? m + off : m), tr ? c3[3 + m - 3] : c3[m - 3], 3);
-      }
-      const int baseN = tmp.n;
-      for (int idx = 0; idx < 3; idx++) {
-        bool inc = false;
-        for (int i = 0; i < baseN; i++) inc = inc || same_mode(tmp.m[i], srt.m[idx]);
-        if (!inc) { tmp.m[tmp.n] = srt.m[idx]; tmp.c[tmp.n] = 0.0; tmp.n++; break; }   // FastMIP: first one only
-      }
+    if (mrlAllowed)                                                            // :635-681
+      for (int li = 0; li < 2; li++)
+        for (int i = 1; i < 6; i++) {
+          const int slot = (li ? VVCB_SLOT_MRL3 : VVCB_SLOT_MRL1) + i - 1;
+          const int mrl = li ? 3 : 1;
+          const double dist = dist_of(slot);
+          sm_push(rd, pack_mode(0, mrl, v.mpm[i]), cost_of(dist, false, mrl, v.mpm[i]), K);
+          sm_push(had, pack_mode(0, mrl, v.mpm[i]), dist, numHad);
+        }
+    if (D) {
+      store_list_detail(rd, &D->n_reg, D->reg_mode, D->reg_cost, VVCB_MAX_LIST);
+      store_list_detail(had, &D->n_reg_had, D->reg_had_mode, D->reg_had_cost, VVCB_MAX_HAD_LIST);
     }
-    rd = tmp;
-    K = rd.n;
-  }
-  store_list(rd, &R.n_rd, R.rd_mode, R.rd_cost, VVCB_MAX_LIST);
-  store_list(had, &R.n_had, R.had_mode, R.had_cost, VVCB_MAX_HAD_LIST);
 
-  for (int i = 0; i < v.num_mpm_cand; i++) {                                 // :777-802
-    const vvcb_mode mp = mk_mode(0, 0, v.mpm[i]);
-    bool inc = false;
-    for (int j = 0; j < K; j++) inc = inc || same_mode(mp, rd.m[j]);
-    if (!inc) { rd.m[rd.n] = mp; rd.c[rd.n] = 0.0; rd.n++; K++; }
+    if (testMip) {                                                             // :704-751
+      double c3[6];                                                            // costs of MIP modes 3,4,5 and their transposes
+#pragma unroll
+      for (int i = 0; i < 6; i++) c3[i] = 0.0;
+      const int off = numMip / 2;
+      for (int m = 0; m < numMip; m++) {
+        const int slot = VVCB_SLOT_MIP + m;
+        const double dist = dist_of(slot);
+        const double c = cost_of(dist, true, 0, m);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { if (m == 3 + i) c3[i] = c; if (m == 3 + i + off) c3[3 + i] = c; }
+        sm_push(rd, pack_mode(1, 0, m), c, K + 1);
+        sm_push(had, pack_mode(1, 0, m), __dmul_rn(0.8, dist), numHad);
+      }
+      // reduceHadCandList, :4333-4405 (compacted in place: the write index never passes the read index)
+      const double thr = __dadd_rn(1.0, __ddiv_rn(1.4, __dsqrt_rn((double)(w * h))));
+      const int maxPerType = K >> 1;
+      const double minCost = rd.c[0];
+      bool keepOne = rd.n > K;
+      int numConv = 0, numMipKept = 0, wn = 0;
+      for (int idx = 0; idx < rd.n - (keepOne ? 0 : 1); idx++) {      // the bound follows keepOne, as in the reference
+        const uint32_t mm = rd.m[idx * kListThreads];
+        const double cc = rd.c[idx * kListThreads];
+        bool add;
+        if (!(mm & 0xff)) { add = numConv < 3; numConv += add; }
+        else {
+          add = numMipKept < maxPerType || cc < __dmul_rn(thr, minCost) || keepOne;
+          keepOne = false;
+          numMipKept += add;
+        }
+        if (add) { rd.m[wn * kListThreads] = mm; rd.c[wn * kListThreads] = cc; wn++; }
+      }
+      rd.n = wn;
+      if (w > 8 && h > 8) {
+        // the three MIP modes 3..5 (or their transposes), cheapest first (stable), first one not yet in the list (FastMIP)
+        double sc[3]; uint32_t smm[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          const bool tr = c3[3 + i] < c3[i];
+          sc[i] = tr ? c3[3 + i] : c3[i];
+          smm[i] = pack_mode(1, 0, tr ? 3 + i + off : 3 + i);
+        }
+        unsigned picked = 0;
+        const int baseN = rd.n;
+        for (int r = 0; r < 3; r++) {
+          int best = -1;
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+            if (!((picked >> i) & 1) && (best < 0 || sc[i] < (best == 0 ? sc[0] : best == 1 ? sc[1] : sc[2]))) best = i;
+          picked |= 1u << best;
+          const uint32_t cand = best == 0 ? smm[0] : best == 1 ? smm[1] : smm[2];
+          bool inc = false;
+          for (int i = 0; i < baseN; i++) inc = inc || rd.m[i * kListThreads] == cand;
+          if (!inc) { rd.m[rd.n * kListThreads] = cand; rd.c[rd.n * kListThreads] = 0.0; rd.n++; break; }
+        }
+      }
+      K = rd.n;
+    }
+    sCount[tid] = rd.n;
+    sCount[kListThreads + tid] = had.n;
+    for (int i = 0; i < v.num_mpm_cand; i++) {                                 // :777-802
+      const uint32_t mp = pack_mode(0, 0, v.mpm[i]);
+      bool inc = false;
+      for (int j = 0; j < K; j++) inc = inc || mp == rd.m[j * kListThreads];
+      if (!inc) { rd.m[rd.n * kListThreads] = mp; rd.c[rd.n * kListThreads] = 0.0; rd.n++; K++; }
+    }
+    sCount[2 * kListThreads + tid] = rd.n;
   }
-  store_list(rd, &R.n_final, R.final_mode, nullptr, VVCB_MAX_LIST);
+  __syncwarp();
+  // ---- cooperative, coalesced store of the warp's 32 result structs (92 words each)
+  const int lane = tid & 31, wbase = tid & ~31;
+  constexpr int kWords = (int)(sizeof(vvcb_rmd_result) / 4);
+  static_assert(sizeof(vvcb_rmd_result) == 368, "result layout");
+  for (int r = 0; r < 32; r++) {
+    const int t = wbase + r;
+    const int vis = blockIdx.x * blockDim.x + t;
+    if (vis >= n) break;
+    const int nRd = sCount[t], nHad = sCount[kListThreads + t], nFinal = sCount[2 * kListThreads + t];
+    uint32_t* dst = reinterpret_cast<uint32_t*>(results + vis);
+    for (int k = lane; k < kWords; k += 32) {
+      uint32_t val = 0;
+      if (k < 4) val = k == 0 ? nRd : k == 1 ? nHad : k == 2 ? nFinal : 0;
+      else if (k < 20) { const int i = k - 4; if (i < nRd) val = sRdM[i * kListThreads + t]; }
+      else if (k < 52) {
+        const int i = (k - 20) >> 1;
+        if (i < nRd) { const unsigned long long b = (unsigned long long)__double_as_longlong(sRdC[i * kListThreads + t]); val = (k & 1) ? (uint32_t)(b >> 32) : (uint32_t)b; }
+      }
+      else if (k < 60) { const int i = k - 52; if (i < nHad) val = sHadM[i * kListThreads + t]; }
+      else if (k < 76) {
+        const int i = (k - 60) >> 1;
+        if (i < nHad) { const unsigned long long b = (unsigned long long)__double_as_longlong(sHadC[i * kListThreads + t]); val = (k & 1) ? (uint32_t)(b >> 32) : (uint32_t)b; }
+      }
+      else { const int i = k - 76; if (i < nFinal) val = sRdM[i * kListThreads + t]; }
+      dst[k] = val;
+    }
+  }
 }
 
 }  // namespace
