@@ -155,28 +155,50 @@ int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t*
  * One job = one candidate transform of one luma TU, i.e. one pass of IntraSearch::xIntraCodingTUBlock
  * (EL/IntraSearch.cpp:2694) after the prediction: TrQuant::transformNxN(trModes) (CL/TrQuant.cpp:1049) when
  * VVCB_TU_QUANT is clear, transformNxN(quant) (:1127) + invTransformNxN (:561) + PelBuf::reconstruct + RdCost::xGetSSE
- * (CL/RdCost.cpp:1739) when it is set.  Quantisation is the scalar Quant::quant (CL/Quant.cpp:994, intra rounding);
- * dependent quantisation / RDOQ are not built yet.                                            */
-#define VVCB_TU_QUANT   1u
+ * (CL/RdCost.cpp:1739) when it is set.  Quantisation is the scalar Quant::quant (CL/Quant.cpp:994, intra rounding) or,
+ * with VVCB_TU_DEPQUANT, the reference's dependent quantisation; RDOQ (transform skip under the shipped cfg) is not built. */
+#define VVCB_TU_QUANT     1u   /* quantise + reconstruct + SSE                                                              */
+#define VVCB_TU_DEPQUANT  2u   /* with VVCB_TU_QUANT: dependent (trellis-coded) quantisation, DQIntern::DepQuant::quant
+                                  (CL/DepQuant.cpp:1592-1731) and its state-machine dequantiser (:741-810), instead of the
+                                  scalar Quant::quant.  Not for transform skip (the reference sends those to RDOQ, :1757).    */
+
+/* Context prices the dependent quantiser's RateEstimator reads (CL/DepQuant.cpp:479-629), luma: BinFracBits::intBits[0..1] of
+ * each context, taken from the CABAC estimator snapshot the reference passes as `ctx` (ctx.getFracBitsAcess()).               */
+typedef struct vvcb_dq_rates {
+  uint32_t sig_sbb[2][2];      /* Ctx::SigCoeffGroup[CHANNEL_TYPE_LUMA](0..1)                                                  */
+  uint32_t sig[3][12][2];      /* Ctx::SigFlag[0], SigFlag[2], SigFlag[4]: one set per quantiser-state class                   */
+  uint32_t par[21][2];         /* Ctx::ParFlag[luma]                                                                          */
+  uint32_t gt1[21][2];         /* Ctx::GtxFlag[2 + luma]                                                                      */
+  uint32_t gt2[21][2];         /* Ctx::GtxFlag[luma]                                                                          */
+  uint32_t last_x[20][2];      /* Ctx::LastX[luma]                                                                            */
+  uint32_t last_y[20][2];      /* Ctx::LastY[luma]                                                                            */
+} vvcb_dq_rates;
+
 typedef struct vvcb_tu_job {
   int16_t  x, y;            /* luma position of the TU (the original block is read from the frame for the SSE)      */
   uint8_t  log2w, log2h;    /* 2..6; 64-point sides keep their 32 low frequencies (CL/TrQuant.cpp:853)             */
   uint8_t  mts_idx;         /* TransformUnit::mtsIdx: 0 DCT2xDCT2, 1 transform skip, 2..5 DST7/DCT8 pairs (:822-829) */
   uint8_t  flags;           /* VVCB_TU_*                                                                            */
-  int16_t  qp_per, qp_rem;  /* QpParam::per / rem of this candidate (CL/Quant.h:71)                                 */
+  int16_t  qp_per, qp_rem;  /* QpParam::per / rem of this candidate (CL/Quant.h:71); dependent quantisation adds its +1 itself */
   uint32_t offset;          /* first sample of this job's dense w*h block in resi/pred/coeff/level/reco            */
+  /* dependent quantisation only */
+  uint16_t rate_idx;        /* which vvcb_dq_rates snapshot prices this TU                                          */
+  uint8_t  lfnst_idx;       /* cu.lfnstIdx: only moves the first tested scan position (CL/DepQuant.cpp:1641-1646)    */
+  uint8_t  pad;
+  int32_t  cbf_delta_bits;  /* cbfDeltaBits of RateEstimator::xSetLastCoeffOffset (CL/DepQuant.cpp:491-540)          */
+  double   lambda;          /* Quant::m_dLambda                                                                     */
 } vvcb_tu_job;
 
 typedef struct vvcb_tu_result {
   int32_t  abs_sum_coeff;   /* int(sum |coeff| * scaleSAD), the MTS pre-selection cost (CL/TrQuant.cpp:1090-1103)   */
-  int32_t  abs_sum_level;   /* uiAbsSum of Quant::quant (0 when VVCB_TU_QUANT is clear)                             */
+  int32_t  abs_sum_level;   /* uiAbsSum of the quantiser (0 when VVCB_TU_QUANT is clear)                            */
   uint64_t sse;             /* sum (org - reco)^2 (0 when VVCB_TU_QUANT is clear)                                    */
 } vvcb_tu_result;
 
 /* resi / pred: HOST int16 arrays of n_samples (residual = org - pred as the reference's cs.getResiBuf holds it);
  * coeff / level (int32) and reco (int16): optional HOST outputs of n_samples; results: n entries.                  */
 int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred, size_t n_samples,
-                 int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results);
+                 const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results);
 /* TrQuant::transformNxN(trModes) candidate selection (CL/TrQuant.cpp:1112-1123) from the pre-selection sums of one
  * TU's candidates in list order (DCT2 first, transform skip second if tested): pure host logic.                    */
 void vvcb_mts_preselect(const int32_t* sums, int n, int width, int height, int max_cand, uint8_t* selected);

@@ -280,3 +280,32 @@ def features_batch(orig, jobs):
     out = np.zeros(len(jobs), FEAT_RESULT_DTYPE)
     lib().orc_features_batch(po, orig.shape[1], C.c_void_p(jobs.ctypes.data), len(jobs), C.c_void_p(out.ctypes.data))
     return out
+
+
+# ---- dependent quantisation (oracle/vvc_oracle_dq.c) -------------------------------------------------------
+DQ_RATES_DTYPE = np.dtype([('sig_sbb', '<u4', (2, 2)), ('sig', '<u4', (3, 12, 2)), ('par', '<u4', (21, 2)), ('gt1', '<u4', (21, 2)),
+                           ('gt2', '<u4', (21, 2)), ('last_x', '<u4', (20, 2)), ('last_y', '<u4', (20, 2))])
+assert DQ_RATES_DTYPE.itemsize == 4 * 2 * (2 + 36 + 63 + 40)
+
+
+def dq_rates_from_flat(flat):
+    """The 'D' record's flat context-price vector -> one vvcb_dq_rates struct."""
+    return np.frombuffer(np.ascontiguousarray(flat, '<u4').tobytes(), DQ_RATES_DTYPE)[0]
+
+
+def dep_quant(coeff, bd, mts_idx, lfnst_idx, qp, lam, rates, cbf_delta_bits):
+    coeff = np.ascontiguousarray(coeff, np.int32)
+    h, w = coeff.shape
+    level = np.zeros((h, w), np.int32)
+    r = np.ascontiguousarray(np.array([rates], DQ_RATES_DTYPE))
+    s = lib().orc_dep_quant(coeff.ctypes.data_as(_p32), w, h, bd, mts_idx, lfnst_idx, qp, C.c_double(lam), C.c_void_p(r.ctypes.data),
+                            cbf_delta_bits, level.ctypes.data_as(_p32))
+    return level, s
+
+
+def dep_dequant(level, bd, qp):
+    level = np.ascontiguousarray(level, np.int32)
+    h, w = level.shape
+    coeff = np.zeros((h, w), np.int32)
+    lib().orc_dep_dequant(level.ctypes.data_as(_p32), w, h, bd, qp, coeff.ctypes.data_as(_p32))
+    return coeff

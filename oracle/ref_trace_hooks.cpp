@@ -88,6 +88,7 @@ int    g_tuFirst     = 2;
 int    g_fullPred    = 0;     // store prediction samples (not only their hash) for the first N visits of each shape
 bool   g_curFull     = false;
 int    g_maxVisits   = 1 << 30;
+const char* g_only   = nullptr;  // VVC_TRACE_ONLY: keep only the records with these tags
 
 IntraSearch* g_is      = nullptr;
 bool         g_inRmd   = false;   // inside the SATD rough-mode-decision part of a recorded visit
@@ -109,6 +110,7 @@ void init()
   if( const char* s = getenv( "VVC_TRACE_TU_FIRST"     ) ) g_tuFirst     = atoi( s );
   if( const char* s = getenv( "VVC_TRACE_FULL_PRED"    ) ) g_fullPred    = atoi( s );
   if( const char* s = getenv( "VVC_TRACE_MAX_VISITS"   ) ) g_maxVisits   = atoi( s );
+  g_only = getenv( "VVC_TRACE_ONLY" );
 }
 
 struct Rec
@@ -122,7 +124,7 @@ struct Rec
   void i16( int v )       { put<int16_t>( (int16_t) v ); }
   void emit( char tag )
   {
-    if( !g_out ) return;
+    if( !g_out || ( g_only && !strchr( g_only, tag ) ) ) return;
     uint8_t  t = (uint8_t) tag;
     uint32_t n = (uint32_t) b.size();
     fwrite( &t, 1, 1, g_out );
@@ -421,6 +423,31 @@ void __wrap__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamR
   const CCoeffBuf lv = tu.getCoeffs( c );
   for( int y = 0; y < (int) rect.height; y++ ) for( int x = 0; x < (int) rect.width; x++ ) r.i32( lv.at( x, y ) );
   r.emit( 'Q' );
+  // 'D' (dependent quantisation, CL/DepQuant.cpp:1592): the same call seen from the quantiser -- coefficients in, the context
+  // prices its RateEstimator reads, levels out.  i32 w,h,bitDepth,mtsIdx,lfnstIdx,qp,per,rem,absSum,cbfDeltaBits, f64 lambda,
+  // u32 sigSbb[2][2], sig[3][12][2], par[21][2], gt1[21][2], gt2[21][2], lastX[20][2], lastY[20][2], coeff[w*h] i32, level[w*h] i32
+  if( tu.cs->slice->getDepQuantEnabledFlag() && !ts )
+  {
+    const FracBitsAccess& fb = ctx.getFracBitsAcess();
+    Rec d;
+    d.i32( rect.width ); d.i32( rect.height ); d.i32( tu.cs->sps->getBitDepth( CHANNEL_TYPE_LUMA ) ); d.i32( tu.mtsIdx ); d.i32( tu.cu->lfnstIdx );
+    d.i32( qp.Qp( false ) ); d.i32( qp.per( false ) ); d.i32( qp.rem( false ) ); d.i32( absSum );
+    // RateEstimator::xSetLastCoeffOffset, intra luma without ISP (CL/DepQuant.cpp:531-540)
+    const BinFracBits cbf = fb.getFracBitsArray( Ctx::QtCbf[COMPONENT_Y]( DeriveCtx::CtxQtCbf( COMPONENT_Y, tu.cbf[COMPONENT_Cb] ) ) );
+    d.i32( int32_t( cbf.intBits[1] ) - int32_t( cbf.intBits[0] ) );
+    d.f64( tq->m_quant->getLambda() );
+    auto put = [&]( const CtxSet& set, int num ) { for( int i = 0; i < num; i++ ) { const BinFracBits b = fb.getFracBitsArray( set( i ) ); d.u32( b.intBits[0] ); d.u32( b.intBits[1] ); } };
+    put( Ctx::SigCoeffGroup[CHANNEL_TYPE_LUMA], 2 );
+    for( int st = 0; st < 3; st++ ) put( Ctx::SigFlag[CHANNEL_TYPE_LUMA + 2 * st], 12 );
+    put( Ctx::ParFlag[CHANNEL_TYPE_LUMA], 21 );
+    put( Ctx::GtxFlag[2 + CHANNEL_TYPE_LUMA], 21 );
+    put( Ctx::GtxFlag[CHANNEL_TYPE_LUMA], 21 );
+    put( Ctx::LastX[CHANNEL_TYPE_LUMA], 20 );
+    put( Ctx::LastY[CHANNEL_TYPE_LUMA], 20 );
+    for( int i = 0; i < n; i++ ) d.i32( co[i] );
+    for( int y = 0; y < (int) rect.height; y++ ) for( int x = 0; x < (int) rect.width; x++ ) d.i32( lv.at( x, y ) );
+    d.emit( 'D' );
+  }
 }
 
 // 'I' (dequant + inverse): i32 w,h,bitDepth,mtsIdx,qp,per,rem, level[w*h] i32, resi[w*h] i16

@@ -64,6 +64,11 @@ void orc_inv_transform(const int32_t* coeff, int w, int h, int bd, int mts_idx, 
 void orc_inv_transform_skip(const int32_t* coeff, int w, int h, int bd, int16_t* resi, int stride);
 uint64_t orc_reconstruct_sse(const int16_t* org, int org_stride, const int16_t* pred, const int16_t* resi, int w, int h, int bd, int16_t* reco);
 
+/* ---- dependent quantisation (vvc_oracle_dq.c); qp = QpParam::Qp of the block ---- */
+int  orc_dep_quant(const int32_t* coeff, int w, int h, int bd, int mts_idx, int lfnst_idx, int qp, double lambda,
+                   const vvcb_dq_rates* rates, int cbf_delta_bits, int32_t* level);
+void orc_dep_dequant(const int32_t* level, int w, int h, int bd, int qp, int32_t* coeff);
+
 /* ---- texture measures (vvc_oracle_feat.c) ---- */
 void orc_ctu_hads_islice(const int16_t* orig, int stride, int pic_w, int pic_h, int ctu, int32_t* out);
 void orc_features(const int16_t* orig, int stride, const vvcb_feat_job* job, vvcb_feat_result* out);

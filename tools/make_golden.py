@@ -93,6 +93,11 @@ def extra_fixtures(which):
         'ref_10b_200x136_ctuhad': lambda n: run(n, 200, 136, 10, 32, dict(VVC_TRACE_VISIT_FIRST=0, VVC_TRACE_VISIT_STRIDE=1000000,
                                                                          VVC_TRACE_MAX_VISITS=0, VVC_TRACE_TU_FIRST=0, VVC_TRACE_TU_STRIDE=100000000),
                                                     extra=['--RateControl=1', '--TargetBitrate=400000']),
+        # a13: dependent quantisation (DepQuant on as shipped): coefficients, context prices and levels of sampled TUs
+        'ref_10b_128x128_qp27_depquant': lambda n: run(n, 128, 128, 10, 27, dict(VVC_TRACE_VISIT_FIRST=0, VVC_TRACE_VISIT_STRIDE=1000000,
+                                                                                 VVC_TRACE_MAX_VISITS=0, VVC_TRACE_TU_FIRST=3, VVC_TRACE_TU_STRIDE=900, VVC_TRACE_ONLY='D')),
+        'ref_8b_128x64_qp37_depquant': lambda n: run(n, 128, 64, 8, 37, dict(VVC_TRACE_VISIT_FIRST=0, VVC_TRACE_VISIT_STRIDE=1000000,
+                                                                             VVC_TRACE_MAX_VISITS=0, VVC_TRACE_TU_FIRST=3, VVC_TRACE_TU_STRIDE=500, VVC_TRACE_ONLY='D')),
     }
     with open(os.path.join(ROOT, 'tests/golden/MANIFEST.txt'), 'a') as f:
         for n in which or sorted(todo):

@@ -128,6 +128,14 @@ def parse_record(tag, payload):
         n = r['w'] * r['h']
         r['level'] = c.i32(n).reshape(r['h'], r['w'])
         r['resi'] = c.i16(n).reshape(r['h'], r['w'])
+    elif tag == 'D':
+        for k in ('w', 'h', 'bd', 'mts', 'lfnst', 'qp', 'per', 'rem', 'abs_sum', 'cbf_delta'):
+            r[k] = c.i32()
+        r['lambda'] = c.f64()
+        r['rates'] = c.u32(2 * (2 + 36 + 63 + 40))
+        n = r['w'] * r['h']
+        r['coeff'] = c.i32(n).reshape(r['h'], r['w'])
+        r['level'] = c.i32(n).reshape(r['h'], r['w'])
     elif tag == 'H':
         r['w'], r['h'], r['result'] = c.i32(), c.i32(), c.i32()
         r['org'] = c.i16(r['w'] * r['h']).reshape(r['h'], r['w'])

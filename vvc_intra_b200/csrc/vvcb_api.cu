@@ -49,6 +49,9 @@ struct vvcb_ctx {
   TrRom* dTrRom;
   void* dTu[7]; size_t capTu[7];    // TU scratch: jobs, resi, pred, coeff, level, reco, results
   void* dFeat[2]; size_t capFeat[2]; // feature scratch: jobs / per-CTU sums, results
+  // copy/compute pipeline of vvcb_rmd_eval for large host batches
+  cudaStream_t sIn, sOut; cudaEvent_t evIn[2], evComp[2], evOut[2];
+  vvcb_rmd_visit* dVisP[2]; vvcb_rmd_result* dResP[2]; bool pipeReady;
   int16_t* dOrig; int16_t* dReco;
   const int16_t* bOrig; const int16_t* bReco;   // planes in use (own or bound)
   int width, height, stride;        // planes share one pitch (in samples)
@@ -145,6 +148,11 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred); cudaFree(ctx->dTrRom);
   for (int i = 0; i < 7; i++) cudaFree(ctx->dTu[i]);
   for (int i = 0; i < 2; i++) cudaFree(ctx->dFeat[i]);
+  if (ctx->pipeReady) {
+    cudaStreamSynchronize(ctx->sIn); cudaStreamSynchronize(ctx->sOut);
+    for (int i = 0; i < 2; i++) { cudaFree(ctx->dVisP[i]); cudaFree(ctx->dResP[i]); cudaEventDestroy(ctx->evIn[i]); cudaEventDestroy(ctx->evComp[i]); cudaEventDestroy(ctx->evOut[i]); }
+    cudaStreamDestroy(ctx->sIn); cudaStreamDestroy(ctx->sOut);
+  }
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->kev[i]);
   cudaStreamDestroy(ctx->stream);
@@ -271,7 +279,7 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   P.orig = ctx->bOrig; P.reco = ctx->bReco; P.stride = ctx->stride; P.bd = ctx->bd; P.ctu = ctx->ctu; P.rom = ctx->dRom;
   P.predOut = dPred;
   const long long maxCtas = ((long long)n * 8 + kWarpsPerCta - 1) / kWarpsPerCta;
-  int grid = ctx->numSms * 2;
+  int grid = ctx->numSms * VVCB_EVAL_MIN_CTAS;
   if (grid > maxCtas) grid = (int)maxCtas;
   if (grid < 1) grid = 1;
   for (int b = 0; b < kNumBuckets; b++) { VVCB_FOR_BUCKET(b, launch_eval_bucket, P, grid, ctx->stream); }
@@ -289,7 +297,7 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   return VVCB_OK;
 }
 
-static int check_visits(vvcb_ctx* ctx, const vvcb_rmd_visit* v, int n)
+static int check_visits(vvcb_ctx* ctx, const vvcb_rmd_visit* v, int n, int first = 0)
 {
   for (int i = 0; i < n; i++) {
     const int w = 1 << v[i].log2w, h = 1 << v[i].log2h;
@@ -304,7 +312,7 @@ static int check_visits(vvcb_ctx* ctx, const vvcb_rmd_visit* v, int n)
     bool mpmOk = true;
     for (int k = 0; k < 6; k++) mpmOk = mpmOk && v[i].mpm[k] < VVCB_NUM_LUMA_MODE;
     if (!ok || !mpmOk) {
-      snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: visit %d is malformed (position/size/availability outside the picture)", i);
+      snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: visit %d is malformed (position/size/availability outside the picture)", first + i);
       return VVCB_ERR_ARG;
     }
   }
@@ -323,15 +331,72 @@ static int ensure_visit_buffers(vvcb_ctx* ctx, int n)
   return VVCB_OK;
 }
 
+// Large host batches: the batch is cut into chunks and the three stages -- visits host->device, the kernels, result lists
+// device->host -- run on three streams with double-buffered chunk storage, so that the PCIe copies and the host-side
+// validation of the next chunk hide behind the kernels of the current one.
+constexpr int kPipeChunk = 98304;
+
+static int ensure_pipeline(vvcb_ctx* ctx)
+{
+  if (ctx->pipeReady) return VVCB_OK;
+  CK(cudaStreamCreateWithFlags(&ctx->sIn, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->sOut, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    CK(cudaEventCreateWithFlags(&ctx->evIn[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->evComp[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->evOut[i], cudaEventDisableTiming));
+    CK(cudaMalloc(&ctx->dVisP[i], (size_t)kPipeChunk * sizeof(vvcb_rmd_visit)));
+    CK(cudaMalloc(&ctx->dResP[i], (size_t)kPipeChunk * sizeof(vvcb_rmd_result)));
+  }
+  ctx->pipeReady = true;
+  return VVCB_OK;
+}
+
+static int rmd_eval_pipelined(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results)
+{
+  int rc = ensure_pipeline(ctx);
+  if (rc) return rc;
+  const int savedTiming = ctx->timing;
+  ctx->timing = 0;                                   // per-kernel timing would serialise the pipeline
+  int status = VVCB_OK;
+  for (int c = 0, off = 0; off < n && status == VVCB_OK; c++, off += kPipeChunk) {
+    const int m = n - off < kPipeChunk ? n - off : kPipeChunk, b = c & 1;
+    if ((status = check_visits(ctx, visits + off, m, off))) break;
+    cudaError_t e = cudaSuccess;
+    if (c >= 2) e = cudaStreamWaitEvent(ctx->sIn, ctx->evComp[b], 0);              // chunk c-2 no longer reads this buffer
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->dVisP[b], visits + off, (size_t)m * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->sIn);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->evIn[b], ctx->sIn);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->evIn[b], 0);
+    if (e == cudaSuccess && c >= 2) e = cudaStreamWaitEvent(ctx->stream, ctx->evOut[b], 0);   // its results have left the device
+    if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: pipeline stage failed: %s", cudaGetErrorString(e)); status = VVCB_ERR_CUDA; break; }
+    if ((status = launch_rmd(ctx, ctx->dVisP[b], m, ctx->dResP[b], nullptr, nullptr))) break;
+    e = cudaEventRecord(ctx->evComp[b], ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->sOut, ctx->evComp[b], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(results + off, ctx->dResP[b], (size_t)m * sizeof(vvcb_rmd_result), cudaMemcpyDeviceToHost, ctx->sOut);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->evOut[b], ctx->sOut);
+    if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: pipeline stage failed: %s", cudaGetErrorString(e)); status = VVCB_ERR_CUDA; }
+  }
+  ctx->timing = savedTiming;
+  // drain in every case: the caller owns the host buffers again when this returns
+  cudaError_t e1 = cudaStreamSynchronize(ctx->sIn), e2 = cudaStreamSynchronize(ctx->stream), e3 = cudaStreamSynchronize(ctx->sOut);
+  if (status == VVCB_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
+    const cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: %s", cudaGetErrorString(e));
+    status = VVCB_ERR_CUDA;
+  }
+  return status;
+}
+
 extern "C" int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results, vvcb_rmd_detail* details)
 {
   if (!ctx) return VVCB_ERR_ARG;
   if (n < 0 || (n > 0 && (!visits || !results))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: bad argument"); return VVCB_ERR_ARG; }
   if (n == 0) return VVCB_OK;
   if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  if (n > kPipeChunk && !details) return rmd_eval_pipelined(ctx, visits, n, results);
   int rc = check_visits(ctx, visits, n);
   if (rc) return rc;
-  CK(cudaSetDevice(ctx->device));
   rc = ensure_visit_buffers(ctx, n);
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->dVisits, visits, (size_t)n * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));

@@ -287,7 +287,15 @@ struct SlotInfo {
   ModeParam p;
 };
 
-VHD int clip_bd(int v, int maxv) { return vmin(vmax(v, 0), maxv); }
+// clip to [0, maxv]: one VIMNMX.RELU on the device
+VHD int clip_bd(int v, int maxv)
+{
+#if defined(__CUDA_ARCH__)
+  return __vimin_s32_relu(v, maxv);
+#else
+  return vmin(vmax(v, 0), maxv);
+#endif
+}
 
 // Angular prediction of the unit whose origin is (c0, r0) in the main/side frame.  ml points at the
 // slot's main line so that ml[t] == refMain0[t] (may be indexed with negative t); side points at

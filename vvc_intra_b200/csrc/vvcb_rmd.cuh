@@ -443,8 +443,11 @@ __device__ __forceinline__ void predict_mip(const WarpSmem& sm, const int16_t* p
 // =====================================================================================================
 // the evaluation kernel, one instantiation per (SATD tile class, prediction kind)
 // =====================================================================================================
+#ifndef VVCB_EVAL_MIN_CTAS
+#define VVCB_EVAL_MIN_CTAS 2
+#endif
 template <int TILE, int KIND>
-__global__ void __launch_bounds__(kThreads, 2) rmd_eval_kernel(EvalParams P)
+__global__ void __launch_bounds__(kThreads, VVCB_EVAL_MIN_CTAS) rmd_eval_kernel(EvalParams P)
 {
   constexpr int S = TILE < 3 ? 4 : 8;
   constexpr int BUCKET = TILE * kNumKinds + KIND;

@@ -49,7 +49,8 @@ class EngineError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libvvc_intra_b200.so')
+    # VVCB_LIBRARY_PATH: developer override used to A/B kernel build variants (tools/variants.sh)
+    return os.environ.get('VVCB_LIBRARY_PATH') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libvvc_intra_b200.so')
 
 
 _lib = None
