@@ -425,7 +425,7 @@ void __wrap__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamR
   r.emit( 'Q' );
   // 'D' (dependent quantisation, CL/DepQuant.cpp:1592): the same call seen from the quantiser -- coefficients in, the context
   // prices its RateEstimator reads, levels out.  i32 w,h,bitDepth,mtsIdx,lfnstIdx,qp,per,rem,absSum,cbfDeltaBits, f64 lambda,
-  // u32 sigSbb[2][2], sig[3][12][2], par[21][2], gt1[21][2], gt2[21][2], lastX[20][2], lastY[20][2], coeff[w*h] i32, level[w*h] i32
+  // u32 sigSbb[2][2], sig[3][12][2], par[21][2], gt1[21][2], gt2[21][2], lastX[20][2], lastY[20][2], resi[w*h] i16, coeff[w*h] i32, level[w*h] i32
   if( tu.cs->slice->getDepQuantEnabledFlag() && !ts )
   {
     const FracBitsAccess& fb = ctx.getFracBitsAcess();
@@ -444,6 +444,7 @@ void __wrap__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamR
     put( Ctx::GtxFlag[CHANNEL_TYPE_LUMA], 21 );
     put( Ctx::LastX[CHANNEL_TYPE_LUMA], 20 );
     put( Ctx::LastY[CHANNEL_TYPE_LUMA], 20 );
+    putBlock( d, tu.cs->getResiBuf( rect ) );
     for( int i = 0; i < n; i++ ) d.i32( co[i] );
     for( int y = 0; y < (int) rect.height; y++ ) for( int x = 0; x < (int) rect.width; x++ ) d.i32( lv.at( x, y ) );
     d.emit( 'D' );

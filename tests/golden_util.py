@@ -272,3 +272,119 @@ def oracle_tu_chain(items, bd):
         out['coeff'][sl], out['level'][sl], out['reco'][sl] = co.ravel(), lvl.ravel(), reco.ravel()
         out['results'][i] = (O.abs_sum_for_preselection(co, it['mts']), s, sse)
     return out
+
+
+# ---- dependent quantisation: batches from the reference's 'D' records ---------------------------------------
+def build_dq_batch(tus, bd, seed=0):
+    """One VVCB_TU_QUANT | VVCB_TU_DEPQUANT job per 'D' record; every record brings its own context-price snapshot.
+    Returns (orig_plane, jobs, resi_flat, pred_flat, rates, items)."""
+    import vvc_intra_b200 as vb
+    rng = np.random.default_rng(seed)
+    recs = [r for r in tus if r['tag'] == 'D' and r['bd'] == bd]
+    n = len(recs)
+    cols = 16
+    orig = np.zeros((64 * ((n + cols - 1) // cols + 1), 64 * cols), np.int16)
+    jobs = np.zeros(n, vb.TU_JOB_DTYPE)
+    rates = np.zeros(n, vb.DQ_RATES_DTYPE)
+    mx = (1 << bd) - 1
+    items, off = [], 0
+    for i, r in enumerate(recs):
+        resi = r['resi']
+        h, w = resi.shape
+        pred = np.clip(rng.integers(0, mx + 1, (h, w)), np.maximum(0, -resi), np.minimum(mx, mx - resi)).astype(np.int16)
+        org = np.clip(pred.astype(np.int32) + resi, 0, mx).astype(np.int16)
+        cx, cy = 64 * (i % cols), 64 * (i // cols)
+        orig[cy:cy + h, cx:cx + w] = org
+        j = jobs[i]
+        j['x'], j['y'], j['log2w'], j['log2h'], j['mts_idx'] = cx, cy, w.bit_length() - 1, h.bit_length() - 1, r['mts']
+        j['flags'] = vb.TU_QUANT | vb.TU_DEPQUANT
+        j['qp_per'], j['qp_rem'], j['offset'] = r['per'], r['rem'], off
+        j['rate_idx'], j['lfnst_idx'], j['cbf_delta_bits'], j['lambda'] = i, r['lfnst'], r['cbf_delta'], r['lambda']
+        rates[i] = np.frombuffer(np.ascontiguousarray(r['rates'], '<u4').tobytes(), vb.DQ_RATES_DTYPE)[0]
+        items.append(dict(rec=r, pred=pred, org=org, off=off))
+        off += w * h
+    return orig, jobs, np.concatenate([r['resi'].ravel() for r in recs]), np.concatenate([it['pred'].ravel() for it in items]), rates, items
+
+
+def check_dq_outputs(items, bd, out):
+    """Coefficients, levels and absSum against the reference's records; reconstruction + SSE against the oracle's
+    state-machine dequantiser followed by the (pinned) inverse transform."""
+    errs = []
+    for i, it in enumerate(items):
+        r = it['rec']
+        h, w = r['resi'].shape
+        sl = slice(it['off'], it['off'] + w * h)
+        res = out['results'][i]
+        if not np.array_equal(out['coeff'][sl].reshape(h, w), r['coeff']):
+            errs.append('job %d %dx%d mts %d: coefficients differ' % (i, w, h, r['mts']))
+        if not np.array_equal(out['level'][sl].reshape(h, w), r['level']):
+            errs.append('job %d %dx%d mts %d: levels differ (%d positions)' % (i, w, h, r['mts'], int((out['level'][sl].reshape(h, w) != r['level']).sum())))
+        if int(res['abs_sum_level']) != r['abs_sum']:
+            errs.append('job %d: abs sum %d != %d' % (i, res['abs_sum_level'], r['abs_sum']))
+        deq = O.dep_dequant(r['level'], bd, r['qp'])
+        resi = O.inv_transform(deq, bd, r['mts'])
+        reco, sse = O.reconstruct_sse(it['org'], it['pred'], resi, bd)
+        if not np.array_equal(out['reco'][sl].reshape(h, w), reco):
+            errs.append('job %d %dx%d mts %d: reconstruction differs' % (i, w, h, r['mts']))
+        if int(res['sse']) != int(sse):
+            errs.append('job %d: sse %d != %d' % (i, res['sse'], sse))
+    return errs
+
+
+def random_dq_case(rng, bd, n_per_kind):
+    """Random residuals, QP, lambda and context prices for every (shape, transform) dependent quantisation accepts."""
+    import vvc_intra_b200 as vb
+    mx = (1 << bd) - 1
+    items = []
+    for lw in range(2, 7):
+        for lh in range(2, 7):
+            for mts in (0, 2, 3, 4, 5):
+                if mts > 1 and (lw > 5 or lh > 5):
+                    continue
+                for _ in range(n_per_kind):
+                    w, h = 1 << lw, 1 << lh
+                    a = min(int(rng.choice([2, 12, 80, 400])), mx)
+                    pred = rng.integers(0, mx + 1, (h, w))
+                    smooth = rng.integers(-a, a + 1, (h // 4 + 1, w // 4 + 1)).repeat(4, 0).repeat(4, 1)[:h, :w]
+                    org = np.clip(pred + smooth + rng.integers(-a // 2 - 1, a // 2 + 2, (h, w)), 0, mx)
+                    qp = int(rng.integers(10, 52)) + 6 * (bd - 8)
+                    items.append(dict(pred=pred.astype(np.int16), org=org.astype(np.int16), resi=(org - pred).astype(np.int16), mts=mts,
+                                      qp=qp, lam=float(rng.uniform(0.3, 3.0) * 0.57 * 2.0 ** ((qp - 6 * (bd - 8) - 12) / 3.0)),
+                                      cbf=int(rng.integers(-40000, 40000)), lfnst=int(rng.integers(0, 3)) if rng.random() < 0.15 else 0))
+    n = len(items)
+    cols = 16
+    orig = np.zeros((64 * ((n + cols - 1) // cols + 1), 64 * cols), np.int16)
+    jobs = np.zeros(n, vb.TU_JOB_DTYPE)
+    n_rates = 7
+    rates = np.zeros(n_rates, vb.DQ_RATES_DTYPE)
+    for name in rates.dtype.names:
+        rates[name] = rng.integers(300, 140000, rates[name].shape)
+    off = 0
+    for i, it in enumerate(items):
+        h, w = it['resi'].shape
+        cx, cy = 64 * (i % cols), 64 * (i // cols)
+        orig[cy:cy + h, cx:cx + w] = it['org']
+        j = jobs[i]
+        j['x'], j['y'], j['log2w'], j['log2h'], j['mts_idx'] = cx, cy, w.bit_length() - 1, h.bit_length() - 1, it['mts']
+        j['flags'] = vb.TU_QUANT | vb.TU_DEPQUANT
+        j['qp_per'], j['qp_rem'], j['offset'] = it['qp'] // 6, it['qp'] % 6, off
+        j['rate_idx'], j['lfnst_idx'], j['cbf_delta_bits'], j['lambda'] = i % n_rates, it['lfnst'], it['cbf'], it['lam']
+        it['off'], it['rate'] = off, rates[i % n_rates]
+        off += w * h
+    return orig, jobs, np.concatenate([it['resi'].ravel() for it in items]), np.concatenate([it['pred'].ravel() for it in items]), rates, items
+
+
+def oracle_dq_chain(items, bd):
+    import vvc_intra_b200 as vb
+    n = sum(it['resi'].size for it in items)
+    out = dict(results=np.zeros(len(items), vb.TU_RESULT_DTYPE), coeff=np.zeros(n, np.int32), level=np.zeros(n, np.int32), reco=np.zeros(n, np.int16))
+    for i, it in enumerate(items):
+        h, w = it['resi'].shape
+        sl = slice(it['off'], it['off'] + w * h)
+        co = O.fwd_transform(it['resi'], bd, it['mts'])
+        lvl, s = O.dep_quant(co, bd, it['mts'], it['lfnst'], it['qp'], it['lam'], it['rate'], it['cbf'])
+        res = O.inv_transform(O.dep_dequant(lvl, bd, it['qp']), bd, it['mts'])
+        reco, sse = O.reconstruct_sse(it['org'], it['pred'], res, bd)
+        out['coeff'][sl], out['level'][sl], out['reco'][sl] = co.ravel(), lvl.ravel(), reco.ravel()
+        out['results'][i] = (O.abs_sum_for_preselection(co, it['mts']), s, sse)
+    return out

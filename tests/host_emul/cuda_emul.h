@@ -12,6 +12,7 @@
 
 struct emu_dim3 { unsigned x, y, z; };
 struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
 
 struct EmuWarp { pthread_barrier_t bar; int xbuf[32]; };
 struct EmuBlock { pthread_barrier_t bar; std::vector<EmuWarp> warps; };

@@ -6,6 +6,8 @@
 #include "../../vvc_intra_b200/csrc/vvcb_rmd.cuh"
 #include "../../vvc_intra_b200/csrc/vvcb_tu.cuh"
 #include "../../vvc_intra_b200/csrc/vvcb_feat.cuh"
+#include "../../vvc_intra_b200/csrc/vvcb_dq.cuh"
+#include <vector>
 #include "../../vvc_intra_b200/csrc/vvcb_romfill.h"
 
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -77,15 +79,39 @@ extern "C" int emul_rmd_eval(const int16_t* orig, const int16_t* reco, int strid
   return 0;
 }
 
+// the three launches of vvcb_tu_eval (vvcb_api.cu): transform pass, dependent quantisation, reconstruction pass
 extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred,
+                            size_t nSamples, const vvcb_dq_rates* rates, int nRates,
                             int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results)
 {
   static TrRom rom;
+  static DqRom dqRom;
   fill_tr_rom(rom);
+  fill_dq_rom(dqRom);
+  std::vector<int> order, bySize[9];
+  for (int i = 0; i < n; i++)
+    if ((jobs[i].flags & (VVCB_TU_QUANT | VVCB_TU_DEPQUANT)) == (VVCB_TU_QUANT | VVCB_TU_DEPQUANT)) bySize[jobs[i].log2w + jobs[i].log2h - 4].push_back(i);
+  for (int c = 8; c >= 0; c--) order.insert(order.end(), bySize[c].begin(), bySize[c].end());
+  const int nDq = (int)order.size();
+  std::vector<int32_t> dqCoeff(nSamples), dqDeq(nSamples, 0);
+  memset(level, 0, nSamples * sizeof(int32_t));
   TuParams P;
   P.jobs = jobs; P.n = n; P.resi = resi; P.pred = pred; P.coeff = coeff; P.level = level; P.reco = reco; P.results = results;
   P.orig = orig; P.stride = stride; P.bd = bd; P.rom = &rom;
+  P.dqCoeff = dqCoeff.data(); P.dqDeq = dqDeq.data(); P.phase = 0;
   emu_launch(2, kTuThreads, [&] { tu_eval_kernel(P); });
+  if (nDq) {
+    std::vector<DqRateTab> tabs(nRates);
+    emu_launch(nRates, 32, [&] { dq_rate_kernel(rates, nRates, tabs.data()); });
+    const int grid = 2;
+    std::vector<uint8_t> scratch((size_t)grid * kDqGroups * kDqSlotBytes);
+    DqParams D;
+    D.jobs = jobs; D.order = order.data(); D.n = nDq; D.coeff = dqCoeff.data(); D.level = level; D.deq = dqDeq.data(); D.results = results;
+    D.rates = rates; D.tabs = tabs.data(); D.rom = &dqRom; D.scratch = scratch.data(); D.bd = bd;
+    emu_launch(grid, kDqThreads, [&] { dq_kernel(D); });
+    P.phase = 1;
+    emu_launch(2, kTuThreads, [&] { tu_eval_kernel(P); });
+  }
   return 0;
 }
 

@@ -257,3 +257,65 @@ def test_features_on_a_partitioned_picture(eng10):
     with pytest.raises(vb.EngineError, match='malformed'):
         eng10.features_eval(bad)
     assert len(eng10.features_eval(jobs[:0])) == 0
+
+
+# ---- dependent quantisation (VVCB_TU_DEPQUANT) -----------------------------------------------------------
+@pytest.mark.parametrize('name,bd', [('ref_10b_128x128_qp27_depquant', 10), ('ref_8b_128x64_qp37_depquant', 8)])
+def test_dep_quant_golden_parity(name, bd, eng8, eng10):
+    """DQIntern::DepQuant::quant as the reference ran it: recorded residuals and context prices in, the recorded
+    coefficients, levels and absSum out; reconstruction + SSE versus the oracle's state-machine dequantiser."""
+    eng = eng8 if bd == 8 else eng10
+    _, tus = G.load_fixture(name)
+    orig, jobs, resi, pred, rates, items = G.build_dq_batch(tus, bd)
+    assert len(items) > 80
+    eng.frame_begin(orig)
+    out = eng.tu_eval(jobs, resi, pred, want_coeff=True, want_level=True, want_reco=True, rates=rates)
+    errs = G.check_dq_outputs(items, bd, out)
+    assert not errs, (len(errs), errs[:6])
+
+
+@pytest.mark.parametrize('bd,seed', [(8, 71), (10, 72), (10, 73)])
+def test_dep_quant_random_blocks_match_oracle(bd, seed, eng8, eng10):
+    """Every shape x transform, random QP / lambda / context prices / LFNST first-position rule, mixed with scalar-quantiser
+    jobs in the same batch (the two quantisers share the transform and reconstruction passes)."""
+    eng = eng8 if bd == 8 else eng10
+    rng = np.random.default_rng(seed)
+    orig, jobs, resi, pred, rates, items = G.random_dq_case(rng, bd, 4)
+    eng.frame_begin(orig)
+    out = eng.tu_eval(jobs, resi, pred, want_coeff=True, want_level=True, want_reco=True, rates=rates)
+    exp = G.oracle_dq_chain(items, bd)
+    for k in ('coeff', 'level', 'reco'):
+        bad = [i for i, it in enumerate(items) if not np.array_equal(out[k][it['off']:it['off'] + it['resi'].size], exp[k][it['off']:it['off'] + it['resi'].size])]
+        assert not bad, (k, len(bad), [(items[i]['resi'].shape, items[i]['mts'], items[i]['qp'], items[i]['lfnst']) for i in bad[:5]])
+    assert out['results'].tobytes() == exp['results'].tobytes()
+    assert (out['results']['abs_sum_level'] > 0).sum() > len(items) // 3
+    # half of the jobs switched to the scalar quantiser: both kinds in one call
+    mixed = jobs.copy()
+    mixed['flags'][::2] = vb.TU_QUANT
+    out2 = eng.tu_eval(mixed, resi, pred, want_level=True, want_reco=True, rates=rates)
+    for i, it in enumerate(items):
+        sl = slice(it['off'], it['off'] + it['resi'].size)
+        if i % 2:
+            assert np.array_equal(out2['level'][sl], exp['level'][sl]) and out2['results'][i].tobytes() == exp['results'][i].tobytes()
+        else:
+            h, w = it['resi'].shape
+            lvl, s = O.quant_scalar(exp['coeff'][sl].reshape(h, w), bd, it['qp'] // 6, it['qp'] % 6, False)
+            assert np.array_equal(out2['level'][sl].reshape(h, w), lvl) and int(out2['results'][i]['abs_sum_level']) == s
+    # deterministic
+    out3 = eng.tu_eval(jobs, resi, pred, want_level=True, rates=rates)
+    assert np.array_equal(out3['level'], out['level'])
+
+
+def test_dep_quant_error_behaviour(eng10):
+    eng10.frame_begin(np.zeros((64, 64), np.int16))
+    j = np.zeros(1, vb.TU_JOB_DTYPE)
+    j['log2w'], j['log2h'], j['flags'], j['lambda'] = 3, 3, vb.TU_QUANT | vb.TU_DEPQUANT, 10.0
+    z = np.zeros(64, np.int16)
+    with pytest.raises(vb.EngineError, match='malformed'):
+        eng10.tu_eval(j, z, z)                                     # no context prices
+    j['mts_idx'] = 1
+    with pytest.raises(vb.EngineError, match='malformed'):
+        eng10.tu_eval(j, z, z, rates=np.zeros(1, vb.DQ_RATES_DTYPE))   # transform skip is not dependent-quantised
+    j['mts_idx'] = 0
+    out = eng10.tu_eval(j, z, z, want_level=True, want_reco=True, rates=np.zeros(1, vb.DQ_RATES_DTYPE))
+    assert not out['level'].any() and out['results']['abs_sum_level'][0] == 0 and out['results']['sse'][0] == 0

@@ -77,14 +77,21 @@ def test_emulated_kernels_match_oracle_on_random_visits(emul, bd, seed):
 
 
 # ---- TU coding kernel (vvcb_tu.cuh) ------------------------------------------------------------------------
-def run_emul_tu(lib, orig, bd, jobs, resi, pred):
+def run_emul_tu(lib, orig, bd, jobs, resi, pred, rates=None):
     import vvc_intra_b200 as vb
     orig = np.ascontiguousarray(orig, np.int16)
+    jobs = np.ascontiguousarray(jobs, vb.TU_JOB_DTYPE)
+    resi = np.ascontiguousarray(resi, np.int16)
+    pred = np.ascontiguousarray(pred, np.int16)
+    lib.emul_tu_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    nr = 0 if rates is None else len(rates)
+    rates = None if rates is None else np.ascontiguousarray(rates, vb.DQ_RATES_DTYPE)
     out = dict(results=np.zeros(len(jobs), vb.TU_RESULT_DTYPE), coeff=np.zeros(resi.size, np.int32), level=np.zeros(resi.size, np.int32),
                reco=np.zeros(resi.size, np.int16))
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.emul_tu_eval(p(orig), orig.shape[1], bd, p(jobs), len(jobs), p(resi), p(pred), p(out['coeff']), p(out['level']), p(out['reco']),
-                          p(out['results']))
+    rc = lib.emul_tu_eval(p(orig), orig.shape[1], bd, p(jobs), len(jobs), p(resi), p(pred), resi.size, p(rates) if nr else None, nr,
+                          p(out['coeff']), p(out['level']), p(out['reco']), p(out['results']))
     assert rc == 0
     return out
 
@@ -139,3 +146,26 @@ def test_emulated_features_kernel_matches_oracle(emul, seed, mx):
     exp = O.features_batch(pic, jobs)
     bad = [i for i in range(len(jobs)) if out[i].tobytes() != exp[i].tobytes()]
     assert not bad, (jobs[bad[0]]['cu'], out[bad[0]]['f'].tolist(), exp[bad[0]]['f'].tolist())
+
+
+# ---- dependent quantisation kernel (vvcb_dq.cuh) --------------------------------------------------------------
+@pytest.mark.parametrize('name,bd', [('ref_10b_128x128_qp27_depquant', 10), ('ref_8b_128x64_qp37_depquant', 8)])
+def test_emulated_dq_kernel_matches_reference(emul, name, bd):
+    _, tus = G.load_fixture(name)
+    orig, jobs, resi, pred, rates, items = G.build_dq_batch(tus, bd)
+    assert len(items) > 80
+    out = run_emul_tu(emul, orig, bd, jobs, resi, pred, rates)
+    errs = G.check_dq_outputs(items, bd, out)
+    assert not errs, (len(errs), errs[:6])
+
+
+@pytest.mark.parametrize('bd,seed', [(8, 61), (10, 62)])
+def test_emulated_dq_kernel_matches_oracle_on_random_blocks(emul, bd, seed):
+    rng = np.random.default_rng(seed)
+    orig, jobs, resi, pred, rates, items = G.random_dq_case(rng, bd, 1)
+    out = run_emul_tu(emul, orig, bd, jobs, resi, pred, rates)
+    exp = G.oracle_dq_chain(items, bd)
+    for k in ('coeff', 'level', 'reco'):
+        bad = [i for i, it in enumerate(items) if not np.array_equal(out[k][it['off']:it['off'] + it['resi'].size], exp[k][it['off']:it['off'] + it['resi'].size])]
+        assert not bad, (k, len(bad), [(items[i]['resi'].shape, items[i]['mts'], items[i]['qp'], items[i]['lfnst']) for i in bad[:5]])
+    assert out['results'].tobytes() == exp['results'].tobytes()

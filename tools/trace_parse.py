@@ -134,6 +134,7 @@ def parse_record(tag, payload):
         r['lambda'] = c.f64()
         r['rates'] = c.u32(2 * (2 + 36 + 63 + 40))
         n = r['w'] * r['h']
+        r['resi'] = c.i16(n).reshape(r['h'], r['w'])
         r['coeff'] = c.i32(n).reshape(r['h'], r['w'])
         r['level'] = c.i32(n).reshape(r['h'], r['w'])
     elif tag == 'H':

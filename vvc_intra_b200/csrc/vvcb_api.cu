@@ -9,6 +9,8 @@
 #include "vvcb_rmd.cuh"
 #include "vvcb_tu.cuh"
 #include "vvcb_feat.cuh"
+#include "vvcb_dq.cuh"
+#include <vector>
 #include "vvcb_romfill.h"
 
 // =====================================================================================================
@@ -47,7 +49,9 @@ struct vvcb_ctx {
   cudaEvent_t ev0, ev1;
   Rom* dRom;
   TrRom* dTrRom;
-  void* dTu[7]; size_t capTu[7];    // TU scratch: jobs, resi, pred, coeff, level, reco, results
+  void* dTu[14]; size_t capTu[14];  // TU scratch: jobs, resi, pred, coeff, level, reco, results; DepQuant: coeff in, dequantised out,
+                                    // job order, context prices, derived rate tables, per-group context memory + trellis
+  DqRom* dDqRom;
   void* dFeat[2]; size_t capFeat[2]; // feature scratch: jobs / per-CTU sums, results
   // copy/compute pipeline of vvcb_rmd_eval for large host batches
   cudaStream_t sIn, sOut; cudaEvent_t evIn[2], evComp[2], evOut[2];
@@ -135,6 +139,14 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
     delete t;
     if (e != cudaSuccess) return fail("cudaMemcpy(trrom)", e);
   }
+  {
+    DqRom* t = new DqRom();
+    fill_dq_rom(*t);
+    if ((e = cudaMalloc(&ctx->dDqRom, sizeof(DqRom))) != cudaSuccess) { delete t; return fail("cudaMalloc(dqrom)", e); }
+    e = cudaMemcpy(ctx->dDqRom, t, sizeof(DqRom), cudaMemcpyHostToDevice);
+    delete t;
+    if (e != cudaSuccess) return fail("cudaMemcpy(dqrom)", e);
+  }
   *out = ctx;
   return VVCB_OK;
 }
@@ -146,7 +158,8 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dSlotMajor);
   cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred); cudaFree(ctx->dTrRom);
-  for (int i = 0; i < 7; i++) cudaFree(ctx->dTu[i]);
+  for (int i = 0; i < 14; i++) cudaFree(ctx->dTu[i]);
+  cudaFree(ctx->dDqRom);
   for (int i = 0; i < 2; i++) cudaFree(ctx->dFeat[i]);
   if (ctx->pipeReady) {
     cudaStreamSynchronize(ctx->sIn); cudaStreamSynchronize(ctx->sOut);
@@ -461,34 +474,52 @@ static int tu_buf(vvcb_ctx* ctx, int i, size_t bytes)
 }
 
 extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred, size_t n_samples,
-                            int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results)
+                            const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results)
 {
   if (!ctx) return VVCB_ERR_ARG;
-  if (n < 0 || (n > 0 && (!jobs || !resi || !results))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: bad argument"); return VVCB_ERR_ARG; }
+  if (n < 0 || n_rates < 0 || (n > 0 && (!jobs || !resi || !results))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: bad argument"); return VVCB_ERR_ARG; }
   if (n == 0) return VVCB_OK;
   bool anyQuant = false;
+  std::vector<int> order;                 // DepQuant jobs, largest TU first (the groups of a warp then walk scans of similar length)
+  std::vector<int> bySize[9];
   for (int i = 0; i < n; i++) {
     const vvcb_tu_job& j = jobs[i];
     const size_t sz = (size_t)1 << (j.log2w + j.log2h);
     const bool q = (j.flags & VVCB_TU_QUANT) != 0;
+    const bool dq = q && (j.flags & VVCB_TU_DEPQUANT);
     anyQuant = anyQuant || q;
     bool ok = j.log2w >= 2 && j.log2w <= 6 && j.log2h >= 2 && j.log2h <= 6 && j.mts_idx <= 5 && (size_t)j.offset + sz <= n_samples &&
               j.qp_rem >= 0 && j.qp_rem < 6 && j.qp_per >= 0 && j.qp_per < 16;
     if (j.mts_idx == 1) ok = ok && j.log2w <= 5 && j.log2h <= 5;                 // TU::isTSAllowed, CL/UnitTools.cpp:4524
     if (j.mts_idx > 1)  ok = ok && j.log2w <= 5 && j.log2h <= 5;                 // TU::isMTSAllowed, :4549
     if (q) ok = ok && ctx->bOrig && j.x >= 0 && j.y >= 0 && j.x + (1 << j.log2w) <= ctx->width && j.y + (1 << j.log2h) <= ctx->height;
+    if (dq) ok = ok && j.mts_idx != 1 && rates && j.rate_idx < n_rates && j.lfnst_idx <= 2 && j.lambda > 0.0;   // CL/DepQuant.cpp:1757: TS goes to RDOQ
     if (!ok) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: job %d is malformed", i); return VVCB_ERR_ARG; }
+    if (dq) bySize[j.log2w + j.log2h - 4].push_back(i);
   }
   if (anyQuant && !pred) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: VVCB_TU_QUANT needs the prediction samples"); return VVCB_ERR_ARG; }
+  for (int c = 8; c >= 0; c--) order.insert(order.end(), bySize[c].begin(), bySize[c].end());
+  const int nDq = (int)order.size();
   CK(cudaSetDevice(ctx->device));
   int rc;
   if ((rc = tu_buf(ctx, 0, (size_t)n * sizeof(vvcb_tu_job)))) return rc;
   if ((rc = tu_buf(ctx, 1, n_samples * sizeof(int16_t)))) return rc;
   if ((rc = tu_buf(ctx, 2, n_samples * sizeof(int16_t)))) return rc;
   if (coeff && (rc = tu_buf(ctx, 3, n_samples * sizeof(int32_t)))) return rc;
-  if (level && (rc = tu_buf(ctx, 4, n_samples * sizeof(int32_t)))) return rc;
+  if ((level || nDq) && (rc = tu_buf(ctx, 4, n_samples * sizeof(int32_t)))) return rc;
   if (reco && (rc = tu_buf(ctx, 5, n_samples * sizeof(int16_t)))) return rc;
   if ((rc = tu_buf(ctx, 6, (size_t)n * sizeof(vvcb_tu_result)))) return rc;
+  int dqGrid = 0;
+  if (nDq) {
+    dqGrid = (nDq + kDqGroups - 1) / kDqGroups;
+    if (dqGrid > ctx->numSms * 4) dqGrid = ctx->numSms * 4;
+    if ((rc = tu_buf(ctx, 7, n_samples * sizeof(int32_t)))) return rc;
+    if ((rc = tu_buf(ctx, 8, n_samples * sizeof(int32_t)))) return rc;
+    if ((rc = tu_buf(ctx, 9, (size_t)nDq * sizeof(int)))) return rc;
+    if ((rc = tu_buf(ctx, 10, (size_t)n_rates * sizeof(vvcb_dq_rates)))) return rc;
+    if ((rc = tu_buf(ctx, 11, (size_t)n_rates * sizeof(DqRateTab)))) return rc;
+    if ((rc = tu_buf(ctx, 12, (size_t)dqGrid * kDqGroups * kDqSlotBytes))) return rc;
+  }
   CK(cudaMemcpyAsync(ctx->dTu[0], jobs, (size_t)n * sizeof(vvcb_tu_job), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->dTu[1], resi, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
   if (pred) CK(cudaMemcpyAsync(ctx->dTu[2], pred, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -496,13 +527,32 @@ extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const
   P.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); P.n = n;
   P.resi = static_cast<const int16_t*>(ctx->dTu[1]); P.pred = static_cast<const int16_t*>(ctx->dTu[2]);
   P.coeff = coeff ? static_cast<int32_t*>(ctx->dTu[3]) : nullptr;
-  P.level = level ? static_cast<int32_t*>(ctx->dTu[4]) : nullptr;
+  P.level = (level || nDq) ? static_cast<int32_t*>(ctx->dTu[4]) : nullptr;
   P.reco = reco ? static_cast<int16_t*>(ctx->dTu[5]) : nullptr;
   P.results = static_cast<vvcb_tu_result*>(ctx->dTu[6]);
   P.orig = ctx->bOrig; P.stride = ctx->stride; P.bd = ctx->bd; P.rom = ctx->dTrRom;
+  P.dqCoeff = static_cast<int32_t*>(ctx->dTu[7]); P.dqDeq = static_cast<const int32_t*>(ctx->dTu[8]); P.phase = 0;
   const int grid = n < ctx->numSms * 8 ? n : ctx->numSms * 8;
+  if (nDq) {
+    CK(cudaMemsetAsync(ctx->dTu[4], 0, n_samples * sizeof(int32_t), ctx->stream));     // levels / dequantised coefficients the
+    CK(cudaMemsetAsync(ctx->dTu[8], 0, n_samples * sizeof(int32_t), ctx->stream));     // trellis does not reach stay zero
+    CK(cudaMemcpyAsync(ctx->dTu[9], order.data(), (size_t)nDq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dTu[10], rates, (size_t)n_rates * sizeof(vvcb_dq_rates), cudaMemcpyHostToDevice, ctx->stream));
+  }
   tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
   ctx->launches++;
+  if (nDq) {
+    dq_rate_kernel<<<n_rates, 32, 0, ctx->stream>>>(static_cast<const vvcb_dq_rates*>(ctx->dTu[10]), n_rates, static_cast<DqRateTab*>(ctx->dTu[11]));
+    DqParams D;
+    D.jobs = P.jobs; D.order = static_cast<const int*>(ctx->dTu[9]); D.n = nDq;
+    D.coeff = P.dqCoeff; D.level = P.level; D.deq = static_cast<int32_t*>(ctx->dTu[8]); D.results = P.results;
+    D.rates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]); D.tabs = static_cast<const DqRateTab*>(ctx->dTu[11]);
+    D.rom = ctx->dDqRom; D.scratch = static_cast<uint8_t*>(ctx->dTu[12]); D.bd = ctx->bd;
+    dq_kernel<<<dqGrid, kDqThreads, 0, ctx->stream>>>(D);
+    P.phase = 1;
+    tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
+    ctx->launches += 3;
+  }
   CK(cudaGetLastError());
   if (coeff) CK(cudaMemcpyAsync(coeff, ctx->dTu[3], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (level) CK(cudaMemcpyAsync(level, ctx->dTu[4], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,0 +1,484 @@
+// vvc_intra_b200 -- dependent (trellis-coded) quantisation kernel (sm_100a).
+//
+// Reference behaviour: DQIntern::DepQuant::quant (CL/DepQuant.cpp:1592-1731) with its RateEstimator (:479-629), Quantizer
+// (:694-844), State / CommonCtx (:895-1397), xDecide / xDecideAndUpdate (:1455-1589) and Quantizer::dequantBlock (:741-810);
+// luma, flat scaling lists, the reference's compile-time switches as shipped (JVET_O0094 / O0052 / O0617 / O0256 on).
+//
+// Mapping.  The trellis is sequential in scan position and four states wide, so a TU is owned by a GROUP OF FOUR LANES
+// (lane k = quantiser state k), eight TUs per warp.  All groups of a warp walk their scans in lock-step (the host sorts
+// the jobs by size so that the groups of a warp have similar lengths); lanes exchange the three candidate costs of a
+// state through shared memory.  The twelve states (current / previous / skip x 4) live in shared memory; the per-TU
+// sub-block context memory (CommonCtx) and the decision trellis live in a global scratch slot owned by the group.
+// After the forward pass lane 0 walks the trellis backwards, writes the levels and -- because the state a coefficient was
+// quantised in is the `prevId` of its decision -- the dequantised coefficients in the same pass.
+#pragma once
+#include "vvcb_core.cuh"
+
+namespace {
+
+using namespace vvcb;
+
+constexpr int kDqThreads = 128;
+constexpr int kDqGroups  = kDqThreads / 4;
+constexpr int kDqScaleBits = 15;
+constexpr long long kDqHuge = 0x7fffffffffffffffll;
+constexpr int kDqCtxBytes = 8 * (1024 + 64);                 // CommonCtx::m_memory for the largest TU
+constexpr int kDqSlotBytes = kDqCtxBytes + 1024 * 16;        // + trellis: 4 packed decisions per scan position
+
+// ---- read-only tables (built on the host at vvcb_create) ------------------------------------------------
+struct DqScanPos {           // one scan position of one TU shape
+  uint16_t idx;              // raster position (stride = TU width)
+  uint8_t  x, y;
+  uint16_t maxDist;          // NbInfoOut::maxDist (relative)
+  uint8_t  numOut;           // neighbours outside the 4x4 sub-block ...
+  uint8_t  pad;
+  uint16_t outPos[5];        // ... relative to the first position of the sub-block
+  uint16_t pad2;
+};
+struct DqShape { int first; int numCoeff, numSbb, widthInSbb, heightInSbb; };   // `first`: index of scan position 0 in DqRom::pos
+struct DqRom {
+  DqShape   shape[5][5];     // [log2w - 2][log2h - 2]
+  DqScanPos pos[8464];       // all shapes back to back: (4 + 8 + 16 + 32 + 32)^2
+  uint16_t  sbbPos[5][5][64];// sub-block scan -> raster position in the sub-block grid
+  uint8_t   nbIn[16][6];     // inside-sub-block neighbours of an in-sub-block position: {num, inPos[5]} (shape independent)
+  int32_t   goRiceBits[4][32];
+  uint8_t   goRicePars[32], goRiceZero[3][32], groupIdx[32];
+  int32_t   quantScales[12], invQuantScales[12];
+};
+
+// per snapshot of context prices, derived once per call by dq_rate_kernel (RateEstimator::xSetGtxFlagBits etc.)
+struct DqRateTab {
+  int32_t gtx[21][6];
+  int32_t sig[3][12][2];
+  int32_t sigSbb[2][2];
+};
+
+struct DqState {             // 96 bytes
+  long long rdCost;
+  uint16_t  ctxInit[24];     // m_absLevelsAndCtxInit
+  int       numSigSbb, remRegBins, refSbbCtxId;
+  int       sbbBits0, sbbBits1;
+  int       sigCtx, gtxCtx;  // indices into DqRateTab::sig[set(stateId)] / gtx
+  int       goRicePar, goRiceZero;
+  int       pad;
+};
+
+struct DqGroupSmem {
+  DqState   st[12];          // [set 0..2][state 0..3]; which set is current / previous / skip rotates
+  long long cand[4][3];      // candidate costs A, Z, B of source state k
+  long long pathCost[4];     // rdCost of the four decisions at scan position 0
+  int32_t   lastX[12], lastY[12];   // ctxBits of RateEstimator::xSetLastCoeffOffset per group index
+};
+
+struct DqParams {
+  const vvcb_tu_job* jobs;
+  const int* order;          // DepQuant job indices, largest TU first
+  int n;                     // number of DepQuant jobs
+  const int32_t* coeff;      // forward-transform output (dense per job at job.offset)
+  int32_t* level;            // out: levels (zero-filled by the caller)
+  int32_t* deq;              // out: dequantised coefficients (zero-filled by the caller)
+  vvcb_tu_result* results;   // abs_sum_level is written here
+  const vvcb_dq_rates* rates;
+  const DqRateTab* tabs;
+  const DqRom* rom;
+  uint8_t* scratch;          // kDqSlotBytes per group of the grid
+  int bd;
+};
+
+__global__ void dq_rate_kernel(const vvcb_dq_rates* rates, int n, DqRateTab* tabs)
+{
+  const int r = blockIdx.x;
+  if (r >= n) return;
+  const vvcb_dq_rates& c = rates[r];
+  DqRateTab& t = tabs[r];
+  for (int i = threadIdx.x; i < 21; i += blockDim.x) {
+    const int par0 = (1 << kDqScaleBits) + (int)c.par[i][0], par1 = (1 << kDqScaleBits) + (int)c.par[i][1];
+    t.gtx[i][0] = 0;
+    t.gtx[i][1] = (int)c.gt1[i][0] + (1 << kDqScaleBits);
+    t.gtx[i][2] = (int)c.gt1[i][1] + par0 + (int)c.gt2[i][0];
+    t.gtx[i][3] = (int)c.gt1[i][1] + par1 + (int)c.gt2[i][0];
+    t.gtx[i][4] = (int)c.gt1[i][1] + par0 + (int)c.gt2[i][1];
+    t.gtx[i][5] = (int)c.gt1[i][1] + par1 + (int)c.gt2[i][1];
+  }
+  for (int i = threadIdx.x; i < 72; i += blockDim.x) (&t.sig[0][0][0])[i] = (int)(&c.sig[0][0][0])[i];
+  for (int i = threadIdx.x; i < 4; i += blockDim.x) (&t.sigSbb[0][0])[i] = (int)(&c.sig_sbb[0][0])[i];
+}
+
+struct DqQuant {             // Quantizer::initQuantBlock, CL/DepQuant.cpp:694-739
+  int qShift, maxQIdx, thres, distShift;
+  long long qAdd, qScale, distAdd, distStepAdd, distOrgFact;
+};
+
+VHD int dq_ceil_log2(unsigned long long x)
+{
+  int n = 0;
+  const int notPow2 = (x & (x - 1)) != 0;
+  while (x > 1) { x >>= 1; n++; }
+  return n + notPow2;
+}
+
+VHD DqQuant dq_init_quant(const DqRom& rom, int bd, int lw, int lh, int qp, double lambda)
+{
+  DqQuant q;
+  const int qpDQ = qp + 1, qpPer = qpDQ / 6, qpRem = qpDQ - 6 * qpPer;
+  const int nomShift = 15 - bd - ((lw + lh) >> 1);
+  const int sqrt2 = (lw + lh) & 1;
+  const int trShift = nomShift - sqrt2;
+  const int invShift = 7 - qpPer - trShift;
+  q.qShift = 13 + qpPer + trShift;
+  q.qAdd = -((3ll << q.qShift) >> 1);
+  q.qScale = rom.quantScales[sqrt2 * 6 + qpRem];
+  q.maxQIdx = (1 << (vmin(16, 32 + invShift - 7) - 1)) - 4;
+  q.thres = (int)((4ll << q.qShift) / (4 * q.qScale));           // thresLast / (4 * defaultQuantisationCoefficient), :1648-1656
+  const int nomDShift = kDqScaleBits - 2 * nomShift + q.qShift + sqrt2;
+  const double qScale2 = (double)(q.qScale * q.qScale);
+  // the reference evaluates these in IEEE double without contraction; every product below is a single rounding
+#if defined(__CUDA_ARCH__)
+  const double den = __dmul_rn(qScale2, lambda);
+  const double f = nomDShift < 0 ? __ddiv_rn(1.0, __dmul_rn((double)(1ll << (-nomDShift)), den)) : __ddiv_rn((double)(1ll << nomDShift), den);
+  const long long pow2 = (long long)__dmul_rn(f, qScale2) + 1;
+#else
+  const double den = qScale2 * lambda;
+  const double f = nomDShift < 0 ? 1.0 / ((double)(1ll << (-nomDShift)) * den) : (double)(1ll << nomDShift) / den;
+  const long long pow2 = (long long)(f * qScale2) + 1;
+#endif
+  q.distShift = 62 + q.qShift - 30 - dq_ceil_log2((unsigned long long)pow2);
+  q.distAdd = (1ll << q.distShift) >> 1;
+#if defined(__CUDA_ARCH__)
+  q.distStepAdd = (long long)__dadd_rn(__dmul_rn(f, (double)(1ll << (q.distShift + q.qShift))), .5);
+  q.distOrgFact = (long long)__dadd_rn(__dmul_rn(f, (double)(1ll << (q.distShift + 1))), .5);
+#else
+  q.distStepAdd = (long long)(f * (double)(1ll << (q.distShift + q.qShift)) + .5);
+  q.distOrgFact = (long long)(f * (double)(1ll << (q.distShift + 1)) + .5);
+#endif
+  return q;
+}
+
+// bits of an absolute level coded with regular bins under the state's greater-than contexts (:977-990)
+__device__ __forceinline__ long long dq_level_bits(const DqRom& rom, const int32_t* gtx, int goRicePar, int absLevel)
+{
+  if (absLevel < 4) return gtx[absLevel];
+  const unsigned value = (unsigned)(absLevel - 4) >> 1;
+  return gtx[absLevel - (int)(value << 1)] + rom.goRiceBits[goRicePar][value < 32u ? value : 31u];
+}
+
+__device__ __forceinline__ uint32_t dq_pack(int absLevel, int prevId) { return (uint32_t)(absLevel & 0xffff) | ((uint32_t)(prevId + 2) << 16); }
+
+__global__ void __launch_bounds__(kDqThreads) dq_kernel(DqParams P)
+{
+  __shared__ DqGroupSmem smem[kDqGroups];
+  const DqRom& rom = *P.rom;
+  const int lane = threadIdx.x & 31, k = lane & 3;                 // k: this lane's quantiser state
+  const int gInCta = threadIdx.x >> 2;
+  DqGroupSmem& sm = smem[gInCta];
+  const int slot = blockIdx.x * kDqGroups + gInCta;
+  uint8_t* ctxMem = P.scratch + (size_t)slot * kDqSlotBytes;
+  uint4* trellis = reinterpret_cast<uint4*>(ctxMem + kDqCtxBytes);
+  const int groupsTotal = gridDim.x * kDqGroups;
+  const int rounds = (P.n + groupsTotal - 1) / groupsTotal;
+
+  for (int round = 0; round < rounds; round++) {
+    // round-robin over the size-sorted job list: the 8 groups of a warp get neighbours in the sorted order
+    const int ji = round * groupsTotal + slot;
+    const bool have = ji < P.n;
+    vvcb_tu_job job;
+    if (have) job = P.jobs[P.order[ji]];
+    else { job.log2w = 2; job.log2h = 2; job.mts_idx = 0; job.offset = 0; job.qp_per = 4; job.qp_rem = 0; job.rate_idx = 0; job.lfnst_idx = 0; job.cbf_delta_bits = 0; job.lambda = 1.0; }
+    const int lw = job.log2w, lh = job.log2h, w = 1 << lw, h = 1 << lh;
+    const DqShape shp = rom.shape[lw - 2][lh - 2];
+    const DqScanPos* scan = rom.pos + shp.first;
+    const uint16_t* sbbPosTab = rom.sbbPos[lw - 2][lh - 2];
+    const DqRateTab& tab = P.tabs[have ? job.rate_idx : 0];
+    const int32_t* coeff = P.coeff + job.offset;
+    const DqQuant Q = dq_init_quant(rom, P.bd, lw, lh, 6 * job.qp_per + job.qp_rem, job.lambda);
+    int effW = w, effH = h;
+    bool zeroOutTu = false;
+    if (job.mts_idx > 1) { effH = h == 32 ? 16 : h; effW = w == 32 ? 16 : w; zeroOutTu = effH < h || effW < w; }
+    const int regBinsInit = (vmin(32, effW) * vmin(32, effH) * 28) >> 4;
+    const int ctxStride = shp.numSbb + shp.numCoeff;
+
+    // ---- first test position (:1638-1662): highest scan index whose coefficient exceeds the threshold
+    int firstTestPos = -1;
+    if (have) {
+      int start = shp.numCoeff - 1;                                 // positions past the 32x32 region are zero-out fillers
+      if (job.lfnst_idx > 0) start = vmin(start, ((w == 4 && h == 4) || (w == 8 && h == 8)) ? 7 : 15);
+      const int limX = (w == 32 && zeroOutTu) ? 16 : 32, limY = (h == 32 && zeroOutTu) ? 16 : 32;
+      for (int s = start - k; s >= 0; s -= 4) {
+        const DqScanPos sp = scan[s];
+        if (sp.x >= limX || sp.y >= limY) continue;
+        if (vabs(coeff[sp.idx]) > Q.thres) { firstTestPos = s; break; }
+      }
+    }
+    firstTestPos = vmax(firstTestPos, __shfl_xor_sync(0xffffffffu, firstTestPos, 1));
+    firstTestPos = vmax(firstTestPos, __shfl_xor_sync(0xffffffffu, firstTestPos, 2));
+    int steps = firstTestPos + 1;
+    for (int o = 4; o < 32; o <<= 1) steps = vmax(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+
+    // ---- init (:1665-1688)
+    __syncwarp();
+    for (int s = k; s < 12; s += 4) {
+      DqState& st = sm.st[s];
+      st.rdCost = kDqHuge >> 1;
+      for (int i = 0; i < 24; i++) st.ctxInit[i] = 0;
+      st.numSigSbb = 0; st.remRegBins = 4; st.refSbbCtxId = -1;
+      st.sbbBits0 = 0; st.sbbBits1 = 0; st.sigCtx = 0; st.gtxCtx = 0; st.goRicePar = 0; st.goRiceZero = 0;
+    }
+    if (k < 2) {                                                   // RateEstimator::xSetLastCoeffOffset :541-567
+      const int size = k ? h : w, lg = k ? lh : lw;
+      const uint32_t (*ctx)[2] = k ? P.rates[job.rate_idx].last_y : P.rates[job.rate_idx].last_x;
+      const int prefix = lg == 2 ? 0 : lg == 3 ? 3 : lg == 4 ? 6 : lg == 5 ? 10 : 15;
+      const int lastShift = (lg + 1) >> 2, bitOffset = k ? job.cbf_delta_bits : 0;
+      const int maxCtxId = rom.groupIdx[vmin(32, size) - 1];
+      int32_t* out = k ? sm.lastY : sm.lastX;
+      uint32_t sum = 0;
+      for (int c = 0; c < maxCtxId; c++) {
+        const uint32_t* b = ctx[prefix + (c >> lastShift)];
+        out[c] = (int32_t)(sum + b[0] + (c > 3 ? (uint32_t)((c - 2) >> 1) << kDqScaleBits : 0u) + (uint32_t)bitOffset);
+        sum += b[1];
+      }
+      out[maxCtxId] = (int32_t)(sum + (maxCtxId > 3 ? (uint32_t)((maxCtxId - 2) >> 1) << kDqScaleBits : 0u) + (uint32_t)bitOffset);
+    }
+    __syncwarp();
+
+    int curr = 0, prev = 1, skip = 2;          // which third of sm.st plays which role
+    int currSet = 0, prevSet = 4;              // CommonCtx::m_currSbbCtx / m_prevSbbCtx
+    const int32_t* sigTab = &tab.sig[vmax(k - 1, 0)][0][0];
+
+    for (int it = 0; it < steps; it++) {
+      const int scanIdx = firstTestPos - it;
+      const bool act = scanIdx >= 0;
+      { const int t = prev; prev = curr; curr = t; }               // std::swap(m_prevStates, m_currStates)
+      long long dCost = kDqHuge >> 2;
+      int dLevel = -1, dPrev = -2;
+      int spt = 0, spX = 0, spY = 0;
+      bool zeroOut = false;
+      int pqLevel[4] = { 0, 0, 0, 0 }; long long pqDist[4] = { 0, 0, 0, 0 };
+      if (act) {
+        const DqScanPos sp = scan[scanIdx];
+        const int inside = scanIdx & 15;
+        spX = sp.x; spY = sp.y;
+        if (inside == 15 && scanIdx > 16 && scanIdx < shp.numCoeff - 1) spt = 1;                 // SCAN_SOCSBB
+        else if (inside == 0 && scanIdx > 0 && scanIdx < shp.numCoeff - 16) spt = 2;             // SCAN_EOCSBB
+        zeroOut = zeroOutTu && (sp.x >= effW || sp.y >= effH);
+        if (!zeroOut) {
+          // ---- Quantizer::preQuantCoeff :812-843 (every lane of the group computes the same four candidates)
+          const int absCoeff = vabs(coeff[sp.idx]);
+          const long long scaledOrg = (long long)absCoeff * Q.qScale;
+          int qIdx = vmax(1, vmin(Q.maxQIdx, (int)((scaledOrg + Q.qAdd) >> Q.qShift)));
+          long long scaledAdd = qIdx * Q.distStepAdd - scaledOrg * Q.distOrgFact;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const long long dd = (scaledAdd * qIdx + Q.distAdd) >> Q.distShift;
+            const int slotI = qIdx & 3;
+            qIdx++;
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (j == slotI) { pqDist[j] = dd; pqLevel[j] = qIdx >> 1; }
+            scaledAdd += Q.distStepAdd;
+          }
+          // ---- State::checkRdCosts of previous state k :924-1049
+          const DqState& ps = sm.st[prev * 4 + k];
+          const int lvA = k < 2 ? pqLevel[0] : pqLevel[3], lvB = k < 2 ? pqLevel[2] : pqLevel[1];
+          long long cA = ps.rdCost + (k < 2 ? pqDist[0] : pqDist[3]);
+          long long cB = ps.rdCost + (k < 2 ? pqDist[2] : pqDist[1]);
+          long long cZ = ps.rdCost;
+          const int32_t* rice = rom.goRiceBits[ps.goRicePar];
+          if (ps.remRegBins >= 4) {
+            const int32_t* gtx = tab.gtx[ps.gtxCtx];
+            const int sig0 = sigTab[ps.sigCtx * 2], sig1 = sigTab[ps.sigCtx * 2 + 1];
+            cA += dq_level_bits(rom, gtx, ps.goRicePar, lvA);
+            cB += dq_level_bits(rom, gtx, ps.goRicePar, lvB);
+            if (spt == 0)      { cA += sig1; cB += sig1; cZ += sig0; }
+            else if (spt == 1) { cA += ps.sbbBits1 + sig1; cB += ps.sbbBits1 + sig1; cZ += ps.sbbBits1 + sig0; }
+            else if (ps.numSigSbb) { cA += sig1; cB += sig1; cZ += sig0; }
+            else cZ = kDqHuge;                                     // "rdCostZ = decisionA.rdCost": can never win
+          } else {
+            cA += (1 << kDqScaleBits) + rice[lvA <= ps.goRiceZero ? lvA - 1 : (lvA < 32 ? lvA : 31)];
+            cB += (1 << kDqScaleBits) + rice[lvB <= ps.goRiceZero ? lvB - 1 : (lvB < 32 ? lvB : 31)];
+            cZ += rice[ps.goRiceZero];
+          }
+          sm.cand[k][0] = cA; sm.cand[k][1] = cZ; sm.cand[k][2] = cB;
+        }
+      }
+      __syncwarp();
+      if (act) {
+        if (!zeroOut) {
+          // decision d collects "A" and "Z" of source sA(d) and "B" of source sB(d): states 0/1 feed decisions 0/2, states 2/3 feed 1/3
+          const int sA = k == 0 ? 0 : k == 1 ? 2 : k == 2 ? 1 : 3, sB = k == 0 ? 1 : k == 1 ? 3 : k == 2 ? 0 : 2;
+          const int lvFromA = sA < 2 ? pqLevel[0] : pqLevel[3];      // pqDataA of source sA
+          const int lvFromB = sB < 2 ? pqLevel[2] : pqLevel[1];      // pqDataB of source sB
+          dCost = kDqHuge >> 2; dLevel = -1; dPrev = -2;
+          // sources are visited in ascending order (xDecide :1474-1477), ties keep the earlier candidate
+          if (sA < sB) {
+            if (sm.cand[sA][0] < dCost) { dCost = sm.cand[sA][0]; dLevel = lvFromA; dPrev = sA; }
+            if (sm.cand[sA][1] < dCost) { dCost = sm.cand[sA][1]; dLevel = 0; dPrev = sA; }
+            if (sm.cand[sB][2] < dCost) { dCost = sm.cand[sB][2]; dLevel = lvFromB; dPrev = sB; }
+          } else {
+            if (sm.cand[sB][2] < dCost) { dCost = sm.cand[sB][2]; dLevel = lvFromB; dPrev = sB; }
+            if (sm.cand[sA][0] < dCost) { dCost = sm.cand[sA][0]; dLevel = lvFromA; dPrev = sA; }
+            if (sm.cand[sA][1] < dCost) { dCost = sm.cand[sA][1]; dLevel = 0; dPrev = sA; }
+          }
+          if (spt == 2) {                                            // checkRdCostSkipSbb :1068-1077
+            const DqState& ss = sm.st[skip * 4 + k];
+            const long long c = ss.rdCost + ss.sbbBits0;
+            if (c < dCost) { dCost = c; dLevel = 0; dPrev = 4 + k; }
+          }
+          if ((k & 1) == 0) {                                        // checkRdCostStart :1051-1066, decisions 0 and 2
+            const int lv = k == 0 ? pqLevel[0] : pqLevel[2];
+            const long long c = (k == 0 ? pqDist[0] : pqDist[2]) + sm.lastX[rom.groupIdx[spX]] + sm.lastY[rom.groupIdx[spY]] +
+                                dq_level_bits(rom, tab.gtx[0], 0, lv);
+            if (c < dCost) { dCost = c; dLevel = lv; dPrev = -1; }
+          }
+        } else if (spt == 2) {                                       // checkRdCostSkipSbbZeroOut :1079-1085
+          const DqState& ss = sm.st[skip * 4 + k];
+          dCost = ss.rdCost + ss.sbbBits0; dLevel = 0; dPrev = 4 + k;
+        }
+        // ---- the decision trellis (entries 4..7 of the reference are implied, see the backward pass)
+        reinterpret_cast<uint32_t*>(trellis + scanIdx)[k] = dq_pack(dLevel, dPrev);
+        if (scanIdx == 0) sm.pathCost[k] = dCost;                    // path costs at the end of the scan
+
+        // ---- state update :1533-1588
+        if (scanIdx) {
+          DqState& cs = sm.st[curr * 4 + k];
+          const DqScanPos nx = scan[scanIdx - 1];
+          const int diag = nx.x + nx.y;
+          const int sigOff = diag < 2 ? 8 : diag < 5 ? 4 : 0;
+          const int gtxOff = diag < 1 ? 16 : diag < 3 ? 11 : diag < 10 ? 6 : 1;
+          const int nextInside = (scanIdx - 1) & 15;
+          if ((scanIdx & 15) == 0) {
+            // ---- State::updateStateEOS :1275-1315 + CommonCtx::update :1317-1397 (after m_commonCtx.swap())
+            const int cSet = prevSet, pSet = currSet;                // the sets after the swap
+            cs.rdCost = dCost;
+            if (dPrev > -2) {
+              const DqState* pst = nullptr;
+              if (dPrev >= 4)      { pst = &sm.st[skip * 4 + dPrev - 4]; cs.numSigSbb = 0; for (int i = 0; i < 8; i++) cs.ctxInit[i] = 0; }
+              else if (dPrev >= 0) { pst = &sm.st[prev * 4 + dPrev]; cs.numSigSbb = pst->numSigSbb + (dLevel != 0); for (int i = 0; i < 8; i++) cs.ctxInit[i] = pst->ctxInit[i]; }
+              else                 { cs.numSigSbb = 1; for (int i = 0; i < 8; i++) cs.ctxInit[i] = 0; }
+              reinterpret_cast<uint8_t*>(cs.ctxInit)[0] = (uint8_t)vmin(255, dLevel);     // insidePos == 0
+              uint8_t* sbbFlags = ctxMem + (size_t)(cSet + k) * ctxStride;
+              uint8_t* levels = sbbFlags + shp.numSbb;
+              const int cp = scan[scanIdx - 1].maxDist;
+              if (pst && pst->refSbbCtxId >= 0) {
+                const uint8_t* srcF = ctxMem + (size_t)(pSet + pst->refSbbCtxId) * ctxStride;
+                const uint8_t* srcL = srcF + shp.numSbb;
+                for (int i = 0; i < shp.numSbb; i++) sbbFlags[i] = srcF[i];
+                for (int i = 0; i < cp; i++) levels[scanIdx + i] = srcL[scanIdx + i];
+              } else {
+                for (int i = 0; i < shp.numSbb; i++) sbbFlags[i] = 0;
+                for (int i = 0; i < cp; i++) levels[scanIdx + i] = 0;
+              }
+              sbbFlags[sbbPosTab[scanIdx >> 4]] = cs.numSigSbb != 0;
+              for (int i = 0; i < 16; i++) levels[scanIdx + i] = reinterpret_cast<const uint8_t*>(cs.ctxInit)[i];
+              const int nsp = sbbPosTab[(scanIdx - 1) >> 4];
+              const int ny = nsp / shp.widthInSbb, nxs = nsp - ny * shp.widthInSbb;
+              const int right = nxs < shp.widthInSbb - 1 ? nsp + 1 : 0, below = ny < shp.heightInSbb - 1 ? nsp + shp.widthInSbb : 0;
+              const int sigNSbb = ((right ? sbbFlags[right] : 0) || (below ? sbbFlags[below] : 0)) ? 1 : 0;
+              cs.numSigSbb = 0;
+              cs.remRegBins = pst ? pst->remRegBins : regBinsInit;
+              cs.goRicePar = 0;
+              cs.refSbbCtxId = k;
+              cs.sbbBits0 = tab.sigSbb[sigNSbb][0]; cs.sbbBits1 = tab.sigSbb[sigNSbb][1];
+              const int scanBeg = scanIdx - 16;
+              const uint8_t* absLevels = levels + scanBeg;
+              for (int id = 0; id < 16; id++) {
+                const DqScanPos nb = scan[scanBeg + id];
+                int sumAbs = 0, sumAbs1 = 0, sumNum = 0;
+                for (int j = 0; j < nb.numOut; j++) {
+                  const int v = absLevels[nb.outPos[j]];
+                  sumAbs += v; sumAbs1 += vmin(4 + (v & 1), v); sumNum += v != 0;
+                }
+                cs.ctxInit[8 + id] = (uint16_t)(sumNum + (sumAbs1 << 3) + (vmin(127, sumAbs) << 8));
+              }
+              for (int i = 0; i < 8; i++) cs.ctxInit[i] = 0;
+              const int tinit = cs.ctxInit[8 + nextInside];
+              const int sumNum = tinit & 7, sumAbs1 = (tinit >> 3) & 31, sumGt1 = sumAbs1 - sumNum;
+              cs.sigCtx = sigOff + vmin((sumAbs1 + 1) >> 1, 3);
+              cs.gtxCtx = gtxOff + (sumGt1 < 4 ? sumGt1 : 4);
+            }
+          } else if (!zeroOut) {
+            // ---- State::updateState<numIPos> :1109-1273
+            cs.rdCost = dCost;
+            if (dPrev > -2) {
+              if (dPrev >= 0) {
+                const DqState& pst = sm.st[prev * 4 + dPrev];
+                cs.numSigSbb = pst.numSigSbb + (dLevel != 0);
+                cs.refSbbCtxId = pst.refSbbCtxId;
+                cs.sbbBits0 = pst.sbbBits0; cs.sbbBits1 = pst.sbbBits1;
+                cs.remRegBins = pst.remRegBins - 1;
+                cs.goRicePar = pst.goRicePar;
+                if (cs.remRegBins >= 4) cs.remRegBins -= dLevel < 2 ? dLevel : 3;
+                for (int i = 0; i < 24; i++) cs.ctxInit[i] = pst.ctxInit[i];
+              } else {
+                cs.numSigSbb = 1; cs.refSbbCtxId = -1;
+                cs.remRegBins = regBinsInit - (dLevel < 2 ? dLevel : 3);
+                for (int i = 0; i < 24; i++) cs.ctxInit[i] = 0;
+              }
+              uint8_t* lv = reinterpret_cast<uint8_t*>(cs.ctxInit);
+              lv[scanIdx & 15] = (uint8_t)vmin(255, dLevel);
+              const uint8_t* nbIn = rom.nbIn[nextInside];
+              const int tinit = cs.ctxInit[8 + nextInside];
+              int sumAbs1 = (tinit >> 3) & 31, sumNum = tinit & 7, sumAbs = tinit >> 8;
+              for (int j = 0; j < nbIn[0]; j++) {
+                const int v = lv[nbIn[1 + j]];
+                sumAbs1 += vmin(4 + (v & 1), v); sumNum += v != 0; sumAbs += v;
+              }
+              if (cs.remRegBins >= 4) {
+                const int sumGt1 = sumAbs1 - sumNum;
+                cs.sigCtx = sigOff + vmin((sumAbs1 + 1) >> 1, 3);
+                cs.gtxCtx = gtxOff + (sumGt1 < 4 ? sumGt1 : 4);
+                cs.goRicePar = rom.goRicePars[vmax(vmin(31, sumAbs - 20), 0)];
+              } else {
+                sumAbs = vmin(31, sumAbs);
+                cs.goRicePar = rom.goRicePars[sumAbs];
+                cs.goRiceZero = rom.goRiceZero[vmax(0, k - 1)][sumAbs];
+              }
+            }
+          }
+        }
+      }
+      // swaps shared by the four lanes of the group (uniform inside the group)
+      if (act && scanIdx) {
+        if ((scanIdx & 15) == 0) { const int t = currSet; currSet = prevSet; prevSet = t; }
+        if (spt == 1) { const int t = prev; prev = skip; skip = t; }
+      }
+      __syncwarp();
+    }
+
+    // ---- best path (:1713-1722) and the backward pass (:1724-1731) fused with Quantizer::dequantBlock (:741-810)
+    if (have && k == 0 && firstTestPos >= 0) {
+      int prevId = -2;
+      long long minPathCost = 0;
+      for (int s = 0; s < 4; s++) if (sm.pathCost[s] < minPathCost) { prevId = s; minPathCost = sm.pathCost[s]; }
+      const int qpDQ = 6 * job.qp_per + job.qp_rem + 1, qpPer = qpDQ / 6, qpRem = qpDQ - 6 * qpPer;
+      const int sqrt2 = (lw + lh) & 1;
+      const int shift = 7 - qpPer - (15 - P.bd - ((lw + lh) >> 1) - sqrt2);
+      const int invScale = rom.invQuantScales[sqrt2 * 6 + qpRem];
+      const long long scaleEff = shift < 0 ? (long long)invScale << -shift : invScale;   // the in-place `invQScale <<= -shift`
+      const long long add = shift < 0 ? 0 : ((1ll << shift) >> 1);
+      int absSum = 0;
+      for (int scanIdx = 0; prevId >= 0; scanIdx++) {
+        int absLevel;
+        if (prevId >= 4 && (scanIdx & 15) != 0) absLevel = 0;        // inside a skipped sub-block: {level 0, prevId unchanged}
+        else {
+          const uint32_t e = reinterpret_cast<const uint32_t*>(trellis + scanIdx)[prevId & 3];   // at eosbb entries 4..7 == 0..3
+          absLevel = (int)(e & 0xffff);
+          prevId = (int)(e >> 16) - 2;
+        }
+        if (absLevel) {
+          const int idx = scan[scanIdx].idx;
+          const bool neg = coeff[idx] < 0;
+          const int state = prevId < 0 ? 0 : (prevId & 3);           // the state this coefficient was quantised in
+          P.level[job.offset + idx] = neg ? -absLevel : absLevel;
+          const long long qIdx = 2ll * absLevel - (state >> 1);
+          long long nom = ((neg ? -qIdx : qIdx) * scaleEff + add) >> (shift < 0 ? 0 : shift);
+          nom = nom < -32768 ? -32768 : (nom > 32767 ? 32767 : nom);
+          P.deq[job.offset + idx] = (int32_t)nom;
+          absSum += absLevel;
+        }
+      }
+      P.results[P.order[ji]].abs_sum_level = absSum;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace

@@ -38,6 +38,11 @@ struct TuParams {
   const int16_t* orig;
   int stride, bd;
   const TrRom* rom;
+  // dependent quantisation runs between two passes of this kernel (vvcb_dq.cuh): pass 0 leaves the coefficients of those jobs
+  // in dqCoeff, pass 1 picks their dequantised coefficients up from dqDeq and finishes (inverse, reconstruction, SSE)
+  int32_t* dqCoeff;
+  const int32_t* dqDeq;
+  int phase;
 };
 
 __device__ __forceinline__ int clip16(int v) { return vmin(vmax(v, -32768), 32767); }
@@ -77,7 +82,13 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
     const int16_t* mv = tr_kernel(rom, ver, lh);
     const int16_t* resi = P.resi + job.offset;
     const int hp = h + 1;
+    const bool dq = (job.flags & (VVCB_TU_QUANT | VVCB_TU_DEPQUANT)) == (VVCB_TU_QUANT | VVCB_TU_DEPQUANT);
+    if (P.phase == 1 && !dq) continue;
     __syncthreads();
+    if (P.phase == 1) {
+      for (int i = threadIdx.x; i < n; i += kTuThreads) A[i] = P.dqDeq[job.offset + i];
+      __syncthreads();
+    } else {
     for (int i = threadIdx.x; i < n; i += kTuThreads) A[i] = ts ? ((int)resi[i] << trShift) : (int)resi[i];
     __syncthreads();
     if (!ts) {
@@ -106,12 +117,25 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
       }
       __syncthreads();
     }
-    long long part = 0;
-    for (int i = threadIdx.x; i < n; i += kTuThreads) {
-      part += vabs(A[i]);
-      if (P.coeff) P.coeff[job.offset + i] = A[i];
     }
-    const long long sumAbs = block_sum(part, red);
+    long long sumAbs = 0;
+    if (P.phase == 0) {
+      long long part = 0;
+      for (int i = threadIdx.x; i < n; i += kTuThreads) {
+        part += vabs(A[i]);
+        if (P.coeff) P.coeff[job.offset + i] = A[i];
+        if (dq) P.dqCoeff[job.offset + i] = A[i];
+      }
+      sumAbs = block_sum(part, red);
+      if (dq) {                                                          // the quantiser is another kernel: finish in pass 1
+        if (threadIdx.x == 0) {
+          vvcb_tu_result r;
+          r.abs_sum_coeff = (int)sumAbs; r.abs_sum_level = 0; r.sse = 0;
+          P.results[ji] = r;
+        }
+        continue;
+      }
+    }
     int absLevel = 0;
     unsigned long long sse = 0;
     if (job.flags & VVCB_TU_QUANT) {
@@ -124,6 +148,7 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
       const int tgt = vmin(16, 32 + rightShift - 7);
       const int inMin = -(1 << (tgt - 1)), inMax = (1 << (tgt - 1)) - 1;
       long long lpart = 0;
+      if (P.phase == 0)
       for (int i = threadIdx.x; i < n; i += kTuThreads) {
         const int c = A[i];
         const long long t = (long long)vabs(c) * qScale;
@@ -173,6 +198,10 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
         }
       }
       sse = (unsigned long long)block_sum(spart, red);
+    }
+    if (P.phase == 1) {
+      if (threadIdx.x == 0) P.results[ji].sse = sse;
+      continue;
     }
     if (threadIdx.x == 0) {
       double scale = 1.0;

@@ -31,11 +31,14 @@ assert VISIT_DTYPE.itemsize == 80 and RESULT_DTYPE.itemsize == 368 and DETAIL_DT
     (VISIT_DTYPE.itemsize, RESULT_DTYPE.itemsize, DETAIL_DTYPE.itemsize)
 
 
-TU_QUANT = 1
+TU_QUANT, TU_DEPQUANT = 1, 2
 TU_JOB_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('log2w', 'u1'), ('log2h', 'u1'), ('mts_idx', 'u1'), ('flags', 'u1'),
-                         ('qp_per', '<i2'), ('qp_rem', '<i2'), ('offset', '<u4')], align=True)
+                         ('qp_per', '<i2'), ('qp_rem', '<i2'), ('offset', '<u4'), ('rate_idx', '<u2'), ('lfnst_idx', 'u1'), ('pad', 'u1'),
+                         ('cbf_delta_bits', '<i4'), ('lambda', '<f8')], align=True)
 TU_RESULT_DTYPE = np.dtype([('abs_sum_coeff', '<i4'), ('abs_sum_level', '<i4'), ('sse', '<u8')], align=True)
-assert TU_JOB_DTYPE.itemsize == 16 and TU_RESULT_DTYPE.itemsize == 16
+DQ_RATES_DTYPE = np.dtype([('sig_sbb', '<u4', (2, 2)), ('sig', '<u4', (3, 12, 2)), ('par', '<u4', (21, 2)), ('gt1', '<u4', (21, 2)),
+                           ('gt2', '<u4', (21, 2)), ('last_x', '<u4', (20, 2)), ('last_y', '<u4', (20, 2))])
+assert TU_JOB_DTYPE.itemsize == 32 and TU_RESULT_DTYPE.itemsize == 16 and DQ_RATES_DTYPE.itemsize == 1128
 
 
 FEAT_CU_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('w', 'u1'), ('h', 'u1'), ('qt_depth', 'u1'), ('mt_depth', 'u1')])
@@ -84,8 +87,8 @@ def load_library():
         L.vvcb_dev_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.vvcb_dev_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.vvcb_sync.argtypes = [C.c_void_p]
-        L.vvcb_tu_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
-                                   C.c_void_p, C.c_void_p]
+        L.vvcb_tu_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
         L.vvcb_mts_preselect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vvcb_mts_preselect.restype = None
         L.vvcb_ctu_hads_islice.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -177,8 +180,9 @@ class IntraCostEngine:
         return pred
 
     # ---- TU coding
-    def tu_eval(self, jobs, resi, pred=None, want_coeff=False, want_level=False, want_reco=False):
-        """vvcb_tu_eval.  resi / pred: flat int16 arrays indexed by job['offset'].  Returns dict of outputs."""
+    def tu_eval(self, jobs, resi, pred=None, want_coeff=False, want_level=False, want_reco=False, rates=None):
+        """vvcb_tu_eval.  resi / pred: flat int16 arrays indexed by job['offset']; rates: DQ_RATES_DTYPE array indexed by
+        job['rate_idx'] (jobs flagged TU_DEPQUANT).  Returns dict of outputs."""
         jobs = np.ascontiguousarray(jobs, TU_JOB_DTYPE)
         resi = np.ascontiguousarray(resi, np.int16).ravel()
         pred = None if pred is None else np.ascontiguousarray(pred, np.int16).ravel()
@@ -190,7 +194,9 @@ class IntraCostEngine:
             out['level'] = np.zeros(ns, np.int32)
         if want_reco:
             out['reco'] = np.zeros(ns, np.int16)
+        rates = None if rates is None else np.ascontiguousarray(rates, DQ_RATES_DTYPE)
         self._ck(self._lib.vvcb_tu_eval(self._ctx, _ptr(jobs), len(jobs), _ptr(resi), _ptr(pred) if pred is not None else None, ns,
+                                        _ptr(rates) if rates is not None else None, 0 if rates is None else len(rates),
                                         _ptr(out['coeff']) if want_coeff else None, _ptr(out['level']) if want_level else None,
                                         _ptr(out['reco']) if want_reco else None, _ptr(out['results'])))
         return out
