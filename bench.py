@@ -123,8 +123,7 @@ def run_b200(args, rank, world, local_rank, dist):
 
     frames = [synth_luma(f) for f in range(NFRAMES)]
     # this rank's share of the (frame, qp) pairs: all-intra frames are independent -> no collective on the path
-    pairs = [(s % NFRAMES, QPS[s % len(QPS)]) for s in range(NFRAMES * len(QPS))]
-    mine = pairs[rank::world] if world > 1 else pairs
+    mine = vb.shard.shard_units(vb.shard.work_units(NFRAMES, QPS), rank, world)
 
     # ---- resident set-up
     pitch = (W + 63) & ~63
@@ -167,11 +166,7 @@ def run_b200(args, rank, world, local_rank, dist):
     k_plan, k_eval, k_lists, k_n = eng.kernel_times()
     eng.kernel_timing(False)
     launches = eng.launch_count - launches0
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms_total], dtype=torch.float64, device='cuda:%d' % local_rank)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = vb.shard.max_over_ranks(ms_total, dist, 'cuda:%d' % local_rank)
 
     # ---- end to end through the C ABI with host buffers
     h_vis = {}
@@ -205,16 +200,13 @@ def run_b200(args, rank, world, local_rank, dist):
         e2e_step(2 + s)
     eng.sync()
     e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        import torch
-        t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda:%d' % local_rank)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = vb.shard.max_over_ranks(e2e_s, dist, 'cuda:%d' % local_rank)
     h2d = 2 * H * W * 2 + n * vb.VISIT_DTYPE.itemsize
     d2h = n * vb.RESULT_DTYPE.itemsize
 
     if rank != 0:
         return
+    tu_stage = None if args.no_tu_stage else tu_stage_leg(eng, vb, base, frames[0], int_peak)
     ms_step = ms_total / args.steps
     value = world * args.steps * CTUS_PER_FRAME / (ms_total * 1e-3)
     eval_ms = k_eval / max(1, k_n)
@@ -249,21 +241,71 @@ def run_b200(args, rank, world, local_rank, dist):
                     'ops_model': 'SURVEY.md 8d: 13 + (6|7|8|9 by SATD tile) = 19..22 integer ops per predicted sample'},
         'kernel_ms': {'plan': k_plan / max(1, k_n), 'eval': eval_ms, 'lists': k_lists / max(1, k_n)},
     }
+    if tu_stage:
+        out['tu_stage'] = tu_stage
     if world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline_port(base, frames[0])
     print(json.dumps(out))
 
 
+def tu_stage_leg(eng, vb, base, frame, int_peak):
+    """Second stage of the cost evaluation, reported next to the headline (its own unit: TUs/s): one DCT-II candidate per
+    candidate CU of frame 0 (sides <= 32) through vvcb_tu_eval -- forward transform, dependent quantisation, inverse,
+    reconstruction, SSE -- with host buffers; kernel times from CUDA events around each launch."""
+    from oracle import oracle_py as O
+    jobs, resi, pred, rates = vb.build_tu_sweep(frame, base, 32, BITS)
+    hj = eng.host_array(len(jobs), vb.TU_JOB_DTYPE)
+    hj[:] = jobs
+    hr = eng.host_array(resi.size, np.int16)
+    hr[:] = resi
+    hp = eng.host_array(pred.size, np.int16)
+    hp[:] = pred
+    eng.frame_begin(frame)
+    eng.tu_eval(hj, hr, hp, rates=rates)                      # warm-up (allocations)
+    eng.kernel_timing(True)
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = eng.tu_eval(hj, hr, hp, rates=rates)
+    wall = (time.perf_counter() - t0) / reps
+    k_tr, k_dq, k_rec, k_n = eng.tu_kernel_times()
+    eng.kernel_timing(False)
+    lw, lh = jobs['log2w'].astype(np.int64), jobs['log2h'].astype(np.int64)
+    # SURVEY.md 8d: a separable transform costs w*h*(w_out + h_out) MACs; forward + inverse
+    macs = float((2 * (1 << (lw + lh)) * ((1 << lw) + (1 << lh))).sum())
+    # CPU port on a bounded sample of the same jobs
+    sel = np.linspace(0, len(jobs) - 1, 3000).astype(int)
+    t0 = time.perf_counter()
+    for i in sel:
+        j = jobs[i]
+        w, h = 1 << int(j['log2w']), 1 << int(j['log2h'])
+        sl = slice(int(j['offset']), int(j['offset']) + w * h)
+        co = O.fwd_transform(resi[sl].reshape(h, w), BITS, 0)
+        lvl, _ = O.dep_quant(co, BITS, 0, 0, 6 * int(j['qp_per']) + int(j['qp_rem']), float(j['lambda']), rates[0], 0)
+        O.inv_transform(O.dep_dequant(lvl, BITS, 6 * int(j['qp_per']) + int(j['qp_rem'])), BITS, 0)
+    cpu_s = time.perf_counter() - t0
+    kern_ms = (k_tr + k_dq + k_rec) / max(1, k_n)
+    return {'workload': 'frame 0, one DCT-II candidate per candidate CU with sides <= 32 (%d TUs, %d samples), QP 32, dependent quantisation' % (len(jobs), resi.size),
+            'tus_per_s_kernels': len(jobs) / (kern_ms * 1e-3) if kern_ms else None,
+            'tus_per_s_e2e': len(jobs) / wall,
+            'kernel_ms': {'transform': k_tr / max(1, k_n), 'dep_quant': k_dq / max(1, k_n), 'reconstruct': k_rec / max(1, k_n)},
+            'e2e_ms': wall * 1e3, 'h2d_bytes': int(jobs.nbytes + resi.nbytes + pred.nbytes), 'd2h_bytes': int(out['results'].nbytes),
+            'transform_gmacs_per_s': macs / (((k_tr + k_rec) / max(1, k_n)) * 1e-3) / 1e9 if k_n else None,
+            'transform_int_alu_frac': (macs / (((k_tr + k_rec) / max(1, k_n)) * 1e-3) / 1e9) / int_peak[0] if k_n and int_peak[0] else None,
+            'nonzero_tu_fraction': float((out['results']['abs_sum_level'] > 0).mean()),
+            'cpu_baseline': {'value': len(sel) / cpu_s, 'unit': 'TU/s', 'cores': 1, 'kind': 'port',
+                             'sample': 'oracle transform + dependent quantisation + inverse on %d of the jobs (ctypes call overhead included), %.1f s' % (len(sel), cpu_s)}}
+
+
 def cpu_baseline_port(base, frame):
     """The oracle (plain-C port of the same sweep) on one host core, on the visits of the first two CTUs."""
     from oracle import oracle_py as O
-    sel = base[(base['x'] < 256) & (base['y'] < 128)]
-    sel = sel[(sel['x'] + (1 << sel['log2w'].astype(int)) <= 256)]
+    sel = base[base['y'] < 256]                          # the first two CTU rows of the frame: 30 CTUs
     t0 = time.perf_counter()
     O.rmd_batch(frame, frame, BITS, CTU, sel)
     dt = time.perf_counter() - t0
-    return {'value': 2.0 / dt, 'unit': 'CTU/s', 'cores': 1, 'kind': 'port',
-            'sample': 'oracle/vvc_oracle.c, same exhaustive sweep, the %d visits of the first two CTUs of frame 0, %.1f s' % (len(sel), dt)}
+    return {'value': 30.0 / dt, 'unit': 'CTU/s', 'cores': 1, 'kind': 'port',
+            'sample': 'oracle/vvc_oracle.c, same exhaustive sweep, the %d visits of the first two CTU rows (30 CTUs) of frame 0, %.1f s' % (len(sel), dt)}
 
 
 def run_reference(args, rank, world):
@@ -328,6 +370,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-tu-stage', action='store_true')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

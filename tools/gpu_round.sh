@@ -19,4 +19,7 @@ for k in 27:eval8x8ang 30:eval16x8ang 18:eval4x4ang; do
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rmd_lists_kernel -s 1 -c 1 -o gpurun_out/prof_lists_$tag -f \
   python tools/profile_sweep.py --width 1920 --height 1080 --passes 2 > gpurun_out/ncu_full_lists_$tag.log 2>&1; echo "ncu lists rc=$?"
+python tools/profile_tu.py --width 1920 --height 1080 --passes 2 > gpurun_out/prof_tu_plain_$tag.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dq_kernel|tu_eval_kernel" -s 3 -c 3 -o gpurun_out/prof_tu_$tag -f \
+  python tools/profile_tu.py --width 1920 --height 1080 --passes 2 > gpurun_out/ncu_full_tu_$tag.log 2>&1; echo "ncu tu rc=$?"
 ls -la gpurun_out

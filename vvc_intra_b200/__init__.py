@@ -12,3 +12,5 @@ from .partition import enumerate_root_candidates, frame_candidates, candidate_av
 __all__ = ['IntraCostEngine', 'EngineError', 'VISIT_DTYPE', 'RESULT_DTYPE', 'DETAIL_DTYPE', 'NUM_SLOTS', 'SLOT_MRL1', 'SLOT_MRL3',
            'SLOT_MIP', 'SAT_NONE', 'library_path', 'enumerate_root_candidates', 'frame_candidates',
            'candidate_availability', 'build_sweep_visits']
+from . import shard
+from .tu_sweep import build_tu_sweep, default_dq_rates, lambda_for_qp

@@ -52,6 +52,7 @@ struct vvcb_ctx {
   void* dTu[14]; size_t capTu[14];  // TU scratch: jobs, resi, pred, coeff, level, reco, results; DepQuant: coeff in, dequantised out,
                                     // job order, context prices, derived rate tables, per-group context memory + trellis
   DqRom* dDqRom;
+  float tuMs[3]; int tuTimed; cudaEvent_t tev[4];   // per-kernel timing of vvcb_tu_eval: transform pass, dependent quantisation, reconstruction pass
   void* dFeat[2]; size_t capFeat[2]; // feature scratch: jobs / per-CTU sums, results
   // copy/compute pipeline of vvcb_rmd_eval for large host batches
   cudaStream_t sIn, sOut; cudaEvent_t evIn[2], evComp[2], evOut[2];
@@ -124,6 +125,7 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
   for (int i = 0; i < 4; i++) if ((e = cudaEventCreate(&ctx->kev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
+  for (int i = 0; i < 4; i++) if ((e = cudaEventCreate(&ctx->tev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
   Rom* h = new Rom();
   fill_rom(*h);
   if ((e = cudaMalloc(&ctx->dRom, sizeof(Rom))) != cudaSuccess) { delete h; return fail("cudaMalloc(rom)", e); }
@@ -167,7 +169,7 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
     cudaStreamDestroy(ctx->sIn); cudaStreamDestroy(ctx->sOut);
   }
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
-  for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->kev[i]);
+  for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->kev[i]); cudaEventDestroy(ctx->tev[i]); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -229,6 +231,7 @@ extern "C" int vvcb_kernel_timing(vvcb_ctx* ctx, int on)
 {
   if (!ctx) return VVCB_ERR_ARG;
   ctx->timing = on; ctx->timedLaunches = 0; ctx->kms[0] = ctx->kms[1] = ctx->kms[2] = 0.f;
+  ctx->tuTimed = 0; ctx->tuMs[0] = ctx->tuMs[1] = ctx->tuMs[2] = 0.f;
   return VVCB_OK;
 }
 
@@ -539,8 +542,11 @@ extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const
     CK(cudaMemcpyAsync(ctx->dTu[9], order.data(), (size_t)nDq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dTu[10], rates, (size_t)n_rates * sizeof(vvcb_dq_rates), cudaMemcpyHostToDevice, ctx->stream));
   }
+  const bool tm = ctx->timing != 0;
+  if (tm) CK(cudaEventRecord(ctx->tev[0], ctx->stream));
   tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
   ctx->launches++;
+  if (tm) CK(cudaEventRecord(ctx->tev[1], ctx->stream));
   if (nDq) {
     dq_rate_kernel<<<n_rates, 32, 0, ctx->stream>>>(static_cast<const vvcb_dq_rates*>(ctx->dTu[10]), n_rates, static_cast<DqRateTab*>(ctx->dTu[11]));
     DqParams D;
@@ -549,16 +555,31 @@ extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const
     D.rates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]); D.tabs = static_cast<const DqRateTab*>(ctx->dTu[11]);
     D.rom = ctx->dDqRom; D.scratch = static_cast<uint8_t*>(ctx->dTu[12]); D.bd = ctx->bd;
     dq_kernel<<<dqGrid, kDqThreads, 0, ctx->stream>>>(D);
+    if (tm) CK(cudaEventRecord(ctx->tev[2], ctx->stream));
     P.phase = 1;
     tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
     ctx->launches += 3;
-  }
+  } else if (tm) CK(cudaEventRecord(ctx->tev[2], ctx->stream));
+  if (tm) CK(cudaEventRecord(ctx->tev[3], ctx->stream));
   CK(cudaGetLastError());
   if (coeff) CK(cudaMemcpyAsync(coeff, ctx->dTu[3], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (level) CK(cudaMemcpyAsync(level, ctx->dTu[4], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (reco) CK(cudaMemcpyAsync(reco, ctx->dTu[5], n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(results, ctx->dTu[6], (size_t)n * sizeof(vvcb_tu_result), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (tm) {
+    for (int i = 0; i < 3; i++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1])); ctx->tuMs[i] += ms; }
+    ctx->tuTimed++;
+  }
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_tu_kernel_times(vvcb_ctx* ctx, float ms[3], int* calls)
+{
+  if (!ctx || !ms) return VVCB_ERR_ARG;
+  for (int i = 0; i < 3; i++) { ms[i] = ctx->tuMs[i]; ctx->tuMs[i] = 0.f; }
+  if (calls) *calls = ctx->tuTimed;
+  ctx->tuTimed = 0;
   return VVCB_OK;
 }
 

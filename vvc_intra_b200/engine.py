@@ -96,6 +96,7 @@ def load_library():
         L.vvcb_frame_bind_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.vvcb_kernel_timing.argtypes = [C.c_void_p, C.c_int]
         L.vvcb_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.vvcb_tu_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.vvcb_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.vvcb_timer_start.argtypes = [C.c_void_p]
         L.vvcb_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -158,6 +159,13 @@ class IntraCostEngine:
         ms = (C.c_float * 3)()
         n = C.c_int()
         self._ck(self._lib.vvcb_kernel_times(self._ctx, ms, C.byref(n)))
+        return ms[0], ms[1], ms[2], n.value
+
+    def tu_kernel_times(self):
+        """(ms transform pass, ms dependent quantisation, ms reconstruction pass, timed calls) since the last call."""
+        ms = (C.c_float * 3)()
+        n = C.c_int()
+        self._ck(self._lib.vvcb_tu_kernel_times(self._ctx, ms, C.byref(n)))
         return ms[0], ms[1], ms[2], n.value
 
     # ---- rough mode decision
