@@ -88,10 +88,9 @@ extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_
   static DqRom dqRom;
   fill_tr_rom(rom);
   fill_dq_rom(dqRom);
-  std::vector<int> order, bySize[9];
+  std::vector<int> order;
   for (int i = 0; i < n; i++)
-    if ((jobs[i].flags & (VVCB_TU_QUANT | VVCB_TU_DEPQUANT)) == (VVCB_TU_QUANT | VVCB_TU_DEPQUANT)) bySize[jobs[i].log2w + jobs[i].log2h - 4].push_back(i);
-  for (int c = 8; c >= 0; c--) order.insert(order.end(), bySize[c].begin(), bySize[c].end());
+    if ((jobs[i].flags & (VVCB_TU_QUANT | VVCB_TU_DEPQUANT)) == (VVCB_TU_QUANT | VVCB_TU_DEPQUANT)) order.push_back(i);
   const int nDq = (int)order.size();
   std::vector<int32_t> dqCoeff(nSamples), dqDeq(nSamples, 0);
   memset(level, 0, nSamples * sizeof(int32_t));
@@ -105,8 +104,11 @@ extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_
     emu_launch(nRates, 32, [&] { dq_rate_kernel(rates, nRates, tabs.data()); });
     const int grid = 2;
     std::vector<uint8_t> scratch((size_t)grid * kDqGroups * kDqSlotBytes);
+    std::vector<int> firstRaw(nDq), orderSorted(nDq), firstSorted(nDq);
+    emu_launch(2, kDqThreads, [&] { dq_first_kernel(jobs, order.data(), nDq, dqCoeff.data(), &dqRom, bd, firstRaw.data()); });
+    emu_launch(1, 1024, [&] { dq_sort_kernel(order.data(), firstRaw.data(), nDq, orderSorted.data(), firstSorted.data()); });
     DqParams D;
-    D.jobs = jobs; D.order = order.data(); D.n = nDq; D.coeff = dqCoeff.data(); D.level = level; D.deq = dqDeq.data(); D.results = results;
+    D.jobs = jobs; D.order = orderSorted.data(); D.firstPos = firstSorted.data(); D.n = nDq; D.coeff = dqCoeff.data(); D.level = level; D.deq = dqDeq.data(); D.results = results;
     D.rates = rates; D.tabs = tabs.data(); D.rom = &dqRom; D.scratch = scratch.data(); D.bd = bd;
     emu_launch(grid, kDqThreads, [&] { dq_kernel(D); });
     P.phase = 1;

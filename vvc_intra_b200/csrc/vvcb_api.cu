@@ -483,8 +483,7 @@ extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const
   if (n < 0 || n_rates < 0 || (n > 0 && (!jobs || !resi || !results))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: bad argument"); return VVCB_ERR_ARG; }
   if (n == 0) return VVCB_OK;
   bool anyQuant = false;
-  std::vector<int> order;                 // DepQuant jobs, largest TU first (the groups of a warp then walk scans of similar length)
-  std::vector<int> bySize[9];
+  std::vector<int> order;                 // DepQuant jobs (sorted on the device by scan length once the coefficients exist)
   for (int i = 0; i < n; i++) {
     const vvcb_tu_job& j = jobs[i];
     const size_t sz = (size_t)1 << (j.log2w + j.log2h);
@@ -498,10 +497,9 @@ extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const
     if (q) ok = ok && ctx->bOrig && j.x >= 0 && j.y >= 0 && j.x + (1 << j.log2w) <= ctx->width && j.y + (1 << j.log2h) <= ctx->height;
     if (dq) ok = ok && j.mts_idx != 1 && rates && j.rate_idx < n_rates && j.lfnst_idx <= 2 && j.lambda > 0.0;   // CL/DepQuant.cpp:1757: TS goes to RDOQ
     if (!ok) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: job %d is malformed", i); return VVCB_ERR_ARG; }
-    if (dq) bySize[j.log2w + j.log2h - 4].push_back(i);
+    if (dq) order.push_back(i);
   }
   if (anyQuant && !pred) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: VVCB_TU_QUANT needs the prediction samples"); return VVCB_ERR_ARG; }
-  for (int c = 8; c >= 0; c--) order.insert(order.end(), bySize[c].begin(), bySize[c].end());
   const int nDq = (int)order.size();
   CK(cudaSetDevice(ctx->device));
   int rc;
@@ -522,6 +520,7 @@ extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const
     if ((rc = tu_buf(ctx, 10, (size_t)n_rates * sizeof(vvcb_dq_rates)))) return rc;
     if ((rc = tu_buf(ctx, 11, (size_t)n_rates * sizeof(DqRateTab)))) return rc;
     if ((rc = tu_buf(ctx, 12, (size_t)dqGrid * kDqGroups * kDqSlotBytes))) return rc;
+    if ((rc = tu_buf(ctx, 13, (size_t)nDq * 3 * sizeof(int)))) return rc;
   }
   CK(cudaMemcpyAsync(ctx->dTu[0], jobs, (size_t)n * sizeof(vvcb_tu_job), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->dTu[1], resi, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -550,7 +549,13 @@ extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const
   if (nDq) {
     dq_rate_kernel<<<n_rates, 32, 0, ctx->stream>>>(static_cast<const vvcb_dq_rates*>(ctx->dTu[10]), n_rates, static_cast<DqRateTab*>(ctx->dTu[11]));
     DqParams D;
-    D.jobs = P.jobs; D.order = static_cast<const int*>(ctx->dTu[9]); D.n = nDq;
+    int* firstRaw = static_cast<int*>(ctx->dTu[13]);
+    int* orderSorted = firstRaw + nDq;
+    int* firstSorted = firstRaw + 2 * nDq;
+    const int firstGrid = (nDq + kDqGroups - 1) / kDqGroups < ctx->numSms * 8 ? (nDq + kDqGroups - 1) / kDqGroups : ctx->numSms * 8;
+    dq_first_kernel<<<firstGrid, kDqThreads, 0, ctx->stream>>>(P.jobs, static_cast<const int*>(ctx->dTu[9]), nDq, P.dqCoeff, ctx->dDqRom, ctx->bd, firstRaw);
+    dq_sort_kernel<<<1, 1024, 0, ctx->stream>>>(static_cast<const int*>(ctx->dTu[9]), firstRaw, nDq, orderSorted, firstSorted);
+    D.jobs = P.jobs; D.order = orderSorted; D.firstPos = firstSorted; D.n = nDq;
     D.coeff = P.dqCoeff; D.level = P.level; D.deq = static_cast<int32_t*>(ctx->dTu[8]); D.results = P.results;
     D.rates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]); D.tabs = static_cast<const DqRateTab*>(ctx->dTu[11]);
     D.rom = ctx->dDqRom; D.scratch = static_cast<uint8_t*>(ctx->dTu[12]); D.bd = ctx->bd;
@@ -558,7 +563,7 @@ extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const
     if (tm) CK(cudaEventRecord(ctx->tev[2], ctx->stream));
     P.phase = 1;
     tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
-    ctx->launches += 3;
+    ctx->launches += 5;
   } else if (tm) CK(cudaEventRecord(ctx->tev[2], ctx->stream));
   if (tm) CK(cudaEventRecord(ctx->tev[3], ctx->stream));
   CK(cudaGetLastError());

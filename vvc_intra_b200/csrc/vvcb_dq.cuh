@@ -53,9 +53,9 @@ struct DqRateTab {
   int32_t sigSbb[2][2];
 };
 
-struct DqState {             // 96 bytes
+struct alignas(16) DqState { // 96 bytes
+  uint16_t  ctxInit[24];     // m_absLevelsAndCtxInit (first: copied as three 16-byte words)
   long long rdCost;
-  uint16_t  ctxInit[24];     // m_absLevelsAndCtxInit
   int       numSigSbb, remRegBins, refSbbCtxId;
   int       sbbBits0, sbbBits1;
   int       sigCtx, gtxCtx;  // indices into DqRateTab::sig[set(stateId)] / gtx
@@ -72,7 +72,8 @@ struct DqGroupSmem {
 
 struct DqParams {
   const vvcb_tu_job* jobs;
-  const int* order;          // DepQuant job indices, largest TU first
+  const int* order;          // DepQuant job indices sorted by first test position, longest scan first (dq_sort_kernel)
+  const int* firstPos;       // first test position of order[i] (-1: nothing to quantise)
   int n;                     // number of DepQuant jobs
   const int32_t* coeff;      // forward-transform output (dense per job at job.offset)
   int32_t* level;            // out: levels (zero-filled by the caller)
@@ -154,6 +155,61 @@ VHD DqQuant dq_init_quant(const DqRom& rom, int bd, int lw, int lh, int qp, doub
   return q;
 }
 
+// ---- first test position of every job (:1638-1662), one 4-lane group per job ---------------------------------
+// jobsIdx: DepQuant job indices in any order; firstOut[i] belongs to jobsIdx[i]
+__global__ void __launch_bounds__(kDqThreads) dq_first_kernel(const vvcb_tu_job* jobs, const int* jobsIdx, int n, const int32_t* coeffAll,
+                                                              const DqRom* romp, int bd, int* firstOut)
+{
+  const DqRom& rom = *romp;
+  const int k = threadIdx.x & 3;
+  for (int base = blockIdx.x * kDqGroups; base < n; base += gridDim.x * kDqGroups) {
+    const int i = base + (threadIdx.x >> 2);
+    int firstTestPos = -1;
+    if (i < n) {
+      const vvcb_tu_job job = jobs[jobsIdx[i]];
+      const int lw = job.log2w, lh = job.log2h, w = 1 << lw, h = 1 << lh;
+      const DqShape shp = rom.shape[lw - 2][lh - 2];
+      const DqScanPos* scan = rom.pos + shp.first;
+      const int32_t* coeff = coeffAll + job.offset;
+      const DqQuant Q = dq_init_quant(rom, bd, lw, lh, 6 * job.qp_per + job.qp_rem, job.lambda);
+      const bool zeroOutTu = job.mts_idx > 1 && (w == 32 || h == 32);
+      int start = shp.numCoeff - 1;                                 // positions past the 32x32 region are zero-out fillers
+      if (job.lfnst_idx > 0) start = vmin(start, ((w == 4 && h == 4) || (w == 8 && h == 8)) ? 7 : 15);
+      const int limX = (w == 32 && zeroOutTu) ? 16 : 32, limY = (h == 32 && zeroOutTu) ? 16 : 32;
+      for (int s = start - k; s >= 0; s -= 4) {
+        const DqScanPos sp = scan[s];
+        if (sp.x >= limX || sp.y >= limY) continue;
+        if (vabs(coeff[sp.idx]) > Q.thres) { firstTestPos = s; break; }
+      }
+    }
+    firstTestPos = vmax(firstTestPos, __shfl_xor_sync(0xffffffffu, firstTestPos, 1));
+    firstTestPos = vmax(firstTestPos, __shfl_xor_sync(0xffffffffu, firstTestPos, 2));
+    if (i < n && k == 0) firstOut[i] = firstTestPos;
+  }
+}
+
+// Counting sort of the jobs by first test position, longest scan first, so that the eight groups of a warp walk scans of the
+// same length and reach their sub-block boundaries in the same iteration.  One block; 1025 bins.
+__global__ void __launch_bounds__(1024) dq_sort_kernel(const int* jobsIdx, const int* firstIn, int n, int* orderOut, int* firstOut)
+{
+  __shared__ int bin[1025];
+  for (int i = threadIdx.x; i < 1025; i += blockDim.x) bin[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&bin[firstIn[i] + 1], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {                       // exclusive prefix over descending keys
+    int acc = 0;
+    for (int b = 1024; b >= 0; b--) { const int c = bin[b]; bin[b] = acc; acc += c; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int f = firstIn[i];
+    const int at = atomicAdd(&bin[f + 1], 1);
+    orderOut[at] = jobsIdx[i];
+    firstOut[at] = f;
+  }
+}
+
 // bits of an absolute level coded with regular bins under the state's greater-than contexts (:977-990)
 __device__ __forceinline__ long long dq_level_bits(const DqRom& rom, const int32_t* gtx, int goRicePar, int absLevel)
 {
@@ -164,7 +220,10 @@ __device__ __forceinline__ long long dq_level_bits(const DqRom& rom, const int32
 
 __device__ __forceinline__ uint32_t dq_pack(int absLevel, int prevId) { return (uint32_t)(absLevel & 0xffff) | ((uint32_t)(prevId + 2) << 16); }
 
-__global__ void __launch_bounds__(kDqThreads) dq_kernel(DqParams P)
+#ifndef VVCB_DQ_MIN_CTAS
+#define VVCB_DQ_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kDqThreads, VVCB_DQ_MIN_CTAS) dq_kernel(DqParams P)
 {
   __shared__ DqGroupSmem smem[kDqGroups];
   const DqRom& rom = *P.rom;
@@ -195,22 +254,10 @@ __global__ void __launch_bounds__(kDqThreads) dq_kernel(DqParams P)
     bool zeroOutTu = false;
     if (job.mts_idx > 1) { effH = h == 32 ? 16 : h; effW = w == 32 ? 16 : w; zeroOutTu = effH < h || effW < w; }
     const int regBinsInit = (vmin(32, effW) * vmin(32, effH) * 28) >> 4;
-    const int ctxStride = shp.numSbb + shp.numCoeff;
+    const int sbbPad = (shp.numSbb + 15) & ~15;                    // the sub-block flags, padded so that the level arrays and the
+    const int ctxStride = sbbPad + shp.numCoeff;                   // eight context sets stay 16-byte aligned (copied as uint4)
 
-    // ---- first test position (:1638-1662): highest scan index whose coefficient exceeds the threshold
-    int firstTestPos = -1;
-    if (have) {
-      int start = shp.numCoeff - 1;                                 // positions past the 32x32 region are zero-out fillers
-      if (job.lfnst_idx > 0) start = vmin(start, ((w == 4 && h == 4) || (w == 8 && h == 8)) ? 7 : 15);
-      const int limX = (w == 32 && zeroOutTu) ? 16 : 32, limY = (h == 32 && zeroOutTu) ? 16 : 32;
-      for (int s = start - k; s >= 0; s -= 4) {
-        const DqScanPos sp = scan[s];
-        if (sp.x >= limX || sp.y >= limY) continue;
-        if (vabs(coeff[sp.idx]) > Q.thres) { firstTestPos = s; break; }
-      }
-    }
-    firstTestPos = vmax(firstTestPos, __shfl_xor_sync(0xffffffffu, firstTestPos, 1));
-    firstTestPos = vmax(firstTestPos, __shfl_xor_sync(0xffffffffu, firstTestPos, 2));
+    const int firstTestPos = have ? P.firstPos[ji] : -1;           // dq_first_kernel, :1638-1662
     int steps = firstTestPos + 1;
     for (int o = 4; o < 32; o <<= 1) steps = vmax(steps, __shfl_xor_sync(0xffffffffu, steps, o));
 
@@ -244,8 +291,12 @@ __global__ void __launch_bounds__(kDqThreads) dq_kernel(DqParams P)
     int currSet = 0, prevSet = 4;              // CommonCtx::m_currSbbCtx / m_prevSbbCtx
     const int32_t* sigTab = &tab.sig[vmax(k - 1, 0)][0][0];
 
+    DqScanPos sp = scan[vmax(firstTestPos, 0)];                    // this iteration's position; the next one is fetched a step ahead
+    int coeffCur = coeff[sp.idx];
     for (int it = 0; it < steps; it++) {
       const int scanIdx = firstTestPos - it;
+      const DqScanPos nx = scan[vmax(scanIdx - 1, 0)];
+      const int coeffNext = coeff[nx.idx];
       const bool act = scanIdx >= 0;
       { const int t = prev; prev = curr; curr = t; }               // std::swap(m_prevStates, m_currStates)
       long long dCost = kDqHuge >> 2;
@@ -254,7 +305,6 @@ __global__ void __launch_bounds__(kDqThreads) dq_kernel(DqParams P)
       bool zeroOut = false;
       int pqLevel[4] = { 0, 0, 0, 0 }; long long pqDist[4] = { 0, 0, 0, 0 };
       if (act) {
-        const DqScanPos sp = scan[scanIdx];
         const int inside = scanIdx & 15;
         spX = sp.x; spY = sp.y;
         if (inside == 15 && scanIdx > 16 && scanIdx < shp.numCoeff - 1) spt = 1;                 // SCAN_SOCSBB
@@ -262,7 +312,7 @@ __global__ void __launch_bounds__(kDqThreads) dq_kernel(DqParams P)
         zeroOut = zeroOutTu && (sp.x >= effW || sp.y >= effH);
         if (!zeroOut) {
           // ---- Quantizer::preQuantCoeff :812-843 (every lane of the group computes the same four candidates)
-          const int absCoeff = vabs(coeff[sp.idx]);
+          const int absCoeff = vabs(coeffCur);
           const long long scaledOrg = (long long)absCoeff * Q.qScale;
           int qIdx = vmax(1, vmin(Q.maxQIdx, (int)((scaledOrg + Q.qAdd) >> Q.qShift)));
           long long scaledAdd = qIdx * Q.distStepAdd - scaledOrg * Q.distOrgFact;
@@ -339,7 +389,6 @@ __global__ void __launch_bounds__(kDqThreads) dq_kernel(DqParams P)
         // ---- state update :1533-1588
         if (scanIdx) {
           DqState& cs = sm.st[curr * 4 + k];
-          const DqScanPos nx = scan[scanIdx - 1];
           const int diag = nx.x + nx.y;
           const int sigOff = diag < 2 ? 8 : diag < 5 ? 4 : 0;
           const int gtxOff = diag < 1 ? 16 : diag < 3 ? 11 : diag < 10 ? 6 : 1;
@@ -351,23 +400,28 @@ __global__ void __launch_bounds__(kDqThreads) dq_kernel(DqParams P)
             if (dPrev > -2) {
               const DqState* pst = nullptr;
               if (dPrev >= 4)      { pst = &sm.st[skip * 4 + dPrev - 4]; cs.numSigSbb = 0; for (int i = 0; i < 8; i++) cs.ctxInit[i] = 0; }
-              else if (dPrev >= 0) { pst = &sm.st[prev * 4 + dPrev]; cs.numSigSbb = pst->numSigSbb + (dLevel != 0); for (int i = 0; i < 8; i++) cs.ctxInit[i] = pst->ctxInit[i]; }
+              else if (dPrev >= 0) { pst = &sm.st[prev * 4 + dPrev]; cs.numSigSbb = pst->numSigSbb + (dLevel != 0); *reinterpret_cast<uint4*>(cs.ctxInit) = *reinterpret_cast<const uint4*>(pst->ctxInit); }
               else                 { cs.numSigSbb = 1; for (int i = 0; i < 8; i++) cs.ctxInit[i] = 0; }
               reinterpret_cast<uint8_t*>(cs.ctxInit)[0] = (uint8_t)vmin(255, dLevel);     // insidePos == 0
               uint8_t* sbbFlags = ctxMem + (size_t)(cSet + k) * ctxStride;
-              uint8_t* levels = sbbFlags + shp.numSbb;
-              const int cp = scan[scanIdx - 1].maxDist;
+              uint8_t* levels = sbbFlags + sbbPad;
+              // the copies run in 16-byte words; rounding the level window up only touches entries no template reads
+              const int cpWords = (nx.maxDist + 15) >> 4, sbbWords = sbbPad >> 4;
+              uint4* dstF = reinterpret_cast<uint4*>(sbbFlags);
+              uint4* dstL = reinterpret_cast<uint4*>(levels + scanIdx);      // scanIdx is a multiple of 16 here
               if (pst && pst->refSbbCtxId >= 0) {
-                const uint8_t* srcF = ctxMem + (size_t)(pSet + pst->refSbbCtxId) * ctxStride;
-                const uint8_t* srcL = srcF + shp.numSbb;
-                for (int i = 0; i < shp.numSbb; i++) sbbFlags[i] = srcF[i];
-                for (int i = 0; i < cp; i++) levels[scanIdx + i] = srcL[scanIdx + i];
+                const uint8_t* srcSet = ctxMem + (size_t)(pSet + pst->refSbbCtxId) * ctxStride;
+                const uint4* srcF = reinterpret_cast<const uint4*>(srcSet);
+                const uint4* srcL = reinterpret_cast<const uint4*>(srcSet + sbbPad + scanIdx);
+                for (int i = 0; i < sbbWords; i++) dstF[i] = srcF[i];
+                for (int i = 1; i < cpWords; i++) dstL[i] = srcL[i];           // word 0 is this sub-block, written below
               } else {
-                for (int i = 0; i < shp.numSbb; i++) sbbFlags[i] = 0;
-                for (int i = 0; i < cp; i++) levels[scanIdx + i] = 0;
+                const uint4 z = { 0u, 0u, 0u, 0u };
+                for (int i = 0; i < sbbWords; i++) dstF[i] = z;
+                for (int i = 1; i < cpWords; i++) dstL[i] = z;
               }
               sbbFlags[sbbPosTab[scanIdx >> 4]] = cs.numSigSbb != 0;
-              for (int i = 0; i < 16; i++) levels[scanIdx + i] = reinterpret_cast<const uint8_t*>(cs.ctxInit)[i];
+              dstL[0] = *reinterpret_cast<const uint4*>(cs.ctxInit);
               const int nsp = sbbPosTab[(scanIdx - 1) >> 4];
               const int ny = nsp / shp.widthInSbb, nxs = nsp - ny * shp.widthInSbb;
               const int right = nxs < shp.widthInSbb - 1 ? nsp + 1 : 0, below = ny < shp.heightInSbb - 1 ? nsp + shp.widthInSbb : 0;
@@ -406,7 +460,8 @@ __global__ void __launch_bounds__(kDqThreads) dq_kernel(DqParams P)
                 cs.remRegBins = pst.remRegBins - 1;
                 cs.goRicePar = pst.goRicePar;
                 if (cs.remRegBins >= 4) cs.remRegBins -= dLevel < 2 ? dLevel : 3;
-                for (int i = 0; i < 24; i++) cs.ctxInit[i] = pst.ctxInit[i];
+#pragma unroll
+                for (int i = 0; i < 3; i++) reinterpret_cast<uint4*>(cs.ctxInit)[i] = reinterpret_cast<const uint4*>(pst.ctxInit)[i];
               } else {
                 cs.numSigSbb = 1; cs.refSbbCtxId = -1;
                 cs.remRegBins = regBinsInit - (dLevel < 2 ? dLevel : 3);
@@ -440,6 +495,7 @@ __global__ void __launch_bounds__(kDqThreads) dq_kernel(DqParams P)
         if ((scanIdx & 15) == 0) { const int t = currSet; currSet = prevSet; prevSet = t; }
         if (spt == 1) { const int t = prev; prev = skip; skip = t; }
       }
+      sp = nx; coeffCur = coeffNext;
       __syncwarp();
     }
 
