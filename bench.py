@@ -94,6 +94,16 @@ def measured_peaks():
         return {'hbm_gbs': 6650.0}, 'fallback (B200_PROFILING.md)'
 
 
+def eval_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the 18 rmd_eval_kernel launches of one 1080p step, from the committed
+    ncu capture (profiles/eval_traffic.json, written by tools/make_traffic.py on the GPU box)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'eval_traffic.json')))
+        return t['dram_bytes_per_step'], t['source']
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def active_slot_counts(vis):
     """Evaluation slots per visit, as the kernels count them."""
     w, h = 1 << vis['log2w'].astype(np.int64), 1 << vis['log2h'].astype(np.int64)
@@ -168,50 +178,53 @@ def run_b200(args, rank, world, local_rank, dist):
     launches = eng.launch_count - launches0
     ms_total = vb.shard.max_over_ranks(ms_total, dist, 'cuda:%d' % local_rank)
 
-    # ---- end to end through the C ABI with host buffers
-    h_vis = {}
-    for qp in QPS:
-        a = eng.host_array(n, vb.VISIT_DTYPE)
-        a[:] = base
-        a['sqrt_lambda'] = vb.partition.sqrt_lambda_for_qp(qp)
-        h_vis[qp] = a
-    h_res = eng.host_array(n, vb.RESULT_DTYPE)
-    h_frames = []
-    for f in range(NFRAMES):
-        a = eng.host_array(H * W, np.int16).reshape(H, W)
-        a[:] = frames[f]
-        h_frames.append(a)
+    e2e_s, e2e_steps = float("nan"), 1
+    if not args.resident_only:
+        # ---- end to end through the C ABI with host buffers
+        h_vis = {}
+        for qp in QPS:
+            a = eng.host_array(n, vb.VISIT_DTYPE)
+            a[:] = base
+            a['sqrt_lambda'] = vb.partition.sqrt_lambda_for_qp(qp)
+            h_vis[qp] = a
+        h_res = eng.host_array(n, vb.RESULT_DTYPE)
+        h_frames = []
+        for f in range(NFRAMES):
+            a = eng.host_array(H * W, np.int16).reshape(H, W)
+            a[:] = frames[f]
+            h_frames.append(a)
 
-    def e2e_step(s):
-        f, qp = mine[s % len(mine)]
-        eng.frame_begin(h_frames[f])
-        eng.reco_update(h_frames[f])
-        eng.rmd_eval(h_vis[qp], out=h_res)
-        return int(h_res['n_rd'][0])
+        def e2e_step(s):
+            f, qp = mine[s % len(mine)]
+            eng.frame_begin(h_frames[f])
+            eng.reco_update(h_frames[f])
+            eng.rmd_eval(h_vis[qp], out=h_res)
+            return int(h_res['n_rd'][0])
 
-    e2e_steps = max(1, min(args.steps, 4))
-    for s in range(2):
-        e2e_step(s)
-    eng.sync()
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for s in range(e2e_steps):
-        e2e_step(2 + s)
-    eng.sync()
-    e2e_s = time.perf_counter() - t0
-    e2e_s = vb.shard.max_over_ranks(e2e_s, dist, 'cuda:%d' % local_rank)
+        e2e_steps = max(1, min(args.steps, 4))
+        for s in range(2):
+            e2e_step(s)
+        eng.sync()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for s in range(e2e_steps):
+            e2e_step(2 + s)
+        eng.sync()
+        e2e_s = time.perf_counter() - t0
+        e2e_s = vb.shard.max_over_ranks(e2e_s, dist, 'cuda:%d' % local_rank)
     h2d = 2 * H * W * 2 + n * vb.VISIT_DTYPE.itemsize
     d2h = n * vb.RESULT_DTYPE.itemsize
 
     if rank != 0:
         return
-    tu_stage = None if args.no_tu_stage else tu_stage_leg(eng, vb, base, frames[0], int_peak)
+    tu_stage = None if (args.no_tu_stage or args.resident_only) else tu_stage_leg(eng, vb, base, frames[0], int_peak)
     ms_step = ms_total / args.steps
     value = world * args.steps * CTUS_PER_FRAME / (ms_total * 1e-3)
     eval_ms = k_eval / max(1, k_n)
     hbm_achieved = bytes_per_step / (eval_ms * 1e-3) / 1e9 if eval_ms > 0 else 0.0
     int_best = max(int_peak)
+    traffic, traffic_src = eval_traffic()
     out = {
         'metric': 'all-intra 1080p10 CTUs/sec (exhaustive RMD sweep: intra pred + SAD/SATD + mode cost + candidate lists)',
         'value': value, 'unit': 'CTU/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -230,7 +243,7 @@ def run_b200(args, rank, world, local_rank, dist):
         'gpu_launches': launches,
         'clocks': clk.summary(),
         'roofline': {'bound': 'hbm', 'kernel': 'rmd_eval_kernel', 'achieved': hbm_achieved, 'peak': peaks.get('hbm_gbs'), 'unit': 'GB/s',
-                     'frac': hbm_achieved / peaks.get('hbm_gbs') if peaks.get('hbm_gbs') else None, 'traffic': None,
+                     'frac': hbm_achieved / peaks.get('hbm_gbs') if peaks.get('hbm_gbs') else None, 'traffic': traffic, 'traffic_source': traffic_src,
                      'peak_source': peak_src, 'kernel_ms': eval_ms, 'kernel_share_of_step': eval_ms / ms_step if ms_step else None,
                      'algorithmic_bytes_per_launch': bytes_per_step,
                      'note': 'the path is integer-issue bound, not HBM bound (SURVEY.md 8d); see int_alu'},
@@ -243,7 +256,7 @@ def run_b200(args, rank, world, local_rank, dist):
     }
     if tu_stage:
         out['tu_stage'] = tu_stage
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.resident_only:
         out['cpu_baseline'] = cpu_baseline_port(base, frames[0])
     print(json.dumps(out))
 
@@ -371,6 +384,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-tu-stage', action='store_true')
+    ap.add_argument('--resident-only', action='store_true', help='profiling aid: only the HBM-resident timed loop (no e2e / TU / CPU legs); not a bench line')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

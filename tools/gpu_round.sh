@@ -8,10 +8,13 @@ tail -15 gpurun_out/pytest_gpu_$tag.log
 python bench.py --steps 8 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"
 cat gpurun_out/bench_$tag.json | head -c 3500
 [ "$2" = "skip-ncu" ] && exit 0
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1 && \
+python bench.py --steps 2 --warmup 3 --resident-only > /dev/null 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv \
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_$tag.log 2>&1; echo "ncu list rc=$?"
+  python bench.py --steps 2 --warmup 3 --resident-only > gpurun_out/ncu_launches_$tag.log 2>&1; echo "ncu list rc=$?"
 python tools/profile_sweep.py --width 1920 --height 1080 --passes 2 > gpurun_out/prof_plain_$tag.log 2>&1 || exit 1
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:rmd_eval_kernel -s 18 -c 18 \
+  --csv --log-file gpurun_out/eval_traffic_$tag.csv python tools/profile_sweep.py --width 1920 --height 1080 --passes 2 > /dev/null 2>&1 && \
+  python tools/make_traffic.py gpurun_out/eval_traffic_$tag.csv $tag
 # second pass of the sweep: 18 eval launches per pass in bucket order (class*3 + kind); 8x8 angular = launch 9, 16x8 angular = 12
 for k in 27:eval8x8ang 30:eval16x8ang 18:eval4x4ang; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:rmd_eval_kernel -s ${k%%:*} -c 1 -o gpurun_out/prof_${k##*:}_$tag -f \
