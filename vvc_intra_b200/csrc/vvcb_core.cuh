@@ -321,7 +321,11 @@ template <int R, int C> VHD void pred_angular_unit(const int16_t* ml, const int1
     for (int j = 0; j < C; j++)
       q[i][j] = clip_bd((f0 * t[j] + f1 * t[j + 1] + f2 * t[j + 2] + f3 * t[j + 3] + 32) >> 6, maxv);
   }
+  #ifdef VVCB_EXP_NO_PDPC
+  if (false) {
+#else
   if (p.pdpc) {
+#endif
     if (angle == 0) {
       const int scale = (vlog2(mw) + vlog2(mh) - 2) >> 2;
       const int lim = vmin(3 << scale, mw);

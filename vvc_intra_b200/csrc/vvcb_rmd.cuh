@@ -19,7 +19,10 @@ using namespace vvcb;
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef VVCB_EVAL_WARPS
+#define VVCB_EVAL_WARPS 8
+#endif
+constexpr int kWarpsPerCta = VVCB_EVAL_WARPS;
 constexpr int kThreads     = kWarpsPerCta * 32;
 constexpr int KIND_ANG = 0, KIND_PDC = 1, KIND_MIP = 2;
 
