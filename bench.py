@@ -396,8 +396,9 @@ def main():
     if world > 1:
         import torch
         import torch.distributed as dist
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')       # keep stdout to the one JSON line
         torch.cuda.set_device(local_rank)
-        dist.init_process_group('nccl')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     run_b200(args, rank, world, local_rank, dist)
     if dist is not None:
         dist.barrier()
