@@ -433,11 +433,15 @@ __global__ void __launch_bounds__(kDqThreads, VVCB_DQ_MIN_CTAS) dq_kernel(DqPara
               cs.sbbBits0 = tab.sigSbb[sigNSbb][0]; cs.sbbBits1 = tab.sigSbb[sigNSbb][1];
               const int scanBeg = scanIdx - 16;
               const uint8_t* absLevels = levels + scanBeg;
+#pragma unroll 4
               for (int id = 0; id < 16; id++) {
                 const DqScanPos nb = scan[scanBeg + id];
                 int sumAbs = 0, sumAbs1 = 0, sumNum = 0;
-                for (int j = 0; j < nb.numOut; j++) {
-                  const int v = absLevels[nb.outPos[j]];
+                // five predicated, independent loads (absent neighbours re-read entry 0 of the window and count as zero)
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                  const bool on = j < nb.numOut;
+                  const int v = on ? absLevels[nb.outPos[j]] : 0;
                   sumAbs += v; sumAbs1 += vmin(4 + (v & 1), v); sumNum += v != 0;
                 }
                 cs.ctxInit[8 + id] = (uint16_t)(sumNum + (sumAbs1 << 3) + (vmin(127, sumAbs) << 8));
@@ -511,24 +515,41 @@ __global__ void __launch_bounds__(kDqThreads, VVCB_DQ_MIN_CTAS) dq_kernel(DqPara
       const long long scaleEff = shift < 0 ? (long long)invScale << -shift : invScale;   // the in-place `invQScale <<= -shift`
       const long long add = shift < 0 ? 0 : ((1ll << shift) >> 1);
       int absSum = 0;
-      for (int scanIdx = 0; prevId >= 0; scanIdx++) {
-        int absLevel;
-        if (prevId >= 4 && (scanIdx & 15) != 0) absLevel = 0;        // inside a skipped sub-block: {level 0, prevId unchanged}
-        else {
-          const uint32_t e = reinterpret_cast<const uint32_t*>(trellis + scanIdx)[prevId & 3];   // at eosbb entries 4..7 == 0..3
-          absLevel = (int)(e & 0xffff);
-          prevId = (int)(e >> 16) - 2;
+      // four positions per round: their trellis words, scan entries and coefficients are fetched together (independent
+      // loads), then the chain is resolved in registers
+      const int lastPos = shp.numCoeff - 1;
+      for (int s0 = 0; prevId >= 0; s0 += 4) {
+        uint4 e[4]; int idx[4], cf[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int s = vmin(s0 + i, lastPos);
+          e[i] = trellis[s];
+          idx[i] = scan[s].idx;
         }
-        if (absLevel) {
-          const int idx = scan[scanIdx].idx;
-          const bool neg = coeff[idx] < 0;
-          const int state = prevId < 0 ? 0 : (prevId & 3);           // the state this coefficient was quantised in
-          P.level[job.offset + idx] = neg ? -absLevel : absLevel;
-          const long long qIdx = 2ll * absLevel - (state >> 1);
-          long long nom = ((neg ? -qIdx : qIdx) * scaleEff + add) >> (shift < 0 ? 0 : shift);
-          nom = nom < -32768 ? -32768 : (nom > 32767 ? 32767 : nom);
-          P.deq[job.offset + idx] = (int32_t)nom;
-          absSum += absLevel;
+#pragma unroll
+        for (int i = 0; i < 4; i++) cf[i] = coeff[idx[i]];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (prevId < 0) break;
+          const int scanIdx = s0 + i;
+          int absLevel;
+          if (prevId >= 4 && (scanIdx & 15) != 0) absLevel = 0;      // inside a skipped sub-block: {level 0, prevId unchanged}
+          else {
+            const int d = prevId & 3;                                // at eosbb entries 4..7 == 0..3
+            const uint32_t w = d == 0 ? e[i].x : d == 1 ? e[i].y : d == 2 ? e[i].z : e[i].w;
+            absLevel = (int)(w & 0xffff);
+            prevId = (int)(w >> 16) - 2;
+          }
+          if (absLevel) {
+            const bool neg = cf[i] < 0;
+            const int state = prevId < 0 ? 0 : (prevId & 3);         // the state this coefficient was quantised in
+            P.level[job.offset + idx[i]] = neg ? -absLevel : absLevel;
+            const long long qIdx = 2ll * absLevel - (state >> 1);
+            long long nom = ((neg ? -qIdx : qIdx) * scaleEff + add) >> (shift < 0 ? 0 : shift);
+            nom = nom < -32768 ? -32768 : (nom > 32767 ? 32767 : nom);
+            P.deq[job.offset + idx[i]] = (int32_t)nom;
+            absSum += absLevel;
+          }
         }
       }
       P.results[P.order[ji]].abs_sum_level = absSum;
