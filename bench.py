@@ -262,52 +262,62 @@ def run_b200(args, rank, world, local_rank, dist):
 
 
 def tu_stage_leg(eng, vb, base, frame, int_peak):
-    """Second stage of the cost evaluation, reported next to the headline (its own unit: TUs/s): one DCT-II candidate per
-    candidate CU of frame 0 (sides <= 32) through vvcb_tu_eval -- forward transform, dependent quantisation, inverse,
-    reconstruction, SSE -- with host buffers; kernel times from CUDA events around each launch."""
+    """Second stage of the cost evaluation, reported next to the headline (its own unit: TUs/s): for every candidate CU of frame 0
+    the best candidate of its rough-mode-decision list goes through vvcb_tu_eval_pred -- intra prediction, residual, forward
+    DCT-II, dependent quantisation, inverse, reconstruction, SSE (IntraSearch::xIntraCodingTUBlock) -- with host buffers for the
+    job descriptions and results; kernel times from CUDA events around each launch."""
     from oracle import oracle_py as O
-    jobs, resi, pred, rates = vb.build_tu_sweep(frame, base, 32, BITS)
+    eng.frame_begin(frame)
+    eng.reco_update(frame)
+    vis = base.copy()
+    vis['sqrt_lambda'] = vb.partition.sqrt_lambda_for_qp(32)
+    res = eng.rmd_eval(vis)
+    src, jobs, n_samples, rates = vb.build_tu_jobs_from_lists(vis, res, 32, BITS)
+    hv = eng.host_array(len(vis), vb.VISIT_DTYPE)
+    hv[:] = vis
+    hs = eng.host_array(len(src), vb.TU_SRC_DTYPE)
+    hs[:] = src
     hj = eng.host_array(len(jobs), vb.TU_JOB_DTYPE)
     hj[:] = jobs
-    hr = eng.host_array(resi.size, np.int16)
-    hr[:] = resi
-    hp = eng.host_array(pred.size, np.int16)
-    hp[:] = pred
-    eng.frame_begin(frame)
-    eng.tu_eval(hj, hr, hp, rates=rates)                      # warm-up (allocations)
+    eng.tu_eval_pred(hv, hs, hj, n_samples, rates=rates)      # warm-up (allocations)
     eng.kernel_timing(True)
     reps = 3
     t0 = time.perf_counter()
     for _ in range(reps):
-        out = eng.tu_eval(hj, hr, hp, rates=rates)
+        out = eng.tu_eval_pred(hv, hs, hj, n_samples, rates=rates)
     wall = (time.perf_counter() - t0) / reps
     k_tr, k_dq, k_rec, k_n = eng.tu_kernel_times()
     eng.kernel_timing(False)
     lw, lh = jobs['log2w'].astype(np.int64), jobs['log2h'].astype(np.int64)
-    # SURVEY.md 8d: a separable transform costs w*h*(w_out + h_out) MACs; forward + inverse
-    macs = float((2 * (1 << (lw + lh)) * ((1 << lw) + (1 << lh))).sum())
-    # CPU port on a bounded sample of the same jobs
-    sel = np.linspace(0, len(jobs) - 1, 3000).astype(int)
+    # SURVEY.md 8d: a separable transform costs w*h*(w_out + h_out) MACs (64-point sides keep 32 outputs); forward + inverse
+    macs = float((2 * (1 << (lw + lh)) * (np.minimum(1 << lw, 32) + np.minimum(1 << lh, 32))).sum())
+    # CPU port on a bounded sample of the same jobs (prediction from the oracle's RMD pass, then the TU chain)
+    sel = np.linspace(0, len(jobs) - 1, 4000).astype(int)
     t0 = time.perf_counter()
-    for i in sel:
+    _, _, preds = O.rmd_batch(frame, frame, BITS, CTU, vis[sel], want_pred=True)
+    for k, i in enumerate(sel):
         j = jobs[i]
         w, h = 1 << int(j['log2w']), 1 << int(j['log2h'])
-        sl = slice(int(j['offset']), int(j['offset']) + w * h)
-        co = O.fwd_transform(resi[sl].reshape(h, w), BITS, 0)
-        lvl, _ = O.dep_quant(co, BITS, 0, 0, 6 * int(j['qp_per']) + int(j['qp_rem']), float(j['lambda']), rates[0], 0)
-        O.inv_transform(O.dep_dequant(lvl, BITS, 6 * int(j['qp_per']) + int(j['qp_rem'])), BITS, 0)
+        p = preds[k][int(src[i]['slot'])]
+        r = (frame[int(j['y']):int(j['y']) + h, int(j['x']):int(j['x']) + w].astype(np.int32) - p).astype(np.int16)
+        qp = 6 * int(j['qp_per']) + int(j['qp_rem'])
+        co = O.fwd_transform(r, BITS, 0)
+        lvl, _ = O.dep_quant(co, BITS, 0, 0, qp, float(j['lambda']), rates[0], 0)
+        O.inv_transform(O.dep_dequant(lvl, BITS, qp), BITS, 0)
     cpu_s = time.perf_counter() - t0
     kern_ms = (k_tr + k_dq + k_rec) / max(1, k_n)
-    return {'workload': 'frame 0, one DCT-II candidate per candidate CU with sides <= 32 (%d TUs, %d samples), QP 32, dependent quantisation' % (len(jobs), resi.size),
+    return {'workload': 'frame 0, the best rough-mode-decision candidate of every candidate CU (%d TUs, %d samples): prediction, residual, DCT-II, '
+                        'dependent quantisation, inverse, reconstruction, SSE; QP 32' % (len(jobs), n_samples),
             'tus_per_s_kernels': len(jobs) / (kern_ms * 1e-3) if kern_ms else None,
             'tus_per_s_e2e': len(jobs) / wall,
-            'kernel_ms': {'transform': k_tr / max(1, k_n), 'dep_quant': k_dq / max(1, k_n), 'reconstruct': k_rec / max(1, k_n)},
-            'e2e_ms': wall * 1e3, 'h2d_bytes': int(jobs.nbytes + resi.nbytes + pred.nbytes), 'd2h_bytes': int(out['results'].nbytes),
+            'kernel_ms': {'transform': k_tr / max(1, k_n), 'dep_quant': k_dq / max(1, k_n), 'reconstruct': k_rec / max(1, k_n),
+                          'note': 'events around the launches of vvcb_tu_eval_pred after the prediction kernel: transform pass, first-position + sort + dependent quantisation, reconstruction pass'},
+            'e2e_ms': wall * 1e3, 'h2d_bytes': int(vis.nbytes + src.nbytes + jobs.nbytes), 'd2h_bytes': int(out['results'].nbytes),
             'transform_gmacs_per_s': macs / (((k_tr + k_rec) / max(1, k_n)) * 1e-3) / 1e9 if k_n else None,
             'transform_int_alu_frac': (macs / (((k_tr + k_rec) / max(1, k_n)) * 1e-3) / 1e9) / int_peak[0] if k_n and int_peak[0] else None,
             'nonzero_tu_fraction': float((out['results']['abs_sum_level'] > 0).mean()),
             'cpu_baseline': {'value': len(sel) / cpu_s, 'unit': 'TU/s', 'cores': 1, 'kind': 'port',
-                             'sample': 'oracle transform + dependent quantisation + inverse on %d of the jobs (ctypes call overhead included), %.1f s' % (len(sel), cpu_s)}}
+                             'sample': 'oracle: all predictions of the visit (its RMD pass) + transform + dependent quantisation + inverse on %d of the jobs, %.1f s' % (len(sel), cpu_s)}}
 
 
 def cpu_baseline_port(base, frame):

@@ -199,6 +199,19 @@ typedef struct vvcb_tu_result {
  * coeff / level (int32) and reco (int16): optional HOST outputs of n_samples; results: n entries.                  */
 int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred, size_t n_samples,
                  const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results);
+/* The whole of IntraSearch::xIntraCodingTUBlock (EL/IntraSearch.cpp:2694-3168) for TUs that cover their CU: the engine also
+ * runs initIntraPatternChType + predIntraAng / predIntraMip (:2820-2870) from the reconstruction plane and forms
+ * resi = org - pred (:2922) itself.  src[i] names the visit (position, size, availability: the same struct the rough mode
+ * decision takes) and the evaluation slot (VVCB_SLOT_*) of job i; jobs[i] must have the visit's position and size.
+ * pred_out (optional, HOST, n_samples): the prediction samples.                                                        */
+typedef struct vvcb_tu_src {
+  uint32_t visit;           /* index into visits[]                                                                  */
+  uint8_t  slot;            /* evaluation slot: regular mode, MPM on reference line 1 / 3, or MIP mode              */
+  uint8_t  pad[3];
+} vvcb_tu_src;
+int vvcb_tu_eval_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n_visits, const vvcb_tu_src* src, const vvcb_tu_job* jobs, int n,
+                      size_t n_samples, const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco,
+                      int16_t* pred_out, vvcb_tu_result* results);
 /* TrQuant::transformNxN(trModes) candidate selection (CL/TrQuant.cpp:1112-1123) from the pre-selection sums of one
  * TU's candidates in list order (DCT2 first, transform skip second if tested): pure host logic.                    */
 void vvcb_mts_preselect(const int32_t* sums, int n, int width, int height, int max_cand, uint8_t* selected);

@@ -388,3 +388,47 @@ def oracle_dq_chain(items, bd):
         out['coeff'][sl], out['level'][sl], out['reco'][sl] = co.ravel(), lvl.ravel(), reco.ravel()
         out['results'][i] = (O.abs_sum_for_preselection(co, it['mts']), s, sse)
     return out
+
+
+# ---- TU coding with device-side prediction (vvcb_tu_eval_pred) ---------------------------------------------
+def pred_tu_case(rng, bd, n_per_shape, slots_per_visit=4):
+    """Random visits (ragged availability) and, per visit, a few evaluation slots of every kind that the visit evaluates,
+    each turned into one dependent-quantisation TU job.  Returns (orig, reco, visits, src, jobs, n_samples, rates, expect)
+    where expect[i] = (prediction block, oracle TU-chain item)."""
+    import vvc_intra_b200 as vb
+    orig, reco, visits = random_case(rng, bd, n_per_shape, plane=(256, 512))
+    _, _, preds = O.rmd_batch(orig, reco, bd, 128, visits, want_pred=True)
+    n_rates = 3
+    rates = np.zeros(n_rates, vb.DQ_RATES_DTYPE)
+    for name in rates.dtype.names:
+        rates[name] = rng.integers(300, 140000, rates[name].shape)
+    src, jobs, items, off = [], [], [], 0
+    for vi, v in enumerate(visits):
+        w, h = 1 << int(v['log2w']), 1 << int(v['log2h'])
+        mrl_ok = not (int(v['flags']) & 1) and (int(v['y']) & 127) != 0      # VVCB_VISIT_NO_MRL
+        n_mip = 0 if (int(v['flags']) & 2) or w > 4 * h or h > 4 * w else (35 if w == h == 4 else 19 if max(w, h) <= 8 else 11)
+        cand = list(rng.choice(67, 2, replace=False)) + [0, 1]
+        if mrl_ok:
+            cand += [O.SLOT_MRL1 + int(rng.integers(0, 5)), O.SLOT_MRL3 + int(rng.integers(0, 5))]
+        if n_mip:
+            cand += [O.SLOT_MIP + int(rng.integers(0, n_mip))]
+        for slot in rng.permutation(cand)[:slots_per_visit]:
+            slot = int(slot)
+            mts = int(rng.choice([0, 0, 2, 5])) if max(w, h) <= 32 else 0
+            qp = int(rng.integers(16, 48)) + 6 * (bd - 8)
+            j = np.zeros(1, vb.TU_JOB_DTYPE)[0]
+            j['x'], j['y'], j['log2w'], j['log2h'], j['mts_idx'] = v['x'], v['y'], v['log2w'], v['log2h'], mts
+            j['flags'] = vb.TU_QUANT | vb.TU_DEPQUANT
+            j['qp_per'], j['qp_rem'], j['offset'] = qp // 6, qp % 6, off
+            lam = float(0.57 * 2.0 ** ((qp - 6 * (bd - 8) - 12) / 3.0))
+            j['rate_idx'], j['cbf_delta_bits'], j['lambda'] = len(jobs) % n_rates, int(rng.integers(-30000, 30000)), lam
+            p = preds[vi][slot]
+            o = orig[int(v['y']):int(v['y']) + h, int(v['x']):int(v['x']) + w]
+            items.append(dict(pred=p, org=o, resi=(o.astype(np.int32) - p).astype(np.int16), mts=mts, qp=qp, lam=lam, cbf=int(j['cbf_delta_bits']),
+                              lfnst=0, off=off, rate=rates[len(jobs) % n_rates]))
+            s = np.zeros(1, vb.TU_SRC_DTYPE)[0]
+            s['visit'], s['slot'] = vi, slot
+            src.append(s)
+            jobs.append(j)
+            off += w * h
+    return orig, reco, visits, np.array(src, vb.TU_SRC_DTYPE), np.array(jobs, vb.TU_JOB_DTYPE), off, rates, items

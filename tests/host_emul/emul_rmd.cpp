@@ -132,3 +132,16 @@ extern "C" int emul_ctu_hads(const int16_t* orig, int stride, int width, int hei
   emu_launch(2, 256, [&] { ctu_hads_kernel(orig, stride, width, height, ctu, perRow, out); });
   return 0;
 }
+
+// tu_pred_kernel: prediction + residual of TU jobs from the planes
+extern "C" int emul_tu_pred(const int16_t* orig, const int16_t* reco, int stride, int bd, int ctu, const vvcb_rmd_visit* visits, const vvcb_tu_src* src,
+                            const vvcb_tu_job* jobs, int n, int16_t* pred, int16_t* resi)
+{
+  static Rom rom;
+  fill_rom(rom);
+  TuPredParams Q;
+  Q.visits = visits; Q.src = src; Q.jobs = jobs; Q.n = n; Q.pred = pred; Q.resi = resi; Q.orig = orig; Q.reco = reco; Q.stride = stride;
+  Q.bd = bd; Q.ctu = ctu; Q.rom = &rom;
+  emu_launch(2, kTuPredWarps * 32, [&] { tu_pred_kernel(Q); });
+  return 0;
+}

@@ -319,3 +319,37 @@ def test_dep_quant_error_behaviour(eng10):
     j['mts_idx'] = 0
     out = eng10.tu_eval(j, z, z, want_level=True, want_reco=True, rates=np.zeros(1, vb.DQ_RATES_DTYPE))
     assert not out['level'].any() and out['results']['abs_sum_level'][0] == 0 and out['results']['sse'][0] == 0
+
+
+# ---- xIntraCodingTUBlock as a whole (vvcb_tu_eval_pred) -----------------------------------------------------
+@pytest.mark.parametrize('bd,seed', [(8, 91), (10, 92)])
+def test_tu_eval_with_device_prediction(bd, seed, eng8, eng10):
+    """Prediction (regular, MRL and MIP slots, ragged availability) -> residual -> transform -> dependent quantisation ->
+    reconstruction -> SSE, all on the device from the frame planes; every stage against the oracle."""
+    eng = eng8 if bd == 8 else eng10
+    rng = np.random.default_rng(seed)
+    orig, reco, visits, src, jobs, n_samples, rates, items = G.pred_tu_case(rng, bd, 6)
+    eng.frame_begin(orig)
+    eng.reco_update(reco)
+    out = eng.tu_eval_pred(visits, src, jobs, n_samples, want_coeff=True, want_level=True, want_reco=True, want_pred=True, rates=rates)
+    exp = G.oracle_dq_chain(items, bd)
+    for i, it in enumerate(items):
+        sl = slice(it['off'], it['off'] + it['pred'].size)
+        assert np.array_equal(out['pred'][sl].reshape(it['pred'].shape), it['pred']), (i, it['pred'].shape, int(src[i]['slot']))
+    for k in ('coeff', 'level', 'reco'):
+        assert np.array_equal(out[k], exp[k]), k
+    assert out['results'].tobytes() == exp['results'].tobytes()
+    # the same jobs through the host-buffer entry point give the same answer
+    resi = np.concatenate([it['resi'].ravel() for it in items])
+    pred = np.concatenate([it['pred'].ravel() for it in items])
+    out2 = eng.tu_eval(jobs, resi, pred, want_level=True, want_reco=True, rates=rates)
+    assert np.array_equal(out2['level'], out['level']) and np.array_equal(out2['reco'], out['reco']) and out2['results'].tobytes() == out['results'].tobytes()
+    # error behaviour: a slot the visit does not evaluate, a job whose geometry is not the visit's
+    bad = src.copy()
+    bad['slot'][0] = 111
+    with pytest.raises(vb.EngineError, match='malformed'):
+        eng.tu_eval_pred(visits, bad, jobs, n_samples, rates=rates)
+    badj = jobs.copy()
+    badj['x'][0] += 4
+    with pytest.raises(vb.EngineError, match='malformed'):
+        eng.tu_eval_pred(visits, src, badj, n_samples, rates=rates)

@@ -169,3 +169,23 @@ def test_emulated_dq_kernel_matches_oracle_on_random_blocks(emul, bd, seed):
         bad = [i for i, it in enumerate(items) if not np.array_equal(out[k][it['off']:it['off'] + it['resi'].size], exp[k][it['off']:it['off'] + it['resi'].size])]
         assert not bad, (k, len(bad), [(items[i]['resi'].shape, items[i]['mts'], items[i]['qp'], items[i]['lfnst']) for i in bad[:5]])
     assert out['results'].tobytes() == exp['results'].tobytes()
+
+
+# ---- prediction + residual of TU jobs (tu_pred_kernel) -----------------------------------------------------------
+@pytest.mark.parametrize('bd,seed', [(8, 81), (10, 82)])
+def test_emulated_tu_prediction_matches_oracle(emul, bd, seed):
+    rng = np.random.default_rng(seed)
+    orig, reco, visits, src, jobs, n_samples, rates, items = G.pred_tu_case(rng, bd, 2)
+    pred = np.zeros(n_samples, np.int16)
+    resi = np.zeros(n_samples, np.int16)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    orig = np.ascontiguousarray(orig, np.int16)
+    reco = np.ascontiguousarray(reco, np.int16)
+    emul.emul_tu_pred(p(orig), p(reco), orig.shape[1], bd, 128, p(visits), p(src), p(jobs), len(jobs), p(pred), p(resi))
+    kinds = set()
+    for s, it in zip(src, items):
+        sl = slice(it['off'], it['off'] + it['pred'].size)
+        assert np.array_equal(pred[sl].reshape(it['pred'].shape), it['pred']), (it['pred'].shape, int(s['slot']))
+        assert np.array_equal(resi[sl].reshape(it['pred'].shape), it['resi']), (it['pred'].shape, int(s['slot']))
+        kinds.add('mip' if s['slot'] >= O.SLOT_MIP else 'mrl' if s['slot'] >= O.SLOT_MRL1 else 'reg')
+    assert kinds == {'mip', 'mrl', 'reg'}

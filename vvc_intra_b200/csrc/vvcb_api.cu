@@ -49,7 +49,7 @@ struct vvcb_ctx {
   cudaEvent_t ev0, ev1;
   Rom* dRom;
   TrRom* dTrRom;
-  void* dTu[14]; size_t capTu[14];  // TU scratch: jobs, resi, pred, coeff, level, reco, results; DepQuant: coeff in, dequantised out,
+  void* dTu[16]; size_t capTu[16];  // TU scratch: jobs, resi, pred, coeff, level, reco, results; DepQuant: coeff in, dequantised out,
                                     // job order, context prices, derived rate tables, per-group context memory + trellis
   DqRom* dDqRom;
   float tuMs[3]; int tuTimed; cudaEvent_t tev[4];   // per-kernel timing of vvcb_tu_eval: transform pass, dependent quantisation, reconstruction pass
@@ -160,7 +160,7 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dSlotMajor);
   cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred); cudaFree(ctx->dTrRom);
-  for (int i = 0; i < 14; i++) cudaFree(ctx->dTu[i]);
+  for (int i = 0; i < 16; i++) cudaFree(ctx->dTu[i]);
   cudaFree(ctx->dDqRom);
   for (int i = 0; i < 2; i++) cudaFree(ctx->dFeat[i]);
   if (ctx->pipeReady) {
@@ -476,12 +476,34 @@ static int tu_buf(vvcb_ctx* ctx, int i, size_t bytes)
   return VVCB_OK;
 }
 
-extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred, size_t n_samples,
-                            const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results)
+// Common body of vvcb_tu_eval (residual and prediction come from the host) and vvcb_tu_eval_pred (src != nullptr: both are
+// produced on the device by tu_pred_kernel from the frame planes).
+static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred, size_t n_samples,
+                        const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results,
+                        const vvcb_rmd_visit* visits, int n_visits, const vvcb_tu_src* src, int16_t* pred_out)
 {
   if (!ctx) return VVCB_ERR_ARG;
-  if (n < 0 || n_rates < 0 || (n > 0 && (!jobs || !resi || !results))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: bad argument"); return VVCB_ERR_ARG; }
+  if (n < 0 || n_rates < 0 || (n > 0 && (!jobs || !results || (!src && !resi) || (src && (!visits || n_visits <= 0))))) {
+    snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: bad argument"); return VVCB_ERR_ARG;
+  }
   if (n == 0) return VVCB_OK;
+  if (src) {
+    if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval_pred: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
+    const int rcv = check_visits(ctx, visits, n_visits);
+    if (rcv) return rcv;
+    for (int i = 0; i < n; i++) {
+      bool ok = src[i].visit < (uint32_t)n_visits && src[i].slot < VVCB_NUM_SLOTS;
+      if (ok) {
+        const vvcb_rmd_visit& v = visits[src[i].visit];
+        const bool mrlAllowed = !(v.flags & VVCB_VISIT_NO_MRL) && (v.y & (ctx->ctu - 1)) != 0;
+        const int numMip = (v.flags & VVCB_VISIT_NO_MIP) ? 0 : mip_num_modes(1 << v.log2w, 1 << v.log2h);
+        const int slot = src[i].slot;
+        ok = (slot < VVCB_SLOT_MRL1 || (slot < VVCB_SLOT_MIP ? mrlAllowed : slot - VVCB_SLOT_MIP < numMip)) &&
+             jobs[i].x == v.x && jobs[i].y == v.y && jobs[i].log2w == v.log2w && jobs[i].log2h == v.log2h;
+      }
+      if (!ok) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval_pred: source %d is malformed (visit index, slot not evaluated for the visit, or job geometry differs from the visit)", i); return VVCB_ERR_ARG; }
+    }
+  }
   bool anyQuant = false;
   std::vector<int> order;                 // DepQuant jobs (sorted on the device by scan length once the coefficients exist)
   for (int i = 0; i < n; i++) {
@@ -499,7 +521,7 @@ extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const
     if (!ok) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: job %d is malformed", i); return VVCB_ERR_ARG; }
     if (dq) order.push_back(i);
   }
-  if (anyQuant && !pred) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: VVCB_TU_QUANT needs the prediction samples"); return VVCB_ERR_ARG; }
+  if (anyQuant && !pred && !src) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: VVCB_TU_QUANT needs the prediction samples"); return VVCB_ERR_ARG; }
   const int nDq = (int)order.size();
   CK(cudaSetDevice(ctx->device));
   int rc;
@@ -523,8 +545,23 @@ extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const
     if ((rc = tu_buf(ctx, 13, (size_t)nDq * 3 * sizeof(int)))) return rc;
   }
   CK(cudaMemcpyAsync(ctx->dTu[0], jobs, (size_t)n * sizeof(vvcb_tu_job), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->dTu[1], resi, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-  if (pred) CK(cudaMemcpyAsync(ctx->dTu[2], pred, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (src) {
+    if ((rc = tu_buf(ctx, 14, (size_t)n_visits * sizeof(vvcb_rmd_visit)))) return rc;
+    if ((rc = tu_buf(ctx, 15, (size_t)n * sizeof(vvcb_tu_src)))) return rc;
+    CK(cudaMemcpyAsync(ctx->dTu[14], visits, (size_t)n_visits * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dTu[15], src, (size_t)n * sizeof(vvcb_tu_src), cudaMemcpyHostToDevice, ctx->stream));
+    TuPredParams Q;
+    Q.visits = static_cast<const vvcb_rmd_visit*>(ctx->dTu[14]); Q.src = static_cast<const vvcb_tu_src*>(ctx->dTu[15]);
+    Q.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); Q.n = n;
+    Q.pred = static_cast<int16_t*>(ctx->dTu[2]); Q.resi = static_cast<int16_t*>(ctx->dTu[1]);
+    Q.orig = ctx->bOrig; Q.reco = ctx->bReco; Q.stride = ctx->stride; Q.bd = ctx->bd; Q.ctu = ctx->ctu; Q.rom = ctx->dRom;
+    const int pg = (n + kTuPredWarps - 1) / kTuPredWarps < ctx->numSms * 8 ? (n + kTuPredWarps - 1) / kTuPredWarps : ctx->numSms * 8;
+    tu_pred_kernel<<<pg, kTuPredWarps * 32, 0, ctx->stream>>>(Q);
+    ctx->launches++;
+  } else {
+    CK(cudaMemcpyAsync(ctx->dTu[1], resi, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (pred) CK(cudaMemcpyAsync(ctx->dTu[2], pred, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
   TuParams P;
   P.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); P.n = n;
   P.resi = static_cast<const int16_t*>(ctx->dTu[1]); P.pred = static_cast<const int16_t*>(ctx->dTu[2]);
@@ -570,6 +607,7 @@ extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const
   if (coeff) CK(cudaMemcpyAsync(coeff, ctx->dTu[3], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (level) CK(cudaMemcpyAsync(level, ctx->dTu[4], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (reco) CK(cudaMemcpyAsync(reco, ctx->dTu[5], n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (pred_out) CK(cudaMemcpyAsync(pred_out, ctx->dTu[2], n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(results, ctx->dTu[6], (size_t)n * sizeof(vvcb_tu_result), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (tm) {
@@ -577,6 +615,20 @@ extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const
     ctx->tuTimed++;
   }
   return VVCB_OK;
+}
+
+extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred, size_t n_samples,
+                            const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results)
+{
+  return tu_eval_impl(ctx, jobs, n, resi, pred, n_samples, rates, n_rates, coeff, level, reco, results, nullptr, 0, nullptr, nullptr);
+}
+
+extern "C" int vvcb_tu_eval_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n_visits, const vvcb_tu_src* src, const vvcb_tu_job* jobs, int n,
+                                 size_t n_samples, const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco,
+                                 int16_t* pred_out, vvcb_tu_result* results)
+{
+  if (ctx && n > 0 && !src) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval_pred: bad argument"); return VVCB_ERR_ARG; }
+  return tu_eval_impl(ctx, jobs, n, nullptr, nullptr, n_samples, rates, n_rates, coeff, level, reco, results, visits, n_visits, src, pred_out);
 }
 
 extern "C" int vvcb_tu_kernel_times(vvcb_ctx* ctx, float ms[3], int* calls)

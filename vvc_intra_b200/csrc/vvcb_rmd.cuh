@@ -642,6 +642,90 @@ __global__ void __launch_bounds__(kThreads, VVCB_EVAL_MIN_CTAS) rmd_eval_kernel(
   }
 }
 
+// =====================================================================================================
+// prediction + residual of TU jobs (the first half of IntraSearch::xIntraCodingTUBlock, EL/IntraSearch.cpp:2820-2925):
+// initIntraPatternChType, predIntraAng / predIntraMip, resi = org - pred.  One warp per job; the lanes share the
+// visit's reference lines and take the units of the block in turn.  Low volume (a handful of surviving modes per CU
+// against ~100 evaluated ones), so all prediction kinds live in this one kernel.
+// =====================================================================================================
+struct TuPredParams {
+  const vvcb_rmd_visit* visits;
+  const vvcb_tu_src*    src;       // per job: which visit, which evaluation slot
+  const vvcb_tu_job*    jobs;
+  int                   n;
+  int16_t*              pred;      // dense w*h blocks at job.offset
+  int16_t*              resi;
+  const int16_t*        orig;
+  const int16_t*        reco;
+  int                   stride, bd, ctu;
+  const Rom*            rom;
+};
+
+constexpr int kTuPredWarps = 4;
+
+__global__ void __launch_bounds__(kTuPredWarps * 32) tu_pred_kernel(TuPredParams P)
+{
+  __shared__ WarpSmem smem[kTuPredWarps];
+  __shared__ uint32_t sFilt[64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpSmem& sm = smem[warp];
+  if (threadIdx.x < 64) sFilt[threadIdx.x] = (&P.rom->filt[0][0])[threadIdx.x];
+  __syncthreads();
+  const Rom& rom = *P.rom;
+  for (int ji = blockIdx.x * kTuPredWarps + warp; ji < P.n; ji += gridDim.x * kTuPredWarps) {
+    const vvcb_tu_src src = P.src[ji];
+    const vvcb_rmd_visit v = P.visits[src.visit];
+    const Shape sh = make_shape(v.log2w, v.log2h);
+    const MipGeom mg = make_mip_geom(sh.w, sh.h);
+    const int slot = src.slot;
+    const SlotInfo s = make_slot_info(rom, v, sh, slot);
+    const int16_t* org = P.orig + (size_t)v.y * P.stride + v.x;
+    int16_t* predOut = P.pred + P.jobs[ji].offset;
+    int16_t* resiOut = P.resi + P.jobs[ji].offset;
+    __syncwarp();
+    build_line_set(sm, 0, 0, v, sh, P.reco, P.stride, P.bd, lane);
+    if (s.mrl) build_line_set(sm, s.set, s.mrl, v, sh, P.reco, P.stride, P.bd, lane);
+    __syncwarp();
+    if (s.kind != 3) build_filtered_set(sm, sh, lane);
+    else             build_mip_inputs(sm, sh, mg, P.bd, lane);
+    __syncwarp();
+    int dc = 0;
+    if (s.kind == 2) {
+      if (s.p.angle < 0) build_projected_line(sm.slot, sm, s, s.p.is_ver ? sh.w : sh.h, s.p.is_ver ? sh.h : sh.w, lane, 32);
+    } else if (s.kind == 3) {
+      build_mip_planes(sm.slot, sm.slot + mip_plane_offset(mg, sh), rom, sm, mg, sh, P.bd, s.mode, lane, 32);
+    } else if (s.kind == 1) {
+      int part = 0;
+      const int16_t* top = sm.lines[s.set][0] + s.mrl + 1;
+      const int16_t* left = sm.lines[s.set][1] + s.mrl + 1;
+      if (sh.w >= sh.h) for (int i = lane; i < sh.w; i += 32) part += top[i];
+      if (sh.w <= sh.h) for (int i = lane; i < sh.h; i += 32) part += left[i];
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const int denom = sh.w == sh.h ? 2 * sh.w : vmax(sh.w, sh.h);
+      dc = (part + (denom >> 1)) >> vlog2(denom);
+    }
+    __syncwarp();
+    const bool transposed = s.kind == 2 && !s.p.is_ver;
+    // 4x4 pieces of the block in raster order, one per lane and round (the same piece functions as the evaluation kernels)
+    const int piecesX = sh.w >> 2, pieces = (sh.w * sh.h) >> 4;
+    for (int u = lane; u < pieces; u += 32) {
+      const int x0 = (u % piecesX) * 4, y0 = (u / piecesX) * 4;
+      int q[4][4];
+      if (s.kind == 2)      predict_angular<4, 4>(sm, sm.slot, s, sh, sFilt, P.bd, x0, y0, 0, q);
+      else if (s.kind == 3) predict_mip<4, 4>(sm, sm.slot + mip_plane_offset(mg, sh), mg, sh, x0, y0, q);
+      else pred_planar_dc_unit<4, 4>(sm.lines[s.set][0], sm.lines[s.set][1], s.kind, s.p.pdpc, dc, sh.lw, sh.lh, x0, y0, q);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int by = transposed ? y0 + j : y0 + i, bx = transposed ? x0 + i : x0 + j;
+          predOut[by * sh.w + bx] = (int16_t)q[i][j];
+          resiOut[by * sh.w + bx] = (int16_t)(org[by * P.stride + bx] - q[i][j]);
+        }
+    }
+  }
+}
+
 // calls F<TILE, KIND>(args) for bucket b
 #define VVCB_FOR_BUCKET(b, F, ...)                                                                          \
   switch (b) {                                                                                               \

@@ -36,9 +36,10 @@ TU_JOB_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('log2w', 'u1'), ('log2h', 
                          ('qp_per', '<i2'), ('qp_rem', '<i2'), ('offset', '<u4'), ('rate_idx', '<u2'), ('lfnst_idx', 'u1'), ('pad', 'u1'),
                          ('cbf_delta_bits', '<i4'), ('lambda', '<f8')], align=True)
 TU_RESULT_DTYPE = np.dtype([('abs_sum_coeff', '<i4'), ('abs_sum_level', '<i4'), ('sse', '<u8')], align=True)
+TU_SRC_DTYPE = np.dtype([('visit', '<u4'), ('slot', 'u1'), ('pad', 'u1', 3)])
 DQ_RATES_DTYPE = np.dtype([('sig_sbb', '<u4', (2, 2)), ('sig', '<u4', (3, 12, 2)), ('par', '<u4', (21, 2)), ('gt1', '<u4', (21, 2)),
                            ('gt2', '<u4', (21, 2)), ('last_x', '<u4', (20, 2)), ('last_y', '<u4', (20, 2))])
-assert TU_JOB_DTYPE.itemsize == 32 and TU_RESULT_DTYPE.itemsize == 16 and DQ_RATES_DTYPE.itemsize == 1128
+assert TU_SRC_DTYPE.itemsize == 8 and TU_JOB_DTYPE.itemsize == 32 and TU_RESULT_DTYPE.itemsize == 16 and DQ_RATES_DTYPE.itemsize == 1128
 
 
 FEAT_CU_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('w', 'u1'), ('h', 'u1'), ('qt_depth', 'u1'), ('mt_depth', 'u1')])
@@ -89,6 +90,8 @@ def load_library():
         L.vvcb_sync.argtypes = [C.c_void_p]
         L.vvcb_tu_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
+        L.vvcb_tu_eval_pred.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.vvcb_mts_preselect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vvcb_mts_preselect.restype = None
         L.vvcb_ctu_hads_islice.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -207,6 +210,22 @@ class IntraCostEngine:
                                         _ptr(rates) if rates is not None else None, 0 if rates is None else len(rates),
                                         _ptr(out['coeff']) if want_coeff else None, _ptr(out['level']) if want_level else None,
                                         _ptr(out['reco']) if want_reco else None, _ptr(out['results'])))
+        return out
+
+    def tu_eval_pred(self, visits, src, jobs, n_samples, want_coeff=False, want_level=False, want_reco=False, want_pred=False, rates=None):
+        """vvcb_tu_eval_pred: prediction and residual are formed on the device from the frame planes (src: TU_SRC_DTYPE)."""
+        visits = np.ascontiguousarray(visits, VISIT_DTYPE)
+        src = np.ascontiguousarray(src, TU_SRC_DTYPE)
+        jobs = np.ascontiguousarray(jobs, TU_JOB_DTYPE)
+        out = dict(results=np.zeros(len(jobs), TU_RESULT_DTYPE))
+        for key, want, dt in (('coeff', want_coeff, np.int32), ('level', want_level, np.int32), ('reco', want_reco, np.int16), ('pred', want_pred, np.int16)):
+            if want:
+                out[key] = np.zeros(n_samples, dt)
+        rates = None if rates is None else np.ascontiguousarray(rates, DQ_RATES_DTYPE)
+        p = lambda k: _ptr(out[k]) if k in out else None
+        self._ck(self._lib.vvcb_tu_eval_pred(self._ctx, _ptr(visits), len(visits), _ptr(src), _ptr(jobs), len(jobs), n_samples,
+                                             _ptr(rates) if rates is not None else None, 0 if rates is None else len(rates),
+                                             p('coeff'), p('level'), p('reco'), p('pred'), _ptr(out['results'])))
         return out
 
     def mts_preselect(self, sums, width, height, max_cand):

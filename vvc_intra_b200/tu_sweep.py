@@ -66,3 +66,42 @@ def build_tu_sweep(orig, visits, qp, bit_depth, transforms=(0,), dep_quant=True,
             resi[dst] = resi_pic[yy, xx].reshape(len(idx), -1)
             pred[dst] = pred_pic[yy, xx].reshape(len(idx), -1)
     return jobs, resi, pred, default_dq_rates()
+
+
+def slots_of_modes(visits, modes):
+    """Evaluation slot (include/vvc_intra_b200.h VVCB_SLOT_*) of one candidate mode per visit.  modes: array of the
+    result lists' vvcb_mode entries (fields mip, mrl, mode), one per visit."""
+    from .engine import SLOT_MRL1, SLOT_MRL3, SLOT_MIP
+    mip, mrl, mode = modes['mip'].astype(np.int64), modes['mrl'].astype(np.int64), modes['mode'].astype(np.int64)
+    slot = mode.copy()
+    slot[mip != 0] = SLOT_MIP + mode[mip != 0]
+    has_mrl = (mip == 0) & (mrl != 0)
+    if has_mrl.any():
+        # MRL candidates are the visit's MPM[1..5] (EL/IntraSearch.cpp:635-681): the slot is indexed by the MPM position
+        pos = (visits['mpm'][:, 1:].astype(np.int64) == mode[:, None]).argmax(axis=1)
+        base = np.where(mrl == 1, SLOT_MRL1, SLOT_MRL3)
+        slot[has_mrl] = (base + pos)[has_mrl]
+    return slot.astype(np.uint8)
+
+
+def build_tu_jobs_from_lists(visits, results, qp, bit_depth, rank=0, dep_quant=True):
+    """One DCT-II TU job per visit for the rank-th entry of its full-RD candidate list (results['final_mode']): what
+    xRecurIntraCodingLumaQT hands to xIntraCodingTUBlock for that candidate.  Prediction and residual are left to the engine
+    (vvcb_tu_eval_pred).  Returns (src, jobs, n_samples, rates)."""
+    from .engine import TU_SRC_DTYPE
+    n = len(visits)
+    k = np.minimum(rank, results['n_final'] - 1)
+    modes = results['final_mode'][np.arange(n), k]
+    src = np.zeros(n, TU_SRC_DTYPE)
+    src['visit'] = np.arange(n)
+    src['slot'] = slots_of_modes(visits, modes)
+    jobs = np.zeros(n, TU_JOB_DTYPE)
+    for name in ('x', 'y', 'log2w', 'log2h'):
+        jobs[name] = visits[name]
+    jobs['flags'] = TU_QUANT | (TU_DEPQUANT if dep_quant else 0)
+    qpi = qp + 6 * (bit_depth - 8)
+    jobs['qp_per'], jobs['qp_rem'] = qpi // 6, qpi % 6
+    sizes = (1 << visits['log2w'].astype(np.int64)) * (1 << visits['log2h'].astype(np.int64))
+    jobs['offset'] = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    jobs['lambda'] = lambda_for_qp(qp, bit_depth)
+    return src, jobs, int(sizes.sum()), default_dq_rates()
