@@ -346,7 +346,7 @@ def test_tu_eval_with_device_prediction(bd, seed, eng8, eng10):
     assert np.array_equal(out2['level'], out['level']) and np.array_equal(out2['reco'], out['reco']) and out2['results'].tobytes() == out['results'].tobytes()
     # error behaviour: a slot the visit does not evaluate, a job whose geometry is not the visit's
     bad = src.copy()
-    bad['slot'][0] = 111
+    bad['slot'][0] = 200
     with pytest.raises(vb.EngineError, match='malformed'):
         eng.tu_eval_pred(visits, bad, jobs, n_samples, rates=rates)
     badj = jobs.copy()
