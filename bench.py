@@ -310,8 +310,8 @@ def tu_stage_leg(eng, vb, base, frame, int_peak):
                         'dependent quantisation, inverse, reconstruction, SSE; QP 32' % (len(jobs), n_samples),
             'tus_per_s_kernels': len(jobs) / (kern_ms * 1e-3) if kern_ms else None,
             'tus_per_s_e2e': len(jobs) / wall,
-            'kernel_ms': {'transform': k_tr / max(1, k_n), 'dep_quant': k_dq / max(1, k_n), 'reconstruct': k_rec / max(1, k_n),
-                          'note': 'events around the launches of vvcb_tu_eval_pred after the prediction kernel: transform pass, first-position + sort + dependent quantisation, reconstruction pass'},
+            'kernel_ms': {'predict_transform': k_tr / max(1, k_n), 'dep_quant': k_dq / max(1, k_n), 'reconstruct': k_rec / max(1, k_n),
+                          'note': 'events around the launches of vvcb_tu_eval_pred: prediction + transform pass, first-position + sort + dependent quantisation, reconstruction pass'},
             'e2e_ms': wall * 1e3, 'h2d_bytes': int(vis.nbytes + src.nbytes + jobs.nbytes), 'd2h_bytes': int(out['results'].nbytes),
             'transform_gmacs_per_s': macs / (((k_tr + k_rec) / max(1, k_n)) * 1e-3) / 1e9 if k_n else None,
             'transform_int_alu_frac': (macs / (((k_tr + k_rec) / max(1, k_n)) * 1e-3) / 1e9) / int_peak[0] if k_n and int_peak[0] else None,

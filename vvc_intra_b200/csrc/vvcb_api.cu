@@ -11,6 +11,8 @@
 #include "vvcb_feat.cuh"
 #include "vvcb_dq.cuh"
 #include <vector>
+#include <thread>
+#include <atomic>
 #include "vvcb_romfill.h"
 
 // =====================================================================================================
@@ -313,9 +315,33 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   return VVCB_OK;
 }
 
+// Host-side validation of large batches runs on a few threads: returns the smallest index for which ok(i) is false, or -1.
+template <class F> static int first_bad_index(int n, F ok)
+{
+  const int kMinPerThread = 32768;
+  int threads = (int)std::thread::hardware_concurrency();
+  if (threads > 8) threads = 8;
+  if (threads < 1 || n < 2 * kMinPerThread) threads = 1;
+  if (threads > n / kMinPerThread) threads = n / kMinPerThread > 0 ? n / kMinPerThread : 1;
+  std::atomic<int> bad(n);
+  auto work = [&](int lo, int hi) {
+    for (int i = lo; i < hi && i < bad.load(std::memory_order_relaxed); i++)
+      if (!ok(i)) { int cur = bad.load(); while (i < cur && !bad.compare_exchange_weak(cur, i)) {} break; }
+  };
+  if (threads == 1) work(0, n);
+  else {
+    std::vector<std::thread> pool;
+    const int per = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) pool.emplace_back(work, t * per, (t + 1) * per < n ? (t + 1) * per : n);
+    for (auto& th : pool) th.join();
+  }
+  const int b = bad.load();
+  return b < n ? b : -1;
+}
+
 static int check_visits(vvcb_ctx* ctx, const vvcb_rmd_visit* v, int n, int first = 0)
 {
-  for (int i = 0; i < n; i++) {
+  const int badIdx = first_bad_index(n, [&](int i) {
     const int w = 1 << v[i].log2w, h = 1 << v[i].log2h;
     const bool ok = v[i].log2w >= 2 && v[i].log2w <= 6 && v[i].log2h >= 2 && v[i].log2h <= 6 && v[i].x >= 0 && v[i].y >= 0 &&
                     (v[i].x & 3) == 0 && (v[i].y & 3) == 0 && v[i].x + w <= ctx->width && v[i].y + h <= ctx->height &&
@@ -327,10 +353,11 @@ static int check_visits(vvcb_ctx* ctx, const vvcb_rmd_visit* v, int n, int first
                     v[i].x + w + 4 * v[i].n_above_right <= ctx->width && v[i].y + h + 4 * v[i].n_below_left <= ctx->height;
     bool mpmOk = true;
     for (int k = 0; k < 6; k++) mpmOk = mpmOk && v[i].mpm[k] < VVCB_NUM_LUMA_MODE;
-    if (!ok || !mpmOk) {
-      snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: visit %d is malformed (position/size/availability outside the picture)", first + i);
-      return VVCB_ERR_ARG;
-    }
+    return ok && mpmOk;
+  });
+  if (badIdx >= 0) {
+    snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: visit %d is malformed (position/size/availability outside the picture)", first + badIdx);
+    return VVCB_ERR_ARG;
   }
   return VVCB_OK;
 }
@@ -491,7 +518,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval_pred: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
     const int rcv = check_visits(ctx, visits, n_visits);
     if (rcv) return rcv;
-    for (int i = 0; i < n; i++) {
+    const int badSrc = first_bad_index(n, [&](int i) {
       bool ok = src[i].visit < (uint32_t)n_visits && src[i].slot < VVCB_NUM_SLOTS;
       if (ok) {
         const vvcb_rmd_visit& v = visits[src[i].visit];
@@ -501,25 +528,31 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
         ok = (slot < VVCB_SLOT_MRL1 || (slot < VVCB_SLOT_MIP ? mrlAllowed : slot - VVCB_SLOT_MIP < numMip)) &&
              jobs[i].x == v.x && jobs[i].y == v.y && jobs[i].log2w == v.log2w && jobs[i].log2h == v.log2h;
       }
-      if (!ok) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval_pred: source %d is malformed (visit index, slot not evaluated for the visit, or job geometry differs from the visit)", i); return VVCB_ERR_ARG; }
-    }
+      return ok;
+    });
+    if (badSrc >= 0) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval_pred: source %d is malformed (visit index, slot not evaluated for the visit, or job geometry differs from the visit)", badSrc); return VVCB_ERR_ARG; }
   }
-  bool anyQuant = false;
-  std::vector<int> order;                 // DepQuant jobs (sorted on the device by scan length once the coefficients exist)
-  for (int i = 0; i < n; i++) {
+  const int badJob = first_bad_index(n, [&](int i) {
     const vvcb_tu_job& j = jobs[i];
     const size_t sz = (size_t)1 << (j.log2w + j.log2h);
     const bool q = (j.flags & VVCB_TU_QUANT) != 0;
     const bool dq = q && (j.flags & VVCB_TU_DEPQUANT);
-    anyQuant = anyQuant || q;
     bool ok = j.log2w >= 2 && j.log2w <= 6 && j.log2h >= 2 && j.log2h <= 6 && j.mts_idx <= 5 && (size_t)j.offset + sz <= n_samples &&
               j.qp_rem >= 0 && j.qp_rem < 6 && j.qp_per >= 0 && j.qp_per < 16;
     if (j.mts_idx == 1) ok = ok && j.log2w <= 5 && j.log2h <= 5;                 // TU::isTSAllowed, CL/UnitTools.cpp:4524
     if (j.mts_idx > 1)  ok = ok && j.log2w <= 5 && j.log2h <= 5;                 // TU::isMTSAllowed, :4549
     if (q) ok = ok && ctx->bOrig && j.x >= 0 && j.y >= 0 && j.x + (1 << j.log2w) <= ctx->width && j.y + (1 << j.log2h) <= ctx->height;
     if (dq) ok = ok && j.mts_idx != 1 && rates && j.rate_idx < n_rates && j.lfnst_idx <= 2 && j.lambda > 0.0;   // CL/DepQuant.cpp:1757: TS goes to RDOQ
-    if (!ok) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: job %d is malformed", i); return VVCB_ERR_ARG; }
-    if (dq) order.push_back(i);
+    return ok;
+  });
+  if (badJob >= 0) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: job %d is malformed", badJob); return VVCB_ERR_ARG; }
+  bool anyQuant = false;
+  std::vector<int> order;                 // DepQuant jobs (sorted on the device by scan length once the coefficients exist)
+  order.reserve(n);
+  for (int i = 0; i < n; i++) {
+    const bool q = (jobs[i].flags & VVCB_TU_QUANT) != 0;
+    anyQuant = anyQuant || q;
+    if (q && (jobs[i].flags & VVCB_TU_DEPQUANT)) order.push_back(i);
   }
   if (anyQuant && !pred && !src) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: VVCB_TU_QUANT needs the prediction samples"); return VVCB_ERR_ARG; }
   const int nDq = (int)order.size();
@@ -545,11 +578,13 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     if ((rc = tu_buf(ctx, 13, (size_t)nDq * 3 * sizeof(int)))) return rc;
   }
   CK(cudaMemcpyAsync(ctx->dTu[0], jobs, (size_t)n * sizeof(vvcb_tu_job), cudaMemcpyHostToDevice, ctx->stream));
+  const bool tm = ctx->timing != 0;
   if (src) {
     if ((rc = tu_buf(ctx, 14, (size_t)n_visits * sizeof(vvcb_rmd_visit)))) return rc;
     if ((rc = tu_buf(ctx, 15, (size_t)n * sizeof(vvcb_tu_src)))) return rc;
     CK(cudaMemcpyAsync(ctx->dTu[14], visits, (size_t)n_visits * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dTu[15], src, (size_t)n * sizeof(vvcb_tu_src), cudaMemcpyHostToDevice, ctx->stream));
+    if (tm) CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     TuPredParams Q;
     Q.visits = static_cast<const vvcb_rmd_visit*>(ctx->dTu[14]); Q.src = static_cast<const vvcb_tu_src*>(ctx->dTu[15]);
     Q.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); Q.n = n;
@@ -578,8 +613,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     CK(cudaMemcpyAsync(ctx->dTu[9], order.data(), (size_t)nDq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dTu[10], rates, (size_t)n_rates * sizeof(vvcb_dq_rates), cudaMemcpyHostToDevice, ctx->stream));
   }
-  const bool tm = ctx->timing != 0;
-  if (tm) CK(cudaEventRecord(ctx->tev[0], ctx->stream));
+  if (tm && !src) CK(cudaEventRecord(ctx->tev[0], ctx->stream));
   tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
   ctx->launches++;
   if (tm) CK(cudaEventRecord(ctx->tev[1], ctx->stream));
