@@ -106,7 +106,11 @@ extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_
     std::vector<uint8_t> scratch((size_t)grid * kDqGroups * kDqSlotBytes);
     std::vector<int> firstRaw(nDq), orderSorted(nDq), firstSorted(nDq);
     emu_launch(2, kDqThreads, [&] { dq_first_kernel(jobs, order.data(), nDq, dqCoeff.data(), &dqRom, bd, firstRaw.data()); });
-    emu_launch(1, 1024, [&] { dq_sort_kernel(order.data(), firstRaw.data(), nDq, orderSorted.data(), firstSorted.data()); });
+    std::vector<int> binCount(kDqBins, 0);
+    const int sortGrid = (nDq + kDqSortPerBlock - 1) / kDqSortPerBlock;
+    emu_launch(sortGrid, kDqSortThreads, [&] { dq_hist_kernel(firstRaw.data(), nDq, binCount.data()); });
+    emu_launch(1, 32, [&] { dq_scan_kernel(binCount.data()); });
+    emu_launch(sortGrid, kDqSortThreads, [&] { dq_scatter_kernel(order.data(), firstRaw.data(), nDq, binCount.data(), orderSorted.data(), firstSorted.data()); });
     DqParams D;
     D.jobs = jobs; D.order = orderSorted.data(); D.firstPos = firstSorted.data(); D.n = nDq; D.coeff = dqCoeff.data(); D.level = level; D.deq = dqDeq.data(); D.results = results;
     D.rates = rates; D.tabs = tabs.data(); D.rom = &dqRom; D.scratch = scratch.data(); D.bd = bd;

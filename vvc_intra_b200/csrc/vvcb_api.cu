@@ -575,7 +575,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     if ((rc = tu_buf(ctx, 10, (size_t)n_rates * sizeof(vvcb_dq_rates)))) return rc;
     if ((rc = tu_buf(ctx, 11, (size_t)n_rates * sizeof(DqRateTab)))) return rc;
     if ((rc = tu_buf(ctx, 12, (size_t)dqGrid * kDqGroups * kDqSlotBytes))) return rc;
-    if ((rc = tu_buf(ctx, 13, (size_t)nDq * 3 * sizeof(int)))) return rc;
+    if ((rc = tu_buf(ctx, 13, ((size_t)nDq * 3 + kDqBins) * sizeof(int)))) return rc;
   }
   CK(cudaMemcpyAsync(ctx->dTu[0], jobs, (size_t)n * sizeof(vvcb_tu_job), cudaMemcpyHostToDevice, ctx->stream));
   const bool tm = ctx->timing != 0;
@@ -625,7 +625,12 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     int* firstSorted = firstRaw + 2 * nDq;
     const int firstGrid = (nDq + kDqGroups - 1) / kDqGroups < ctx->numSms * 8 ? (nDq + kDqGroups - 1) / kDqGroups : ctx->numSms * 8;
     dq_first_kernel<<<firstGrid, kDqThreads, 0, ctx->stream>>>(P.jobs, static_cast<const int*>(ctx->dTu[9]), nDq, P.dqCoeff, ctx->dDqRom, ctx->bd, firstRaw);
-    dq_sort_kernel<<<1, 1024, 0, ctx->stream>>>(static_cast<const int*>(ctx->dTu[9]), firstRaw, nDq, orderSorted, firstSorted);
+    int* binCount = firstRaw + 3 * (size_t)nDq;
+    const int sortGrid = (nDq + kDqSortPerBlock - 1) / kDqSortPerBlock;
+    CK(cudaMemsetAsync(binCount, 0, kDqBins * sizeof(int), ctx->stream));
+    dq_hist_kernel<<<sortGrid, kDqSortThreads, 0, ctx->stream>>>(firstRaw, nDq, binCount);
+    dq_scan_kernel<<<1, 32, 0, ctx->stream>>>(binCount);
+    dq_scatter_kernel<<<sortGrid, kDqSortThreads, 0, ctx->stream>>>(static_cast<const int*>(ctx->dTu[9]), firstRaw, nDq, binCount, orderSorted, firstSorted);
     D.jobs = P.jobs; D.order = orderSorted; D.firstPos = firstSorted; D.n = nDq;
     D.coeff = P.dqCoeff; D.level = P.level; D.deq = static_cast<int32_t*>(ctx->dTu[8]); D.results = P.results;
     D.rates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]); D.tabs = static_cast<const DqRateTab*>(ctx->dTu[11]);
@@ -634,7 +639,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     if (tm) CK(cudaEventRecord(ctx->tev[2], ctx->stream));
     P.phase = 1;
     tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
-    ctx->launches += 5;
+    ctx->launches += 7;
   } else if (tm) CK(cudaEventRecord(ctx->tev[2], ctx->stream));
   if (tm) CK(cudaEventRecord(ctx->tev[3], ctx->stream));
   CK(cudaGetLastError());

@@ -189,22 +189,46 @@ __global__ void __launch_bounds__(kDqThreads) dq_first_kernel(const vvcb_tu_job*
 }
 
 // Counting sort of the jobs by first test position, longest scan first, so that the eight groups of a warp walk scans of the
-// same length and reach their sub-block boundaries in the same iteration.  One block; 1025 bins.
-__global__ void __launch_bounds__(1024) dq_sort_kernel(const int* jobsIdx, const int* firstIn, int n, int* orderOut, int* firstOut)
+// same length and reach their sub-block boundaries in the same iteration.  1025 bins; three launches: per-block histograms
+// folded into a global one, a one-block exclusive scan over descending keys, and a scatter in which every block reserves its
+// share of each bin with one global atomic and places its own elements with shared-memory atomics.
+constexpr int kDqSortThreads = 256;
+constexpr int kDqSortPerBlock = 4096;       // elements per block
+constexpr int kDqBins = 1025;
+
+__global__ void __launch_bounds__(kDqSortThreads) dq_hist_kernel(const int* firstIn, int n, int* binCount)
 {
-  __shared__ int bin[1025];
-  for (int i = threadIdx.x; i < 1025; i += blockDim.x) bin[i] = 0;
+  __shared__ int bin[kDqBins];
+  for (int i = threadIdx.x; i < kDqBins; i += blockDim.x) bin[i] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&bin[firstIn[i] + 1], 1);
+  const int lo = blockIdx.x * kDqSortPerBlock, hi = vmin(n, lo + kDqSortPerBlock);
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&bin[firstIn[i] + 1], 1);
   __syncthreads();
-  if (threadIdx.x == 0) {                       // exclusive prefix over descending keys
+  for (int i = threadIdx.x; i < kDqBins; i += blockDim.x) if (bin[i]) atomicAdd(&binCount[i], bin[i]);
+}
+
+__global__ void dq_scan_kernel(int* binCount)      // in place: count -> first output index of the bin (descending keys)
+{
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     int acc = 0;
-    for (int b = 1024; b >= 0; b--) { const int c = bin[b]; bin[b] = acc; acc += c; }
+    for (int b = kDqBins - 1; b >= 0; b--) { const int c = binCount[b]; binCount[b] = acc; acc += c; }
   }
+}
+
+__global__ void __launch_bounds__(kDqSortThreads) dq_scatter_kernel(const int* jobsIdx, const int* firstIn, int n, int* binCursor,
+                                                                    int* orderOut, int* firstOut)
+{
+  __shared__ int bin[kDqBins], base[kDqBins];
+  for (int i = threadIdx.x; i < kDqBins; i += blockDim.x) bin[i] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  const int lo = blockIdx.x * kDqSortPerBlock, hi = vmin(n, lo + kDqSortPerBlock);
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&bin[firstIn[i] + 1], 1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kDqBins; i += blockDim.x) { base[i] = bin[i] ? atomicAdd(&binCursor[i], bin[i]) : 0; bin[i] = 0; }
+  __syncthreads();
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const int f = firstIn[i];
-    const int at = atomicAdd(&bin[f + 1], 1);
+    const int at = base[f + 1] + atomicAdd(&bin[f + 1], 1);
     orderOut[at] = jobsIdx[i];
     firstOut[at] = f;
   }
