@@ -58,6 +58,7 @@ struct vvcb_ctx {
   void* dFeat[2]; size_t capFeat[2]; // feature scratch: jobs / per-CTU sums, results
   // copy/compute pipeline of vvcb_rmd_eval for large host batches
   cudaStream_t sIn, sOut; cudaEvent_t evIn[2], evComp[2], evOut[2];
+  cudaStream_t sKind[2]; cudaEvent_t evPlan, evKind[2];   // planar/DC and MIP buckets run beside the angular ones: their CTAs fill the tails
   vvcb_rmd_visit* dVisP[2]; vvcb_rmd_result* dResP[2]; bool pipeReady;
   int16_t* dOrig; int16_t* dReco;
   const int16_t* bOrig; const int16_t* bReco;   // planes in use (own or bound)
@@ -124,6 +125,11 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
   ctx->numSms = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  for (int i = 0; i < 2; i++) {
+    if ((e = cudaStreamCreateWithFlags(&ctx->sKind[i], cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->evKind[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  }
+  if ((e = cudaEventCreateWithFlags(&ctx->evPlan, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
   for (int i = 0; i < 4; i++) if ((e = cudaEventCreate(&ctx->kev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -172,6 +178,8 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   }
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->kev[i]); cudaEventDestroy(ctx->tev[i]); }
+  for (int i = 0; i < 2; i++) { cudaStreamSynchronize(ctx->sKind[i]); cudaStreamDestroy(ctx->sKind[i]); cudaEventDestroy(ctx->evKind[i]); }
+  cudaEventDestroy(ctx->evPlan);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -300,7 +308,15 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   int grid = ctx->numSms * VVCB_EVAL_MIN_CTAS;
   if (grid > maxCtas) grid = (int)maxCtas;
   if (grid < 1) grid = 1;
-  for (int b = 0; b < kNumBuckets; b++) { VVCB_FOR_BUCKET(b, launch_eval_bucket, P, grid, ctx->stream); }
+  // one stream per prediction kind: the launches of a kind stay ordered, kernels of different kinds overlap at their tails
+  CK(cudaEventRecord(ctx->evPlan, ctx->stream));
+  for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(ctx->sKind[i], ctx->evPlan, 0));
+  for (int b = 0; b < kNumBuckets; b++) {
+    const int kind = b % kNumKinds;
+    cudaStream_t st = kind == 0 ? ctx->stream : ctx->sKind[kind - 1];
+    VVCB_FOR_BUCKET(b, launch_eval_bucket, P, grid, st);
+  }
+  for (int i = 0; i < 2; i++) { CK(cudaEventRecord(ctx->evKind[i], ctx->sKind[i])); CK(cudaStreamWaitEvent(ctx->stream, ctx->evKind[i], 0)); }
   if (tm) CK(cudaEventRecord(ctx->kev[2], ctx->stream));
   if (dDetails) { rmd_detail_kernel<<<(n + 31) / 32, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dDetails, P.sadSM, P.satdSM); ctx->launches++; }
   rmd_lists_kernel<<<(n + kListThreads - 1) / kListThreads, kListThreads, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dResults, dDetails, P.sadSM, P.satdSM);
