@@ -156,14 +156,18 @@ int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t*
  * (EL/IntraSearch.cpp:2694) after the prediction: TrQuant::transformNxN(trModes) (CL/TrQuant.cpp:1049) when
  * VVCB_TU_QUANT is clear, transformNxN(quant) (:1127) + invTransformNxN (:561) + PelBuf::reconstruct + RdCost::xGetSSE
  * (CL/RdCost.cpp:1739) when it is set.  Quantisation is the scalar Quant::quant (CL/Quant.cpp:994, intra rounding) or,
- * with VVCB_TU_DEPQUANT, the reference's dependent quantisation; RDOQ (transform skip under the shipped cfg) is not built. */
+ * with VVCB_TU_DEPQUANT, the reference's dependent quantisation, or, with VVCB_TU_RDOQ_TS, its RDOQ for transform skip.        */
 #define VVCB_TU_QUANT     1u   /* quantise + reconstruct + SSE                                                              */
 #define VVCB_TU_DEPQUANT  2u   /* with VVCB_TU_QUANT: dependent (trellis-coded) quantisation, DQIntern::DepQuant::quant
                                   (CL/DepQuant.cpp:1592-1731) and its state-machine dequantiser (:741-810), instead of the
                                   scalar Quant::quant.  Not for transform skip (the reference sends those to RDOQ, :1757).    */
+#define VVCB_TU_RDOQ_TS   4u   /* with VVCB_TU_QUANT, transform skip only: QuantRDOQ::xRateDistOptQuantTS (CL/QuantRDOQ.cpp:1243),
+                                  what the shipped configuration (RDOQTS 1) runs for transform-skip candidates; uses lambda and
+                                  rate_idx like dependent quantisation.                                                      */
 
-/* Context prices the dependent quantiser's RateEstimator reads (CL/DepQuant.cpp:479-629), luma: BinFracBits::intBits[0..1] of
- * each context, taken from the CABAC estimator snapshot the reference passes as `ctx` (ctx.getFracBitsAcess()).               */
+/* Context prices the rate-distortion quantisers read, luma: BinFracBits::intBits[0..1] of each context, taken from the CABAC
+ * estimator snapshot the reference passes as `ctx` (ctx.getFracBitsAcess()).  First block: the dependent quantiser's
+ * RateEstimator (CL/DepQuant.cpp:479-629).                                                                                 */
 typedef struct vvcb_dq_rates {
   uint32_t sig_sbb[2][2];      /* Ctx::SigCoeffGroup[CHANNEL_TYPE_LUMA](0..1)                                                  */
   uint32_t sig[3][12][2];      /* Ctx::SigFlag[0], SigFlag[2], SigFlag[4]: one set per quantiser-state class                   */
@@ -172,6 +176,13 @@ typedef struct vvcb_dq_rates {
   uint32_t gt2[21][2];         /* Ctx::GtxFlag[luma]                                                                          */
   uint32_t last_x[20][2];      /* Ctx::LastX[luma]                                                                            */
   uint32_t last_y[20][2];      /* Ctx::LastY[luma]                                                                            */
+  /* transform-skip residual coding, read by QuantRDOQ::xRateDistOptQuantTS (CL/QuantRDOQ.cpp:1243-1485); VVCB_TU_RDOQ_TS only */
+  uint32_t ts_sig_sbb[3][2];   /* Ctx::TsSigCoeffGroup                                                                        */
+  uint32_t ts_sig[3][2];       /* Ctx::TsSigFlag                                                                              */
+  uint32_t ts_par[1][2];       /* Ctx::TsParFlag                                                                              */
+  uint32_t ts_gtx[5][2];       /* Ctx::TsGtxFlag                                                                              */
+  uint32_t ts_lrg1[4][2];      /* Ctx::TsLrg1Flag                                                                             */
+  uint32_t ts_sign[6][2];      /* Ctx::TsResidualSign                                                                         */
 } vvcb_dq_rates;
 
 typedef struct vvcb_tu_job {

@@ -284,13 +284,20 @@ def features_batch(orig, jobs):
 
 # ---- dependent quantisation (oracle/vvc_oracle_dq.c) -------------------------------------------------------
 DQ_RATES_DTYPE = np.dtype([('sig_sbb', '<u4', (2, 2)), ('sig', '<u4', (3, 12, 2)), ('par', '<u4', (21, 2)), ('gt1', '<u4', (21, 2)),
-                           ('gt2', '<u4', (21, 2)), ('last_x', '<u4', (20, 2)), ('last_y', '<u4', (20, 2))])
-assert DQ_RATES_DTYPE.itemsize == 4 * 2 * (2 + 36 + 63 + 40)
+                           ('gt2', '<u4', (21, 2)), ('last_x', '<u4', (20, 2)), ('last_y', '<u4', (20, 2)),
+                           ('ts_sig_sbb', '<u4', (3, 2)), ('ts_sig', '<u4', (3, 2)), ('ts_par', '<u4', (1, 2)), ('ts_gtx', '<u4', (5, 2)),
+                           ('ts_lrg1', '<u4', (4, 2)), ('ts_sign', '<u4', (6, 2))])
+assert DQ_RATES_DTYPE.itemsize == 4 * 2 * (2 + 36 + 63 + 40 + 22)
 
 
-def dq_rates_from_flat(flat):
-    """The 'D' record's flat context-price vector -> one vvcb_dq_rates struct."""
-    return np.frombuffer(np.ascontiguousarray(flat, '<u4').tobytes(), DQ_RATES_DTYPE)[0]
+def dq_rates_from_flat(flat, ts_flat=None):
+    """The 'D' record's flat context-price vector (282 words) and / or the 'T' record's (44 words) -> one vvcb_dq_rates struct."""
+    buf = np.zeros(DQ_RATES_DTYPE.itemsize // 4, '<u4')
+    if flat is not None:
+        buf[:282] = flat
+    if ts_flat is not None:
+        buf[282:] = ts_flat
+    return np.frombuffer(buf.tobytes(), DQ_RATES_DTYPE)[0]
 
 
 def dep_quant(coeff, bd, mts_idx, lfnst_idx, qp, lam, rates, cbf_delta_bits):
@@ -309,3 +316,13 @@ def dep_dequant(level, bd, qp):
     coeff = np.zeros((h, w), np.int32)
     lib().orc_dep_dequant(level.ctypes.data_as(_p32), w, h, bd, qp, coeff.ctypes.data_as(_p32))
     return coeff
+
+
+def rdoq_ts(coeff, bd, qp, lam, rates):
+    """QuantRDOQ::xRateDistOptQuantTS.  coeff: transform-skip coefficients (residual << transformShift)."""
+    coeff = np.ascontiguousarray(coeff, np.int32)
+    h, w = coeff.shape
+    level = np.zeros((h, w), np.int32)
+    r = np.ascontiguousarray(np.array([rates], DQ_RATES_DTYPE))
+    s = lib().orc_rdoq_ts(coeff.ctypes.data_as(_p32), w, h, bd, qp, C.c_double(lam), C.c_void_p(r.ctypes.data), level.ctypes.data_as(_p32))
+    return level, s

@@ -449,6 +449,22 @@ void __wrap__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamR
     for( int y = 0; y < (int) rect.height; y++ ) for( int x = 0; x < (int) rect.width; x++ ) d.i32( lv.at( x, y ) );
     d.emit( 'D' );
   }
+  // 'T' (RDOQ for transform skip, CL/QuantRDOQ.cpp:1243): i32 w,h,bitDepth,qp,per,rem,absSum, f64 lambda,
+  // u32 tsSigSbb[3][2], tsSig[3][2], tsPar[1][2], tsGtx[5][2], tsLrg1[4][2], tsSign[6][2], resi[w*h] i16, coeff[w*h] i32, level[w*h] i32
+  if( ts && !tu.cu->bdpcmMode )
+  {
+    const FracBitsAccess& fb = ctx.getFracBitsAcess();
+    Rec d;
+    d.i32( rect.width ); d.i32( rect.height ); d.i32( tu.cs->sps->getBitDepth( CHANNEL_TYPE_LUMA ) );
+    d.i32( qp.Qp( true ) ); d.i32( qp.per( true ) ); d.i32( qp.rem( true ) ); d.i32( absSum );
+    d.f64( tq->m_quant->getLambda() );
+    auto put = [&]( const CtxSet& set, int num ) { for( int i = 0; i < num; i++ ) { const BinFracBits b = fb.getFracBitsArray( set( i ) ); d.u32( b.intBits[0] ); d.u32( b.intBits[1] ); } };
+    put( Ctx::TsSigCoeffGroup, 3 ); put( Ctx::TsSigFlag, 3 ); put( Ctx::TsParFlag, 1 ); put( Ctx::TsGtxFlag, 5 ); put( Ctx::TsLrg1Flag, 4 ); put( Ctx::TsResidualSign, 6 );
+    putBlock( d, tu.cs->getResiBuf( rect ) );
+    for( int i = 0; i < n; i++ ) d.i32( co[i] );
+    for( int y = 0; y < (int) rect.height; y++ ) for( int x = 0; x < (int) rect.width; x++ ) d.i32( lv.at( x, y ) );
+    d.emit( 'T' );
+  }
 }
 
 // 'I' (dequant + inverse): i32 w,h,bitDepth,mtsIdx,qp,per,rem, level[w*h] i32, resi[w*h] i16

@@ -300,7 +300,7 @@ def build_dq_batch(tus, bd, seed=0):
         j['flags'] = vb.TU_QUANT | vb.TU_DEPQUANT
         j['qp_per'], j['qp_rem'], j['offset'] = r['per'], r['rem'], off
         j['rate_idx'], j['lfnst_idx'], j['cbf_delta_bits'], j['lambda'] = i, r['lfnst'], r['cbf_delta'], r['lambda']
-        rates[i] = np.frombuffer(np.ascontiguousarray(r['rates'], '<u4').tobytes(), vb.DQ_RATES_DTYPE)[0]
+        rates[i] = O.dq_rates_from_flat(r['rates'])
         items.append(dict(rec=r, pred=pred, org=org, off=off))
         off += w * h
     return orig, jobs, np.concatenate([r['resi'].ravel() for r in recs]), np.concatenate([it['pred'].ravel() for it in items]), rates, items
@@ -432,3 +432,105 @@ def pred_tu_case(rng, bd, n_per_shape, slots_per_visit=4):
             jobs.append(j)
             off += w * h
     return orig, reco, visits, np.array(src, vb.TU_SRC_DTYPE), np.array(jobs, vb.TU_JOB_DTYPE), off, rates, items
+
+
+# ---- RDOQ of transform-skip TUs: batches from the reference's 'T' records -----------------------------------
+def build_rdoq_batch(tus, bd, seed=0):
+    import vvc_intra_b200 as vb
+    rng = np.random.default_rng(seed)
+    recs = [r for r in tus if r['tag'] == 'T' and r['bd'] == bd]
+    n = len(recs)
+    cols = 16
+    orig = np.zeros((64 * ((n + cols - 1) // cols + 1), 64 * cols), np.int16)
+    jobs = np.zeros(n, vb.TU_JOB_DTYPE)
+    rates = np.zeros(n, vb.DQ_RATES_DTYPE)
+    mx = (1 << bd) - 1
+    items, off = [], 0
+    for i, r in enumerate(recs):
+        resi = r['resi']
+        h, w = resi.shape
+        pred = np.clip(rng.integers(0, mx + 1, (h, w)), np.maximum(0, -resi), np.minimum(mx, mx - resi)).astype(np.int16)
+        org = np.clip(pred.astype(np.int32) + resi, 0, mx).astype(np.int16)
+        cx, cy = 64 * (i % cols), 64 * (i // cols)
+        orig[cy:cy + h, cx:cx + w] = org
+        j = jobs[i]
+        j['x'], j['y'], j['log2w'], j['log2h'], j['mts_idx'] = cx, cy, w.bit_length() - 1, h.bit_length() - 1, 1
+        j['flags'] = vb.TU_QUANT | vb.TU_RDOQ_TS
+        j['qp_per'], j['qp_rem'], j['offset'], j['rate_idx'], j['lambda'] = r['per'], r['rem'], off, i, r['lambda']
+        rates[i] = O.dq_rates_from_flat(None, r['rates'])
+        items.append(dict(rec=r, pred=pred, org=org, off=off))
+        off += w * h
+    return orig, jobs, np.concatenate([r['resi'].ravel() for r in recs]), np.concatenate([it['pred'].ravel() for it in items]), rates, items
+
+
+def check_rdoq_outputs(items, bd, out):
+    errs = []
+    for i, it in enumerate(items):
+        r = it['rec']
+        h, w = r['resi'].shape
+        sl = slice(it['off'], it['off'] + w * h)
+        res = out['results'][i]
+        if not np.array_equal(out['level'][sl].reshape(h, w), r['level']):
+            errs.append('job %d %dx%d: levels differ (%d positions)' % (i, w, h, int((out['level'][sl].reshape(h, w) != r['level']).sum())))
+        if int(res['abs_sum_level']) != r['abs_sum']:
+            errs.append('job %d: abs sum %d != %d' % (i, res['abs_sum_level'], r['abs_sum']))
+        deq = O.dequant(r['level'], bd, r['per'], r['rem'], True)
+        resi = O.inv_transform(deq, bd, 1)
+        reco, sse = O.reconstruct_sse(it['org'], it['pred'], resi, bd)
+        if not np.array_equal(out['reco'][sl].reshape(h, w), reco):
+            errs.append('job %d %dx%d: reconstruction differs' % (i, w, h))
+        if int(res['sse']) != int(sse):
+            errs.append('job %d: sse %d != %d' % (i, res['sse'], sse))
+    return errs
+
+
+def random_rdoq_case(rng, bd, n_per_shape):
+    import vvc_intra_b200 as vb
+    mx = (1 << bd) - 1
+    items = []
+    for lw in range(2, 6):
+        for lh in range(2, 6):
+            for _ in range(n_per_shape):
+                w, h = 1 << lw, 1 << lh
+                a = min(int(rng.choice([1, 4, 20, 120, mx])), mx)
+                pred = rng.integers(0, mx + 1, (h, w))
+                org = np.clip(pred + rng.integers(-a, a + 1, (h, w)), 0, mx)
+                qp = int(rng.integers(4, 52)) + 6 * (bd - 8)
+                items.append(dict(pred=pred.astype(np.int16), org=org.astype(np.int16), resi=(org - pred).astype(np.int16), qp=qp,
+                                  lam=float(rng.uniform(0.3, 3.0) * 0.57 * 2.0 ** ((qp - 6 * (bd - 8) - 12) / 3.0))))
+    n = len(items)
+    cols = 16
+    orig = np.zeros((64 * ((n + cols - 1) // cols + 1), 64 * cols), np.int16)
+    jobs = np.zeros(n, vb.TU_JOB_DTYPE)
+    n_rates = 5
+    rates = np.zeros(n_rates, vb.DQ_RATES_DTYPE)
+    for name in rates.dtype.names:
+        rates[name] = rng.integers(300, 140000, rates[name].shape)
+    off = 0
+    for i, it in enumerate(items):
+        h, w = it['resi'].shape
+        cx, cy = 64 * (i % cols), 64 * (i // cols)
+        orig[cy:cy + h, cx:cx + w] = it['org']
+        j = jobs[i]
+        j['x'], j['y'], j['log2w'], j['log2h'], j['mts_idx'] = cx, cy, w.bit_length() - 1, h.bit_length() - 1, 1
+        j['flags'] = vb.TU_QUANT | vb.TU_RDOQ_TS
+        j['qp_per'], j['qp_rem'], j['offset'], j['rate_idx'], j['lambda'] = it['qp'] // 6, it['qp'] % 6, off, i % n_rates, it['lam']
+        it['off'], it['rate'] = off, rates[i % n_rates]
+        off += w * h
+    return orig, jobs, np.concatenate([it['resi'].ravel() for it in items]), np.concatenate([it['pred'].ravel() for it in items]), rates, items
+
+
+def oracle_rdoq_chain(items, bd):
+    import vvc_intra_b200 as vb
+    n = sum(it['resi'].size for it in items)
+    out = dict(results=np.zeros(len(items), vb.TU_RESULT_DTYPE), coeff=np.zeros(n, np.int32), level=np.zeros(n, np.int32), reco=np.zeros(n, np.int16))
+    for i, it in enumerate(items):
+        h, w = it['resi'].shape
+        sl = slice(it['off'], it['off'] + w * h)
+        co = O.fwd_transform(it['resi'], bd, 1)
+        lvl, s = O.rdoq_ts(co, bd, it['qp'], it['lam'], it['rate'])
+        res = O.inv_transform(O.dequant(lvl, bd, it['qp'] // 6, it['qp'] % 6, True), bd, 1)
+        reco, sse = O.reconstruct_sse(it['org'], it['pred'], res, bd)
+        out['coeff'][sl], out['level'][sl], out['reco'][sl] = co.ravel(), lvl.ravel(), reco.ravel()
+        out['results'][i] = (O.abs_sum_for_preselection(co, 1), s, sse)
+    return out

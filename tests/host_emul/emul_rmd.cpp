@@ -88,9 +88,11 @@ extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_
   static DqRom dqRom;
   fill_tr_rom(rom);
   fill_dq_rom(dqRom);
-  std::vector<int> order;
-  for (int i = 0; i < n; i++)
+  std::vector<int> order, tsOrder;
+  for (int i = 0; i < n; i++) {
     if ((jobs[i].flags & (VVCB_TU_QUANT | VVCB_TU_DEPQUANT)) == (VVCB_TU_QUANT | VVCB_TU_DEPQUANT)) order.push_back(i);
+    else if ((jobs[i].flags & (VVCB_TU_QUANT | VVCB_TU_RDOQ_TS)) == (VVCB_TU_QUANT | VVCB_TU_RDOQ_TS)) tsOrder.push_back(i);
+  }
   const int nDq = (int)order.size();
   std::vector<int32_t> dqCoeff(nSamples), dqDeq(nSamples, 0);
   memset(level, 0, nSamples * sizeof(int32_t));
@@ -115,6 +117,14 @@ extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_
     D.jobs = jobs; D.order = orderSorted.data(); D.firstPos = firstSorted.data(); D.n = nDq; D.coeff = dqCoeff.data(); D.level = level; D.deq = dqDeq.data(); D.results = results;
     D.rates = rates; D.tabs = tabs.data(); D.rom = &dqRom; D.scratch = scratch.data(); D.bd = bd;
     emu_launch(grid, kDqThreads, [&] { dq_kernel(D); });
+  }
+  if (!tsOrder.empty()) {
+    RdoqParams R;
+    R.jobs = jobs; R.order = tsOrder.data(); R.n = (int)tsOrder.size(); R.coeff = dqCoeff.data(); R.level = level; R.deq = dqDeq.data();
+    R.results = results; R.rates = rates; R.rom = &dqRom; R.bd = bd;
+    emu_launch(1, 128, [&] { rdoq_ts_kernel(R); });
+  }
+  if (nDq || !tsOrder.empty()) {
     P.phase = 1;
     emu_launch(2, kTuThreads, [&] { tu_eval_kernel(P); });
   }

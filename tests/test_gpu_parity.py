@@ -353,3 +353,34 @@ def test_tu_eval_with_device_prediction(bd, seed, eng8, eng10):
     badj['x'][0] += 4
     with pytest.raises(vb.EngineError, match='malformed'):
         eng.tu_eval_pred(visits, src, badj, n_samples, rates=rates)
+
+
+# ---- RDOQ of transform-skip TUs (VVCB_TU_RDOQ_TS) -----------------------------------------------------------
+@pytest.mark.parametrize('name,bd', [('ref_10b_128x128_qp27_rdoqts', 10), ('ref_8b_128x64_qp37_rdoqts', 8)])
+def test_rdoq_ts_golden_parity(name, bd, eng8, eng10):
+    """QuantRDOQ::xRateDistOptQuantTS as the reference ran it (RDOQTS on as shipped): recorded residuals and context prices in,
+    the recorded levels and absSum out; reconstruction + SSE versus the oracle."""
+    eng = eng8 if bd == 8 else eng10
+    _, tus = G.load_fixture(name)
+    orig, jobs, resi, pred, rates, items = G.build_rdoq_batch(tus, bd)
+    eng.frame_begin(orig)
+    out = eng.tu_eval(jobs, resi, pred, want_coeff=True, want_level=True, want_reco=True, rates=rates)
+    errs = G.check_rdoq_outputs(items, bd, out)
+    assert not errs, (len(errs), errs[:6])
+
+
+@pytest.mark.parametrize('bd,seed', [(8, 111), (10, 112)])
+def test_rdoq_ts_random_blocks_match_oracle(bd, seed, eng8, eng10):
+    eng = eng8 if bd == 8 else eng10
+    rng = np.random.default_rng(seed)
+    orig, jobs, resi, pred, rates, items = G.random_rdoq_case(rng, bd, 12)
+    eng.frame_begin(orig)
+    out = eng.tu_eval(jobs, resi, pred, want_coeff=True, want_level=True, want_reco=True, rates=rates)
+    exp = G.oracle_rdoq_chain(items, bd)
+    for k in ('coeff', 'level', 'reco'):
+        assert np.array_equal(out[k], exp[k]), k
+    assert out['results'].tobytes() == exp['results'].tobytes()
+    bad = jobs[:1].copy()
+    bad['mts_idx'] = 0                                       # RDOQ_TS is for transform skip only
+    with pytest.raises(vb.EngineError, match='malformed'):
+        eng.tu_eval(bad, resi, pred, rates=rates)

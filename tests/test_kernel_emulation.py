@@ -189,3 +189,27 @@ def test_emulated_tu_prediction_matches_oracle(emul, bd, seed):
         assert np.array_equal(resi[sl].reshape(it['pred'].shape), it['resi']), (it['pred'].shape, int(s['slot']))
         kinds.add('mip' if s['slot'] >= O.SLOT_MIP else 'mrl' if s['slot'] >= O.SLOT_MRL1 else 'reg')
     assert kinds == {'mip', 'mrl', 'reg'}
+
+
+# ---- RDOQ of transform-skip TUs (rdoq_ts_kernel) -----------------------------------------------------------------
+@pytest.mark.parametrize('name,bd', [('ref_10b_128x128_qp27_rdoqts', 10), ('ref_8b_128x64_qp37_rdoqts', 8)])
+def test_emulated_rdoq_ts_kernel_matches_reference(emul, name, bd):
+    _, tus = G.load_fixture(name)
+    orig, jobs, resi, pred, rates, items = G.build_rdoq_batch(tus, bd)
+    assert len(items) > 100
+    out = run_emul_tu(emul, orig, bd, jobs, resi, pred, rates)
+    errs = G.check_rdoq_outputs(items, bd, out)
+    assert not errs, (len(errs), errs[:6])
+
+
+@pytest.mark.parametrize('bd,seed', [(8, 101), (10, 102)])
+def test_emulated_rdoq_ts_kernel_matches_oracle_on_random_blocks(emul, bd, seed):
+    rng = np.random.default_rng(seed)
+    orig, jobs, resi, pred, rates, items = G.random_rdoq_case(rng, bd, 3)
+    out = run_emul_tu(emul, orig, bd, jobs, resi, pred, rates)
+    exp = G.oracle_rdoq_chain(items, bd)
+    for k in ('coeff', 'level', 'reco'):
+        bad = [i for i, it in enumerate(items) if not np.array_equal(out[k][it['off']:it['off'] + it['resi'].size], exp[k][it['off']:it['off'] + it['resi'].size])]
+        assert not bad, (k, len(bad), [(items[i]['resi'].shape, items[i]['qp']) for i in bad[:5]])
+    assert out['results'].tobytes() == exp['results'].tobytes()
+    assert (exp['results']['abs_sum_level'] > 0).sum() > len(items) // 3

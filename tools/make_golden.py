@@ -98,6 +98,11 @@ def extra_fixtures(which):
                                                                                  VVC_TRACE_MAX_VISITS=0, VVC_TRACE_TU_FIRST=3, VVC_TRACE_TU_STRIDE=900, VVC_TRACE_ONLY='D')),
         'ref_8b_128x64_qp37_depquant': lambda n: run(n, 128, 64, 8, 37, dict(VVC_TRACE_VISIT_FIRST=0, VVC_TRACE_VISIT_STRIDE=1000000,
                                                                              VVC_TRACE_MAX_VISITS=0, VVC_TRACE_TU_FIRST=3, VVC_TRACE_TU_STRIDE=500, VVC_TRACE_ONLY='D')),
+        # a13: RDOQ of transform-skip TUs (RDOQTS on as shipped)
+        'ref_10b_128x128_qp27_rdoqts': lambda n: run(n, 128, 128, 10, 27, dict(VVC_TRACE_VISIT_FIRST=0, VVC_TRACE_VISIT_STRIDE=1000000,
+                                                                               VVC_TRACE_MAX_VISITS=0, VVC_TRACE_TU_FIRST=3, VVC_TRACE_TU_STRIDE=40, VVC_TRACE_ONLY='T')),
+        'ref_8b_128x64_qp37_rdoqts': lambda n: run(n, 128, 64, 8, 37, dict(VVC_TRACE_VISIT_FIRST=0, VVC_TRACE_VISIT_STRIDE=1000000,
+                                                                           VVC_TRACE_MAX_VISITS=0, VVC_TRACE_TU_FIRST=3, VVC_TRACE_TU_STRIDE=20, VVC_TRACE_ONLY='T')),
     }
     with open(os.path.join(ROOT, 'tests/golden/MANIFEST.txt'), 'a') as f:
         for n in which or sorted(todo):

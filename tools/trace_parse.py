@@ -137,6 +137,15 @@ def parse_record(tag, payload):
         r['resi'] = c.i16(n).reshape(r['h'], r['w'])
         r['coeff'] = c.i32(n).reshape(r['h'], r['w'])
         r['level'] = c.i32(n).reshape(r['h'], r['w'])
+    elif tag == 'T':
+        for k in ('w', 'h', 'bd', 'qp', 'per', 'rem', 'abs_sum'):
+            r[k] = c.i32()
+        r['lambda'] = c.f64()
+        r['rates'] = c.u32(2 * 22)
+        n = r['w'] * r['h']
+        r['resi'] = c.i16(n).reshape(r['h'], r['w'])
+        r['coeff'] = c.i32(n).reshape(r['h'], r['w'])
+        r['level'] = c.i32(n).reshape(r['h'], r['w'])
     elif tag == 'H':
         r['w'], r['h'], r['result'] = c.i32(), c.i32(), c.i32()
         r['org'] = c.i16(r['w'] * r['h']).reshape(r['h'], r['w'])

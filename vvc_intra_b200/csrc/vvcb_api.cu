@@ -51,7 +51,7 @@ struct vvcb_ctx {
   cudaEvent_t ev0, ev1;
   Rom* dRom;
   TrRom* dTrRom;
-  void* dTu[16]; size_t capTu[16];  // TU scratch: jobs, resi, pred, coeff, level, reco, results; DepQuant: coeff in, dequantised out,
+  void* dTu[17]; size_t capTu[17];  // TU scratch: jobs, resi, pred, coeff, level, reco, results; DepQuant: coeff in, dequantised out,
                                     // job order, context prices, derived rate tables, per-group context memory + trellis
   DqRom* dDqRom;
   float tuMs[3]; int tuTimed; cudaEvent_t tev[4];   // per-kernel timing of vvcb_tu_eval: transform pass, dependent quantisation, reconstruction pass
@@ -168,7 +168,7 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dSlotMajor);
   cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred); cudaFree(ctx->dTrRom);
-  for (int i = 0; i < 16; i++) cudaFree(ctx->dTu[i]);
+  for (int i = 0; i < 17; i++) cudaFree(ctx->dTu[i]);
   cudaFree(ctx->dDqRom);
   for (int i = 0; i < 2; i++) cudaFree(ctx->dFeat[i]);
   if (ctx->pipeReady) {
@@ -559,17 +559,23 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     if (j.mts_idx > 1)  ok = ok && j.log2w <= 5 && j.log2h <= 5;                 // TU::isMTSAllowed, :4549
     if (q) ok = ok && ctx->bOrig && j.x >= 0 && j.y >= 0 && j.x + (1 << j.log2w) <= ctx->width && j.y + (1 << j.log2h) <= ctx->height;
     if (dq) ok = ok && j.mts_idx != 1 && rates && j.rate_idx < n_rates && j.lfnst_idx <= 2 && j.lambda > 0.0;   // CL/DepQuant.cpp:1757: TS goes to RDOQ
+    if (j.flags & VVCB_TU_RDOQ_TS) ok = ok && q && !dq && j.mts_idx == 1 && rates && j.rate_idx < n_rates && j.lambda > 0.0;
     return ok;
   });
   if (badJob >= 0) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: job %d is malformed", badJob); return VVCB_ERR_ARG; }
   bool anyQuant = false;
   std::vector<int> order;                 // DepQuant jobs (sorted on the device by scan length once the coefficients exist)
+  std::vector<int> tsBySize[7];
   order.reserve(n);
   for (int i = 0; i < n; i++) {
     const bool q = (jobs[i].flags & VVCB_TU_QUANT) != 0;
     anyQuant = anyQuant || q;
     if (q && (jobs[i].flags & VVCB_TU_DEPQUANT)) order.push_back(i);
+    else if (q && (jobs[i].flags & VVCB_TU_RDOQ_TS)) tsBySize[jobs[i].log2w + jobs[i].log2h - 4].push_back(i);
   }
+  std::vector<int> tsOrder;               // RDOQ transform-skip jobs, largest block first (one thread per block: equal chain lengths per warp)
+  for (int c = 6; c >= 0; c--) tsOrder.insert(tsOrder.end(), tsBySize[c].begin(), tsBySize[c].end());
+  const int nTs = (int)tsOrder.size();
   if (anyQuant && !pred && !src) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: VVCB_TU_QUANT needs the prediction samples"); return VVCB_ERR_ARG; }
   const int nDq = (int)order.size();
   CK(cudaSetDevice(ctx->device));
@@ -578,17 +584,20 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
   if ((rc = tu_buf(ctx, 1, n_samples * sizeof(int16_t)))) return rc;
   if ((rc = tu_buf(ctx, 2, n_samples * sizeof(int16_t)))) return rc;
   if (coeff && (rc = tu_buf(ctx, 3, n_samples * sizeof(int32_t)))) return rc;
-  if ((level || nDq) && (rc = tu_buf(ctx, 4, n_samples * sizeof(int32_t)))) return rc;
+  if ((level || nDq || nTs) && (rc = tu_buf(ctx, 4, n_samples * sizeof(int32_t)))) return rc;
   if (reco && (rc = tu_buf(ctx, 5, n_samples * sizeof(int16_t)))) return rc;
   if ((rc = tu_buf(ctx, 6, (size_t)n * sizeof(vvcb_tu_result)))) return rc;
   int dqGrid = 0;
+  if (nDq || nTs) {
+    if ((rc = tu_buf(ctx, 7, n_samples * sizeof(int32_t)))) return rc;
+    if ((rc = tu_buf(ctx, 8, n_samples * sizeof(int32_t)))) return rc;
+    if ((rc = tu_buf(ctx, 10, (size_t)n_rates * sizeof(vvcb_dq_rates)))) return rc;
+    if (nTs && (rc = tu_buf(ctx, 16, (size_t)nTs * sizeof(int)))) return rc;
+  }
   if (nDq) {
     dqGrid = (nDq + kDqGroups - 1) / kDqGroups;
     if (dqGrid > ctx->numSms * 4) dqGrid = ctx->numSms * 4;
-    if ((rc = tu_buf(ctx, 7, n_samples * sizeof(int32_t)))) return rc;
-    if ((rc = tu_buf(ctx, 8, n_samples * sizeof(int32_t)))) return rc;
     if ((rc = tu_buf(ctx, 9, (size_t)nDq * sizeof(int)))) return rc;
-    if ((rc = tu_buf(ctx, 10, (size_t)n_rates * sizeof(vvcb_dq_rates)))) return rc;
     if ((rc = tu_buf(ctx, 11, (size_t)n_rates * sizeof(DqRateTab)))) return rc;
     if ((rc = tu_buf(ctx, 12, (size_t)dqGrid * kDqGroups * kDqSlotBytes))) return rc;
     if ((rc = tu_buf(ctx, 13, ((size_t)nDq * 3 + kDqBins) * sizeof(int)))) return rc;
@@ -617,16 +626,17 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
   P.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); P.n = n;
   P.resi = static_cast<const int16_t*>(ctx->dTu[1]); P.pred = static_cast<const int16_t*>(ctx->dTu[2]);
   P.coeff = coeff ? static_cast<int32_t*>(ctx->dTu[3]) : nullptr;
-  P.level = (level || nDq) ? static_cast<int32_t*>(ctx->dTu[4]) : nullptr;
+  P.level = (level || nDq || nTs) ? static_cast<int32_t*>(ctx->dTu[4]) : nullptr;
   P.reco = reco ? static_cast<int16_t*>(ctx->dTu[5]) : nullptr;
   P.results = static_cast<vvcb_tu_result*>(ctx->dTu[6]);
   P.orig = ctx->bOrig; P.stride = ctx->stride; P.bd = ctx->bd; P.rom = ctx->dTrRom;
   P.dqCoeff = static_cast<int32_t*>(ctx->dTu[7]); P.dqDeq = static_cast<const int32_t*>(ctx->dTu[8]); P.phase = 0;
   const int grid = n < ctx->numSms * 8 ? n : ctx->numSms * 8;
-  if (nDq) {
+  if (nDq || nTs) {
     CK(cudaMemsetAsync(ctx->dTu[4], 0, n_samples * sizeof(int32_t), ctx->stream));     // levels / dequantised coefficients the
-    CK(cudaMemsetAsync(ctx->dTu[8], 0, n_samples * sizeof(int32_t), ctx->stream));     // trellis does not reach stay zero
-    CK(cudaMemcpyAsync(ctx->dTu[9], order.data(), (size_t)nDq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dTu[8], 0, n_samples * sizeof(int32_t), ctx->stream));     // quantiser kernels do not reach stay zero
+    if (nDq) CK(cudaMemcpyAsync(ctx->dTu[9], order.data(), (size_t)nDq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (nTs) CK(cudaMemcpyAsync(ctx->dTu[16], tsOrder.data(), (size_t)nTs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dTu[10], rates, (size_t)n_rates * sizeof(vvcb_dq_rates), cudaMemcpyHostToDevice, ctx->stream));
   }
   if (tm && !src) CK(cudaEventRecord(ctx->tev[0], ctx->stream));
@@ -652,11 +662,22 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     D.rates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]); D.tabs = static_cast<const DqRateTab*>(ctx->dTu[11]);
     D.rom = ctx->dDqRom; D.scratch = static_cast<uint8_t*>(ctx->dTu[12]); D.bd = ctx->bd;
     dq_kernel<<<dqGrid, kDqThreads, 0, ctx->stream>>>(D);
-    if (tm) CK(cudaEventRecord(ctx->tev[2], ctx->stream));
+    ctx->launches += 6;
+  }
+  if (nTs) {
+    RdoqParams R;
+    R.jobs = P.jobs; R.order = static_cast<const int*>(ctx->dTu[16]); R.n = nTs; R.coeff = P.dqCoeff; R.level = P.level;
+    R.deq = static_cast<int32_t*>(ctx->dTu[8]); R.results = P.results; R.rates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]);
+    R.rom = ctx->dDqRom; R.bd = ctx->bd;
+    rdoq_ts_kernel<<<(nTs + 127) / 128, 128, 0, ctx->stream>>>(R);
+    ctx->launches++;
+  }
+  if (tm) CK(cudaEventRecord(ctx->tev[2], ctx->stream));
+  if (nDq || nTs) {
     P.phase = 1;
     tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
-    ctx->launches += 7;
-  } else if (tm) CK(cudaEventRecord(ctx->tev[2], ctx->stream));
+    ctx->launches++;
+  }
   if (tm) CK(cudaEventRecord(ctx->tev[3], ctx->stream));
   CK(cudaGetLastError());
   if (coeff) CK(cudaMemcpyAsync(coeff, ctx->dTu[3], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -43,6 +43,7 @@ struct DqRom {
   uint8_t   nbIn[16][6];     // inside-sub-block neighbours of an in-sub-block position: {num, inPos[5]} (shape independent)
   int32_t   goRiceBits[4][32];
   uint8_t   goRicePars[32], goRiceZero[3][32], groupIdx[32];
+  uint8_t   tsRicePars[32];  // CoeffCodingContext::templateAbsSumTS (CL/ContextModelling.h:350-365)
   int32_t   quantScales[12], invQuantScales[12];
 };
 
@@ -579,6 +580,187 @@ __global__ void __launch_bounds__(kDqThreads, VVCB_DQ_MIN_CTAS) dq_kernel(DqPara
       P.results[P.order[ji]].abs_sum_level = absSum;
     }
     __syncwarp();
+  }
+}
+
+// =====================================================================================================
+// RDOQ of transform-skip blocks: QuantRDOQ::xRateDistOptQuantTS (CL/QuantRDOQ.cpp:1243-1485) with xGetCodedLevelTSPred
+// (:2000-2065), xGetICRateTS (:2067-2150), xGetErrScaleCoeff (:383-393) and the transform-skip contexts of
+// CoeffCodingContext (CL/ContextModelling.h:197-365).  The decision of a coefficient depends on the decided levels of its
+// left and upper neighbours and on the sub-block flags before it, so a block is one serial chain: one thread per block,
+// the host sorts the jobs by size so that the lanes of a warp run chains of equal length.  Costs are IEEE doubles combined
+// in the reference's order (no contraction).
+// =====================================================================================================
+struct RdoqParams {
+  const vvcb_tu_job* jobs;
+  const int* order;          // RDOQ job indices, largest block first
+  int n;
+  const int32_t* coeff;      // transform-skip coefficients (residual << transformShift), dense per job at job.offset
+  int32_t* level;            // out (zero-filled by the caller)
+  int32_t* deq;              // out: dequantised coefficients, Quant::dequant (CL/Quant.cpp:423-540)
+  vvcb_tu_result* results;
+  const vvcb_dq_rates* rates;
+  const DqRom* rom;
+  int bd;
+};
+
+__device__ __forceinline__ int rdoq_ic_rate_ts(int absLevel, const vvcb_dq_rates& r, const uint32_t* sign, const uint32_t* gt1, int sgn, int ricePar)
+{
+  int rate = (int)sign[sgn];
+  if (absLevel > 1) {
+    rate += (int)gt1[1];
+    rate += (int)r.ts_par[0][(absLevel - 2) & 1];
+    int cutoff = 2;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (absLevel >= cutoff) rate += (int)r.ts_gtx[cutoff >> 1][absLevel >= cutoff + 2];
+      cutoff += 2;
+    }
+    if (absLevel >= cutoff) {
+      unsigned symbol = (unsigned)(absLevel - cutoff) >> 1, length;
+      if (symbol < (5u << ricePar)) {
+        length = symbol >> ricePar;
+        rate += (int)((length + 1 + ricePar) << kDqScaleBits);
+      } else {
+        length = (unsigned)ricePar;
+        symbol -= 5u << ricePar;
+        while (symbol >= (1u << length)) symbol -= 1u << (length++);
+        rate += (int)((5 + length + 1 - ricePar + length) << kDqScaleBits);
+      }
+    }
+  } else if (absLevel == 1) rate += (int)gt1[0];
+  else rate = 0;
+  return rate;
+}
+
+__global__ void __launch_bounds__(128) rdoq_ts_kernel(RdoqParams P)
+{
+  const DqRom& rom = *P.rom;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < P.n; t += gridDim.x * blockDim.x) {
+    const int ji = P.order[t];
+    const vvcb_tu_job job = P.jobs[ji];
+    const vvcb_dq_rates& R = P.rates[job.rate_idx];
+    const int lw = job.log2w, lh = job.log2h, w = 1 << lw;
+    const DqShape shp = rom.shape[lw - 2][lh - 2];
+    const DqScanPos* scan = rom.pos + shp.first;
+    const uint16_t* sbbPosTab = rom.sbbPos[lw - 2][lh - 2];
+    const int32_t* coeff = P.coeff + job.offset;
+    int32_t* level = P.level + job.offset;
+    int32_t* deq = P.deq + job.offset;
+    const double lambda = job.lambda;
+    const int trShift = 15 - P.bd - ((lw + lh) >> 1);
+    const int qBits = 14 + job.qp_per + trShift;
+    const int quantCoeff = rom.quantScales[job.qp_rem];
+    // xGetErrScaleCoeff: 2^15 * 2^(-2 transformShift) / QStep / QStep
+    const double errorScale = __ddiv_rn(__ddiv_rn(ldexp(32768.0, -2 * trShift), (double)quantCoeff), (double)quantCoeff);
+    const int iScale = rom.invQuantScales[job.qp_rem];
+    const int rightShift = 6 - (trShift + job.qp_per);
+    const int tgt = vmin(16, 32 + rightShift - 7);
+    const int inMin = -(1 << (tgt - 1)), inMax = (1 << (tgt - 1)) - 1;
+    unsigned long long sigGroups = 0;                 // m_sigCoeffGroupFlag, by raster position of the sub-block
+    bool anySigCG = false;
+    int absSum = 0;
+    for (int sb = 0; sb < shp.numSbb; sb++) {
+      const int sbPos = sbbPosTab[sb];
+      const int sy = sbPos / shp.widthInSbb, sx = sbPos - sy * shp.widthInSbb;
+      const int sigLeft = sx > 0 ? (int)((sigGroups >> (sbPos - 1)) & 1) : 0;
+      const int sigAbove = sy > 0 ? (int)((sigGroups >> (sbPos - shp.widthInSbb)) & 1) : 0;
+      const uint32_t* bitsSigGroup = R.ts_sig_sbb[sigLeft + sigAbove];
+      int noCoeffCoded = 0;
+      bool sig = false;
+      double baseCost = 0.0, sigCostSum = 0.0, codedLevelAndDist = 0.0, uncodedDist = 0.0;
+      for (int i = 0; i < 16; i++) {
+        const DqScanPos sp = scan[sb * 16 + i];
+        const int blk = sp.idx;
+        const int c = coeff[blk];
+        const long long tmpLevel = (long long)vabs(c) * quantCoeff;
+        const long long cap = 0x7fffffffll - (1ll << (qBits - 1));
+        const int levelDouble = (int)(tmpLevel < cap ? tmpLevel : cap);
+        const int roundAbs = vmin(32767, (int)(((long long)levelDouble + (1ll << (qBits - 1))) >> qBits));
+        const int minAbs = roundAbs > 1 ? roundAbs - 1 : 1;
+        const int upAbs = vmin(32767, vmin(32767, levelDouble >> qBits) + 1);
+        const int right = sp.x > 0 ? level[blk - 1] : 0;       // neighTS: left ...
+        const int below = sp.y > 0 ? level[blk - w] : 0;       // ... and upper neighbour
+        const int pred1 = vmax(vabs(below), vabs(right));
+        int tested[3], nTested = 0;
+        tested[nTested++] = roundAbs;
+        if (minAbs != roundAbs) tested[nTested++] = minAbs;
+        const int predPixel = upAbs == pred1 ? 1 : (upAbs < pred1 ? upAbs + 1 : upAbs);
+        if (upAbs != roundAbs && upAbs != minAbs && predPixel == 1) tested[nTested++] = upAbs;
+        const double dErr = (double)levelDouble;
+        const double cost0 = __dmul_rn(__dmul_rn(dErr, dErr), errorScale);
+        const int numPos = (right != 0) + (below != 0);
+        const uint32_t* bitsSig = R.ts_sig[numPos];
+        const int ricePar = rom.tsRicePars[vmin(vabs(right) + vabs(below), 31)];
+        int signCtx;
+        if ((right == 0 && below == 0) || ((long long)right * below < 0)) signCtx = 0;
+        else if (right >= 0 && below >= 0) signCtx = 1;
+        else signCtx = 2;
+        const uint32_t* bitsSign = R.ts_sign[signCtx];
+        const uint32_t* bitsGt1 = R.ts_lrg1[numPos];
+        const int sgn = c < 0;
+        const bool isLast = i == 15 && noCoeffCoded == 0;
+        // xGetCodedLevelTSPred
+        double cost, csig = 0.0, currCostSig = 0.0;
+        int best = 0;
+        bool done = false;
+        if (!isLast && tested[0] < 3) {
+          csig = __dmul_rn(lambda, (double)bitsSig[0]);
+          cost = __dadd_rn(cost0, csig);
+          done = tested[0] == 0;
+        } else cost = 1.7976931348623157e308;
+        if (!done) {
+          if (!isLast) currCostSig = __dmul_rn(lambda, (double)bitsSig[1]);
+          for (int k = 0; k < nTested; k++) {
+            const int absLevel = tested[k];
+            const double e = (double)(levelDouble - (int)((unsigned)absLevel << qBits));
+            const double err = __dmul_rn(__dmul_rn(e, e), errorScale);
+            const int mod = absLevel == pred1 ? 1 : (absLevel < pred1 ? absLevel + 1 : absLevel);
+            double cur = __dadd_rn(err, __dmul_rn(lambda, (double)rdoq_ic_rate_ts(mod, R, bitsSign, bitsGt1, sgn, ricePar)));
+            cur = __dadd_rn(cur, currCostSig);
+            if (cur < cost) { best = absLevel; cost = cur; csig = currCostSig; }
+          }
+        }
+        if (best > 0) noCoeffCoded++;
+        const int lv = (best != 0 && c < 0) ? -best : best;
+        level[blk] = lv;
+        baseCost = __dadd_rn(baseCost, cost);
+        sigCostSum = __dadd_rn(sigCostSum, csig);
+        if (lv) {
+          sig = true;
+          codedLevelAndDist = __dadd_rn(codedLevelAndDist, __dsub_rn(cost, csig));
+          uncodedDist = __dadd_rn(uncodedDist, cost0);
+        }
+      }
+      if (sig && (sb != shp.numSbb - 1 || anySigCG)) {
+        double costZeroSB = baseCost;
+        baseCost = __dadd_rn(baseCost, __dmul_rn(lambda, (double)bitsSigGroup[1]));
+        costZeroSB = __dadd_rn(costZeroSB, __dmul_rn(lambda, (double)bitsSigGroup[0]));
+        costZeroSB = __dadd_rn(costZeroSB, uncodedDist);
+        costZeroSB = __dsub_rn(costZeroSB, codedLevelAndDist);
+        costZeroSB = __dsub_rn(costZeroSB, sigCostSum);
+        if (costZeroSB < baseCost) {
+          sig = false;
+          for (int i = 0; i < 16; i++) level[scan[sb * 16 + i].idx] = 0;
+        } else anySigCG = true;
+      }
+      if (sig) {
+        sigGroups |= 1ull << sbPos;
+        for (int i = 0; i < 16; i++) {
+          const int blk = scan[sb * 16 + i].idx;
+          const int lv = level[blk];
+          if (lv) {
+            absSum += vabs(lv);
+            const int qc = vmin(vmax(lv, inMin), inMax);
+            int d;
+            if (rightShift > 0) d = (qc * iScale + (1 << (rightShift - 1))) >> rightShift;
+            else                d = (int)((unsigned)(qc * iScale) << (-rightShift));
+            deq[blk] = vmin(vmax(d, -32768), 32767);
+          }
+        }
+      }
+    }
+    P.results[ji].abs_sum_level = absSum;
   }
 }
 

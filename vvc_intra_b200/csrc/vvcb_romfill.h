@@ -66,6 +66,8 @@ template <class T> inline void fill_dq_rom(T& r)
   static const uint8_t groupIdx[32] = { 0,1,2,3,4,4,5,5,6,6,6,6,7,7,7,7,8,8,8,8,8,8,8,8,9,9,9,9,9,9,9,9 };
   memcpy(r.goRiceBits, riceBits, sizeof(riceBits)); memcpy(r.goRicePars, ricePars, 32); memcpy(r.goRiceZero, riceZero, 96);
   memcpy(r.groupIdx, groupIdx, 32);
+  static const uint8_t tsRice[32] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2 };
+  memcpy(r.tsRicePars, tsRice, 32);
   for (int i = 0; i < 12; i++) { r.quantScales[i] = kQuantScales[i]; r.invQuantScales[i] = kInvQuantScales[i]; }
 
   // up-right diagonal order of a bw x bh grid

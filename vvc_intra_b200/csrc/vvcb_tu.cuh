@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
     const int16_t* mv = tr_kernel(rom, ver, lh);
     const int16_t* resi = P.resi + job.offset;
     const int hp = h + 1;
-    const bool dq = (job.flags & (VVCB_TU_QUANT | VVCB_TU_DEPQUANT)) == (VVCB_TU_QUANT | VVCB_TU_DEPQUANT);
+    // jobs whose quantiser is a kernel of its own (dependent quantisation, RDOQ for transform skip): vvcb_dq.cuh
+    const bool dq = (job.flags & VVCB_TU_QUANT) && (job.flags & (VVCB_TU_DEPQUANT | VVCB_TU_RDOQ_TS));
     if (P.phase == 1 && !dq) continue;
     __syncthreads();
     if (P.phase == 1) {
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
       if (dq) {                                                          // the quantiser is another kernel: finish in pass 1
         if (threadIdx.x == 0) {
           vvcb_tu_result r;
-          r.abs_sum_coeff = (int)sumAbs; r.abs_sum_level = 0; r.sse = 0;
+          r.abs_sum_coeff = (int)__dmul_rn((double)(int)sumAbs, ts && ((lw + lh) & 1) ? 1.0 / 1.414213562 : 1.0);   // CL/TrQuant.cpp:1098-1102
+          r.abs_sum_level = 0; r.sse = 0;
           P.results[ji] = r;
         }
         continue;

@@ -31,15 +31,17 @@ assert VISIT_DTYPE.itemsize == 80 and RESULT_DTYPE.itemsize == 368 and DETAIL_DT
     (VISIT_DTYPE.itemsize, RESULT_DTYPE.itemsize, DETAIL_DTYPE.itemsize)
 
 
-TU_QUANT, TU_DEPQUANT = 1, 2
+TU_QUANT, TU_DEPQUANT, TU_RDOQ_TS = 1, 2, 4
 TU_JOB_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('log2w', 'u1'), ('log2h', 'u1'), ('mts_idx', 'u1'), ('flags', 'u1'),
                          ('qp_per', '<i2'), ('qp_rem', '<i2'), ('offset', '<u4'), ('rate_idx', '<u2'), ('lfnst_idx', 'u1'), ('pad', 'u1'),
                          ('cbf_delta_bits', '<i4'), ('lambda', '<f8')], align=True)
 TU_RESULT_DTYPE = np.dtype([('abs_sum_coeff', '<i4'), ('abs_sum_level', '<i4'), ('sse', '<u8')], align=True)
 TU_SRC_DTYPE = np.dtype([('visit', '<u4'), ('slot', 'u1'), ('pad', 'u1', 3)])
 DQ_RATES_DTYPE = np.dtype([('sig_sbb', '<u4', (2, 2)), ('sig', '<u4', (3, 12, 2)), ('par', '<u4', (21, 2)), ('gt1', '<u4', (21, 2)),
-                           ('gt2', '<u4', (21, 2)), ('last_x', '<u4', (20, 2)), ('last_y', '<u4', (20, 2))])
-assert TU_SRC_DTYPE.itemsize == 8 and TU_JOB_DTYPE.itemsize == 32 and TU_RESULT_DTYPE.itemsize == 16 and DQ_RATES_DTYPE.itemsize == 1128
+                           ('gt2', '<u4', (21, 2)), ('last_x', '<u4', (20, 2)), ('last_y', '<u4', (20, 2)),
+                           ('ts_sig_sbb', '<u4', (3, 2)), ('ts_sig', '<u4', (3, 2)), ('ts_par', '<u4', (1, 2)), ('ts_gtx', '<u4', (5, 2)),
+                           ('ts_lrg1', '<u4', (4, 2)), ('ts_sign', '<u4', (6, 2))])
+assert TU_SRC_DTYPE.itemsize == 8 and TU_JOB_DTYPE.itemsize == 32 and TU_RESULT_DTYPE.itemsize == 16 and DQ_RATES_DTYPE.itemsize == 1304
 
 
 FEAT_CU_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('w', 'u1'), ('h', 'u1'), ('qt_depth', 'u1'), ('mt_depth', 'u1')])
