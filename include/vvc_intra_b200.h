@@ -192,10 +192,12 @@ typedef struct vvcb_tu_job {
   uint8_t  flags;           /* VVCB_TU_*                                                                            */
   int16_t  qp_per, qp_rem;  /* QpParam::per / rem of this candidate (CL/Quant.h:71); dependent quantisation adds its +1 itself */
   uint32_t offset;          /* first sample of this job's dense w*h block in resi/pred/coeff/level/reco            */
-  /* dependent quantisation only */
+  /* rate-distortion quantisers (dependent quantisation, transform-skip RDOQ) and LFNST */
   uint16_t rate_idx;        /* which vvcb_dq_rates snapshot prices this TU                                          */
-  uint8_t  lfnst_idx;       /* cu.lfnstIdx: only moves the first tested scan position (CL/DepQuant.cpp:1641-1646)    */
-  uint8_t  pad;
+  uint8_t  lfnst_idx;       /* cu.lfnstIdx 0..2: forward LFNST after the primary transform and inverse before it (TrQuant::xFwdLfnst /
+                               xInvLfnst, CL/TrQuant.cpp:316-560); the primary transform then keeps the top-left 4x4 / 8x8 only (:853-867)
+                               and the dependent quantiser starts at scan position 7 / 15 (CL/DepQuant.cpp:1641-1646)            */
+  uint8_t  intra_mode;      /* with lfnst_idx: PU::getFinalIntraMode of the block, PLANAR (0) for MIP (CL/TrQuant.cpp:330-347)        */
   int32_t  cbf_delta_bits;  /* cbfDeltaBits of RateEstimator::xSetLastCoeffOffset (CL/DepQuant.cpp:491-540)          */
   double   lambda;          /* Quant::m_dLambda                                                                     */
 } vvcb_tu_job;

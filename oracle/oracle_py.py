@@ -197,14 +197,14 @@ def rmd_batch(orig, reco, bd, ctu_size, visits, want_pred=False):
 _p32 = C.POINTER(C.c_int32)
 
 
-def fwd_transform(resi, bd, mts_idx):
+def fwd_transform(resi, bd, mts_idx, lfnst_idx=0):
     resi, pr = _a16(resi)
     h, w = resi.shape
     coeff = np.zeros((h, w), np.int32)
     if mts_idx == 1:
         lib().orc_transform_skip(pr, w, w, h, bd, coeff.ctypes.data_as(_p32))
     else:
-        lib().orc_fwd_transform(pr, w, w, h, bd, mts_idx, coeff.ctypes.data_as(_p32))
+        lib().orc_fwd_transform_ex(pr, w, w, h, bd, mts_idx, lfnst_idx, coeff.ctypes.data_as(_p32))
     return coeff
 
 
@@ -326,3 +326,17 @@ def rdoq_ts(coeff, bd, qp, lam, rates):
     r = np.ascontiguousarray(np.array([rates], DQ_RATES_DTYPE))
     s = lib().orc_rdoq_ts(coeff.ctypes.data_as(_p32), w, h, bd, qp, C.c_double(lam), C.c_void_p(r.ctypes.data), level.ctypes.data_as(_p32))
     return level, s
+
+
+def fwd_lfnst(coeff, intra_mode, lfnst_idx):
+    c = np.ascontiguousarray(coeff, np.int32).copy()
+    h, w = c.shape
+    lib().orc_fwd_lfnst(c.ctypes.data_as(_p32), w, h, intra_mode, lfnst_idx)
+    return c
+
+
+def inv_lfnst(coeff, intra_mode, lfnst_idx):
+    c = np.ascontiguousarray(coeff, np.int32).copy()
+    h, w = c.shape
+    lib().orc_inv_lfnst(c.ctypes.data_as(_p32), w, h, intra_mode, lfnst_idx)
+    return c

@@ -407,6 +407,37 @@ void __wrap__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamR
 {
   g_inRmd = false;
   __real__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamRiRK3Ctxb( tq, tu, c, qp, absSum, ctx, loadTr );
+  if( g_out && c == COMPONENT_Y && !tu.noResidual && !tu.cu->ispMode && tu.cu->lfnstIdx && tu.mtsIdx != MTS_SKIP && tu.cs->slice->getDepQuantEnabledFlag() )
+  {
+    // 'F' (forward primary transform + forward LFNST + dependent quantisation, CL/TrQuant.cpp:437-560, :1220): i32 w,h,bitDepth,mtsIdx,
+    // lfnstIdx,intraMode (PU::getFinalIntraMode, planar for MIP),qp,per,rem,absSum,cbfDeltaBits, f64 lambda, u32 rates[282] (as 'D'),
+    // resi[w*h] i16, coeff[w*h] i32 (after LFNST), level[w*h] i32
+    const CompArea& rect = tu.blocks[c];
+    if( keepTu( rect.width + 3000, rect.height ) )
+    {
+      const int n = rect.width * rect.height;
+      const PredictionUnit& pu = *tu.cs->getPU( rect.pos(), CHANNEL_TYPE_LUMA );
+      const int intraMode = PU::isMIP( pu, CHANNEL_TYPE_LUMA ) ? PLANAR_IDX : (int) PU::getFinalIntraMode( pu, CHANNEL_TYPE_LUMA );
+      const FracBitsAccess& fb = ctx.getFracBitsAcess();
+      Rec d;
+      d.i32( rect.width ); d.i32( rect.height ); d.i32( tu.cs->sps->getBitDepth( CHANNEL_TYPE_LUMA ) ); d.i32( tu.mtsIdx ); d.i32( tu.cu->lfnstIdx ); d.i32( intraMode );
+      d.i32( qp.Qp( false ) ); d.i32( qp.per( false ) ); d.i32( qp.rem( false ) ); d.i32( absSum );
+      const BinFracBits cbf = fb.getFracBitsArray( Ctx::QtCbf[COMPONENT_Y]( DeriveCtx::CtxQtCbf( COMPONENT_Y, tu.cbf[COMPONENT_Cb] ) ) );
+      d.i32( int32_t( cbf.intBits[1] ) - int32_t( cbf.intBits[0] ) );
+      d.f64( tq->m_quant->getLambda() );
+      auto put = [&]( const CtxSet& set, int num ) { for( int i = 0; i < num; i++ ) { const BinFracBits b = fb.getFracBitsArray( set( i ) ); d.u32( b.intBits[0] ); d.u32( b.intBits[1] ); } };
+      put( Ctx::SigCoeffGroup[CHANNEL_TYPE_LUMA], 2 );
+      for( int st = 0; st < 3; st++ ) put( Ctx::SigFlag[CHANNEL_TYPE_LUMA + 2 * st], 12 );
+      put( Ctx::ParFlag[CHANNEL_TYPE_LUMA], 21 ); put( Ctx::GtxFlag[2 + CHANNEL_TYPE_LUMA], 21 ); put( Ctx::GtxFlag[CHANNEL_TYPE_LUMA], 21 );
+      put( Ctx::LastX[CHANNEL_TYPE_LUMA], 20 ); put( Ctx::LastY[CHANNEL_TYPE_LUMA], 20 );
+      putBlock( d, tu.cs->getResiBuf( rect ) );
+      const TCoeff* co = loadTr ? tq->m_mtsCoeffs[tu.mtsIdx] : tq->m_tempCoeff;
+      for( int i = 0; i < n; i++ ) d.i32( co[i] );
+      const CCoeffBuf lv = tu.getCoeffs( c );
+      for( int y = 0; y < (int) rect.height; y++ ) for( int x = 0; x < (int) rect.width; x++ ) d.i32( lv.at( x, y ) );
+      d.emit( 'F' );
+    }
+  }
   if( !g_out || c != COMPONENT_Y || tu.noResidual || tu.cu->ispMode || tu.cu->lfnstIdx ) return;
   const CompArea& rect = tu.blocks[c];
   if( !keepTu( rect.width + 1000, rect.height ) ) return;
@@ -471,6 +502,24 @@ void __wrap__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamR
 void __wrap__ZN7TrQuant15invTransformNxNER13TransformUnitRK11ComponentIDR7AreaBufIsERK7QpParam( TrQuant* tq, TransformUnit& tu, const ComponentID& c, PelBuf& resi, const QpParam& qp )
 {
   __real__ZN7TrQuant15invTransformNxNER13TransformUnitRK11ComponentIDR7AreaBufIsERK7QpParam( tq, tu, c, resi, qp );
+  if( g_out && c == COMPONENT_Y && !tu.cu->ispMode && tu.cu->lfnstIdx && !tu.cu->bdpcmMode && tu.mtsIdx != MTS_SKIP && tu.cs->slice->getDepQuantEnabledFlag() )
+  {
+    // 'J' (dependent dequantisation + inverse LFNST + inverse primary, CL/TrQuant.cpp:316-435, :561): i32 w,h,bitDepth,mtsIdx,lfnstIdx,
+    // intraMode,qp, level[w*h] i32, resi[w*h] i16
+    const CompArea& rect = tu.blocks[c];
+    if( keepTu( rect.width + 4000, rect.height ) )
+    {
+      const PredictionUnit& pu = *tu.cs->getPU( rect.pos(), CHANNEL_TYPE_LUMA );
+      const int intraMode = PU::isMIP( pu, CHANNEL_TYPE_LUMA ) ? PLANAR_IDX : (int) PU::getFinalIntraMode( pu, CHANNEL_TYPE_LUMA );
+      Rec r;
+      r.i32( rect.width ); r.i32( rect.height ); r.i32( tu.cs->sps->getBitDepth( CHANNEL_TYPE_LUMA ) ); r.i32( tu.mtsIdx ); r.i32( tu.cu->lfnstIdx ); r.i32( intraMode );
+      r.i32( qp.Qp( false ) );
+      const CCoeffBuf lv = tu.getCoeffs( c );
+      for( int y = 0; y < (int) rect.height; y++ ) for( int x = 0; x < (int) rect.width; x++ ) r.i32( lv.at( x, y ) );
+      putBlock( r, resi );
+      r.emit( 'J' );
+    }
+  }
   if( !g_out || c != COMPONENT_Y || tu.cu->ispMode || tu.cu->lfnstIdx || tu.cu->bdpcmMode ) return;
   const CompArea& rect = tu.blocks[c];
   if( !keepTu( rect.width + 2000, rect.height ) ) return;

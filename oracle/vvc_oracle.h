@@ -55,6 +55,7 @@ uint64_t orc_fnv1a(const int16_t* p, int n);
 /* ---- TU coding (vvc_oracle_tr.c) ---- */
 void orc_tr_types(int mts_idx, int* hor, int* ver);
 void orc_fwd_transform(const int16_t* resi, int stride, int w, int h, int bd, int mts_idx, int32_t* coeff);
+void orc_fwd_transform_ex(const int16_t* resi, int stride, int w, int h, int bd, int mts_idx, int lfnst_idx, int32_t* coeff);
 void orc_transform_skip(const int16_t* resi, int stride, int w, int h, int bd, int32_t* coeff);
 int  orc_abs_sum_for_preselection(const int32_t* coeff, int w, int h, int mts_idx);
 void orc_mts_preselect(const int* sums, int n, int w, int h, int max_cand, uint8_t* selected);
@@ -63,6 +64,10 @@ void orc_dequant(const int32_t* level, int w, int h, int bd, int per, int rem, i
 void orc_inv_transform(const int32_t* coeff, int w, int h, int bd, int mts_idx, int16_t* resi, int stride);
 void orc_inv_transform_skip(const int32_t* coeff, int w, int h, int bd, int16_t* resi, int stride);
 uint64_t orc_reconstruct_sse(const int16_t* org, int org_stride, const int16_t* pred, const int16_t* resi, int w, int h, int bd, int16_t* reco);
+
+/* LFNST (vvc_oracle_tr.c), in place on a dense w*h coefficient block; intra_mode = PU::getFinalIntraMode (planar for MIP) */
+void orc_fwd_lfnst(int32_t* coeff, int w, int h, int intra_mode, int lfnst_idx);
+void orc_inv_lfnst(int32_t* coeff, int w, int h, int intra_mode, int lfnst_idx);
 
 /* ---- dependent quantisation (vvc_oracle_dq.c); qp = QpParam::Qp of the block ---- */
 int  orc_dep_quant(const int32_t* coeff, int w, int h, int bd, int mts_idx, int lfnst_idx, int qp, double lambda,

@@ -45,8 +45,14 @@ static void skips(int w, int h, int hor, int ver, int* skipW, int* skipH)
   *skipH = (ver != 0 && h == 32) ? 16 : (h > 32 ? h - 32 : 0);
 }
 
-/* a12  TrQuant::xT (CL/TrQuant.cpp:835-915): rows first, then columns, high frequencies zeroed */
 void orc_fwd_transform(const int16_t* resi, int stride, int w, int h, int bd, int mts_idx, int32_t* coeff)
+{
+  orc_fwd_transform_ex(resi, stride, w, h, bd, mts_idx, 0, coeff);
+}
+
+/* a12  TrQuant::xT (CL/TrQuant.cpp:835-915): rows first, then columns, high frequencies zeroed; with LFNST only the
+ * top-left 4x4 / 8x8 of primary coefficients is produced (JVET_O0094, :853-867) */
+void orc_fwd_transform_ex(const int16_t* resi, int stride, int w, int h, int bd, int mts_idx, int lfnst_idx, int32_t* coeff)
 {
   int hor, ver, skipW, skipH, j, k, n, l;
   int32_t* tmp = (int32_t*)malloc(sizeof(int32_t) * w * h);
@@ -55,6 +61,10 @@ void orc_fwd_transform(const int16_t* resi, int stride, int w, int h, int bd, in
   const int16_t *mh, *mv;
   orc_tr_types(mts_idx, &hor, &ver);
   skips(w, h, hor, ver, &skipW, &skipH);
+  if (lfnst_idx) {
+    if ((w == 4 && h > 4) || (w > 4 && h == 4)) { skipW = w - 4; skipH = h - 4; }
+    else if (w >= 8 && h >= 8) { skipW = w - 8; skipH = h - 8; }
+  }
   mh = kernel_of(hor, w); mv = kernel_of(ver, h);
   memset(coeff, 0, sizeof(int32_t) * w * h);
   for (j = 0; j < h; j++)
@@ -200,4 +210,88 @@ uint64_t orc_reconstruct_sse(const int16_t* org, int org_stride, const int16_t* 
       sse += (uint64_t)(d * d);
     }
   return sse;
+}
+
+/* ---- LFNST: TrQuant::xFwdLfnst / xInvLfnst, fwdLfnstNxN / invLfnstNxN (CL/TrQuant.cpp:239-560) ---- */
+
+/* PU::getWideAngIntraMode (CL/UnitTools.cpp:963-989) then TrQuant::getLFNSTIntraMode (CL/TrQuant.cpp:288-306): 0..94 */
+static int lfnst_intra_mode(int w, int h, int dirMode)
+{
+  static const int modeShift[] = { 0, 6, 10, 12, 14, 15 };
+  int predMode = dirMode;
+  if (dirMode >= 2) {
+    const int delta = abs(ilog2(w) - ilog2(h));
+    if (w > h && dirMode < 2 + modeShift[delta]) predMode += 66 - 1;
+    else if (h > w && predMode > 66 - modeShift[delta]) predMode -= 66 + 1;
+  }
+  if (predMode < 0) return predMode + (28 >> 1) + 67;          /* NUM_EXT_LUMA_MODE 28, NUM_LUMA_MODE 67 */
+  if (predMode >= 67) return predMode + (28 >> 1);
+  return predMode;
+}
+
+static int lfnst_transpose(int m) { return (m >= 67 && m >= 67 + (28 >> 1)) || (m < 67 && m > 34); }   /* getTransposeFlag :308-312 */
+
+/* scan of the LFNST region: the top-left 8x8 in 4x4 groups (g_coefTopLeftDiagScan8x8, CL/Rom.cpp:369-392) when w,h >= 8,
+ * else the block's own grouped scan, whose first 16 entries are the diagonal scan of the top-left 4x4 */
+static void lfnst_scan(int w, int whge3, int* idx)
+{
+  int gx[4], gy[4], ix[16], iy[16], n = 0, d, y, g, i;
+  for (d = 0; d <= 6; d++) for (y = d < 3 ? d : 3; y >= 0 && d - y <= 3; y--) { ix[n] = d - y; iy[n] = y; n++; }
+  gx[0] = 0; gy[0] = 0; gx[1] = 0; gy[1] = 1; gx[2] = 1; gy[2] = 0; gx[3] = 1; gy[3] = 1;      /* diagonal order of a 2x2 grid */
+  for (g = 0; g < (whge3 ? 4 : 1); g++)
+    for (i = 0; i < 16; i++) idx[g * 16 + i] = (gy[g] * 4 + iy[i]) * w + gx[g] * 4 + ix[i];
+}
+
+void orc_fwd_lfnst(int32_t* coeff, int w, int h, int intra_mode, int lfnst_idx)
+{
+  const int whge3 = w >= 8 && h >= 8, sb = whge3 ? 8 : 4, trSize = whge3 ? 48 : 16;
+  const int zeroOut = ((w == 4 && h == 4) || (w == 8 && h == 8)) ? 8 : 16;
+  const int m = lfnst_intra_mode(w, h, intra_mode), tr = lfnst_transpose(m), set = kLfnstLut[m];
+  const int8_t* mat = whge3 ? kLfnst8x8 + (set * 2 + lfnst_idx - 1) * 16 * 48 : kLfnst4x4 + (set * 2 + lfnst_idx - 1) * 16 * 16;
+  int in[48], out[48], scan[64], x, y, j, i, n = 0;
+  if (!lfnst_idx) return;
+  if (tr) {                                     /* column-major gathering, the bottom-right 4x4 of an 8x8 is left out */
+    if (sb == 4) { for (y = 0; y < 4; y++) for (x = 0; x < 4; x++) in[y + 4 * x] = coeff[y * w + x]; }
+    else for (y = 0; y < 8; y++) {
+      for (x = 0; x < 4; x++) in[y + 8 * x] = coeff[y * w + x];
+      if (y < 4) for (x = 4; x < 8; x++) in[32 + y + 4 * (x - 4)] = coeff[y * w + x];
+    }
+  } else {
+    for (y = 0; y < sb; y++) { const int len = y < 4 ? sb : 4; for (x = 0; x < len; x++) in[n++] = coeff[y * w + x]; }
+  }
+  for (j = 0; j < trSize; j++) out[j] = 0;
+  for (j = 0; j < zeroOut; j++) {
+    int acc = 0;
+    for (i = 0; i < trSize; i++) acc += in[i] * mat[j * trSize + i];
+    out[j] = (acc + 64) >> 7;
+  }
+  lfnst_scan(w, whge3, scan);
+  for (j = 0; j < (sb == 4 ? 16 : 48); j++) coeff[scan[j]] = out[j];
+}
+
+void orc_inv_lfnst(int32_t* coeff, int w, int h, int intra_mode, int lfnst_idx)
+{
+  const int whge3 = w >= 8 && h >= 8, sb = whge3 ? 8 : 4, trSize = whge3 ? 48 : 16;
+  const int zeroOut = ((w == 4 && h == 4) || (w == 8 && h == 8)) ? 8 : 16;
+  const int m = lfnst_intra_mode(w, h, intra_mode), tr = lfnst_transpose(m), set = kLfnstLut[m];
+  const int8_t* mat = whge3 ? kLfnst8x8 + (set * 2 + lfnst_idx - 1) * 16 * 48 : kLfnst4x4 + (set * 2 + lfnst_idx - 1) * 16 * 16;
+  int in[16], out[48], scan[64], x, y, j, i, n = 0;
+  if (!lfnst_idx) return;
+  lfnst_scan(w, whge3, scan);
+  for (i = 0; i < 16; i++) in[i] = coeff[scan[i]];
+  for (j = 0; j < trSize; j++) {
+    int acc = 0, v;
+    for (i = 0; i < zeroOut; i++) acc += in[i] * mat[i * trSize + j];
+    v = (acc + 64) >> 7;
+    out[j] = v < -32768 ? -32768 : (v > 32767 ? 32767 : v);
+  }
+  if (tr) {
+    if (sb == 4) { for (y = 0; y < 4; y++) for (x = 0; x < 4; x++) coeff[y * w + x] = out[y + 4 * x]; }
+    else for (y = 0; y < 8; y++) {
+      for (x = 0; x < 4; x++) coeff[y * w + x] = out[y + 8 * x];
+      if (y < 4) for (x = 4; x < 8; x++) coeff[y * w + x] = out[32 + y + 4 * (x - 4)];
+    }
+  } else {
+    for (y = 0; y < sb; y++) { const int len = y < 4 ? sb : 4; for (x = 0; x < len; x++) coeff[y * w + x] = out[n++]; }
+  }
 }

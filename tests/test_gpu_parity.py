@@ -384,3 +384,31 @@ def test_rdoq_ts_random_blocks_match_oracle(bd, seed, eng8, eng10):
     bad['mts_idx'] = 0                                       # RDOQ_TS is for transform skip only
     with pytest.raises(vb.EngineError, match='malformed'):
         eng.tu_eval(bad, resi, pred, rates=rates)
+
+
+# ---- LFNST (cu.lfnstIdx 1 / 2) ---------------------------------------------------------------------------------
+@pytest.mark.parametrize('name,bd', [('ref_10b_128x128_qp27_lfnst', 10), ('ref_8b_128x64_qp32_lfnst', 8)])
+def test_lfnst_golden_parity(name, bd, eng8, eng10):
+    """TrQuant::xFwdLfnst / xInvLfnst around the dependent quantiser as the reference ran them: coefficients of the LFNST region,
+    levels, absSum from the 'F' records; reconstruction + SSE versus the oracle chain (inverse half pinned by the 'J' records)."""
+    eng = eng8 if bd == 8 else eng10
+    _, tus = G.load_fixture(name)
+    orig, jobs, resi, pred, rates, items = G.build_dq_batch(tus, bd, tag='F')
+    eng.frame_begin(orig)
+    out = eng.tu_eval(jobs, resi, pred, want_coeff=True, want_level=True, want_reco=True, rates=rates)
+    errs = G.check_dq_outputs(items, bd, out)
+    assert not errs, (len(errs), errs[:6])
+    # the scalar quantiser with LFNST: same coefficients, levels of Quant::quant on them (oracle)
+    sc = jobs.copy()
+    sc['flags'] = vb.TU_QUANT
+    out2 = eng.tu_eval(sc, resi, pred, want_coeff=True, want_level=True, want_reco=True)
+    assert np.array_equal(out2['coeff'], out['coeff'])
+    for i, it in enumerate(items[:40]):
+        r = it['rec']
+        h, w = r['resi'].shape
+        sl = slice(it['off'], it['off'] + w * h)
+        lvl, s = O.quant_scalar(out['coeff'][sl].reshape(h, w), bd, r['per'], r['rem'], False)
+        assert np.array_equal(out2['level'][sl].reshape(h, w), lvl)
+        res = O.inv_transform(O.inv_lfnst(O.dequant(lvl, bd, r['per'], r['rem'], False), r['intra_mode'], r['lfnst']), bd, r['mts'])
+        reco, sse = O.reconstruct_sse(it['org'], it['pred'], res, bd)
+        assert np.array_equal(out2['reco'][sl].reshape(h, w), reco) and int(out2['results'][i]['sse']) == int(sse)

@@ -213,3 +213,17 @@ def test_emulated_rdoq_ts_kernel_matches_oracle_on_random_blocks(emul, bd, seed)
         assert not bad, (k, len(bad), [(items[i]['resi'].shape, items[i]['qp']) for i in bad[:5]])
     assert out['results'].tobytes() == exp['results'].tobytes()
     assert (exp['results']['abs_sum_level'] > 0).sum() > len(items) // 3
+
+
+# ---- LFNST inside the TU kernel -------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name,bd', [('ref_10b_128x128_qp27_lfnst', 10), ('ref_8b_128x64_qp32_lfnst', 8)])
+def test_emulated_lfnst_matches_reference(emul, name, bd):
+    """Primary transform restricted to the LFNST region, forward LFNST, dependent quantisation from scan position 7 / 15,
+    dequantisation, inverse LFNST, inverse primary, reconstruction: against the reference's 'F' records and the oracle chain
+    (whose inverse half is pinned by the 'J' records)."""
+    _, tus = G.load_fixture(name)
+    orig, jobs, resi, pred, rates, items = G.build_dq_batch(tus, bd, tag='F')
+    assert len(items) > 50
+    out = run_emul_tu(emul, orig, bd, jobs, resi, pred, rates)
+    errs = G.check_dq_outputs(items, bd, out)
+    assert not errs, (len(errs), errs[:6])

@@ -137,6 +137,21 @@ def parse_record(tag, payload):
         r['resi'] = c.i16(n).reshape(r['h'], r['w'])
         r['coeff'] = c.i32(n).reshape(r['h'], r['w'])
         r['level'] = c.i32(n).reshape(r['h'], r['w'])
+    elif tag == 'F':
+        for k in ('w', 'h', 'bd', 'mts', 'lfnst', 'intra_mode', 'qp', 'per', 'rem', 'abs_sum', 'cbf_delta'):
+            r[k] = c.i32()
+        r['lambda'] = c.f64()
+        r['rates'] = c.u32(2 * (2 + 36 + 63 + 40))
+        n = r['w'] * r['h']
+        r['resi'] = c.i16(n).reshape(r['h'], r['w'])
+        r['coeff'] = c.i32(n).reshape(r['h'], r['w'])
+        r['level'] = c.i32(n).reshape(r['h'], r['w'])
+    elif tag == 'J':
+        for k in ('w', 'h', 'bd', 'mts', 'lfnst', 'intra_mode', 'qp'):
+            r[k] = c.i32()
+        n = r['w'] * r['h']
+        r['level'] = c.i32(n).reshape(r['h'], r['w'])
+        r['resi'] = c.i16(n).reshape(r['h'], r['w'])
     elif tag == 'T':
         for k in ('w', 'h', 'bd', 'qp', 'per', 'rem', 'abs_sum'):
             r[k] = c.i32()

@@ -45,6 +45,9 @@ template <class T> inline void fill_tr_rom(T& r)
   memcpy(r.dct8, kDct8_4, 32); memcpy(r.dct8 + 16, kDct8_8, 128); memcpy(r.dct8 + 80, kDct8_16, 512); memcpy(r.dct8 + 336, kDct8_32, 2048);
   memcpy(r.dst7, kDst7_4, 32); memcpy(r.dst7 + 16, kDst7_8, 128); memcpy(r.dst7 + 80, kDst7_16, 512); memcpy(r.dst7 + 336, kDst7_32, 2048);
   for (int i = 0; i < 12; i++) { r.quantScales[i] = kQuantScales[i]; r.invQuantScales[i] = kInvQuantScales[i]; }
+  memcpy(r.lfnst8, kLfnst8x8, sizeof(kLfnst8x8)); memcpy(r.lfnst4, kLfnst4x4, sizeof(kLfnst4x4)); memcpy(r.lfnstLut, kLfnstLut, 95);
+  int n = 0;                                           // up-right diagonal order of a 4x4 group
+  for (int d = 0; d <= 6; d++) for (int y = d < 3 ? d : 3; y >= 0 && d - y <= 3; y--) r.diag4[n++] = (uint8_t)((d - y) | (y << 2));
 }
 
 // Tables of the dependent-quantisation kernel (vvcb_dq.cuh's DqRom; T has that layout): the grouped 4x4 up-right diagonal

@@ -16,7 +16,102 @@ struct TrRom {                     // forward kernels M[k][n], int16, by type (0
   int16_t dct8[16 + 64 + 256 + 1024];
   int16_t dst7[16 + 64 + 256 + 1024];
   int32_t quantScales[12], invQuantScales[12];
+  // low-frequency non-separable transform (CL/RomLFNST.cpp): kernels [4 sets][2][16 out][48 | 16 in], extended mode -> set,
+  // and the diagonal order of a 4x4 group as x | y << 2
+  int8_t  lfnst8[4 * 2 * 16 * 48], lfnst4[4 * 2 * 16 * 16];
+  uint8_t lfnstLut[96], diag4[16];
 };
+
+// LFNST geometry of one job (TrQuant::xFwdLfnst / xInvLfnst, CL/TrQuant.cpp:316-560)
+struct LfnstGeom {
+  bool on, transpose;
+  int sb, trSize, zeroOut;        // region side (4 or 8), inputs of the kernel (16 or 48), outputs kept (8 or 16)
+  const int8_t* mat;              // [16][trSize]
+};
+
+__device__ __forceinline__ LfnstGeom make_lfnst(const TrRom& rom, int w, int h, int lw, int lh, bool ts, int lfnstIdx, int dirMode)
+{
+  LfnstGeom g;
+  g.on = lfnstIdx > 0 && !ts;
+  const bool whge3 = w >= 8 && h >= 8;
+  g.sb = whge3 ? 8 : 4; g.trSize = whge3 ? 48 : 16;
+  g.zeroOut = ((w == 4 && h == 4) || (w == 8 && h == 8)) ? 8 : 16;
+  // PU::getWideAngIntraMode (CL/UnitTools.cpp:963-989) and TrQuant::getLFNSTIntraMode / getTransposeFlag (CL/TrQuant.cpp:288-312)
+  int predMode = dirMode;
+  if (dirMode >= 2) {
+    const int delta = vabs(lw - lh);
+    const int shift = delta == 0 ? 0 : delta == 1 ? 6 : delta == 2 ? 10 : delta == 3 ? 12 : delta == 4 ? 14 : 15;
+    if (w > h && dirMode < 2 + shift) predMode += 65;
+    else if (h > w && predMode > 66 - shift) predMode -= 67;
+  }
+  const int m = predMode < 0 ? predMode + 14 + 67 : (predMode >= 67 ? predMode + 14 : predMode);
+  g.transpose = (m >= 67 + 14) || (m < 67 && m > 34);
+  const int set = rom.lfnstLut[m];
+  const int idx = vmax(lfnstIdx, 1) - 1;
+  g.mat = whge3 ? rom.lfnst8 + (set * 2 + idx) * 16 * 48 : rom.lfnst4 + (set * 2 + idx) * 16 * 16;
+  return g;
+}
+
+// position of region sample (x, y) in the LFNST input / output vector: row-major over the region without the bottom-right 4x4
+// of an 8x8, column-major when transposed
+__device__ __forceinline__ int lfnst_vec_index(const LfnstGeom& g, int x, int y)
+{
+  const int a = g.transpose ? y : x, b = g.transpose ? x : y;      // a runs fastest
+  return g.sb == 4 ? b * 4 + a : (b < 4 ? b * 8 + a : 32 + (b - 4) * 4 + a);
+}
+
+// raster position (stride w) of the j-th entry of the LFNST scan: 4x4 groups (0,0), (0,1), (1,0) in diagonal order
+__device__ __forceinline__ int lfnst_scan_pos(const TrRom& rom, int j, int w)
+{
+  const int g = j >> 4, d = rom.diag4[j & 15];
+  const int x = (g == 2 ? 4 : 0) + (d & 3), y = (g == 1 ? 4 : 0) + (d >> 2);
+  return y * w + x;
+}
+
+// forward LFNST in place on the block A (stride w); tmp: 96 ints of scratch.  All threads of the CTA call it.
+__device__ __forceinline__ void lfnst_forward(const TrRom& rom, const LfnstGeom& g, int* A, int w, int* tmp)
+{
+  int* in = tmp; int* out = tmp + 48;
+  __syncthreads();
+  for (int t = threadIdx.x; t < g.sb * g.sb; t += blockDim.x) {
+    const int x = t % g.sb, y = t / g.sb;
+    if (x < 4 || y < 4) in[lfnst_vec_index(g, x, y)] = A[y * w + x];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < g.trSize; j += blockDim.x) {
+    int v = 0;
+    if (j < g.zeroOut) {
+      int acc = 0;
+      for (int i = 0; i < g.trSize; i++) acc += in[i] * (int)g.mat[j * g.trSize + i];
+      v = (acc + 64) >> 7;
+    }
+    out[j] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < (g.sb == 4 ? 16 : 48); j += blockDim.x) A[lfnst_scan_pos(rom, j, w)] = out[j];
+  __syncthreads();
+}
+
+// inverse LFNST in place (CL/TrQuant.cpp:262-286, 316-435)
+__device__ __forceinline__ void lfnst_inverse(const TrRom& rom, const LfnstGeom& g, int* A, int w, int* tmp)
+{
+  int* in = tmp; int* out = tmp + 48;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16; i += blockDim.x) in[i] = A[lfnst_scan_pos(rom, i, w)];
+  __syncthreads();
+  for (int j = threadIdx.x; j < g.trSize; j += blockDim.x) {
+    int acc = 0;
+    for (int i = 0; i < g.zeroOut; i++) acc += in[i] * (int)g.mat[i * g.trSize + j];
+    out[j] = vmin(vmax((acc + 64) >> 7, -32768), 32767);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < g.sb * g.sb; t += blockDim.x) {
+    const int x = t % g.sb, y = t / g.sb;
+    if (x < 4 || y < 4) A[y * w + x] = out[lfnst_vec_index(g, x, y)];
+  }
+  __syncthreads();
+}
+
 
 __device__ __forceinline__ const int16_t* tr_kernel(const TrRom& rom, int type, int lg)
 {
@@ -75,8 +170,13 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
     const bool ts = job.mts_idx == 1;
     const int hor = job.mts_idx > 1 ? (((job.mts_idx - 2) & 1) ? 1 : 2) : 0;
     const int ver = job.mts_idx > 1 ? (((job.mts_idx - 2) >> 1) ? 1 : 2) : 0;
-    const int wKeep = w - ((hor != 0 && w == 32) ? 16 : (w > 32 ? w - 32 : 0));
-    const int hKeep = h - ((ver != 0 && h == 32) ? 16 : (h > 32 ? h - 32 : 0));
+    int wKeep = w - ((hor != 0 && w == 32) ? 16 : (w > 32 ? w - 32 : 0));
+    int hKeep = h - ((ver != 0 && h == 32) ? 16 : (h > 32 ? h - 32 : 0));
+    const LfnstGeom lf = make_lfnst(rom, w, h, lw, lh, ts, job.lfnst_idx, job.intra_mode);
+    if (lf.on) {                                                   // only the LFNST region of primary coefficients exists (:853-867)
+      if ((w == 4 && h > 4) || (w > 4 && h == 4)) { wKeep = 4; hKeep = 4; }
+      else if (w >= 8 && h >= 8) { wKeep = 8; hKeep = 8; }
+    }
     const int trShift = 15 - P.bd - ((lw + lh) >> 1);
     const int16_t* mh = tr_kernel(rom, hor, lw);
     const int16_t* mv = tr_kernel(rom, ver, lh);
@@ -117,6 +217,7 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
         A[o] = v;
       }
       __syncthreads();
+      if (lf.on) lfnst_forward(rom, lf, A, w, B);
     }
     }
     long long sumAbs = 0;
@@ -171,6 +272,7 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
       long long spart = 0;
       if (!ts) {
         const int shift2 = 20 - P.bd;
+        if (lf.on) lfnst_inverse(rom, lf, A, w, B);
         for (int o = threadIdx.x; o < wKeep * h; o += kTuThreads) {        // columns first: B[j][y]
           const int j = o % wKeep, y = o / wKeep;
           int acc = 0;

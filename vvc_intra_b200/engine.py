@@ -33,7 +33,7 @@ assert VISIT_DTYPE.itemsize == 80 and RESULT_DTYPE.itemsize == 368 and DETAIL_DT
 
 TU_QUANT, TU_DEPQUANT, TU_RDOQ_TS = 1, 2, 4
 TU_JOB_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('log2w', 'u1'), ('log2h', 'u1'), ('mts_idx', 'u1'), ('flags', 'u1'),
-                         ('qp_per', '<i2'), ('qp_rem', '<i2'), ('offset', '<u4'), ('rate_idx', '<u2'), ('lfnst_idx', 'u1'), ('pad', 'u1'),
+                         ('qp_per', '<i2'), ('qp_rem', '<i2'), ('offset', '<u4'), ('rate_idx', '<u2'), ('lfnst_idx', 'u1'), ('intra_mode', 'u1'),
                          ('cbf_delta_bits', '<i4'), ('lambda', '<f8')], align=True)
 TU_RESULT_DTYPE = np.dtype([('abs_sum_coeff', '<i4'), ('abs_sum_level', '<i4'), ('sse', '<u8')], align=True)
 TU_SRC_DTYPE = np.dtype([('visit', '<u4'), ('slot', 'u1'), ('pad', 'u1', 3)])
