@@ -412,3 +412,78 @@ def test_lfnst_golden_parity(name, bd, eng8, eng10):
         res = O.inv_transform(O.inv_lfnst(O.dequant(lvl, bd, r['per'], r['rem'], False), r['intra_mode'], r['lfnst']), bd, r['mts'])
         reco, sse = O.reconstruct_sse(it['org'], it['pred'], res, bd)
         assert np.array_equal(out2['reco'][sl].reshape(h, w), reco) and int(out2['results'][i]['sse']) == int(sse)
+
+
+# ---- full-size runs of the later stages ---------------------------------------------------------------------
+def test_full_1080p_tu_stage_properties(eng10):
+    """BASELINE config 2 size for the second stage: the best RMD candidate of every candidate CU of a 1920x1080 10-bit picture
+    (679 260 TUs) through vvcb_tu_eval_pred.  Checked by (i) a seeded sample against the oracle chain, (ii) determinism,
+    (iii) size-independent properties: SSE equals the host-side sum of squared differences of the returned reconstruction,
+    a zero level block reconstructs the prediction, abs sums equal the sums of the returned levels."""
+    from make_golden import synth_yuv
+    Y = synth_yuv(1920, 1080, 10)[0].astype(np.int16)
+    vis = vb.build_sweep_visits(1920, 1080, qp=32)
+    eng10.frame_begin(Y)
+    eng10.reco_update(Y)
+    res = eng10.rmd_eval(vis)
+    src, jobs, n_samples, rates = vb.build_tu_jobs_from_lists(vis, res, 32, 10)
+    assert len(jobs) == 679260
+    out = eng10.tu_eval_pred(vis, src, jobs, n_samples, want_level=True, want_reco=True, want_pred=True, rates=rates)
+    out2 = eng10.tu_eval_pred(vis, src, jobs, n_samples, want_level=True, rates=rates)
+    assert np.array_equal(out['level'], out2['level']) and out['results'].tobytes() == out2['results'].tobytes()
+    r = out['results']
+    rng = np.random.default_rng(17)
+    idx = np.sort(rng.choice(len(jobs), 400, replace=False))
+    _, _, preds = O.rmd_batch(Y, Y, 10, 128, vis[idx], want_pred=True)
+    for k, i in enumerate(idx):
+        j = jobs[i]
+        w, h = 1 << int(j['log2w']), 1 << int(j['log2h'])
+        sl = slice(int(j['offset']), int(j['offset']) + w * h)
+        p = preds[k][int(src[i]['slot'])]
+        assert np.array_equal(out['pred'][sl].reshape(h, w), p)
+        org = Y[int(j['y']):int(j['y']) + h, int(j['x']):int(j['x']) + w]
+        qp = 6 * int(j['qp_per']) + int(j['qp_rem'])
+        co = O.fwd_transform((org.astype(np.int32) - p).astype(np.int16), 10, 0)
+        lvl, s = O.dep_quant(co, 10, 0, 0, qp, float(j['lambda']), rates[0], 0)
+        assert np.array_equal(out['level'][sl].reshape(h, w), lvl) and int(r[i]['abs_sum_level']) == s
+        reco, sse = O.reconstruct_sse(org, p, O.inv_transform(O.dep_dequant(lvl, 10, qp), 10, 0), 10)
+        assert np.array_equal(out['reco'][sl].reshape(h, w), reco) and int(r[i]['sse']) == int(sse)
+    # properties over every TU, vectorised per shape
+    abs_levels = np.abs(out['level'])
+    sizes = (1 << jobs['log2w'].astype(np.int64)) * (1 << jobs['log2h'].astype(np.int64))
+    ends = np.cumsum(sizes)
+    csum = np.concatenate([[0], np.cumsum(abs_levels, dtype=np.int64)])
+    assert np.array_equal(csum[ends] - csum[ends - sizes], r['abs_sum_level'].astype(np.int64))
+    for lw in range(2, 7):
+        for lh in range(2, 7):
+            sel = np.nonzero((jobs['log2w'] == lw) & (jobs['log2h'] == lh))[0][:4000]
+            if not len(sel):
+                continue
+            w, h = 1 << lw, 1 << lh
+            pos = jobs['offset'][sel].astype(np.int64)[:, None] + np.arange(w * h)[None, :]
+            yy = jobs['y'][sel].astype(np.int64)[:, None, None] + np.arange(h)[None, :, None]
+            xx = jobs['x'][sel].astype(np.int64)[:, None, None] + np.arange(w)[None, None, :]
+            org = Y[yy, xx].reshape(len(sel), -1).astype(np.int64)
+            rec = out['reco'][pos].astype(np.int64)
+            assert np.array_equal(((org - rec) ** 2).sum(axis=1), r['sse'][sel].astype(np.int64))
+            zero = r['abs_sum_level'][sel] == 0
+            assert np.array_equal(rec[zero], out['pred'][pos][zero].astype(np.int64))
+
+
+def test_2160p_sweep_properties(eng10):
+    """BASELINE config 3 picture size (3840x2160 10-bit, 2 720 940 visits in one call): sampled visits against the oracle,
+    the chunked host pipeline against itself, and the list invariants."""
+    from make_golden import synth_yuv
+    Y = synth_yuv(3840, 2160, 10)[0].astype(np.int16)
+    vis = vb.build_sweep_visits(3840, 2160, qp=27)
+    assert len(vis) == 2720940          # 30 x 17 CTUs; the bottom CTU row is 112 luma rows high, candidates below the picture are dropped
+    eng10.frame_begin(Y)
+    eng10.reco_update(Y)
+    res = eng10.rmd_eval(vis)
+    assert res['n_rd'].min() >= 2 and res['n_final'].max() <= vb.engine.MAX_LIST and (res['n_final'] >= res['n_rd']).all()
+    rng = np.random.default_rng(23)
+    idx = np.sort(rng.choice(len(vis), 1500, replace=False))
+    ora, _ = O.rmd_batch(Y, Y, 10, 128, vis[idx])
+    assert res[idx].tobytes() == ora.tobytes()
+    res2 = eng10.rmd_eval(vis[:300000])
+    assert res2.tobytes() == res[:300000].tobytes()
