@@ -120,6 +120,10 @@ int  vvcb_create (vvcb_ctx** out, int device, int bit_depth, int ctu_size);
 void vvcb_destroy(vvcb_ctx* ctx);
 const char* vvcb_last_error(const vvcb_ctx* ctx);   /* ctx may be NULL: error of the last failed create */
 int  vvcb_device_count(void);
+/* Slice-level tool switches the kernels need to know.  VVCB_OPT_DEP_QUANT: slice->getDepQuantEnabledFlag() (default 1, the shipped
+ * configuration): residual_coding then picks its significance context set with the quantiser state machine (EL/CABACWriter.cpp:3866). */
+#define VVCB_OPT_DEP_QUANT 1
+int  vvcb_set_option(vvcb_ctx* ctx, int option, int value);
 
 /* ---- picture planes -------------------------------------------------------------------------
  * frame_begin uploads the (LMCS-mapped) original luma, which is constant during the CTU loop
@@ -161,6 +165,11 @@ int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t*
 #define VVCB_TU_DEPQUANT  2u   /* with VVCB_TU_QUANT: dependent (trellis-coded) quantisation, DQIntern::DepQuant::quant
                                   (CL/DepQuant.cpp:1592-1731) and its state-machine dequantiser (:741-810), instead of the
                                   scalar Quant::quant.  Not for transform skip (the reference sends those to RDOQ, :1757).    */
+#define VVCB_TU_TS_ALLOWED   8u   /* TU::isTSAllowed  (CL/UnitTools.cpp:4524) -- only read by VVCB_TU_RATE (mts_coding)              */
+#define VVCB_TU_MTS_ALLOWED 16u   /* TU::isMTSAllowed (CL/UnitTools.cpp:4549)                                                       */
+#define VVCB_TU_RATE        32u   /* with VVCB_TU_QUANT: results[i].frac_bits = fractional bits of CABACWriter::residual_coding( tu, Y ) for
+                                     the quantised levels (0 when all levels are zero: the reference does not call it then), priced and
+                                     adapted on states[rate_idx]                                                                    */
 #define VVCB_TU_RDOQ_TS   4u   /* with VVCB_TU_QUANT, transform skip only: QuantRDOQ::xRateDistOptQuantTS (CL/QuantRDOQ.cpp:1243),
                                   what the shipped configuration (RDOQTS 1) runs for transform-skip candidates; uses lambda and
                                   rate_idx like dependent quantisation.                                                      */
@@ -185,6 +194,17 @@ typedef struct vvcb_dq_rates {
   uint32_t ts_sign[6][2];      /* Ctx::TsResidualSign                                                                         */
 } vvcb_dq_rates;
 
+/* Probability states of the CABAC estimator's contexts that CABACWriter::residual_coding touches for a luma TU (EL/CABACWriter.cpp:3773):
+ * BinProbModel_Std::m_state[0..1] and m_rate (CL/Contexts.h:90-163) at the moment the reference would start coding the TU.  With
+ * VVCB_TU_RATE the engine codes the TU's levels on a private copy of these models exactly as the bit estimator does (every context-coded
+ * bin is priced, then adapts its model) and returns the fractional bits.                                                            */
+typedef struct vvcb_bin_model { uint16_t state[2]; uint8_t rate; uint8_t pad; } vvcb_bin_model;
+typedef struct vvcb_ctx_states {
+  vvcb_bin_model mts_idx[11];                                   /* Ctx::MTSIndex                                            */
+  vvcb_bin_model sig_sbb[2], sig[3][12], par[21], gt1[21], gt2[21], last_x[20], last_y[20];   /* as vvcb_dq_rates            */
+  vvcb_bin_model ts_sig_sbb[3], ts_sig[3], ts_par[1], ts_gtx[5], ts_lrg1[4], ts_sign[6];
+} vvcb_ctx_states;
+
 typedef struct vvcb_tu_job {
   int16_t  x, y;            /* luma position of the TU (the original block is read from the frame for the SSE)      */
   uint8_t  log2w, log2h;    /* 2..6; 64-point sides keep their 32 low frequencies (CL/TrQuant.cpp:853)             */
@@ -206,12 +226,15 @@ typedef struct vvcb_tu_result {
   int32_t  abs_sum_coeff;   /* int(sum |coeff| * scaleSAD), the MTS pre-selection cost (CL/TrQuant.cpp:1090-1103)   */
   int32_t  abs_sum_level;   /* uiAbsSum of the quantiser (0 when VVCB_TU_QUANT is clear)                            */
   uint64_t sse;             /* sum (org - reco)^2 (0 when VVCB_TU_QUANT is clear)                                    */
+  uint64_t frac_bits;       /* VVCB_TU_RATE: bits of residual_coding in 1/32768 bit (what getEstFracBits() grows by)  */
 } vvcb_tu_result;
 
 /* resi / pred: HOST int16 arrays of n_samples (residual = org - pred as the reference's cs.getResiBuf holds it);
  * coeff / level (int32) and reco (int16): optional HOST outputs of n_samples; results: n entries.                  */
+/* rates / states: n_rates entries each (either may be NULL when no job needs it), indexed by job.rate_idx.                      */
 int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred, size_t n_samples,
-                 const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results);
+                 const vvcb_dq_rates* rates, const vvcb_ctx_states* states, int n_rates,
+                 int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results);
 /* The whole of IntraSearch::xIntraCodingTUBlock (EL/IntraSearch.cpp:2694-3168) for TUs that cover their CU: the engine also
  * runs initIntraPatternChType + predIntraAng / predIntraMip (:2820-2870) from the reconstruction plane and forms
  * resi = org - pred (:2922) itself.  src[i] names the visit (position, size, availability: the same struct the rough mode
@@ -223,8 +246,13 @@ typedef struct vvcb_tu_src {
   uint8_t  pad[3];
 } vvcb_tu_src;
 int vvcb_tu_eval_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n_visits, const vvcb_tu_src* src, const vvcb_tu_job* jobs, int n,
-                      size_t n_samples, const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco,
-                      int16_t* pred_out, vvcb_tu_result* results);
+                      size_t n_samples, const vvcb_dq_rates* rates, const vvcb_ctx_states* states, int n_rates,
+                      int32_t* coeff, int32_t* level, int16_t* reco, int16_t* pred_out, vvcb_tu_result* results);
+/* The residual part of IntraSearch::xGetIntraFracBitsQT (EL/IntraSearch.cpp:2566: xEncCoeffQT -> CABACWriter::residual_coding on the bit
+ * estimator) for levels the caller already has.  levels: HOST int32, dense w*h per job at job.offset; of a job only log2w, log2h, mts_idx,
+ * the VVCB_TU_TS_ALLOWED / VVCB_TU_MTS_ALLOWED flags, offset and rate_idx are read; bits[i]: fractional bits, 0 for an all-zero block.      */
+int vvcb_residual_bits(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int32_t* levels, size_t n_samples,
+                       const vvcb_ctx_states* states, int n_states, uint64_t* bits);
 /* TrQuant::transformNxN(trModes) candidate selection (CL/TrQuant.cpp:1112-1123) from the pre-selection sums of one
  * TU's candidates in list order (DCT2 first, transform skip second if tested): pure host logic.                    */
 void vvcb_mts_preselect(const int32_t* sums, int n, int width, int height, int max_cand, uint8_t* selected);

@@ -340,3 +340,28 @@ def inv_lfnst(coeff, intra_mode, lfnst_idx):
     h, w = c.shape
     lib().orc_inv_lfnst(c.ctypes.data_as(_p32), w, h, intra_mode, lfnst_idx)
     return c
+
+
+# ---- residual rate estimation (oracle/vvc_oracle_rate.c) ---------------------------------------------------------
+BIN_MODEL_DTYPE = np.dtype([('state', '<u2', 2), ('rate', 'u1'), ('pad', 'u1')])
+CTX_STATES_DTYPE = np.dtype([('mts_idx', BIN_MODEL_DTYPE, 11), ('sig_sbb', BIN_MODEL_DTYPE, 2), ('sig', BIN_MODEL_DTYPE, (3, 12)), ('par', BIN_MODEL_DTYPE, 21),
+                             ('gt1', BIN_MODEL_DTYPE, 21), ('gt2', BIN_MODEL_DTYPE, 21), ('last_x', BIN_MODEL_DTYPE, 20), ('last_y', BIN_MODEL_DTYPE, 20),
+                             ('ts_sig_sbb', BIN_MODEL_DTYPE, 3), ('ts_sig', BIN_MODEL_DTYPE, 3), ('ts_par', BIN_MODEL_DTYPE, 1), ('ts_gtx', BIN_MODEL_DTYPE, 5),
+                             ('ts_lrg1', BIN_MODEL_DTYPE, 4), ('ts_sign', BIN_MODEL_DTYPE, 6)])
+assert CTX_STATES_DTYPE.itemsize == 174 * 6
+
+
+def ctx_states_from_record(states):
+    """The 'C' record's (174, 3) array of (state0, state1, rate) -> one vvcb_ctx_states struct."""
+    flat = np.zeros(174, BIN_MODEL_DTYPE)
+    flat['state'] = states[:, :2]
+    flat['rate'] = states[:, 2]
+    return np.frombuffer(flat.tobytes(), CTX_STATES_DTYPE)[0]
+
+
+def residual_bits(level, mts_idx, ts_allowed, mts_allowed, dep_quant, states):
+    level = np.ascontiguousarray(level, np.int32)
+    h, w = level.shape
+    st = np.ascontiguousarray(np.array([states], CTX_STATES_DTYPE))
+    lib().orc_residual_bits.restype = C.c_uint64
+    return int(lib().orc_residual_bits(level.ctypes.data_as(_p32), w, h, mts_idx, int(ts_allowed), int(mts_allowed), int(dep_quant), C.c_void_p(st.ctypes.data)))

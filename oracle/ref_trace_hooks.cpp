@@ -184,6 +184,7 @@ void __real__ZN11CABACWriter20intra_luma_pred_modeERK14PredictionUnit( CABACWrit
 void __real__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamPSt6vectorISt4pairIibESaISA_EEi( TrQuant*, TransformUnit&, const ComponentID&, const QpParam&, std::vector<TrMode>*, int );
 void __real__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamRiRK3Ctxb( TrQuant*, TransformUnit&, const ComponentID&, const QpParam&, TCoeff&, const Ctx&, bool );
 void __real__ZN7TrQuant15invTransformNxNER13TransformUnitRK11ComponentIDR7AreaBufIsERK7QpParam( TrQuant*, TransformUnit&, const ComponentID&, PelBuf&, const QpParam& );
+void __real__ZN11CABACWriter15residual_codingERK13TransformUnit11ComponentIDP5CUCtx( CABACWriter*, const TransformUnit&, ComponentID, CUCtx* );
 
 // ---- visit ---------------------------------------------------------------------------------------------
 // 'V': u32 visitId, i32 poc,x,y,w,h,lfnstIdx,mtsFlag,bitDepth,qp, f64 sqrtLambda, i32 mpm[6], i32 numCandMpm,
@@ -545,6 +546,47 @@ int __wrap__ZN5EncCu19updateCtuDataISliceE7AreaBufIKsE( EncCu* cu, const CPelBuf
   for( int y = 0; y < (int) buf.height; y++ ) for( int x = 0; x < (int) buf.width; x++ ) r.i16( buf.at( x, y ) );
   r.emit( 'H' );
   return res;
+}
+
+// 'C' (CABACWriter::residual_coding on the bit estimator, EL/CABACWriter.cpp:3773; called from IntraSearch::xEncCoeffQT):
+// i32 w,h,mtsIdx,tsAllowed,mtsAllowed,depQuant, u64 fracBits of the call, then the estimator's context states BEFORE the call as
+// {u16 state0, u16 state1, u16 rate} for MTSIndex[11], SigCoeffGroup[2], SigFlag[0|2|4][12], ParFlag[21], GtxFlag[2][21] (gt1),
+// GtxFlag[0][21] (gt2), LastX[20], LastY[20], TsSigCoeffGroup[3], TsSigFlag[3], TsParFlag[1], TsGtxFlag[5], TsLrg1Flag[4],
+// TsResidualSign[6]; level[w*h] i32
+void __wrap__ZN11CABACWriter15residual_codingERK13TransformUnit11ComponentIDP5CUCtx( CABACWriter* cw, const TransformUnit& tu, ComponentID c, CUCtx* cuCtx )
+{
+  init();
+  const bool rec = g_out && c == COMPONENT_Y && !cw->m_BinEncoder.isEncoding() && !tu.cu->ispMode && !tu.cu->bdpcmMode;
+  Rec r;
+  uint64_t before = 0;
+  if( rec )
+  {
+    const CompArea& rect = tu.blocks[c];
+    r.i32( rect.width ); r.i32( rect.height ); r.i32( tu.mtsIdx ); r.i32( TU::isTSAllowed( tu, c ) ); r.i32( TU::isMTSAllowed( tu, c ) );
+    r.i32( tu.cs->slice->getDepQuantEnabledFlag() );
+    before = cw->m_BinEncoder.getEstFracBits();
+  }
+  std::vector<uint16_t> st;
+  if( rec )
+  {
+    const Ctx& ctx = cw->getCtx();
+    auto put = [&]( const CtxSet& set, int num ) { for( int i = 0; i < num; i++ ) { const BinProbModel_Std& m = ctx.m_CtxStore_Std[ set( i ) ]; st.push_back( m.m_state[0] ); st.push_back( m.m_state[1] ); st.push_back( m.m_rate ); } };
+    put( Ctx::MTSIndex, 11 );
+    put( Ctx::SigCoeffGroup[CHANNEL_TYPE_LUMA], 2 );
+    for( int k = 0; k < 3; k++ ) put( Ctx::SigFlag[CHANNEL_TYPE_LUMA + 2 * k], 12 );
+    put( Ctx::ParFlag[CHANNEL_TYPE_LUMA], 21 ); put( Ctx::GtxFlag[2 + CHANNEL_TYPE_LUMA], 21 ); put( Ctx::GtxFlag[CHANNEL_TYPE_LUMA], 21 );
+    put( Ctx::LastX[CHANNEL_TYPE_LUMA], 20 ); put( Ctx::LastY[CHANNEL_TYPE_LUMA], 20 );
+    put( Ctx::TsSigCoeffGroup, 3 ); put( Ctx::TsSigFlag, 3 ); put( Ctx::TsParFlag, 1 ); put( Ctx::TsGtxFlag, 5 ); put( Ctx::TsLrg1Flag, 4 ); put( Ctx::TsResidualSign, 6 );
+  }
+  __real__ZN11CABACWriter15residual_codingERK13TransformUnit11ComponentIDP5CUCtx( cw, tu, c, cuCtx );
+  if( !rec ) return;
+  const CompArea& rect = tu.blocks[c];
+  if( !keepTu( rect.width + 5000 + ( tu.mtsIdx == MTS_SKIP ? 1000 : 0 ), rect.height ) ) return;
+  r.u64( cw->m_BinEncoder.getEstFracBits() - before );
+  for( uint16_t v : st ) r.put<uint16_t>( v );
+  const CCoeffBuf lv = tu.getCoeffs( c );
+  for( int y = 0; y < (int) rect.height; y++ ) for( int x = 0; x < (int) rect.width; x++ ) r.i32( lv.at( x, y ) );
+  r.emit( 'C' );
 }
 
 } // extern "C"

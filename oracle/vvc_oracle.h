@@ -77,6 +77,10 @@ void orc_dep_dequant(const int32_t* level, int w, int h, int bd, int qp, int32_t
 /* ---- RDOQ of transform-skip blocks (vvc_oracle_rdoq.c); qp = QpParam::Qp(true) ---- */
 int  orc_rdoq_ts(const int32_t* coeff, int w, int h, int bd, int qp, double lambda, const vvcb_dq_rates* rates, int32_t* level);
 
+/* ---- residual rate estimation (vvc_oracle_rate.c): fractional bits of CABACWriter::residual_coding( tu, COMPONENT_Y ) ---- */
+uint64_t orc_residual_bits(const int32_t* level, int w, int h, int mts_idx, int ts_allowed, int mts_allowed, int dep_quant,
+                           const vvcb_ctx_states* states);
+
 /* ---- texture measures (vvc_oracle_feat.c) ---- */
 void orc_ctu_hads_islice(const int16_t* orig, int stride, int pic_w, int pic_h, int ctu, int32_t* out);
 void orc_features(const int16_t* orig, int stride, const vvcb_feat_job* job, vvcb_feat_result* out);

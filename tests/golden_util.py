@@ -270,7 +270,7 @@ def oracle_tu_chain(items, bd):
         res = O.inv_transform(O.dequant(lvl, bd, it['per'], it['rem'], it['mts'] == 1), bd, it['mts'])
         reco, sse = O.reconstruct_sse(it['org'], it['pred'], res, bd)
         out['coeff'][sl], out['level'][sl], out['reco'][sl] = co.ravel(), lvl.ravel(), reco.ravel()
-        out['results'][i] = (O.abs_sum_for_preselection(co, it['mts']), s, sse)
+        out['results'][i] = (O.abs_sum_for_preselection(co, it['mts']), s, sse, it.get('bits_fn', lambda lv: 0)(lvl))
     return out
 
 
@@ -402,7 +402,7 @@ def oracle_dq_chain(items, bd):
         res = O.inv_transform(deq, bd, it['mts'])
         reco, sse = O.reconstruct_sse(it['org'], it['pred'], res, bd)
         out['coeff'][sl], out['level'][sl], out['reco'][sl] = co.ravel(), lvl.ravel(), reco.ravel()
-        out['results'][i] = (O.abs_sum_for_preselection(co, it['mts']), s, sse)
+        out['results'][i] = (O.abs_sum_for_preselection(co, it['mts']), s, sse, it.get('bits_fn', lambda lv: 0)(lvl))
     return out
 
 
@@ -548,5 +548,26 @@ def oracle_rdoq_chain(items, bd):
         res = O.inv_transform(O.dequant(lvl, bd, it['qp'] // 6, it['qp'] % 6, True), bd, 1)
         reco, sse = O.reconstruct_sse(it['org'], it['pred'], res, bd)
         out['coeff'][sl], out['level'][sl], out['reco'][sl] = co.ravel(), lvl.ravel(), reco.ravel()
-        out['results'][i] = (O.abs_sum_for_preselection(co, 1), s, sse)
+        out['results'][i] = (O.abs_sum_for_preselection(co, 1), s, sse, it.get('bits_fn', lambda lv: 0)(lvl))
     return out
+
+
+# ---- residual rate estimation: batches from the reference's 'C' records ------------------------------------
+def build_rate_batch(tus):
+    """One pricing job per 'C' record: levels, TU geometry, mtsIdx and the two mts_coding switches; every record brings its own
+    context-state snapshot.  Returns (jobs, levels_flat, states, records)."""
+    import vvc_intra_b200 as vb
+    recs = [r for r in tus if r['tag'] == 'C']
+    jobs = np.zeros(len(recs), vb.TU_JOB_DTYPE)
+    states = np.zeros(len(recs), vb.CTX_STATES_DTYPE)
+    off = 0
+    for i, r in enumerate(recs):
+        j = jobs[i]
+        j['log2w'], j['log2h'], j['mts_idx'] = r['w'].bit_length() - 1, r['h'].bit_length() - 1, r['mts']
+        j['flags'] = vb.TU_QUANT | vb.TU_RATE | (vb.TU_TS_ALLOWED if r['ts_allowed'] else 0) | (vb.TU_MTS_ALLOWED if r['mts_allowed'] else 0)
+        j['offset'], j['rate_idx'] = off, i
+        st = np.zeros(174, vb.BIN_MODEL_DTYPE)
+        st['state'], st['rate'] = r['states'][:, :2], r['states'][:, 2]
+        states[i] = np.frombuffer(st.tobytes(), vb.CTX_STATES_DTYPE)[0]
+        off += r['w'] * r['h']
+    return jobs, np.concatenate([r['level'].ravel() for r in recs]).astype(np.int32), states, recs

@@ -7,6 +7,7 @@
 #include "../../vvc_intra_b200/csrc/vvcb_tu.cuh"
 #include "../../vvc_intra_b200/csrc/vvcb_feat.cuh"
 #include "../../vvc_intra_b200/csrc/vvcb_dq.cuh"
+#include "../../vvc_intra_b200/csrc/vvcb_rate.cuh"
 #include <vector>
 #include "../../vvc_intra_b200/csrc/vvcb_romfill.h"
 
@@ -81,7 +82,7 @@ extern "C" int emul_rmd_eval(const int16_t* orig, const int16_t* reco, int strid
 
 // the three launches of vvcb_tu_eval (vvcb_api.cu): transform pass, dependent quantisation, reconstruction pass
 extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred,
-                            size_t nSamples, const vvcb_dq_rates* rates, int nRates,
+                            size_t nSamples, const vvcb_dq_rates* rates, const vvcb_ctx_states* states, int nRates,
                             int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results)
 {
   static TrRom rom;
@@ -128,6 +129,16 @@ extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_
     P.phase = 1;
     emu_launch(2, kTuThreads, [&] { tu_eval_kernel(P); });
   }
+  std::vector<int> rateOrder;
+  for (int i = 0; i < n; i++) if ((jobs[i].flags & (VVCB_TU_QUANT | VVCB_TU_RATE)) == (VVCB_TU_QUANT | VVCB_TU_RATE)) rateOrder.push_back(i);
+  if (!rateOrder.empty()) {
+    static RateRom rr;
+    for (int i = 0; i < 512; i++) rr.binFracBits[i] = kBinFracBits[i];
+    RateParams R;
+    R.jobs = jobs; R.order = rateOrder.data(); R.n = (int)rateOrder.size(); R.level = level; R.results = results; R.states = states;
+    R.rom = &dqRom; R.rate = &rr; R.depQuant = 1;
+    emu_launch(2, kRateThreads, [&] { rate_kernel(R); });
+  }
   return 0;
 }
 
@@ -157,5 +168,20 @@ extern "C" int emul_tu_pred(const int16_t* orig, const int16_t* reco, int stride
   Q.visits = visits; Q.src = src; Q.jobs = jobs; Q.n = n; Q.pred = pred; Q.resi = resi; Q.orig = orig; Q.reco = reco; Q.stride = stride;
   Q.bd = bd; Q.ctu = ctu; Q.rom = &rom;
   emu_launch(2, kTuPredWarps * 32, [&] { tu_pred_kernel(Q); });
+  return 0;
+}
+
+// rate_kernel on given levels (vvcb_residual_bits)
+extern "C" int emul_residual_bits(const vvcb_tu_job* jobs, int n, const int32_t* levels, const vvcb_ctx_states* states, int depQuant, vvcb_tu_result* results)
+{
+  static DqRom dqRom;
+  static RateRom rr;
+  fill_dq_rom(dqRom);
+  for (int i = 0; i < 512; i++) rr.binFracBits[i] = kBinFracBits[i];
+  std::vector<int> order(n);
+  for (int i = 0; i < n; i++) order[i] = i;
+  RateParams R;
+  R.jobs = jobs; R.order = order.data(); R.n = n; R.level = levels; R.results = results; R.states = states; R.rom = &dqRom; R.rate = &rr; R.depQuant = depQuant;
+  emu_launch(2, kRateThreads, [&] { rate_kernel(R); });
   return 0;
 }

@@ -487,3 +487,50 @@ def test_2160p_sweep_properties(eng10):
     assert res[idx].tobytes() == ora.tobytes()
     res2 = eng10.rmd_eval(vis[:300000])
     assert res2.tobytes() == res[:300000].tobytes()
+
+
+# ---- residual rate estimation (vvcb_residual_bits, VVCB_TU_RATE) --------------------------------------------
+@pytest.mark.parametrize('name', ['ref_10b_128x128_qp27_resbits', 'ref_8b_128x64_qp22_resbits'])
+def test_residual_bits_golden_parity(name, eng10):
+    """CABACWriter::residual_coding on the reference's bit estimator: recorded levels and context states in, the fractional bits the
+    call added out (regular, MTS and transform-skip residual coding)."""
+    _, tus = G.load_fixture(name)
+    jobs, levels, states, recs = G.build_rate_batch(tus)
+    got = eng10.residual_bits(jobs, levels, states)
+    bad = [(r['w'], r['h'], r['mts'], int(g), r['bits']) for g, r in zip(got, recs) if int(g) != r['bits']]
+    assert not bad, (len(bad), bad[:5])
+    assert eng10.residual_bits(jobs, np.zeros_like(levels), states).max() == 0        # nothing to code
+    eng10.set_option(vb.OPT_DEP_QUANT, 0)                                             # without the quantiser state machine: set 0 always
+    try:
+        alt = eng10.residual_bits(jobs, levels, states)
+        exp = [O.residual_bits(r['level'], r['mts'], r['ts_allowed'], r['mts_allowed'], 0, O.ctx_states_from_record(r['states'])) for r in recs]
+        assert alt.tolist() == exp and alt.tolist() != got.tolist()
+    finally:
+        eng10.set_option(vb.OPT_DEP_QUANT, 1)
+
+
+@pytest.mark.parametrize('bd,seed', [(8, 121), (10, 122)])
+def test_tu_stage_returns_residual_bits(bd, seed, eng8, eng10):
+    """VVCB_TU_RATE inside the TU pipeline: the bits of the levels the quantisers just produced (dependent quantisation with and without
+    LFNST / MTS, transform-skip RDOQ), against the oracle pricing the oracle's levels."""
+    eng = eng8 if bd == 8 else eng10
+    rng = np.random.default_rng(seed)
+    orig, jobs, resi, pred, rates, items = G.random_dq_case(rng, bd, 2)
+    states = np.zeros(len(rates), vb.CTX_STATES_DTYPE)
+    flat = states.view(vb.BIN_MODEL_DTYPE).reshape(len(rates), -1)
+    flat['state'][..., 0] = rng.integers(1, 1023, flat.shape) << 5                  # MASK_0 domain
+    flat['state'][..., 1] = rng.integers(1, 16383, flat.shape) << 1                 # MASK_1 domain
+    flat['rate'] = (rng.integers(4, 8, flat.shape) << 4) | rng.integers(4, 10, flat.shape)
+    jobs = jobs.copy()
+    jobs['flags'] |= vb.TU_RATE | vb.TU_TS_ALLOWED
+    jobs['flags'][(jobs['log2w'] <= 5) & (jobs['log2h'] <= 5)] |= vb.TU_MTS_ALLOWED
+    for it, j in zip(items, jobs):
+        it['bits_fn'] = (lambda lv, j=j: O.residual_bits(lv, int(j['mts_idx']), True, bool(j['flags'] & vb.TU_MTS_ALLOWED), 1, states[int(j['rate_idx'])]))
+    eng.frame_begin(orig)
+    out = eng.tu_eval(jobs, resi, pred, want_level=True, rates=rates, states=states)
+    exp = G.oracle_dq_chain(items, bd)
+    assert np.array_equal(out['level'], exp['level'])
+    assert out['results'].tobytes() == exp['results'].tobytes()
+    assert (out['results']['frac_bits'] > 0).sum() > len(items) // 3
+    # the stand-alone entry point on the same levels
+    assert eng.residual_bits(jobs, out['level'], states).tolist() == out['results']['frac_bits'].tolist()

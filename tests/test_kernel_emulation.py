@@ -77,20 +77,22 @@ def test_emulated_kernels_match_oracle_on_random_visits(emul, bd, seed):
 
 
 # ---- TU coding kernel (vvcb_tu.cuh) ------------------------------------------------------------------------
-def run_emul_tu(lib, orig, bd, jobs, resi, pred, rates=None):
+def run_emul_tu(lib, orig, bd, jobs, resi, pred, rates=None, states=None):
     import vvc_intra_b200 as vb
     orig = np.ascontiguousarray(orig, np.int16)
     jobs = np.ascontiguousarray(jobs, vb.TU_JOB_DTYPE)
     resi = np.ascontiguousarray(resi, np.int16)
     pred = np.ascontiguousarray(pred, np.int16)
-    lib.emul_tu_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+    lib.emul_tu_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    nr = 0 if rates is None else len(rates)
+    nr = len(rates) if rates is not None else (len(states) if states is not None else 0)
     rates = None if rates is None else np.ascontiguousarray(rates, vb.DQ_RATES_DTYPE)
+    states = None if states is None else np.ascontiguousarray(states, vb.CTX_STATES_DTYPE)
     out = dict(results=np.zeros(len(jobs), vb.TU_RESULT_DTYPE), coeff=np.zeros(resi.size, np.int32), level=np.zeros(resi.size, np.int32),
                reco=np.zeros(resi.size, np.int16))
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.emul_tu_eval(p(orig), orig.shape[1], bd, p(jobs), len(jobs), p(resi), p(pred), resi.size, p(rates) if nr else None, nr,
+    rc = lib.emul_tu_eval(p(orig), orig.shape[1], bd, p(jobs), len(jobs), p(resi), p(pred), resi.size, p(rates) if rates is not None else None,
+                          p(states) if states is not None else None, nr,
                           p(out['coeff']), p(out['level']), p(out['reco']), p(out['results']))
     assert rc == 0
     return out
@@ -227,3 +229,25 @@ def test_emulated_lfnst_matches_reference(emul, name, bd):
     out = run_emul_tu(emul, orig, bd, jobs, resi, pred, rates)
     errs = G.check_dq_outputs(items, bd, out)
     assert not errs, (len(errs), errs[:6])
+
+
+# ---- residual rate estimation (rate_kernel) ----------------------------------------------------------------------------
+def run_emul_rate(lib, jobs, levels, states):
+    import vvc_intra_b200 as vb
+    jobs = np.ascontiguousarray(jobs, vb.TU_JOB_DTYPE)
+    levels = np.ascontiguousarray(levels, np.int32)
+    states = np.ascontiguousarray(states, vb.CTX_STATES_DTYPE)
+    res = np.zeros(len(jobs), vb.TU_RESULT_DTYPE)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.emul_residual_bits(p(jobs), len(jobs), p(levels), p(states), 1, p(res))
+    return res['frac_bits']
+
+
+@pytest.mark.parametrize('name', ['ref_10b_128x128_qp27_resbits', 'ref_8b_128x64_qp22_resbits'])
+def test_emulated_rate_kernel_matches_reference(emul, name):
+    _, tus = G.load_fixture(name)
+    jobs, levels, states, recs = G.build_rate_batch(tus)
+    assert len(recs) > 150
+    got = run_emul_rate(emul, jobs, levels, states)
+    bad = [(r['w'], r['h'], r['mts'], int(g), r['bits']) for g, r in zip(got, recs) if int(g) != r['bits']]
+    assert not bad, (len(bad), bad[:5])

@@ -108,6 +108,11 @@ def extra_fixtures(which):
                                                                               VVC_TRACE_MAX_VISITS=0, VVC_TRACE_TU_FIRST=2, VVC_TRACE_TU_STRIDE=700, VVC_TRACE_ONLY='FJ')),
         'ref_8b_128x64_qp32_lfnst': lambda n: run(n, 128, 64, 8, 32, dict(VVC_TRACE_VISIT_FIRST=0, VVC_TRACE_VISIT_STRIDE=1000000,
                                                                           VVC_TRACE_MAX_VISITS=0, VVC_TRACE_TU_FIRST=2, VVC_TRACE_TU_STRIDE=400, VVC_TRACE_ONLY='FJ')),
+        # f2: residual rate estimation -- CABACWriter::residual_coding on the bit estimator (context states in, fractional bits out)
+        'ref_10b_128x128_qp27_resbits': lambda n: run(n, 128, 128, 10, 27, dict(VVC_TRACE_VISIT_FIRST=0, VVC_TRACE_VISIT_STRIDE=1000000,
+                                                                                VVC_TRACE_MAX_VISITS=0, VVC_TRACE_TU_FIRST=3, VVC_TRACE_TU_STRIDE=700, VVC_TRACE_ONLY='C')),
+        'ref_8b_128x64_qp22_resbits': lambda n: run(n, 128, 64, 8, 22, dict(VVC_TRACE_VISIT_FIRST=0, VVC_TRACE_VISIT_STRIDE=1000000,
+                                                                            VVC_TRACE_MAX_VISITS=0, VVC_TRACE_TU_FIRST=3, VVC_TRACE_TU_STRIDE=900, VVC_TRACE_ONLY='C')),
     }
     with open(os.path.join(ROOT, 'tests/golden/MANIFEST.txt'), 'a') as f:
         for n in which or sorted(todo):

@@ -30,6 +30,11 @@ class _Cur:
         self.o += 4 * n
         return v
 
+    def take(self, nbytes):
+        v = bytes(self.b[self.o:self.o + nbytes])
+        self.o += nbytes
+        return v
+
     def u64(self):
         v = struct.unpack_from('<Q', self.b, self.o)[0]
         self.o += 8
@@ -137,6 +142,12 @@ def parse_record(tag, payload):
         r['resi'] = c.i16(n).reshape(r['h'], r['w'])
         r['coeff'] = c.i32(n).reshape(r['h'], r['w'])
         r['level'] = c.i32(n).reshape(r['h'], r['w'])
+    elif tag == 'C':
+        for k in ('w', 'h', 'mts', 'ts_allowed', 'mts_allowed', 'dep_quant'):
+            r[k] = c.i32()
+        r['bits'] = c.u64()
+        r['states'] = np.frombuffer(c.take(2 * 3 * 174), '<u2').reshape(174, 3).copy()
+        r['level'] = c.i32(r['w'] * r['h']).reshape(r['h'], r['w'])
     elif tag == 'F':
         for k in ('w', 'h', 'bd', 'mts', 'lfnst', 'intra_mode', 'qp', 'per', 'rem', 'abs_sum', 'cbf_delta'):
             r[k] = c.i32()

@@ -10,6 +10,7 @@
 #include "vvcb_tu.cuh"
 #include "vvcb_feat.cuh"
 #include "vvcb_dq.cuh"
+#include "vvcb_rate.cuh"
 #include <vector>
 #include <thread>
 #include <atomic>
@@ -51,9 +52,11 @@ struct vvcb_ctx {
   cudaEvent_t ev0, ev1;
   Rom* dRom;
   TrRom* dTrRom;
-  void* dTu[17]; size_t capTu[17];  // TU scratch: jobs, resi, pred, coeff, level, reco, results; DepQuant: coeff in, dequantised out,
+  void* dTu[19]; size_t capTu[19];  // TU scratch: jobs, resi, pred, coeff, level, reco, results; DepQuant: coeff in, dequantised out,
                                     // job order, context prices, derived rate tables, per-group context memory + trellis
   DqRom* dDqRom;
+  RateRom* dRateRom;
+  int depQuant;                     // slice->getDepQuantEnabledFlag() (vvcb_set_option), 1 = the shipped configuration
   float tuMs[3]; int tuTimed; cudaEvent_t tev[4];   // per-kernel timing of vvcb_tu_eval: transform pass, dependent quantisation, reconstruction pass
   void* dFeat[2]; size_t capFeat[2]; // feature scratch: jobs / per-CTU sums, results
   // copy/compute pipeline of vvcb_rmd_eval for large host batches
@@ -114,7 +117,7 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
   vvcb_ctx* ctx = new (std::nothrow) vvcb_ctx();
   if (!ctx) return VVCB_ERR_ARG;
   memset(ctx, 0, sizeof(*ctx));
-  ctx->device = device; ctx->bd = bit_depth; ctx->ctu = ctu_size;
+  ctx->device = device; ctx->bd = bit_depth; ctx->ctu = ctu_size; ctx->depQuant = 1;
   auto fail = [&](const char* what, cudaError_t err) {
     snprintf(g_createErr, sizeof(g_createErr), "vvcb_create: %s: %s", what, cudaGetErrorString(err));
     delete ctx;
@@ -157,6 +160,12 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
     delete t;
     if (e != cudaSuccess) return fail("cudaMemcpy(dqrom)", e);
   }
+  {
+    RateRom t;
+    for (int i = 0; i < 512; i++) t.binFracBits[i] = kBinFracBits[i];
+    if ((e = cudaMalloc(&ctx->dRateRom, sizeof(RateRom))) != cudaSuccess) return fail("cudaMalloc(raterom)", e);
+    if ((e = cudaMemcpy(ctx->dRateRom, &t, sizeof(RateRom), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy(raterom)", e);
+  }
   *out = ctx;
   return VVCB_OK;
 }
@@ -168,7 +177,8 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dSlotMajor);
   cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred); cudaFree(ctx->dTrRom);
-  for (int i = 0; i < 17; i++) cudaFree(ctx->dTu[i]);
+  for (int i = 0; i < 19; i++) cudaFree(ctx->dTu[i]);
+  cudaFree(ctx->dRateRom);
   cudaFree(ctx->dDqRom);
   for (int i = 0; i < 2; i++) cudaFree(ctx->dFeat[i]);
   if (ctx->pipeReady) {
@@ -182,6 +192,14 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaEventDestroy(ctx->evPlan);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+extern "C" int vvcb_set_option(vvcb_ctx* ctx, int option, int value)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (option == VVCB_OPT_DEP_QUANT && (value == 0 || value == 1)) { ctx->depQuant = value; return VVCB_OK; }
+  snprintf(ctx->err, sizeof(ctx->err), "vvcb_set_option: unknown option %d or bad value %d", option, value);
+  return VVCB_ERR_ARG;
 }
 
 extern "C" int vvcb_frame_begin(vvcb_ctx* ctx, const int16_t* orig, int stride, int width, int height)
@@ -522,7 +540,7 @@ static int tu_buf(vvcb_ctx* ctx, int i, size_t bytes)
 // Common body of vvcb_tu_eval (residual and prediction come from the host) and vvcb_tu_eval_pred (src != nullptr: both are
 // produced on the device by tu_pred_kernel from the frame planes).
 static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred, size_t n_samples,
-                        const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results,
+                        const vvcb_dq_rates* rates, const vvcb_ctx_states* states, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results,
                         const vvcb_rmd_visit* visits, int n_visits, const vvcb_tu_src* src, int16_t* pred_out)
 {
   if (!ctx) return VVCB_ERR_ARG;
@@ -561,19 +579,24 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     if (dq) ok = ok && j.mts_idx != 1 && rates && j.rate_idx < n_rates && j.lfnst_idx <= 2 && j.lambda > 0.0;   // CL/DepQuant.cpp:1757: TS goes to RDOQ
     if (j.flags & VVCB_TU_RDOQ_TS) ok = ok && q && !dq && j.mts_idx == 1 && rates && j.rate_idx < n_rates && j.lambda > 0.0;
     ok = ok && j.lfnst_idx <= 2 && (j.lfnst_idx == 0 || j.intra_mode < VVCB_NUM_LUMA_MODE);
+    if (j.flags & VVCB_TU_RATE) ok = ok && q && states && j.rate_idx < n_rates;
     return ok;
   });
   if (badJob >= 0) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: job %d is malformed", badJob); return VVCB_ERR_ARG; }
   bool anyQuant = false;
   std::vector<int> order;                 // DepQuant jobs (sorted on the device by scan length once the coefficients exist)
-  std::vector<int> tsBySize[7];
+  std::vector<int> tsBySize[7], rateBySize[9];
   order.reserve(n);
   for (int i = 0; i < n; i++) {
     const bool q = (jobs[i].flags & VVCB_TU_QUANT) != 0;
     anyQuant = anyQuant || q;
     if (q && (jobs[i].flags & VVCB_TU_DEPQUANT)) order.push_back(i);
     else if (q && (jobs[i].flags & VVCB_TU_RDOQ_TS)) tsBySize[jobs[i].log2w + jobs[i].log2h - 4].push_back(i);
+    if (q && (jobs[i].flags & VVCB_TU_RATE)) rateBySize[jobs[i].log2w + jobs[i].log2h - 4].push_back(i);
   }
+  std::vector<int> rateOrder;             // jobs whose residual bits are wanted, largest TU first
+  for (int c = 8; c >= 0; c--) rateOrder.insert(rateOrder.end(), rateBySize[c].begin(), rateBySize[c].end());
+  const int nRate = (int)rateOrder.size();
   std::vector<int> tsOrder;               // RDOQ transform-skip jobs, largest block first (one thread per block: equal chain lengths per warp)
   for (int c = 6; c >= 0; c--) tsOrder.insert(tsOrder.end(), tsBySize[c].begin(), tsBySize[c].end());
   const int nTs = (int)tsOrder.size();
@@ -585,7 +608,9 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
   if ((rc = tu_buf(ctx, 1, n_samples * sizeof(int16_t)))) return rc;
   if ((rc = tu_buf(ctx, 2, n_samples * sizeof(int16_t)))) return rc;
   if (coeff && (rc = tu_buf(ctx, 3, n_samples * sizeof(int32_t)))) return rc;
-  if ((level || nDq || nTs) && (rc = tu_buf(ctx, 4, n_samples * sizeof(int32_t)))) return rc;
+  if ((level || nDq || nTs || nRate) && (rc = tu_buf(ctx, 4, n_samples * sizeof(int32_t)))) return rc;
+  if (nRate && (rc = tu_buf(ctx, 17, (size_t)nRate * sizeof(int)))) return rc;
+  if (nRate && (rc = tu_buf(ctx, 18, (size_t)n_rates * sizeof(vvcb_ctx_states)))) return rc;
   if (reco && (rc = tu_buf(ctx, 5, n_samples * sizeof(int16_t)))) return rc;
   if ((rc = tu_buf(ctx, 6, (size_t)n * sizeof(vvcb_tu_result)))) return rc;
   int dqGrid = 0;
@@ -627,7 +652,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
   P.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); P.n = n;
   P.resi = static_cast<const int16_t*>(ctx->dTu[1]); P.pred = static_cast<const int16_t*>(ctx->dTu[2]);
   P.coeff = coeff ? static_cast<int32_t*>(ctx->dTu[3]) : nullptr;
-  P.level = (level || nDq || nTs) ? static_cast<int32_t*>(ctx->dTu[4]) : nullptr;
+  P.level = (level || nDq || nTs || nRate) ? static_cast<int32_t*>(ctx->dTu[4]) : nullptr;
   P.reco = reco ? static_cast<int16_t*>(ctx->dTu[5]) : nullptr;
   P.results = static_cast<vvcb_tu_result*>(ctx->dTu[6]);
   P.orig = ctx->bOrig; P.stride = ctx->stride; P.bd = ctx->bd; P.rom = ctx->dTrRom;
@@ -679,6 +704,15 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
     ctx->launches++;
   }
+  if (nRate) {                                                     // levels are final: price them (CABACWriter::residual_coding on the estimator)
+    CK(cudaMemcpyAsync(ctx->dTu[17], rateOrder.data(), (size_t)nRate * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dTu[18], states, (size_t)n_rates * sizeof(vvcb_ctx_states), cudaMemcpyHostToDevice, ctx->stream));
+    RateParams R;
+    R.jobs = P.jobs; R.order = static_cast<const int*>(ctx->dTu[17]); R.n = nRate; R.level = P.level; R.results = P.results;
+    R.states = static_cast<const vvcb_ctx_states*>(ctx->dTu[18]); R.rom = ctx->dDqRom; R.rate = ctx->dRateRom; R.depQuant = ctx->depQuant;
+    rate_kernel<<<(nRate + kRateThreads - 1) / kRateThreads, kRateThreads, 0, ctx->stream>>>(R);
+    ctx->launches++;
+  }
   if (tm) CK(cudaEventRecord(ctx->tev[3], ctx->stream));
   CK(cudaGetLastError());
   if (coeff) CK(cudaMemcpyAsync(coeff, ctx->dTu[3], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -695,17 +729,62 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
 }
 
 extern "C" int vvcb_tu_eval(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred, size_t n_samples,
-                            const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results)
+                            const vvcb_dq_rates* rates, const vvcb_ctx_states* states, int n_rates,
+                            int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results)
 {
-  return tu_eval_impl(ctx, jobs, n, resi, pred, n_samples, rates, n_rates, coeff, level, reco, results, nullptr, 0, nullptr, nullptr);
+  return tu_eval_impl(ctx, jobs, n, resi, pred, n_samples, rates, states, n_rates, coeff, level, reco, results, nullptr, 0, nullptr, nullptr);
 }
 
 extern "C" int vvcb_tu_eval_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n_visits, const vvcb_tu_src* src, const vvcb_tu_job* jobs, int n,
-                                 size_t n_samples, const vvcb_dq_rates* rates, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco,
-                                 int16_t* pred_out, vvcb_tu_result* results)
+                                 size_t n_samples, const vvcb_dq_rates* rates, const vvcb_ctx_states* states, int n_rates,
+                                 int32_t* coeff, int32_t* level, int16_t* reco, int16_t* pred_out, vvcb_tu_result* results)
 {
   if (ctx && n > 0 && !src) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval_pred: bad argument"); return VVCB_ERR_ARG; }
-  return tu_eval_impl(ctx, jobs, n, nullptr, nullptr, n_samples, rates, n_rates, coeff, level, reco, results, visits, n_visits, src, pred_out);
+  return tu_eval_impl(ctx, jobs, n, nullptr, nullptr, n_samples, rates, states, n_rates, coeff, level, reco, results, visits, n_visits, src, pred_out);
+}
+
+// CABACWriter::residual_coding on given levels (HOST int32, dense per job at job.offset): jobs carry geometry, mts_idx, the
+// VVCB_TU_TS_ALLOWED / VVCB_TU_MTS_ALLOWED switches and rate_idx; bits[i] = fractional bits (0 for an all-zero block).
+extern "C" int vvcb_residual_bits(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int32_t* levels, size_t n_samples,
+                                  const vvcb_ctx_states* states, int n_states, uint64_t* bits)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (n < 0 || (n > 0 && (!jobs || !levels || !states || !bits || n_states <= 0))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_residual_bits: bad argument"); return VVCB_ERR_ARG; }
+  if (n == 0) return VVCB_OK;
+  const int bad = first_bad_index(n, [&](int i) {
+    const vvcb_tu_job& j = jobs[i];
+    bool ok = j.log2w >= 2 && j.log2w <= 6 && j.log2h >= 2 && j.log2h <= 6 && j.mts_idx <= 5 && j.rate_idx < n_states &&
+              (size_t)j.offset + ((size_t)1 << (j.log2w + j.log2h)) <= n_samples;
+    if (j.mts_idx >= 1) ok = ok && j.log2w <= 5 && j.log2h <= 5;
+    return ok;
+  });
+  if (bad >= 0) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_residual_bits: job %d is malformed", bad); return VVCB_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = tu_buf(ctx, 0, (size_t)n * sizeof(vvcb_tu_job)))) return rc;
+  if ((rc = tu_buf(ctx, 4, n_samples * sizeof(int32_t)))) return rc;
+  if ((rc = tu_buf(ctx, 6, (size_t)n * sizeof(vvcb_tu_result)))) return rc;
+  if ((rc = tu_buf(ctx, 17, (size_t)n * sizeof(int)))) return rc;
+  if ((rc = tu_buf(ctx, 18, (size_t)n_states * sizeof(vvcb_ctx_states)))) return rc;
+  std::vector<int> bySize[9], order;
+  for (int i = 0; i < n; i++) bySize[jobs[i].log2w + jobs[i].log2h - 4].push_back(i);
+  for (int c = 8; c >= 0; c--) order.insert(order.end(), bySize[c].begin(), bySize[c].end());
+  CK(cudaMemcpyAsync(ctx->dTu[0], jobs, (size_t)n * sizeof(vvcb_tu_job), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dTu[4], levels, n_samples * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dTu[17], order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dTu[18], states, (size_t)n_states * sizeof(vvcb_ctx_states), cudaMemcpyHostToDevice, ctx->stream));
+  RateParams R;
+  R.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); R.order = static_cast<const int*>(ctx->dTu[17]); R.n = n;
+  R.level = static_cast<const int32_t*>(ctx->dTu[4]); R.results = static_cast<vvcb_tu_result*>(ctx->dTu[6]);
+  R.states = static_cast<const vvcb_ctx_states*>(ctx->dTu[18]); R.rom = ctx->dDqRom; R.rate = ctx->dRateRom; R.depQuant = ctx->depQuant;
+  rate_kernel<<<(n + kRateThreads - 1) / kRateThreads, kRateThreads, 0, ctx->stream>>>(R);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  std::vector<vvcb_tu_result> res(n);
+  CK(cudaMemcpyAsync(res.data(), ctx->dTu[6], (size_t)n * sizeof(vvcb_tu_result), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; i++) bits[i] = res[i].frac_bits;
+  return VVCB_OK;
 }
 
 extern "C" int vvcb_tu_kernel_times(vvcb_ctx* ctx, float ms[3], int* calls)

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
         if (threadIdx.x == 0) {
           vvcb_tu_result r;
           r.abs_sum_coeff = (int)__dmul_rn((double)(int)sumAbs, ts && ((lw + lh) & 1) ? 1.0 / 1.414213562 : 1.0);   // CL/TrQuant.cpp:1098-1102
-          r.abs_sum_level = 0; r.sse = 0;
+          r.abs_sum_level = 0; r.sse = 0; r.frac_bits = 0;
           P.results[ji] = r;
         }
         continue;
@@ -314,6 +314,7 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
       r.abs_sum_coeff = (int)__dmul_rn((double)(int)sumAbs, scale);
       r.abs_sum_level = absLevel;
       r.sse = sse;
+      r.frac_bits = 0;
       P.results[ji] = r;
     }
   }

@@ -31,17 +31,23 @@ assert VISIT_DTYPE.itemsize == 80 and RESULT_DTYPE.itemsize == 368 and DETAIL_DT
     (VISIT_DTYPE.itemsize, RESULT_DTYPE.itemsize, DETAIL_DTYPE.itemsize)
 
 
-TU_QUANT, TU_DEPQUANT, TU_RDOQ_TS = 1, 2, 4
+OPT_DEP_QUANT = 1
+TU_QUANT, TU_DEPQUANT, TU_RDOQ_TS, TU_TS_ALLOWED, TU_MTS_ALLOWED, TU_RATE = 1, 2, 4, 8, 16, 32
+BIN_MODEL_DTYPE = np.dtype([('state', '<u2', 2), ('rate', 'u1'), ('pad', 'u1')])
+CTX_STATES_DTYPE = np.dtype([('mts_idx', BIN_MODEL_DTYPE, 11), ('sig_sbb', BIN_MODEL_DTYPE, 2), ('sig', BIN_MODEL_DTYPE, (3, 12)), ('par', BIN_MODEL_DTYPE, 21),
+                             ('gt1', BIN_MODEL_DTYPE, 21), ('gt2', BIN_MODEL_DTYPE, 21), ('last_x', BIN_MODEL_DTYPE, 20), ('last_y', BIN_MODEL_DTYPE, 20),
+                             ('ts_sig_sbb', BIN_MODEL_DTYPE, 3), ('ts_sig', BIN_MODEL_DTYPE, 3), ('ts_par', BIN_MODEL_DTYPE, 1), ('ts_gtx', BIN_MODEL_DTYPE, 5),
+                             ('ts_lrg1', BIN_MODEL_DTYPE, 4), ('ts_sign', BIN_MODEL_DTYPE, 6)])
 TU_JOB_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('log2w', 'u1'), ('log2h', 'u1'), ('mts_idx', 'u1'), ('flags', 'u1'),
                          ('qp_per', '<i2'), ('qp_rem', '<i2'), ('offset', '<u4'), ('rate_idx', '<u2'), ('lfnst_idx', 'u1'), ('intra_mode', 'u1'),
                          ('cbf_delta_bits', '<i4'), ('lambda', '<f8')], align=True)
-TU_RESULT_DTYPE = np.dtype([('abs_sum_coeff', '<i4'), ('abs_sum_level', '<i4'), ('sse', '<u8')], align=True)
+TU_RESULT_DTYPE = np.dtype([('abs_sum_coeff', '<i4'), ('abs_sum_level', '<i4'), ('sse', '<u8'), ('frac_bits', '<u8')], align=True)
 TU_SRC_DTYPE = np.dtype([('visit', '<u4'), ('slot', 'u1'), ('pad', 'u1', 3)])
 DQ_RATES_DTYPE = np.dtype([('sig_sbb', '<u4', (2, 2)), ('sig', '<u4', (3, 12, 2)), ('par', '<u4', (21, 2)), ('gt1', '<u4', (21, 2)),
                            ('gt2', '<u4', (21, 2)), ('last_x', '<u4', (20, 2)), ('last_y', '<u4', (20, 2)),
                            ('ts_sig_sbb', '<u4', (3, 2)), ('ts_sig', '<u4', (3, 2)), ('ts_par', '<u4', (1, 2)), ('ts_gtx', '<u4', (5, 2)),
                            ('ts_lrg1', '<u4', (4, 2)), ('ts_sign', '<u4', (6, 2))])
-assert TU_SRC_DTYPE.itemsize == 8 and TU_JOB_DTYPE.itemsize == 32 and TU_RESULT_DTYPE.itemsize == 16 and DQ_RATES_DTYPE.itemsize == 1304
+assert TU_SRC_DTYPE.itemsize == 8 and TU_JOB_DTYPE.itemsize == 32 and TU_RESULT_DTYPE.itemsize == 24 and CTX_STATES_DTYPE.itemsize == 1044 and DQ_RATES_DTYPE.itemsize == 1304
 
 
 FEAT_CU_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('w', 'u1'), ('h', 'u1'), ('qt_depth', 'u1'), ('mt_depth', 'u1')])
@@ -78,6 +84,7 @@ def load_library():
         L.vvcb_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
         L.vvcb_destroy.argtypes = [C.c_void_p]
         L.vvcb_destroy.restype = None
+        L.vvcb_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.vvcb_frame_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.vvcb_reco_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.vvcb_rmd_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -90,10 +97,11 @@ def load_library():
         L.vvcb_dev_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.vvcb_dev_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.vvcb_sync.argtypes = [C.c_void_p]
-        L.vvcb_tu_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p,
+        L.vvcb_tu_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
-        L.vvcb_tu_eval_pred.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
+        L.vvcb_tu_eval_pred.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.vvcb_residual_bits.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
         L.vvcb_mts_preselect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vvcb_mts_preselect.restype = None
         L.vvcb_ctu_hads_islice.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -144,6 +152,9 @@ class IntraCostEngine:
         if rc != 0:
             raise EngineError('%s (status %d)' % (self._lib.vvcb_last_error(self._ctx).decode(), rc))
 
+    def set_option(self, option, value):
+        self._ck(self._lib.vvcb_set_option(self._ctx, option, value))
+
     # ---- planes
     def frame_begin(self, orig):
         orig = np.ascontiguousarray(orig, np.int16)
@@ -193,7 +204,17 @@ class IntraCostEngine:
         return pred
 
     # ---- TU coding
-    def tu_eval(self, jobs, resi, pred=None, want_coeff=False, want_level=False, want_reco=False, rates=None):
+    @staticmethod
+    def _snapshots(rates, states):
+        """Context prices (DQ_RATES_DTYPE) and context states (CTX_STATES_DTYPE) are parallel arrays indexed by job['rate_idx']."""
+        rates = None if rates is None else np.ascontiguousarray(rates, DQ_RATES_DTYPE)
+        states = None if states is None else np.ascontiguousarray(states, CTX_STATES_DTYPE)
+        if rates is not None and states is not None and len(rates) != len(states):
+            raise ValueError('rates and states must have the same length')
+        nr = len(rates) if rates is not None else (len(states) if states is not None else 0)
+        return rates, states, nr
+
+    def tu_eval(self, jobs, resi, pred=None, want_coeff=False, want_level=False, want_reco=False, rates=None, states=None):
         """vvcb_tu_eval.  resi / pred: flat int16 arrays indexed by job['offset']; rates: DQ_RATES_DTYPE array indexed by
         job['rate_idx'] (jobs flagged TU_DEPQUANT).  Returns dict of outputs."""
         jobs = np.ascontiguousarray(jobs, TU_JOB_DTYPE)
@@ -207,14 +228,14 @@ class IntraCostEngine:
             out['level'] = np.zeros(ns, np.int32)
         if want_reco:
             out['reco'] = np.zeros(ns, np.int16)
-        rates = None if rates is None else np.ascontiguousarray(rates, DQ_RATES_DTYPE)
+        rates, states, nr = self._snapshots(rates, states)
         self._ck(self._lib.vvcb_tu_eval(self._ctx, _ptr(jobs), len(jobs), _ptr(resi), _ptr(pred) if pred is not None else None, ns,
-                                        _ptr(rates) if rates is not None else None, 0 if rates is None else len(rates),
+                                        _ptr(rates) if rates is not None else None, _ptr(states) if states is not None else None, nr,
                                         _ptr(out['coeff']) if want_coeff else None, _ptr(out['level']) if want_level else None,
                                         _ptr(out['reco']) if want_reco else None, _ptr(out['results'])))
         return out
 
-    def tu_eval_pred(self, visits, src, jobs, n_samples, want_coeff=False, want_level=False, want_reco=False, want_pred=False, rates=None):
+    def tu_eval_pred(self, visits, src, jobs, n_samples, want_coeff=False, want_level=False, want_reco=False, want_pred=False, rates=None, states=None):
         """vvcb_tu_eval_pred: prediction and residual are formed on the device from the frame planes (src: TU_SRC_DTYPE)."""
         visits = np.ascontiguousarray(visits, VISIT_DTYPE)
         src = np.ascontiguousarray(src, TU_SRC_DTYPE)
@@ -223,12 +244,21 @@ class IntraCostEngine:
         for key, want, dt in (('coeff', want_coeff, np.int32), ('level', want_level, np.int32), ('reco', want_reco, np.int16), ('pred', want_pred, np.int16)):
             if want:
                 out[key] = np.zeros(n_samples, dt)
-        rates = None if rates is None else np.ascontiguousarray(rates, DQ_RATES_DTYPE)
+        rates, states, nr = self._snapshots(rates, states)
         p = lambda k: _ptr(out[k]) if k in out else None
         self._ck(self._lib.vvcb_tu_eval_pred(self._ctx, _ptr(visits), len(visits), _ptr(src), _ptr(jobs), len(jobs), n_samples,
-                                             _ptr(rates) if rates is not None else None, 0 if rates is None else len(rates),
+                                             _ptr(rates) if rates is not None else None, _ptr(states) if states is not None else None, nr,
                                              p('coeff'), p('level'), p('reco'), p('pred'), _ptr(out['results'])))
         return out
+
+    def residual_bits(self, jobs, levels, states):
+        """vvcb_residual_bits: fractional bits of residual_coding for the given levels (flat int32 indexed by job['offset'])."""
+        jobs = np.ascontiguousarray(jobs, TU_JOB_DTYPE)
+        levels = np.ascontiguousarray(levels, np.int32).ravel()
+        states = np.ascontiguousarray(states, CTX_STATES_DTYPE)
+        bits = np.zeros(len(jobs), np.uint64)
+        self._ck(self._lib.vvcb_residual_bits(self._ctx, _ptr(jobs), len(jobs), _ptr(levels), levels.size, _ptr(states), len(states), _ptr(bits)))
+        return bits
 
     def mts_preselect(self, sums, width, height, max_cand):
         sums = np.ascontiguousarray(sums, np.int32)
