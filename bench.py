@@ -272,21 +272,22 @@ def tu_stage_leg(eng, vb, base, frame, int_peak):
     vis = base.copy()
     vis['sqrt_lambda'] = vb.partition.sqrt_lambda_for_qp(32)
     res = eng.rmd_eval(vis)
-    src, jobs, n_samples, rates = vb.build_tu_jobs_from_lists(vis, res, 32, BITS)
+    src, jobs, n_samples, rates = vb.build_tu_jobs_from_lists(vis, res, 32, BITS, rate=True)
+    states = vb.default_ctx_states()
     hv = eng.host_array(len(vis), vb.VISIT_DTYPE)
     hv[:] = vis
     hs = eng.host_array(len(src), vb.TU_SRC_DTYPE)
     hs[:] = src
     hj = eng.host_array(len(jobs), vb.TU_JOB_DTYPE)
     hj[:] = jobs
-    eng.tu_eval_pred(hv, hs, hj, n_samples, rates=rates)      # warm-up (allocations)
+    eng.tu_eval_pred(hv, hs, hj, n_samples, rates=rates, states=states)      # warm-up (allocations)
     eng.kernel_timing(True)
     reps = 3
     t0 = time.perf_counter()
     for _ in range(reps):
-        out = eng.tu_eval_pred(hv, hs, hj, n_samples, rates=rates)
+        out = eng.tu_eval_pred(hv, hs, hj, n_samples, rates=rates, states=states)
     wall = (time.perf_counter() - t0) / reps
-    k_tr, k_dq, k_rec, k_n = eng.tu_kernel_times()
+    k_tr, k_dq, k_rec, k_rate, k_n = eng.tu_kernel_times()
     eng.kernel_timing(False)
     lw, lh = jobs['log2w'].astype(np.int64), jobs['log2h'].astype(np.int64)
     # a separable transform costs w*h*(w_out + h_out) MACs (64-point sides keep 32 outputs); forward + inverse
@@ -304,20 +305,22 @@ def tu_stage_leg(eng, vb, base, frame, int_peak):
         co = O.fwd_transform(r, BITS, 0)
         lvl, _ = O.dep_quant(co, BITS, 0, 0, qp, float(j['lambda']), rates[0], 0)
         O.inv_transform(O.dep_dequant(lvl, BITS, qp), BITS, 0)
+        O.residual_bits(lvl, 0, w <= 32 and h <= 32, w <= 32 and h <= 32, 1, states[0])
     cpu_s = time.perf_counter() - t0
-    kern_ms = (k_tr + k_dq + k_rec) / max(1, k_n)
+    kern_ms = (k_tr + k_dq + k_rec + k_rate) / max(1, k_n)
     return {'workload': 'frame 0, the best rough-mode-decision candidate of every candidate CU (%d TUs, %d samples): prediction, residual, DCT-II, '
-                        'dependent quantisation, inverse, reconstruction, SSE; QP 32' % (len(jobs), n_samples),
+                        'dependent quantisation, inverse, reconstruction, SSE, residual bits; QP 32' % (len(jobs), n_samples),
             'tus_per_s_kernels': len(jobs) / (kern_ms * 1e-3) if kern_ms else None,
             'tus_per_s_e2e': len(jobs) / wall,
-            'kernel_ms': {'predict_transform': k_tr / max(1, k_n), 'dep_quant': k_dq / max(1, k_n), 'reconstruct': k_rec / max(1, k_n),
+            'kernel_ms': {'predict_transform': k_tr / max(1, k_n), 'dep_quant': k_dq / max(1, k_n), 'reconstruct': k_rec / max(1, k_n), 'residual_bits': k_rate / max(1, k_n),
                           'note': 'events around the launches of vvcb_tu_eval_pred: prediction + transform pass, first-position + sort + dependent quantisation, reconstruction pass'},
             'e2e_ms': wall * 1e3, 'h2d_bytes': int(vis.nbytes + src.nbytes + jobs.nbytes), 'd2h_bytes': int(out['results'].nbytes),
             'transform_gmacs_per_s': macs / (((k_tr + k_rec) / max(1, k_n)) * 1e-3) / 1e9 if k_n else None,
             'transform_int_alu_frac': (macs / (((k_tr + k_rec) / max(1, k_n)) * 1e-3) / 1e9) / int_peak[0] if k_n and int_peak[0] else None,
             'nonzero_tu_fraction': float((out['results']['abs_sum_level'] > 0).mean()),
+            'mean_residual_bits': float(out['results']['frac_bits'].mean() / 32768.0),
             'cpu_baseline': {'value': len(sel) / cpu_s, 'unit': 'TU/s', 'cores': 1, 'kind': 'port',
-                             'sample': 'oracle: all predictions of the visit (its RMD pass) + transform + dependent quantisation + inverse on %d of the jobs, %.1f s' % (len(sel), cpu_s)}}
+                             'sample': 'oracle: all predictions of the visit (its RMD pass) + transform + dependent quantisation + inverse + residual bits on %d of the jobs, %.1f s' % (len(sel), cpu_s)}}
 
 
 def cpu_baseline_port(base, frame):

@@ -301,8 +301,9 @@ int vvcb_timer_stop (vvcb_ctx* ctx, float* ms);
  * the last call; enable with on != 0.  ms[0] plan, ms[1] eval (prediction+SAD+SATD), ms[2] lists.   */
 int vvcb_kernel_timing(vvcb_ctx* ctx, int on);
 int vvcb_kernel_times(vvcb_ctx* ctx, float ms[3], int* launches);
-/* same for vvcb_tu_eval / vvcb_tu_eval_pred: ms[0] (prediction +) transform pass, ms[1] dependent quantisation, ms[2] reconstruction pass */
-int vvcb_tu_kernel_times(vvcb_ctx* ctx, float ms[3], int* calls);
+/* same for vvcb_tu_eval / vvcb_tu_eval_pred: ms[0] (prediction +) transform pass, ms[1] quantiser kernels, ms[2] reconstruction pass,
+ * ms[3] residual rate estimation                                                                                         */
+int vvcb_tu_kernel_times(vvcb_ctx* ctx, float ms[4], int* calls);
 /* Integer-ALU roofline denominator, measured live: dependent-free IMAD / IADD3+LOP3 / 1:1 mixed
  * instruction streams on every SM; results in 10^9 lane-operations per second.                  */
 int vvcb_measure_int_peak(vvcb_ctx* ctx, double* gops_imad, double* gops_alu, double* gops_mixed);

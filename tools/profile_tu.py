@@ -34,5 +34,5 @@ with vb.IntraCostEngine(0, 10, 128) as eng:
         out = eng.tu_eval(jobs, resi, pred, rates=rates)
         dt = time.perf_counter() - t0
     r = out['results']
-    print('kernel ms (transform, depquant, recon, n):', eng.tu_kernel_times(), 'last call %.1f ms' % (dt * 1e3),
+    print('kernel ms (transform, quantisers, recon, rate, n):', eng.tu_kernel_times(), 'last call %.1f ms' % (dt * 1e3),
           'nonzero TUs %.3f' % float((r['abs_sum_level'] > 0).mean()), 'mean abs sum %.2f' % float(r['abs_sum_level'].mean()))

@@ -57,7 +57,7 @@ struct vvcb_ctx {
   DqRom* dDqRom;
   RateRom* dRateRom;
   int depQuant;                     // slice->getDepQuantEnabledFlag() (vvcb_set_option), 1 = the shipped configuration
-  float tuMs[3]; int tuTimed; cudaEvent_t tev[4];   // per-kernel timing of vvcb_tu_eval: transform pass, dependent quantisation, reconstruction pass
+  float tuMs[4]; int tuTimed; cudaEvent_t tev[5];   // per-kernel timing of vvcb_tu_eval: transform pass, dependent quantisation, reconstruction pass
   void* dFeat[2]; size_t capFeat[2]; // feature scratch: jobs / per-CTU sums, results
   // copy/compute pipeline of vvcb_rmd_eval for large host batches
   cudaStream_t sIn, sOut; cudaEvent_t evIn[2], evComp[2], evOut[2];
@@ -136,7 +136,7 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
   for (int i = 0; i < 4; i++) if ((e = cudaEventCreate(&ctx->kev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
-  for (int i = 0; i < 4; i++) if ((e = cudaEventCreate(&ctx->tev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
+  for (int i = 0; i < 5; i++) if ((e = cudaEventCreate(&ctx->tev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
   Rom* h = new Rom();
   fill_rom(*h);
   if ((e = cudaMalloc(&ctx->dRom, sizeof(Rom))) != cudaSuccess) { delete h; return fail("cudaMalloc(rom)", e); }
@@ -187,7 +187,8 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
     cudaStreamDestroy(ctx->sIn); cudaStreamDestroy(ctx->sOut);
   }
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
-  for (int i = 0; i < 4; i++) { cudaEventDestroy(ctx->kev[i]); cudaEventDestroy(ctx->tev[i]); }
+  for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->kev[i]);
+  for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->tev[i]);
   for (int i = 0; i < 2; i++) { cudaStreamSynchronize(ctx->sKind[i]); cudaStreamDestroy(ctx->sKind[i]); cudaEventDestroy(ctx->evKind[i]); }
   cudaEventDestroy(ctx->evPlan);
   cudaStreamDestroy(ctx->stream);
@@ -259,7 +260,7 @@ extern "C" int vvcb_kernel_timing(vvcb_ctx* ctx, int on)
 {
   if (!ctx) return VVCB_ERR_ARG;
   ctx->timing = on; ctx->timedLaunches = 0; ctx->kms[0] = ctx->kms[1] = ctx->kms[2] = 0.f;
-  ctx->tuTimed = 0; ctx->tuMs[0] = ctx->tuMs[1] = ctx->tuMs[2] = 0.f;
+  ctx->tuTimed = 0; ctx->tuMs[0] = ctx->tuMs[1] = ctx->tuMs[2] = ctx->tuMs[3] = 0.f;
   return VVCB_OK;
 }
 
@@ -704,6 +705,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
     ctx->launches++;
   }
+  if (tm) CK(cudaEventRecord(ctx->tev[3], ctx->stream));
   if (nRate) {                                                     // levels are final: price them (CABACWriter::residual_coding on the estimator)
     CK(cudaMemcpyAsync(ctx->dTu[17], rateOrder.data(), (size_t)nRate * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dTu[18], states, (size_t)n_rates * sizeof(vvcb_ctx_states), cudaMemcpyHostToDevice, ctx->stream));
@@ -713,7 +715,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     rate_kernel<<<(nRate + kRateThreads - 1) / kRateThreads, kRateThreads, 0, ctx->stream>>>(R);
     ctx->launches++;
   }
-  if (tm) CK(cudaEventRecord(ctx->tev[3], ctx->stream));
+  if (tm) CK(cudaEventRecord(ctx->tev[4], ctx->stream));
   CK(cudaGetLastError());
   if (coeff) CK(cudaMemcpyAsync(coeff, ctx->dTu[3], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (level) CK(cudaMemcpyAsync(level, ctx->dTu[4], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -722,7 +724,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
   CK(cudaMemcpyAsync(results, ctx->dTu[6], (size_t)n * sizeof(vvcb_tu_result), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (tm) {
-    for (int i = 0; i < 3; i++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1])); ctx->tuMs[i] += ms; }
+    for (int i = 0; i < 4; i++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1])); ctx->tuMs[i] += ms; }
     ctx->tuTimed++;
   }
   return VVCB_OK;
@@ -787,10 +789,10 @@ extern "C" int vvcb_residual_bits(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n,
   return VVCB_OK;
 }
 
-extern "C" int vvcb_tu_kernel_times(vvcb_ctx* ctx, float ms[3], int* calls)
+extern "C" int vvcb_tu_kernel_times(vvcb_ctx* ctx, float ms[4], int* calls)
 {
   if (!ctx || !ms) return VVCB_ERR_ARG;
-  for (int i = 0; i < 3; i++) { ms[i] = ctx->tuMs[i]; ctx->tuMs[i] = 0.f; }
+  for (int i = 0; i < 4; i++) { ms[i] = ctx->tuMs[i]; ctx->tuMs[i] = 0.f; }
   if (calls) *calls = ctx->tuTimed;
   ctx->tuTimed = 0;
   return VVCB_OK;

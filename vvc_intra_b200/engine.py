@@ -178,11 +178,11 @@ class IntraCostEngine:
         return ms[0], ms[1], ms[2], n.value
 
     def tu_kernel_times(self):
-        """(ms transform pass, ms dependent quantisation, ms reconstruction pass, timed calls) since the last call."""
-        ms = (C.c_float * 3)()
+        """(ms prediction + transform pass, ms quantiser kernels, ms reconstruction pass, ms rate estimation, timed calls)."""
+        ms = (C.c_float * 4)()
         n = C.c_int()
         self._ck(self._lib.vvcb_tu_kernel_times(self._ctx, ms, C.byref(n)))
-        return ms[0], ms[1], ms[2], n.value
+        return ms[0], ms[1], ms[2], ms[3], n.value
 
     # ---- rough mode decision
     def rmd_eval(self, visits, out=None, detail=False, detail_out=None):

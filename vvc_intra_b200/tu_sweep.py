@@ -84,7 +84,20 @@ def slots_of_modes(visits, modes):
     return slot.astype(np.uint8)
 
 
-def build_tu_jobs_from_lists(visits, results, qp, bit_depth, rank=0, dep_quant=True):
+def default_ctx_states(seed=0):
+    """A fixed pseudo-random estimator state (see default_dq_rates): every model somewhere between 'strongly 0' and 'strongly 1'."""
+    from .engine import CTX_STATES_DTYPE, BIN_MODEL_DTYPE
+    rng = np.random.default_rng(seed)
+    st = np.zeros(1, CTX_STATES_DTYPE)
+    flat = st.view(BIN_MODEL_DTYPE).reshape(1, -1)
+    p = rng.integers(2000, 30000, flat.shape)
+    flat['state'][..., 0] = p & 0x7fe0
+    flat['state'][..., 1] = p & 0x7ffe
+    flat['rate'] = (4 << 4) | 7                     # window sizes of the shipped initialisation tables lie around these
+    return st
+
+
+def build_tu_jobs_from_lists(visits, results, qp, bit_depth, rank=0, dep_quant=True, rate=False):
     """One DCT-II TU job per visit for the rank-th entry of its full-RD candidate list (results['final_mode']): what
     xRecurIntraCodingLumaQT hands to xIntraCodingTUBlock for that candidate.  Prediction and residual are left to the engine
     (vvcb_tu_eval_pred).  Returns (src, jobs, n_samples, rates)."""
@@ -99,6 +112,11 @@ def build_tu_jobs_from_lists(visits, results, qp, bit_depth, rank=0, dep_quant=T
     for name in ('x', 'y', 'log2w', 'log2h'):
         jobs[name] = visits[name]
     jobs['flags'] = TU_QUANT | (TU_DEPQUANT if dep_quant else 0)
+    if rate:                                            # TU::isTSAllowed / isMTSAllowed: sides <= 32 (CL/UnitTools.cpp:4524-4565)
+        from .engine import TU_RATE, TU_TS_ALLOWED, TU_MTS_ALLOWED
+        small = (visits['log2w'] <= 5) & (visits['log2h'] <= 5)
+        jobs['flags'] |= TU_RATE
+        jobs['flags'][small] |= TU_TS_ALLOWED | TU_MTS_ALLOWED
     qpi = qp + 6 * (bit_depth - 8)
     jobs['qp_per'], jobs['qp_rem'] = qpi // 6, qpi % 6
     sizes = (1 << visits['log2w'].astype(np.int64)) * (1 << visits['log2h'].astype(np.int64))
