@@ -144,7 +144,7 @@ static int sccd(const int* v, int n)
 void orc_features(const int16_t* orig, int stride, const vvcb_feat_job* job, vvcb_feat_result* out)
 {
   const int x = job->cu.x, y = job->cu.y, w = job->cu.w, h = job->cu.h, n = w * h;
-  uint8_t* px = (uint8_t*)malloc(n);
+  uint8_t* px = (uint8_t*)calloc((size_t)n, 1);
   uint8_t* g[4];
   int* madp = (int*)malloc(sizeof(int) * n);
   int* f = out->f;
