@@ -98,10 +98,16 @@ extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_
   std::vector<int32_t> dqCoeff(nSamples), dqDeq(nSamples, 0);
   memset(level, 0, nSamples * sizeof(int32_t));
   TuParams P;
-  P.jobs = jobs; P.n = n; P.resi = resi; P.pred = pred; P.coeff = coeff; P.level = level; P.reco = reco; P.results = results;
+  std::vector<int> smallList, largeList;
+  for (int i = 0; i < n; i++) (jobs[i].log2w + jobs[i].log2h <= 8 ? smallList : largeList).push_back(i);
+  auto launch_tu = [&](TuParams Q) {
+    if (!smallList.empty()) { Q.list = smallList.data(); Q.n = (int)smallList.size(); emu_launch(2, kTuThreads, [&] { tu_eval_kernel<32>(Q); }); }
+    if (!largeList.empty()) { Q.list = largeList.data(); Q.n = (int)largeList.size(); emu_launch(2, kTuThreads, [&] { tu_eval_kernel<128>(Q); }); }
+  };
+  P.jobs = jobs; P.list = nullptr; P.n = 0; P.resi = resi; P.pred = pred; P.coeff = coeff; P.level = level; P.reco = reco; P.results = results;
   P.orig = orig; P.stride = stride; P.bd = bd; P.rom = &rom;
   P.dqCoeff = dqCoeff.data(); P.dqDeq = dqDeq.data(); P.phase = 0;
-  emu_launch(2, kTuThreads, [&] { tu_eval_kernel(P); });
+  launch_tu(P);
   if (nDq) {
     std::vector<DqRateTab> tabs(nRates);
     emu_launch(nRates, 32, [&] { dq_rate_kernel(rates, nRates, tabs.data()); });
@@ -127,7 +133,7 @@ extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_
   }
   if (nDq || !tsOrder.empty()) {
     P.phase = 1;
-    emu_launch(2, kTuThreads, [&] { tu_eval_kernel(P); });
+    launch_tu(P);
   }
   std::vector<int> rateOrder;
   for (int i = 0; i < n; i++) if ((jobs[i].flags & (VVCB_TU_QUANT | VVCB_TU_RATE)) == (VVCB_TU_QUANT | VVCB_TU_RATE)) rateOrder.push_back(i);

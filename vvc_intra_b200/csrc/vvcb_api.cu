@@ -52,7 +52,7 @@ struct vvcb_ctx {
   cudaEvent_t ev0, ev1;
   Rom* dRom;
   TrRom* dTrRom;
-  void* dTu[19]; size_t capTu[19];  // TU scratch: jobs, resi, pred, coeff, level, reco, results; DepQuant: coeff in, dequantised out,
+  void* dTu[20]; size_t capTu[20];  // TU scratch: jobs, resi, pred, coeff, level, reco, results; DepQuant: coeff in, dequantised out,
                                     // job order, context prices, derived rate tables, per-group context memory + trellis
   DqRom* dDqRom;
   RateRom* dRateRom;
@@ -177,7 +177,7 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dSlotMajor);
   cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred); cudaFree(ctx->dTrRom);
-  for (int i = 0; i < 19; i++) cudaFree(ctx->dTu[i]);
+  for (int i = 0; i < 20; i++) cudaFree(ctx->dTu[i]);
   cudaFree(ctx->dRateRom);
   cudaFree(ctx->dDqRom);
   for (int i = 0; i < 2; i++) cudaFree(ctx->dFeat[i]);
@@ -650,7 +650,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     if (pred) CK(cudaMemcpyAsync(ctx->dTu[2], pred, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
   }
   TuParams P;
-  P.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); P.n = n;
+  P.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); P.list = nullptr; P.n = 0;
   P.resi = static_cast<const int16_t*>(ctx->dTu[1]); P.pred = static_cast<const int16_t*>(ctx->dTu[2]);
   P.coeff = coeff ? static_cast<int32_t*>(ctx->dTu[3]) : nullptr;
   P.level = (level || nDq || nTs || nRate) ? static_cast<int32_t*>(ctx->dTu[4]) : nullptr;
@@ -658,7 +658,31 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
   P.results = static_cast<vvcb_tu_result*>(ctx->dTu[6]);
   P.orig = ctx->bOrig; P.stride = ctx->stride; P.bd = ctx->bd; P.rom = ctx->dTrRom;
   P.dqCoeff = static_cast<int32_t*>(ctx->dTu[7]); P.dqDeq = static_cast<const int32_t*>(ctx->dTu[8]); P.phase = 0;
-  const int grid = n < ctx->numSms * 8 ? n : ctx->numSms * 8;
+  // job index lists of the two team sizes of tu_eval_kernel: blocks of up to 256 samples go to one warp each
+  std::vector<int> teamList(n);
+  int nSmall = 0;
+  {
+    int lo = 0, hi = n;
+    for (int i = 0; i < n; i++) { if (jobs[i].log2w + jobs[i].log2h <= 8) teamList[lo++] = i; else teamList[--hi] = i; }
+    nSmall = lo;
+  }
+  const int nLarge = n - nSmall;
+  if ((rc = tu_buf(ctx, 19, (size_t)n * sizeof(int)))) return rc;
+  CK(cudaMemcpyAsync(ctx->dTu[19], teamList.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  auto launch_tu = [&](TuParams Q) {
+    if (nSmall) {
+      Q.list = static_cast<const int*>(ctx->dTu[19]); Q.n = nSmall;
+      const int g = (nSmall + 3) / 4 < ctx->numSms * 8 ? (nSmall + 3) / 4 : ctx->numSms * 8;
+      tu_eval_kernel<32><<<g, kTuThreads, 0, ctx->stream>>>(Q);
+      ctx->launches++;
+    }
+    if (nLarge) {
+      Q.list = static_cast<const int*>(ctx->dTu[19]) + nSmall; Q.n = nLarge;
+      const int g = nLarge < ctx->numSms * 8 ? nLarge : ctx->numSms * 8;
+      tu_eval_kernel<128><<<g, kTuThreads, 0, ctx->stream>>>(Q);
+      ctx->launches++;
+    }
+  };
   if (nDq || nTs) {
     CK(cudaMemsetAsync(ctx->dTu[4], 0, n_samples * sizeof(int32_t), ctx->stream));     // levels / dequantised coefficients the
     CK(cudaMemsetAsync(ctx->dTu[8], 0, n_samples * sizeof(int32_t), ctx->stream));     // quantiser kernels do not reach stay zero
@@ -667,8 +691,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     CK(cudaMemcpyAsync(ctx->dTu[10], rates, (size_t)n_rates * sizeof(vvcb_dq_rates), cudaMemcpyHostToDevice, ctx->stream));
   }
   if (tm && !src) CK(cudaEventRecord(ctx->tev[0], ctx->stream));
-  tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
-  ctx->launches++;
+  launch_tu(P);
   if (tm) CK(cudaEventRecord(ctx->tev[1], ctx->stream));
   if (nDq) {
     dq_rate_kernel<<<n_rates, 32, 0, ctx->stream>>>(static_cast<const vvcb_dq_rates*>(ctx->dTu[10]), n_rates, static_cast<DqRateTab*>(ctx->dTu[11]));
@@ -702,8 +725,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
   if (tm) CK(cudaEventRecord(ctx->tev[2], ctx->stream));
   if (nDq || nTs) {
     P.phase = 1;
-    tu_eval_kernel<<<grid, kTuThreads, 0, ctx->stream>>>(P);
-    ctx->launches++;
+    launch_tu(P);
   }
   if (tm) CK(cudaEventRecord(ctx->tev[3], ctx->stream));
   if (nRate) {                                                     // levels are final: price them (CABACWriter::residual_coding on the estimator)

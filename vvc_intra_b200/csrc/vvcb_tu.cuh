@@ -68,17 +68,24 @@ __device__ __forceinline__ int lfnst_scan_pos(const TrRom& rom, int j, int w)
   return y * w + x;
 }
 
-// forward LFNST in place on the block A (stride w); tmp: 96 ints of scratch.  All threads of the CTA call it.
+// A job is worked on by a TEAM of NT threads: the whole 128-thread CTA for large blocks, one warp (four jobs per CTA) for blocks of up
+// to 256 samples, where 128 threads would mostly idle at barriers.
+template <int NT> __device__ __forceinline__ int team_tid() { return NT == 32 ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
+template <int NT> __device__ __forceinline__ void team_sync() { if (NT == 32) __syncwarp(); else __syncthreads(); }
+
+// forward LFNST in place on the block A (stride w); tmp: 96 ints of scratch.  All threads of the team call it.
+template <int NT>
 __device__ __forceinline__ void lfnst_forward(const TrRom& rom, const LfnstGeom& g, int* A, int w, int* tmp)
 {
   int* in = tmp; int* out = tmp + 48;
-  __syncthreads();
-  for (int t = threadIdx.x; t < g.sb * g.sb; t += blockDim.x) {
+  const int tid = team_tid<NT>();
+  team_sync<NT>();
+  for (int t = tid; t < g.sb * g.sb; t += NT) {
     const int x = t % g.sb, y = t / g.sb;
     if (x < 4 || y < 4) in[lfnst_vec_index(g, x, y)] = A[y * w + x];
   }
-  __syncthreads();
-  for (int j = threadIdx.x; j < g.trSize; j += blockDim.x) {
+  team_sync<NT>();
+  for (int j = tid; j < g.trSize; j += NT) {
     int v = 0;
     if (j < g.zeroOut) {
       int acc = 0;
@@ -87,29 +94,31 @@ __device__ __forceinline__ void lfnst_forward(const TrRom& rom, const LfnstGeom&
     }
     out[j] = v;
   }
-  __syncthreads();
-  for (int j = threadIdx.x; j < (g.sb == 4 ? 16 : 48); j += blockDim.x) A[lfnst_scan_pos(rom, j, w)] = out[j];
-  __syncthreads();
+  team_sync<NT>();
+  for (int j = tid; j < (g.sb == 4 ? 16 : 48); j += NT) A[lfnst_scan_pos(rom, j, w)] = out[j];
+  team_sync<NT>();
 }
 
 // inverse LFNST in place (CL/TrQuant.cpp:262-286, 316-435)
+template <int NT>
 __device__ __forceinline__ void lfnst_inverse(const TrRom& rom, const LfnstGeom& g, int* A, int w, int* tmp)
 {
   int* in = tmp; int* out = tmp + 48;
-  __syncthreads();
-  for (int i = threadIdx.x; i < 16; i += blockDim.x) in[i] = A[lfnst_scan_pos(rom, i, w)];
-  __syncthreads();
-  for (int j = threadIdx.x; j < g.trSize; j += blockDim.x) {
+  const int tid = team_tid<NT>();
+  team_sync<NT>();
+  for (int i = tid; i < 16; i += NT) in[i] = A[lfnst_scan_pos(rom, i, w)];
+  team_sync<NT>();
+  for (int j = tid; j < g.trSize; j += NT) {
     int acc = 0;
     for (int i = 0; i < g.zeroOut; i++) acc += in[i] * (int)g.mat[i * g.trSize + j];
     out[j] = vmin(vmax((acc + 64) >> 7, -32768), 32767);
   }
-  __syncthreads();
-  for (int t = threadIdx.x; t < g.sb * g.sb; t += blockDim.x) {
+  team_sync<NT>();
+  for (int t = tid; t < g.sb * g.sb; t += NT) {
     const int x = t % g.sb, y = t / g.sb;
     if (x < 4 || y < 4) A[y * w + x] = out[lfnst_vec_index(g, x, y)];
   }
-  __syncthreads();
+  team_sync<NT>();
 }
 
 
@@ -123,7 +132,8 @@ constexpr int kTuThreads = 128;
 
 struct TuParams {
   const vvcb_tu_job* jobs;
-  int n;
+  const int* list;     // indices of the jobs this launch works on
+  int n;               // their number
   const int16_t* resi;
   const int16_t* pred;
   int32_t* coeff;      // optional
@@ -142,14 +152,16 @@ struct TuParams {
 
 __device__ __forceinline__ int clip16(int v) { return vmin(vmax(v, -32768), 32767); }
 
-// block-wide sum of one int per thread (result valid in every thread)
-__device__ __forceinline__ long long block_sum(long long v, long long* red)
+// team-wide sum of one value per thread (result valid in every thread)
+template <int NT>
+__device__ __forceinline__ long long team_sum(long long v, long long* red)
 {
   for (int o = 16; o > 0; o >>= 1) {
     const int lo = __shfl_xor_sync(0xffffffffu, (int)(v & 0xffffffffll), o);
     const int hi = __shfl_xor_sync(0xffffffffu, (int)(v >> 32), o);
     v += ((long long)hi << 32) | (unsigned)lo;
   }
+  if (NT == 32) return v;
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
@@ -158,13 +170,22 @@ __device__ __forceinline__ long long block_sum(long long v, long long* red)
   return t;
 }
 
+constexpr int kTuSmallSamples = 256;      // blocks up to this size are worked on by one warp
+constexpr int kTuSmallB = 288;            // their transposed intermediate: kept columns x (height + 1), largest for 32x8
+
+template <int NT>
 __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
 {
-  __shared__ int A[64 * 64];
-  __shared__ int B[32 * 65];
+  constexpr int TEAMS = kTuThreads / NT;
+  __shared__ int sA[NT == 32 ? TEAMS * kTuSmallSamples : 64 * 64];
+  __shared__ int sB[NT == 32 ? TEAMS * kTuSmallB : 32 * 65];
   __shared__ long long red[kTuThreads / 32];
+  const int team = NT == 32 ? (int)(threadIdx.x >> 5) : 0, tid = team_tid<NT>();
+  int* A = sA + (NT == 32 ? team * kTuSmallSamples : 0);
+  int* B = sB + (NT == 32 ? team * kTuSmallB : 0);
   const TrRom& rom = *P.rom;
-  for (int ji = blockIdx.x; ji < P.n; ji += gridDim.x) {
+  for (int q = blockIdx.x * TEAMS + team; q < P.n; q += gridDim.x * TEAMS) {
+    const int ji = P.list[q];
     const vvcb_tu_job job = P.jobs[ji];
     const int lw = job.log2w, lh = job.log2h, w = 1 << lw, h = 1 << lh, n = w * h;
     const bool ts = job.mts_idx == 1;
@@ -185,17 +206,17 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
     // jobs whose quantiser is a kernel of its own (dependent quantisation, RDOQ for transform skip): vvcb_dq.cuh
     const bool dq = (job.flags & VVCB_TU_QUANT) && (job.flags & (VVCB_TU_DEPQUANT | VVCB_TU_RDOQ_TS));
     if (P.phase == 1 && !dq) continue;
-    __syncthreads();
+    team_sync<NT>();
     if (P.phase == 1) {
-      for (int i = threadIdx.x; i < n; i += kTuThreads) A[i] = P.dqDeq[job.offset + i];
-      __syncthreads();
+      for (int i = tid; i < n; i += NT) A[i] = P.dqDeq[job.offset + i];
+      team_sync<NT>();
     } else {
-    for (int i = threadIdx.x; i < n; i += kTuThreads) A[i] = ts ? ((int)resi[i] << trShift) : (int)resi[i];
-    __syncthreads();
+    for (int i = tid; i < n; i += NT) A[i] = ts ? ((int)resi[i] << trShift) : (int)resi[i];
+    team_sync<NT>();
     if (!ts) {
       const int shift1 = lw + P.bd + 6 - 15, shift2 = lh + 6;
       const int add1 = shift1 > 0 ? 1 << (shift1 - 1) : 0, add2 = 1 << (shift2 - 1);
-      for (int o = threadIdx.x; o < wKeep * h; o += kTuThreads) {          // rows: B[k][j]
+      for (int o = tid; o < wKeep * h; o += NT) {          // rows: B[k][j]
         const int k = o % wKeep, j = o / wKeep;
         const int16_t* m = mh + k * w;
         const int* a = A + j * w;
@@ -203,8 +224,8 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
         for (int t = 0; t < w; t++) acc += (int)m[t] * a[t];
         B[k * hp + j] = (acc + add1) >> shift1;
       }
-      __syncthreads();
-      for (int o = threadIdx.x; o < n; o += kTuThreads) {                 // columns: A[l][k]
+      team_sync<NT>();
+      for (int o = tid; o < n; o += NT) {                 // columns: A[l][k]
         const int k = o & (w - 1), l = o >> lw;
         int v = 0;
         if (k < wKeep && l < hKeep) {
@@ -216,21 +237,21 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
         }
         A[o] = v;
       }
-      __syncthreads();
-      if (lf.on) lfnst_forward(rom, lf, A, w, B);
+      team_sync<NT>();
+      if (lf.on) lfnst_forward<NT>(rom, lf, A, w, B);
     }
     }
     long long sumAbs = 0;
     if (P.phase == 0) {
       long long part = 0;
-      for (int i = threadIdx.x; i < n; i += kTuThreads) {
+      for (int i = tid; i < n; i += NT) {
         part += vabs(A[i]);
         if (P.coeff) P.coeff[job.offset + i] = A[i];
         if (dq) P.dqCoeff[job.offset + i] = A[i];
       }
-      sumAbs = block_sum(part, red);
+      sumAbs = team_sum<NT>(part, red);
       if (dq) {                                                          // the quantiser is another kernel: finish in pass 1
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
           vvcb_tu_result r;
           r.abs_sum_coeff = (int)__dmul_rn((double)(int)sumAbs, ts && ((lw + lh) & 1) ? 1.0 / 1.414213562 : 1.0);   // CL/TrQuant.cpp:1098-1102
           r.abs_sum_level = 0; r.sse = 0; r.frac_bits = 0;
@@ -252,7 +273,7 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
       const int inMin = -(1 << (tgt - 1)), inMax = (1 << (tgt - 1)) - 1;
       long long lpart = 0;
       if (P.phase == 0)
-      for (int i = threadIdx.x; i < n; i += kTuThreads) {
+      for (int i = tid; i < n; i += NT) {
         const int c = A[i];
         const long long t = (long long)vabs(c) * qScale;
         const int mag = (int)((t + qadd) >> qbits);
@@ -265,22 +286,22 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
         else                d = (int)((unsigned)(qc * iScale) << (-rightShift));
         A[i] = clip16(d);
       }
-      absLevel = (int)block_sum(lpart, red);
+      absLevel = (int)team_sum<NT>(lpart, red);
       const int16_t* pred = P.pred + job.offset;
       const int16_t* org = P.orig + (size_t)job.y * P.stride + job.x;
       const int maxv = (1 << P.bd) - 1;
       long long spart = 0;
       if (!ts) {
         const int shift2 = 20 - P.bd;
-        if (lf.on) lfnst_inverse(rom, lf, A, w, B);
-        for (int o = threadIdx.x; o < wKeep * h; o += kTuThreads) {        // columns first: B[j][y]
+        if (lf.on) lfnst_inverse<NT>(rom, lf, A, w, B);
+        for (int o = tid; o < wKeep * h; o += NT) {        // columns first: B[j][y]
           const int j = o % wKeep, y = o / wKeep;
           int acc = 0;
           for (int k = 0; k < hKeep; k++) acc += (int)mv[k * h + y] * A[k * w + j];
           B[j * hp + y] = clip16((acc + 64) >> 7);
         }
-        __syncthreads();
-        for (int o = threadIdx.x; o < n; o += kTuThreads) {               // rows
+        team_sync<NT>();
+        for (int o = tid; o < n; o += NT) {               // rows
           const int x = o & (w - 1), y = o >> lw;
           int acc = 0;
           for (int k = 0; k < wKeep; k++) acc += (int)mh[k * w + x] * B[k * hp + y];
@@ -292,7 +313,7 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
         }
       } else {
         const int off = trShift == 0 ? 0 : 1 << (trShift - 1);
-        for (int o = threadIdx.x; o < n; o += kTuThreads) {
+        for (int o = tid; o < n; o += NT) {
           const int x = o & (w - 1), y = o >> lw;
           const int r = (int)(int16_t)((A[o] + off) >> trShift);
           const int rec = vmin(vmax((int)pred[o] + r, 0), maxv);
@@ -301,13 +322,13 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
           spart += (long long)d * d;
         }
       }
-      sse = (unsigned long long)block_sum(spart, red);
+      sse = (unsigned long long)team_sum<NT>(spart, red);
     }
     if (P.phase == 1) {
-      if (threadIdx.x == 0) P.results[ji].sse = sse;
+      if (tid == 0) P.results[ji].sse = sse;
       continue;
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       double scale = 1.0;
       if (ts && ((lw + lh) & 1)) scale = 1.0 / 1.414213562;               // CL/TrQuant.cpp:1098-1102
       vvcb_tu_result r;
