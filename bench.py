@@ -43,48 +43,76 @@ def synth_luma(frame):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe): NVML polled every few milliseconds from a
+    thread of this process (the timed region of the default run is ~150 ms, too short for `nvidia-smi -lms`); nvidia-smi as a fallback."""
+    REASONS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.stop, self.thread, self.smi = index, [], threading.Event(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((sm, self.max_sm, mask))
+            except Exception:
+                pass
+            self.stop.wait(0.004)
+
+    def _read_smi(self):
+        for line in self.smi.stdout:
+            c = [x.strip() for x in line.split(',')]
+            try:
+                mask = sum(bit for (_, bit), v in zip(self.REASONS, c[2:6]) if v.lower().startswith('active'))
+                self.rows.append((float(c[0]), float(c[1]), mask))
+            except (ValueError, IndexError):
+                continue
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
+        else:
+            try:
+                q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+                     'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+                self.smi = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '20'],
+                                            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._read_smi, daemon=True)
+                self.thread.start()
+            except OSError:
+                self.smi = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
-
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
+        self.stop.set()
+        if self.smi:
+            time.sleep(0.05)
+            self.smi.terminate()
+        if self.thread:
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        if not sm:
+        if not self.rows:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+        mask = 0
+        for r in self.rows:
+            mask |= r[2]
+        return {'sm_mhz': statistics.median(r[0] for r in self.rows), 'sm_max_mhz': max(r[1] for r in self.rows),
+                'reasons': sorted(name for name, bit in self.REASONS if mask & bit), 'samples': len(self.rows),
+                'source': 'nvml' if self.nv is not None else 'nvidia-smi'}
 
 
 def measured_peaks():
