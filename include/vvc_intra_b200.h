@@ -154,6 +154,9 @@ int vvcb_rmd_eval_device(vvcb_ctx* ctx, const void* d_visits, int n, void* d_res
 
 /* Prediction samples of one evaluation slot (debug / parity): writes w*h samples.               */
 int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t* pred);
+/* ... of every evaluation slot at once: pred[VVCB_NUM_SLOTS][h][w]; slots the visit does not evaluate are left untouched.  What a
+ * host shim at seam S3 (IntraPrediction::predIntraAng / predIntraMip, CL/IntraPrediction.h:176-191) fetches once per visit.        */
+int vvcb_rmd_pred_all(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int16_t* pred);
 
 /* ---- TU coding: forward transform, MTS pre-selection sums, scalar quantisation, inverse, reconstruction, SSE ----
  * One job = one candidate transform of one luma TU, i.e. one pass of IntraSearch::xIntraCodingTUBlock

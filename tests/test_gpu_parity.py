@@ -534,3 +534,34 @@ def test_tu_stage_returns_residual_bits(bd, seed, eng8, eng10):
     assert (out['results']['frac_bits'] > 0).sum() > len(items) // 3
     # the stand-alone entry point on the same levels
     assert eng.residual_bits(jobs, out['level'], states).tolist() == out['results']['frac_bits'].tolist()
+
+
+# ---- the unmodified reference encoder with the engine plugged in ---------------------------------------------
+@pytest.mark.parametrize('w,h,bits,qp', [(128, 64, 8, 32), (128, 128, 10, 27)])
+def test_reference_encoder_with_gpu_rmd_is_bit_identical(w, h, bits, qp, tmp_path):
+    """Drop-in check at the reference's own seam: oracle/_ref/EncoderAppGpu is the unmodified reference encoder linked (ld --wrap,
+    oracle/ref_gpu_shim.cpp) so that every rough-mode-decision prediction comes from libvvc_intra_b200.so and every candidate list the
+    reference builds is compared with vvcb_rmd_eval's.  The shim aborts on the first difference; the bitstream must be byte-identical
+    to the plain reference encoder's."""
+    import json
+    import os
+    import subprocess
+    from make_golden import synth_yuv
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    plain, plugged, cfg = (os.path.join(root, 'oracle/_ref', f) for f in ('EncoderApp', 'EncoderAppGpu', 'encoder_intra.cfg'))
+    if not all(os.path.exists(p) for p in (plain, plugged, cfg)):
+        pytest.skip('oracle/_ref binaries are built only in the container that has /root/reference')
+    Y, U, V = synth_yuv(w, h, bits)
+    (tmp_path / 'in.yuv').write_bytes(Y.tobytes() + U.tobytes() + V.tobytes())
+    (tmp_path / 'Time_python.dat').write_bytes(b'')
+    args = ['-c', cfg, '-i', 'in.yuv', '-wdt', str(w), '-hgt', str(h), '-q', str(qp), '-f', '1', '-fr', '30',
+            '--InputBitDepth=%d' % bits, '--InternalBitDepth=%d' % bits, '--OutputBitDepth=%d' % bits]
+    env = dict(os.environ, VVCB_SHIM_REPORT=str(tmp_path / 'report.json'))
+    r1 = subprocess.run([plain] + args + ['-b', 'plain.bin'], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r1.returncode == 0, r1.stdout[-2000:]
+    r2 = subprocess.run([plugged] + args + ['-b', 'gpu.bin'], cwd=tmp_path, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r2.returncode == 0, r2.stdout[-2000:]
+    a, b = (tmp_path / 'plain.bin').read_bytes(), (tmp_path / 'gpu.bin').read_bytes()
+    assert len(a) > 100 and a == b
+    rep = json.loads((tmp_path / 'report.json').read_text())
+    assert rep['mismatches'] == 0 and rep['visits'] > 200 and rep['lists_compared'] == rep['visits'] and rep['predictions_replaced'] > 40 * rep['visits']

@@ -499,18 +499,22 @@ extern "C" int vvcb_rmd_eval_device(vvcb_ctx* ctx, const void* d_visits, int n, 
                     static_cast<vvcb_rmd_detail*>(d_details), nullptr);
 }
 
-extern "C" int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t* pred)
+// slot >= 0: the prediction of that slot (w*h samples); slot < 0: all VVCB_NUM_SLOTS predictions back to back (slots the visit does
+// not evaluate are left untouched)
+static int rmd_pred_impl(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t* pred)
 {
   if (!ctx) return VVCB_ERR_ARG;
-  if (!visit || !pred || slot < 0 || slot >= VVCB_NUM_SLOTS) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: bad argument"); return VVCB_ERR_ARG; }
+  if (!visit || !pred || slot >= VVCB_NUM_SLOTS) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: bad argument"); return VVCB_ERR_ARG; }
   if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: no frame"); return VVCB_ERR_STATE; }
   int rc = check_visits(ctx, visit, 1);
   if (rc) return rc;
   const int w = 1 << visit->log2w, h = 1 << visit->log2h;
   const bool mrlAllowed = !(visit->flags & VVCB_VISIT_NO_MRL) && (visit->y & (ctx->ctu - 1)) != 0;
   const int numMip = (visit->flags & VVCB_VISIT_NO_MIP) ? 0 : mip_num_modes(w, h);
-  const bool evaluated = slot < VVCB_SLOT_MRL1 || (slot < VVCB_SLOT_MIP ? mrlAllowed : slot - VVCB_SLOT_MIP < numMip);
-  if (!evaluated) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: slot %d is not evaluated for this visit", slot); return VVCB_ERR_ARG; }
+  if (slot >= 0) {
+    const bool evaluated = slot < VVCB_SLOT_MRL1 || (slot < VVCB_SLOT_MIP ? mrlAllowed : slot - VVCB_SLOT_MIP < numMip);
+    if (!evaluated) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: slot %d is not evaluated for this visit", slot); return VVCB_ERR_ARG; }
+  }
   CK(cudaSetDevice(ctx->device));
   rc = ensure_visit_buffers(ctx, 1);
   if (rc) return rc;
@@ -523,10 +527,19 @@ extern "C" int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slo
   CK(cudaMemcpyAsync(ctx->dVisits, visit, sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
   rc = launch_rmd(ctx, ctx->dVisits, 1, ctx->dResults, nullptr, ctx->dPred);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(pred, ctx->dPred + (size_t)slot * w * h, (size_t)w * h * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (slot >= 0) CK(cudaMemcpyAsync(pred, ctx->dPred + (size_t)slot * w * h, (size_t)w * h * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  else           CK(cudaMemcpyAsync(pred, ctx->dPred, need * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return VVCB_OK;
 }
+
+extern "C" int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t* pred)
+{
+  if (ctx && slot < 0) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: bad argument"); return VVCB_ERR_ARG; }
+  return rmd_pred_impl(ctx, visit, slot, pred);
+}
+
+extern "C" int vvcb_rmd_pred_all(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int16_t* pred) { return rmd_pred_impl(ctx, visit, -1, pred); }
 
 static int tu_buf(vvcb_ctx* ctx, int i, size_t bytes)
 {

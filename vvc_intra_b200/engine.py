@@ -90,6 +90,7 @@ def load_library():
         L.vvcb_rmd_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.vvcb_rmd_eval_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.vvcb_rmd_pred.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.vvcb_rmd_pred_all.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.vvcb_dev_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.vvcb_dev_free.argtypes = [C.c_void_p, C.c_void_p]
         L.vvcb_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
@@ -201,6 +202,14 @@ class IntraCostEngine:
         w, h = 1 << int(visit[0]['log2w']), 1 << int(visit[0]['log2h'])
         pred = np.zeros((h, w), np.int16)
         self._ck(self._lib.vvcb_rmd_pred(self._ctx, _ptr(visit), slot, _ptr(pred)))
+        return pred
+
+    def rmd_pred_all(self, visit):
+        """vvcb_rmd_pred_all: (NUM_SLOTS, h, w) prediction samples of one visit."""
+        visit = np.ascontiguousarray(visit, VISIT_DTYPE).reshape(1)
+        w, h = 1 << int(visit['log2w'][0]), 1 << int(visit['log2h'][0])
+        pred = np.zeros((NUM_SLOTS, h, w), np.int16)
+        self._ck(self._lib.vvcb_rmd_pred_all(self._ctx, _ptr(visit), _ptr(pred)))
         return pred
 
     # ---- TU coding
