@@ -12,6 +12,13 @@
 //      from GPU predictions,
 //   4. on return compares the engine's RD / HAD / full-RD candidate lists (modes and IEEE-double costs) with the ones the
 //      reference saved (m_uiSavedRdModeListLFNST, m_dSavedModeCostLFNST, m_uiSavedHadModeListLFNST, m_savedRdModeList).
+//   5. TU coding (seam S2 / a11-a14): for every luma TU without ISP / BDPCM, TrQuant::transformNxN(trModes) -- the MTS pre-selection -- is
+//      repeated by vvcb_tu_eval (coefficients of every candidate transform, the pre-selection sums, vvcb_mts_preselect) and
+//      TrQuant::transformNxN(quant) by vvcb_tu_eval with the quantiser the reference runs (dependent quantisation with the context prices
+//      of the estimator snapshot, or RDOQ for transform skip; LFNST included): coefficients, levels and absSum must be identical, the
+//      encoder goes on with the engine's levels, and the engine's reconstruction is compared with what invTransformNxN + reconstruct
+//      produce afterwards,
+//   6. CABACWriter::residual_coding on the bit estimator is repeated by vvcb_residual_bits from the estimator's context states.
 // Any difference aborts the encoder.  At exit a summary goes to $VVCB_SHIM_REPORT.  tests/test_gpu_parity.py runs the result
 // (oracle/_ref/EncoderAppGpu, built by oracle/Makefile.ref in the container that has /root/reference) next to the plain
 // oracle/_ref/EncoderApp and requires byte-identical bitstreams.
@@ -84,6 +91,11 @@ vvcb_rmd_detail      g_det;
 std::vector<int16_t> g_pred;              // [VVCB_NUM_SLOTS][h][w] of the current visit
 int                  g_w = 0, g_h = 0;
 long                 g_visits = 0, g_preds = 0, g_lists = 0;
+long                 g_tuPre = 0, g_tuPreCand = 0, g_tuQuant = 0, g_tuQuantDq = 0, g_tuQuantTs = 0, g_tuQuantLfnst = 0, g_tuReco = 0, g_tuBits = 0;
+const bool           g_serveTu = !getenv( "VVCB_SHIM_NO_TU" );
+
+// the TU whose quantisation the engine has just repeated: its prediction and the engine's reconstruction wait for invTransformNxN
+struct PendingTu { const TransformUnit* tu = nullptr; int x = 0, y = 0, w = 0, h = 0; std::vector<int16_t> pred, reco; } g_pend;
 
 void die( const char* what, const char* detail = "" )
 {
@@ -102,10 +114,29 @@ void report()
   if( const char* p = getenv( "VVCB_SHIM_REPORT" ) )
     if( FILE* f = fopen( p, "w" ) )
     {
-      fprintf( f, "{\"visits\": %ld, \"predictions_replaced\": %ld, \"lists_compared\": %ld, \"mismatches\": 0}\n", g_visits, g_preds, g_lists );
+      fprintf( f, "{\"visits\": %ld, \"predictions_replaced\": %ld, \"lists_compared\": %ld, \"tu_preselections\": %ld, \"tu_preselection_candidates\": %ld, "
+                  "\"tu_quantised\": %ld, \"tu_dep_quant\": %ld, \"tu_rdoq_ts\": %ld, \"tu_lfnst\": %ld, \"tu_reconstructions\": %ld, \"tu_residual_bits\": %ld, \"mismatches\": 0}\n",
+               g_visits, g_preds, g_lists, g_tuPre, g_tuPreCand, g_tuQuant, g_tuQuantDq, g_tuQuantTs, g_tuQuantLfnst, g_tuReco, g_tuBits );
       fclose( f );
     }
   if( g_gpu ) vvcb_destroy( g_gpu );
+}
+
+void ensureFrame( const CodingStructure& cs )
+{
+  const SPS& sps = *cs.sps;
+  if( !g_gpu )
+  {
+    if( vvcb_create( &g_gpu, 0, sps.getBitDepth( CHANNEL_TYPE_LUMA ), sps.getMaxCUWidth() ) != VVCB_OK ) die( "vvcb_create:", vvcb_last_error( nullptr ) );
+    gpuCheck( vvcb_set_option( g_gpu, VVCB_OPT_DEP_QUANT, cs.slice->getDepQuantEnabledFlag() ? 1 : 0 ), "vvcb_set_option:" );
+    atexit( report );
+  }
+  if( cs.slice->getPOC() != g_poc )
+  {
+    g_poc = cs.slice->getPOC();
+    const CPelBuf org = cs.picture->getOrigBuf( COMPONENT_Y );         // constant during the CTU loop (EL/EncGOP.cpp:1692)
+    gpuCheck( vvcb_frame_begin( g_gpu, org.buf, org.stride, org.width, org.height ), "vvcb_frame_begin:" );
+  }
 }
 
 bool unitAvail( const CodingStructure& cs, const CodingUnit& cu, const Position& p )
@@ -168,17 +199,7 @@ bool __wrap__ZN11IntraSearch18estIntraPredLumaQTER10CodingUnitR11Partitionerdbii
 
   if( rmdRuns )
   {
-    if( !g_gpu )
-    {
-      if( vvcb_create( &g_gpu, 0, sps.getBitDepth( CHANNEL_TYPE_LUMA ), sps.getMaxCUWidth() ) != VVCB_OK ) die( "vvcb_create:", vvcb_last_error( nullptr ) );
-      atexit( report );
-    }
-    if( cs.slice->getPOC() != g_poc )
-    {
-      g_poc = cs.slice->getPOC();
-      const CPelBuf org = cs.picture->getOrigBuf( COMPONENT_Y );         // constant during the CTU loop (EL/EncGOP.cpp:1692)
-      gpuCheck( vvcb_frame_begin( g_gpu, org.buf, org.stride, org.width, org.height ), "vvcb_frame_begin:" );
-    }
+    ensureFrame( cs );
     PredictionUnit& pu = *cu.firstPU;
     const Position lt = pu.Y();
     vvcb_rmd_visit& v = g_visit;
@@ -278,17 +299,202 @@ void __wrap__ZN15IntraPrediction12predIntraMipE11ComponentIDR7AreaBufIsERK14Pred
   if( g_inRmd && c == COMPONENT_Y ) servePrediction( pred, pu, true );
 }
 
-// the RMD block of a visit ends where its first TU is coded
+} // extern "C"
+
+// ---- TU coding (a11-a14) -------------------------------------------------------------------------------------------------------
+namespace {
+
+bool tuServed( const TransformUnit& tu, ComponentID c )
+{
+  return g_serveTu && c == COMPONENT_Y && !tu.noResidual && !tu.cu->ispMode && !tu.cu->bdpcmMode && CU::isIntra( *tu.cu );
+}
+
+void denseResidualAndPrediction( const TransformUnit& tu, std::vector<int16_t>& resi, std::vector<int16_t>& pred )
+{
+  const CompArea& rect = tu.blocks[COMPONENT_Y];
+  const CPelBuf r = tu.cs->getResiBuf( rect );
+  const CPelBuf o = tu.cs->picture->getOrigBuf( COMPONENT_Y );
+  const int w = rect.width, h = rect.height;
+  resi.resize( w * h ); pred.resize( w * h );
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ )
+    {
+      resi[y * w + x] = r.at( x, y );
+      pred[y * w + x] = o.at( rect.x + x, rect.y + y ) - r.at( x, y );     // resi = org - pred (EL/IntraSearch.cpp:2922)
+    }
+}
+
+void fillJobGeometry( vvcb_tu_job& j, const TransformUnit& tu )
+{
+  const CompArea& rect = tu.blocks[COMPONENT_Y];
+  memset( &j, 0, sizeof( j ) );
+  j.x = rect.x; j.y = rect.y; j.log2w = floorLog2( rect.width ); j.log2h = floorLog2( rect.height );
+}
+
+void fillRates( vvcb_dq_rates& out, const Ctx& ctx )
+{
+  const FracBitsAccess& fb = ctx.getFracBitsAcess();
+  uint32_t* p = reinterpret_cast<uint32_t*>( &out );
+  auto put = [&]( const CtxSet& set, int num ) { for( int i = 0; i < num; i++ ) { const BinFracBits b = fb.getFracBitsArray( set( i ) ); *p++ = b.intBits[0]; *p++ = b.intBits[1]; } };
+  put( Ctx::SigCoeffGroup[CHANNEL_TYPE_LUMA], 2 );
+  for( int st = 0; st < 3; st++ ) put( Ctx::SigFlag[CHANNEL_TYPE_LUMA + 2 * st], 12 );
+  put( Ctx::ParFlag[CHANNEL_TYPE_LUMA], 21 ); put( Ctx::GtxFlag[2 + CHANNEL_TYPE_LUMA], 21 ); put( Ctx::GtxFlag[CHANNEL_TYPE_LUMA], 21 );
+  put( Ctx::LastX[CHANNEL_TYPE_LUMA], 20 ); put( Ctx::LastY[CHANNEL_TYPE_LUMA], 20 );
+  put( Ctx::TsSigCoeffGroup, 3 ); put( Ctx::TsSigFlag, 3 ); put( Ctx::TsParFlag, 1 ); put( Ctx::TsGtxFlag, 5 ); put( Ctx::TsLrg1Flag, 4 ); put( Ctx::TsResidualSign, 6 );
+  if( (char*) p != (char*) &out + sizeof( out ) ) die( "vvcb_dq_rates layout" );
+}
+
+void fillStates( vvcb_ctx_states& out, const Ctx& ctx )
+{
+  vvcb_bin_model* p = reinterpret_cast<vvcb_bin_model*>( &out );
+  auto put = [&]( const CtxSet& set, int num ) { for( int i = 0; i < num; i++ ) { const BinProbModel_Std& m = ctx.m_CtxStore_Std[set( i )]; p->state[0] = m.m_state[0]; p->state[1] = m.m_state[1]; p->rate = m.m_rate; p->pad = 0; p++; } };
+  put( Ctx::MTSIndex, 11 );
+  put( Ctx::SigCoeffGroup[CHANNEL_TYPE_LUMA], 2 );
+  for( int k = 0; k < 3; k++ ) put( Ctx::SigFlag[CHANNEL_TYPE_LUMA + 2 * k], 12 );
+  put( Ctx::ParFlag[CHANNEL_TYPE_LUMA], 21 ); put( Ctx::GtxFlag[2 + CHANNEL_TYPE_LUMA], 21 ); put( Ctx::GtxFlag[CHANNEL_TYPE_LUMA], 21 );
+  put( Ctx::LastX[CHANNEL_TYPE_LUMA], 20 ); put( Ctx::LastY[CHANNEL_TYPE_LUMA], 20 );
+  put( Ctx::TsSigCoeffGroup, 3 ); put( Ctx::TsSigFlag, 3 ); put( Ctx::TsParFlag, 1 ); put( Ctx::TsGtxFlag, 5 ); put( Ctx::TsLrg1Flag, 4 ); put( Ctx::TsResidualSign, 6 );
+  if( (char*) p != (char*) &out + sizeof( out ) ) die( "vvcb_ctx_states layout" );
+}
+
+} // namespace
+
+extern "C" {
+
+void __real__ZN7TrQuant15invTransformNxNER13TransformUnitRK11ComponentIDR7AreaBufIsERK7QpParam( TrQuant*, TransformUnit&, const ComponentID&, PelBuf&, const QpParam& );
+void __real__ZN11CABACWriter15residual_codingERK13TransformUnit11ComponentIDP5CUCtx( CABACWriter*, const TransformUnit&, ComponentID, CUCtx* );
+
+// TrQuant::transformNxN(trModes), CL/TrQuant.cpp:1049-1124: every candidate transform of the TU + the pre-selection.  (The RMD block of a
+// visit ends where its first TU is coded.)
 void __wrap__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamPSt6vectorISt4pairIibESaISA_EEi( TrQuant* tq, TransformUnit& tu, const ComponentID& c, const QpParam& qp, std::vector<TrMode>* modes, int maxCand )
 {
   g_inRmd = false;
+  const bool serve = tuServed( tu, c ) && tu.cu->lfnstIdx == 0 && !modes->empty();
+  std::vector<int16_t> resi, pred;
+  if( serve ) { ensureFrame( *tu.cs ); denseResidualAndPrediction( tu, resi, pred ); }
   __real__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamPSt6vectorISt4pairIibESaISA_EEi( tq, tu, c, qp, modes, maxCand );
+  if( !serve ) return;
+  const CompArea& rect = tu.blocks[c];
+  const int n = rect.width * rect.height, k = (int) modes->size();
+  std::vector<vvcb_tu_job> jobs( k );
+  std::vector<int16_t> resiAll( (size_t) n * k );
+  for( int i = 0; i < k; i++ )
+  {
+    fillJobGeometry( jobs[i], tu );
+    jobs[i].mts_idx = ( *modes )[i].first;
+    jobs[i].offset  = i * n;
+    memcpy( &resiAll[(size_t) i * n], resi.data(), n * sizeof( int16_t ) );
+  }
+  std::vector<int32_t> coeff( (size_t) n * k );
+  std::vector<vvcb_tu_result> res( k );
+  gpuCheck( vvcb_tu_eval( g_gpu, jobs.data(), k, resiAll.data(), nullptr, (size_t) n * k, nullptr, nullptr, 0, coeff.data(), nullptr, nullptr, res.data() ), "vvcb_tu_eval (pre-selection):" );
+  std::vector<int32_t> sums( k );
+  std::vector<uint8_t> sel( k );
+  for( int i = 0; i < k; i++ )
+  {
+    sums[i] = res[i].abs_sum_coeff;
+    if( memcmp( &coeff[(size_t) i * n], tq->m_mtsCoeffs[( *modes )[i].first], n * sizeof( int32_t ) ) ) die( "coefficients of a candidate transform differ from the reference's" );
+  }
+  vvcb_mts_preselect( sums.data(), k, rect.width, rect.height, maxCand, sel.data() );
+  for( int i = 0; i < k; i++ )
+    if( ( sel[i] != 0 ) != ( *modes )[i].second ) die( "MTS pre-selection differs from the reference's" );
+  g_tuPre++; g_tuPreCand += k;
 }
 
+// TrQuant::transformNxN(quant), CL/TrQuant.cpp:1127-1260: (forward transform, LFNST,) quantisation with the estimator's context prices
 void __wrap__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamRiRK3Ctxb( TrQuant* tq, TransformUnit& tu, const ComponentID& c, const QpParam& qp, TCoeff& absSum, const Ctx& ctx, bool loadTr )
 {
   g_inRmd = false;
+  g_pend.tu = nullptr;
+  const bool ts = tu.mtsIdx == MTS_SKIP;
+  const bool dq = tu.cs->slice->getDepQuantEnabledFlag() && !ts;
+  const bool serve = tuServed( tu, c ) && ( dq || ( ts && tq->m_quant->m_useRDOQ && tq->m_quant->m_useRDOQTS ) );
+  std::vector<int16_t> resi, pred;
+  if( serve ) { ensureFrame( *tu.cs ); denseResidualAndPrediction( tu, resi, pred ); }
   __real__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamRiRK3Ctxb( tq, tu, c, qp, absSum, ctx, loadTr );
+  if( !serve ) return;
+  const CompArea& rect = tu.blocks[c];
+  const int w = rect.width, h = rect.height, n = w * h;
+  vvcb_tu_job j;
+  fillJobGeometry( j, tu );
+  j.mts_idx = tu.mtsIdx;
+  j.flags   = VVCB_TU_QUANT | ( dq ? VVCB_TU_DEPQUANT : VVCB_TU_RDOQ_TS );
+  j.qp_per  = qp.per( ts ); j.qp_rem = qp.rem( ts );
+  j.lfnst_idx = ts ? 0 : tu.cu->lfnstIdx;
+  if( j.lfnst_idx )
+  {
+    const PredictionUnit& pu = *tu.cs->getPU( rect.pos(), CHANNEL_TYPE_LUMA );
+    j.intra_mode = PU::isMIP( pu, CHANNEL_TYPE_LUMA ) ? PLANAR_IDX : (int) PU::getFinalIntraMode( pu, CHANNEL_TYPE_LUMA );
+  }
+  const BinFracBits cbf = ctx.getFracBitsAcess().getFracBitsArray( Ctx::QtCbf[COMPONENT_Y]( DeriveCtx::CtxQtCbf( COMPONENT_Y, tu.cbf[COMPONENT_Cb] ) ) );
+  j.cbf_delta_bits = int32_t( cbf.intBits[1] ) - int32_t( cbf.intBits[0] );      // RateEstimator::xSetLastCoeffOffset, CL/DepQuant.cpp:531-540
+  j.lambda = tq->m_quant->getLambda();
+  static vvcb_dq_rates rates;
+  fillRates( rates, ctx );
+  std::vector<int32_t> coeff( n ), level( n );
+  g_pend.reco.resize( n );
+  vvcb_tu_result res;
+  gpuCheck( vvcb_tu_eval( g_gpu, &j, 1, resi.data(), pred.data(), n, &rates, nullptr, 1, coeff.data(), level.data(), g_pend.reco.data(), &res ), "vvcb_tu_eval (quantisation):" );
+  // coefficients: with LFNST the reference's buffer keeps stale values outside the top-left 8x8 / 4x4 (tests/test_oracle_lfnst.py)
+  const TCoeff* co = loadTr ? tq->m_mtsCoeffs[tu.mtsIdx] : tq->m_tempCoeff;
+  const int sb = j.lfnst_idx ? ( std::min( w, h ) >= 8 ? 8 : 4 ) : 1 << 30;
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ )
+      if( x < sb && y < sb ? coeff[y * w + x] != co[y * w + x] : ( j.lfnst_idx && coeff[y * w + x] != 0 ) ) die( "transform coefficients differ from the reference's" );
+  CoeffBuf lv = tu.getCoeffs( c );
+  for( int y = 0; y < h; y++ )
+    for( int x = 0; x < w; x++ )
+    {
+      if( lv.at( x, y ) != level[y * w + x] ) die( dq ? "dependent-quantisation levels differ from the reference's" : "transform-skip RDOQ levels differ from the reference's" );
+      lv.at( x, y ) = level[y * w + x];            // the encoder goes on with the engine's levels
+    }
+  if( res.abs_sum_level != absSum ) die( "absSum differs from the reference's" );
+  absSum = res.abs_sum_level;
+  g_tuQuant++; g_tuQuantDq += dq; g_tuQuantTs += !dq; g_tuQuantLfnst += j.lfnst_idx != 0;
+  if( absSum > 0 ) { g_pend.tu = &tu; g_pend.x = rect.x; g_pend.y = rect.y; g_pend.w = w; g_pend.h = h; g_pend.pred.swap( pred ); }
+}
+
+// TrQuant::invTransformNxN, CL/TrQuant.cpp:561 (+ PelBuf::reconstruct, EL/IntraSearch.cpp:3050): the engine's reconstruction of the TU it
+// has just quantised must equal clip( pred + inverse residual )
+void __wrap__ZN7TrQuant15invTransformNxNER13TransformUnitRK11ComponentIDR7AreaBufIsERK7QpParam( TrQuant* tq, TransformUnit& tu, const ComponentID& c, PelBuf& resi, const QpParam& qp )
+{
+  __real__ZN7TrQuant15invTransformNxNER13TransformUnitRK11ComponentIDR7AreaBufIsERK7QpParam( tq, tu, c, resi, qp );
+  if( c != COMPONENT_Y || g_pend.tu != &tu ) return;
+  const CompArea& rect = tu.blocks[c];
+  if( rect.x != g_pend.x || rect.y != g_pend.y || (int) rect.width != g_pend.w || (int) rect.height != g_pend.h || (int) resi.width != g_pend.w || (int) resi.height != g_pend.h ) { g_pend.tu = nullptr; return; }
+  const int maxv = ( 1 << tu.cs->sps->getBitDepth( CHANNEL_TYPE_LUMA ) ) - 1;
+  for( int y = 0; y < g_pend.h; y++ )
+    for( int x = 0; x < g_pend.w; x++ )
+    {
+      const int v = std::min( maxv, std::max( 0, g_pend.pred[y * g_pend.w + x] + resi.at( x, y ) ) );
+      if( v != g_pend.reco[y * g_pend.w + x] ) die( "reconstruction differs from the reference's" );
+    }
+  g_pend.tu = nullptr;
+  g_tuReco++;
+}
+
+// CABACWriter::residual_coding on the bit estimator (EL/CABACWriter.cpp:3773, from IntraSearch::xEncCoeffQT)
+void __wrap__ZN11CABACWriter15residual_codingERK13TransformUnit11ComponentIDP5CUCtx( CABACWriter* cw, const TransformUnit& tu, ComponentID c, CUCtx* cuCtx )
+{
+  const bool serve = g_serveTu && g_gpu && c == COMPONENT_Y && !cw->m_BinEncoder.isEncoding() && !tu.cu->ispMode && !tu.cu->bdpcmMode && CU::isIntra( *tu.cu );
+  static vvcb_ctx_states states;
+  uint64_t before = 0;
+  if( serve ) { fillStates( states, cw->getCtx() ); before = cw->m_BinEncoder.getEstFracBits(); }
+  __real__ZN11CABACWriter15residual_codingERK13TransformUnit11ComponentIDP5CUCtx( cw, tu, c, cuCtx );
+  if( !serve ) return;
+  const CompArea& rect = tu.blocks[c];
+  const int w = rect.width, h = rect.height;
+  vvcb_tu_job j;
+  fillJobGeometry( j, tu );
+  j.mts_idx = tu.mtsIdx;
+  j.flags   = ( TU::isTSAllowed( tu, c ) ? VVCB_TU_TS_ALLOWED : 0 ) | ( TU::isMTSAllowed( tu, c ) ? VVCB_TU_MTS_ALLOWED : 0 );
+  std::vector<int32_t> level( w * h );
+  const CCoeffBuf lv = tu.getCoeffs( c );
+  for( int y = 0; y < h; y++ ) for( int x = 0; x < w; x++ ) level[y * w + x] = lv.at( x, y );
+  uint64_t bits = 0;
+  gpuCheck( vvcb_residual_bits( g_gpu, &j, 1, level.data(), level.size(), &states, 1, &bits ), "vvcb_residual_bits:" );
+  if( bits != cw->m_BinEncoder.getEstFracBits() - before ) die( "residual bits differ from the reference's estimator" );
+  g_tuBits++;
 }
 
 } // extern "C"

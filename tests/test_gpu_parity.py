@@ -541,8 +541,10 @@ def test_tu_stage_returns_residual_bits(bd, seed, eng8, eng10):
 def test_reference_encoder_with_gpu_rmd_is_bit_identical(w, h, bits, qp, tmp_path):
     """Drop-in check at the reference's own seam: oracle/_ref/EncoderAppGpu is the unmodified reference encoder linked (ld --wrap,
     oracle/ref_gpu_shim.cpp) so that every rough-mode-decision prediction comes from libvvc_intra_b200.so and every candidate list the
-    reference builds is compared with vvcb_rmd_eval's.  The shim aborts on the first difference; the bitstream must be byte-identical
-    to the plain reference encoder's."""
+    reference builds is compared with vvcb_rmd_eval's; every luma TU (no ISP) is transformed, pre-selected, quantised (dependent quantisation,
+    transform-skip RDOQ, LFNST) and reconstructed by vvcb_tu_eval and priced by vvcb_residual_bits next to the reference, the encoder going
+    on with the engine's levels.  The shim aborts on the first difference; the bitstream must be byte-identical to the plain reference
+    encoder's."""
     import json
     import os
     import subprocess
@@ -565,3 +567,7 @@ def test_reference_encoder_with_gpu_rmd_is_bit_identical(w, h, bits, qp, tmp_pat
     assert len(a) > 100 and a == b
     rep = json.loads((tmp_path / 'report.json').read_text())
     assert rep['mismatches'] == 0 and rep['visits'] > 200 and rep['lists_compared'] == rep['visits'] and rep['predictions_replaced'] > 40 * rep['visits']
+    assert rep['tu_quantised'] > 1000 and rep['tu_dep_quant'] > 500 and rep['tu_rdoq_ts'] > 50 and rep['tu_lfnst'] > 100
+    assert rep['tu_preselections'] > 200 and rep['tu_preselection_candidates'] >= 2 * rep['tu_preselections']
+    assert rep['tu_reconstructions'] > 500 and rep['tu_residual_bits'] > 500
+    print('shim report', rep)
