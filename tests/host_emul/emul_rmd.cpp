@@ -49,9 +49,9 @@ void emu_launch(unsigned grid, unsigned block, const std::function<void()>& fn)
   }
 }
 
-template <int TILE, int KIND> static void emul_eval_bucket(const EvalParams& P)
+template <int TILE, int KIND, int MODE> static void emul_eval_bucket(const EvalParams& P)
 {
-  emu_launch(1, kThreads, [&] { rmd_eval_kernel<TILE, KIND>(P); });
+  emu_launch(1, EvalCfg<MODE == 1>::kThreads, [&] { rmd_eval_kernel<TILE, KIND, MODE>(P); });
 }
 
 extern "C" int emul_rmd_eval(const int16_t* orig, const int16_t* reco, int stride, int bd, int ctu,
@@ -63,17 +63,21 @@ extern "C" int emul_rmd_eval(const int16_t* orig, const int16_t* reco, int strid
   std::vector<WorkItem> items((size_t)n * 60 + 8);
   PlanState plan;
   memset(&plan, 0, sizeof(plan));
-  emu_launch((n + 255) / 256, 256, [&] { rmd_plan_count(visits, n, ctu, &plan); });
+  const int pack = predOut ? 0 : 1;
+  emu_launch((n + 255) / 256, 256, [&] { rmd_plan_count(visits, n, ctu, &plan, pack); });
   emu_launch(1, 32, [&] { rmd_plan_scan(&plan); });
-  emu_launch((n + 255) / 256, 256, [&] { rmd_plan_fill(visits, n, ctu, &plan, items.data()); });
+  emu_launch((n + 255) / 256, 256, [&] { rmd_plan_fill(visits, n, ctu, &plan, items.data(), pack); });
   EvalParams P;
   P.visits = visits; P.items = items.data(); P.plan = &plan;
   std::vector<uint32_t> sm((size_t)2 * VVCB_NUM_SLOTS * n);
   P.sadSM = sm.data(); P.satdSM = sm.data() + (size_t)VVCB_NUM_SLOTS * n; P.nVisits = n;
   P.orig = orig; P.reco = reco; P.stride = stride; P.bd = bd; P.ctu = ctu; P.rom = &rom; P.predOut = predOut;
   for (int b = 0; b < kNumBuckets; b++) {
-    if (!plan.count[b]) continue;
-    VVCB_FOR_BUCKET(b, emul_eval_bucket, P);
+    bool packed = false;
+    for (int i = 0; i < pack_shape_count(b / kNumKinds); i++) packed = packed || plan.count[kNumBuckets + pack_shape(b / kNumKinds, i) * kNumKinds + b % kNumKinds];
+    if (packed) VVCB_FOR_BUCKET(b, 1, emul_eval_bucket, P);
+    if (plan.count[b] && predOut) VVCB_FOR_BUCKET(b, 2, emul_eval_bucket, P);
+    if (plan.count[b] && !predOut) VVCB_FOR_BUCKET(b, 0, emul_eval_bucket, P);
   }
   if (details) emu_launch((n + 31) / 32, 256, [&] { rmd_detail_kernel(visits, n, ctu, details, P.sadSM, P.satdSM); });
   emu_launch((n + kListThreads - 1) / kListThreads, kListThreads, [&] { rmd_lists_kernel(visits, n, ctu, results, details, P.sadSM, P.satdSM); });

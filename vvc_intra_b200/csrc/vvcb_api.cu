@@ -294,9 +294,14 @@ static int ensure_details(vvcb_ctx* ctx, int n)
   return VVCB_OK;
 }
 
-template <int TILE, int KIND> static void launch_eval_bucket(const EvalParams& P, int grid, cudaStream_t stream)
+template <int TILE, int KIND, int MODE> static void launch_eval_bucket(const EvalParams& P, int numSms, long long maxWarps, cudaStream_t stream)
 {
-  rmd_eval_kernel<TILE, KIND><<<grid, kThreads, 0, stream>>>(P);
+  using Cfg = EvalCfg<MODE == 1>;
+  long long grid = (long long)numSms * Cfg::kMinCtas;
+  const long long maxCtas = (maxWarps + Cfg::kWarps - 1) / Cfg::kWarps;
+  if (grid > maxCtas) grid = maxCtas;
+  if (grid < 1) grid = 1;
+  rmd_eval_kernel<TILE, KIND, MODE><<<(int)grid, Cfg::kThreads, 0, stream>>>(P);
 }
 
 static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_rmd_result* dResults, vvcb_rmd_detail* dDetails,
@@ -314,32 +319,33 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   CK(cudaMemsetAsync(ctx->dPlan, 0, sizeof(PlanState), ctx->stream));
   const bool tm = ctx->timing != 0;
   if (tm) CK(cudaEventRecord(ctx->kev[0], ctx->stream));
-  rmd_plan_count<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan);
+  const int pack = dPred ? 0 : 1;     // the prediction-output kernels (parity / integration entry points) take plain items only
+  rmd_plan_count<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan, pack);
   rmd_plan_scan<<<1, 32, 0, ctx->stream>>>(ctx->dPlan);
-  rmd_plan_fill<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan, ctx->dItems);
+  rmd_plan_fill<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan, ctx->dItems, pack);
   if (tm) CK(cudaEventRecord(ctx->kev[1], ctx->stream));
   EvalParams P;
   P.visits = dVisits; P.items = ctx->dItems; P.plan = ctx->dPlan;
   P.sadSM = ctx->dSlotMajor; P.satdSM = ctx->dSlotMajor + (size_t)VVCB_NUM_SLOTS * n; P.nVisits = n;
   P.orig = ctx->bOrig; P.reco = ctx->bReco; P.stride = ctx->stride; P.bd = ctx->bd; P.ctu = ctx->ctu; P.rom = ctx->dRom;
   P.predOut = dPred;
-  const long long maxCtas = ((long long)n * 8 + kWarpsPerCta - 1) / kWarpsPerCta;
-  int grid = ctx->numSms * VVCB_EVAL_MIN_CTAS;
-  if (grid > maxCtas) grid = (int)maxCtas;
-  if (grid < 1) grid = 1;
+  const long long maxWarps = (long long)n * 8;          // no point in more warps than work items
   // one stream per prediction kind: the launches of a kind stay ordered, kernels of different kinds overlap at their tails
   CK(cudaEventRecord(ctx->evPlan, ctx->stream));
   for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(ctx->sKind[i], ctx->evPlan, 0));
   for (int b = 0; b < kNumBuckets; b++) {
     const int kind = b % kNumKinds;
     cudaStream_t st = kind == 0 ? ctx->stream : ctx->sKind[kind - 1];
-    VVCB_FOR_BUCKET(b, launch_eval_bucket, P, grid, st);
+    // the packed small shapes of the tile class first (most of the work), then its larger shapes (the 4x4 class has none)
+    if (dPred) { VVCB_FOR_BUCKET(b, 2, launch_eval_bucket, P, ctx->numSms, maxWarps, st); continue; }
+    VVCB_FOR_BUCKET(b, 1, launch_eval_bucket, P, ctx->numSms, maxWarps, st);
+    if (b >= kNumKinds) VVCB_FOR_BUCKET(b, 0, launch_eval_bucket, P, ctx->numSms, maxWarps, st);
   }
   for (int i = 0; i < 2; i++) { CK(cudaEventRecord(ctx->evKind[i], ctx->sKind[i])); CK(cudaStreamWaitEvent(ctx->stream, ctx->evKind[i], 0)); }
   if (tm) CK(cudaEventRecord(ctx->kev[2], ctx->stream));
   if (dDetails) { rmd_detail_kernel<<<(n + 31) / 32, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dDetails, P.sadSM, P.satdSM); ctx->launches++; }
   rmd_lists_kernel<<<(n + kListThreads - 1) / kListThreads, kListThreads, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dResults, dDetails, P.sadSM, P.satdSM);
-  ctx->launches += 3 + kNumBuckets + 1;
+  ctx->launches += 3 + (dPred ? kNumBuckets : 2 * kNumBuckets - kNumKinds) + 1;
   CK(cudaGetLastError());
   if (tm) {
     CK(cudaEventRecord(ctx->kev[3], ctx->stream));

@@ -26,19 +26,48 @@ constexpr int kWarpsPerCta = VVCB_EVAL_WARPS;
 constexpr int kThreads     = kWarpsPerCta * 32;
 constexpr int KIND_ANG = 0, KIND_PDC = 1, KIND_MIP = 2;
 
-struct WarpSmem {
-  int16_t lines[kNumSets][2][kLineMax];   // [set][0 top / 1 left][index], tails replicated for positive angles
-  int16_t slot[kSlotLineWords];           // per-slot scratch of the slots in flight
+// Reference lines and MIP inputs of one visit.  LMAX = kLineMax holds any CU; the packed kernels (several small visits per work
+// item) use kLineSmall.
+template <int LMAX> struct VisitSmem {
+  int16_t lines[kNumSets][2][LMAX];       // [set][0 top / 1 left][index], tails replicated for positive angles
   int16_t mipBnd[8];                      // Haar-averaged boundary: [0..4) top, [4..8) left
   int16_t mipIn[2][8];                    // rebased MIP input vectors: [0] normal, [1] transposed orientation
   int     mipAux[4];                      // first boundary sample of each orientation, sum of each input vector
+  int     pad;                            // odd number of words: the visits of a packed item start in different banks
 };
+using WarpSmem = VisitSmem<kLineMax>;
+
+// ---- packed work items -------------------------------------------------------------------------------
+// A visit of a small CU has few lane-tasks per prediction kind (8x8: 75 angular, 2-4 planar/DC, 19 MIP slots, one lane each), so a
+// warp iteration that serves one visit runs mostly empty (profiles/r1r: 22-26 of 32 lanes active in the angular kernels, 2-4 in the
+// planar/DC ones).  Shapes of at most two lanes per slot are therefore planned into buckets of their own, one per exact shape, and
+// the packed kernel instantiation takes kPackVisits visits of one shape at a time: their reference lines sit side by side in shared
+// memory and the slots of all of them form one flat task list.
+constexpr int kPackVisits  = 8;
+constexpr int kLineSmall   = 52;          // sides <= 16: 2*16 + 1 + 3 + the replicated tail of 14 (16x4 on reference line 3)
+constexpr int kSmallShapes = 8;
+constexpr int kNumBucketsAll = kNumBuckets + kSmallShapes * kNumKinds;
+static_assert((sizeof(VisitSmem<kLineSmall>) / 4) % 2 == 1, "bank stride of the packed line sets");
+
+// index of the shape among the packed ones (4x4, 8x4, 4x8, 8x8, 16x4, 4x16, 16x8, 8x16), -1 for the larger shapes
+__host__ __device__ __forceinline__ int small_shape_index(int lw, int lh)
+{
+  if (lw + lh > 7 || lw > 4 || lh > 4) return -1;
+  if (lw == 2 && lh == 2) return 0;
+  if (lw == 3 && lh == 2) return 1;
+  if (lw == 2 && lh == 3) return 2;
+  if (lw == 3 && lh == 3) return 3;
+  if (lw == 4 && lh == 2) return 4;
+  if (lw == 2 && lh == 4) return 5;
+  if (lw == 4 && lh == 3) return 6;
+  return 7;
+}
 
 struct PlanState {                        // device-resident, zeroed before every call
-  unsigned count[kNumBuckets];            // items per bucket
-  unsigned offset[kNumBuckets];           // first item of the bucket
-  unsigned fill[kNumBuckets];             // fill cursor (plan) ...
-  unsigned cursor[kNumBuckets];           // ... and consume cursor (eval)
+  unsigned count[kNumBucketsAll];         // items per bucket: [0, kNumBuckets) by (tile class, kind), then by (packed shape, kind)
+  unsigned offset[kNumBucketsAll];        // first item of the bucket
+  unsigned fill[kNumBucketsAll];          // fill cursor (plan) ...
+  unsigned cursor[kNumBucketsAll];        // ... and consume cursor (eval)
 };
 
 struct EvalParams {
@@ -106,66 +135,76 @@ __device__ __forceinline__ int kind_slot(const Rom& rom, const vvcb_rmd_visit& v
 // =====================================================================================================
 // planning
 // =====================================================================================================
-__device__ __forceinline__ int items_of(int nSlots, int lanes, int& perItem)
+__device__ __forceinline__ int items_of(int nSlots, int lanes, int& perItem, bool packed)
 {
+  if (packed) { perItem = nSlots; return nSlots ? 1 : 0; }     // a packed visit is one item per kind
   perItem = lanes >= kItemTasks ? 1 : kItemTasks / lanes;
   return (nSlots + perItem - 1) / perItem;
 }
 
-// Both planning passes aggregate per block in shared memory first: one global atomic per bucket per block.
-__global__ void rmd_plan_count(const vvcb_rmd_visit* visits, int n, int ctu, PlanState* plan)
+__device__ __forceinline__ int bucket_of(const Shape& sh, int kind, bool packed)
 {
-  __shared__ unsigned hist[kNumBuckets];
-  if (threadIdx.x < kNumBuckets) hist[threadIdx.x] = 0;
+  const int small = packed ? small_shape_index(sh.lw, sh.lh) : -1;
+  return small >= 0 ? kNumBuckets + small * kNumKinds + kind : sh.tile * kNumKinds + kind;
+}
+
+// Both planning passes aggregate per block in shared memory first: one global atomic per bucket per block.
+__global__ void rmd_plan_count(const vvcb_rmd_visit* visits, int n, int ctu, PlanState* plan, int pack)
+{
+  __shared__ unsigned hist[kNumBucketsAll];
+  if (threadIdx.x < kNumBucketsAll) hist[threadIdx.x] = 0;
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     const vvcb_rmd_visit v = visits[i];
     const Shape sh = make_shape(v.log2w, v.log2h);
+    const bool packed = pack && small_shape_index(sh.lw, sh.lh) >= 0;
     for (int kind = 0; kind < kNumKinds; kind++) {
       int perItem;
-      const int nItems = items_of(kind_slot_count(v, kind, ctu), sh.lanes, perItem);
-      if (nItems) atomicAdd(&hist[sh.tile * kNumKinds + kind], (unsigned)nItems);
+      const int nItems = items_of(kind_slot_count(v, kind, ctu), sh.lanes, perItem, packed);
+      if (nItems) atomicAdd(&hist[bucket_of(sh, kind, packed)], (unsigned)nItems);
     }
   }
   __syncthreads();
-  if (threadIdx.x < kNumBuckets && hist[threadIdx.x]) atomicAdd(&plan->count[threadIdx.x], hist[threadIdx.x]);
+  if (threadIdx.x < kNumBucketsAll && hist[threadIdx.x]) atomicAdd(&plan->count[threadIdx.x], hist[threadIdx.x]);
 }
 
 __global__ void rmd_plan_scan(PlanState* plan)
 {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned acc = 0;
-    for (int b = 0; b < kNumBuckets; b++) { plan->offset[b] = acc; acc += plan->count[b]; plan->fill[b] = 0; plan->cursor[b] = 0; }
+    for (int b = 0; b < kNumBucketsAll; b++) { plan->offset[b] = acc; acc += plan->count[b]; plan->fill[b] = 0; plan->cursor[b] = 0; }
   }
 }
 
-__global__ void rmd_plan_fill(const vvcb_rmd_visit* visits, int n, int ctu, PlanState* plan, WorkItem* items)
+__global__ void rmd_plan_fill(const vvcb_rmd_visit* visits, int n, int ctu, PlanState* plan, WorkItem* items, int pack)
 {
-  __shared__ unsigned hist[kNumBuckets], base[kNumBuckets];
-  if (threadIdx.x < kNumBuckets) hist[threadIdx.x] = 0;
+  __shared__ unsigned hist[kNumBucketsAll], base[kNumBucketsAll];
+  if (threadIdx.x < kNumBucketsAll) hist[threadIdx.x] = 0;
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   vvcb_rmd_visit v;
   Shape sh = make_shape(2, 2);
   unsigned local[kNumKinds] = { 0, 0, 0 };
   int nItems[kNumKinds] = { 0, 0, 0 }, perItem[kNumKinds] = { 1, 1, 1 }, nSlots[kNumKinds] = { 0, 0, 0 };
+  bool packed = false;
   if (i < n) {
     v = visits[i];
     sh = make_shape(v.log2w, v.log2h);
+    packed = pack && small_shape_index(sh.lw, sh.lh) >= 0;
     for (int kind = 0; kind < kNumKinds; kind++) {
       nSlots[kind] = kind_slot_count(v, kind, ctu);
-      nItems[kind] = items_of(nSlots[kind], sh.lanes, perItem[kind]);
-      if (nItems[kind]) local[kind] = atomicAdd(&hist[sh.tile * kNumKinds + kind], (unsigned)nItems[kind]);
+      nItems[kind] = items_of(nSlots[kind], sh.lanes, perItem[kind], packed);
+      if (nItems[kind]) local[kind] = atomicAdd(&hist[bucket_of(sh, kind, packed)], (unsigned)nItems[kind]);
     }
   }
   __syncthreads();
-  if (threadIdx.x < kNumBuckets && hist[threadIdx.x])
+  if (threadIdx.x < kNumBucketsAll && hist[threadIdx.x])
     base[threadIdx.x] = plan->offset[threadIdx.x] + atomicAdd(&plan->fill[threadIdx.x], hist[threadIdx.x]);
   __syncthreads();
   if (i < n)
     for (int kind = 0; kind < kNumKinds; kind++) {
-      const unsigned at = base[sh.tile * kNumKinds + kind] + local[kind];
+      const unsigned at = base[bucket_of(sh, kind, packed)] + local[kind];
       for (int k = 0; k < nItems[kind]; k++) {
         WorkItem w;
         w.visit = (uint32_t)i;
@@ -179,7 +218,8 @@ __global__ void rmd_plan_fill(const vvcb_rmd_visit* visits, int n, int ctu, Plan
 // =====================================================================================================
 // reference lines of one visit into the warp's shared memory
 // =====================================================================================================
-__device__ void build_line_set(WarpSmem& sm, int set, int mrl, const vvcb_rmd_visit& v, const Shape& sh,
+template <class SM>
+__device__ void build_line_set(SM& sm, int set, int mrl, const vvcb_rmd_visit& v, const Shape& sh,
                                const int16_t* reco, int stride, int bd, int lane)
 {
   const LineGeom g = make_line_geom(v, sh.w, sh.h, mrl);
@@ -210,7 +250,8 @@ __device__ void build_line_set(WarpSmem& sm, int set, int mrl, const vvcb_rmd_vi
 }
 
 // [1 2 1]/4 smoothing of set 0 into set 1 (CL/IntraPrediction.cpp:1470-1522), tails copied
-__device__ void build_filtered_set(WarpSmem& sm, const Shape& sh, int lane)
+template <class SM>
+__device__ void build_filtered_set(SM& sm, const Shape& sh, int lane)
 {
   const int nTop = 2 * sh.w + 1, nLeft = 2 * sh.h + 1;
   const int16_t* top = sm.lines[0][0];
@@ -233,7 +274,8 @@ __device__ void build_filtered_set(WarpSmem& sm, const Shape& sh, int lane)
 
 // MIP inputs of one visit (CL/MatrixIntraPrediction.cpp:71-124): Haar-averaged boundary, then the two rebased
 // input vectors (normal and transposed orientation) with their sums.
-__device__ void build_mip_inputs(WarpSmem& sm, const Shape& sh, const MipGeom& mg, int bd, int lane)
+template <class SM>
+__device__ void build_mip_inputs(SM& sm, const Shape& sh, const MipGeom& mg, int bd, int lane)
 {
   if (lane < 8) {
     const int side = lane >> 2, i = lane & 3;          // 0 top, 1 left
@@ -292,7 +334,8 @@ __device__ __forceinline__ SlotInfo make_slot_info(const Rom& rom, const vvcb_rm
 
 // Main reference of a negative-angle slot with its projected extension (CL/IntraPrediction.cpp:654-673):
 // buf[t + mh] = refMain0[t], t in [-mh, mw + 1 + mrl].  Positive angles read the visit's lines directly.
-__device__ void build_projected_line(int16_t* buf, const WarpSmem& sm, const SlotInfo& s, int mw, int mh, int gl, int gsize)
+template <class SM>
+__device__ void build_projected_line(int16_t* buf, const SM& sm, const SlotInfo& s, int mw, int mh, int gl, int gsize)
 {
   const int16_t* mainSrc = sm.lines[s.set][s.p.is_ver ? 0 : 1];
   const int16_t* sideSrc = sm.lines[s.set][s.p.is_ver ? 1 : 0];
@@ -353,8 +396,8 @@ __device__ __forceinline__ void store_pred(int16_t* out, int w, int x0, int y0, 
 // =====================================================================================================
 // (x0, y0): block position of the lane's unit; rOff: first row of the piece inside the unit, counted along the side
 // direction of the prediction frame (block rows for vertical modes, block columns for horizontal ones)
-template <int R, int C>
-__device__ __forceinline__ void predict_angular(const WarpSmem& sm, const int16_t* projected, const SlotInfo& s, const Shape& sh,
+template <int R, int C, class SM>
+__device__ __forceinline__ void predict_angular(const SM& sm, const int16_t* projected, const SlotInfo& s, const Shape& sh,
                                                 const uint32_t* filt, int bd, int x0, int y0, int rOff, int (&q)[R][C])
 {
   const bool ver = s.p.is_ver;
@@ -373,7 +416,8 @@ __device__ __forceinline__ int mip_plane_offset(const MipGeom& mg, const Shape& 
   return identity ? 0 : mg.redW * mg.redH;
 }
 
-__device__ void build_mip_planes(int16_t* red, int16_t* plane, const Rom& rom, const WarpSmem& sm, const MipGeom& mg, const Shape& sh,
+template <class SM>
+__device__ void build_mip_planes(int16_t* red, int16_t* plane, const Rom& rom, const SM& sm, const MipGeom& mg, const Shape& sh,
                                  int bd, int mode, int gl, int gsize)
 {
   const MipSlot ms = make_mip_slot(rom, mg, sm.mipIn, sm.mipAux, mode);
@@ -407,8 +451,8 @@ __device__ void build_mip_planes(int16_t* red, int16_t* plane, const Rom& rom, c
   }
 }
 
-template <int R, int C>
-__device__ __forceinline__ void predict_mip(const WarpSmem& sm, const int16_t* plane, const MipGeom& mg, const Shape& sh,
+template <int R, int C, class SM>
+__device__ __forceinline__ void predict_mip(const SM& sm, const int16_t* plane, const MipGeom& mg, const Shape& sh,
                                             int x0, int y0, int (&q)[R][C])
 {
   const int16_t* top = sm.lines[0][0];
@@ -449,63 +493,128 @@ __device__ __forceinline__ void predict_mip(const WarpSmem& sm, const int16_t* p
 #ifndef VVCB_EVAL_MIN_CTAS
 #define VVCB_EVAL_MIN_CTAS 2
 #endif
-template <int TILE, int KIND>
-__global__ void __launch_bounds__(kThreads, VVCB_EVAL_MIN_CTAS) rmd_eval_kernel(EvalParams P)
+// PACK = false: one work item = a slot range of one visit (any shape).  PACK = true: one work item = up to kPackVisits visits of one
+// small shape with all their slots of this kind; half as many warps per CTA (their shared memory holds kPackVisits line sets each).
+template <bool PACK> struct EvalCfg {
+  static constexpr int kWarps   = PACK ? kWarpsPerCta / 2 : kWarpsPerCta;
+  static constexpr int kThreads = kWarps * 32;
+  static constexpr int kMinCtas = PACK ? 2 * VVCB_EVAL_MIN_CTAS : VVCB_EVAL_MIN_CTAS;
+  static constexpr int kVisits  = PACK ? kPackVisits : 1;
+  using Smem = VisitSmem<PACK ? kLineSmall : kLineMax>;
+};
+
+// the packed shapes of a tile class, in bucket order
+__host__ __device__ __forceinline__ int pack_shape_count(int tile) { return tile == 1 || tile == 2 ? 2 : 1; }
+__host__ __device__ __forceinline__ int pack_shape(int tile, int i)
 {
+  return tile == 0 ? 0 : tile == 1 ? (i ? 4 : 1) : tile == 2 ? (i ? 5 : 2) : tile == 3 ? 3 : tile == 4 ? 6 : 7;
+}
+
+// MODE 0: plain items; MODE 1: packed items; MODE 2: plain items + the prediction samples of visit 0 written to P.predOut (the parity /
+// integration entry points vvcb_rmd_pred*; kept out of the throughput kernels: 350 instructions in the middle of their hot loop)
+template <int TILE, int KIND, int MODE>
+__global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 1>::kMinCtas) rmd_eval_kernel(EvalParams P)
+{
+  constexpr bool PACK = MODE == 1, WITH_PRED = MODE == 2;
+  using Cfg = EvalCfg<PACK>;
+  using SM = typename Cfg::Smem;
   constexpr int S = TILE < 3 ? 4 : 8;
-  constexpr int BUCKET = TILE * kNumKinds + KIND;
-  __shared__ WarpSmem smem[kWarpsPerCta];
+  constexpr int V = Cfg::kVisits;
+  __shared__ SM smem[Cfg::kWarps][V];
+  __shared__ int16_t sScratch[Cfg::kWarps][kSlotLineWords];       // per-slot scratch of the slots in flight
+  __shared__ vvcb_rmd_visit sVisit[Cfg::kWarps][V];
+  __shared__ int sFirst[Cfg::kWarps][V + 1];                      // first flat task of each visit of the item
+  __shared__ unsigned sIndex[Cfg::kWarps][V];                     // the visits' indices in the batch
   __shared__ uint32_t sFilt[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpSmem& sm = smem[warp];
   if (threadIdx.x < 64) sFilt[threadIdx.x] = (&P.rom->filt[0][0])[threadIdx.x];
   __syncthreads();
   const Rom& rom = *P.rom;
+
+#pragma unroll 1
+  for (int ps = 0; ps < (PACK ? pack_shape_count(TILE) : 1); ps++) {
+  const int BUCKET = PACK ? kNumBuckets + pack_shape(TILE, ps) * kNumKinds + KIND : TILE * kNumKinds + KIND;
   const unsigned nItems = P.plan->count[BUCKET];
   const WorkItem* items = P.items + P.plan->offset[BUCKET];
 
   for (;;) {
     unsigned it = 0;
-    if (lane == 0) it = atomicAdd(&P.plan->cursor[BUCKET], 1u);
+    if (lane == 0) it = atomicAdd(&P.plan->cursor[BUCKET], (unsigned)V);
     it = __shfl_sync(0xffffffffu, it, 0);
     if (it >= nItems) break;
-    const WorkItem item = items[it];
-    const vvcb_rmd_visit v = P.visits[item.visit];
-    const Shape sh = make_shape(v.log2w, v.log2h);
-    const MipGeom mg = make_mip_geom(sh.w, sh.h);
-    uint32_t* sadOut  = P.sadSM + item.visit;
-    uint32_t* satdOut = P.satdSM + item.visit;
-    const int16_t* org = P.orig + (size_t)v.y * P.stride + v.x;
-
-    // ---- reference lines needed by this item's slots
+    const int nv = PACK ? (int)(nItems - it < (unsigned)V ? nItems - it : (unsigned)V) : 1;
+    const WorkItem item = items[it];                  // PACK: slot range = all slots of the kind, for every visit of the item
     __syncwarp();
-    build_line_set(sm, 0, 0, v, sh, P.reco, P.stride, P.bd, lane);
-    if (KIND != KIND_MIP) {
-      const int lastSlot = kind_slot(rom, v, KIND, item.slot_begin + item.slot_count - 1);
-      if (lastSlot >= VVCB_SLOT_MRL1) {        // reference lines 1 and 3 (the MRL slots sit at the end of the kind's list)
-        build_line_set(sm, 2, 1, v, sh, P.reco, P.stride, P.bd, lane);
-        build_line_set(sm, 3, 3, v, sh, P.reco, P.stride, P.bd, lane);
+    // ---- the item's visits into shared memory (20 words each)
+#pragma unroll 1
+    for (int i = lane; i < nv * 20; i += 32) {
+      const int j = i / 20, k = i - j * 20;
+      reinterpret_cast<uint32_t*>(&sVisit[warp][j])[k] = reinterpret_cast<const uint32_t*>(P.visits + items[it + j].visit)[k];
+    }
+    if (lane < nv) sIndex[warp][lane] = items[it + lane].visit;
+    __syncwarp();
+    const Shape sh = make_shape(sVisit[warp][0].log2w, sVisit[warp][0].log2h);    // one shape per packed item
+    const MipGeom mg = make_mip_geom(sh.w, sh.h);
+    {
+      // flat task list: the slots of visit 0, then of visit 1, ...
+      if (lane < nv) sFirst[warp][lane + 1] = (PACK ? kind_slot_count(sVisit[warp][lane], KIND, P.ctu) : (int)item.slot_count) * sh.lanes;
+      __syncwarp();
+      if (lane == 0) {
+        int acc = 0;
+        sFirst[warp][0] = 0;
+        for (int j = 0; j < V; j++) {
+          if (j < nv) acc += sFirst[warp][j + 1];
+          sFirst[warp][j + 1] = j < nv ? acc : 0x3fffffff;
+        }
       }
     }
+
+    // ---- reference lines needed by the item's slots (loops kept rolled: code size, profiles/r1s)
+#pragma unroll 1
+    for (int j = 0; j < nv; j++) {
+      const vvcb_rmd_visit& v = sVisit[warp][j];
+      SM& sm = smem[warp][j];
+      int nSets = 1;                             // line 0, plus lines 1 and 3 when the item holds MRL slots (they end the kind's list)
+      if (KIND != KIND_MIP) {
+        const int lastSlot = kind_slot(rom, v, KIND, PACK ? kind_slot_count(v, KIND, P.ctu) - 1 : item.slot_begin + item.slot_count - 1);
+        if (lastSlot >= VVCB_SLOT_MRL1) nSets = 3;
+      }
+#pragma unroll 1
+      for (int q = 0; q < nSets; q++) build_line_set(sm, q ? q + 1 : 0, q == 2 ? 3 : q, v, sh, P.reco, P.stride, P.bd, lane);
+    }
     __syncwarp();
-    if (KIND != KIND_MIP) build_filtered_set(sm, sh, lane);
-    else                  build_mip_inputs(sm, sh, mg, P.bd, lane);
+#pragma unroll 1
+    for (int j = 0; j < nv; j++) {
+      if (KIND != KIND_MIP) build_filtered_set(smem[warp][j], sh, lane);
+      else                  build_mip_inputs(smem[warp][j], sh, mg, P.bd, lane);
+    }
     __syncwarp();
 
     const int lanes = sh.lanes;                       // lanes per slot
     const int gsize = lanes > 32 ? 32 : lanes;        // lanes of one slot inside this warp iteration
     const int lgG   = lanes > 32 ? 5 : sh.lgLanes;
     const int gidx  = lane >> lgG, gl = lane & (gsize - 1);
-    int16_t* scratch = sm.slot + gidx * ((kSlotLineWords / 32) << lgG);
-    const int nTasks = item.slot_count * lanes;
+    int16_t* scratch = sScratch[warp] + gidx * ((kSlotLineWords / 32) << lgG);
+    const int nTasks = sFirst[warp][nv];          // (written before the __syncwarp()s above)
     int accSad = 0, accSatd = 0;
 
     for (int base = 0; base < nTasks; base += 32) {
       const int task = base + lane;
       const bool act = task < nTasks;
-      const int tk = act ? task : nTasks - 1;
+      int tk = act ? task : nTasks - 1;
+      int vi = 0;
+      if (PACK) {
+#pragma unroll
+        for (int j = 1; j < V; j++) vi += tk >= sFirst[warp][j];
+        tk -= sFirst[warp][vi];
+      }
+      const vvcb_rmd_visit& v = sVisit[warp][vi];
+      const SM& sm = smem[warp][vi];
+      uint32_t* sadOut  = P.sadSM + sIndex[warp][vi];
+      uint32_t* satdOut = P.satdSM + sIndex[warp][vi];
+      const int16_t* org = P.orig + (size_t)v.y * P.stride + v.x;
       const int u = tk & (lanes - 1);
-      const int slot = kind_slot(rom, v, KIND, item.slot_begin + (tk >> sh.lgLanes));
+      const int slot = kind_slot(rom, v, KIND, (PACK ? 0 : item.slot_begin) + (tk >> sh.lgLanes));
       const SlotInfo s = make_slot_info(rom, v, sh, slot);
 
       // ---- per-slot scratch built by the slot's lanes
@@ -551,7 +660,7 @@ __global__ void __launch_bounds__(kThreads, VVCB_EVAL_MIN_CTAS) rmd_eval_kernel(
           if (KIND == KIND_ANG)      predict_angular<4, 8>(sm, scratch, s, sh, sFilt, P.bd, x0, y0, 4 * k, q);
           else if (KIND == KIND_MIP) predict_mip<4, 8>(sm, scratch + mip_plane_offset(mg, sh), mg, sh, hx, hy, q);
           else pred_planar_dc_unit<4, 8>(sm.lines[s.set][0], sm.lines[s.set][1], s.kind, s.p.pdpc, dc, sh.lw, sh.lh, hx, hy, q);
-          if (P.predOut && act) store_pred<4, 8>(P.predOut + (size_t)slot * sh.w * sh.h, sh.w, hx, hy, transposed, q);
+          if (WITH_PRED && P.predOut && act) store_pred<4, 8>(P.predOut + (size_t)slot * sh.w * sh.h, sh.w, hx, hy, transposed, q);
           if (transposed) residual_unit<4, 8, true>(org + hy * P.stride + hx, P.stride, q, d, sad);
           else            residual_unit<4, 8, false>(org + hy * P.stride + hx, P.stride, q, d, sad);
           wht_rows_rc<4, 8>(d);
@@ -595,7 +704,7 @@ __global__ void __launch_bounds__(kThreads, VVCB_EVAL_MIN_CTAS) rmd_eval_kernel(
           if (KIND == KIND_ANG)      predict_angular<4, 4>(sm, scratch, s, sh, sFilt, P.bd, x0, y0, 0, q);
           else if (KIND == KIND_MIP) predict_mip<4, 4>(sm, scratch + mip_plane_offset(mg, sh), mg, sh, x0, y0, q);
           else pred_planar_dc_unit<4, 4>(sm.lines[s.set][0], sm.lines[s.set][1], s.kind, s.p.pdpc, dc, sh.lw, sh.lh, x0, y0, q);
-          if (P.predOut && act) store_pred<4, 4>(P.predOut + (size_t)slot * sh.w * sh.h, sh.w, x0, y0, transposed, q);
+          if (WITH_PRED && P.predOut && act) store_pred<4, 4>(P.predOut + (size_t)slot * sh.w * sh.h, sh.w, x0, y0, transposed, q);
           if (transposed) residual_unit<4, 4, true>(org + y0 * P.stride + x0, P.stride, q, d, sad);
           else            residual_unit<4, 4, false>(org + y0 * P.stride + x0, P.stride, q, d, sad);
           wht_rows<4>(d);
@@ -640,6 +749,7 @@ __global__ void __launch_bounds__(kThreads, VVCB_EVAL_MIN_CTAS) rmd_eval_kernel(
       }
     }
   }
+  }
 }
 
 // =====================================================================================================
@@ -666,9 +776,11 @@ constexpr int kTuPredWarps = 4;
 __global__ void __launch_bounds__(kTuPredWarps * 32) tu_pred_kernel(TuPredParams P)
 {
   __shared__ WarpSmem smem[kTuPredWarps];
+  __shared__ int16_t sScratch[kTuPredWarps][kSlotLineWords];
   __shared__ uint32_t sFilt[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpSmem& sm = smem[warp];
+  int16_t* const slotBuf = sScratch[warp];
   if (threadIdx.x < 64) sFilt[threadIdx.x] = (&P.rom->filt[0][0])[threadIdx.x];
   __syncthreads();
   const Rom& rom = *P.rom;
@@ -691,9 +803,9 @@ __global__ void __launch_bounds__(kTuPredWarps * 32) tu_pred_kernel(TuPredParams
     __syncwarp();
     int dc = 0;
     if (s.kind == 2) {
-      if (s.p.angle < 0) build_projected_line(sm.slot, sm, s, s.p.is_ver ? sh.w : sh.h, s.p.is_ver ? sh.h : sh.w, lane, 32);
+      if (s.p.angle < 0) build_projected_line(slotBuf, sm, s, s.p.is_ver ? sh.w : sh.h, s.p.is_ver ? sh.h : sh.w, lane, 32);
     } else if (s.kind == 3) {
-      build_mip_planes(sm.slot, sm.slot + mip_plane_offset(mg, sh), rom, sm, mg, sh, P.bd, s.mode, lane, 32);
+      build_mip_planes(slotBuf, slotBuf + mip_plane_offset(mg, sh), rom, sm, mg, sh, P.bd, s.mode, lane, 32);
     } else if (s.kind == 1) {
       int part = 0;
       const int16_t* top = sm.lines[s.set][0] + s.mrl + 1;
@@ -711,8 +823,8 @@ __global__ void __launch_bounds__(kTuPredWarps * 32) tu_pred_kernel(TuPredParams
     for (int u = lane; u < pieces; u += 32) {
       const int x0 = (u % piecesX) * 4, y0 = (u / piecesX) * 4;
       int q[4][4];
-      if (s.kind == 2)      predict_angular<4, 4>(sm, sm.slot, s, sh, sFilt, P.bd, x0, y0, 0, q);
-      else if (s.kind == 3) predict_mip<4, 4>(sm, sm.slot + mip_plane_offset(mg, sh), mg, sh, x0, y0, q);
+      if (s.kind == 2)      predict_angular<4, 4>(sm, slotBuf, s, sh, sFilt, P.bd, x0, y0, 0, q);
+      else if (s.kind == 3) predict_mip<4, 4>(sm, slotBuf + mip_plane_offset(mg, sh), mg, sh, x0, y0, q);
       else pred_planar_dc_unit<4, 4>(sm.lines[s.set][0], sm.lines[s.set][1], s.kind, s.p.pdpc, dc, sh.lw, sh.lh, x0, y0, q);
 #pragma unroll
       for (int i = 0; i < 4; i++)
@@ -726,15 +838,15 @@ __global__ void __launch_bounds__(kTuPredWarps * 32) tu_pred_kernel(TuPredParams
   }
 }
 
-// calls F<TILE, KIND>(args) for bucket b
-#define VVCB_FOR_BUCKET(b, F, ...)                                                                          \
+// calls F<TILE, KIND, MODE>(args) for launch b = tile class * kNumKinds + kind
+#define VVCB_FOR_BUCKET(b, PACK, F, ...)                                                                    \
   switch (b) {                                                                                               \
-    case 0:  F<0, 0>(__VA_ARGS__); break;  case 1:  F<0, 1>(__VA_ARGS__); break;  case 2:  F<0, 2>(__VA_ARGS__); break; \
-    case 3:  F<1, 0>(__VA_ARGS__); break;  case 4:  F<1, 1>(__VA_ARGS__); break;  case 5:  F<1, 2>(__VA_ARGS__); break; \
-    case 6:  F<2, 0>(__VA_ARGS__); break;  case 7:  F<2, 1>(__VA_ARGS__); break;  case 8:  F<2, 2>(__VA_ARGS__); break; \
-    case 9:  F<3, 0>(__VA_ARGS__); break;  case 10: F<3, 1>(__VA_ARGS__); break;  case 11: F<3, 2>(__VA_ARGS__); break; \
-    case 12: F<4, 0>(__VA_ARGS__); break;  case 13: F<4, 1>(__VA_ARGS__); break;  case 14: F<4, 2>(__VA_ARGS__); break; \
-    case 15: F<5, 0>(__VA_ARGS__); break;  case 16: F<5, 1>(__VA_ARGS__); break;  case 17: F<5, 2>(__VA_ARGS__); break; \
+    case 0:  F<0, 0, PACK>(__VA_ARGS__); break;  case 1:  F<0, 1, PACK>(__VA_ARGS__); break;  case 2:  F<0, 2, PACK>(__VA_ARGS__); break; \
+    case 3:  F<1, 0, PACK>(__VA_ARGS__); break;  case 4:  F<1, 1, PACK>(__VA_ARGS__); break;  case 5:  F<1, 2, PACK>(__VA_ARGS__); break; \
+    case 6:  F<2, 0, PACK>(__VA_ARGS__); break;  case 7:  F<2, 1, PACK>(__VA_ARGS__); break;  case 8:  F<2, 2, PACK>(__VA_ARGS__); break; \
+    case 9:  F<3, 0, PACK>(__VA_ARGS__); break;  case 10: F<3, 1, PACK>(__VA_ARGS__); break;  case 11: F<3, 2, PACK>(__VA_ARGS__); break; \
+    case 12: F<4, 0, PACK>(__VA_ARGS__); break;  case 13: F<4, 1, PACK>(__VA_ARGS__); break;  case 14: F<4, 2, PACK>(__VA_ARGS__); break; \
+    case 15: F<5, 0, PACK>(__VA_ARGS__); break;  case 16: F<5, 1, PACK>(__VA_ARGS__); break;  case 17: F<5, 2, PACK>(__VA_ARGS__); break; \
   }
 
 // =====================================================================================================
