@@ -12,11 +12,12 @@ python bench.py --steps 2 --warmup 3 --resident-only > /dev/null 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv \
   python bench.py --steps 2 --warmup 3 --resident-only > gpurun_out/ncu_launches_$tag.log 2>&1; echo "ncu list rc=$?"
 python tools/profile_sweep.py --width 1920 --height 1080 --passes 2 > gpurun_out/prof_plain_$tag.log 2>&1 || exit 1
-timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:rmd_eval_kernel -s 18 -c 18 \
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:rmd_eval_kernel -s 33 -c 33 \
   --csv --log-file gpurun_out/eval_traffic_$tag.csv python tools/profile_sweep.py --width 1920 --height 1080 --passes 2 > /dev/null 2>&1 && \
   python tools/make_traffic.py gpurun_out/eval_traffic_$tag.csv $tag
-# second pass of the sweep: 18 eval launches per pass in bucket order (class*3 + kind); 8x8 angular = launch 9, 16x8 angular = 12
-for k in 27:eval8x8ang 30:eval16x8ang 18:eval4x4ang; do
+# second pass of the sweep: 33 eval launches per pass (per tile class x kind: the packed small shapes, then -- classes 1..5 -- the larger
+# shapes): 8x8 angular packed = launch 15, 16x16+ angular = 16, 16x8 angular packed = 21, 32x8 / 32x16 angular = 22, 4x4 angular = 0
+for k in 48:eval8x8ang 49:eval16x16ang 55:eval32x8ang 33:eval4x4ang; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:rmd_eval_kernel -s ${k%%:*} -c 1 -o gpurun_out/prof_${k##*:}_$tag -f \
     python tools/profile_sweep.py --width 1920 --height 1080 --passes 2 > gpurun_out/ncu_full_${k##*:}_$tag.log 2>&1; echo "ncu ${k##*:} rc=$?"
 done

@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
   __shared__ SM smem[Cfg::kWarps][V];
   __shared__ int16_t sScratch[Cfg::kWarps][kSlotLineWords];       // per-slot scratch of the slots in flight
   __shared__ vvcb_rmd_visit sVisit[Cfg::kWarps][V];
-  __shared__ int sFirst[Cfg::kWarps][V + 1];                      // first flat task of each visit of the item
+  __shared__ int sFirst[Cfg::kWarps][V + 1];                      // packed items: number of slots of each visit
   __shared__ unsigned sIndex[Cfg::kWarps][V];                     // the visits' indices in the batch
   __shared__ uint32_t sFilt[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -555,18 +555,16 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
     __syncwarp();
     const Shape sh = make_shape(sVisit[warp][0].log2w, sVisit[warp][0].log2h);    // one shape per packed item
     const MipGeom mg = make_mip_geom(sh.w, sh.h);
-    {
-      // flat task list: the slots of visit 0, then of visit 1, ...
-      if (lane < nv) sFirst[warp][lane + 1] = (PACK ? kind_slot_count(sVisit[warp][lane], KIND, P.ctu) : (int)item.slot_count) * sh.lanes;
-      __syncwarp();
-      if (lane == 0) {
-        int acc = 0;
-        sFirst[warp][0] = 0;
-        for (int j = 0; j < V; j++) {
-          if (j < nv) acc += sFirst[warp][j + 1];
-          sFirst[warp][j + 1] = j < nv ? acc : 0x3fffffff;
-        }
-      }
+    // Task list of a packed item, slot-major: task = ((slot index * V + visit) * lanes + unit), so that the 32 lanes of a warp
+    // iteration work on the same few slot indices of all the visits -- the angular slots are ordered by (hor / ver, PDPC class)
+    // per shape, which keeps projection, PDPC and transposition branches uniform across the iteration (profiles/r1s: with the
+    // visits' slots laid end to end 21.5 of 32 lanes were active per instruction).
+    int maxSlots = PACK ? 0 : (int)item.slot_count;
+    if (PACK) {
+      int c = lane < nv ? kind_slot_count(sVisit[warp][lane], KIND, P.ctu) : 0;
+      if (lane < V) sFirst[warp][lane] = c;
+      for (int o = V >> 1; o > 0; o >>= 1) c = vmax(c, __shfl_xor_sync(0xffffffffu, c, o));
+      maxSlots = __shfl_sync(0xffffffffu, c, 0);
     }
 
     // ---- reference lines needed by the item's slots (loops kept rolled: code size, profiles/r1s)
@@ -595,18 +593,22 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
     const int lgG   = lanes > 32 ? 5 : sh.lgLanes;
     const int gidx  = lane >> lgG, gl = lane & (gsize - 1);
     int16_t* scratch = sScratch[warp] + gidx * ((kSlotLineWords / 32) << lgG);
-    const int nTasks = sFirst[warp][nv];          // (written before the __syncwarp()s above)
+    const int nTasks = maxSlots * V * lanes;
     int accSad = 0, accSatd = 0;
 
     for (int base = 0; base < nTasks; base += 32) {
       const int task = base + lane;
-      const bool act = task < nTasks;
+      bool act = task < nTasks;
       int tk = act ? task : nTasks - 1;
       int vi = 0;
       if (PACK) {
-#pragma unroll
-        for (int j = 1; j < V; j++) vi += tk >= sFirst[warp][j];
-        tk -= sFirst[warp][vi];
+        const int r = tk >> sh.lgLanes;
+        vi = r & (V - 1);
+        int idx = r / V;
+        act = act && vi < nv && idx < sFirst[warp][vi];
+        if (vi >= nv) vi = nv - 1;                                   // idle lanes shadow a real task
+        if (idx >= sFirst[warp][vi]) idx = sFirst[warp][vi] - 1;
+        tk = (idx << sh.lgLanes) | (tk & (lanes - 1));
       }
       const vvcb_rmd_visit& v = sVisit[warp][vi];
       const SM& sm = smem[warp][vi];
