@@ -218,35 +218,88 @@ __global__ void rmd_plan_fill(const vvcb_rmd_visit* visits, int n, int ctu, Plan
 // =====================================================================================================
 // reference lines of one visit into the warp's shared memory
 // =====================================================================================================
+// One entry of a line set: walk position i (past the walk: the replicated tails) -> the sample, or mid-grey when nothing is available.
+// The load is issued here; the caller stores it with store_line_entry once all the loads of its batch are in flight.
+struct LineCtx { LineGeom g; int extTop, extLeft, nTop, nLeft, total; };
+
+__device__ __forceinline__ LineCtx make_line_ctx(const vvcb_rmd_visit& v, const Shape& sh, int mrl)
+{
+  LineCtx c;
+  c.g = make_line_geom(v, sh.w, sh.h, mrl);
+  // tails: the main reference of positive angles is extended by replication (CL/IntraPrediction.cpp:717-726)
+  c.extTop = (mrl << vmax(0, sh.lw - sh.lh)) + 2; c.extLeft = (mrl << vmax(0, sh.lh - sh.lw)) + 2;
+  c.nTop = 2 * sh.w + 1 + mrl; c.nLeft = 2 * sh.h + 1 + mrl;
+  c.total = c.g.n + c.extTop + c.extLeft;
+  return c;
+}
+
+__device__ __forceinline__ int load_line_entry(const LineCtx& c, const int16_t* base, int stride, int bd, int i)
+{
+  const int pos = i < c.g.n ? i : (i < c.g.n + c.extTop ? c.g.n - 1 : 0);
+  const int src = line_source(c.g, pos);
+  int val = 1 << (bd - 1);
+  if (src >= 0) {
+    bool isLeft; int k, dx, dy;
+    line_pos(c.g, src, isLeft, k, dx, dy);
+    val = base[dy * stride + dx];
+  }
+  return val;
+}
+
+template <class SM>
+__device__ __forceinline__ void store_line_entry(SM& sm, int set, const LineCtx& c, int i, int val)
+{
+  if (i < c.g.n) {
+    bool isLeft; int k, dx, dy;
+    line_pos(c.g, i, isLeft, k, dx, dy);
+    if (isLeft) sm.lines[set][1][k] = (int16_t)val;
+    else {
+      sm.lines[set][0][k] = (int16_t)val;
+      if (k == 0) sm.lines[set][1][0] = (int16_t)val;
+    }
+  } else if (i < c.g.n + c.extTop) sm.lines[set][0][c.nTop + (i - c.g.n)] = (int16_t)val;
+  else sm.lines[set][1][c.nLeft + (i - c.g.n - c.extTop)] = (int16_t)val;
+}
+
+// Reference line 0 (set 0) of one visit, or -- NS == 3 -- lines 0, 1 and 3 (sets 0, 2, 3), straight from the reconstruction plane.
+// Every lane issues the loads of two walk positions of all NS lines before it stores any of them, so a small CU costs one memory
+// round trip instead of one per line and 32 positions -- at the price of 2 NS inlined copies of the walk arithmetic.
+template <int NS, class SM>
+__device__ void build_line_sets(SM& sm, const vvcb_rmd_visit& v, const Shape& sh, const int16_t* reco, int stride, int bd, int lane)
+{
+  const int16_t* base = reco + (size_t)v.y * stride + v.x;
+  LineCtx c[NS];
+#pragma unroll
+  for (int q = 0; q < NS; q++) c[q] = make_line_ctx(v, sh, q == 2 ? 3 : q);
+  const int total = c[NS - 1].total;               // the longest walk
+#pragma unroll 1
+  for (int i0 = lane; i0 < total; i0 += 64) {
+    int val[NS][2];
+#pragma unroll
+    for (int q = 0; q < NS; q++)
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int i = i0 + 32 * u;
+        val[q][u] = i < c[q].total ? load_line_entry(c[q], base, stride, bd, i) : 0;
+      }
+#pragma unroll
+    for (int q = 0; q < NS; q++)
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const int i = i0 + 32 * u;
+        if (i < c[q].total) store_line_entry(sm, q ? q + 1 : 0, c[q], i, val[q][u]);
+      }
+  }
+}
+
+// one line set (TU prediction kernel: a job needs line 0 and at most one more)
 template <class SM>
 __device__ void build_line_set(SM& sm, int set, int mrl, const vvcb_rmd_visit& v, const Shape& sh,
                                const int16_t* reco, int stride, int bd, int lane)
 {
-  const LineGeom g = make_line_geom(v, sh.w, sh.h, mrl);
+  const LineCtx c = make_line_ctx(v, sh, mrl);
   const int16_t* base = reco + (size_t)v.y * stride + v.x;
-  // tails: the main reference of positive angles is extended by replication (CL/IntraPrediction.cpp:717-726)
-  const int extTop = (mrl << vmax(0, sh.lw - sh.lh)) + 2, extLeft = (mrl << vmax(0, sh.lh - sh.lw)) + 2;
-  const int nTop = 2 * sh.w + 1 + mrl, nLeft = 2 * sh.h + 1 + mrl;
-  const int total = g.n + extTop + extLeft;
-  for (int i = lane; i < total; i += 32) {
-    const int pos = i < g.n ? i : (i < g.n + extTop ? g.n - 1 : 0);
-    const int src = line_source(g, pos);
-    int val = 1 << (bd - 1);
-    bool isLeft; int k, dx, dy;
-    if (src >= 0) {
-      line_pos(g, src, isLeft, k, dx, dy);
-      val = base[dy * stride + dx];
-    }
-    if (i < g.n) {
-      line_pos(g, i, isLeft, k, dx, dy);
-      if (isLeft) sm.lines[set][1][k] = (int16_t)val;
-      else {
-        sm.lines[set][0][k] = (int16_t)val;
-        if (k == 0) sm.lines[set][1][0] = (int16_t)val;
-      }
-    } else if (i < g.n + extTop) sm.lines[set][0][nTop + (i - g.n)] = (int16_t)val;
-    else sm.lines[set][1][nLeft + (i - g.n - extTop)] = (int16_t)val;
-  }
+  for (int i = lane; i < c.total; i += 32) store_line_entry(sm, set, c, i, load_line_entry(c, base, stride, bd, i));
 }
 
 // [1 2 1]/4 smoothing of set 0 into set 1 (CL/IntraPrediction.cpp:1470-1522), tails copied
@@ -577,8 +630,15 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
         const int lastSlot = kind_slot(rom, v, KIND, PACK ? kind_slot_count(v, KIND, P.ctu) - 1 : item.slot_begin + item.slot_count - 1);
         if (lastSlot >= VVCB_SLOT_MRL1) nSets = 3;
       }
+      if (KIND == KIND_PDC) {
+        // planar / DC items are all set-up (one warp iteration of arithmetic): overlap the loads of the lines
+        if (nSets == 3) build_line_sets<3>(sm, v, sh, P.reco, P.stride, P.bd, lane);
+        else            build_line_sets<1>(sm, v, sh, P.reco, P.stride, P.bd, lane);
+      } else {
+        // angular / MIP kernels: one rolled copy (their hot loops feel every extra KB of code, profiles/r1s, r1u)
 #pragma unroll 1
-      for (int q = 0; q < nSets; q++) build_line_set(sm, q ? q + 1 : 0, q == 2 ? 3 : q, v, sh, P.reco, P.stride, P.bd, lane);
+        for (int q = 0; q < nSets; q++) build_line_set(sm, q ? q + 1 : 0, q == 2 ? 3 : q, v, sh, P.reco, P.stride, P.bd, lane);
+      }
     }
     __syncwarp();
 #pragma unroll 1
