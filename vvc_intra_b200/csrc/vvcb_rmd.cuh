@@ -968,6 +968,45 @@ __device__ __forceinline__ void sm_push(SmList& L, uint32_t m, double cost, int 
   L.m[pos * kListThreads] = m; L.c[pos * kListThreads] = cost;
 }
 
+// The same list in registers while the slots are being pushed (profiles/r1r: the shared-memory insertion loops were 55 % of the
+// kernel's instructions and its threads diverge on them).  Fixed capacity, every step statically indexed; `worst` caches the
+// last entry of a full list so that the common case -- no better than anything kept -- is one comparison.
+template <int CAP> struct RegList { uint32_t m[CAP]; double c[CAP]; int n; double worst; };
+
+template <int CAP> __device__ __forceinline__ void reg_init(RegList<CAP>& L)
+{
+#pragma unroll
+  for (int i = 0; i < CAP; i++) { L.m[i] = 0u; L.c[i] = 0.0; }
+  L.n = 0; L.worst = 0.0;
+}
+
+// updateCandList (CL/UnitTools.h:261-307): stable bounded insertion, strict '<'
+template <int CAP> __device__ __forceinline__ void reg_push(RegList<CAP>& L, uint32_t m, double cost, int cap)
+{
+  const int live = L.n < cap ? L.n : cap;
+  if (live == cap && !(cost < L.worst)) return;
+  int pos = 0;                                     // entries that stay in front: the list is sorted, ties keep the earlier entry
+#pragma unroll
+  for (int i = 0; i < CAP; i++) pos += (i < live && !(cost < L.c[i])) ? 1 : 0;
+  const int last = live < cap ? live : cap - 1;    // where the shifted tail ends
+#pragma unroll
+  for (int i = CAP - 1; i >= 1; i--) if (i > pos && i <= last) { L.m[i] = L.m[i - 1]; L.c[i] = L.c[i - 1]; }
+#pragma unroll
+  for (int i = 0; i < CAP; i++) if (i == pos) { L.m[i] = m; L.c[i] = cost; }
+  if (L.n < cap) L.n++;
+  if (L.n >= cap) {
+#pragma unroll
+    for (int i = 0; i < CAP; i++) if (i == cap - 1) L.worst = L.c[i];
+  }
+}
+
+template <int CAP> __device__ __forceinline__ void reg_to_sm(const RegList<CAP>& R, SmList& L)
+{
+#pragma unroll
+  for (int i = 0; i < CAP; i++) { L.m[i * kListThreads] = R.m[i]; L.c[i * kListThreads] = R.c[i]; }
+  L.n = R.n;
+}
+
 __device__ void store_list_detail(const SmList& L, int32_t* n, vvcb_mode* m, double* c, int cap)
 {
   *n = L.n;
@@ -993,6 +1032,9 @@ __global__ void __launch_bounds__(kListThreads) rmd_lists_kernel(const vvcb_rmd_
   SmList rd, had;
   rd.m = sRdM + tid; rd.c = sRdC + tid; rd.n = 0;
   had.m = sHadM + tid; had.c = sHadC + tid; had.n = 0;
+  constexpr int kRegRd = 10, kRegHad = 6;                    // K + 1 <= 9 (64x64 with MIP), numHad <= 6
+  RegList<kRegRd> rrd; RegList<kRegHad> rhad;
+  reg_init(rrd); reg_init(rhad);
   if (live) {
     const vvcb_rmd_visit v = visits[vi];
     const int w = 1 << v.log2w, h = 1 << v.log2h;
@@ -1021,10 +1063,11 @@ __global__ void __launch_bounds__(kListThreads) rmd_lists_kernel(const vvcb_rmd_
       if (m > 1 && (m & 1)) continue;
       if (m < 64) checked0 |= 1ull << m; else checked1 |= 1ull << (m - 64);
       const double dist = dist_of(m);
-      sm_push(rd, pack_mode(0, 0, m), cost_of(dist, false, 0, m), K);
-      sm_push(had, pack_mode(0, 0, m), dist, numHad);
+      reg_push(rrd, pack_mode(0, 0, m), cost_of(dist, false, 0, m), K);
+      reg_push(rhad, pack_mode(0, 0, m), dist, numHad);
     }
-    for (int i = 0; i < K; i++) sParent[i * kListThreads + tid] = (uint8_t)(rd.m[i * kListThreads] >> 16);
+#pragma unroll
+    for (int i = 0; i < 8; i++) if (i < K) sParent[i * kListThreads + tid] = (uint8_t)(rrd.m[i] >> 16);
     for (int i = 0; i < K; i++) {                                              // :577-623
       const int pm = sParent[i * kListThreads + tid];
       if (pm > 2 && pm < 66)
@@ -1033,8 +1076,8 @@ __global__ void __launch_bounds__(kListThreads) rmd_lists_kernel(const vvcb_rmd_
           const bool done = m < 64 ? (checked0 >> m) & 1 : (checked1 >> (m - 64)) & 1;
           if (done) continue;
           const double dist = dist_of(m);
-          sm_push(rd, pack_mode(0, 0, m), cost_of(dist, false, 0, m), K);
-          sm_push(had, pack_mode(0, 0, m), dist, numHad);
+          reg_push(rrd, pack_mode(0, 0, m), cost_of(dist, false, 0, m), K);
+          reg_push(rhad, pack_mode(0, 0, m), dist, numHad);
           if (m < 64) checked0 |= 1ull << m; else checked1 |= 1ull << (m - 64);
         }
     }
@@ -1044,10 +1087,11 @@ __global__ void __launch_bounds__(kListThreads) rmd_lists_kernel(const vvcb_rmd_
           const int slot = (li ? VVCB_SLOT_MRL3 : VVCB_SLOT_MRL1) + i - 1;
           const int mrl = li ? 3 : 1;
           const double dist = dist_of(slot);
-          sm_push(rd, pack_mode(0, mrl, v.mpm[i]), cost_of(dist, false, mrl, v.mpm[i]), K);
-          sm_push(had, pack_mode(0, mrl, v.mpm[i]), dist, numHad);
+          reg_push(rrd, pack_mode(0, mrl, v.mpm[i]), cost_of(dist, false, mrl, v.mpm[i]), K);
+          reg_push(rhad, pack_mode(0, mrl, v.mpm[i]), dist, numHad);
         }
     if (D) {
+      reg_to_sm(rrd, rd); reg_to_sm(rhad, had);
       store_list_detail(rd, &D->n_reg, D->reg_mode, D->reg_cost, VVCB_MAX_LIST);
       store_list_detail(had, &D->n_reg_had, D->reg_had_mode, D->reg_had_cost, VVCB_MAX_HAD_LIST);
     }
@@ -1063,9 +1107,10 @@ __global__ void __launch_bounds__(kListThreads) rmd_lists_kernel(const vvcb_rmd_
         const double c = cost_of(dist, true, 0, m);
 #pragma unroll
         for (int i = 0; i < 3; i++) { if (m == 3 + i) c3[i] = c; if (m == 3 + i + off) c3[3 + i] = c; }
-        sm_push(rd, pack_mode(1, 0, m), c, K + 1);
-        sm_push(had, pack_mode(1, 0, m), __dmul_rn(0.8, dist), numHad);
+        reg_push(rrd, pack_mode(1, 0, m), c, K + 1);
+        reg_push(rhad, pack_mode(1, 0, m), __dmul_rn(0.8, dist), numHad);
       }
+      reg_to_sm(rrd, rd); reg_to_sm(rhad, had);           // the rest edits the lists in place (dynamic positions)
       // reduceHadCandList, :4333-4405 (compacted in place: the write index never passes the read index)
       const double thr = __dadd_rn(1.0, __ddiv_rn(1.4, __dsqrt_rn((double)(w * h))));
       const int maxPerType = K >> 1;
@@ -1109,6 +1154,8 @@ __global__ void __launch_bounds__(kListThreads) rmd_lists_kernel(const vvcb_rmd_
         }
       }
       K = rd.n;
+    } else {
+      reg_to_sm(rrd, rd); reg_to_sm(rhad, had);
     }
     sCount[tid] = rd.n;
     sCount[kListThreads + tid] = had.n;
