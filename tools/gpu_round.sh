@@ -15,9 +15,9 @@ python tools/profile_sweep.py --width 1920 --height 1080 --passes 2 > gpurun_out
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:rmd_eval_kernel -s 33 -c 33 \
   --csv --log-file gpurun_out/eval_traffic_$tag.csv python tools/profile_sweep.py --width 1920 --height 1080 --passes 2 > /dev/null 2>&1 && \
   python tools/make_traffic.py gpurun_out/eval_traffic_$tag.csv $tag
-# second pass of the sweep: 33 eval launches per pass (per tile class x kind: the packed small shapes, then -- classes 1..5 -- the larger
-# shapes): 8x8 angular packed = launch 15, 16x16+ angular = 16, 16x8 angular packed = 21, 32x8 / 32x16 angular = 22, 4x4 angular = 0
-for k in 48:eval8x8ang 49:eval16x16ang 55:eval32x8ang 33:eval4x4ang; do
+# second pass of the sweep: 33 eval launches per pass, longest first (angular: classes 3, 4, 5, 1, 2, 0, each packed then plain; then
+# MIP; then planar / DC): 8x8 angular packed = launch 0, 16x16+ angular = 1, 16x8 packed = 2, 32x8 / 32x16 angular = 3
+for k in 33:eval8x8ang 34:eval16x16ang 36:eval32x8ang; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:rmd_eval_kernel -s ${k%%:*} -c 1 -o gpurun_out/prof_${k##*:}_$tag -f \
     python tools/profile_sweep.py --width 1920 --height 1080 --passes 2 > gpurun_out/ncu_full_${k##*:}_$tag.log 2>&1; echo "ncu ${k##*:} rc=$?"
 done
@@ -26,4 +26,4 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:rmd_
 python tools/profile_tu.py --width 1920 --height 1080 --passes 2 > gpurun_out/prof_tu_plain_$tag.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dq_kernel|tu_eval_kernel" -s 3 -c 3 -o gpurun_out/prof_tu_$tag -f \
   python tools/profile_tu.py --width 1920 --height 1080 --passes 2 > gpurun_out/ncu_full_tu_$tag.log 2>&1; echo "ncu tu rc=$?"
-ls -la gpurun_out
+du -sh gpurun_out

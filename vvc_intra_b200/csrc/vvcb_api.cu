@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(const int* in, int* out, 
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
+constexpr int kSideStreams = 7;
 struct vvcb_ctx {
   int device, bd, ctu;
   cudaStream_t stream;
@@ -61,7 +62,8 @@ struct vvcb_ctx {
   void* dFeat[2]; size_t capFeat[2]; // feature scratch: jobs / per-CTU sums, results
   // copy/compute pipeline of vvcb_rmd_eval for large host batches
   cudaStream_t sIn, sOut; cudaEvent_t evIn[2], evComp[2], evOut[2];
-  cudaStream_t sKind[2]; cudaEvent_t evPlan, evKind[2];   // planar/DC and MIP buckets run beside the angular ones: their CTAs fill the tails
+  cudaStream_t sKind[kSideStreams]; cudaEvent_t evPlan, evKind[kSideStreams];   // evaluation launches are dealt over the main stream and these: the CTAs of the next kernels fill the tail of each one
+  int evalStreams;                  // streams in use (1 + side streams), VVCB_EVAL_STREAMS for A/B runs
   vvcb_rmd_visit* dVisP[2]; vvcb_rmd_result* dResP[2]; bool pipeReady;
   int16_t* dOrig; int16_t* dReco;
   const int16_t* bOrig; const int16_t* bReco;   // planes in use (own or bound)
@@ -128,7 +130,12 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
   ctx->numSms = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
-  for (int i = 0; i < 2; i++) {
+  {
+    const char* env = getenv("VVCB_EVAL_STREAMS");
+    const int v = env ? atoi(env) : 0;
+    ctx->evalStreams = v >= 1 && v <= kSideStreams + 1 ? v : kSideStreams + 1;
+  }
+  for (int i = 0; i < kSideStreams; i++) {
     if ((e = cudaStreamCreateWithFlags(&ctx->sKind[i], cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->evKind[i], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   }
@@ -189,7 +196,7 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->kev[i]);
   for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->tev[i]);
-  for (int i = 0; i < 2; i++) { cudaStreamSynchronize(ctx->sKind[i]); cudaStreamDestroy(ctx->sKind[i]); cudaEventDestroy(ctx->evKind[i]); }
+  for (int i = 0; i < kSideStreams; i++) { cudaStreamSynchronize(ctx->sKind[i]); cudaStreamDestroy(ctx->sKind[i]); cudaEventDestroy(ctx->evKind[i]); }
   cudaEventDestroy(ctx->evPlan);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -330,18 +337,26 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   P.orig = ctx->bOrig; P.reco = ctx->bReco; P.stride = ctx->stride; P.bd = ctx->bd; P.ctu = ctx->ctu; P.rom = ctx->dRom;
   P.predOut = dPred;
   const long long maxWarps = (long long)n * 8;          // no point in more warps than work items
-  // one stream per prediction kind: the launches of a kind stay ordered, kernels of different kinds overlap at their tails
+  // The launches are independent of each other (disjoint work items, disjoint scratch entries).  Every grid fills the GPU, so a kernel
+  // queued behind another one in the same stream would wait for its last CTA; dealt over several streams, the CTAs of the following
+  // kernels move in as soon as SM slots free up and no tail is exposed (profiles/r1w: 12 tails of ~50 us per sweep and per pipeline
+  // chunk).  Longest first: angular, then MIP, then planar / DC.
+  const int nSide = ctx->evalStreams - 1;
   CK(cudaEventRecord(ctx->evPlan, ctx->stream));
-  for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(ctx->sKind[i], ctx->evPlan, 0));
-  for (int b = 0; b < kNumBuckets; b++) {
-    const int kind = b % kNumKinds;
-    cudaStream_t st = kind == 0 ? ctx->stream : ctx->sKind[kind - 1];
-    // the packed small shapes of the tile class first (most of the work), then its larger shapes (the 4x4 class has none)
-    if (dPred) { VVCB_FOR_BUCKET(b, 2, launch_eval_bucket, P, ctx->numSms, maxWarps, st); continue; }
-    VVCB_FOR_BUCKET(b, 1, launch_eval_bucket, P, ctx->numSms, maxWarps, st);
-    if (b >= kNumKinds) VVCB_FOR_BUCKET(b, 0, launch_eval_bucket, P, ctx->numSms, maxWarps, st);
-  }
-  for (int i = 0; i < 2; i++) { CK(cudaEventRecord(ctx->evKind[i], ctx->sKind[i])); CK(cudaStreamWaitEvent(ctx->stream, ctx->evKind[i], 0)); }
+  for (int i = 0; i < nSide; i++) CK(cudaStreamWaitEvent(ctx->sKind[i], ctx->evPlan, 0));
+  static const int kindOrder[kNumKinds] = { KIND_ANG, KIND_MIP, KIND_PDC };
+  static const int tileOrder[kNumClasses] = { 3, 4, 5, 1, 2, 0 };
+  int dealt = 0;
+  auto next_stream = [&]() { const int k = dealt++ % ctx->evalStreams; return k == 0 ? ctx->stream : ctx->sKind[k - 1]; };
+  for (int ki = 0; ki < kNumKinds; ki++)
+    for (int ti = 0; ti < kNumClasses; ti++) {
+      const int b = tileOrder[ti] * kNumKinds + kindOrder[ki];
+      if (dPred) { VVCB_FOR_BUCKET(b, 2, launch_eval_bucket, P, ctx->numSms, maxWarps, next_stream()); continue; }
+      // the packed small shapes of the tile class, and its larger shapes (the 4x4 class has none)
+      VVCB_FOR_BUCKET(b, 1, launch_eval_bucket, P, ctx->numSms, maxWarps, next_stream());
+      if (b >= kNumKinds) VVCB_FOR_BUCKET(b, 0, launch_eval_bucket, P, ctx->numSms, maxWarps, next_stream());
+    }
+  for (int i = 0; i < nSide; i++) { CK(cudaEventRecord(ctx->evKind[i], ctx->sKind[i])); CK(cudaStreamWaitEvent(ctx->stream, ctx->evKind[i], 0)); }
   if (tm) CK(cudaEventRecord(ctx->kev[2], ctx->stream));
   if (dDetails) { rmd_detail_kernel<<<(n + 31) / 32, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dDetails, P.sadSM, P.satdSM); ctx->launches++; }
   rmd_lists_kernel<<<(n + kListThreads - 1) / kListThreads, kListThreads, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dResults, dDetails, P.sadSM, P.satdSM);
@@ -418,7 +433,18 @@ static int ensure_visit_buffers(vvcb_ctx* ctx, int n)
 // Large host batches: the batch is cut into chunks and the three stages -- visits host->device, the kernels, result lists
 // device->host -- run on three streams with double-buffered chunk storage, so that the PCIe copies and the host-side
 // validation of the next chunk hide behind the kernels of the current one.
-constexpr int kPipeChunk = 98304;
+constexpr int kPipeChunkDefault = 172032;
+// VVCB_PIPE_CHUNK (visits per chunk) is a tuning aid for the A/B runs in profiles/; read once
+static int pipe_chunk()
+{
+  static int chunk = 0;
+  if (!chunk) {
+    const char* e = getenv("VVCB_PIPE_CHUNK");
+    const long v = e ? atol(e) : 0;
+    chunk = v >= 4096 && v <= (1 << 22) ? (int)v : kPipeChunkDefault;
+  }
+  return chunk;
+}
 
 static int ensure_pipeline(vvcb_ctx* ctx)
 {
@@ -429,8 +455,8 @@ static int ensure_pipeline(vvcb_ctx* ctx)
     CK(cudaEventCreateWithFlags(&ctx->evIn[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->evComp[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->evOut[i], cudaEventDisableTiming));
-    CK(cudaMalloc(&ctx->dVisP[i], (size_t)kPipeChunk * sizeof(vvcb_rmd_visit)));
-    CK(cudaMalloc(&ctx->dResP[i], (size_t)kPipeChunk * sizeof(vvcb_rmd_result)));
+    CK(cudaMalloc(&ctx->dVisP[i], (size_t)pipe_chunk() * sizeof(vvcb_rmd_visit)));
+    CK(cudaMalloc(&ctx->dResP[i], (size_t)pipe_chunk() * sizeof(vvcb_rmd_result)));
   }
   ctx->pipeReady = true;
   return VVCB_OK;
@@ -443,8 +469,18 @@ static int rmd_eval_pipelined(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n
   const int savedTiming = ctx->timing;
   ctx->timing = 0;                                   // per-kernel timing would serialise the pipeline
   int status = VVCB_OK;
-  for (int c = 0, off = 0; off < n && status == VVCB_OK; c++, off += kPipeChunk) {
-    const int m = n - off < kPipeChunk ? n - off : kPipeChunk, b = c & 1;
+  // Chunk schedule: a short first chunk (the kernels start after a fraction of a millisecond of copying) and a short last one (the
+  // copy of its results is all that is left when the kernels end); VVCB_PIPE_EDGE for A/B runs.
+  const int chunk = pipe_chunk();
+  static int edge = -1;
+  if (edge < 0) { const char* e = getenv("VVCB_PIPE_EDGE"); const long v = e ? atol(e) : 0; edge = e && v >= 0 && v <= chunk ? (int)v : chunk / 4; }
+  for (int c = 0, off = 0, m = 0; off < n && status == VVCB_OK; c++, off += m) {
+    const int rest = n - off, b = c & 1;
+    m = rest < chunk ? rest : chunk;
+    if (edge > 0) {
+      if (c == 0 && rest > edge) m = edge;
+      else if (rest > edge && rest - m < edge) m = rest - edge;      // leave exactly one short chunk for the end
+    }
     if ((status = check_visits(ctx, visits + off, m, off))) break;
     cudaError_t e = cudaSuccess;
     if (c >= 2) e = cudaStreamWaitEvent(ctx->sIn, ctx->evComp[b], 0);              // chunk c-2 no longer reads this buffer
@@ -478,7 +514,7 @@ extern "C" int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n,
   if (n == 0) return VVCB_OK;
   if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
   CK(cudaSetDevice(ctx->device));
-  if (n > kPipeChunk && !details) return rmd_eval_pipelined(ctx, visits, n, results);
+  if (n > pipe_chunk() && !details) return rmd_eval_pipelined(ctx, visits, n, results);
   int rc = check_visits(ctx, visits, n);
   if (rc) return rc;
   rc = ensure_visit_buffers(ctx, n);
