@@ -123,7 +123,7 @@ def measured_peaks():
 
 
 def eval_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the 18 rmd_eval_kernel launches of one 1080p step, from the committed
+    """dram__bytes_read.sum + dram__bytes_write.sum of the rmd_eval_kernel launches (33: per tile class and prediction kind, packed small shapes and larger shapes) of one 1080p step, from the committed
     ncu capture (profiles/eval_traffic.json, written by tools/make_traffic.py on the GPU box)."""
     try:
         t = json.load(open(os.path.join(ROOT, 'profiles', 'eval_traffic.json')))

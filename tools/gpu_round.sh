@@ -26,4 +26,16 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:rmd_
 python tools/profile_tu.py --width 1920 --height 1080 --passes 2 > gpurun_out/prof_tu_plain_$tag.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dq_kernel|tu_eval_kernel" -s 3 -c 3 -o gpurun_out/prof_tu_$tag -f \
   python tools/profile_tu.py --width 1920 --height 1080 --passes 2 > gpurun_out/ncu_full_tu_$tag.log 2>&1; echo "ncu tu rc=$?"
+# text summaries of every capture (these are what profiles/ keeps), then trim the captures themselves: gpurun merges at most 64 MiB back
+for k in eval8x8ang eval16x16ang eval32x8ang lists tu; do
+  [ -f gpurun_out/prof_${k}_$tag.ncu-rep ] && python tools/ncu_summary.py gpurun_out/prof_${k}_$tag.ncu-rep > gpurun_out/summary_${k}_$tag.txt 2>&1
+done
+python tools/ncu_lines.py gpurun_out/prof_eval8x8ang_$tag.ncu-rep 0 ILi3ELi0ELi1 40 > gpurun_out/lines_eval8x8ang_$tag.txt 2>&1
+python tools/ncu_lines.py gpurun_out/prof_eval16x16ang_$tag.ncu-rep 0 ILi3ELi0ELi0 40 > gpurun_out/lines_eval16x16ang_$tag.txt 2>&1
+python tools/ncu_lines.py gpurun_out/prof_lists_$tag.ncu-rep 0 rmd_lists_kernel 30 rmd_lists_kernel > gpurun_out/lines_lists_$tag.txt 2>&1
+python tools/ncu_opmix.py gpurun_out/prof_eval16x16ang_$tag.ncu-rep 0 > gpurun_out/opmix_eval16x16ang_$tag.txt 2>&1
+for f in $(ls -S gpurun_out/*.ncu-rep); do
+  [ $(du -sm gpurun_out | cut -f1) -lt 56 ] && break
+  rm -f $f
+done
 du -sh gpurun_out

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""ncu CSV (dram__bytes_read.sum, dram__bytes_write.sum, gpu__time_duration.sum of the 18 rmd_eval_kernel launches of one
+"""ncu CSV (dram__bytes_read.sum, dram__bytes_write.sum, gpu__time_duration.sum of the rmd_eval_kernel launches of one
 1080p sweep) -> profiles/eval_traffic.json, which bench.py reports as roofline.traffic.
 usage: make_traffic.py <csv> <tag>"""
 import collections
