@@ -246,9 +246,17 @@ __device__ __forceinline__ int load_line_entry(const LineCtx& c, const int16_t* 
   return val;
 }
 
+#if defined(__CUDACC__)
+#define VVCB_EMUL_ASSERT(x)
+#else
+#include <assert.h>
+#define VVCB_EMUL_ASSERT(x) assert(x)          // host emulation of this source (tests/host_emul): bounds of the shared-memory lines
+#endif
+
 template <class SM>
 __device__ __forceinline__ void store_line_entry(SM& sm, int set, const LineCtx& c, int i, int val)
 {
+  VVCB_EMUL_ASSERT(c.nTop + c.extTop <= (int)(sizeof(sm.lines[0][0]) / sizeof(int16_t)) && c.nLeft + c.extLeft <= (int)(sizeof(sm.lines[0][0]) / sizeof(int16_t)));
   if (i < c.g.n) {
     bool isLeft; int k, dx, dy;
     line_pos(c.g, i, isLeft, k, dx, dy);
