@@ -247,6 +247,7 @@ def run_b200(args, rank, world, local_rank, dist):
     if rank != 0:
         return
     tu_stage = None if (args.no_tu_stage or args.resident_only) else tu_stage_leg(eng, vb, base, frames[0], int_peak)
+    feat_stage = None if (args.no_tu_stage or args.resident_only) else features_stage_leg(eng, vb, frames[0])
     ms_step = ms_total / args.steps
     value = world * args.steps * CTUS_PER_FRAME / (ms_total * 1e-3)
     eval_ms = k_eval / max(1, k_n)
@@ -284,9 +285,43 @@ def run_b200(args, rank, world, local_rank, dist):
     }
     if tu_stage:
         out['tu_stage'] = tu_stage
+    if feat_stage:
+        out['features_stage'] = feat_stage
     if world == 1 and not args.no_cpu_baseline and not args.resident_only:
         out['cpu_baseline'] = cpu_baseline_port(base, frames[0])
     print(json.dumps(out))
+
+
+def features_stage_leg(eng, vb, frame):
+    """configs[3]: the FAST_ALGORITHM classifier inputs (EL/EncCu.cpp:816-1138) of every candidate CU of a 1080p 10-bit frame (4x4
+    excluded as in the reference) plus the per-CTU Hadamard texture sums (EncCu::updateCtuDataISlice), through the host-buffer
+    entry points (job upload and result download inside the timed region); its own unit (CUs/s), next to the oracle on one core."""
+    from oracle import oracle_py as O
+    from vvc_intra_b200.features import build_sweep_feature_jobs
+    eng.frame_begin(frame)
+    jobs = build_sweep_feature_jobs(W, H)
+    hj = eng.host_array(len(jobs), vb.FEAT_JOB_DTYPE)
+    hj[:] = jobs
+    eng.features_eval(hj[:4096])
+    eng.sync()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        res = eng.features_eval(hj)
+        had = eng.ctu_hads_islice(W, H)
+    wall = (time.perf_counter() - t0) / reps
+    sample = jobs[::5]
+    t0 = time.perf_counter()
+    exp = O.features_batch(frame, sample)
+    cpu_s = time.perf_counter() - t0
+    if exp.tobytes() != res[::5].tobytes() or had.tolist() != O.ctu_hads_islice(frame, ctu=CTU).tolist():
+        raise SystemExit('bench: features differ from the oracle')
+    return {'workload': 'configs[3]: 27 classifier features of the %d candidate CUs of frame 0 (1920x1080 10-bit; the picture-size gate of the '
+                        'reference, hard-coded 416x240, not applied) + per-CTU Hadamard sums' % len(jobs),
+            'cus_per_s_e2e': len(jobs) / wall, 'e2e_ms': wall * 1e3, 'h2d_bytes': int(jobs.nbytes), 'd2h_bytes': int(res.nbytes + had.nbytes),
+            'valid_fraction': float((res['valid'] != 0).mean()),
+            'cpu_baseline': {'value': len(sample) / cpu_s, 'unit': 'CU/s', 'cores': 1, 'kind': 'port',
+                             'sample': 'oracle/vvc_oracle_feat.c on every 5th job (%d jobs, %.1f s); the same jobs are compared bit-exactly' % (len(sample), cpu_s)}}
 
 
 def tu_stage_leg(eng, vb, base, frame, int_peak):

@@ -259,6 +259,29 @@ def test_features_on_a_partitioned_picture(eng10):
     assert len(eng10.features_eval(jobs[:0])) == 0
 
 
+def test_features_full_1080p_sweep(eng10):
+    """Config 4 at its stated size: the features of every candidate CU of a 1920x1080 10-bit frame (549 660 jobs, 10-bit content
+    saturating to 255 as the reference's convertTo(CV_8U) does).  Every 97th job against the oracle; size-independent properties on
+    all of them: f0..f3 echo the job, valid <=> at least three neighbours, and a CU of a flat picture has zero gradients and variances."""
+    from make_golden import synth_yuv
+    from vvc_intra_b200.features import build_sweep_feature_jobs
+    Y = synth_yuv(1920, 1080, 10)[0].astype(np.int16)
+    jobs = build_sweep_feature_jobs(1920, 1080)
+    assert len(jobs) == 549660
+    eng10.frame_begin(Y)
+    got = eng10.features_eval(jobs)
+    sel = slice(None, None, 97)
+    assert got[sel].tobytes() == O.features_batch(Y, jobs[sel]).tobytes()
+    assert np.array_equal(got['f'][:, 0], jobs['cu']['h']) and np.array_equal(got['f'][:, 1], jobs['cu']['w'])
+    assert np.array_equal(got['f'][:, 2], jobs['cu']['qt_depth']) and np.array_equal(got['f'][:, 3], jobs['cu']['mt_depth'])
+    assert np.array_equal(got['valid'] != 0, jobs['n_neighbours'] >= 3)
+    flat = np.full_like(Y, 130)
+    eng10.frame_begin(flat)
+    gf = eng10.features_eval(jobs[::11])
+    v = gf['valid'] != 0
+    assert v.sum() > 1000 and not gf['f'][v][:, 4:12].any() and not gf['f'][v][:, 21:26].any()
+
+
 # ---- dependent quantisation (VVCB_TU_DEPQUANT) -----------------------------------------------------------
 @pytest.mark.parametrize('name,bd', [('ref_10b_128x128_qp27_depquant', 10), ('ref_8b_128x64_qp37_depquant', 8)])
 def test_dep_quant_golden_parity(name, bd, eng8, eng10):

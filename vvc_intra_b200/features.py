@@ -65,3 +65,35 @@ def classifier_decision(features, predicted_class):
     if features[26] >= 1 and predicted_class == 0:
         return None
     return PARTITION_OF_CLASS[predicted_class]
+
+
+def build_sweep_feature_jobs(width, height, ctu=128):
+    """Feature jobs of the exhaustive sweep of one picture (bench / full-size tests): every candidate CU of every 64x64 root
+    except the 4x4 ones (EL/EncCu.cpp:842), with the neighbour CUs a uniform partition into blocks of the CU's own size would
+    offer -- left, left-down, up and left-up where they lie inside the picture (a right-up block of the same size starts at
+    x + w and fails the reference's `< x + w` test, :897).  The picture-size gate of `feature_gate` (the reference's hard-coded
+    416x240) is the caller's business and not applied here."""
+    from .partition import frame_candidates
+    c = frame_candidates(width, height)
+    c = c[~((c[:, 2] == 4) & (c[:, 3] == 4))]
+    x, y, w, h = (c[:, i].astype(np.int64) for i in range(4))
+    side = np.maximum(w, h)
+    lg = np.log2(side).astype(np.int64)
+    qt = (np.log2(ctu).astype(np.int64) - lg).astype(np.uint8)
+    mt = np.minimum(3, (lg - np.log2(w).astype(np.int64)) + (lg - np.log2(h).astype(np.int64))).astype(np.uint8)
+    jobs = np.zeros(len(c), FEAT_JOB_DTYPE)
+    jobs['cu']['x'], jobs['cu']['y'], jobs['cu']['w'], jobs['cu']['h'] = x, y, w, h
+    jobs['cu']['qt_depth'], jobs['cu']['mt_depth'] = qt, mt
+    has_left, has_up = x >= w, y >= h
+    cand = [(has_left, x - w, y), (has_left & (y + 2 * h <= height), x - w, y + h), (has_up, x, y - h), (has_left & has_up, x - w, y - h)]
+    n = np.zeros(len(c), np.int64)
+    idx = np.arange(len(c))
+    for ok, nx, ny in cand:
+        sel = idx[ok]
+        k = n[sel]
+        nb = jobs['nb']
+        nb['x'][sel, k], nb['y'][sel, k], nb['w'][sel, k], nb['h'][sel, k] = nx[sel], ny[sel], w[sel], h[sel]
+        nb['qt_depth'][sel, k], nb['mt_depth'][sel, k] = qt[sel], mt[sel]
+        n[sel] += 1
+    jobs['n_neighbours'] = n
+    return jobs
