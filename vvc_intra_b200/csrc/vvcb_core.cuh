@@ -166,9 +166,11 @@ struct WorkItem {            // 8 bytes
 // unavailable sample takes the nearest earlier available sample on the walk, or the first available one.
 struct LineGeom {
   int w, h, mrl, n;          // n = walk length
-  int lo[5], hi[5];          // available intervals, ascending, [lo, hi)
-  int cnt;
+  int lo[5], hi[5];          // available intervals [lo, hi) in walk order: below-left, left, corner, above, above-right; an absent
+                             // one has lo = kNoInterval (never reached).  Fixed slots, statically indexed: the struct stays in registers.
+  int first;                 // first available walk position, -1 when nothing is available
 };
+constexpr int kNoInterval = 0x3fffffff;
 
 VHD LineGeom make_line_geom(const vvcb_rmd_visit& v, int w, int h, int mrl)
 {
@@ -176,24 +178,24 @@ VHD LineGeom make_line_geom(const vvcb_rmd_visit& v, int w, int h, int mrl)
   g.w = w; g.h = h; g.mrl = mrl;
   const int C = 2 * h + 2 * mrl + 1;
   g.n = C + 2 * w;
-  g.cnt = 0;
-  if (v.n_below_left) { g.lo[g.cnt] = h - 4 * v.n_below_left; g.hi[g.cnt] = h; g.cnt++; }
-  if (v.n_left)       { g.lo[g.cnt] = 2 * h - 4 * v.n_left;   g.hi[g.cnt] = 2 * h; g.cnt++; }
-  if (v.avail_al)     { g.lo[g.cnt] = 2 * h;                  g.hi[g.cnt] = C; g.cnt++; }
-  if (v.n_above)      { g.lo[g.cnt] = C;                      g.hi[g.cnt] = C + 4 * v.n_above; g.cnt++; }
-  if (v.n_above_right){ g.lo[g.cnt] = C + w;                  g.hi[g.cnt] = C + w + 4 * v.n_above_right; g.cnt++; }
+  g.lo[0] = v.n_below_left  ? h - 4 * v.n_below_left : kNoInterval;  g.hi[0] = h;
+  g.lo[1] = v.n_left        ? 2 * h - 4 * v.n_left   : kNoInterval;  g.hi[1] = 2 * h;
+  g.lo[2] = v.avail_al      ? 2 * h                  : kNoInterval;  g.hi[2] = C;
+  g.lo[3] = v.n_above       ? C                      : kNoInterval;  g.hi[3] = C + 4 * v.n_above;
+  g.lo[4] = v.n_above_right ? C + w                  : kNoInterval;  g.hi[4] = C + w + 4 * v.n_above_right;
+  g.first = -1;
+#pragma unroll
+  for (int k = 4; k >= 0; k--) if (g.lo[k] != kNoInterval) g.first = g.lo[k];
   return g;
 }
 
 // walk position the sample at walk position i is copied from (-1: nothing available -> mid-grey)
 VHD int line_source(const LineGeom& g, int i)
 {
-  if (g.cnt == 0) return -1;
-  int src = g.lo[0];                       // before the first interval: its first sample
-  for (int k = 0; k < 5; k++) {
-    if (k >= g.cnt) break;
+  int src = g.first;                       // before the first interval: its first sample
+#pragma unroll
+  for (int k = 0; k < 5; k++)
     if (i >= g.lo[k]) src = i < g.hi[k] ? i : g.hi[k] - 1;
-  }
   return src;
 }
 
