@@ -289,7 +289,7 @@ def run_b200(args, rank, world, local_rank, dist):
         out['features_stage'] = feat_stage
     if world == 1 and not args.no_cpu_baseline and not args.resident_only:
         out['cpu_baseline'] = cpu_baseline_port(base, frames[0])
-    print(json.dumps(out))
+    emit(out)
 
 
 def features_stage_leg(eng, vb, frame):
@@ -403,7 +403,7 @@ def run_reference(args, rank, world):
     enc = os.path.join(ROOT, 'oracle/_ref/EncoderApp')
     cfg = os.path.join(ROOT, 'oracle/_ref/encoder_intra.cfg')
     if not (os.path.exists(enc) and os.path.exists(cfg)):
-        print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref/EncoderApp was not built (run __graft_entry__.build() in the container that has /root/reference)'}))
+        emit({'impl': 'reference', 'unavailable': 'oracle/_ref/EncoderApp was not built (run __graft_entry__.build() in the container that has /root/reference)'})
         return
     cores = max(1, min(os.cpu_count() or 1, 64))
     frames = [synth_luma(f) for f in range(NFRAMES)]
@@ -438,7 +438,7 @@ def run_reference(args, rank, world):
     sample = ('unmodified reference encoder (VTM 6.1 fork, encoder_intra.cfg, all tools on, AVX2 dispatch), one process per 128x128 '
               '10-bit crop (1 CTU) of the same synthetic frames, %d processes at a time, QP cycling 32/27/37/22; '
               'full encode of the CTU (split search + full RD), not only the RMD sweep' % cores)
-    print(json.dumps({
+    emit({
         'impl': 'reference',
         'metric': 'all-intra 1080p10 CTUs/sec (exhaustive RMD sweep: intra pred + SAD/SATD + mode cost + candidate lists)',
         'value': value, 'unit': 'CTU/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -447,12 +447,26 @@ def run_reference(args, rank, world):
         'config': {'workload': 'configs[1]: all-intra 1920x1080 10-bit synthetic YUV, 8 frames, QP 22/27/32/37 (bounded sample: %d CTU crops per step)' % cores},
         'cpu_baseline': {'value': value, 'unit': 'CTU/s', 'cores': cores, 'kind': 'reference', 'sample': sample},
         'e2e': {'value': value, 'unit': 'CTU/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }))
+    })
     import shutil
     shutil.rmtree(tmp, ignore_errors=True)
 
 
+_JSON_OUT = None
+
+
+def emit(obj):
+    """The one JSON line of the contract, on the process's original stdout."""
+    _JSON_OUT.write(json.dumps(obj) + '\n')
+    _JSON_OUT.flush()
+
+
 def main():
+    global _JSON_OUT
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version there) are sent to stderr
+    _JSON_OUT = os.fdopen(os.dup(1), 'w')
+    sys.stdout.flush()
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=8)
@@ -472,7 +486,6 @@ def main():
     if world > 1:
         import torch
         import torch.distributed as dist
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')       # keep stdout to the one JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     run_b200(args, rank, world, local_rank, dist)
