@@ -30,7 +30,10 @@ constexpr int kSlotLineWords = 53 * 32;    // int16 per warp for per-slot scratc
 constexpr int kNumClasses = 6;             // SATD tile of the shape: 0 4x4, 1 8x4, 2 4x8, 3 8x8, 4 16x8, 5 8x16
 constexpr int kNumKinds   = 3;             // 0 angular, 1 planar/DC, 2 MIP
 constexpr int kNumBuckets = kNumClasses * kNumKinds;
-constexpr int kItemTasks = 128;            // lane-tasks per work item (4 warp iterations)
+#ifndef VVCB_ITEM_TASKS
+#define VVCB_ITEM_TASKS 512
+#endif
+constexpr int kItemTasks = VVCB_ITEM_TASKS;  // lane-tasks per plain work item (16 warp iterations; 128 -> 512: 2.4 % fewer line set-ups, profiles/r1w)
 
 VHD int vmin(int a, int b) { return a < b ? a : b; }
 VHD int vmax(int a, int b) { return a > b ? a : b; }

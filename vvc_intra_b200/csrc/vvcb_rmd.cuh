@@ -43,7 +43,10 @@ using WarpSmem = VisitSmem<kLineMax>;
 // planar/DC ones).  Shapes of at most two lanes per slot are therefore planned into buckets of their own, one per exact shape, and
 // the packed kernel instantiation takes kPackVisits visits of one shape at a time: their reference lines sit side by side in shared
 // memory and the slots of all of them form one flat task list.
-constexpr int kPackVisits  = 8;
+#ifndef VVCB_PACK_VISITS
+#define VVCB_PACK_VISITS 8
+#endif
+constexpr int kPackVisits  = VVCB_PACK_VISITS;
 constexpr int kLineSmall   = 52;          // sides <= 16: 2*16 + 1 + 3 + the replicated tail of 14 (16x4 on reference line 3)
 constexpr int kSmallShapes = 8;
 constexpr int kNumBucketsAll = kNumBuckets + kSmallShapes * kNumKinds;
