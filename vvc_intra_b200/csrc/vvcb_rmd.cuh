@@ -1030,7 +1030,10 @@ __device__ void store_list_detail(const SmList& L, int32_t* n, vvcb_mode* m, dou
 // One thread per visit: EL/IntraSearch.cpp:489-802 minus the predictions (already reduced to SAD/SATD, read from
 // the slot-major scratch: coalesced across the visits of a warp whenever they look at the same slot).  The result
 // structs are written by the whole warp, one visit after the other, so that every store is a full line.
-__global__ void __launch_bounds__(kListThreads) rmd_lists_kernel(const vvcb_rmd_visit* visits, int n, int ctu, vvcb_rmd_result* results,
+#ifndef VVCB_LIST_MIN_CTAS
+#define VVCB_LIST_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kListThreads, VVCB_LIST_MIN_CTAS) rmd_lists_kernel(const vvcb_rmd_visit* visits, int n, int ctu, vvcb_rmd_result* results,
                                                                  vvcb_rmd_detail* details, const uint32_t* sadSM, const uint32_t* satdSM)
 {
   __shared__ double   sRdC[kRdCap * kListThreads], sHadC[kHadCap * kListThreads];
