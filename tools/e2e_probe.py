@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Wall-clock of the host-buffer path (vvcb_frame_begin + vvcb_reco_update + vvcb_rmd_eval, pinned buffers) for one 1080p sweep."""
+"""Wall-clock of the host-buffer path (vvcb_frame_begin + vvcb_reco_update + vvcb_rmd_eval, pinned buffers) for one 1080p sweep,
+and of its parts."""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,10 +14,12 @@ with vb.IntraCostEngine(0, 10, 128) as eng:
     hv = eng.host_array(len(vis), vb.VISIT_DTYPE); hv[:] = vis
     hr = eng.host_array(len(vis), vb.RESULT_DTYPE)
     hy = eng.host_array(H * W, np.int16).reshape(H, W); hy[:] = Y
-    def step():
-        eng.frame_begin(hy); eng.reco_update(hy); eng.rmd_eval(hv, out=hr)
-    step(); step()
-    t0 = time.perf_counter()
-    for _ in range(5): step()
-    dt = (time.perf_counter() - t0) / 5
-    print('chunk', os.environ.get('VVCB_PIPE_CHUNK', 'default'), 'e2e ms per sweep %.2f' % (dt * 1e3), 'CTU/s %.0f' % (135 / dt))
+    def timed(fn, reps=5):
+        fn(); fn()
+        t0 = time.perf_counter()
+        for _ in range(reps): fn()
+        return (time.perf_counter() - t0) / reps * 1e3
+    planes = timed(lambda: (eng.frame_begin(hy), eng.reco_update(hy)))
+    evalonly = timed(lambda: eng.rmd_eval(hv, out=hr))
+    full = timed(lambda: (eng.frame_begin(hy), eng.reco_update(hy), eng.rmd_eval(hv, out=hr)))
+    print('chunk', os.environ.get('VVCB_PIPE_CHUNK', 'default'), 'planes %.2f ms, rmd_eval %.2f ms, full step %.2f ms = %.0f CTU/s' % (planes, evalonly, full, 135 / (full * 1e-3)))

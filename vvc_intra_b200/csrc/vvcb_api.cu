@@ -337,10 +337,10 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   P.orig = ctx->bOrig; P.reco = ctx->bReco; P.stride = ctx->stride; P.bd = ctx->bd; P.ctu = ctx->ctu; P.rom = ctx->dRom;
   P.predOut = dPred;
   const long long maxWarps = (long long)n * 8;          // no point in more warps than work items
-  // The launches are independent of each other (disjoint work items, disjoint scratch entries).  Every grid fills the GPU, so a kernel
-  // queued behind another one in the same stream would wait for its last CTA; dealt over several streams, the CTAs of the following
-  // kernels move in as soon as SM slots free up and no tail is exposed (profiles/r1w: 12 tails of ~50 us per sweep and per pipeline
-  // chunk).  Longest first: angular, then MIP, then planar / DC.
+  // The launches are independent of each other (disjoint work items, disjoint scratch entries) and every grid fills the GPU.  Dealt over
+  // several streams, longest first, the CTAs of the following kernels move in as soon as SM slots free up.  Measured (profiles/r1x_summary.md):
+  // no effect on a whole resident sweep (persistent warps drain within one item of each other), 20.3 -> 17.7 ms for the chunked host-buffer
+  // path, where every chunk pays the hand-over between its 33 launches.
   const int nSide = ctx->evalStreams - 1;
   CK(cudaEventRecord(ctx->evPlan, ctx->stream));
   for (int i = 0; i < nSide; i++) CK(cudaStreamWaitEvent(ctx->sKind[i], ctx->evPlan, 0));
