@@ -107,3 +107,23 @@ def test_classifier_decision():
     assert vb.classifier_decision(f, 0) is None               # fuzzy / complex blocks are never terminated early (:1197-1203)
     assert vb.classifier_decision(f, 3) == 'ETM_SPLIT_BT_V'
     assert vb.classifier_decision(f, -1) is None and vb.classifier_decision(f, None) is None
+
+
+def test_training_set_twin_differs_only_on_the_left_down_edge_case():
+    """GET_TRAINING_SET (EL/CABACWriter.cpp:515-858) collects the same neighbours as the inference side except for one comparison:
+    a left-down CU that starts exactly at the CU's bottom edge is accepted by EncCu (`<=`, :886) and rejected by the writer (`<`, :581)."""
+    rng = np.random.default_rng(17)
+    cus = random_partition(rng, 416, 240)
+    get_cu = cu_lookup(cus, 416, 240)
+    differ = same = 0
+    for c in cus:
+        a = vb.select_feature_neighbours(get_cu, c['x'], c['y'], c['w'], c['h'])
+        b = vb.select_feature_neighbours(get_cu, c['x'], c['y'], c['w'], c['h'], training_set=True)
+        if a == b:
+            same += 1
+            continue
+        differ += 1
+        dropped = [n for n in a if n not in b]
+        assert len(dropped) == 1 and b == [n for n in a if n is not dropped[0]]
+        assert dropped[0]['y'] == c['y'] + c['h'] and dropped[0]['x'] < c['x']       # the left-down CU on the edge
+    assert differ > 5 and same > 5

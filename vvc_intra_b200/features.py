@@ -23,11 +23,14 @@ def feature_gate(x, y, w, h, mt_depth, is_luma=True):
     return not (h == 4 and w == 4)
 
 
-def select_feature_neighbours(get_cu, x, y, w, h):
+def select_feature_neighbours(get_cu, x, y, w, h, training_set=False):
     """Neighbour CUs in the order the reference collects them (EL/EncCu.cpp:852-933).
 
     get_cu(px, py) -> None or a dict(x, y, w, h, qt_depth, mt_depth): the coding structure's CU covering luma
-    position (px, py) (tempCS->getCU).  Returns the list of accepted neighbours (valid_num = its length)."""
+    position (px, py) (tempCS->getCU).  Returns the list of accepted neighbours (valid_num = its length).
+    training_set=True follows the GET_TRAINING_SET twin that dumps the same features from the bitstream writer
+    (EL/CABACWriter.cpp:515-858): identical except that it accepts the left-down CU only when it starts strictly above the
+    CU's bottom edge (`<` at EL/CABACWriter.cpp:581 against `<=` at EL/EncCu.cpp:886)."""
     out = []
     left = get_cu(x - 1, y)
     up = get_cu(x, y - 1)
@@ -35,7 +38,7 @@ def select_feature_neighbours(get_cu, x, y, w, h):
     if left is not None:
         out.append(left)
         left_down = get_cu(x - 1, y + left['h'] + 1)             # offset(-1, cuLeft->lheight() + 1), :873
-        if left_down is not None and left_down['y'] <= y + h:    # :876
+        if left_down is not None and (left_down['y'] < y + h if training_set else left_down['y'] <= y + h):    # :886 / CABACWriter.cpp:581
             out.append(left_down)
     if up is not None:
         out.append(up)
