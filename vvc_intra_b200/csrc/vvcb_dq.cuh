@@ -328,7 +328,15 @@ __global__ void __launch_bounds__(kDqThreads, VVCB_DQ_MIN_CTAS) dq_kernel(DqPara
       int dLevel = -1, dPrev = -2;
       int spt = 0, spX = 0, spY = 0;
       bool zeroOut = false;
-      int pqLevel[4] = { 0, 0, 0, 0 }; long long pqDist[4] = { 0, 0, 0, 0 };
+      // Quantizer::preQuantCoeff :812-843 yields four candidates, quantisation indices q0 .. q0 + 3 filed under slot (index & 3).  A lane
+      // needs two or three of them, so instead of building the table it evaluates the slot it wants: candidate i = (slot - q0) & 3.
+      int q0 = 0;
+      long long sAdd0 = 0;
+      auto pq_level = [&](int slot) { return (q0 + ((slot - q0) & 3) + 1) >> 1; };
+      auto pq_dist = [&](int slot) {
+        const int i = (slot - q0) & 3;
+        return ((sAdd0 + (long long)i * Q.distStepAdd) * (q0 + i) + Q.distAdd) >> Q.distShift;
+      };
       if (act) {
         const int inside = scanIdx & 15;
         spX = sp.x; spY = sp.y;
@@ -336,25 +344,16 @@ __global__ void __launch_bounds__(kDqThreads, VVCB_DQ_MIN_CTAS) dq_kernel(DqPara
         else if (inside == 0 && scanIdx > 0 && scanIdx < shp.numCoeff - 16) spt = 2;             // SCAN_EOCSBB
         zeroOut = zeroOutTu && (sp.x >= effW || sp.y >= effH);
         if (!zeroOut) {
-          // ---- Quantizer::preQuantCoeff :812-843 (every lane of the group computes the same four candidates)
           const int absCoeff = vabs(coeffCur);
           const long long scaledOrg = (long long)absCoeff * Q.qScale;
-          int qIdx = vmax(1, vmin(Q.maxQIdx, (int)((scaledOrg + Q.qAdd) >> Q.qShift)));
-          long long scaledAdd = qIdx * Q.distStepAdd - scaledOrg * Q.distOrgFact;
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const long long dd = (scaledAdd * qIdx + Q.distAdd) >> Q.distShift;
-            const int slotI = qIdx & 3;
-            qIdx++;
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (j == slotI) { pqDist[j] = dd; pqLevel[j] = qIdx >> 1; }
-            scaledAdd += Q.distStepAdd;
-          }
+          q0 = vmax(1, vmin(Q.maxQIdx, (int)((scaledOrg + Q.qAdd) >> Q.qShift)));
+          sAdd0 = q0 * Q.distStepAdd - scaledOrg * Q.distOrgFact;
           // ---- State::checkRdCosts of previous state k :924-1049
           const DqState& ps = sm.st[prev * 4 + k];
-          const int lvA = k < 2 ? pqLevel[0] : pqLevel[3], lvB = k < 2 ? pqLevel[2] : pqLevel[1];
-          long long cA = ps.rdCost + (k < 2 ? pqDist[0] : pqDist[3]);
-          long long cB = ps.rdCost + (k < 2 ? pqDist[2] : pqDist[1]);
+          const int slotA = k < 2 ? 0 : 3, slotB = k < 2 ? 2 : 1;
+          const int lvA = pq_level(slotA), lvB = pq_level(slotB);
+          long long cA = ps.rdCost + pq_dist(slotA);
+          long long cB = ps.rdCost + pq_dist(slotB);
           long long cZ = ps.rdCost;
           const int32_t* rice = rom.goRiceBits[ps.goRicePar];
           if (ps.remRegBins >= 4) {
@@ -379,8 +378,8 @@ __global__ void __launch_bounds__(kDqThreads, VVCB_DQ_MIN_CTAS) dq_kernel(DqPara
         if (!zeroOut) {
           // decision d collects "A" and "Z" of source sA(d) and "B" of source sB(d): states 0/1 feed decisions 0/2, states 2/3 feed 1/3
           const int sA = k == 0 ? 0 : k == 1 ? 2 : k == 2 ? 1 : 3, sB = k == 0 ? 1 : k == 1 ? 3 : k == 2 ? 0 : 2;
-          const int lvFromA = sA < 2 ? pqLevel[0] : pqLevel[3];      // pqDataA of source sA
-          const int lvFromB = sB < 2 ? pqLevel[2] : pqLevel[1];      // pqDataB of source sB
+          const int lvFromA = pq_level(sA < 2 ? 0 : 3);              // pqDataA of source sA
+          const int lvFromB = pq_level(sB < 2 ? 2 : 1);              // pqDataB of source sB
           dCost = kDqHuge >> 2; dLevel = -1; dPrev = -2;
           // sources are visited in ascending order (xDecide :1474-1477), ties keep the earlier candidate
           if (sA < sB) {
@@ -398,8 +397,8 @@ __global__ void __launch_bounds__(kDqThreads, VVCB_DQ_MIN_CTAS) dq_kernel(DqPara
             if (c < dCost) { dCost = c; dLevel = 0; dPrev = 4 + k; }
           }
           if ((k & 1) == 0) {                                        // checkRdCostStart :1051-1066, decisions 0 and 2
-            const int lv = k == 0 ? pqLevel[0] : pqLevel[2];
-            const long long c = (k == 0 ? pqDist[0] : pqDist[2]) + sm.lastX[rom.groupIdx[spX]] + sm.lastY[rom.groupIdx[spY]] +
+            const int lv = pq_level(k);                              // pqData[0] for decision 0, pqData[2] for decision 2
+            const long long c = pq_dist(k) + sm.lastX[rom.groupIdx[spX]] + sm.lastY[rom.groupIdx[spY]] +
                                 dq_level_bits(rom, tab.gtx[0], 0, lv);
             if (c < dCost) { dCost = c; dLevel = lv; dPrev = -1; }
           }
