@@ -664,7 +664,9 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
     const int lgG   = lanes > 32 ? 5 : sh.lgLanes;
     const int gidx  = lane >> lgG, gl = lane & (gsize - 1);
     int16_t* scratch = sScratch[warp] + gidx * ((kSlotLineWords / 32) << lgG);
-    const int nTasks = maxSlots * V * lanes;
+    // visits interleaved in the task list: V, or the next power of two when the item holds fewer (the tail of a bucket; single-visit calls)
+    const int lgV = !PACK ? 0 : nv > 4 ? 3 : nv > 2 ? 2 : nv > 1 ? 1 : 0;
+    const int nTasks = (maxSlots << lgV) * lanes;
     int accSad = 0, accSatd = 0;
 
     for (int base = 0; base < nTasks; base += 32) {
@@ -674,8 +676,8 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
       int vi = 0;
       if (PACK) {
         const int r = tk >> sh.lgLanes;
-        vi = r & (V - 1);
-        int idx = r / V;
+        vi = r & ((1 << lgV) - 1);
+        int idx = r >> lgV;
         act = act && vi < nv && idx < sFirst[warp][vi];
         if (vi >= nv) vi = nv - 1;                                   // idle lanes shadow a real task
         if (idx >= sFirst[warp][vi]) idx = sFirst[warp][vi] - 1;
