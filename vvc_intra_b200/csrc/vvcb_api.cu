@@ -338,7 +338,7 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   P.predOut = dPred;
   const long long maxWarps = (long long)n * 8;          // no point in more warps than work items
   // The launches are independent of each other (disjoint work items, disjoint scratch entries) and every grid fills the GPU.  Dealt over
-  // several streams, longest first, the CTAs of the following kernels move in as soon as SM slots free up.  Measured (profiles/r1x_summary.md):
+  // several streams, longest first, the CTAs of the following kernels move in as soon as SM slots free up.  Measured (profiles/r1z_summary.md):
   // no effect on a whole resident sweep (persistent warps drain within one item of each other), 20.3 -> 17.7 ms for the chunked host-buffer
   // path, where every chunk pays the hand-over between its 33 launches.
   const int nSide = ctx->evalStreams - 1;

@@ -33,7 +33,7 @@ constexpr int kNumBuckets = kNumClasses * kNumKinds;
 #ifndef VVCB_ITEM_TASKS
 #define VVCB_ITEM_TASKS 512
 #endif
-constexpr int kItemTasks = VVCB_ITEM_TASKS;  // lane-tasks per plain work item (16 warp iterations; 128 -> 512: 2.4 % fewer line set-ups, profiles/r1x_summary.md)
+constexpr int kItemTasks = VVCB_ITEM_TASKS;  // lane-tasks per plain work item (16 warp iterations; 128 -> 512: 2.4 % fewer line set-ups, profiles/r1z_summary.md)
 
 VHD int vmin(int a, int b) { return a < b ? a : b; }
 VHD int vmax(int a, int b) { return a > b ? a : b; }
