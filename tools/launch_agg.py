@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Average duration per kernel (template instantiation) from an ncu launch list (--metrics gpu__time_duration.sum --csv).
+usage: launch_agg.py <csv>"""
 import csv,re,collections,sys
 rows=list(csv.reader(open(sys.argv[1])))
 for i,r in enumerate(rows):
