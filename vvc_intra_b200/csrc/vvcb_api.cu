@@ -375,8 +375,16 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
 template <class F> static int first_bad_index(int n, F ok)
 {
   const int kMinPerThread = 32768;
-  int threads = (int)std::thread::hardware_concurrency();
-  if (threads > 8) threads = 8;
+  // a share of the host's cores: one process per GPU is the deployment (torchrun exports LOCAL_WORLD_SIZE), VVCB_HOST_THREADS overrides
+  static int maxThreads = 0;
+  if (!maxThreads) {
+    int hc = (int)std::thread::hardware_concurrency();
+    const char* e = getenv("VVCB_HOST_THREADS");
+    const char* lw = getenv("LOCAL_WORLD_SIZE");
+    int t = e ? atoi(e) : (lw && atoi(lw) > 1 ? hc / atoi(lw) : hc);
+    maxThreads = t < 1 ? 1 : (t > 8 ? 8 : t);
+  }
+  int threads = maxThreads;
   if (threads < 1 || n < 2 * kMinPerThread) threads = 1;
   if (threads > n / kMinPerThread) threads = n / kMinPerThread > 0 ? n / kMinPerThread : 1;
   std::atomic<int> bad(n);
