@@ -76,6 +76,25 @@ def test_emulated_kernels_match_oracle_on_random_visits(emul, bd, seed):
     assert not bad, (len(bad), arr[bad[0]])
 
 
+def test_emulated_packed_items_ragged_tails_and_ctu_rows(emul):
+    """Packed work items (eight visits of one small shape per warp item, slot-major task list): 19 visits of each of the eight small
+    shapes, i.e. items of 8, 8 and 3 visits, a third of them on a CTU row boundary (no multi-reference-line slots: the visits of one
+    item have different slot counts), mixed NO_MRL / NO_MIP flags and ragged availability -- against the oracle."""
+    rng = np.random.default_rng(77)
+    bd = 10
+    orig, reco, arr = G.random_case(rng, bd, 19, plane=(512, 512))
+    small = [(2, 2), (3, 2), (2, 3), (3, 3), (4, 2), (2, 4), (4, 3), (3, 4)]
+    arr = arr[np.isin(arr['log2w'] * 8 + arr['log2h'], [lw * 8 + lh for lw, lh in small])].copy()
+    assert len(arr) == 19 * 8
+    on_row = rng.random(len(arr)) < 0.33
+    arr['y'][on_row] = 128 * rng.integers(1, 3, int(on_row.sum()))
+    res, det, _ = run_emul(emul, orig, reco, bd, arr)
+    ora, odet = O.rmd_batch(orig, reco, bd, 128, arr)
+    bad = [i for i in range(len(arr)) if res[i].tobytes() != ora[i].tobytes() or det[i].tobytes() != odet[i].tobytes()]
+    assert not bad, (len(bad), arr[bad[0]])
+    assert (det['sad'][on_row][:, 67:77] == 0xFFFFFFFF).all()          # no MRL evaluations on a CTU row boundary
+
+
 # ---- TU coding kernel (vvcb_tu.cuh) ------------------------------------------------------------------------
 def run_emul_tu(lib, orig, bd, jobs, resi, pred, rates=None, states=None):
     import vvc_intra_b200 as vb
