@@ -1,15 +1,17 @@
 // vvc_intra_b200 -- RMD device kernels (sm_100a).  Included by vvcb_api.cu (the product) and, through a
 // CUDA-on-pthreads shim, by tests/host_emul/emul_rmd.cpp (test-only lane emulation of this very source).
 //
-// Pipeline of one vvcb_rmd_eval call (all on the context's stream):
+// Pipeline of one vvcb_rmd_eval call:
 //   rmd_plan_count / rmd_plan_scan / rmd_plan_fill
-//                      cut every visit into work items of <= kItemTasks lane-tasks and bucket them by
-//                      (SATD tile class of the shape) x (prediction kind: angular, planar/DC, MIP)
-//   rmd_eval_kernel<TILE, KIND>   one launch per bucket, persistent warps pull the bucket's items.  Every
-//                      warp of a launch runs the same straight-line code (profiles/r1a: a monolithic kernel
-//                      was instruction-fetch bound).  A lane predicts one 8x8 (or 4x4) unit of one evaluation
-//                      slot, keeps the residual in registers, computes SAD and the Walsh-Hadamard SATD there,
-//                      and the slot's lanes reduce with warp shuffles.
+//                      cut every visit into work items and bucket them: the eight small shapes (at most two lanes per slot) get one
+//                      item per (visit, kind) in a bucket per (exact shape, kind); the larger shapes items of <= kItemTasks lane-tasks
+//                      in a bucket per (SATD tile class of the shape) x (prediction kind: angular, planar/DC, MIP)
+//   rmd_eval_kernel<TILE, KIND, MODE>   one launch per (tile class, kind) and item flavour (MODE 1: packed -- eight small visits per warp
+//                      item; MODE 0: plain; MODE 2: plain + prediction samples out), dealt over several streams; persistent warps pull
+//                      the bucket's items.  Every warp of a launch runs the same straight-line code (profiles/r1a: a monolithic kernel
+//                      was instruction-fetch bound; profiles/r1z: so is any instantiation above ~45 KB).  A lane predicts one 8x8 (or
+//                      4x4) unit of one evaluation slot, keeps the residual in registers, computes SAD and the Walsh-Hadamard SATD
+//                      there, and the slot's lanes reduce with warp shuffles.
 //   rmd_lists_kernel   one thread per visit: mode bits, double-precision costs and the exact replay of
 //                      the reference's candidate-list insertions
 #pragma once
