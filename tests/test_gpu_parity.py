@@ -123,6 +123,43 @@ def test_full_1080p_sweep_properties(eng10):
     assert np.all(d3['satd'][has_nb][:, :2] == 0) and np.all(d3['sad'][has_nb][:, :2] == 0)
 
 
+def test_pipeline_chunk_schedule_edges(eng10, tmp_path):
+    """The chunked host-buffer path (short first chunk, full chunks, short last chunk) for batch sizes around every boundary of the
+    schedule: a child process with VVCB_PIPE_CHUNK=4096 (edge chunks of 1024 visits) must return, for each size, exactly what the
+    one-shot path returns here."""
+    import hashlib
+    import json
+    import os
+    import subprocess
+    import sys
+    from make_golden import synth_yuv
+    sizes = [4097, 5120, 5121, 8191, 8192, 8193, 9216, 9217, 12289, 20000]
+    Y = synth_yuv(416, 240, 10)[0].astype(np.int16)
+    vis = vb.build_sweep_visits(416, 240, qp=32)
+    assert len(vis) >= max(sizes)
+    eng10.frame_begin(Y)
+    eng10.reco_update(Y)
+    want = {n: hashlib.sha256(eng10.rmd_eval(vis[:n], detail=True)[0].tobytes()).hexdigest() for n in sizes}      # detail => one shot
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = (
+        "import sys, json, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r + '/tools')\n"
+        "import vvc_intra_b200 as vb\n"
+        "from make_golden import synth_yuv\n"
+        "Y = synth_yuv(416, 240, 10)[0].astype(np.int16)\n"
+        "vis = vb.build_sweep_visits(416, 240, qp=32)\n"
+        "out = {}\n"
+        "with vb.IntraCostEngine(0, 10, 128) as eng:\n"
+        "    eng.frame_begin(Y); eng.reco_update(Y)\n"
+        "    for n in %r:\n"
+        "        out[n] = hashlib.sha256(eng.rmd_eval(vis[:n]).tobytes()).hexdigest()\n"
+        "print(json.dumps(out))\n" % (root, root, sizes))
+    r = subprocess.run([sys.executable, '-c', child], env=dict(os.environ, VVCB_PIPE_CHUNK='4096'), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = {int(k): v for k, v in json.loads(r.stdout.strip().splitlines()[-1]).items()}
+    assert got == want
+
+
 def test_error_behaviour(eng10):
     orig = np.zeros((64, 64), np.int16)
     eng10.frame_begin(orig)
