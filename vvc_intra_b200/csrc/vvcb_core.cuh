@@ -25,8 +25,8 @@ namespace vvcb {
 // ---- geometry -------------------------------------------------------------------------------------
 constexpr int kLineMax   = 140;            // samples per reference line (2*64 + 1 + 3, padded)
 constexpr int kNumSets   = 4;              // 0: line 0 unfiltered, 1: line 0 filtered, 2: line 1, 3: line 3
-constexpr int kSlotLineWords = 53 * 32;    // int16 per warp for per-slot scratch in flight (projected main lines, MIP planes): 8x8 MIP needs 16 + 32 per lane; odd stride
-                                           // spreads the lanes' scratch over the banks
+constexpr int kSlotLineWords = 54 * 32;    // int16 per warp for per-slot scratch in flight (projected main lines, MIP planes): 8x8 MIP needs 16 + 32 per lane; 54 int16 =
+                                           // 27 words per lane: word aligned (projected lines are copied in words), odd word stride over the banks
 constexpr int kNumClasses = 6;             // SATD tile of the shape: 0 4x4, 1 8x4, 2 4x8, 3 8x8, 4 16x8, 5 8x16
 constexpr int kNumKinds   = 3;             // 0 angular, 1 planar/DC, 2 MIP
 constexpr int kNumBuckets = kNumClasses * kNumKinds;

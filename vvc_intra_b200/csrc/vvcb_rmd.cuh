@@ -405,12 +405,15 @@ __device__ void build_projected_line(int16_t* buf, const SM& sm, const SlotInfo&
 {
   const int16_t* mainSrc = sm.lines[s.set][s.p.is_ver ? 0 : 1];
   const int16_t* sideSrc = sm.lines[s.set][s.p.is_ver ? 1 : 0];
-  const int n = mh + mw + 2 + s.mrl;
   const int inv = s.p.inv_angle;
-  for (int i = gl; i < n; i += gsize) {
-    const int t = i - mh;
-    buf[i] = t >= 0 ? mainSrc[t] : sideSrc[vmin((-t * inv + 256) >> 9, mh)];
-  }
+  // projected part, t in [-mh, -1]
+  for (int i = gl; i < mh; i += gsize) buf[i] = sideSrc[vmin(((mh - i) * inv + 256) >> 9, mh)];
+  // straight part, t in [0, mw + 1 + mrl], two samples per move: mh is even, the line arrays and the slot scratch are word aligned
+  // (an odd count copies one sample past the end: inside both arrays, never read)
+  const uint32_t* src2 = reinterpret_cast<const uint32_t*>(mainSrc);
+  uint32_t* dst2 = reinterpret_cast<uint32_t*>(buf + mh);
+  const int words = (mw + 3 + s.mrl) >> 1;
+  for (int i = gl; i < words; i += gsize) dst2[i] = src2[i];
 }
 
 // residual of one R x C piece against the original block, SAD accumulated.  TRANSPOSED: the prediction q is in the
