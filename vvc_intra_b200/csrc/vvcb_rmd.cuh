@@ -41,7 +41,7 @@ using WarpSmem = VisitSmem<kLineMax>;
 
 // ---- packed work items -------------------------------------------------------------------------------
 // A visit of a small CU has few lane-tasks per prediction kind (8x8: 75 angular, 2-4 planar/DC, 19 MIP slots, one lane each), so a
-// warp iteration that serves one visit runs mostly empty (profiles/r1r: 22-26 of 32 lanes active in the angular kernels, 2-4 in the
+// warp iteration that serves one visit runs mostly empty (profiles/r1z_summary.md: 22-26 of 32 lanes active in the angular kernels, 2-4 in the
 // planar/DC ones).  Shapes of at most two lanes per slot are therefore planned into buckets of their own, one per exact shape, and
 // the packed kernel instantiation takes kPackVisits visits of one shape at a time: their reference lines sit side by side in shared
 // memory and the slots of all of them form one flat task list.
@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
   __shared__ SM smem[Cfg::kWarps][V];
   __shared__ int16_t sScratch[Cfg::kWarps][kSlotLineWords];       // per-slot scratch of the slots in flight
   __shared__ vvcb_rmd_visit sVisit[Cfg::kWarps][V];
-  __shared__ int sFirst[Cfg::kWarps][V + 1];                      // packed items: number of slots of each visit
+  __shared__ int sSlots[Cfg::kWarps][V + 1];                      // packed items: number of slots of each visit
   __shared__ unsigned sIndex[Cfg::kWarps][V];                     // the visits' indices in the batch
   __shared__ uint32_t sFilt[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -626,17 +626,17 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
     const MipGeom mg = make_mip_geom(sh.w, sh.h);
     // Task list of a packed item, slot-major: task = ((slot index * V + visit) * lanes + unit), so that the 32 lanes of a warp
     // iteration work on the same few slot indices of all the visits -- the angular slots are ordered by (hor / ver, PDPC class)
-    // per shape, which keeps projection, PDPC and transposition branches uniform across the iteration (profiles/r1s: with the
+    // per shape, which keeps projection, PDPC and transposition branches uniform across the iteration (profiles/r1z_summary.md: with the
     // visits' slots laid end to end 21.5 of 32 lanes were active per instruction).
     int maxSlots = PACK ? 0 : (int)item.slot_count;
     if (PACK) {
       int c = lane < nv ? kind_slot_count(sVisit[warp][lane], KIND, P.ctu) : 0;
-      if (lane < V) sFirst[warp][lane] = c;
+      if (lane < V) sSlots[warp][lane] = c;
       for (int o = V >> 1; o > 0; o >>= 1) c = vmax(c, __shfl_xor_sync(0xffffffffu, c, o));
       maxSlots = __shfl_sync(0xffffffffu, c, 0);
     }
 
-    // ---- reference lines needed by the item's slots (loops kept rolled: code size, profiles/r1s)
+    // ---- reference lines needed by the item's slots (loops kept rolled: code size, profiles/r1z_summary.md)
 #pragma unroll 1
     for (int j = 0; j < nv; j++) {
       const vvcb_rmd_visit& v = sVisit[warp][j];
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
         if (nSets == 3) build_line_sets<3>(sm, v, sh, P.reco, P.stride, P.bd, lane);
         else            build_line_sets<1>(sm, v, sh, P.reco, P.stride, P.bd, lane);
       } else {
-        // angular / MIP kernels: one rolled copy (their hot loops feel every extra KB of code, profiles/r1s, r1u)
+        // angular / MIP kernels: one rolled copy (their hot loops feel every extra KB of code, profiles/r1z_summary.md)
 #pragma unroll 1
         for (int q = 0; q < nSets; q++) build_line_set(sm, q ? q + 1 : 0, q == 2 ? 3 : q, v, sh, P.reco, P.stride, P.bd, lane);
       }
@@ -683,9 +683,9 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
         const int r = tk >> sh.lgLanes;
         vi = r & ((1 << lgV) - 1);
         int idx = r >> lgV;
-        act = act && vi < nv && idx < sFirst[warp][vi];
+        act = act && vi < nv && idx < sSlots[warp][vi];
         if (vi >= nv) vi = nv - 1;                                   // idle lanes shadow a real task
-        if (idx >= sFirst[warp][vi]) idx = sFirst[warp][vi] - 1;
+        if (idx >= sSlots[warp][vi]) idx = sSlots[warp][vi] - 1;
         tk = (idx << sh.lgLanes) | (tk & (lanes - 1));
       }
       const vvcb_rmd_visit& v = sVisit[warp][vi];
@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
       const bool transposed = KIND == KIND_ANG && !s.p.is_ver;
       if constexpr (S == 8) {
         // An 8x8 unit is processed as two 4x8 halves by the same loop body (kept rolled: the fully unrolled unit was
-        // > 64 KB of code and instruction-fetch bound, profiles/r1e).  Rows and the first two column stages of the
+        // > 64 KB of code and instruction-fetch bound, profiles/r1m_summary.md history).  Rows and the first two column stages of the
         // Hadamard run inside a half; the column stage across the halves is folded into the absolute sum,
         // |a+b| + |a-b| = 2 max(|a|, |b|); for 16x8 / 8x16 tiles the stage across the two units of the tile is a real
         // butterfly with the partner lane.
@@ -965,7 +965,7 @@ __global__ void __launch_bounds__(256) rmd_detail_kernel(const vvcb_rmd_visit* v
 }
 
 // ---- candidate lists in shared memory: entry i of thread t lives at [i * kListThreads + t] (conflict-free, and no
-// per-thread local-memory arrays: profiles/r1e showed the local-memory version waiting on the long scoreboard)
+// per-thread local-memory arrays: an early profile (history in profiles/r1m_summary.md) showed the local-memory version waiting on the long scoreboard)
 constexpr int kRdCap = VVCB_MAX_LIST + 2, kHadCap = VVCB_MAX_HAD_LIST;
 
 struct SmList { uint32_t* m; double* c; int n; };
@@ -986,7 +986,7 @@ __device__ __forceinline__ void sm_push(SmList& L, uint32_t m, double cost, int 
   L.m[pos * kListThreads] = m; L.c[pos * kListThreads] = cost;
 }
 
-// The same list in registers while the slots are being pushed (profiles/r1r: the shared-memory insertion loops were 55 % of the
+// The same list in registers while the slots are being pushed (profiles/r1z_summary.md: the shared-memory insertion loops were 55 % of the
 // kernel's instructions and its threads diverge on them).  Fixed capacity, every step statically indexed; `worst` caches the
 // last entry of a full list so that the common case -- no better than anything kept -- is one comparison.
 template <int CAP> struct RegList { uint32_t m[CAP]; double c[CAP]; int n; double worst; };
