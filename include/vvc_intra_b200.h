@@ -133,6 +133,18 @@ int  vvcb_set_option(vvcb_ctx* ctx, int option, int value);
 int vvcb_frame_begin(vvcb_ctx* ctx, const int16_t* orig, int stride, int width, int height);
 int vvcb_reco_update(vvcb_ctx* ctx, const int16_t* reco, int stride, int x, int y, int w, int h);
 
+/* Several pictures in one context: vvcb_frame_alloc makes cleared planes of the given size without uploading anything,
+ * vvcb_orig_update writes a rectangle of the original plane (what vvcb_reco_update does for the reconstruction).  The broker
+ * (vvc_intra_b200_broker.h) keeps the pictures of all its clients side by side in one such plane; a visit's x / y then
+ * carry the picture's offset, which must be a multiple of the CTU size.                                             */
+int vvcb_frame_alloc(vvcb_ctx* ctx, int width, int height);
+int vvcb_orig_update(vvcb_ctx* ctx, const int16_t* orig, int stride, int x, int y, int w, int h);
+/* Many small reconstruction rectangles in one call (one copy + one scatter kernel): what a host walk pushes before a visit
+ * is the few rows above and columns left of the CU (EL/EncCu.cpp:1581, EL/IntraSearch.cpp:3761).  Rectangle i is the dense
+ * w*h block at samples + rects[i].offset.                                                                          */
+typedef struct vvcb_rect { int16_t x, y, w, h; uint32_t offset; } vvcb_rect;
+int vvcb_reco_update_rects(vvcb_ctx* ctx, const vvcb_rect* rects, int n, const int16_t* samples, size_t n_samples);
+
 /* Resident variant: use planes that already live in device memory (from vvcb_dev_alloc); nothing is
  * copied, the caller keeps ownership.  stride in samples, a multiple of 4.                          */
 int vvcb_frame_bind_device(vvcb_ctx* ctx, const void* d_orig, const void* d_reco, int stride, int width, int height);
@@ -251,6 +263,26 @@ typedef struct vvcb_tu_src {
 int vvcb_tu_eval_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n_visits, const vvcb_tu_src* src, const vvcb_tu_job* jobs, int n,
                       size_t n_samples, const vvcb_dq_rates* rates, const vvcb_ctx_states* states, int n_rates,
                       int32_t* coeff, int32_t* level, int16_t* reco, int16_t* pred_out, vvcb_tu_result* results);
+/* ---- one round trip per CU of the host walk ----------------------------------------------------------------------------
+ * What IntraSearch::estIntraPredLumaQT (EL/IntraSearch.cpp:289) needs from the engine for one luma CU, in one call: push the
+ * reconstructed neighbourhood (rects), run the rough mode decision of the visit (want_rmd: lists + every SAD / SATD, :430-802) and
+ * code a set of candidate TUs of that CU (jobs: xIntraCodingTUBlock, :2694, for the (mode, transform, LFNST) combinations the
+ * full-RD loop :1158 may reach; all priced on one context snapshot, rate_idx 0, because the reference restores the estimator
+ * before every candidate, :1222 / :3448).  slots[k] is the evaluation slot (VVCB_SLOT_*) of job k; jobs[k].offset addresses this
+ * request's own level / reco / pred arrays (n_jobs dense w*h blocks).  The requests of one call are independent: they may
+ * belong to different pictures of the plane (broker), which is why the reconstruction rectangles travel with them.            */
+typedef struct vvcb_cu_request {
+  const vvcb_rect* rects; int n_rects; const int16_t* rect_samples; size_t n_rect_samples;
+  const vvcb_rmd_visit* visit;           /* may be NULL when the request only pushes rectangles                                  */
+  int want_rmd;
+  const vvcb_tu_job* jobs; const uint8_t* slots; int n_jobs;
+  const vvcb_dq_rates* rates; const vvcb_ctx_states* states;   /* one snapshot each (NULL when no job needs it)                  */
+  vvcb_rmd_result* result; vvcb_rmd_detail* detail;            /* outputs of want_rmd (detail optional)                          */
+  int32_t* level; int16_t* reco; int16_t* pred;                /* optional outputs of the jobs, n_jobs * w * h each              */
+  vvcb_tu_result* tu_results;                                  /* n_jobs                                                         */
+} vvcb_cu_request;
+int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n);
+
 /* The residual part of IntraSearch::xGetIntraFracBitsQT (EL/IntraSearch.cpp:2566: xEncCoeffQT -> CABACWriter::residual_coding on the bit
  * estimator) for levels the caller already has.  levels: HOST int32, dense w*h per job at job.offset; of a job only log2w, log2h, mts_idx,
  * the VVCB_TU_TS_ALLOWED / VVCB_TU_MTS_ALLOWED flags, offset and rate_idx are read; bits[i]: fractional bits, 0 for an all-zero block.      */

@@ -77,6 +77,9 @@ struct vvcb_ctx {
   PlanState* dPlan;
   int16_t* dPred; size_t capPred;
   int numSms;
+  void* remote;                     // broker client proxy: VVCB_BROKER was set at vvcb_create (vvcb_broker.inc)
+  void* hPin[8]; size_t capPin[8];  // page-locked staging of vvcb_cu_eval / vvcb_reco_update_rects
+  void* dRect[2]; size_t capRect[2];
   uint64_t launches;
   int timing; int timedLaunches; float kms[3]; cudaEvent_t kev[4];
   char err[512];
@@ -92,6 +95,8 @@ static char g_createErr[512] = "";
       return VVCB_ERR_CUDA;                                                                               \
     }                                                                                                     \
   } while (0)
+
+#include "vvcb_broker.inc"
 
 extern "C" int vvcb_device_count(void)
 {
@@ -109,6 +114,16 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
     return VVCB_ERR_ARG;
   }
   *out = nullptr;
+  if (const char* path = getenv("VVCB_BROKER")) {         // this process is a walker: the engine lives in the broker's server process
+    vvcb_ctx* ctx = new (std::nothrow) vvcb_ctx();
+    if (!ctx) return VVCB_ERR_ARG;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = -1; ctx->bd = bit_depth; ctx->ctu = ctu_size; ctx->depQuant = 1;
+    ctx->remote = vvcbc_connect(path, bit_depth, ctu_size, g_createErr, sizeof(g_createErr));
+    if (!ctx->remote) { delete ctx; return VVCB_ERR_STATE; }
+    *out = ctx;
+    return VVCB_OK;
+  }
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || device < 0 || device >= n) {
@@ -180,8 +195,11 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
 extern "C" void vvcb_destroy(vvcb_ctx* ctx)
 {
   if (!ctx) return;
+  if (ctx->remote) { vvcbc_disconnect(ctx->remote); delete ctx; return; }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 8; i++) if (ctx->hPin[i]) cudaFreeHost(ctx->hPin[i]);
+  cudaFree(ctx->dRect[0]); cudaFree(ctx->dRect[1]);
   cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dSlotMajor);
   cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred); cudaFree(ctx->dTrRom);
   for (int i = 0; i < 20; i++) cudaFree(ctx->dTu[i]);
@@ -205,7 +223,10 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
 extern "C" int vvcb_set_option(vvcb_ctx* ctx, int option, int value)
 {
   if (!ctx) return VVCB_ERR_ARG;
-  if (option == VVCB_OPT_DEP_QUANT && (value == 0 || value == 1)) { ctx->depQuant = value; return VVCB_OK; }
+  if (option == VVCB_OPT_DEP_QUANT && (value == 0 || value == 1)) {
+    ctx->depQuant = value;
+    return ctx->remote ? vvcbc_set_option(ctx->remote, option, value, ctx->err, sizeof(ctx->err)) : VVCB_OK;
+  }
   snprintf(ctx->err, sizeof(ctx->err), "vvcb_set_option: unknown option %d or bad value %d", option, value);
   return VVCB_ERR_ARG;
 }
@@ -217,6 +238,7 @@ extern "C" int vvcb_frame_begin(vvcb_ctx* ctx, const int16_t* orig, int stride, 
     snprintf(ctx->err, sizeof(ctx->err), "vvcb_frame_begin: bad argument (width/height must be positive multiples of 4)");
     return VVCB_ERR_ARG;
   }
+  if (ctx->remote) return vvcbc_frame_begin(ctx->remote, orig, stride, width, height, ctx->err, sizeof(ctx->err));
   CK(cudaSetDevice(ctx->device));
   const int pitch = (width + 63) & ~63;
   const size_t samples = (size_t)pitch * height;
@@ -236,9 +258,128 @@ extern "C" int vvcb_frame_begin(vvcb_ctx* ctx, const int16_t* orig, int stride, 
   return VVCB_OK;
 }
 
+#define REMOTE_UNAVAILABLE(name)                                                                                      \
+  if (ctx->remote) { snprintf(ctx->err, sizeof(ctx->err), name ": not available through the broker"); return VVCB_ERR_STATE; }
+
+extern "C" int vvcb_frame_alloc(vvcb_ctx* ctx, int width, int height)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_frame_alloc");
+  if (width <= 0 || height <= 0 || (width & 3) || (height & 3)) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_frame_alloc: bad argument"); return VVCB_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const int pitch = (width + 63) & ~63;
+  const size_t samples = (size_t)pitch * height;
+  if (samples > ctx->planeSamples) {
+    cudaFree(ctx->dOrig); cudaFree(ctx->dReco);
+    ctx->dOrig = ctx->dReco = nullptr; ctx->planeSamples = 0;
+    CK(cudaMalloc(&ctx->dOrig, samples * sizeof(int16_t)));
+    CK(cudaMalloc(&ctx->dReco, samples * sizeof(int16_t)));
+    ctx->planeSamples = samples;
+  }
+  ctx->width = width; ctx->height = height; ctx->stride = pitch;
+  ctx->bOrig = ctx->dOrig; ctx->bReco = ctx->dReco;
+  CK(cudaMemsetAsync(ctx->dOrig, 0, samples * sizeof(int16_t), ctx->stream));
+  CK(cudaMemsetAsync(ctx->dReco, 0, samples * sizeof(int16_t), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_orig_update(vvcb_ctx* ctx, const int16_t* orig, int stride, int x, int y, int w, int h)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_orig_update");
+  if (!ctx->dOrig || ctx->bOrig != ctx->dOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_orig_update: no frame owned by the context"); return VVCB_ERR_STATE; }
+  if (!orig || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > ctx->width || y + h > ctx->height || stride < w) {
+    snprintf(ctx->err, sizeof(ctx->err), "vvcb_orig_update: rectangle outside the picture");
+    return VVCB_ERR_ARG;
+  }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpy2DAsync(ctx->dOrig + (size_t)y * ctx->stride + x, ctx->stride * sizeof(int16_t), orig, stride * sizeof(int16_t),
+                       w * sizeof(int16_t), h, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+
+// page-locked staging buffer i of at least `bytes`
+static int pin_buf(vvcb_ctx* ctx, int i, size_t bytes)
+{
+  if (bytes > ctx->capPin[i]) {
+    if (ctx->hPin[i]) cudaFreeHost(ctx->hPin[i]);
+    ctx->hPin[i] = nullptr; ctx->capPin[i] = 0;
+    const size_t cap = bytes + bytes / 2 + 4096;
+    CK(cudaHostAlloc(&ctx->hPin[i], cap, cudaHostAllocDefault));
+    ctx->capPin[i] = cap;
+  }
+  return VVCB_OK;
+}
+
+// one CTA per rectangle: dense w*h block -> the reconstruction plane
+__global__ void __launch_bounds__(128) reco_scatter_kernel(const vvcb_rect* __restrict__ rects, int n, const int16_t* __restrict__ samples, int16_t* __restrict__ plane, int stride)
+{
+  for (int r = blockIdx.x; r < n; r += gridDim.x) {
+    const vvcb_rect q = rects[r];
+    const int16_t* src = samples + q.offset;
+    int16_t* dst = plane + (size_t)q.y * stride + q.x;
+    const int cnt = q.w * q.h;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) { const int yy = i / q.w; dst[(size_t)yy * stride + (i - yy * q.w)] = src[i]; }
+  }
+}
+
+// rectangles + samples are already validated and sit in host memory the copies may read asynchronously until the next sync
+static int launch_reco_rects(vvcb_ctx* ctx, const vvcb_rect* rects, int n, const int16_t* samples, size_t n_samples)
+{
+  if (n == 0) return VVCB_OK;
+  for (int i = 0; i < 2; i++) {
+    const size_t need = i == 0 ? (size_t)n * sizeof(vvcb_rect) : n_samples * sizeof(int16_t);
+    if (need > ctx->capRect[i]) {
+      cudaFree(ctx->dRect[i]); ctx->dRect[i] = nullptr; ctx->capRect[i] = 0;
+      CK(cudaMalloc(&ctx->dRect[i], need * 2));
+      ctx->capRect[i] = need * 2;
+    }
+  }
+  CK(cudaMemcpyAsync(ctx->dRect[0], rects, (size_t)n * sizeof(vvcb_rect), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dRect[1], samples, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  reco_scatter_kernel<<<n < ctx->numSms * 8 ? n : ctx->numSms * 8, 128, 0, ctx->stream>>>(static_cast<const vvcb_rect*>(ctx->dRect[0]), n, static_cast<const int16_t*>(ctx->dRect[1]), ctx->dReco, ctx->stride);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return VVCB_OK;
+}
+
+static bool rect_ok(const vvcb_ctx* ctx, const vvcb_rect& r, size_t n_samples)
+{
+  return r.x >= 0 && r.y >= 0 && r.w > 0 && r.h > 0 && r.x + r.w <= ctx->width && r.y + r.h <= ctx->height && (size_t)r.offset + (size_t)r.w * r.h <= n_samples;
+}
+
+extern "C" int vvcb_reco_update_rects(vvcb_ctx* ctx, const vvcb_rect* rects, int n, const int16_t* samples, size_t n_samples)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (n < 0 || (n > 0 && (!rects || !samples))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_reco_update_rects: bad argument"); return VVCB_ERR_ARG; }
+  if (ctx->remote) {
+    vvcb_cu_request rq;
+    memset(&rq, 0, sizeof(rq));
+    rq.rects = rects; rq.n_rects = n; rq.rect_samples = samples; rq.n_rect_samples = n_samples;
+    return vvcbc_cu_eval(ctx->remote, &rq, 1, ctx->err, sizeof(ctx->err));
+  }
+  if (!ctx->dReco || ctx->bReco != ctx->dReco) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_reco_update_rects: no frame owned by the context"); return VVCB_ERR_STATE; }
+  for (int i = 0; i < n; i++)
+    if (!rect_ok(ctx, rects[i], n_samples)) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_reco_update_rects: rectangle %d is malformed or outside the picture", i); return VVCB_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const int rc = launch_reco_rects(ctx, rects, n, samples, n_samples);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+
 extern "C" int vvcb_reco_update(vvcb_ctx* ctx, const int16_t* reco, int stride, int x, int y, int w, int h)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  if (ctx->remote) {
+    if (!reco || w <= 0 || h <= 0 || stride < w) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_reco_update: bad argument"); return VVCB_ERR_ARG; }
+    std::vector<int16_t> dense((size_t)w * h);
+    for (int r = 0; r < h; r++) memcpy(&dense[(size_t)r * w], reco + (size_t)r * stride, (size_t)w * sizeof(int16_t));
+    const vvcb_rect rc = { (int16_t)x, (int16_t)y, (int16_t)w, (int16_t)h, 0 };
+    return vvcb_reco_update_rects(ctx, &rc, 1, dense.data(), dense.size());
+  }
   if (!ctx->dReco || ctx->bReco != ctx->dReco) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_reco_update: no frame owned by the context"); return VVCB_ERR_STATE; }
   if (!reco || x < 0 || y < 0 || w <= 0 || h <= 0 || x + w > ctx->width || y + h > ctx->height || stride < w) {
     snprintf(ctx->err, sizeof(ctx->err), "vvcb_reco_update: rectangle outside the picture");
@@ -254,6 +395,7 @@ extern "C" int vvcb_reco_update(vvcb_ctx* ctx, const int16_t* reco, int stride, 
 extern "C" int vvcb_frame_bind_device(vvcb_ctx* ctx, const void* d_orig, const void* d_reco, int stride, int width, int height)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_frame_bind_device");
   if (!d_orig || !d_reco || width <= 0 || height <= 0 || stride < width || (width & 3) || (height & 3) || (stride & 3)) {
     snprintf(ctx->err, sizeof(ctx->err), "vvcb_frame_bind_device: bad argument");
     return VVCB_ERR_ARG;
@@ -520,6 +662,12 @@ extern "C" int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n,
   if (!ctx) return VVCB_ERR_ARG;
   if (n < 0 || (n > 0 && (!visits || !results))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: bad argument"); return VVCB_ERR_ARG; }
   if (n == 0) return VVCB_OK;
+  if (ctx->remote) {
+    std::vector<vvcb_cu_request> rq(n);
+    memset(rq.data(), 0, (size_t)n * sizeof(vvcb_cu_request));
+    for (int i = 0; i < n; i++) { rq[i].visit = &visits[i]; rq[i].want_rmd = 1; rq[i].result = &results[i]; rq[i].detail = details ? &details[i] : nullptr; }
+    return vvcbc_cu_eval(ctx->remote, rq.data(), n, ctx->err, sizeof(ctx->err));
+  }
   if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
   CK(cudaSetDevice(ctx->device));
   if (n > pipe_chunk() && !details) return rmd_eval_pipelined(ctx, visits, n, results);
@@ -543,6 +691,7 @@ extern "C" int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n,
 extern "C" int vvcb_rmd_eval_device(vvcb_ctx* ctx, const void* d_visits, int n, void* d_results, void* d_details)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_rmd_eval_device");
   if (n < 0 || (n > 0 && (!d_visits || !d_results))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval_device: bad argument"); return VVCB_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   return launch_rmd(ctx, static_cast<const vvcb_rmd_visit*>(d_visits), n, static_cast<vvcb_rmd_result*>(d_results),
@@ -554,6 +703,7 @@ extern "C" int vvcb_rmd_eval_device(vvcb_ctx* ctx, const void* d_visits, int n, 
 static int rmd_pred_impl(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slot, int16_t* pred)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_rmd_pred");
   if (!visit || !pred || slot >= VVCB_NUM_SLOTS) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: bad argument"); return VVCB_ERR_ARG; }
   if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_pred: no frame"); return VVCB_ERR_STATE; }
   int rc = check_visits(ctx, visit, 1);
@@ -608,6 +758,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
                         const vvcb_rmd_visit* visits, int n_visits, const vvcb_tu_src* src, int16_t* pred_out)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_tu_eval");
   if (n < 0 || n_rates < 0 || (n > 0 && (!jobs || !results || (!src && !resi) || (src && (!visits || n_visits <= 0))))) {
     snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: bad argument"); return VVCB_ERR_ARG;
   }
@@ -830,12 +981,137 @@ extern "C" int vvcb_tu_eval_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, in
   return tu_eval_impl(ctx, jobs, n, nullptr, nullptr, n_samples, rates, states, n_rates, coeff, level, reco, results, visits, n_visits, src, pred_out);
 }
 
+// One round trip per CU of a host walk, for any number of independent CUs (several walkers behind the broker): the reconstruction
+// rectangles of all requests travel in one copy and one scatter launch, the rough mode decisions of all requests are one launch_rmd
+// batch, the TU candidates of all requests one tu_eval_impl batch (job offsets, visit indices and snapshot indices are re-based onto
+// the merged arrays); one stream synchronisation at the end.
+extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (n < 0 || (n > 0 && !reqs)) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: bad argument"); return VVCB_ERR_ARG; }
+  if (n == 0) return VVCB_OK;
+  if (ctx->remote) return vvcbc_cu_eval(ctx->remote, reqs, n, ctx->err, sizeof(ctx->err));
+  if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: no frame (vvcb_frame_begin / vvcb_frame_alloc)"); return VVCB_ERR_STATE; }
+  size_t nRects = 0, nRectSamples = 0, nJobs = 0, nSamples = 0;
+  int nRmd = 0, nTuReq = 0;
+  bool anyDetail = false;
+  for (int i = 0; i < n; i++) {
+    const vvcb_cu_request& q = reqs[i];
+    bool ok = q.n_rects >= 0 && q.n_jobs >= 0 && (!q.n_rects || (q.rects && q.rect_samples)) && (!(q.want_rmd || q.n_jobs) || q.visit) &&
+              (!q.want_rmd || q.result) && (!q.n_jobs || (q.jobs && q.slots && q.tu_results));
+    if (ok && q.n_rects && (!ctx->dReco || ctx->bReco != ctx->dReco)) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: rectangles need a frame owned by the context"); return VVCB_ERR_STATE; }
+    for (int k = 0; ok && k < q.n_rects; k++) ok = rect_ok(ctx, q.rects[k], q.n_rect_samples);
+    if (ok && q.n_jobs) {
+      ok = q.visit->log2w >= 2 && q.visit->log2w <= 6 && q.visit->log2h >= 2 && q.visit->log2h <= 6;
+      const size_t bs = ok ? (size_t)1 << (q.visit->log2w + q.visit->log2h) : 0;
+      for (int k = 0; ok && k < q.n_jobs; k++) {
+        const vvcb_tu_job& j = q.jobs[k];
+        ok = j.rate_idx == 0 && (size_t)j.offset + bs <= (size_t)q.n_jobs * bs &&
+             (!(j.flags & (VVCB_TU_DEPQUANT | VVCB_TU_RDOQ_TS)) || q.rates) && (!(j.flags & VVCB_TU_RATE) || q.states);
+      }
+      nJobs += (size_t)q.n_jobs; nSamples += (size_t)q.n_jobs * bs; nTuReq++;
+    }
+    if (!ok) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: request %d is malformed (pointers, rectangle outside the picture, job offset / snapshot)", i); return VVCB_ERR_ARG; }
+    nRects += (size_t)q.n_rects; nRectSamples += q.n_rects ? q.n_rect_samples : 0;
+    nRmd += q.want_rmd != 0; anyDetail = anyDetail || (q.want_rmd && q.detail);
+  }
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  // ---- reconstruction rectangles ----
+  if (nRects) {
+    if ((rc = pin_buf(ctx, 0, nRects * sizeof(vvcb_rect)))) return rc;
+    if ((rc = pin_buf(ctx, 1, nRectSamples * sizeof(int16_t)))) return rc;
+    vvcb_rect* hr = static_cast<vvcb_rect*>(ctx->hPin[0]);
+    int16_t* hs = static_cast<int16_t*>(ctx->hPin[1]);
+    size_t ri = 0, so = 0;
+    for (int i = 0; i < n; i++) {
+      const vvcb_cu_request& q = reqs[i];
+      if (!q.n_rects) continue;
+      for (int k = 0; k < q.n_rects; k++) { hr[ri] = q.rects[k]; hr[ri].offset += (uint32_t)so; ri++; }
+      memcpy(hs + so, q.rect_samples, q.n_rect_samples * sizeof(int16_t));
+      so += q.n_rect_samples;
+    }
+    if ((rc = launch_reco_rects(ctx, hr, (int)nRects, hs, nRectSamples))) return rc;
+  }
+  // ---- rough mode decision ----
+  vvcb_rmd_result* hRes = nullptr; vvcb_rmd_detail* hDet = nullptr;
+  if (nRmd) {
+    if ((rc = pin_buf(ctx, 2, (size_t)nRmd * sizeof(vvcb_rmd_visit)))) return rc;
+    if ((rc = pin_buf(ctx, 3, (size_t)nRmd * sizeof(vvcb_rmd_result)))) return rc;
+    if (anyDetail && (rc = pin_buf(ctx, 4, (size_t)nRmd * sizeof(vvcb_rmd_detail)))) return rc;
+    vvcb_rmd_visit* hv = static_cast<vvcb_rmd_visit*>(ctx->hPin[2]);
+    hRes = static_cast<vvcb_rmd_result*>(ctx->hPin[3]);
+    hDet = anyDetail ? static_cast<vvcb_rmd_detail*>(ctx->hPin[4]) : nullptr;
+    int vi = 0;
+    for (int i = 0; i < n; i++) if (reqs[i].want_rmd) hv[vi++] = *reqs[i].visit;
+    if ((rc = check_visits(ctx, hv, nRmd))) return rc;
+    if ((rc = ensure_visit_buffers(ctx, nRmd))) return rc;
+    if (anyDetail && (rc = ensure_details(ctx, nRmd))) return rc;
+    CK(cudaMemcpyAsync(ctx->dVisits, hv, (size_t)nRmd * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_rmd(ctx, ctx->dVisits, nRmd, ctx->dResults, anyDetail ? ctx->dDetails : nullptr, nullptr))) return rc;
+    CK(cudaMemcpyAsync(hRes, ctx->dResults, (size_t)nRmd * sizeof(vvcb_rmd_result), cudaMemcpyDeviceToHost, ctx->stream));
+    if (anyDetail) CK(cudaMemcpyAsync(hDet, ctx->dDetails, (size_t)nRmd * sizeof(vvcb_rmd_detail), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  // ---- TU candidates ----
+  int32_t* hLevel = nullptr; int16_t* hReco = nullptr; int16_t* hPred = nullptr;
+  std::vector<vvcb_tu_result> tuRes;
+  if (nJobs) {
+    bool wantLevel = false, wantReco = false, wantPred = false;
+    for (int i = 0; i < n; i++) if (reqs[i].n_jobs) { wantLevel = wantLevel || reqs[i].level; wantReco = wantReco || reqs[i].reco; wantPred = wantPred || reqs[i].pred; }
+    if (wantLevel) { if ((rc = pin_buf(ctx, 5, nSamples * sizeof(int32_t)))) return rc; hLevel = static_cast<int32_t*>(ctx->hPin[5]); }
+    if (wantReco)  { if ((rc = pin_buf(ctx, 6, nSamples * sizeof(int16_t)))) return rc; hReco = static_cast<int16_t*>(ctx->hPin[6]); }
+    if (wantPred)  { if ((rc = pin_buf(ctx, 7, nSamples * sizeof(int16_t)))) return rc; hPred = static_cast<int16_t*>(ctx->hPin[7]); }
+    std::vector<vvcb_rmd_visit> tv(nTuReq);
+    std::vector<vvcb_dq_rates> rates(nTuReq);
+    std::vector<vvcb_ctx_states> states(nTuReq);
+    std::vector<vvcb_tu_job> jobs(nJobs);
+    std::vector<vvcb_tu_src> src(nJobs);
+    tuRes.resize(nJobs);
+    size_t ji = 0, so = 0; int ti = 0;
+    for (int i = 0; i < n; i++) {
+      const vvcb_cu_request& q = reqs[i];
+      if (!q.n_jobs) continue;
+      tv[ti] = *q.visit;
+      if (q.rates) rates[ti] = *q.rates; else memset(&rates[ti], 0, sizeof(vvcb_dq_rates));
+      if (q.states) states[ti] = *q.states; else memset(&states[ti], 0, sizeof(vvcb_ctx_states));
+      for (int k = 0; k < q.n_jobs; k++, ji++) {
+        jobs[ji] = q.jobs[k]; jobs[ji].offset += (uint32_t)so; jobs[ji].rate_idx = (uint16_t)ti;
+        src[ji].visit = (uint32_t)ti; src[ji].slot = q.slots[k]; src[ji].pad[0] = src[ji].pad[1] = src[ji].pad[2] = 0;
+      }
+      so += (size_t)q.n_jobs << (q.visit->log2w + q.visit->log2h);
+      ti++;
+    }
+    if (nTuReq > 65535) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: more than 65535 requests with TU jobs in one call"); return VVCB_ERR_ARG; }
+    rc = tu_eval_impl(ctx, jobs.data(), (int)nJobs, nullptr, nullptr, nSamples, rates.data(), states.data(), nTuReq, nullptr, hLevel, hReco, tuRes.data(),
+                      tv.data(), nTuReq, src.data(), hPred);
+    if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+  } else CK(cudaStreamSynchronize(ctx->stream));
+  // ---- hand the outputs back ----
+  {
+    int vi = 0; size_t ji = 0, so = 0;
+    for (int i = 0; i < n; i++) {
+      vvcb_cu_request& q = reqs[i];
+      if (q.want_rmd) { *q.result = hRes[vi]; if (q.detail) *q.detail = hDet[vi]; vi++; }
+      if (q.n_jobs) {
+        const size_t ns = (size_t)q.n_jobs << (q.visit->log2w + q.visit->log2h);
+        if (q.level) memcpy(q.level, hLevel + so, ns * sizeof(int32_t));
+        if (q.reco) memcpy(q.reco, hReco + so, ns * sizeof(int16_t));
+        if (q.pred) memcpy(q.pred, hPred + so, ns * sizeof(int16_t));
+        memcpy(q.tu_results, &tuRes[ji], (size_t)q.n_jobs * sizeof(vvcb_tu_result));
+        so += ns; ji += (size_t)q.n_jobs;
+      }
+    }
+  }
+  return VVCB_OK;
+}
+
 // CABACWriter::residual_coding on given levels (HOST int32, dense per job at job.offset): jobs carry geometry, mts_idx, the
 // VVCB_TU_TS_ALLOWED / VVCB_TU_MTS_ALLOWED switches and rate_idx; bits[i] = fractional bits (0 for an all-zero block).
 extern "C" int vvcb_residual_bits(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int32_t* levels, size_t n_samples,
                                   const vvcb_ctx_states* states, int n_states, uint64_t* bits)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_residual_bits");
   if (n < 0 || (n > 0 && (!jobs || !levels || !states || !bits || n_states <= 0))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_residual_bits: bad argument"); return VVCB_ERR_ARG; }
   if (n == 0) return VVCB_OK;
   const int bad = first_bad_index(n, [&](int i) {
@@ -913,6 +1189,7 @@ static int feat_buf(vvcb_ctx* ctx, int i, size_t bytes)
 extern "C" int vvcb_ctu_hads_islice(vvcb_ctx* ctx, int32_t* out, int n_ctus)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_ctu_hads_islice");
   if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_ctu_hads_islice: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
   const int perRow = (ctx->width + ctx->ctu - 1) / ctx->ctu, rows = (ctx->height + ctx->ctu - 1) / ctx->ctu;
   if (!out || n_ctus != perRow * rows) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_ctu_hads_islice: the frame has %d CTUs", perRow * rows); return VVCB_ERR_ARG; }
@@ -941,6 +1218,7 @@ static bool feat_cu_ok(const vvcb_ctx* ctx, const vvcb_feat_cu& c)
 extern "C" int vvcb_features_eval(vvcb_ctx* ctx, const vvcb_feat_job* jobs, int n, vvcb_feat_result* results)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_features_eval");
   if (n < 0 || (n > 0 && (!jobs || !results))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_features_eval: bad argument"); return VVCB_ERR_ARG; }
   if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_features_eval: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
   if (n == 0) return VVCB_OK;
@@ -976,6 +1254,8 @@ extern "C" int vvcb_dev_alloc(vvcb_ctx* ctx, size_t bytes, void** out)
 extern "C" int vvcb_dev_free(vvcb_ctx* ctx, void* p)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_dev_free");
+  REMOTE_UNAVAILABLE("vvcb_dev_alloc");
   CK(cudaSetDevice(ctx->device));
   CK(cudaFree(p));
   return VVCB_OK;
@@ -990,12 +1270,15 @@ extern "C" int vvcb_host_alloc(vvcb_ctx* ctx, size_t bytes, void** out)
 extern "C" int vvcb_host_free(vvcb_ctx* ctx, void* p)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_host_free");
+  REMOTE_UNAVAILABLE("vvcb_host_alloc");
   CK(cudaFreeHost(p));
   return VVCB_OK;
 }
 extern "C" int vvcb_dev_upload(vvcb_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_dev_upload");
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1004,6 +1287,7 @@ extern "C" int vvcb_dev_upload(vvcb_ctx* ctx, void* dst, const void* src, size_t
 extern "C" int vvcb_dev_download(vvcb_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_dev_download");
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1012,6 +1296,7 @@ extern "C" int vvcb_dev_download(vvcb_ctx* ctx, void* dst, const void* src, size
 extern "C" int vvcb_sync(vvcb_ctx* ctx)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_sync");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   return VVCB_OK;
@@ -1019,6 +1304,7 @@ extern "C" int vvcb_sync(vvcb_ctx* ctx)
 extern "C" int vvcb_timer_start(vvcb_ctx* ctx)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_timer_start");
   CK(cudaSetDevice(ctx->device));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   return VVCB_OK;
@@ -1035,6 +1321,8 @@ extern "C" int vvcb_timer_stop(vvcb_ctx* ctx, float* ms)
 extern "C" int vvcb_measure_int_peak(vvcb_ctx* ctx, double* gops_imad, double* gops_alu, double* gops_mixed)
 {
   if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_measure_int_peak");
+  REMOTE_UNAVAILABLE("vvcb_timer_stop");
   CK(cudaSetDevice(ctx->device));
   const int grid = ctx->numSms * 8, iters = 4096;
   int *dIn = nullptr, *dOut = nullptr;

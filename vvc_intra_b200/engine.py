@@ -56,6 +56,18 @@ FEAT_RESULT_DTYPE = np.dtype([('f', '<i4', 27), ('valid', '<i4')])
 assert FEAT_JOB_DTYPE.itemsize == 56 and FEAT_RESULT_DTYPE.itemsize == 112
 
 
+RECT_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('w', '<i2'), ('h', '<i2'), ('offset', '<u4')])
+assert RECT_DTYPE.itemsize == 12
+
+
+class CuRequest(C.Structure):
+    """struct vvcb_cu_request: one CU of a host walk (rectangles to push, the visit, TU candidates, output pointers)."""
+    _fields_ = [('rects', C.c_void_p), ('n_rects', C.c_int), ('rect_samples', C.c_void_p), ('n_rect_samples', C.c_size_t),
+                ('visit', C.c_void_p), ('want_rmd', C.c_int), ('jobs', C.c_void_p), ('slots', C.c_void_p), ('n_jobs', C.c_int),
+                ('rates', C.c_void_p), ('states', C.c_void_p), ('result', C.c_void_p), ('detail', C.c_void_p),
+                ('level', C.c_void_p), ('reco', C.c_void_p), ('pred', C.c_void_p), ('tu_results', C.c_void_p)]
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -112,6 +124,13 @@ def load_library():
         L.vvcb_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.vvcb_tu_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.vvcb_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.vvcb_frame_alloc.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.vvcb_orig_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.vvcb_reco_update_rects.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.vvcb_cu_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.vvcb_broker_serve.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.vvcb_broker_stop.argtypes = [C.c_char_p]
+        L.vvcb_broker_read_stats.argtypes = [C.c_char_p, C.c_void_p]
         L.vvcb_timer_start.argtypes = [C.c_void_p]
         L.vvcb_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         _lib = L
@@ -164,6 +183,57 @@ class IntraCostEngine:
     def reco_update(self, reco, x=0, y=0):
         reco = np.ascontiguousarray(reco, np.int16)
         self._ck(self._lib.vvcb_reco_update(self._ctx, _ptr(reco), reco.shape[1], x, y, reco.shape[1], reco.shape[0]))
+
+    def frame_alloc(self, width, height):
+        """vvcb_frame_alloc: cleared planes for several pictures side by side (what the broker keeps)."""
+        self._ck(self._lib.vvcb_frame_alloc(self._ctx, width, height))
+
+    def orig_update(self, orig, x=0, y=0):
+        orig = np.ascontiguousarray(orig, np.int16)
+        self._ck(self._lib.vvcb_orig_update(self._ctx, _ptr(orig), orig.shape[1], x, y, orig.shape[1], orig.shape[0]))
+
+    def reco_update_rects(self, rects, samples):
+        rects = np.ascontiguousarray(rects, RECT_DTYPE)
+        samples = np.ascontiguousarray(samples, np.int16).ravel()
+        self._ck(self._lib.vvcb_reco_update_rects(self._ctx, _ptr(rects), len(rects), _ptr(samples), samples.size))
+
+    def cu_eval(self, requests):
+        """vvcb_cu_eval.  requests: list of dicts with optional keys rects (RECT_DTYPE) + rect_samples, visit (VISIT_DTYPE, 1 entry),
+        want_rmd, jobs (TU_JOB_DTYPE) + slots (uint8) [+ rates (DQ_RATES_DTYPE, 1), states (CTX_STATES_DTYPE, 1)].  Returns a list of
+        dicts: result / detail (want_rmd), level / reco / pred / tu_results (jobs)."""
+        arr = (CuRequest * len(requests))()
+        keep, outs = [], []
+        for r, q in zip(arr, requests):
+            o = {}
+            if q.get('rects') is not None and len(q['rects']):
+                rc = np.ascontiguousarray(q['rects'], RECT_DTYPE)
+                sm = np.ascontiguousarray(q['rect_samples'], np.int16).ravel()
+                keep += [rc, sm]
+                r.rects, r.n_rects, r.rect_samples, r.n_rect_samples = rc.ctypes.data, len(rc), sm.ctypes.data, sm.size
+            if q.get('visit') is not None:
+                v = np.ascontiguousarray(q['visit'], VISIT_DTYPE).reshape(1)
+                keep.append(v)
+                r.visit = v.ctypes.data
+                bs = 1 << (int(v['log2w'][0]) + int(v['log2h'][0]))
+            if q.get('want_rmd'):
+                o['result'], o['detail'] = np.zeros(1, RESULT_DTYPE), np.zeros(1, DETAIL_DTYPE)
+                r.want_rmd, r.result, r.detail = 1, o['result'].ctypes.data, o['detail'].ctypes.data
+            if q.get('jobs') is not None and len(q['jobs']):
+                jb = np.ascontiguousarray(q['jobs'], TU_JOB_DTYPE)
+                sl = np.ascontiguousarray(q['slots'], np.uint8)
+                keep += [jb, sl]
+                r.jobs, r.slots, r.n_jobs = jb.ctypes.data, sl.ctypes.data, len(jb)
+                for key, dt in (('rates', DQ_RATES_DTYPE), ('states', CTX_STATES_DTYPE)):
+                    if q.get(key) is not None:
+                        a = np.ascontiguousarray(q[key], dt).reshape(1)
+                        keep.append(a)
+                        setattr(r, key, a.ctypes.data)
+                o['level'], o['reco'], o['pred'] = np.zeros(len(jb) * bs, np.int32), np.zeros(len(jb) * bs, np.int16), np.zeros(len(jb) * bs, np.int16)
+                o['tu_results'] = np.zeros(len(jb), TU_RESULT_DTYPE)
+                r.level, r.reco, r.pred, r.tu_results = o['level'].ctypes.data, o['reco'].ctypes.data, o['pred'].ctypes.data, o['tu_results'].ctypes.data
+            outs.append(o)
+        self._ck(self._lib.vvcb_cu_eval(self._ctx, C.byref(arr), len(requests)))
+        return outs
 
     def frame_bind_device(self, d_orig, d_reco, stride, width, height):
         self._ck(self._lib.vvcb_frame_bind_device(self._ctx, d_orig, d_reco, stride, width, height))
