@@ -289,6 +289,8 @@ def run_b200(args, rank, world, local_rank, dist):
         out['features_stage'] = feat_stage
     if world == 1 and not args.no_cpu_baseline and not args.resident_only:
         out['cpu_baseline'] = cpu_baseline_port(base, frames[0])
+    if world == 1 and not args.no_bitexact and not args.resident_only:
+        out['bitexact'] = bitexact_leg(frames, local_rank)
     emit(out)
 
 
@@ -397,6 +399,97 @@ def cpu_baseline_port(base, frame):
             'sample': 'oracle/vvc_oracle.c, same exhaustive sweep, the %d visits of the first two CTU rows (30 CTUs) of frame 0, %.1f s' % (len(sel), dt)}
 
 
+def write_crop(d, frames, k):
+    """Input of walker k: a 128x128 10-bit crop (1 CTU) of the synthetic frames with flat chroma -- the same crops the reference arm encodes."""
+    crops = [(cx, cy) for cy in range(0, H - CTU + 1, CTU) for cx in range(0, W - CTU + 1, CTU)]
+    cx, cy = crops[(7 * k) % len(crops)]
+    os.makedirs(d, exist_ok=True)
+    y = frames[k % NFRAMES][cy:cy + CTU, cx:cx + CTU].astype('<u2')
+    c = np.full((CTU // 2, CTU // 2), 512, '<u2')
+    open(os.path.join(d, 'in.yuv'), 'wb').write(y.tobytes() + c.tobytes() + c.tobytes())
+    open(os.path.join(d, 'Time_python.dat'), 'w').close()
+
+
+def encoder_cmd(enc, cfg, qp, out):
+    return [enc, '-c', cfg, '-i', 'in.yuv', '-wdt', str(CTU), '-hgt', str(CTU), '-q', str(qp), '-f', '1', '-fr', '30', '-b', out,
+            '--InputBitDepth=10', '--InternalBitDepth=10', '--OutputBitDepth=10']
+
+
+def bitexact_leg(frames, device):
+    """The bit-exact use of the engine, measured like for like (SURVEY.md 7.2 option A): N walker processes -- the UNMODIFIED reference
+    encoder with its luma intra cost evaluation served by the engine (oracle/_ref/EncoderAppServe), one 128x128 10-bit CTU crop each,
+    QP cycling 22/27/32/37 -- share ONE engine context through the broker (vvc_intra_b200/vvcb_broker); next to it the plain reference
+    encoder on the same crops and the same host cores.  Every served bitstream must equal the plain one byte for byte."""
+    ref = os.path.join(ROOT, 'oracle/_ref')
+    plain, served, cfg = (os.path.join(ref, f) for f in ('EncoderApp', 'EncoderAppServe', 'encoder_intra.cfg'))
+    broker = os.environ.get('VVCB_BENCH_BROKER') or os.path.join(ROOT, 'vvc_intra_b200/vvcb_broker')     # override: development against the CPU stand-in
+    if not all(os.path.exists(p) for p in (plain, served, cfg, broker)):
+        return {'unavailable': 'oracle/_ref/EncoderAppServe or vvc_intra_b200/vvcb_broker was not built (run __graft_entry__.build() in the container that has /root/reference)'}
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    over = max(1, int(os.environ.get('VVCB_BENCH_OVERSUBSCRIBE', '4')))
+    workers = max(1, int(os.environ.get('VVCB_BENCH_WORKERS', '6')))
+    n = cores * over
+    tmp = tempfile.mkdtemp(prefix='vvcbit_')
+    env = dict(os.environ)
+    env.pop('VVCB_BROKER', None)
+    qps = [QPS[k % len(QPS)] for k in range(n)]
+    for k in range(n):
+        write_crop(os.path.join(tmp, 'w%d' % k), frames, k)
+    # plain reference: `cores` processes at a time
+    t0 = time.perf_counter()
+    for base in range(0, n, cores):
+        procs = [subprocess.Popen(encoder_cmd(plain, cfg, qps[k], 'plain.bin'), cwd=os.path.join(tmp, 'w%d' % k), env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                 for k in range(base, min(n, base + cores))]
+        if any(p.wait() for p in procs):
+            raise SystemExit('bench: the plain reference encoder failed')
+    plain_s = time.perf_counter() - t0
+    # served: all walkers at once behind one broker (they sleep while the engine works, so more walkers than cores keep the cores busy)
+    path = os.path.join(tmp, 'broker.shm')
+    server = subprocess.Popen([broker, path, '--device', str(device), '--bit-depth', '10', '--clients', str(n), '--frame', '%dx%d' % (CTU, CTU), '--workers', str(workers)], env=env,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    try:
+        for _ in range(1200):
+            if os.path.exists(path) or server.poll() is not None:
+                break
+            time.sleep(0.05)
+        if server.poll() is not None:
+            raise SystemExit('bench: the broker did not start: ' + server.stderr.read()[-500:])
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen(encoder_cmd(served, cfg, qps[k], 'served.bin'), cwd=os.path.join(tmp, 'w%d' % k),
+                                  env=dict(env, VVCB_BROKER=path, VVCB_SHIM_REPORT=os.path.join(tmp, 'w%d' % k, 'report.json')), stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+                 for k in range(n)]
+        for p in procs:
+            _, err = p.communicate()
+            if p.returncode:
+                raise SystemExit('bench: a served encoder failed: ' + err[-500:])
+        served_s = time.perf_counter() - t0
+        stats = json.loads(subprocess.check_output([broker, path, '--stats'], env=env))
+    finally:
+        subprocess.run([broker, path, '--stop'], env=env)
+        try:
+            server.wait(timeout=60)
+        except subprocess.TimeoutExpired:
+            server.kill()
+    same = sum(open(os.path.join(tmp, 'w%d' % k, 'plain.bin'), 'rb').read() == open(os.path.join(tmp, 'w%d' % k, 'served.bin'), 'rb').read() for k in range(n))
+    if same != n:
+        raise SystemExit('bench: %d of %d served bitstreams differ from the plain reference encoder\'s' % (n - same, n))
+    reps = [json.load(open(os.path.join(tmp, 'w%d' % k, 'report.json'))) for k in range(n)]
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    tot = lambda key: sum(r[key] for r in reps)
+    return {'workload': '%d walkers = %d host cores x %d: 128x128 10-bit CTU crops of the synthetic 1080p frames, QP cycling 32/27/37/22, shipped cfg (all tools on); '
+                        'full encode of the CTU (split search + full RD + chroma), luma whole-CU cost evaluation served by the engine through one broker context' % (n, cores, over),
+            'ctus_per_s': n / served_s, 'plain_reference_ctus_per_s': n / plain_s, 'ratio': plain_s / served_s, 'cores': cores, 'walkers': n, 'broker_workers': workers,
+            'bitstreams_identical': same, 'seconds': {'served': served_s, 'plain': plain_s},
+            'engine_busy_frac': stats['busy_ns'] / stats['wall_ns'] / workers if stats['wall_ns'] else None,
+            'broker': {k: stats[k] for k in ('cycles', 'requests', 'visits', 'tu_jobs', 'max_batch', 'kernel_launches')},
+            'mean_round_trips_merged_per_batch': stats['requests'] / max(1, stats['cycles']),
+            'walker_wait_for_engine_s_mean': tot('engine_wait_s') / n,
+            'served_calls': {k: tot(k) for k in ('visits', 'predictions_skipped', 'distortions_served', 'tu_quantised', 'tu_sse', 'tu_residual_bits', 'jobs_prefetched', 'demand_round_trips')},
+            'note': 'like for like: same crops, same cores, same encoder binary objects; ISP sub-partitions, chroma and the split walk itself still run the reference code on the host '
+                    '(about 60 % of its CPU time), which bounds the ratio (Amdahl); engine_busy_frac = share of wall time a broker worker thread spends inside engine calls (mean over the workers)'}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -474,6 +567,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-tu-stage', action='store_true')
+    ap.add_argument('--no-bitexact', action='store_true', help='skip the brokered bit-exact encode leg (walker processes + plain reference on the host cores)')
     ap.add_argument('--resident-only', action='store_true', help='profiling aid: only the HBM-resident timed loop (no e2e / TU / CPU legs); not a bench line')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

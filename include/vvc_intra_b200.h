@@ -123,6 +123,9 @@ int  vvcb_device_count(void);
 /* Slice-level tool switches the kernels need to know.  VVCB_OPT_DEP_QUANT: slice->getDepQuantEnabledFlag() (default 1, the shipped
  * configuration): residual_coding then picks its significance context set with the quantiser state machine (EL/CABACWriter.cpp:3866). */
 #define VVCB_OPT_DEP_QUANT 1
+/* VVCB_OPT_YIELD_SYNC (default 0): 1 = the calling thread sleeps while it waits for the device (blocking event) instead of polling; for
+ * hosts whose cores are shared with the encoder's walkers (the broker's worker threads).                                            */
+#define VVCB_OPT_YIELD_SYNC 2
 int  vvcb_set_option(vvcb_ctx* ctx, int option, int value);
 
 /* ---- picture planes -------------------------------------------------------------------------
@@ -138,6 +141,10 @@ int vvcb_reco_update(vvcb_ctx* ctx, const int16_t* reco, int stride, int x, int 
  * (vvc_intra_b200_broker.h) keeps the pictures of all its clients side by side in one such plane; a visit's x / y then
  * carry the picture's offset, which must be a multiple of the CTU size.                                             */
 int vvcb_frame_alloc(vvcb_ctx* ctx, int width, int height);
+/* dst uses the planes of src (same device, src owns them and must outlive dst): several contexts -- one per worker thread of the broker,
+ * each with its own stream and scratch -- evaluate requests of different pictures of one plane concurrently.  Rectangle updates through
+ * dst write the shared reconstruction plane; callers keep concurrent writers on disjoint pictures.                                    */
+int vvcb_frame_share(vvcb_ctx* dst, vvcb_ctx* src);
 int vvcb_orig_update(vvcb_ctx* ctx, const int16_t* orig, int stride, int x, int y, int w, int h);
 /* Many small reconstruction rectangles in one call (one copy + one scatter kernel): what a host walk pushes before a visit
  * is the few rows above and columns left of the CU (EL/EncCu.cpp:1581, EL/IntraSearch.cpp:3761).  Rectangle i is the dense

@@ -24,16 +24,18 @@ typedef struct vvcb_broker_stats {
   uint64_t cu_requests;       /* vvcb_cu_request entries inside them                                          */
   uint64_t visits, tu_jobs;   /* rough-mode-decision visits and TU jobs evaluated                             */
   uint64_t max_batch;         /* largest number of round trips merged into one batch                          */
-  uint64_t busy_ns;           /* wall time the server spent inside engine calls                               */
+  uint64_t busy_ns;           /* time the worker threads spent inside engine calls, summed over the workers   */
   uint64_t wall_ns;           /* wall time since the server started serving                                   */
   uint64_t clients_seen;      /* clients that ever connected                                                  */
   uint64_t kernel_launches;   /* vvcb_launch_count of the server's context                                    */
 } vvcb_broker_stats;
 
-/* Server: creates the broker file at `path`, the engine context on `device` and a plane that holds max_clients pictures of at
- * most frame_width x frame_height, then serves until vvcb_broker_stop(path) is called (from any process).  Blocking; returns
- * VVCB_OK after a clean stop.                                                                                                 */
-int vvcb_broker_serve(const char* path, int device, int bit_depth, int ctu_size, int max_clients, int frame_width, int frame_height);
+/* Server: creates the broker file at `path`, `workers` engine contexts on `device` (one per worker thread, each with its own stream,
+ * all sharing one plane that holds max_clients pictures of at most frame_width x frame_height), then serves until
+ * vvcb_broker_stop(path) is called (from any process).  A worker claims the requests that are pending when it looks and runs them as
+ * one batch; several workers keep several batches in flight, so a batch with a long serial chain (a 32x32 dependent quantisation)
+ * does not hold up the walkers of the next one.  Blocking; returns VVCB_OK after a clean stop.                                     */
+int vvcb_broker_serve(const char* path, int device, int bit_depth, int ctu_size, int max_clients, int frame_width, int frame_height, int workers);
 int vvcb_broker_stop(const char* path);
 int vvcb_broker_read_stats(const char* path, vvcb_broker_stats* out);   /* readable while serving and after the stop        */
 

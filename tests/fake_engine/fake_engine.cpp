@@ -11,18 +11,21 @@
 #include <string.h>
 #include <vector>
 #include <map>
+#include <mutex>
 #include "../../oracle/vvc_oracle.h"
 #include "../../include/vvc_intra_b200_broker.h"
 
 struct vvcb_ctx {
   int bd, ctu, depQuant;
   int width, height;
-  std::vector<int16_t> orig, reco;
+  std::vector<int16_t> origOwn, recoOwn;
+  std::vector<int16_t>* origP; std::vector<int16_t>* recoP;   // own planes, or another context's (vvcb_frame_share)
   void* remote;                 // broker client proxy (vvcb_broker.inc)
   char err[512];
 };
 
 static char g_createErr[512] = "";
+static std::mutex g_oracleMutex;      // the oracle keeps static scratch (single-threaded checker): the broker's worker threads take turns
 #define FAIL(code, ...) do { snprintf(ctx->err, sizeof(ctx->err), __VA_ARGS__); return code; } while (0)
 
 #define VVCB_BROKER_IMPL_FAKE 1
@@ -39,6 +42,7 @@ int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_size)
   if (!out || bit_depth < 8 || bit_depth > 12 || ctu_size < 32 || (ctu_size & (ctu_size - 1))) { snprintf(g_createErr, sizeof(g_createErr), "vvcb_create: bad argument"); return VVCB_ERR_ARG; }
   vvcb_ctx* ctx = new vvcb_ctx();
   ctx->bd = bit_depth; ctx->ctu = ctu_size; ctx->depQuant = 1; ctx->width = ctx->height = 0; ctx->remote = nullptr; ctx->err[0] = 0;
+  ctx->origP = &ctx->origOwn; ctx->recoP = &ctx->recoOwn;
   if (const char* path = getenv("VVCB_BROKER")) {
     ctx->remote = vvcbc_connect(path, bit_depth, ctu_size, g_createErr, sizeof(g_createErr));
     if (!ctx->remote) { delete ctx; return VVCB_ERR_STATE; }
@@ -57,6 +61,7 @@ int vvcb_set_option(vvcb_ctx* ctx, int option, int value)
     if (ctx->remote) return vvcbc_set_option(ctx->remote, option, value, ctx->err, sizeof(ctx->err));
     return VVCB_OK;
   }
+  if (option == VVCB_OPT_YIELD_SYNC && (value == 0 || value == 1)) return VVCB_OK;
   FAIL(VVCB_ERR_ARG, "vvcb_set_option: unknown option");
 }
 
@@ -66,7 +71,15 @@ int vvcb_frame_alloc(vvcb_ctx* ctx, int width, int height)
   if (ctx->remote) FAIL(VVCB_ERR_STATE, "vvcb_frame_alloc: not available through the broker");
   if (width <= 0 || height <= 0 || (width & 3) || (height & 3)) FAIL(VVCB_ERR_ARG, "vvcb_frame_alloc: bad argument");
   ctx->width = width; ctx->height = height;
-  ctx->orig.assign((size_t)width * height, 0); ctx->reco.assign((size_t)width * height, 0);
+  ctx->origP = &ctx->origOwn; ctx->recoP = &ctx->recoOwn;
+  (*ctx->origP).assign((size_t)width * height, 0); (*ctx->recoP).assign((size_t)width * height, 0);
+  return VVCB_OK;
+}
+
+int vvcb_frame_share(vvcb_ctx* dst, vvcb_ctx* src)
+{
+  if (!dst || !src || src->origOwn.empty()) return VVCB_ERR_STATE;
+  dst->origP = &src->origOwn; dst->recoP = &src->recoOwn; dst->width = src->width; dst->height = src->height;
   return VVCB_OK;
 }
 
@@ -77,7 +90,7 @@ int vvcb_frame_begin(vvcb_ctx* ctx, const int16_t* orig, int stride, int width, 
   if (ctx->remote) return vvcbc_frame_begin(ctx->remote, orig, stride, width, height, ctx->err, sizeof(ctx->err));
   int rc = vvcb_frame_alloc(ctx, width, height);
   if (rc) return rc;
-  for (int y = 0; y < height; y++) memcpy(&ctx->orig[(size_t)y * width], orig + (size_t)y * stride, width * sizeof(int16_t));
+  for (int y = 0; y < height; y++) memcpy(&(*ctx->origP)[(size_t)y * width], orig + (size_t)y * stride, width * sizeof(int16_t));
   return VVCB_OK;
 }
 
@@ -99,14 +112,14 @@ int vvcb_reco_update(vvcb_ctx* ctx, const int16_t* reco, int stride, int x, int 
     vvcb_rect rc = { (int16_t)x, (int16_t)y, (int16_t)w, (int16_t)h, 0 };
     return vvcb_reco_update_rects(ctx, &rc, 1, dense.data(), dense.size());
   }
-  return put_rect(ctx, ctx->reco, reco, stride, x, y, w, h, "vvcb_reco_update");
+  return put_rect(ctx, (*ctx->recoP), reco, stride, x, y, w, h, "vvcb_reco_update");
 }
 
 int vvcb_orig_update(vvcb_ctx* ctx, const int16_t* orig, int stride, int x, int y, int w, int h)
 {
   if (!ctx) return VVCB_ERR_ARG;
   if (ctx->remote) FAIL(VVCB_ERR_STATE, "vvcb_orig_update: not available through the broker");
-  return put_rect(ctx, ctx->orig, orig, stride, x, y, w, h, "vvcb_orig_update");
+  return put_rect(ctx, (*ctx->origP), orig, stride, x, y, w, h, "vvcb_orig_update");
 }
 
 int vvcb_reco_update_rects(vvcb_ctx* ctx, const vvcb_rect* rects, int n, const int16_t* samples, size_t n_samples)
@@ -121,7 +134,7 @@ int vvcb_reco_update_rects(vvcb_ctx* ctx, const vvcb_rect* rects, int n, const i
   }
   for (int i = 0; i < n; i++) {
     if (rects[i].w <= 0 || rects[i].h <= 0 || (size_t)rects[i].offset + (size_t)rects[i].w * rects[i].h > n_samples) FAIL(VVCB_ERR_ARG, "vvcb_reco_update_rects: rectangle %d is malformed", i);
-    int rc = put_rect(ctx, ctx->reco, samples + rects[i].offset, rects[i].w, rects[i].x, rects[i].y, rects[i].w, rects[i].h, "vvcb_reco_update_rects");
+    int rc = put_rect(ctx, (*ctx->recoP), samples + rects[i].offset, rects[i].w, rects[i].x, rects[i].y, rects[i].w, rects[i].h, "vvcb_reco_update_rects");
     if (rc) return rc;
   }
   return VVCB_OK;
@@ -149,10 +162,10 @@ int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_r
     for (int i = 0; i < n; i++) { rq[i].visit = &visits[i]; rq[i].want_rmd = 1; rq[i].result = &results[i]; rq[i].detail = details ? &details[i] : nullptr; }
     return vvcbc_cu_eval(ctx->remote, rq.data(), n, ctx->err, sizeof(ctx->err));
   }
-  if (ctx->orig.empty()) FAIL(VVCB_ERR_STATE, "vvcb_rmd_eval: vvcb_frame_begin has not been called");
+  if ((*ctx->origP).empty()) FAIL(VVCB_ERR_STATE, "vvcb_rmd_eval: vvcb_frame_begin has not been called");
   for (int i = 0; i < n; i++) if (!visit_ok(ctx, visits[i])) FAIL(VVCB_ERR_ARG, "vvcb_rmd_eval: visit %d is malformed", i);
   for (int i = 0; i < n; i++)
-    orc_rmd_visit(ctx->orig.data(), ctx->width, ctx->reco.data(), ctx->width, ctx->bd, ctx->ctu, &visits[i], &results[i], details ? &details[i] : nullptr, nullptr);
+    orc_rmd_visit((*ctx->origP).data(), ctx->width, (*ctx->recoP).data(), ctx->width, ctx->bd, ctx->ctu, &visits[i], &results[i], details ? &details[i] : nullptr, nullptr);
   return VVCB_OK;
 }
 
@@ -166,7 +179,7 @@ int vvcb_rmd_pred_all(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int16_t* pred)
   std::vector<int16_t> all((size_t)VVCB_NUM_SLOTS * w * h, (int16_t)0x7fff);
   std::vector<int16_t> keep(pred, pred + all.size());
   vvcb_rmd_detail det;
-  orc_rmd_visit(ctx->orig.data(), ctx->width, ctx->reco.data(), ctx->width, ctx->bd, ctx->ctu, visit, &r, &det, all.data());
+  orc_rmd_visit((*ctx->origP).data(), ctx->width, (*ctx->recoP).data(), ctx->width, ctx->bd, ctx->ctu, visit, &r, &det, all.data());
   for (int s = 0; s < VVCB_NUM_SLOTS; s++)
     if (det.sad[s] != VVCB_SAT_NONE) memcpy(pred + (size_t)s * w * h, &all[(size_t)s * w * h], (size_t)w * h * sizeof(int16_t));
   return VVCB_OK;
@@ -222,7 +235,7 @@ static void tu_chain(vvcb_ctx* ctx, const vvcb_tu_job& j, const int16_t* resi, c
   if (!ts && j.lfnst_idx) orc_inv_lfnst(deq.data(), w, h, j.intra_mode, j.lfnst_idx);
   if (ts) orc_inv_transform_skip(deq.data(), w, h, bd, res.data(), w);
   else    orc_inv_transform(deq.data(), w, h, bd, j.mts_idx, res.data(), w);
-  r.sse = orc_reconstruct_sse(&ctx->orig[(size_t)j.y * ctx->width + j.x], ctx->width, pred, res.data(), w, h, bd, reco.data());
+  r.sse = orc_reconstruct_sse(&(*ctx->origP)[(size_t)j.y * ctx->width + j.x], ctx->width, pred, res.data(), w, h, bd, reco.data());
   if ((j.flags & VVCB_TU_RATE) && r.abs_sum_level)
     r.frac_bits = orc_residual_bits(level.data(), w, h, j.mts_idx, (j.flags & VVCB_TU_TS_ALLOWED) != 0, (j.flags & VVCB_TU_MTS_ALLOWED) != 0, ctx->depQuant, &states[j.rate_idx]);
   if (levelOut) memcpy(levelOut, level.data(), n * sizeof(int32_t));
@@ -235,7 +248,7 @@ static bool job_ok(const vvcb_ctx* ctx, const vvcb_tu_job& j, size_t n_samples, 
   const bool q = (j.flags & VVCB_TU_QUANT) != 0, dq = q && (j.flags & VVCB_TU_DEPQUANT);
   bool ok = j.log2w >= 2 && j.log2w <= 6 && j.log2h >= 2 && j.log2h <= 6 && j.mts_idx <= 5 && (size_t)j.offset + sz <= n_samples && j.qp_rem >= 0 && j.qp_rem < 6 && j.qp_per >= 0 && j.qp_per < 16;
   if (j.mts_idx >= 1) ok = ok && j.log2w <= 5 && j.log2h <= 5;
-  if (q) ok = ok && !ctx->orig.empty() && j.x >= 0 && j.y >= 0 && j.x + (1 << j.log2w) <= ctx->width && j.y + (1 << j.log2h) <= ctx->height;
+  if (q) ok = ok && !(*ctx->origP).empty() && j.x >= 0 && j.y >= 0 && j.x + (1 << j.log2w) <= ctx->width && j.y + (1 << j.log2h) <= ctx->height;
   if (dq) ok = ok && j.mts_idx != 1 && rates && j.rate_idx < n_rates && j.lfnst_idx <= 2 && j.lambda > 0.0;
   if (j.flags & VVCB_TU_RDOQ_TS) ok = ok && q && !dq && j.mts_idx == 1 && rates && j.rate_idx < n_rates && j.lambda > 0.0;
   ok = ok && j.lfnst_idx <= 2 && (j.lfnst_idx == 0 || j.intra_mode < VVCB_NUM_LUMA_MODE);
@@ -266,7 +279,7 @@ static int tu_eval_pred_local(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n
 {
   if (n < 0 || (n > 0 && (!jobs || !results || !src || !visits || n_visits <= 0))) FAIL(VVCB_ERR_ARG, "vvcb_tu_eval_pred: bad argument");
   if (n == 0) return VVCB_OK;
-  if (ctx->orig.empty()) FAIL(VVCB_ERR_STATE, "vvcb_tu_eval_pred: vvcb_frame_begin has not been called");
+  if ((*ctx->origP).empty()) FAIL(VVCB_ERR_STATE, "vvcb_tu_eval_pred: vvcb_frame_begin has not been called");
   for (int i = 0; i < n_visits; i++) if (!visit_ok(ctx, visits[i])) FAIL(VVCB_ERR_ARG, "vvcb_tu_eval_pred: visit %d is malformed", i);
   std::map<uint32_t, std::vector<int16_t>> preds;
   std::map<uint32_t, vvcb_rmd_detail> dets;
@@ -280,7 +293,7 @@ static int tu_eval_pred_local(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n
       std::vector<int16_t>& p = preds[src[i].visit];
       p.resize((size_t)VVCB_NUM_SLOTS * w * h);
       vvcb_rmd_result r;
-      orc_rmd_visit(ctx->orig.data(), ctx->width, ctx->reco.data(), ctx->width, ctx->bd, ctx->ctu, &v, &r, &dets[src[i].visit], p.data());
+      orc_rmd_visit((*ctx->origP).data(), ctx->width, (*ctx->recoP).data(), ctx->width, ctx->bd, ctx->ctu, &v, &r, &dets[src[i].visit], p.data());
     }
     if (dets[src[i].visit].sad[src[i].slot] == VVCB_SAT_NONE) FAIL(VVCB_ERR_ARG, "vvcb_tu_eval_pred: source %d: slot not evaluated for the visit", i);
   }
@@ -289,7 +302,7 @@ static int tu_eval_pred_local(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n
     const int w = 1 << j.log2w, h = 1 << j.log2h;
     const int16_t* p = &preds[src[i].visit][(size_t)src[i].slot * w * h];
     std::vector<int16_t> resi((size_t)w * h);
-    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) resi[y * w + x] = (int16_t)(ctx->orig[(size_t)(j.y + y) * ctx->width + j.x + x] - p[y * w + x]);
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) resi[y * w + x] = (int16_t)((*ctx->origP)[(size_t)(j.y + y) * ctx->width + j.x + x] - p[y * w + x]);
     const size_t o = j.offset;
     tu_chain(ctx, j, resi.data(), p, rates, states, coeff ? coeff + o : nullptr, level ? level + o : nullptr, reco ? reco + o : nullptr, results[i]);
     if (pred_out) memcpy(pred_out + o, p, (size_t)w * h * sizeof(int16_t));
@@ -327,6 +340,7 @@ int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
   if (!ctx) return VVCB_ERR_ARG;
   if (n < 0 || (n > 0 && !reqs)) FAIL(VVCB_ERR_ARG, "vvcb_cu_eval: bad argument");
   if (ctx->remote) return vvcbc_cu_eval(ctx->remote, reqs, n, ctx->err, sizeof(ctx->err));
+  std::lock_guard<std::mutex> lock(g_oracleMutex);
   for (int i = 0; i < n; i++) {                      // reconstruction first: requests of one call belong to different pictures
     vvcb_cu_request& q = reqs[i];
     if (q.n_rects) { int rc = vvcb_reco_update_rects(ctx, q.rects, q.n_rects, q.rect_samples, q.n_rect_samples); if (rc) return rc; }

@@ -631,3 +631,162 @@ def test_reference_encoder_with_gpu_rmd_is_bit_identical(w, h, bits, qp, tmp_pat
     assert rep['tu_preselections'] > 200 and rep['tu_preselection_candidates'] >= 2 * rep['tu_preselections']
     assert rep['tu_reconstructions'] > 500 and rep['tu_residual_bits'] > 500
     print('shim report', rep)
+
+
+# ---- one round trip per CU: vvcb_cu_eval over several pictures of one plane -------------------------------------------------
+@pytest.mark.parametrize('bd,seed', [(8, 131), (10, 132)])
+def test_cu_eval_merges_independent_requests(bd, seed, eng8, eng10):
+    """vvcb_cu_eval with requests that belong to three pictures lying side by side in one plane (what the broker does): rectangles pushed
+    with the request, rough mode decision and TU candidates in one call; every output equals the oracle run on each picture alone, and
+    equals the separate entry points (vvcb_reco_update_rects + vvcb_rmd_eval + vvcb_tu_eval_pred)."""
+    eng = eng8 if bd == 8 else eng10
+    rng = np.random.default_rng(seed)
+    cell = (256, 512)
+    pics = [G.pred_tu_case(np.random.default_rng(seed * 10 + k), bd, 2, slots_per_visit=3) for k in range(3)]
+    eng.frame_alloc(3 * cell[1], cell[0])
+    reqs, expect = [], []
+    for k, (orig, reco, visits, src, jobs, n_samples, rates, items) in enumerate(pics):
+        ox = k * cell[1]
+        eng.orig_update(orig, ox, 0)
+        res, det = O.rmd_batch(orig, reco, bd, 128, visits)
+        states = np.zeros(1, vb.CTX_STATES_DTYPE)
+        for vi, v in enumerate(visits):
+            w, h = 1 << int(v['log2w']), 1 << int(v['log2h'])
+            x, y = int(v['x']), int(v['y'])
+            # the reconstructed neighbourhood of this CU: 4 rows above, 4 columns left (what the shim pushes)
+            rects, samples = [], []
+            for (rx, ry, rw, rh) in ((max(0, x - 4), y - 4, min(cell[1], x + 2 * w + 4) - max(0, x - 4), 4), (x - 4, y, 4, min(cell[0], y + 2 * h + 4) - y)):
+                rects.append((rx + ox, ry, rw, rh, sum(len(s) for s in samples)))
+                samples.append(reco[ry:ry + rh, rx:rx + rw].ravel())
+            mine = [i for i in range(len(jobs)) if int(src[i]['visit']) == vi]
+            jb = jobs[mine].copy()
+            jb['x'] += ox
+            jb['offset'] = np.arange(len(mine)) * w * h
+            jb['rate_idx'] = 0
+            vv = visits[vi:vi + 1].copy()
+            vv['x'] += ox
+            # one snapshot per request: take the first job's
+            rate_of = [int(jobs[i]['rate_idx']) for i in mine]
+            keep = [i for i, r in zip(mine, rate_of) if r == rate_of[0]] if mine else []
+            sel = [mine.index(i) for i in keep]
+            reqs.append(dict(rects=np.array(rects, vb.RECT_DTYPE), rect_samples=np.concatenate(samples), visit=vv, want_rmd=vi % 2 == 0,
+                             jobs=jb[sel] if keep else None, slots=src['slot'][keep] if keep else None, rates=rates[rate_of[0]:rate_of[0] + 1] if keep else None, states=states))
+            if keep:
+                reqs[-1]['jobs']['offset'] = np.arange(len(keep)) * w * h
+            expect.append((res[vi], det[vi], [items[i] for i in keep]))
+    order = rng.permutation(len(reqs))
+    outs = eng.cu_eval([reqs[i] for i in order])
+    n_rmd = n_tu = 0
+    for o, i in zip(outs, order):
+        res, det, its = expect[i]
+        if reqs[i]['want_rmd']:
+            assert o['result'][0].tobytes() == res.tobytes() and o['detail'][0].tobytes() == det.tobytes()
+            n_rmd += 1
+        if its:
+            exp = G.oracle_dq_chain([dict(it, off=k * it['pred'].size) for k, it in enumerate(its)], bd)
+            assert np.array_equal(o['level'], exp['level']) and np.array_equal(o['reco'], exp['reco'])
+            assert np.array_equal(o['pred'], np.concatenate([it['pred'].ravel() for it in its]))
+            assert o['tu_results'].tobytes() == exp['results'].tobytes()
+            n_tu += len(its)
+    assert n_rmd > 10 and n_tu > 30
+    # error behaviour: a job that points outside its request's arrays, a rectangle outside the plane
+    bad = dict(reqs[order[0]])
+    if bad['jobs'] is not None:
+        bad['jobs'] = bad['jobs'].copy()
+        bad['jobs']['offset'][0] = 1 << 20
+        with pytest.raises(vb.EngineError, match='malformed'):
+            eng.cu_eval([bad])
+    bad = dict(reqs[order[0]])
+    bad['rects'] = bad['rects'].copy()
+    bad['rects']['x'][0] = 3 * cell[1] - 2
+    with pytest.raises(vb.EngineError, match='malformed|outside'):
+        eng.cu_eval([bad])
+
+
+def _encoder_args(cfg, w, h, bits, qp):
+    return ['-c', cfg, '-i', 'in.yuv', '-wdt', str(w), '-hgt', str(h), '-q', str(qp), '-f', '1', '-fr', '30',
+            '--InputBitDepth=%d' % bits, '--InternalBitDepth=%d' % bits, '--OutputBitDepth=%d' % bits]
+
+
+def _ref_binaries(*names):
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    paths = [os.path.join(root, 'oracle/_ref', f) for f in names] + [os.path.join(root, 'oracle/_ref/encoder_intra.cfg')]
+    if not all(os.path.exists(p) for p in paths):
+        pytest.skip('oracle/_ref binaries are built only in the container that has /root/reference')
+    return root, paths
+
+
+@pytest.mark.parametrize('w,h,bits,qp', [(128, 64, 8, 32), (128, 128, 10, 27), (128, 128, 10, 37)])
+def test_reference_encoder_served_by_the_engine_is_bit_identical(w, h, bits, qp, tmp_path):
+    """oracle/_ref/EncoderAppServe: the unmodified reference encoder whose luma intra cost evaluation inside estIntraPredLumaQT is SERVED by
+    libvvc_intra_b200.so (oracle/ref_gpu_serve.cpp): no reference prediction, SAD / SATD, transform, quantiser, reconstruction, SSE or
+    residual pricing runs for a whole-CU luma TU.  Same bitstream as the plain encoder, byte for byte."""
+    import json
+    import os
+    import subprocess
+    from make_golden import synth_yuv
+    root, (plain, served, cfg) = _ref_binaries('EncoderApp', 'EncoderAppServe')
+    Y, U, V = synth_yuv(w, h, bits)
+    (tmp_path / 'in.yuv').write_bytes(Y.tobytes() + U.tobytes() + V.tobytes())
+    (tmp_path / 'Time_python.dat').write_bytes(b'')
+    env = dict(os.environ, VVCB_SHIM_REPORT=str(tmp_path / 'report.json'))
+    env.pop('VVCB_BROKER', None)
+    env.pop('LD_LIBRARY_PATH', None)
+    r1 = subprocess.run([plain] + _encoder_args(cfg, w, h, bits, qp) + ['-b', 'plain.bin'], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r1.returncode == 0, r1.stdout[-2000:]
+    r2 = subprocess.run([served] + _encoder_args(cfg, w, h, bits, qp) + ['-b', 'gpu.bin'], cwd=tmp_path, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r2.returncode == 0, r2.stdout[-2000:]
+    a, b = (tmp_path / 'plain.bin').read_bytes(), (tmp_path / 'gpu.bin').read_bytes()
+    assert len(a) > 100 and a == b
+    rep = json.loads((tmp_path / 'report.json').read_text())
+    assert rep['enabled'] == 1 and rep['visits'] > 1000 and rep['demand_round_trips'] == 0 and rep['stale_context'] == 0
+    assert rep['distortions_served'] == 2 * rep['predictions_skipped'] and rep['tu_quantised'] > 10000 and rep['tu_sse'] == rep['tu_quantised']
+    assert rep['tu_residual_bits'] > 5000 and rep['tu_residual_bits_reference'] == 0
+    print('serve report', rep)
+
+
+def test_broker_serves_several_encoders_bit_identically(tmp_path):
+    """Four encoder processes (different pictures, QP 22 / 27 / 32 / 37, 10 bit) share ONE engine context through the broker
+    (vvc_intra_b200/vvcb_broker): bitstreams byte-identical to the plain encoder's, requests of different clients merged into engine batches."""
+    import json
+    import os
+    import subprocess
+    from make_golden import synth_yuv
+    root, (plain, served, cfg) = _ref_binaries('EncoderApp', 'EncoderAppServe')
+    broker = os.path.join(root, 'vvc_intra_b200/vvcb_broker')
+    path = str(tmp_path / 'broker.shm')
+    env0 = dict(os.environ)
+    env0.pop('LD_LIBRARY_PATH', None)
+    env0.pop('VVCB_BROKER', None)
+    server = subprocess.Popen([broker, path, '--bit-depth', '10', '--clients', '8', '--frame', '128x128', '--workers', '3'], env=env0, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        procs = []
+        for i, qp in enumerate((22, 27, 32, 37)):
+            d = tmp_path / ('c%d' % i)
+            d.mkdir()
+            w, h = (128, 128) if i % 2 == 0 else (128, 64)
+            Y, U, V = synth_yuv(w, h, 10, i)
+            (d / 'in.yuv').write_bytes(Y.tobytes() + U.tobytes() + V.tobytes())
+            (d / 'Time_python.dat').write_bytes(b'')
+            procs.append((d, subprocess.Popen([plain] + _encoder_args(cfg, w, h, 10, qp) + ['-b', 'plain.bin'], cwd=d, env=env0, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True),
+                          subprocess.Popen([served] + _encoder_args(cfg, w, h, 10, qp) + ['-b', 'gpu.bin'], cwd=d, env=dict(env0, VVCB_BROKER=path, VVCB_SHIM_REPORT=str(d / 'report.json')),
+                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        for d, p1, p2 in procs:
+            o1, _ = p1.communicate(timeout=900)
+            o2, _ = p2.communicate(timeout=900)
+            assert p1.returncode == 0, o1[-2000:]
+            assert p2.returncode == 0, o2[-2000:]
+            a, b = (d / 'plain.bin').read_bytes(), (d / 'gpu.bin').read_bytes()
+            assert len(a) > 100 and a == b
+        stats = json.loads(subprocess.check_output([broker, path, '--stats'], env=env0))
+        print('broker stats', stats)
+        assert stats['clients_seen'] == 4 and stats['max_batch'] >= 2 and stats['cycles'] < stats['requests'] and stats['kernel_launches'] > 1000
+    finally:
+        subprocess.run([broker, path, '--stop'], env=env0)
+        try:
+            out, _ = server.communicate(timeout=60)
+        except subprocess.TimeoutExpired:
+            server.kill()
+            out = ''
+    assert server.returncode == 0, out[-2000:]

@@ -94,7 +94,7 @@ def test_broker_batches_several_encoders(built, tmp_path):
     byte-identical to its plain encoder's and the server merged requests of different clients into one engine batch."""
     cases = [(64, 64, 8, 32, 0), (64, 64, 8, 27, 1), (128, 64, 8, 37, 2)]
     path = str(tmp_path / 'broker.shm')
-    server = subprocess.Popen([os.path.join(FAKE, 'vvcb_broker'), path, '--bit-depth', '8', '--clients', '4', '--frame', '128x64'],
+    server = subprocess.Popen([os.path.join(FAKE, 'vvcb_broker'), path, '--bit-depth', '8', '--clients', '4', '--frame', '128x64', '--workers', '2'],
                               env=dict(os.environ, LD_LIBRARY_PATH=FAKE), stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     try:
         procs = []

@@ -77,6 +77,8 @@ struct vvcb_ctx {
   PlanState* dPlan;
   int16_t* dPred; size_t capPred;
   int numSms;
+  int16_t* wReco;                   // writable reconstruction plane: own (dReco) or another context's (vvcb_frame_share)
+  int yieldSync; cudaEvent_t evYield;   // VVCB_OPT_YIELD_SYNC
   void* remote;                     // broker client proxy: VVCB_BROKER was set at vvcb_create (vvcb_broker.inc)
   void* hPin[8]; size_t capPin[8];  // page-locked staging of vvcb_cu_eval / vvcb_reco_update_rects
   void* dRect[2]; size_t capRect[2];
@@ -95,6 +97,14 @@ static char g_createErr[512] = "";
       return VVCB_ERR_CUDA;                                                                               \
     }                                                                                                     \
   } while (0)
+
+// wait for the context's stream: polling (default) or, with VVCB_OPT_YIELD_SYNC, sleeping on a blocking event
+static cudaError_t ctx_sync(vvcb_ctx* ctx)
+{
+  if (!ctx->yieldSync) return cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaEventRecord(ctx->evYield, ctx->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->evYield);
+}
 
 #include "vvcb_broker.inc"
 
@@ -156,6 +166,7 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
   }
   if ((e = cudaEventCreateWithFlags(&ctx->evPlan, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->evYield, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
   for (int i = 0; i < 4; i++) if ((e = cudaEventCreate(&ctx->kev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
   for (int i = 0; i < 5; i++) if ((e = cudaEventCreate(&ctx->tev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -211,7 +222,7 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
     for (int i = 0; i < 2; i++) { cudaFree(ctx->dVisP[i]); cudaFree(ctx->dResP[i]); cudaEventDestroy(ctx->evIn[i]); cudaEventDestroy(ctx->evComp[i]); cudaEventDestroy(ctx->evOut[i]); }
     cudaStreamDestroy(ctx->sIn); cudaStreamDestroy(ctx->sOut);
   }
-  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evYield);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->kev[i]);
   for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->tev[i]);
   for (int i = 0; i < kSideStreams; i++) { cudaStreamSynchronize(ctx->sKind[i]); cudaStreamDestroy(ctx->sKind[i]); cudaEventDestroy(ctx->evKind[i]); }
@@ -227,6 +238,7 @@ extern "C" int vvcb_set_option(vvcb_ctx* ctx, int option, int value)
     ctx->depQuant = value;
     return ctx->remote ? vvcbc_set_option(ctx->remote, option, value, ctx->err, sizeof(ctx->err)) : VVCB_OK;
   }
+  if (option == VVCB_OPT_YIELD_SYNC && (value == 0 || value == 1)) { ctx->yieldSync = value; return VVCB_OK; }
   snprintf(ctx->err, sizeof(ctx->err), "vvcb_set_option: unknown option %d or bad value %d", option, value);
   return VVCB_ERR_ARG;
 }
@@ -250,7 +262,7 @@ extern "C" int vvcb_frame_begin(vvcb_ctx* ctx, const int16_t* orig, int stride, 
     ctx->planeSamples = samples;
   }
   ctx->width = width; ctx->height = height; ctx->stride = pitch;
-  ctx->bOrig = ctx->dOrig; ctx->bReco = ctx->dReco;
+  ctx->bOrig = ctx->dOrig; ctx->bReco = ctx->dReco; ctx->wReco = ctx->dReco;
   CK(cudaMemcpy2DAsync(ctx->dOrig, pitch * sizeof(int16_t), orig, stride * sizeof(int16_t), width * sizeof(int16_t), height,
                        cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(ctx->dReco, 0, samples * sizeof(int16_t), ctx->stream));
@@ -277,10 +289,24 @@ extern "C" int vvcb_frame_alloc(vvcb_ctx* ctx, int width, int height)
     ctx->planeSamples = samples;
   }
   ctx->width = width; ctx->height = height; ctx->stride = pitch;
-  ctx->bOrig = ctx->dOrig; ctx->bReco = ctx->dReco;
+  ctx->bOrig = ctx->dOrig; ctx->bReco = ctx->dReco; ctx->wReco = ctx->dReco;
   CK(cudaMemsetAsync(ctx->dOrig, 0, samples * sizeof(int16_t), ctx->stream));
   CK(cudaMemsetAsync(ctx->dReco, 0, samples * sizeof(int16_t), ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_frame_share(vvcb_ctx* dst, vvcb_ctx* src)
+{
+  if (!dst) return VVCB_ERR_ARG;
+  vvcb_ctx* ctx = dst;
+  REMOTE_UNAVAILABLE("vvcb_frame_share");
+  if (!src || src->remote || !src->dOrig || src->bOrig != src->dOrig || src->device != dst->device) {
+    snprintf(ctx->err, sizeof(ctx->err), "vvcb_frame_share: the source context owns no frame on this device");
+    return VVCB_ERR_STATE;
+  }
+  dst->bOrig = src->dOrig; dst->bReco = src->dReco; dst->wReco = src->dReco;
+  dst->width = src->width; dst->height = src->height; dst->stride = src->stride;
   return VVCB_OK;
 }
 
@@ -339,7 +365,7 @@ static int launch_reco_rects(vvcb_ctx* ctx, const vvcb_rect* rects, int n, const
   }
   CK(cudaMemcpyAsync(ctx->dRect[0], rects, (size_t)n * sizeof(vvcb_rect), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->dRect[1], samples, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-  reco_scatter_kernel<<<n < ctx->numSms * 8 ? n : ctx->numSms * 8, 128, 0, ctx->stream>>>(static_cast<const vvcb_rect*>(ctx->dRect[0]), n, static_cast<const int16_t*>(ctx->dRect[1]), ctx->dReco, ctx->stride);
+  reco_scatter_kernel<<<n < ctx->numSms * 8 ? n : ctx->numSms * 8, 128, 0, ctx->stream>>>(static_cast<const vvcb_rect*>(ctx->dRect[0]), n, static_cast<const int16_t*>(ctx->dRect[1]), ctx->wReco, ctx->stride);
   ctx->launches++;
   CK(cudaGetLastError());
   return VVCB_OK;
@@ -360,7 +386,7 @@ extern "C" int vvcb_reco_update_rects(vvcb_ctx* ctx, const vvcb_rect* rects, int
     rq.rects = rects; rq.n_rects = n; rq.rect_samples = samples; rq.n_rect_samples = n_samples;
     return vvcbc_cu_eval(ctx->remote, &rq, 1, ctx->err, sizeof(ctx->err));
   }
-  if (!ctx->dReco || ctx->bReco != ctx->dReco) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_reco_update_rects: no frame owned by the context"); return VVCB_ERR_STATE; }
+  if (!ctx->wReco || ctx->bReco != ctx->wReco) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_reco_update_rects: no writable frame (vvcb_frame_begin / vvcb_frame_alloc / vvcb_frame_share)"); return VVCB_ERR_STATE; }
   for (int i = 0; i < n; i++)
     if (!rect_ok(ctx, rects[i], n_samples)) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_reco_update_rects: rectangle %d is malformed or outside the picture", i); return VVCB_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
@@ -400,7 +426,7 @@ extern "C" int vvcb_frame_bind_device(vvcb_ctx* ctx, const void* d_orig, const v
     snprintf(ctx->err, sizeof(ctx->err), "vvcb_frame_bind_device: bad argument");
     return VVCB_ERR_ARG;
   }
-  ctx->bOrig = static_cast<const int16_t*>(d_orig); ctx->bReco = static_cast<const int16_t*>(d_reco);
+  ctx->bOrig = static_cast<const int16_t*>(d_orig); ctx->bReco = static_cast<const int16_t*>(d_reco); ctx->wReco = nullptr;
   ctx->width = width; ctx->height = height; ctx->stride = stride;
   return VVCB_OK;
 }
@@ -958,7 +984,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
   if (reco) CK(cudaMemcpyAsync(reco, ctx->dTu[5], n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (pred_out) CK(cudaMemcpyAsync(pred_out, ctx->dTu[2], n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(results, ctx->dTu[6], (size_t)n * sizeof(vvcb_tu_result), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(ctx_sync(ctx));
   if (tm) {
     for (int i = 0; i < 4; i++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1])); ctx->tuMs[i] += ms; }
     ctx->tuTimed++;
@@ -999,7 +1025,7 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
     const vvcb_cu_request& q = reqs[i];
     bool ok = q.n_rects >= 0 && q.n_jobs >= 0 && (!q.n_rects || (q.rects && q.rect_samples)) && (!(q.want_rmd || q.n_jobs) || q.visit) &&
               (!q.want_rmd || q.result) && (!q.n_jobs || (q.jobs && q.slots && q.tu_results));
-    if (ok && q.n_rects && (!ctx->dReco || ctx->bReco != ctx->dReco)) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: rectangles need a frame owned by the context"); return VVCB_ERR_STATE; }
+    if (ok && q.n_rects && (!ctx->wReco || ctx->bReco != ctx->wReco)) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: rectangles need a writable frame"); return VVCB_ERR_STATE; }
     for (int k = 0; ok && k < q.n_rects; k++) ok = rect_ok(ctx, q.rects[k], q.n_rect_samples);
     if (ok && q.n_jobs) {
       ok = q.visit->log2w >= 2 && q.visit->log2w <= 6 && q.visit->log2h >= 2 && q.visit->log2h <= 6;
@@ -1085,7 +1111,7 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
     rc = tu_eval_impl(ctx, jobs.data(), (int)nJobs, nullptr, nullptr, nSamples, rates.data(), states.data(), nTuReq, nullptr, hLevel, hReco, tuRes.data(),
                       tv.data(), nTuReq, src.data(), hPred);
     if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
-  } else CK(cudaStreamSynchronize(ctx->stream));
+  } else CK(ctx_sync(ctx));
   // ---- hand the outputs back ----
   {
     int vi = 0; size_t ji = 0, so = 0;

@@ -1,6 +1,6 @@
 // vvcb_broker -- the server process of include/vvc_intra_b200_broker.h: one per GPU, owns the engine context that the walker
 // processes (VVCB_BROKER=<path> in their environment) share.
-//   vvcb_broker <path> [--device D] [--bit-depth B] [--ctu C] [--clients N] [--frame WxH]
+//   vvcb_broker <path> [--device D] [--bit-depth B] [--ctu C] [--clients N] [--frame WxH] [--workers T]
 // Runs until `vvcb_broker <path> --stop` (or vvcb_broker_stop from any process).  `--stats` prints the counters as JSON.
 #include <stdio.h>
 #include <stdlib.h>
@@ -9,9 +9,9 @@
 
 int main(int argc, char** argv)
 {
-  if (argc < 2) { fprintf(stderr, "usage: vvcb_broker <path> [--device D] [--bit-depth B] [--ctu C] [--clients N] [--frame WxH] | --stop | --stats\n"); return 2; }
+  if (argc < 2) { fprintf(stderr, "usage: vvcb_broker <path> [--device D] [--bit-depth B] [--ctu C] [--clients N] [--frame WxH] [--workers T] | --stop | --stats\n"); return 2; }
   const char* path = argv[1];
-  int device = 0, bd = 10, ctu = 128, clients = 64, fw = 1920, fh = 1080;
+  int device = 0, bd = 10, ctu = 128, clients = 64, fw = 1920, fh = 1080, workers = 4;
   for (int i = 2; i < argc; i++) {
     if (!strcmp(argv[i], "--stop")) return vvcb_broker_stop(path) == VVCB_OK ? 0 : 1;
     if (!strcmp(argv[i], "--stats")) {
@@ -28,10 +28,11 @@ int main(int argc, char** argv)
     else if (!strcmp(argv[i], "--bit-depth")) bd = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--ctu")) ctu = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--clients")) clients = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--workers")) workers = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--frame")) { if (sscanf(argv[++i], "%dx%d", &fw, &fh) != 2) { fprintf(stderr, "vvcb_broker: --frame WxH\n"); return 2; } }
     else { fprintf(stderr, "vvcb_broker: unknown option %s\n", argv[i]); return 2; }
   }
-  const int rc = vvcb_broker_serve(path, device, bd, ctu, clients, fw, fh);
+  const int rc = vvcb_broker_serve(path, device, bd, ctu, clients, fw, fh, workers);
   if (rc != VVCB_OK) fprintf(stderr, "vvcb_broker: serve failed (%d): %s\n", rc, vvcb_last_error(nullptr));
   return rc == VVCB_OK ? 0 : 1;
 }

@@ -128,7 +128,8 @@ def load_library():
         L.vvcb_orig_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.vvcb_reco_update_rects.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.vvcb_cu_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-        L.vvcb_broker_serve.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.vvcb_broker_serve.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.vvcb_frame_share.argtypes = [C.c_void_p, C.c_void_p]
         L.vvcb_broker_stop.argtypes = [C.c_char_p]
         L.vvcb_broker_read_stats.argtypes = [C.c_char_p, C.c_void_p]
         L.vvcb_timer_start.argtypes = [C.c_void_p]
