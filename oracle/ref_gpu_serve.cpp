@@ -157,6 +157,12 @@ void report()
               (int)g_enabled, g_st.estCalls, g_st.visits, g_st.cuReuse, g_st.rmdRoundTrips, g_st.tuRoundTrips, g_st.demandRoundTrips, g_st.jobsPrefetched, g_st.jobsDemand,
               g_st.refFetchSkipped, g_st.predSkipped, g_st.predServed, g_st.distServed, g_st.preselServed, g_st.quantServed, g_st.quantDq, g_st.quantTs, g_st.quantLfnst,
               g_st.invServed, g_st.sseServed, g_st.bitsServed, g_st.bitsReal, g_st.staleRate, g_st.engineNs * 1e-9, g_tEst.ns * 1e-9, g_tPre.ns * 1e-9, g_tWrap.ns * 1e-9);
+      if (g_gpu && getenv("VVCB_SHIM_KERNEL_TIMES")) {
+        float t[4] = { 0, 0, 0, 0 }, r[3] = { 0, 0, 0 }; int calls = 0, launches = 0;
+        vvcb_tu_kernel_times(g_gpu, t, &calls);
+        vvcb_kernel_times(g_gpu, r, &launches);
+        fprintf(f, ", \"tu_kernel_ms\": [%.1f, %.1f, %.1f, %.1f], \"tu_calls\": %d, \"rmd_kernel_ms\": [%.1f, %.1f, %.1f], \"rmd_calls\": %d", t[0], t[1], t[2], t[3], calls, r[0], r[1], r[2], launches);
+      }
       if (g_profile) for (int k = 0; k < 8; k++) fprintf(f, ", \"real_%s_s\": [%.3f, %.3f, %.3f]", kFamily[k], g_prof[k][0].ns * 1e-9, g_prof[k][1].ns * 1e-9, g_prof[k][2].ns * 1e-9);
       fprintf(f, "}\n");
       fclose(f);
@@ -187,6 +193,7 @@ void ensureFrame(const CodingStructure& cs)
     g_ctu = sps.getMaxCUWidth();
     if (vvcb_create(&g_gpu, 0, sps.getBitDepth(CHANNEL_TYPE_LUMA), g_ctu) != VVCB_OK) die("vvcb_create:", vvcb_last_error(nullptr));
     gpuCheck(vvcb_set_option(g_gpu, VVCB_OPT_DEP_QUANT, cs.slice->getDepQuantEnabledFlag() ? 1 : 0), "vvcb_set_option:");
+    if (getenv("VVCB_SHIM_KERNEL_TIMES")) vvcb_kernel_timing(g_gpu, 1);          // profiling aid: CUDA events around the kernel stages of every call
     atexit(report);
   }
   if (cs.slice->getPOC() != g_poc) {

@@ -479,8 +479,10 @@ template <int TILE, int KIND, int MODE> static void launch_eval_bucket(const Eva
   rmd_eval_kernel<TILE, KIND, MODE><<<(int)grid, Cfg::kThreads, 0, stream>>>(P);
 }
 
+// hostVisits (optional): the same visits in host memory.  Small batches (the broker's: a handful of CUs per call) touch few of the 33
+// (tile class, prediction kind, packed / plain) kernels; with the visits at hand the empty ones are not launched at all.
 static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_rmd_result* dResults, vvcb_rmd_detail* dDetails,
-                      int16_t* dPred)
+                      int16_t* dPred, const vvcb_rmd_visit* hostVisits = nullptr)
 {
   if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
   if (n == 0) return VVCB_OK;
@@ -495,6 +497,17 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   const bool tm = ctx->timing != 0;
   if (tm) CK(cudaEventRecord(ctx->kev[0], ctx->stream));
   const int pack = dPred ? 0 : 1;     // the prediction-output kernels (parity / integration entry points) take plain items only
+  bool needAll = !hostVisits || n > 4096, need[2][kNumBuckets] = {};
+  if (!needAll)
+    for (int i = 0; i < n; i++) {
+      const vvcb_rmd_visit& v = hostVisits[i];
+      const Shape sh = make_shape(v.log2w, v.log2h);
+      const int packed = pack && small_shape_index(sh.lw, sh.lh) >= 0 ? 1 : 0;
+      const bool mip = !(v.flags & VVCB_VISIT_NO_MIP) && mip_num_modes(sh.w, sh.h) > 0;
+      need[packed][sh.tile * kNumKinds + KIND_ANG] = need[packed][sh.tile * kNumKinds + KIND_PDC] = true;
+      if (mip) need[packed][sh.tile * kNumKinds + KIND_MIP] = true;
+    }
+  int evalLaunches = 0;
   rmd_plan_count<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan, pack);
   rmd_plan_scan<<<1, 32, 0, ctx->stream>>>(ctx->dPlan);
   rmd_plan_fill<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan, ctx->dItems, pack);
@@ -509,26 +522,27 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   // several streams, longest first, the CTAs of the following kernels move in as soon as SM slots free up.  Measured (profiles/r1z_summary.md):
   // no effect on a whole resident sweep (persistent warps drain within one item of each other), 20.3 -> 17.7 ms for the chunked host-buffer
   // path, where every chunk pays the hand-over between its 33 launches.
-  const int nSide = ctx->evalStreams - 1;
+  const int useStreams = needAll ? ctx->evalStreams : (ctx->evalStreams < 3 ? ctx->evalStreams : 3);   // a handful of launches: fewer hand-overs
+  const int nSide = useStreams - 1;
   CK(cudaEventRecord(ctx->evPlan, ctx->stream));
   for (int i = 0; i < nSide; i++) CK(cudaStreamWaitEvent(ctx->sKind[i], ctx->evPlan, 0));
   static const int kindOrder[kNumKinds] = { KIND_ANG, KIND_MIP, KIND_PDC };
   static const int tileOrder[kNumClasses] = { 3, 4, 5, 1, 2, 0 };
   int dealt = 0;
-  auto next_stream = [&]() { const int k = dealt++ % ctx->evalStreams; return k == 0 ? ctx->stream : ctx->sKind[k - 1]; };
+  auto next_stream = [&]() { const int k = dealt++ % useStreams; return k == 0 ? ctx->stream : ctx->sKind[k - 1]; };
   for (int ki = 0; ki < kNumKinds; ki++)
     for (int ti = 0; ti < kNumClasses; ti++) {
       const int b = tileOrder[ti] * kNumKinds + kindOrder[ki];
-      if (dPred) { VVCB_FOR_BUCKET(b, 2, launch_eval_bucket, P, ctx->numSms, maxWarps, next_stream()); continue; }
+      if (dPred) { if (needAll || need[0][b]) { VVCB_FOR_BUCKET(b, 2, launch_eval_bucket, P, ctx->numSms, maxWarps, next_stream()); evalLaunches++; } continue; }
       // the packed small shapes of the tile class, and its larger shapes (the 4x4 class has none)
-      VVCB_FOR_BUCKET(b, 1, launch_eval_bucket, P, ctx->numSms, maxWarps, next_stream());
-      if (b >= kNumKinds) VVCB_FOR_BUCKET(b, 0, launch_eval_bucket, P, ctx->numSms, maxWarps, next_stream());
+      if (needAll || need[1][b]) { VVCB_FOR_BUCKET(b, 1, launch_eval_bucket, P, ctx->numSms, maxWarps, next_stream()); evalLaunches++; }
+      if (b >= kNumKinds && (needAll || need[0][b])) { VVCB_FOR_BUCKET(b, 0, launch_eval_bucket, P, ctx->numSms, maxWarps, next_stream()); evalLaunches++; }
     }
   for (int i = 0; i < nSide; i++) { CK(cudaEventRecord(ctx->evKind[i], ctx->sKind[i])); CK(cudaStreamWaitEvent(ctx->stream, ctx->evKind[i], 0)); }
   if (tm) CK(cudaEventRecord(ctx->kev[2], ctx->stream));
   if (dDetails) { rmd_detail_kernel<<<(n + 31) / 32, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dDetails, P.sadSM, P.satdSM); ctx->launches++; }
   rmd_lists_kernel<<<(n + kListThreads - 1) / kListThreads, kListThreads, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dResults, dDetails, P.sadSM, P.satdSM);
-  ctx->launches += 3 + (dPred ? kNumBuckets : 2 * kNumBuckets - kNumKinds) + 1;
+  ctx->launches += 3 + evalLaunches + 1;
   CK(cudaGetLastError());
   if (tm) {
     CK(cudaEventRecord(ctx->kev[3], ctx->stream));
@@ -1074,7 +1088,7 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
     if ((rc = ensure_visit_buffers(ctx, nRmd))) return rc;
     if (anyDetail && (rc = ensure_details(ctx, nRmd))) return rc;
     CK(cudaMemcpyAsync(ctx->dVisits, hv, (size_t)nRmd * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = launch_rmd(ctx, ctx->dVisits, nRmd, ctx->dResults, anyDetail ? ctx->dDetails : nullptr, nullptr))) return rc;
+    if ((rc = launch_rmd(ctx, ctx->dVisits, nRmd, ctx->dResults, anyDetail ? ctx->dDetails : nullptr, nullptr, hv))) return rc;
     CK(cudaMemcpyAsync(hRes, ctx->dResults, (size_t)nRmd * sizeof(vvcb_rmd_result), cudaMemcpyDeviceToHost, ctx->stream));
     if (anyDetail) CK(cudaMemcpyAsync(hDet, ctx->dDetails, (size_t)nRmd * sizeof(vvcb_rmd_detail), cudaMemcpyDeviceToHost, ctx->stream));
   }
