@@ -206,7 +206,7 @@ def run_b200(args, rank, world, local_rank, dist):
     launches = eng.launch_count - launches0
     ms_total = vb.shard.max_over_ranks(ms_total, dist, 'cuda:%d' % local_rank)
 
-    e2e_s, e2e_steps = float("nan"), 1
+    e2e_s, e2e_steps, e2e_full_s = float("nan"), 1, float("nan")
     if not args.resident_only:
         # ---- end to end through the C ABI with host buffers
         h_vis = {}
@@ -215,21 +215,23 @@ def run_b200(args, rank, world, local_rank, dist):
             a[:] = base
             a['sqrt_lambda'] = vb.partition.sqrt_lambda_for_qp(qp)
             h_vis[qp] = a
-        h_res = eng.host_array(n, vb.RESULT_DTYPE)
+        h_res = eng.host_array(n, vb.BRIEF_DTYPE)
         h_frames = []
         for f in range(NFRAMES):
             a = eng.host_array(H * W, np.int16).reshape(H, W)
             a[:] = frames[f]
             h_frames.append(a)
+        # the sweep's visits come from this process's own planner (vvc_intra_b200.partition): no host-side re-validation of 679 260 structs per step
+        eng.set_option(vb.OPT_TRUSTED_VISITS, 1)
 
         def e2e_step(s):
             f, qp = mine[s % len(mine)]
             eng.frame_begin(h_frames[f])
             eng.reco_update(h_frames[f])
-            eng.rmd_eval(h_vis[qp], out=h_res)
+            eng.rmd_eval_brief(h_vis[qp], out=h_res)       # 64-byte records: the mode lists the walk consumes
             return int(h_res['n_rd'][0])
 
-        e2e_steps = max(1, min(args.steps, 4))
+        e2e_steps = max(1, args.steps)
         for s in range(2):
             e2e_step(s)
         eng.sync()
@@ -241,8 +243,21 @@ def run_b200(args, rank, world, local_rank, dist):
         eng.sync()
         e2e_s = time.perf_counter() - t0
         e2e_s = vb.shard.max_over_ranks(e2e_s, dist, 'cuda:%d' % local_rank)
+        eng.set_option(vb.OPT_TRUSTED_VISITS, 0)
+        # the same through the full 368-byte records (costs as doubles, three lists), for the record
+        h_full = eng.host_array(n, vb.RESULT_DTYPE)
+        eng.rmd_eval(h_vis[QPS[0]], out=h_full)
+        eng.sync()
+        t0 = time.perf_counter()
+        for s in range(2):
+            f, qp = mine[s % len(mine)]
+            eng.frame_begin(h_frames[f])
+            eng.reco_update(h_frames[f])
+            eng.rmd_eval(h_vis[qp], out=h_full)
+        eng.sync()
+        e2e_full_s = (time.perf_counter() - t0) / 2
     h2d = 2 * H * W * 2 + n * vb.VISIT_DTYPE.itemsize
-    d2h = n * vb.RESULT_DTYPE.itemsize
+    d2h = n * vb.BRIEF_DTYPE.itemsize
 
     if rank != 0:
         return
@@ -268,19 +283,23 @@ def run_b200(args, rank, world, local_rank, dist):
         'satd_evals_per_s': world * args.steps * evals_per_step / (ms_total * 1e-3),
         'e2e': {'value': world * e2e_steps * CTUS_PER_FRAME / e2e_s, 'unit': 'CTU/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
-                'note': 'vvcb_frame_begin + vvcb_reco_update + vvcb_rmd_eval with page-locked host buffers, wall clock'},
+                'full_records_ctus_per_s': world * CTUS_PER_FRAME / e2e_full_s, 'full_records_d2h_bytes_per_step': n * vb.RESULT_DTYPE.itemsize,
+                'note': 'vvcb_frame_begin + vvcb_reco_update + vvcb_rmd_eval_brief (64-byte records: the mode lists) with page-locked host buffers, wall clock; '
+                        'full_records_*: the same step through vvcb_rmd_eval (368-byte records with the double costs)'},
         'gpu_launches': launches,
         'clocks': clk.summary(),
-        'roofline': {'bound': 'hbm', 'kernel': 'rmd_eval_kernel', 'achieved': hbm_achieved, 'peak': peaks.get('hbm_gbs'), 'unit': 'GB/s',
-                     'frac': hbm_achieved / peaks.get('hbm_gbs') if peaks.get('hbm_gbs') else None, 'traffic': traffic, 'traffic_source': traffic_src,
-                     'peak_source': peak_src, 'kernel_ms': eval_ms, 'kernel_share_of_step': eval_ms / ms_step if ms_step else None,
-                     'algorithmic_bytes_per_launch': bytes_per_step,
-                     'note': 'the path is integer-issue bound, not HBM bound (SURVEY.md 8d); see int_alu'},
+        # the dominant kernels are integer-issue bound: the roofline is the measured integer issue peak; the HBM view is kept beside it
+        'roofline': {'bound': 'int_alu', 'kernel': 'rmd_eval_kernel', 'achieved': ops_per_step / (eval_ms * 1e-3) / 1e12 if eval_ms > 0 else 0.0,
+                     'peak': int_best / 1e3, 'unit': 'Tera lane-ops/s', 'frac': (ops_per_step / (eval_ms * 1e-3) / 1e9) / int_best if eval_ms > 0 and int_best else None,
+                     'traffic': traffic, 'traffic_source': traffic_src,
+                     'peak_source': 'measured live (vvcb_measure_int_peak): dependent-free IMAD / IADD3+LOP3 / mixed streams = %.0f / %.0f / %.0f Gop/s; MEASURED_PEAKS.json has no integer peak' % int_peak,
+                     'kernel_ms': eval_ms, 'kernel_share_of_step': eval_ms / ms_step if ms_step else None,
+                     'algorithmic_ops_per_launch': ops_per_step,
+                     'ops_model': 'SURVEY.md 8d: 13 + (6|7|8|9 by SATD tile) = 19..22 integer ops per predicted sample',
+                     'hbm': {'achieved_gbs': hbm_achieved, 'peak_gbs': peaks.get('hbm_gbs'), 'frac': hbm_achieved / peaks.get('hbm_gbs') if peaks.get('hbm_gbs') else None,
+                             'algorithmic_bytes_per_launch': bytes_per_step, 'peak_source': peak_src}},
         'int_alu': {'achieved_gops': ops_per_step / (eval_ms * 1e-3) / 1e9 if eval_ms > 0 else 0.0,
-                    'peak_gops': int_best, 'frac': (ops_per_step / (eval_ms * 1e-3) / 1e9) / int_best if eval_ms > 0 and int_best else None,
-                    'peak_source': 'measured live: dependent-free IMAD / IADD3+LOP3 / mixed streams = %.0f / %.0f / %.0f Gop/s' % int_peak,
-                    'algorithmic_ops_per_launch': ops_per_step,
-                    'ops_model': 'SURVEY.md 8d: 13 + (6|7|8|9 by SATD tile) = 19..22 integer ops per predicted sample'},
+                    'peak_gops': int_best, 'frac': (ops_per_step / (eval_ms * 1e-3) / 1e9) / int_best if eval_ms > 0 and int_best else None},
         'kernel_ms': {'plan': k_plan / max(1, k_n), 'eval': eval_ms, 'lists': k_lists / max(1, k_n)},
     }
     if tu_stage:

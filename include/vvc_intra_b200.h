@@ -13,6 +13,7 @@
  *   - sample planes are int16_t (Pel, CL/TypeDef.h:488), row-major, stride in samples (CL/Buffer.h:99).
  *   - all calls are synchronous from the caller's view; one context per host thread / frame in flight.
  *   - there is no CPU fallback: without a CUDA device every call fails with VVCB_ERR_CUDA.
+ *   - bit depths 8..10 (the reference's Pel is int16; 11/12 bit would need transform-skip paths that have no golden coverage).
  */
 #ifndef VVC_INTRA_B200_H
 #define VVC_INTRA_B200_H
@@ -153,7 +154,10 @@ typedef struct vvcb_rect { int16_t x, y, w, h; uint32_t offset; } vvcb_rect;
 int vvcb_reco_update_rects(vvcb_ctx* ctx, const vvcb_rect* rects, int n, const int16_t* samples, size_t n_samples);
 
 /* Resident variant: use planes that already live in device memory (from vvcb_dev_alloc); nothing is
- * copied, the caller keeps ownership.  stride in samples, a multiple of 4.                          */
+ * copied, the caller keeps ownership.  stride in samples, a multiple of 8; both planes 16-byte aligned.
+ * Visits evaluated on bound planes through vvcb_rmd_eval_device are NOT validated: they must satisfy what vvcb_rmd_eval checks
+ * (sizes 4..64, positions multiples of 4 inside the picture, availability counts within the CU's extent and inside the picture,
+ * MPMs < 67); a malformed device-resident visit reads and writes out of bounds.                                                 */
 int vvcb_frame_bind_device(vvcb_ctx* ctx, const void* d_orig, const void* d_reco, int stride, int width, int height);
 
 /* ---- rough mode decision: intra prediction + SAD/SATD + mode cost + candidate lists ---------
@@ -165,6 +169,21 @@ int vvcb_frame_bind_device(vvcb_ctx* ctx, const void* d_orig, const void* d_reco
  * asynchronous DMA); copies in both directions happen inside the call.                          */
 int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results,
                   vvcb_rmd_detail* details /* may be NULL */);
+
+/* The same evaluation with a brief result record (64 bytes instead of 368): what a host walk in an intra slice consumes are the MODES
+ * of the lists -- uiRdModeList is the first n_rd entries of the final list (the MPMs of :777-802 are appended behind them) and the
+ * Hadamard list's costs only matter to PBINTRA in inter slices (EL/IntraSearch.cpp:966).  A mode code is
+ * modeId | mRefId << 8 | mipFlg << 15.  Less than a fifth of the device-to-host traffic of vvcb_rmd_eval.                       */
+typedef struct vvcb_rmd_brief {
+  uint8_t  n_rd, n_had, n_final, pad;
+  uint16_t final_mode[VVCB_MAX_LIST];
+  uint16_t had_mode[VVCB_MAX_HAD_LIST];
+  uint8_t  reserved[12];
+} vvcb_rmd_brief;
+int vvcb_rmd_eval_brief(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_brief* out);
+/* VVCB_OPT_TRUSTED_VISITS (default 0): 1 = the caller guarantees well-formed visits (positions inside the picture, availability
+ * within the picture, sizes 4..64): the host-side validation pass of the batch entry points is skipped.                          */
+#define VVCB_OPT_TRUSTED_VISITS 3
 
 /* Same work with visits/results already resident on the device (device pointers from
  * vvcb_dev_alloc); used to time the kernels without the PCIe copies.                            */
@@ -298,6 +317,10 @@ int vvcb_residual_bits(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int3
 /* TrQuant::transformNxN(trModes) candidate selection (CL/TrQuant.cpp:1112-1123) from the pre-selection sums of one
  * TU's candidates in list order (DCT2 first, transform skip second if tested): pure host logic.                    */
 void vvcb_mts_preselect(const int32_t* sums, int n, int width, int height, int max_cand, uint8_t* selected);
+/* RdCost::calcRdCost (CL/RdCost.cpp:63-74): (32768 / lambda) * distortion + frac_bits in IEEE double, the reference's operation order
+ * (lambda = RdCost::getLambda()).  Pure host logic: cost of a candidate from vvcb_tu_result::sse and the bits the walk has summed
+ * (vvcb_tu_result::frac_bits + its own header bits).                                                                          */
+double vvcb_calc_rd_cost(double lambda, uint64_t frac_bits, uint64_t distortion);
 
 /* ---- texture features (orig-only, trivially parallel) ------------------------------------------------------------
  * vvcb_ctu_hads_islice: EncCu::updateCtuDataISlice (EL/EncCu.cpp:564-675) for every CTU of the frame, as

@@ -80,7 +80,17 @@ extern "C" int emul_rmd_eval(const int16_t* orig, const int16_t* reco, int strid
     if (plan.count[b] && !predOut) VVCB_FOR_BUCKET(b, 0, emul_eval_bucket, P);
   }
   if (details) emu_launch((n + 31) / 32, 256, [&] { rmd_detail_kernel(visits, n, ctu, details, P.sadSM, P.satdSM); });
-  emu_launch((n + kListThreads - 1) / kListThreads, kListThreads, [&] { rmd_lists_kernel(visits, n, ctu, results, details, P.sadSM, P.satdSM); });
+  emu_launch((n + kListThreads - 1) / kListThreads, kListThreads, [&] { rmd_lists_kernel(visits, n, ctu, results, details, P.sadSM, P.satdSM, nullptr); });
+  return 0;
+}
+
+// the list kernel alone, writing brief records (vvcb_rmd_eval_brief), from given SAD / SATD tables
+extern "C" int emul_rmd_brief(const vvcb_rmd_visit* visits, int n, int ctu, const vvcb_rmd_detail* details, vvcb_rmd_brief* brief)
+{
+  std::vector<uint32_t> sm((size_t)2 * VVCB_NUM_SLOTS * n);
+  for (int i = 0; i < n; i++)
+    for (int s = 0; s < VVCB_NUM_SLOTS; s++) { sm[(size_t)s * n + i] = details[i].sad[s]; sm[(size_t)(VVCB_NUM_SLOTS + s) * n + i] = details[i].satd[s]; }
+  emu_launch((n + kListThreads - 1) / kListThreads, kListThreads, [&] { rmd_lists_kernel(visits, n, ctu, nullptr, nullptr, sm.data(), sm.data() + (size_t)VVCB_NUM_SLOTS * n, brief); });
   return 0;
 }
 

@@ -82,3 +82,15 @@ def test_sweep_visits_are_well_formed(built):
     inner = v[(v['x'] == 64) & (v['y'] == 128) & (v['log2w'] == 6)]   # above-right lies in the previous CTU row
     assert inner['avail_al'][0] == 1 and inner['n_above'][0] == 16 and inner['n_left'][0] == 16
     assert inner['n_above_right'][0] == 16 and inner['n_below_left'][0] == 0
+
+
+def test_calc_rd_cost_is_the_reference_formula(built):
+    """vvcb_calc_rd_cost = RdCost::calcRdCost (CL/RdCost.cpp:63-74): (32768 / lambda) * dist + bits in IEEE double, that order (host logic)."""
+    import random
+    r = random.Random(7)
+    for _ in range(2000):
+        lam = r.uniform(0.5, 4000.0)
+        bits, dist = r.randrange(0, 1 << 40), r.randrange(0, 1 << 36)
+        scale = float(1 << 15) / lam
+        assert built.IntraCostEngine.calc_rd_cost(lam, bits, dist) == scale * float(dist) + float(bits)
+    assert built.IntraCostEngine.calc_rd_cost(57.0, 0, 0) == 0.0

@@ -790,3 +790,43 @@ def test_broker_serves_several_encoders_bit_identically(tmp_path):
             server.kill()
             out = ''
     assert server.returncode == 0, out[-2000:]
+
+
+# ---- brief result records (vvcb_rmd_eval_brief) ------------------------------------------------------------------------
+def _brief_matches(brief, full):
+    from test_kernel_emulation import brief_matches
+    return brief_matches(brief, full)
+
+
+def test_brief_records_carry_the_same_lists(eng10):
+    """vvcb_rmd_eval_brief (64-byte records) against vvcb_rmd_eval (368-byte records): counts, final list (whose first n_rd entries are the RD
+    list) and Hadamard list, on random visits (one-shot path) and on a whole 1080p sweep (chunked copy / compute pipeline, trusted visits)."""
+    rng = np.random.default_rng(141)
+    orig, reco, visits = G.random_case(rng, 10, 12)
+    eng10.frame_begin(orig)
+    eng10.reco_update(reco)
+    full = eng10.rmd_eval(visits)
+    brief = eng10.rmd_eval_brief(visits)
+    assert _brief_matches(brief, full)
+    from bench import synth_luma, W, H
+    frame = synth_luma(1)
+    eng10.frame_begin(frame)
+    eng10.reco_update(frame)
+    sweep = vb.build_sweep_visits(W, H, qp=27, ctu=128)
+    assert len(sweep) > 600000
+    eng10.set_option(vb.OPT_TRUSTED_VISITS, 1)
+    try:
+        b = eng10.rmd_eval_brief(sweep)
+    finally:
+        eng10.set_option(vb.OPT_TRUSTED_VISITS, 0)
+    f = eng10.rmd_eval(sweep)
+    assert np.array_equal(b['n_rd'], f['n_rd'].astype(np.uint8)) and np.array_equal(b['n_final'], f['n_final'].astype(np.uint8)) and np.array_equal(b['n_had'], f['n_had'].astype(np.uint8))
+    code = f['final_mode']['mode'].astype(np.uint16) | (f['final_mode']['mrl'].astype(np.uint16) << 8) | (f['final_mode']['mip'].astype(np.uint16) << 15)
+    mask = np.arange(16)[None, :] < f['n_final'][:, None]
+    assert np.array_equal(np.where(mask, b['final_mode'], 0), np.where(mask, code, 0)) and not np.where(mask, 0, b['final_mode']).any()
+    sel = rng.choice(len(sweep), 2000, replace=False)
+    assert _brief_matches(b[sel], f[sel])
+    bad = visits.copy()
+    bad['log2w'][3] = 9
+    with pytest.raises(vb.EngineError, match='malformed'):
+        eng10.rmd_eval_brief(bad)

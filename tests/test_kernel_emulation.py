@@ -39,6 +39,22 @@ def run_emul(lib, orig, reco, bd, visits, pred_of_first=False):
     return res, det, pred
 
 
+def brief_matches(brief, full):
+    """vvcb_rmd_brief against vvcb_rmd_result: counts, final list (its first n_rd entries are the RD list) and Hadamard list as mode codes."""
+    code = lambda m: m['mode'].astype(np.uint16) | (m['mrl'].astype(np.uint16) << 8) | (m['mip'].astype(np.uint16) << 15)
+    for b, r in zip(brief, full):
+        if (int(b['n_rd']), int(b['n_had']), int(b['n_final'])) != (int(r['n_rd']), int(r['n_had']), int(r['n_final'])):
+            return False
+        nf, nh = int(r['n_final']), int(r['n_had'])
+        if not np.array_equal(b['final_mode'][:nf], code(r['final_mode'][:nf])) or b['final_mode'][nf:].any():
+            return False
+        if not np.array_equal(b['final_mode'][:int(r['n_rd'])], code(r['rd_mode'][:int(r['n_rd'])])):
+            return False
+        if not np.array_equal(b['had_mode'][:nh], code(r['had_mode'][:nh])) or b['had_mode'][nh:].any():
+            return False
+    return True
+
+
 def pick(visits, per_shape):
     seen, out = {}, []
     for v in visits:
@@ -72,6 +88,11 @@ def test_emulated_kernels_match_oracle_on_random_visits(emul, bd, seed):
     orig, reco, arr = G.random_case(rng, bd, 4, plane=(256, 512))
     res, det, _ = run_emul(emul, orig, reco, bd, arr)
     ora, odet = O.rmd_batch(orig, reco, bd, 128, arr)
+    # the brief records (vvcb_rmd_eval_brief) carry the same lists as mode codes
+    import vvc_intra_b200 as vb
+    brief = np.zeros(len(arr), vb.BRIEF_DTYPE)
+    assert emul.emul_rmd_brief(arr.ctypes.data_as(C.c_void_p), len(arr), 128, odet.ctypes.data_as(C.c_void_p), brief.ctypes.data_as(C.c_void_p)) == 0
+    assert brief_matches(brief, ora)
     bad = [i for i in range(len(arr)) if res[i].tobytes() != ora[i].tobytes() or det[i].tobytes() != odet[i].tobytes()]
     assert not bad, (len(bad), arr[bad[0]])
 
@@ -90,6 +111,11 @@ def test_emulated_packed_items_ragged_tails_and_ctu_rows(emul):
     arr['y'][on_row] = 128 * rng.integers(1, 3, int(on_row.sum()))
     res, det, _ = run_emul(emul, orig, reco, bd, arr)
     ora, odet = O.rmd_batch(orig, reco, bd, 128, arr)
+    # the brief records (vvcb_rmd_eval_brief) carry the same lists as mode codes
+    import vvc_intra_b200 as vb
+    brief = np.zeros(len(arr), vb.BRIEF_DTYPE)
+    assert emul.emul_rmd_brief(arr.ctypes.data_as(C.c_void_p), len(arr), 128, odet.ctypes.data_as(C.c_void_p), brief.ctypes.data_as(C.c_void_p)) == 0
+    assert brief_matches(brief, ora)
     bad = [i for i in range(len(arr)) if res[i].tobytes() != ora[i].tobytes() or det[i].tobytes() != odet[i].tobytes()]
     assert not bad, (len(bad), arr[bad[0]])
     assert (det['sad'][on_row][:, 67:77] == 0xFFFFFFFF).all()          # no MRL evaluations on a CTU row boundary

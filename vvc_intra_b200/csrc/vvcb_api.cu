@@ -65,6 +65,8 @@ struct vvcb_ctx {
   cudaStream_t sKind[kSideStreams]; cudaEvent_t evPlan, evKind[kSideStreams];   // evaluation launches are dealt over the main stream and these: the CTAs of the next kernels fill the tail of each one
   int evalStreams;                  // streams in use (1 + side streams), VVCB_EVAL_STREAMS for A/B runs
   vvcb_rmd_visit* dVisP[2]; vvcb_rmd_result* dResP[2]; bool pipeReady;
+  vvcb_rmd_brief* dBrief; size_t capBrief;   // brief records of the un-pipelined path (the pipeline re-uses dResP)
+  int trusted;                      // VVCB_OPT_TRUSTED_VISITS
   int16_t* dOrig; int16_t* dReco;
   const int16_t* bOrig; const int16_t* bReco;   // planes in use (own or bound)
   int width, height, stride;        // planes share one pitch (in samples)
@@ -117,10 +119,14 @@ extern "C" int vvcb_device_count(void)
 
 extern "C" const char* vvcb_last_error(const vvcb_ctx* ctx) { return ctx ? ctx->err : g_createErr; }
 
+extern "C" void vvcb_destroy(vvcb_ctx* ctx);
+
 extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_size)
 {
-  if (!out || bit_depth < 8 || bit_depth > 12 || ctu_size < 32 || (ctu_size & (ctu_size - 1))) {
-    snprintf(g_createErr, sizeof(g_createErr), "vvcb_create: bad argument");
+  // bit depths above 10 would need the negative transform-skip shift branch of TrQuant::xTransformSkip (CL/TrQuant.cpp:1394) and have no
+  // golden coverage: refused rather than computed differently
+  if (!out || bit_depth < 8 || bit_depth > 10 || ctu_size < 32 || (ctu_size & (ctu_size - 1))) {
+    snprintf(g_createErr, sizeof(g_createErr), "vvcb_create: bad argument (bit depth 8..10, CTU size a power of two >= 32)");
     return VVCB_ERR_ARG;
   }
   *out = nullptr;
@@ -147,7 +153,7 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
   ctx->device = device; ctx->bd = bit_depth; ctx->ctu = ctu_size; ctx->depQuant = 1;
   auto fail = [&](const char* what, cudaError_t err) {
     snprintf(g_createErr, sizeof(g_createErr), "vvcb_create: %s: %s", what, cudaGetErrorString(err));
-    delete ctx;
+    vvcb_destroy(ctx);                       // releases whatever was created so far (the context is zero-initialised)
     return VVCB_ERR_CUDA;
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
@@ -210,7 +216,7 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 8; i++) if (ctx->hPin[i]) cudaFreeHost(ctx->hPin[i]);
-  cudaFree(ctx->dRect[0]); cudaFree(ctx->dRect[1]);
+  cudaFree(ctx->dRect[0]); cudaFree(ctx->dRect[1]); cudaFree(ctx->dBrief);
   cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dSlotMajor);
   cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred); cudaFree(ctx->dTrRom);
   for (int i = 0; i < 20; i++) cudaFree(ctx->dTu[i]);
@@ -239,6 +245,7 @@ extern "C" int vvcb_set_option(vvcb_ctx* ctx, int option, int value)
     return ctx->remote ? vvcbc_set_option(ctx->remote, option, value, ctx->err, sizeof(ctx->err)) : VVCB_OK;
   }
   if (option == VVCB_OPT_YIELD_SYNC && (value == 0 || value == 1)) { ctx->yieldSync = value; return VVCB_OK; }
+  if (option == VVCB_OPT_TRUSTED_VISITS && (value == 0 || value == 1)) { ctx->trusted = value; return VVCB_OK; }
   snprintf(ctx->err, sizeof(ctx->err), "vvcb_set_option: unknown option %d or bad value %d", option, value);
   return VVCB_ERR_ARG;
 }
@@ -422,8 +429,10 @@ extern "C" int vvcb_frame_bind_device(vvcb_ctx* ctx, const void* d_orig, const v
 {
   if (!ctx) return VVCB_ERR_ARG;
   REMOTE_UNAVAILABLE("vvcb_frame_bind_device");
-  if (!d_orig || !d_reco || width <= 0 || height <= 0 || stride < width || (width & 3) || (height & 3) || (stride & 3)) {
-    snprintf(ctx->err, sizeof(ctx->err), "vvcb_frame_bind_device: bad argument");
+  // the texture kernels read 8-sample rows as one 16-byte word: pitch a multiple of 8 samples, planes 16-byte aligned
+  if (!d_orig || !d_reco || width <= 0 || height <= 0 || stride < width || (width & 3) || (height & 3) || (stride & 7) ||
+      (reinterpret_cast<uintptr_t>(d_orig) & 15) || (reinterpret_cast<uintptr_t>(d_reco) & 15)) {
+    snprintf(ctx->err, sizeof(ctx->err), "vvcb_frame_bind_device: bad argument (stride must be a multiple of 8 samples, planes 16-byte aligned)");
     return VVCB_ERR_ARG;
   }
   ctx->bOrig = static_cast<const int16_t*>(d_orig); ctx->bReco = static_cast<const int16_t*>(d_reco); ctx->wReco = nullptr;
@@ -450,6 +459,7 @@ extern "C" int vvcb_kernel_times(vvcb_ctx* ctx, float ms[3], int* launches)
 
 static int ensure_items(vvcb_ctx* ctx, int n)
 {
+  static_assert(kItemTasks >= 128, "the item bound below assumes at least 128 lane-tasks per plain work item");
   const size_t need = (size_t)n * 60 + 8; // worst case 64x64: three kinds, ceil(slots * 64 lanes / kItemTasks) items each
   if (need > ctx->capItems) {
     cudaFree(ctx->dItems); ctx->dItems = nullptr; ctx->capItems = 0;
@@ -482,7 +492,7 @@ template <int TILE, int KIND, int MODE> static void launch_eval_bucket(const Eva
 // hostVisits (optional): the same visits in host memory.  Small batches (the broker's: a handful of CUs per call) touch few of the 33
 // (tile class, prediction kind, packed / plain) kernels; with the visits at hand the empty ones are not launched at all.
 static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_rmd_result* dResults, vvcb_rmd_detail* dDetails,
-                      int16_t* dPred, const vvcb_rmd_visit* hostVisits = nullptr)
+                      int16_t* dPred, const vvcb_rmd_visit* hostVisits = nullptr, vvcb_rmd_brief* dBrief = nullptr)
 {
   if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
   if (n == 0) return VVCB_OK;
@@ -541,7 +551,7 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   for (int i = 0; i < nSide; i++) { CK(cudaEventRecord(ctx->evKind[i], ctx->sKind[i])); CK(cudaStreamWaitEvent(ctx->stream, ctx->evKind[i], 0)); }
   if (tm) CK(cudaEventRecord(ctx->kev[2], ctx->stream));
   if (dDetails) { rmd_detail_kernel<<<(n + 31) / 32, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dDetails, P.sadSM, P.satdSM); ctx->launches++; }
-  rmd_lists_kernel<<<(n + kListThreads - 1) / kListThreads, kListThreads, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dResults, dDetails, P.sadSM, P.satdSM);
+  rmd_lists_kernel<<<(n + kListThreads - 1) / kListThreads, kListThreads, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dResults, dDetails, P.sadSM, P.satdSM, dBrief);
   ctx->launches += 3 + evalLaunches + 1;
   CK(cudaGetLastError());
   if (tm) {
@@ -587,6 +597,7 @@ template <class F> static int first_bad_index(int n, F ok)
 
 static int check_visits(vvcb_ctx* ctx, const vvcb_rmd_visit* v, int n, int first = 0)
 {
+  if (ctx->trusted) return VVCB_OK;
   const int badIdx = first_bad_index(n, [&](int i) {
     const int w = 1 << v[i].log2w, h = 1 << v[i].log2h;
     const bool ok = v[i].log2w >= 2 && v[i].log2w <= 6 && v[i].log2h >= 2 && v[i].log2h <= 6 && v[i].x >= 0 && v[i].y >= 0 &&
@@ -652,7 +663,8 @@ static int ensure_pipeline(vvcb_ctx* ctx)
   return VVCB_OK;
 }
 
-static int rmd_eval_pipelined(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results)
+// results or brief (exactly one): the record the chunks copy back
+static int rmd_eval_pipelined(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results, vvcb_rmd_brief* brief = nullptr)
 {
   int rc = ensure_pipeline(ctx);
   if (rc) return rc;
@@ -679,10 +691,13 @@ static int rmd_eval_pipelined(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->evIn[b], 0);
     if (e == cudaSuccess && c >= 2) e = cudaStreamWaitEvent(ctx->stream, ctx->evOut[b], 0);   // its results have left the device
     if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: pipeline stage failed: %s", cudaGetErrorString(e)); status = VVCB_ERR_CUDA; break; }
-    if ((status = launch_rmd(ctx, ctx->dVisP[b], m, ctx->dResP[b], nullptr, nullptr))) break;
+    // brief records are written into the chunk's result buffer (a fifth of its size)
+    if ((status = brief ? launch_rmd(ctx, ctx->dVisP[b], m, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<vvcb_rmd_brief*>(ctx->dResP[b]))
+                        : launch_rmd(ctx, ctx->dVisP[b], m, ctx->dResP[b], nullptr, nullptr))) break;
     e = cudaEventRecord(ctx->evComp[b], ctx->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->sOut, ctx->evComp[b], 0);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(results + off, ctx->dResP[b], (size_t)m * sizeof(vvcb_rmd_result), cudaMemcpyDeviceToHost, ctx->sOut);
+    if (e == cudaSuccess) e = brief ? cudaMemcpyAsync(brief + off, ctx->dResP[b], (size_t)m * sizeof(vvcb_rmd_brief), cudaMemcpyDeviceToHost, ctx->sOut)
+                                    : cudaMemcpyAsync(results + off, ctx->dResP[b], (size_t)m * sizeof(vvcb_rmd_result), cudaMemcpyDeviceToHost, ctx->sOut);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->evOut[b], ctx->sOut);
     if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: pipeline stage failed: %s", cudaGetErrorString(e)); status = VVCB_ERR_CUDA; }
   }
@@ -724,6 +739,30 @@ extern "C" int vvcb_rmd_eval(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n,
   if (rc) return rc;
   CK(cudaMemcpyAsync(results, ctx->dResults, (size_t)n * sizeof(vvcb_rmd_result), cudaMemcpyDeviceToHost, ctx->stream));
   if (details) CK(cudaMemcpyAsync(details, ctx->dDetails, (size_t)n * sizeof(vvcb_rmd_detail), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_rmd_eval_brief(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_brief* out)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_rmd_eval_brief");
+  if (n < 0 || (n > 0 && (!visits || !out))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval_brief: bad argument"); return VVCB_ERR_ARG; }
+  if (n == 0) return VVCB_OK;
+  if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval_brief: vvcb_frame_begin has not been called"); return VVCB_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  if (n > pipe_chunk()) return rmd_eval_pipelined(ctx, visits, n, nullptr, out);
+  int rc = check_visits(ctx, visits, n);
+  if (rc) return rc;
+  if ((rc = ensure_visit_buffers(ctx, n))) return rc;
+  if ((size_t)n > ctx->capBrief) {
+    cudaFree(ctx->dBrief); ctx->dBrief = nullptr; ctx->capBrief = 0;
+    CK(cudaMalloc(&ctx->dBrief, (size_t)n * sizeof(vvcb_rmd_brief)));
+    ctx->capBrief = (size_t)n;
+  }
+  CK(cudaMemcpyAsync(ctx->dVisits, visits, (size_t)n * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = launch_rmd(ctx, ctx->dVisits, n, nullptr, nullptr, nullptr, nullptr, ctx->dBrief))) return rc;
+  CK(cudaMemcpyAsync(out, ctx->dBrief, (size_t)n * sizeof(vvcb_rmd_brief), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return VVCB_OK;
 }
@@ -1197,6 +1236,15 @@ extern "C" int vvcb_tu_kernel_times(vvcb_ctx* ctx, float ms[4], int* calls)
   if (calls) *calls = ctx->tuTimed;
   ctx->tuTimed = 0;
   return VVCB_OK;
+}
+
+// RdCost::calcRdCost (CL/RdCost.cpp:63-74) with m_DistScale = 32768 / lambda (RdCost::setLambda, :76-79): IEEE double, one multiply and
+// one add in the reference's order.  Host logic: the walk adds its own header bits to vvcb_tu_result::frac_bits before calling it.
+extern "C" double vvcb_calc_rd_cost(double lambda, uint64_t frac_bits, uint64_t distortion)
+{
+  const volatile double distScale = double(1 << 15) / lambda;
+  const volatile double scaled = distScale * double(distortion);
+  return scaled + double(frac_bits);
 }
 
 // host logic: CL/TrQuant.cpp:1112-1123

@@ -1041,7 +1041,7 @@ __device__ void store_list_detail(const SmList& L, int32_t* n, vvcb_mode* m, dou
 #define VVCB_LIST_MIN_CTAS 4
 #endif
 __global__ void __launch_bounds__(kListThreads, VVCB_LIST_MIN_CTAS) rmd_lists_kernel(const vvcb_rmd_visit* visits, int n, int ctu, vvcb_rmd_result* results,
-                                                                 vvcb_rmd_detail* details, const uint32_t* sadSM, const uint32_t* satdSM)
+                                                                 vvcb_rmd_detail* details, const uint32_t* sadSM, const uint32_t* satdSM, vvcb_rmd_brief* brief)
 {
   __shared__ double   sRdC[kRdCap * kListThreads], sHadC[kHadCap * kListThreads];
   __shared__ uint32_t sRdM[kRdCap * kListThreads], sHadM[kHadCap * kListThreads];
@@ -1193,6 +1193,24 @@ __global__ void __launch_bounds__(kListThreads, VVCB_LIST_MIN_CTAS) rmd_lists_ke
   const int lane = tid & 31, wbase = tid & ~31;
   constexpr int kWords = (int)(sizeof(vvcb_rmd_result) / 4);
   static_assert(sizeof(vvcb_rmd_result) == 368, "result layout");
+  if (brief) {
+    // brief records: 16 words per visit, the warp's 32 records are 512 consecutive words
+    static_assert(sizeof(vvcb_rmd_brief) == 64, "brief layout");
+    const int vis0 = blockIdx.x * blockDim.x + wbase;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(brief + vis0);
+    auto code = [](uint32_t m) -> uint32_t { return ((m >> 16) & 0xff) | (((m >> 8) & 0xff) << 8) | ((m & 1) << 15); };   // pack_mode -> modeId | mRefId << 8 | mipFlg << 15
+    for (int k = lane; k < 32 * 16; k += 32) {
+      const int r = k >> 4, wd = k & 15, t = wbase + r;
+      if (vis0 + r >= n) break;
+      const int nRd = sCount[t], nHad = sCount[kListThreads + t], nFinal = sCount[2 * kListThreads + t];
+      uint32_t val = 0;
+      if (wd == 0) val = (uint32_t)nRd | (uint32_t)nHad << 8 | (uint32_t)nFinal << 16;
+      else if (wd < 9) { const int i = 2 * (wd - 1); if (i < nFinal) val = code(sRdM[i * kListThreads + t]); if (i + 1 < nFinal) val |= code(sRdM[(i + 1) * kListThreads + t]) << 16; }
+      else if (wd < 13) { const int i = 2 * (wd - 9); if (i < nHad) val = code(sHadM[i * kListThreads + t]); if (i + 1 < nHad) val |= code(sHadM[(i + 1) * kListThreads + t]) << 16; }
+      dst[k] = val;
+    }
+  }
+  if (results)
   for (int r = 0; r < 32; r++) {
     const int t = wbase + r;
     const int vis = blockIdx.x * blockDim.x + t;

@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(kTuThreads) tu_eval_kernel(TuParams P)
         A[i] = clip16(d);
       }
       absLevel = (int)team_sum<NT>(lpart, red);
+      team_sync<NT>();                                     // A[] written per lane above, read across lanes below (the warp-team sum only shuffles)
       const int16_t* pred = P.pred + job.offset;
       const int16_t* org = P.orig + (size_t)job.y * P.stride + job.x;
       const int maxv = (1 << P.bd) - 1;

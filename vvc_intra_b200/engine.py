@@ -56,6 +56,9 @@ FEAT_RESULT_DTYPE = np.dtype([('f', '<i4', 27), ('valid', '<i4')])
 assert FEAT_JOB_DTYPE.itemsize == 56 and FEAT_RESULT_DTYPE.itemsize == 112
 
 
+BRIEF_DTYPE = np.dtype([('n_rd', 'u1'), ('n_had', 'u1'), ('n_final', 'u1'), ('pad', 'u1'), ('final_mode', '<u2', MAX_LIST), ('had_mode', '<u2', MAX_HAD_LIST), ('reserved', 'u1', 12)])
+assert BRIEF_DTYPE.itemsize == 64
+OPT_YIELD_SYNC, OPT_TRUSTED_VISITS = 2, 3
 RECT_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('w', '<i2'), ('h', '<i2'), ('offset', '<u4')])
 assert RECT_DTYPE.itemsize == 12
 
@@ -100,6 +103,7 @@ def load_library():
         L.vvcb_frame_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.vvcb_reco_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.vvcb_rmd_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.vvcb_rmd_eval_brief.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.vvcb_rmd_eval_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.vvcb_rmd_pred.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.vvcb_rmd_pred_all.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -117,6 +121,8 @@ def load_library():
         L.vvcb_residual_bits.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
         L.vvcb_mts_preselect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vvcb_mts_preselect.restype = None
+        L.vvcb_calc_rd_cost.argtypes = [C.c_double, C.c_uint64, C.c_uint64]
+        L.vvcb_calc_rd_cost.restype = C.c_double
         L.vvcb_ctu_hads_islice.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.vvcb_features_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.vvcb_frame_bind_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -262,11 +268,25 @@ class IntraCostEngine:
         visits = np.ascontiguousarray(visits, VISIT_DTYPE)
         if out is None:
             out = np.empty(len(visits), RESULT_DTYPE)
+        elif out.dtype != RESULT_DTYPE or len(out) < len(visits) or not out.flags['C_CONTIGUOUS']:
+            raise ValueError('out must be a contiguous RESULT_DTYPE array of at least len(visits) records')
         if detail and detail_out is None:
             detail_out = np.empty(len(visits), DETAIL_DTYPE)
+        if detail_out is not None and (detail_out.dtype != DETAIL_DTYPE or len(detail_out) < len(visits) or not detail_out.flags['C_CONTIGUOUS']):
+            raise ValueError('detail_out must be a contiguous DETAIL_DTYPE array of at least len(visits) records')
         self._ck(self._lib.vvcb_rmd_eval(self._ctx, _ptr(visits), len(visits), _ptr(out),
                                          _ptr(detail_out) if detail_out is not None else None))
         return (out, detail_out) if detail_out is not None else out
+
+    def rmd_eval_brief(self, visits, out=None):
+        """vvcb_rmd_eval_brief: 64-byte records (mode codes of the final and Hadamard lists)."""
+        visits = np.ascontiguousarray(visits, VISIT_DTYPE)
+        if out is None:
+            out = np.empty(len(visits), BRIEF_DTYPE)
+        elif out.dtype != BRIEF_DTYPE or len(out) < len(visits) or not out.flags['C_CONTIGUOUS']:
+            raise ValueError('out must be a contiguous BRIEF_DTYPE array of at least len(visits) records')
+        self._ck(self._lib.vvcb_rmd_eval_brief(self._ctx, _ptr(visits), len(visits), _ptr(out)))
+        return out
 
     def rmd_pred(self, visit, slot):
         visit = np.ascontiguousarray(visit, VISIT_DTYPE).reshape(1)
@@ -340,6 +360,11 @@ class IntraCostEngine:
         self._ck(self._lib.vvcb_residual_bits(self._ctx, _ptr(jobs), len(jobs), _ptr(levels), levels.size, _ptr(states), len(states), _ptr(bits)))
         return bits
 
+    @staticmethod
+    def calc_rd_cost(lam, frac_bits, distortion):
+        """vvcb_calc_rd_cost: RdCost::calcRdCost (pure host logic, no context needed)."""
+        return float(load_library().vvcb_calc_rd_cost(float(lam), int(frac_bits), int(distortion)))
+
     def mts_preselect(self, sums, width, height, max_cand):
         sums = np.ascontiguousarray(sums, np.int32)
         sel = np.zeros(len(sums), np.uint8)
@@ -380,7 +405,8 @@ class IntraCostEngine:
         self._ck(self._lib.vvcb_rmd_eval_device(self._ctx, d_visits, n, d_results, d_details))
 
     def host_array(self, n, dtype):
-        """numpy array of n items backed by page-locked host memory (vvcb_host_alloc)."""
+        """numpy array of n items backed by page-locked host memory (vvcb_host_alloc).  The memory belongs to the engine: the array (and
+        every view of it) must not be used after close()."""
         dtype = np.dtype(dtype)
         p = C.c_void_p()
         nbytes = max(1, n * dtype.itemsize)
