@@ -227,7 +227,7 @@ def run_b200(args, rank, world, local_rank, dist):
         def e2e_step(s):
             f, qp = mine[s % len(mine)]
             eng.frame_begin(h_frames[f])
-            eng.reco_update(h_frames[f])
+            eng.reco_from_orig()                           # the sweep's neighbours are the original picture: copied on the device
             eng.rmd_eval_brief(h_vis[qp], out=h_res)       # 64-byte records: the mode lists the walk consumes
             return int(h_res['n_rd'][0])
 
@@ -256,7 +256,7 @@ def run_b200(args, rank, world, local_rank, dist):
             eng.rmd_eval(h_vis[qp], out=h_full)
         eng.sync()
         e2e_full_s = (time.perf_counter() - t0) / 2
-    h2d = 2 * H * W * 2 + n * vb.VISIT_DTYPE.itemsize
+    h2d = H * W * 2 + n * vb.VISIT_DTYPE.itemsize
     d2h = n * vb.BRIEF_DTYPE.itemsize
 
     if rank != 0:
@@ -284,7 +284,7 @@ def run_b200(args, rank, world, local_rank, dist):
         'e2e': {'value': world * e2e_steps * CTUS_PER_FRAME / e2e_s, 'unit': 'CTU/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
                 'full_records_ctus_per_s': world * CTUS_PER_FRAME / e2e_full_s, 'full_records_d2h_bytes_per_step': n * vb.RESULT_DTYPE.itemsize,
-                'note': 'vvcb_frame_begin + vvcb_reco_update + vvcb_rmd_eval_brief (64-byte records: the mode lists) with page-locked host buffers, wall clock; '
+                'note': 'vvcb_frame_begin + vvcb_reco_from_orig + vvcb_rmd_eval_brief (64-byte records: the mode lists) with page-locked host buffers, wall clock; '
                         'full_records_*: the same step through vvcb_rmd_eval (368-byte records with the double costs)'},
         'gpu_launches': launches,
         'clocks': clk.summary(),

@@ -137,6 +137,10 @@ int  vvcb_set_option(vvcb_ctx* ctx, int option, int value);
 int vvcb_frame_begin(vvcb_ctx* ctx, const int16_t* orig, int stride, int width, int height);
 int vvcb_reco_update(vvcb_ctx* ctx, const int16_t* reco, int stride, int x, int y, int w, int h);
 
+/* reconstruction := original, on the device (no host traffic): the neighbours of the exhaustive candidate sweep (bench.py, configs[4])
+ * are taken from the original picture.                                                                              */
+int vvcb_reco_from_orig(vvcb_ctx* ctx);
+
 /* Several pictures in one context: vvcb_frame_alloc makes cleared planes of the given size without uploading anything,
  * vvcb_orig_update writes a rectangle of the original plane (what vvcb_reco_update does for the reconstruction).  The broker
  * (vvc_intra_b200_broker.h) keeps the pictures of all its clients side by side in one such plane; a visit's x / y then

@@ -811,7 +811,7 @@ def test_brief_records_carry_the_same_lists(eng10):
     from bench import synth_luma, W, H
     frame = synth_luma(1)
     eng10.frame_begin(frame)
-    eng10.reco_update(frame)
+    eng10.reco_from_orig()                                  # == reco_update(frame), without the upload
     sweep = vb.build_sweep_visits(W, H, qp=27, ctu=128)
     assert len(sweep) > 600000
     eng10.set_option(vb.OPT_TRUSTED_VISITS, 1)
@@ -819,6 +819,7 @@ def test_brief_records_carry_the_same_lists(eng10):
         b = eng10.rmd_eval_brief(sweep)
     finally:
         eng10.set_option(vb.OPT_TRUSTED_VISITS, 0)
+    eng10.reco_update(frame)
     f = eng10.rmd_eval(sweep)
     assert np.array_equal(b['n_rd'], f['n_rd'].astype(np.uint8)) and np.array_equal(b['n_final'], f['n_final'].astype(np.uint8)) and np.array_equal(b['n_had'], f['n_had'].astype(np.uint8))
     code = f['final_mode']['mode'].astype(np.uint16) | (f['final_mode']['mrl'].astype(np.uint16) << 8) | (f['final_mode']['mip'].astype(np.uint16) << 15)
@@ -830,3 +831,71 @@ def test_brief_records_carry_the_same_lists(eng10):
     bad['log2w'][3] = 9
     with pytest.raises(vb.EngineError, match='malformed'):
         eng10.rmd_eval_brief(bad)
+
+
+# ---- BASELINE.json configurations through the drop-in ------------------------------------------------------------------
+def _run_served_vs_plain(tmp_path, cases, bits, frame_wh, workers=4):
+    """cases: list of (name, Y, U, V, w, h, qp).  Plain and served encoders of all cases run concurrently (served ones share one broker);
+    returns the broker statistics after checking bitstream AND reconstruction identity of every case."""
+    import json
+    import os
+    import subprocess
+    root, (plain, served, cfg) = _ref_binaries('EncoderApp', 'EncoderAppServe')
+    broker = os.path.join(root, 'vvc_intra_b200/vvcb_broker')
+    path = str(tmp_path / 'broker.shm')
+    env0 = dict(os.environ)
+    env0.pop('LD_LIBRARY_PATH', None)
+    env0.pop('VVCB_BROKER', None)
+    server = subprocess.Popen([broker, path, '--bit-depth', str(bits), '--clients', str(max(2, len(cases))), '--frame', '%dx%d' % frame_wh, '--workers', str(workers)],
+                              env=env0, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        procs = []
+        for name, Y, U, V, w, h, qp in cases:
+            d = tmp_path / name
+            d.mkdir()
+            (d / 'in.yuv').write_bytes(Y.tobytes() + U.tobytes() + V.tobytes())
+            (d / 'Time_python.dat').write_bytes(b'')
+            args = _encoder_args(cfg, w, h, bits, qp)
+            procs.append((d, subprocess.Popen([plain] + args + ['-b', 'plain.bin', '-o', 'plain.yuv'], cwd=d, env=env0, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True),
+                          subprocess.Popen([served] + args + ['-b', 'gpu.bin', '-o', 'gpu.yuv'], cwd=d, env=dict(env0, VVCB_BROKER=path, VVCB_SHIM_REPORT=str(d / 'report.json')),
+                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        for d, p1, p2 in procs:
+            o1, _ = p1.communicate(timeout=1500)
+            o2, _ = p2.communicate(timeout=1500)
+            assert p1.returncode == 0, o1[-2000:]
+            assert p2.returncode == 0, o2[-2000:]
+            a, b = (d / 'plain.bin').read_bytes(), (d / 'gpu.bin').read_bytes()
+            assert len(a) > 100 and a == b, d.name
+            assert (d / 'plain.yuv').read_bytes() == (d / 'gpu.yuv').read_bytes(), d.name          # reconstruction (after the loop filters) as well
+            rep = json.loads((d / 'report.json').read_text())
+            assert rep['enabled'] == 1 and rep['demand_round_trips'] == 0 and rep['stale_context'] == 0 and rep['tu_residual_bits_reference'] == 0, rep
+        stats = json.loads(subprocess.check_output([broker, path, '--stats'], env=env0))
+    finally:
+        subprocess.run([broker, path, '--stop'], env=env0)
+        try:
+            server.communicate(timeout=60)
+        except subprocess.TimeoutExpired:
+            server.kill()
+    return stats
+
+
+def test_config1_416x240_full_frame_served_is_bit_identical(tmp_path):
+    """BASELINE.json configs[0]: encoder_intra.cfg, synthetic 416x240 8-bit 4:2:0, 1 frame, QP 32 (SURVEY.md App. G input) -- the whole frame
+    through the served drop-in: bitstream and reconstruction equal the plain reference encoder's."""
+    from make_golden import synth_yuv
+    Y, U, V = synth_yuv(416, 240, 8)
+    stats = _run_served_vs_plain(tmp_path, [('c1', Y, U, V, 416, 240, 32)], 8, (416, 240), workers=2)
+    print('C1 broker stats', stats)
+    assert stats['visits'] > 50000 and stats['tu_jobs'] > 1000000
+
+
+def test_config2_1080p10_ctu_row_at_four_qps_served_is_bit_identical(tmp_path):
+    """BASELINE.json configs[1] (bounded): the first CTU row of a 1920x1080 10-bit synthetic frame (1920x128, 15 CTUs) at QP 22, 27, 32 and 37,
+    four encoder processes behind one broker: bitstreams and reconstructions equal the plain reference encoder's."""
+    from make_golden import synth_yuv
+    Y, U, V = synth_yuv(1920, 1080, 10)
+    row = (Y[:128], U[:64], V[:64])
+    cases = [('qp%d' % qp, row[0], row[1], row[2], 1920, 128, qp) for qp in (22, 27, 32, 37)]
+    stats = _run_served_vs_plain(tmp_path, cases, 10, (1920, 128), workers=4)
+    print('1080p10 CTU row broker stats', stats)
+    assert stats['clients_seen'] == 4 and stats['visits'] > 400000 and stats['max_batch'] >= 2

@@ -303,6 +303,17 @@ extern "C" int vvcb_frame_alloc(vvcb_ctx* ctx, int width, int height)
   return VVCB_OK;
 }
 
+extern "C" int vvcb_reco_from_orig(vvcb_ctx* ctx)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_reco_from_orig");
+  if (!ctx->dReco || ctx->bReco != ctx->dReco || ctx->bOrig != ctx->dOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_reco_from_orig: no frame owned by the context"); return VVCB_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  // stream ordered: every later launch of this context (the pipelined path's kernels included) runs behind it
+  CK(cudaMemcpyAsync(ctx->dReco, ctx->dOrig, (size_t)ctx->stride * ctx->height * sizeof(int16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  return VVCB_OK;
+}
+
 extern "C" int vvcb_frame_share(vvcb_ctx* dst, vvcb_ctx* src)
 {
   if (!dst) return VVCB_ERR_ARG;

@@ -131,6 +131,7 @@ def load_library():
         L.vvcb_tu_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.vvcb_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.vvcb_frame_alloc.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.vvcb_reco_from_orig.argtypes = [C.c_void_p]
         L.vvcb_orig_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.vvcb_reco_update_rects.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.vvcb_cu_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -190,6 +191,10 @@ class IntraCostEngine:
     def reco_update(self, reco, x=0, y=0):
         reco = np.ascontiguousarray(reco, np.int16)
         self._ck(self._lib.vvcb_reco_update(self._ctx, _ptr(reco), reco.shape[1], x, y, reco.shape[1], reco.shape[0]))
+
+    def reco_from_orig(self):
+        """vvcb_reco_from_orig: reconstruction := original on the device (the exhaustive sweep's neighbours)."""
+        self._ck(self._lib.vvcb_reco_from_orig(self._ctx))
 
     def frame_alloc(self, width, height):
         """vvcb_frame_alloc: cleared planes for several pictures side by side (what the broker keeps)."""
