@@ -259,6 +259,7 @@ def run_b200(args, rank, world, local_rank, dist):
     h2d = H * W * 2 + n * vb.VISIT_DTYPE.itemsize
     d2h = n * vb.BRIEF_DTYPE.itemsize
 
+    strong = None if (args.no_strong or args.resident_only) else strong_scaling_leg(eng, vb, rank, world, dist, local_rank)
     if rank != 0:
         return
     tu_stage = None if (args.no_tu_stage or args.resident_only) else tu_stage_leg(eng, vb, base, frames[0], int_peak)
@@ -302,6 +303,8 @@ def run_b200(args, rank, world, local_rank, dist):
                     'peak_gops': int_best, 'frac': (ops_per_step / (eval_ms * 1e-3) / 1e9) / int_best if eval_ms > 0 and int_best else None},
         'kernel_ms': {'plan': k_plan / max(1, k_n), 'eval': eval_ms, 'lists': k_lists / max(1, k_n)},
     }
+    if strong:
+        out['strong_scaling'] = strong
     if tu_stage:
         out['tu_stage'] = tu_stage
     if feat_stage:
@@ -311,6 +314,49 @@ def run_b200(args, rank, world, local_rank, dist):
     if world == 1 and not args.no_bitexact and not args.resident_only:
         out['bitexact'] = bitexact_leg(frames, local_rank)
     emit(out)
+
+
+def strong_scaling_leg(eng, vb, rank, world, dist, local_rank):
+    """BASELINE.json configs[2]: 64 frames of 3840x2160 10-bit, a FIXED job sharded by frame over the ranks (frame f -> rank f mod N), through the
+    host-buffer entry points (planes and visits up, brief records down), ending with the gather of the per-frame statistics on every rank.
+    Wall clock around the whole job, max over ranks; the driver's SCALE run gives it at N = 1, 2, 4, 8."""
+    from make_golden import synth_yuv
+    w4, h4, n_frames, qp = 3840, 2160, 64, 32
+    vis = vb.build_sweep_visits(w4, h4, qp=qp, ctu=CTU)
+    n = len(vis)
+    hv = eng.host_array(n, vb.VISIT_DTYPE)
+    hv[:] = vis
+    hr = eng.host_array(n, vb.BRIEF_DTYPE)
+    # four distinct synthetic 2160p frames (generating 64 takes longer than encoding them); frame f of the job is picture f % 4
+    pics = []
+    for f in range(4):
+        a = eng.host_array(h4 * w4, np.int16).reshape(h4, w4)
+        a[:] = synth_yuv(w4, h4, BITS, f)[0]
+        pics.append(a)
+    mine = [f for f in range(n_frames) if f % world == rank]
+    eng.set_option(vb.OPT_TRUSTED_VISITS, 1)
+    eng.frame_begin(pics[0]); eng.reco_from_orig(); eng.rmd_eval_brief(hv, out=hr)      # warm-up: allocations, pipeline buffers
+    eng.sync()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    stats = []
+    for f in mine:
+        eng.frame_begin(pics[f % 4])
+        eng.reco_from_orig()
+        eng.rmd_eval_brief(hv, out=hr)
+        stats.append((f, int(hr['n_final'].sum()), int(hr['final_mode'][:, 0].astype(np.int64).sum())))     # per-frame statistics of the chosen lists
+    eng.sync()
+    merged = vb.shard.gather_stats(stats, dist)
+    dt = vb.shard.max_over_ranks(time.perf_counter() - t0, dist, 'cuda:%d' % local_rank)
+    eng.set_option(vb.OPT_TRUSTED_VISITS, 0)
+    if sorted(m[0] for m in merged) != list(range(n_frames)):
+        raise SystemExit('bench: the strong-scaling gather lost frames')
+    ctus = ((w4 + CTU - 1) // CTU) * ((h4 + CTU - 1) // CTU)
+    return {'workload': 'configs[2]: 64 frames 3840x2160 10-bit, exhaustive RMD sweep (%d visits per frame), sharded by frame over %d rank(s), host buffers, final statistics gather' % (n, world),
+            'scaling': 'strong', 'n_gpus': world, 'seconds': dt, 'frames_per_s': n_frames / dt, 'ctus_per_s': n_frames * ctus / dt,
+            'h2d_bytes_per_frame': int(h4 * w4 * 2 + n * vb.VISIT_DTYPE.itemsize), 'd2h_bytes_per_frame': int(n * vb.BRIEF_DTYPE.itemsize),
+            'stats_checksum': int(sum(m[1] + m[2] for m in merged) & 0xffffffff)}
 
 
 def features_stage_leg(eng, vb, frame):
@@ -550,6 +596,24 @@ def run_reference(args, rank, world):
         one_step(args.warmup + s)
     dt = time.perf_counter() - t0
     value = args.steps * cores / dt
+    # BASELINE.json's second metric, like for like: the rough-mode-decision evaluations (one prediction + SAD + SATD each) the plain encoder
+    # makes per CTU, counted by the pass-through twin (oracle/_ref/EncoderAppServe with VVCB_SHIM_OFF=1: every call runs the reference's own
+    # code, the link-time wrappers only count) on one crop per QP, outside the timed region
+    evals_per_ctu = None
+    twin = os.path.join(ROOT, 'oracle/_ref/EncoderAppServe')
+    if os.path.exists(twin):
+        procs = []
+        for k, qp in enumerate(QPS):
+            d = os.path.join(tmp, 'count%d' % k)
+            write_crop(d, frames, k)
+            procs.append((d, subprocess.Popen(encoder_cmd(twin, cfg, qp, 'out.bin'), cwd=d, env=dict(os.environ, VVCB_SHIM_OFF='1', VVCB_SHIM_REPORT=os.path.join(d, 'report.json')),
+                                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)))
+        counts = []
+        for d, pr in procs:
+            if pr.wait() == 0 and os.path.exists(os.path.join(d, 'report.json')):
+                counts.append(json.load(open(os.path.join(d, 'report.json')))['reference_satd_evals'])
+        if counts:
+            evals_per_ctu = sum(counts) / len(counts)
     sample = ('unmodified reference encoder (VTM 6.1 fork, encoder_intra.cfg, all tools on, AVX2 dispatch), one process per 128x128 '
               '10-bit crop (1 CTU) of the same synthetic frames, %d processes at a time, QP cycling 32/27/37/22; '
               'full encode of the CTU (split search + full RD), not only the RMD sweep' % cores)
@@ -562,6 +626,10 @@ def run_reference(args, rank, world):
         'config': {'workload': 'configs[1]: all-intra 1920x1080 10-bit synthetic YUV, 8 frames, QP 22/27/32/37 (bounded sample: %d CTU crops per step)' % cores},
         'cpu_baseline': {'value': value, 'unit': 'CTU/s', 'cores': cores, 'kind': 'reference', 'sample': sample},
         'e2e': {'value': value, 'unit': 'CTU/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'satd_evals_per_s': value * evals_per_ctu if evals_per_ctu else None,
+        'satd_evals_per_ctu': evals_per_ctu,
+        'satd_evals_note': 'rough-mode-decision evaluations (prediction + SAD + SATD of one mode of one CU) the plain encoder makes per CTU, counted on one crop per QP by the '
+                           'pass-through twin; the b200 arm evaluates every slot of every candidate CU (satd_evals_per_step), the reference only the ones its pruned walk reaches',
     })
     import shutil
     shutil.rmtree(tmp, ignore_errors=True)
@@ -589,6 +657,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-tu-stage', action='store_true')
+    ap.add_argument('--no-strong', action='store_true', help='skip the configs[2] strong-scaling leg (64 x 2160p frames sharded over the ranks)')
     ap.add_argument('--no-bitexact', action='store_true', help='skip the brokered bit-exact encode leg (walker processes + plain reference on the host cores)')
     ap.add_argument('--resident-only', action='store_true', help='profiling aid: only the HBM-resident timed loop (no e2e / TU / CPU legs); not a bench line')
     args = ap.parse_args()

@@ -122,6 +122,13 @@ bool      g_inRmd = false;                  // between initIntraPatternChType( f
 int       g_curSlot = -1;                   // slot of the last skipped RMD prediction
 IntraSearch* g_is = nullptr;
 
+// VVCB_SHIM_OFF=1 (every call runs the reference's own code): the wrappers only count the rough-mode-decision evaluations of the plain
+// encoder -- one prediction + SAD + SATD each -- for bench.py's reference arm (BASELINE.json's second metric, SATD block-mode evals / s)
+bool g_counting = false, g_countRmd = false;
+int  g_cntX = 0, g_cntY = 0, g_cntW = 0, g_cntH = 0;
+long g_satdEvals = 0, g_tuQuantReal = 0;
+bool countArea(const CompArea& a) { return g_counting && a.compID == COMPONENT_Y && a.x == g_cntX && a.y == g_cntY && (int)a.width == g_cntW && (int)a.height == g_cntH; }
+
 struct PendingTu { const TransformUnit* tu = nullptr; TuEntry* e = nullptr; const Pel* recoBuf = nullptr; } g_pend;
 
 struct Tm { long long ns = 0; };
@@ -157,6 +164,7 @@ void report()
               (int)g_enabled, g_st.estCalls, g_st.visits, g_st.cuReuse, g_st.rmdRoundTrips, g_st.tuRoundTrips, g_st.demandRoundTrips, g_st.jobsPrefetched, g_st.jobsDemand,
               g_st.refFetchSkipped, g_st.predSkipped, g_st.predServed, g_st.distServed, g_st.preselServed, g_st.quantServed, g_st.quantDq, g_st.quantTs, g_st.quantLfnst,
               g_st.invServed, g_st.sseServed, g_st.bitsServed, g_st.bitsReal, g_st.staleRate, g_st.engineNs * 1e-9, g_tEst.ns * 1e-9, g_tPre.ns * 1e-9, g_tWrap.ns * 1e-9);
+      fprintf(f, ", \"reference_satd_evals\": %ld, \"reference_tu_quantisations\": %ld", g_satdEvals, g_tuQuantReal);
       if (g_gpu && getenv("VVCB_SHIM_KERNEL_TIMES")) {
         float t[4] = { 0, 0, 0, 0 }, r[3] = { 0, 0, 0 }; int calls = 0, launches = 0;
         vvcb_tu_kernel_times(g_gpu, t, &calls);
@@ -469,7 +477,11 @@ bool __wrap__ZN11IntraSearch18estIntraPredLumaQTER10CodingUnitR11Partitionerdbii
     if (!reg && !g_gpu) { reg = true; atexit(report); }
     Scope scEst(g_tEst);
     g_st.estCalls++;
-    return __real__ZN11IntraSearch18estIntraPredLumaQTER10CodingUnitR11Partitionerdbiib(is, cu, pm, best, mtsCheckRange, mtsFirst, mtsLast, moreProbFirst);
+    g_counting = true; g_countRmd = false;
+    g_cntX = cu.firstPU->Y().x; g_cntY = cu.firstPU->Y().y; g_cntW = pm.currArea().lwidth(); g_cntH = pm.currArea().lheight();
+    const bool r = __real__ZN11IntraSearch18estIntraPredLumaQTER10CodingUnitR11Partitionerdbiib(is, cu, pm, best, mtsCheckRange, mtsFirst, mtsLast, moreProbFirst);
+    g_counting = false;
+    return r;
   }
 
   Scope scEst(g_tEst);
@@ -620,6 +632,7 @@ void __wrap__ZN15IntraPrediction22initIntraPatternChTypeERK10CodingUnitRK8CompAr
     g_st.refFetchSkipped++;
     return;
   }
+  if (countArea(area) && !cu.ispMode) g_countRmd = forceRefFilterFlag;
   if (g_profile) { Scope sc(g_prof[0][catOf(area.compID, cu)]); __real__ZN15IntraPrediction22initIntraPatternChTypeERK10CodingUnitRK8CompAreab(ip, cu, area, forceRefFilterFlag); return; }
   __real__ZN15IntraPrediction22initIntraPatternChTypeERK10CodingUnitRK8CompAreab(ip, cu, area, forceRefFilterFlag);
 }
@@ -627,6 +640,7 @@ void __wrap__ZN15IntraPrediction22initIntraPatternChTypeERK10CodingUnitRK8CompAr
 void __wrap__ZN15IntraPrediction12initIntraMipERK14PredictionUnit(IntraPrediction* ip, const PredictionUnit& pu)
 {
   if (g_inEst && cuMatches(pu.Y()) && !pu.cu->ispMode) { g_inRmd = true; return; }    // :712-714: the MIP pass of the RMD block
+  if (countArea(pu.Y())) g_countRmd = true;
   __real__ZN15IntraPrediction12initIntraMipERK14PredictionUnit(ip, pu);
 }
 
@@ -657,6 +671,7 @@ static void servePrediction(PelBuf& pred, const PredictionUnit& pu, bool mip)
 void __wrap__ZN15IntraPrediction12predIntraAngE11ComponentIDR7AreaBufIsERK14PredictionUnit(IntraPrediction* ip, ComponentID c, PelBuf& pred, const PredictionUnit& pu)
 {
   if (g_inEst && c == COMPONENT_Y && !pu.cu->ispMode && !pu.cu->bdpcmMode && cuMatches(pu.Y())) { servePrediction(pred, pu, false); return; }
+  if (c == COMPONENT_Y && g_countRmd && countArea(pu.Y()) && !pu.cu->ispMode) g_satdEvals++;
   if (g_profile) { Scope sc(g_prof[1][catOf(c, *pu.cu)]); __real__ZN15IntraPrediction12predIntraAngE11ComponentIDR7AreaBufIsERK14PredictionUnit(ip, c, pred, pu); return; }
   __real__ZN15IntraPrediction12predIntraAngE11ComponentIDR7AreaBufIsERK14PredictionUnit(ip, c, pred, pu);
 }
@@ -664,6 +679,7 @@ void __wrap__ZN15IntraPrediction12predIntraAngE11ComponentIDR7AreaBufIsERK14Pred
 void __wrap__ZN15IntraPrediction12predIntraMipE11ComponentIDR7AreaBufIsERK14PredictionUnit(IntraPrediction* ip, ComponentID c, PelBuf& pred, const PredictionUnit& pu)
 {
   if (g_inEst && c == COMPONENT_Y && !pu.cu->ispMode && cuMatches(pu.Y())) { servePrediction(pred, pu, true); return; }
+  if (c == COMPONENT_Y && g_countRmd && countArea(pu.Y()) && !pu.cu->ispMode) g_satdEvals++;
   if (g_profile) { Scope sc(g_prof[1][catOf(c, *pu.cu)]); __real__ZN15IntraPrediction12predIntraMipE11ComponentIDR7AreaBufIsERK14PredictionUnit(ip, c, pred, pu); return; }
   __real__ZN15IntraPrediction12predIntraMipE11ComponentIDR7AreaBufIsERK14PredictionUnit(ip, c, pred, pu);
 }
@@ -700,6 +716,8 @@ void __wrap__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamR
 {
   g_pend = PendingTu();
   if (!tuServed(tu, c)) {
+    g_countRmd = false;                                  // the full-RD loop has begun
+    g_tuQuantReal++;
     std::unique_ptr<Scope> sc(g_profile ? new Scope(g_prof[4][catOf(c, *tu.cu)]) : nullptr);
     __real__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamRiRK3Ctxb(tq, tu, c, qp, absSum, ctx, loadTr);
     return;

@@ -335,6 +335,19 @@ int vvcb_residual_bits(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int3
   return VVCB_OK;
 }
 
+// profiling entry points the shims reference: nothing to time here
+int vvcb_kernel_timing(vvcb_ctx* ctx, int) { return ctx ? VVCB_OK : VVCB_ERR_ARG; }
+int vvcb_kernel_times(vvcb_ctx* ctx, float ms[3], int* launches) { if (!ctx || !ms) return VVCB_ERR_ARG; ms[0] = ms[1] = ms[2] = 0.f; if (launches) *launches = 0; return VVCB_OK; }
+int vvcb_tu_kernel_times(vvcb_ctx* ctx, float ms[4], int* calls) { if (!ctx || !ms) return VVCB_ERR_ARG; ms[0] = ms[1] = ms[2] = ms[3] = 0.f; if (calls) *calls = 0; return VVCB_OK; }
+
+int vvcb_reco_from_orig(vvcb_ctx* ctx)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  if (ctx->remote || (*ctx->origP).empty()) FAIL(VVCB_ERR_STATE, "vvcb_reco_from_orig: no frame owned by the context");
+  *ctx->recoP = *ctx->origP;
+  return VVCB_OK;
+}
+
 int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
 {
   if (!ctx) return VVCB_ERR_ARG;
