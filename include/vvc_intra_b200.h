@@ -185,6 +185,10 @@ typedef struct vvcb_rmd_brief {
   uint8_t  reserved[12];
 } vvcb_rmd_brief;
 int vvcb_rmd_eval_brief(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_brief* out);
+/* ... with the visits already resident on the device (uploaded once with vvcb_dev_upload: a static plan such as the exhaustive candidate sweep,
+ * the same for every picture): per call only the brief records travel, in chunks that overlap the kernels.  No validation (see
+ * vvcb_frame_bind_device).  out: HOST.                                                                                            */
+int vvcb_rmd_eval_brief_resident(vvcb_ctx* ctx, const void* d_visits, int n, vvcb_rmd_brief* out);
 /* VVCB_OPT_TRUSTED_VISITS (default 0): 1 = the caller guarantees well-formed visits (positions inside the picture, availability
  * within the picture, sizes 4..64): the host-side validation pass of the batch entry points is skipped.                          */
 #define VVCB_OPT_TRUSTED_VISITS 3

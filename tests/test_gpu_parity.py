@@ -819,6 +819,12 @@ def test_brief_records_carry_the_same_lists(eng10):
         b = eng10.rmd_eval_brief(sweep)
     finally:
         eng10.set_option(vb.OPT_TRUSTED_VISITS, 0)
+    # the visits as a resident plan: same records
+    d_plan = eng10.dev_alloc(sweep.nbytes)
+    eng10.dev_upload(d_plan, sweep)
+    b2 = eng10.rmd_eval_brief_resident(d_plan, len(sweep), np.zeros(len(sweep), vb.BRIEF_DTYPE))
+    eng10.dev_free(d_plan)
+    assert b2.tobytes() == b.tobytes()
     eng10.reco_update(frame)
     f = eng10.rmd_eval(sweep)
     assert np.array_equal(b['n_rd'], f['n_rd'].astype(np.uint8)) and np.array_equal(b['n_final'], f['n_final'].astype(np.uint8)) and np.array_equal(b['n_had'], f['n_had'].astype(np.uint8))

@@ -675,7 +675,9 @@ static int ensure_pipeline(vvcb_ctx* ctx)
 }
 
 // results or brief (exactly one): the record the chunks copy back
-static int rmd_eval_pipelined(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results, vvcb_rmd_brief* brief = nullptr)
+// dResident (optional): the visits already live on the device (a static plan such as the exhaustive sweep's): nothing is uploaded or validated
+static int rmd_eval_pipelined(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n, vvcb_rmd_result* results, vvcb_rmd_brief* brief = nullptr,
+                              const vvcb_rmd_visit* dResident = nullptr)
 {
   int rc = ensure_pipeline(ctx);
   if (rc) return rc;
@@ -694,17 +696,20 @@ static int rmd_eval_pipelined(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n
       if (c == 0 && rest > edge) m = edge;
       else if (rest > edge && rest - m < edge) m = rest - edge;      // leave exactly one short chunk for the end
     }
-    if ((status = check_visits(ctx, visits + off, m, off))) break;
+    if (!dResident && (status = check_visits(ctx, visits + off, m, off))) break;
     cudaError_t e = cudaSuccess;
-    if (c >= 2) e = cudaStreamWaitEvent(ctx->sIn, ctx->evComp[b], 0);              // chunk c-2 no longer reads this buffer
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->dVisP[b], visits + off, (size_t)m * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->sIn);
-    if (e == cudaSuccess) e = cudaEventRecord(ctx->evIn[b], ctx->sIn);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->evIn[b], 0);
+    const vvcb_rmd_visit* dIn = dResident ? dResident + off : ctx->dVisP[b];
+    if (!dResident) {
+      if (c >= 2) e = cudaStreamWaitEvent(ctx->sIn, ctx->evComp[b], 0);              // chunk c-2 no longer reads this buffer
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->dVisP[b], visits + off, (size_t)m * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->sIn);
+      if (e == cudaSuccess) e = cudaEventRecord(ctx->evIn[b], ctx->sIn);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->evIn[b], 0);
+    }
     if (e == cudaSuccess && c >= 2) e = cudaStreamWaitEvent(ctx->stream, ctx->evOut[b], 0);   // its results have left the device
     if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval: pipeline stage failed: %s", cudaGetErrorString(e)); status = VVCB_ERR_CUDA; break; }
     // brief records are written into the chunk's result buffer (a fifth of its size)
-    if ((status = brief ? launch_rmd(ctx, ctx->dVisP[b], m, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<vvcb_rmd_brief*>(ctx->dResP[b]))
-                        : launch_rmd(ctx, ctx->dVisP[b], m, ctx->dResP[b], nullptr, nullptr))) break;
+    if ((status = brief ? launch_rmd(ctx, dIn, m, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<vvcb_rmd_brief*>(ctx->dResP[b]))
+                        : launch_rmd(ctx, dIn, m, ctx->dResP[b], nullptr, nullptr))) break;
     e = cudaEventRecord(ctx->evComp[b], ctx->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->sOut, ctx->evComp[b], 0);
     if (e == cudaSuccess) e = brief ? cudaMemcpyAsync(brief + off, ctx->dResP[b], (size_t)m * sizeof(vvcb_rmd_brief), cudaMemcpyDeviceToHost, ctx->sOut)
@@ -776,6 +781,17 @@ extern "C" int vvcb_rmd_eval_brief(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, 
   CK(cudaMemcpyAsync(out, ctx->dBrief, (size_t)n * sizeof(vvcb_rmd_brief), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return VVCB_OK;
+}
+
+extern "C" int vvcb_rmd_eval_brief_resident(vvcb_ctx* ctx, const void* d_visits, int n, vvcb_rmd_brief* out)
+{
+  if (!ctx) return VVCB_ERR_ARG;
+  REMOTE_UNAVAILABLE("vvcb_rmd_eval_brief_resident");
+  if (n < 0 || (n > 0 && (!d_visits || !out))) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval_brief_resident: bad argument"); return VVCB_ERR_ARG; }
+  if (n == 0) return VVCB_OK;
+  if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_rmd_eval_brief_resident: no frame"); return VVCB_ERR_STATE; }
+  CK(cudaSetDevice(ctx->device));
+  return rmd_eval_pipelined(ctx, nullptr, n, nullptr, out, static_cast<const vvcb_rmd_visit*>(d_visits));
 }
 
 extern "C" int vvcb_rmd_eval_device(vvcb_ctx* ctx, const void* d_visits, int n, void* d_results, void* d_details)

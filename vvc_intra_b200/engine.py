@@ -104,6 +104,7 @@ def load_library():
         L.vvcb_reco_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.vvcb_rmd_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.vvcb_rmd_eval_brief.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.vvcb_rmd_eval_brief_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.vvcb_rmd_eval_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.vvcb_rmd_pred.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.vvcb_rmd_pred_all.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -291,6 +292,13 @@ class IntraCostEngine:
         elif out.dtype != BRIEF_DTYPE or len(out) < len(visits) or not out.flags['C_CONTIGUOUS']:
             raise ValueError('out must be a contiguous BRIEF_DTYPE array of at least len(visits) records')
         self._ck(self._lib.vvcb_rmd_eval_brief(self._ctx, _ptr(visits), len(visits), _ptr(out)))
+        return out
+
+    def rmd_eval_brief_resident(self, d_visits, n, out):
+        """vvcb_rmd_eval_brief_resident: visits resident on the device (dev_alloc + dev_upload), brief records to the host array `out`."""
+        if out.dtype != BRIEF_DTYPE or len(out) < n or not out.flags['C_CONTIGUOUS']:
+            raise ValueError('out must be a contiguous BRIEF_DTYPE array of at least n records')
+        self._ck(self._lib.vvcb_rmd_eval_brief_resident(self._ctx, d_visits, n, _ptr(out)))
         return out
 
     def rmd_pred(self, visit, slot):
