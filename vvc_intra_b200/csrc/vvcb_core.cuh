@@ -56,6 +56,29 @@ VHD int vsad(int a, int b, int c)
 #endif
 }
 
+// ---- absolute Hadamard coefficients as u16 pairs ---------------------------------------------------------------------------------
+// |coefficient| of a 4x8 half stays below 2^16 (10-bit residual x 8 x 4, x 2 for the 16x8 / 8x16 partner stage), so the first half's
+// values are kept two per register; the fold over the halves, sum of max(|a|, |b|), is one packed unsigned max (VIMNMX.U16x2) and
+// one dot product with (1, 1) (IDP.2A.U16.U8) per pair.
+VHD uint32_t pack_u16x2(int lo, int hi) { return (uint32_t)lo | ((uint32_t)hi << 16); }
+VHD uint32_t max_u16x2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+  return __vmaxu2(a, b);
+#else
+  const uint32_t al = a & 0xffffu, bl = b & 0xffffu, ah = a >> 16, bh = b >> 16;
+  return (al > bl ? al : bl) | ((ah > bh ? ah : bh) << 16);
+#endif
+}
+VHD int add_halves_u16x2(uint32_t w, int acc)
+{
+#if defined(__CUDA_ARCH__)
+  return (int)__dp2a_lo(w, 0x00000101u, (unsigned)acc);
+#else
+  return acc + (int)(w & 0xffffu) + (int)(w >> 16);
+#endif
+}
+
 // Per (shape, mode) prediction parameters, precomputed on the host at context creation.
 struct ModeParam {
   int16_t  angle;        // intraPredAngle (signed)

@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
         const int x0 = ux * 8, y0 = uy * 8;
         const int partnerMask = TILE == 4 ? 1 : sh.unitsX;
         const bool owner = TILE == 4 ? (ux & 1) == 0 : (uy & 1) == 0;
-        int c0[4][8];
+        uint32_t c0[4][4];                     // |coefficients| of the first half, two per register
         int t = 0;
 #pragma unroll 1
         for (int k = 0; k < 2; k++) {
@@ -758,12 +758,12 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-              for (int j = 0; j < 8; j++) c0[i][j] = vabs(d[i][j]);
+              for (int j = 0; j < 4; j++) c0[i][j] = pack_u16x2(vabs(d[i][2 * j]), vabs(d[i][2 * j + 1]));
           } else {
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-              for (int j = 0; j < 8; j++) t += vmax(c0[i][j], vabs(d[i][j]));
+              for (int j = 0; j < 4; j++) t = add_halves_u16x2(max_u16x2(c0[i][j], pack_u16x2(vabs(d[i][2 * j]), vabs(d[i][2 * j + 1]))), t);
           }
         }
         if (TILE == 3) satd = (2 * t + 2) >> 2;                                // CL/RdCost.cpp:2306
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
       } else {
         // 4xN / Nx4 shapes: a lane owns one SATD tile = one (4x4) or two (8x4, 4x8) 4x4 units
         const int tx = u & ((1 << sh.lgTilesX) - 1), ty = u >> sh.lgTilesX;
-        int c0[4][4];
+        uint32_t c0[4][2];                     // |coefficients| of the first 4x4 unit of the tile, two per register
         int t = 0;
 #pragma unroll
         for (int k = 0; k < (TILE == 0 ? 1 : 2); k++) {
@@ -796,12 +796,12 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
 #pragma unroll
               for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) c0[i][j] = vabs(d[i][j]);
+                for (int j = 0; j < 2; j++) c0[i][j] = pack_u16x2(vabs(d[i][2 * j]), vabs(d[i][2 * j + 1]));
             } else {
 #pragma unroll
               for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) t += vmax(c0[i][j], vabs(d[i][j]));
+                for (int j = 0; j < 2; j++) t = add_halves_u16x2(max_u16x2(c0[i][j], pack_u16x2(vabs(d[i][2 * j]), vabs(d[i][2 * j + 1]))), t);
             }
           }
         }
