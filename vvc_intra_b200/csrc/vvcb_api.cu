@@ -1013,6 +1013,12 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
   if (tm && !src) CK(cudaEventRecord(ctx->tev[0], ctx->stream));
   launch_tu(P);
   if (tm) CK(cudaEventRecord(ctx->tev[1], ctx->stream));
+  // transform-skip RDOQ and dependent quantisation work on disjoint jobs: the former runs on a side stream next to the latter
+  const bool tsAside = nTs && nDq;
+  if (tsAside) {
+    CK(cudaEventRecord(ctx->evPlan, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->sKind[0], ctx->evPlan, 0));
+  }
   if (nDq) {
     dq_rate_kernel<<<n_rates, 32, 0, ctx->stream>>>(static_cast<const vvcb_dq_rates*>(ctx->dTu[10]), n_rates, static_cast<DqRateTab*>(ctx->dTu[11]));
     DqParams D;
@@ -1021,26 +1027,36 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     int* firstSorted = firstRaw + 2 * nDq;
     const int firstGrid = (nDq + kDqGroups - 1) / kDqGroups < ctx->numSms * 8 ? (nDq + kDqGroups - 1) / kDqGroups : ctx->numSms * 8;
     dq_first_kernel<<<firstGrid, kDqThreads, 0, ctx->stream>>>(P.jobs, static_cast<const int*>(ctx->dTu[9]), nDq, P.dqCoeff, ctx->dDqRom, ctx->bd, firstRaw);
-    int* binCount = firstRaw + 3 * (size_t)nDq;
-    const int sortGrid = (nDq + kDqSortPerBlock - 1) / kDqSortPerBlock;
-    CK(cudaMemsetAsync(binCount, 0, kDqBins * sizeof(int), ctx->stream));
-    dq_hist_kernel<<<sortGrid, kDqSortThreads, 0, ctx->stream>>>(firstRaw, nDq, binCount);
-    dq_scan_kernel<<<1, 32, 0, ctx->stream>>>(binCount);
-    dq_scatter_kernel<<<sortGrid, kDqSortThreads, 0, ctx->stream>>>(static_cast<const int*>(ctx->dTu[9]), firstRaw, nDq, binCount, orderSorted, firstSorted);
-    D.jobs = P.jobs; D.order = orderSorted; D.firstPos = firstSorted; D.n = nDq;
+    // The counting sort by first test position buys warp efficiency for sweeps (eight TUs per warp walk scans of equal length); a walk's batch
+    // of a few dozen candidates is latency bound and skips its three launches.
+    const bool sortJobs = nDq > 2048;
+    if (sortJobs) {
+      int* binCount = firstRaw + 3 * (size_t)nDq;
+      const int sortGrid = (nDq + kDqSortPerBlock - 1) / kDqSortPerBlock;
+      CK(cudaMemsetAsync(binCount, 0, kDqBins * sizeof(int), ctx->stream));
+      dq_hist_kernel<<<sortGrid, kDqSortThreads, 0, ctx->stream>>>(firstRaw, nDq, binCount);
+      dq_scan_kernel<<<1, 32, 0, ctx->stream>>>(binCount);
+      dq_scatter_kernel<<<sortGrid, kDqSortThreads, 0, ctx->stream>>>(static_cast<const int*>(ctx->dTu[9]), firstRaw, nDq, binCount, orderSorted, firstSorted);
+      ctx->launches += 3;
+    }
+    D.jobs = P.jobs; D.order = sortJobs ? orderSorted : static_cast<const int*>(ctx->dTu[9]); D.firstPos = sortJobs ? firstSorted : firstRaw; D.n = nDq;
     D.coeff = P.dqCoeff; D.level = P.level; D.deq = static_cast<int32_t*>(ctx->dTu[8]); D.results = P.results;
     D.rates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]); D.tabs = static_cast<const DqRateTab*>(ctx->dTu[11]);
     D.rom = ctx->dDqRom; D.scratch = static_cast<uint8_t*>(ctx->dTu[12]); D.bd = ctx->bd;
     dq_kernel<<<dqGrid, kDqThreads, 0, ctx->stream>>>(D);
-    ctx->launches += 6;
+    ctx->launches += 3;
   }
   if (nTs) {
     RdoqParams R;
     R.jobs = P.jobs; R.order = static_cast<const int*>(ctx->dTu[16]); R.n = nTs; R.coeff = P.dqCoeff; R.level = P.level;
     R.deq = static_cast<int32_t*>(ctx->dTu[8]); R.results = P.results; R.rates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]);
     R.rom = ctx->dDqRom; R.bd = ctx->bd;
-    rdoq_ts_kernel<<<(nTs + 127) / 128, 128, 0, ctx->stream>>>(R);
+    rdoq_ts_kernel<<<(nTs + 127) / 128, 128, 0, tsAside ? ctx->sKind[0] : ctx->stream>>>(R);
     ctx->launches++;
+    if (tsAside) {
+      CK(cudaEventRecord(ctx->evKind[0], ctx->sKind[0]));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->evKind[0], 0));
+    }
   }
   if (tm) CK(cudaEventRecord(ctx->tev[2], ctx->stream));
   if (nDq || nTs) {
