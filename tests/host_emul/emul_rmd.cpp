@@ -70,7 +70,7 @@ extern "C" int emul_rmd_eval(const int16_t* orig, const int16_t* reco, int strid
   EvalParams P;
   P.visits = visits; P.items = items.data(); P.plan = &plan;
   std::vector<uint32_t> sm((size_t)2 * VVCB_NUM_SLOTS * n);
-  P.sadSM = sm.data(); P.satdSM = sm.data() + (size_t)VVCB_NUM_SLOTS * n; P.nVisits = n;
+  P.sadSM = sm.data(); P.satdSM = (details || predOut) ? sm.data() + (size_t)VVCB_NUM_SLOTS * n : nullptr; P.nVisits = n;   // as launch_rmd (vvcb_api.cu)
   P.orig = orig; P.reco = reco; P.stride = stride; P.bd = bd; P.ctu = ctu; P.rom = &rom; P.predOut = predOut;
   for (int b = 0; b < kNumBuckets; b++) {
     bool packed = false;

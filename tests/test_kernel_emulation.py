@@ -88,6 +88,11 @@ def test_emulated_kernels_match_oracle_on_random_visits(emul, bd, seed):
     orig, reco, arr = G.random_case(rng, bd, 4, plane=(256, 512))
     res, det, _ = run_emul(emul, orig, reco, bd, arr)
     ora, odet = O.rmd_batch(orig, reco, bd, 128, arr)
+    # without detail tables only min(2 * SAD, SATD) is handed from the evaluation kernels to the list kernel: same lists
+    res2 = np.zeros(len(arr), O.RESULT_DTYPE)
+    assert emul.emul_rmd_eval(np.ascontiguousarray(orig, np.int16).ctypes.data_as(C.c_void_p), np.ascontiguousarray(reco, np.int16).ctypes.data_as(C.c_void_p), orig.shape[1], bd, 128,
+                              arr.ctypes.data_as(C.c_void_p), len(arr), res2.ctypes.data_as(C.c_void_p), None, None) == 0
+    assert res2.tobytes() == ora.tobytes()
     # the brief records (vvcb_rmd_eval_brief) carry the same lists as mode codes
     import vvc_intra_b200 as vb
     brief = np.zeros(len(arr), vb.BRIEF_DTYPE)
@@ -111,6 +116,11 @@ def test_emulated_packed_items_ragged_tails_and_ctu_rows(emul):
     arr['y'][on_row] = 128 * rng.integers(1, 3, int(on_row.sum()))
     res, det, _ = run_emul(emul, orig, reco, bd, arr)
     ora, odet = O.rmd_batch(orig, reco, bd, 128, arr)
+    # without detail tables only min(2 * SAD, SATD) is handed from the evaluation kernels to the list kernel: same lists
+    res2 = np.zeros(len(arr), O.RESULT_DTYPE)
+    assert emul.emul_rmd_eval(np.ascontiguousarray(orig, np.int16).ctypes.data_as(C.c_void_p), np.ascontiguousarray(reco, np.int16).ctypes.data_as(C.c_void_p), orig.shape[1], bd, 128,
+                              arr.ctypes.data_as(C.c_void_p), len(arr), res2.ctypes.data_as(C.c_void_p), None, None) == 0
+    assert res2.tobytes() == ora.tobytes()
     # the brief records (vvcb_rmd_eval_brief) carry the same lists as mode codes
     import vvc_intra_b200 as vb
     brief = np.zeros(len(arr), vb.BRIEF_DTYPE)

@@ -535,7 +535,8 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   if (tm) CK(cudaEventRecord(ctx->kev[1], ctx->stream));
   EvalParams P;
   P.visits = dVisits; P.items = ctx->dItems; P.plan = ctx->dPlan;
-  P.sadSM = ctx->dSlotMajor; P.satdSM = ctx->dSlotMajor + (size_t)VVCB_NUM_SLOTS * n; P.nVisits = n;
+  // without detail tables the lists only need min(2 * SAD, SATD): one scratch plane instead of two
+  P.sadSM = ctx->dSlotMajor; P.satdSM = (dDetails || dPred) ? ctx->dSlotMajor + (size_t)VVCB_NUM_SLOTS * n : nullptr; P.nVisits = n;
   P.orig = ctx->bOrig; P.reco = ctx->bReco; P.stride = ctx->stride; P.bd = ctx->bd; P.ctu = ctx->ctu; P.rom = ctx->dRom;
   P.predOut = dPred;
   const long long maxWarps = (long long)n * 8;          // no point in more warps than work items

@@ -80,7 +80,7 @@ struct EvalParams {
   const WorkItem*       items;
   PlanState*            plan;
   uint32_t*             sadSM;    // slot-major scratch: sadSM[slot * nVisits + visit] (coalesced for the list kernel)
-  uint32_t*             satdSM;
+  uint32_t*             satdSM;   // nullptr: only min(2 * SAD, SATD) is handed over, in sadSM (no detail tables were asked for: the lists need nothing else)
   int                   nVisits;
   const int16_t*        orig;
   const int16_t*        reco;
@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
       const vvcb_rmd_visit& v = sVisit[warp][vi];
       const SM& sm = smem[warp][vi];
       uint32_t* sadOut  = P.sadSM + sIndex[warp][vi];
-      uint32_t* satdOut = P.satdSM + sIndex[warp][vi];
+      uint32_t* satdOut = P.satdSM ? P.satdSM + sIndex[warp][vi] : nullptr;
       const int16_t* org = P.orig + (size_t)v.y * P.stride + v.x;
       const int u = tk & (lanes - 1);
       const int slot = kind_slot(rom, v, KIND, (PACK ? 0 : item.slot_begin) + (tk >> sh.lgLanes));
@@ -814,7 +814,10 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
           sad  += __shfl_xor_sync(0xffffffffu, sad, o);
           satd += __shfl_xor_sync(0xffffffffu, satd, o);
         }
-        if (act && gl == 0) { sadOut[(size_t)slot * P.nVisits] = (uint32_t)sad; satdOut[(size_t)slot * P.nVisits] = (uint32_t)satd; }
+        if (act && gl == 0) {
+          if (P.satdSM) { sadOut[(size_t)slot * P.nVisits] = (uint32_t)sad; satdOut[(size_t)slot * P.nVisits] = (uint32_t)satd; }
+          else sadOut[(size_t)slot * P.nVisits] = (uint32_t)vmin(2 * sad, satd);                     // EL/IntraSearch.cpp:515
+        }
       } else {
         // 64 lanes per slot: two consecutive warp iterations belong to the same slot
         accSad += sad; accSatd += satd;
@@ -823,7 +826,10 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
             accSad  += __shfl_xor_sync(0xffffffffu, accSad, o);
             accSatd += __shfl_xor_sync(0xffffffffu, accSatd, o);
           }
-          if (lane == 0) { sadOut[(size_t)slot * P.nVisits] = (uint32_t)accSad; satdOut[(size_t)slot * P.nVisits] = (uint32_t)accSatd; }
+          if (lane == 0) {
+            if (P.satdSM) { sadOut[(size_t)slot * P.nVisits] = (uint32_t)accSad; satdOut[(size_t)slot * P.nVisits] = (uint32_t)accSatd; }
+            else sadOut[(size_t)slot * P.nVisits] = (uint32_t)vmin(2 * accSad, accSatd);
+          }
           accSad = 0; accSatd = 0;
         }
       }
@@ -1064,10 +1070,11 @@ __global__ void __launch_bounds__(kListThreads, VVCB_LIST_MIN_CTAS) rmd_lists_ke
     const bool testMip = numMip > 0;
     const bool mrlAllowed = visit_mrl_allowed(v, ctu);
     const uint32_t* mySad = sadSM + vi;
-    const uint32_t* mySatd = satdSM + vi;
+    const uint32_t* mySatd = satdSM ? satdSM + vi : nullptr;        // nullptr: sadSM already holds min(2 * SAD, SATD)
     vvcb_rmd_detail* D = details ? details + vi : nullptr;
 
     auto dist_of = [&](int slot) -> double {
+      if (!mySatd) return (double)mySad[(size_t)slot * n];
       const uint64_t sad = mySad[(size_t)slot * n], satd = mySatd[(size_t)slot * n];
       return (double)(sad * 2 < satd ? sad * 2 : satd);                        // :515
     };
