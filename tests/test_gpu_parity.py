@@ -905,3 +905,21 @@ def test_config2_1080p10_ctu_row_at_four_qps_served_is_bit_identical(tmp_path):
     stats = _run_served_vs_plain(tmp_path, cases, 10, (1920, 128), workers=4)
     print('1080p10 CTU row broker stats', stats)
     assert stats['clients_seen'] == 4 and stats['visits'] > 400000 and stats['max_batch'] >= 2
+
+
+def test_training_set_dump_through_the_feature_kernel(eng10, tmp_path):
+    """GET_TRAINING_SET (EL/CABACWriter.cpp:515-858) on the device: every node of a random final coding tree of a 416x240 picture, features from
+    vvcb_features_eval, the four .dat files; records equal the oracle's features, labels the tree's splits."""
+    from test_host_features import random_tree, cu_lookup
+    from make_golden import synth_yuv
+    from vvc_intra_b200 import training_set as T
+    Y = synth_yuv(416, 240, 8)[0].astype(np.int16)
+    nodes, leaves = random_tree(np.random.default_rng(12), 416, 240)
+    get_cu = cu_lookup(leaves, 416, 240)
+    eng10.frame_begin(Y)
+    n = T.dump_training_set(eng10, nodes, get_cu, str(tmp_path))
+    jobs, labels = T.training_jobs(nodes, get_cu)
+    assert n == len(jobs) > 100
+    data = np.fromfile(tmp_path / 'Data_Partition.dat', '<i4').reshape(-1, 26)
+    assert np.array_equal(data, O.features_batch(Y, jobs)['f'][:, :26])
+    assert np.array_equal(np.fromfile(tmp_path / 'Label_Partition.dat', '<i4'), labels)
