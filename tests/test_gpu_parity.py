@@ -91,7 +91,7 @@ def test_extreme_sample_values(eng10):
 
 def test_full_1080p_sweep_properties(eng10):
     """BASELINE config 2 size: every candidate CU of a 1920x1080 10-bit picture (679 260 visits).  Checked by
-    (i) a seeded sample of visits against the oracle, (ii) determinism, (iii) domain properties: DC-only
+    (i) ALL visits against the oracle (lists, costs, SAD / SATD of every slot), (ii) determinism, (iii) domain properties: DC-only
     content has zero distortion for planar/DC, list costs ascend, SATD of identical blocks is zero."""
     import sys
     sys.path.insert(0, 'tools')
@@ -105,10 +105,19 @@ def test_full_1080p_sweep_properties(eng10):
     res, det = eng10.rmd_eval(vis, detail=True)
     res2 = eng10.rmd_eval(vis)
     assert res.tobytes() == res2.tobytes()
+    # EVERY visit of the frame against the oracle: lists (modes and double costs) and the SAD / SATD of every slot; the oracle is a plain-C
+    # loop over visits without shared state, so the host's cores share it (ctypes releases the GIL)
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    O.rmd_batch(orig, orig, 10, 128, vis[:1])                        # loads the library before the threads start
+    parts = np.array_split(np.arange(len(vis)), 8 * (os.cpu_count() or 1))
+    def check(ix):
+        ora, odet = O.rmd_batch(orig, orig, 10, 128, vis[ix])
+        return res[ix].tobytes() == ora.tobytes() and det[ix].tobytes() == odet.tobytes()
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as pool:
+        assert all(pool.map(check, parts))
     rng = np.random.default_rng(11)
     idx = np.sort(rng.choice(len(vis), 3000, replace=False))
-    ora, odet = O.rmd_batch(orig, orig, 10, 128, vis[idx])
-    assert res[idx].tobytes() == ora.tobytes() and det[idx].tobytes() == odet.tobytes()
     n_rd = res['n_rd']
     assert n_rd.min() >= 2 and n_rd.max() <= vb.engine.MAX_LIST
     for i in idx[:200]:
