@@ -305,6 +305,20 @@ int vvcb_tu_eval_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, int n_visits,
  * before every candidate, :1222 / :3448).  slots[k] is the evaluation slot (VVCB_SLOT_*) of job k; jobs[k].offset addresses this
  * request's own level / reco / pred arrays (n_jobs dense w*h blocks).  The requests of one call are independent: they may
  * belong to different pictures of the plane (broker), which is why the reconstruction rectangles travel with them.            */
+/* Candidates named by the engine itself: which modes survive the rough mode decision is only known after it ran, so a request may carry
+ * TEMPLATES instead of jobs -- (transform, LFNST index, flags, QP, lambda) prototypes -- and the engine combines each with every mode of
+ * the visit's final list (modes & VVCB_AUTO_FINAL) and / or of the regular-only list of vvcb_rmd_detail that is not in the final list
+ * (modes & VVCB_AUTO_REGULAR: what the LFNST passes of small blocks restore, EL/IntraSearch.cpp:686-701), modes in list order, templates in
+ * the given order; skip_mip drops MIP modes (LFNST is not combined with MIP for small blocks, allowLfnstWithMip).  One round trip instead of two. */
+#define VVCB_AUTO_FINAL    1u
+#define VVCB_AUTO_REGULAR  2u
+typedef struct vvcb_cu_auto {
+  vvcb_tu_job job;            /* prototype: position, size, mts_idx, flags, QP, lfnst_idx, lambda, cbf_delta_bits; offset / intra_mode / rate_idx are filled in */
+  uint8_t modes;              /* VVCB_AUTO_*                                                                                       */
+  uint8_t skip_mip;
+  uint8_t pad[6];
+} vvcb_cu_auto;
+
 typedef struct vvcb_cu_request {
   const vvcb_rect* rects; int n_rects; const int16_t* rect_samples; size_t n_rect_samples;
   const vvcb_rmd_visit* visit;           /* may be NULL when the request only pushes rectangles                                  */
@@ -314,6 +328,12 @@ typedef struct vvcb_cu_request {
   vvcb_rmd_result* result; vvcb_rmd_detail* detail;            /* outputs of want_rmd (detail optional)                          */
   int32_t* level; int16_t* reco; int16_t* pred;                /* optional outputs of the jobs, n_jobs * w * h each              */
   vvcb_tu_result* tu_results;                                  /* n_jobs                                                         */
+  /* templates (need want_rmd, and detail when a template names the regular-only list); the expanded candidates come back in the auto_* arrays */
+  const vvcb_cu_auto* autos; int n_autos; int max_auto;        /* max_auto: capacity of the auto_* arrays (further candidates are dropped) */
+  int* n_auto;                                                 /* out: number of expanded candidates                             */
+  uint8_t* auto_slot; uint8_t* auto_tmpl;                      /* out: evaluation slot and template index of each                */
+  int32_t* auto_level; int16_t* auto_reco; int16_t* auto_pred; /* optional outputs, max_auto * w * h each                        */
+  vvcb_tu_result* auto_results;                                /* max_auto                                                       */
 } vvcb_cu_request;
 int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n);
 

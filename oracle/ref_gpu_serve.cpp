@@ -387,6 +387,57 @@ void fetch(CuCache& cu, bool wantRmd, const std::vector<TuSpec>& specs, const Sn
   }
 }
 
+// First pass of a CU in ONE round trip: the rectangles, the rough mode decision, and templates (vvcb_cu_auto) the engine expands over the lists it has
+// just produced -- every candidate the passes of EncCu::xCheckRDCostIntra (EL/EncCu.cpp:2453-2776) can reach: the final list x {DCT-II, transform skip},
+// the final and the regular-only list x {DST-VII/DST-VII, DCT-II + LFNST 1, DCT-II + LFNST 2}.
+void fetchFirstPass(CuCache& cu, const Snapshot& s, bool tsAllowed, bool mtsAllowed, bool mtsPass, bool lfnstWithMip)
+{
+  struct Tm { int lfnst, mts; uint8_t modes, skipMip; };
+  std::vector<Tm> tm;
+  tm.push_back(Tm{ 0, MTS_DCT2_DCT2, VVCB_AUTO_FINAL, 0 });
+  if (tsAllowed) tm.push_back(Tm{ 0, MTS_SKIP, VVCB_AUTO_FINAL, 0 });
+  if (mtsPass) tm.push_back(Tm{ 0, MTS_DST7_DST7, VVCB_AUTO_FINAL | VVCB_AUTO_REGULAR, 0 });
+  tm.push_back(Tm{ 1, MTS_DCT2_DCT2, VVCB_AUTO_FINAL | VVCB_AUTO_REGULAR, (uint8_t)!lfnstWithMip });
+  tm.push_back(Tm{ 2, MTS_DCT2_DCT2, VVCB_AUTO_FINAL | VVCB_AUTO_REGULAR, (uint8_t)!lfnstWithMip });
+  std::vector<vvcb_cu_auto> autos(tm.size());
+  for (size_t i = 0; i < tm.size(); i++) {
+    memset(&autos[i], 0, sizeof(vvcb_cu_auto));
+    makeJob(autos[i].job, cu, TuSpec{ 0, tm[i].lfnst, tm[i].mts, 0 }, s, tsAllowed, mtsAllowed, 0);
+    autos[i].modes = tm[i].modes; autos[i].skip_mip = tm[i].skipMip;
+  }
+  const int maxAuto = 96, bs = cu.w * cu.h;
+  std::vector<int32_t> level((size_t)maxAuto * bs);
+  std::vector<int16_t> reco((size_t)maxAuto * bs), pred((size_t)maxAuto * bs);
+  std::vector<vvcb_tu_result> res(maxAuto);
+  std::vector<uint8_t> slots(maxAuto), tmpl(maxAuto);
+  int nAuto = 0;
+  vvcb_cu_request q;
+  memset(&q, 0, sizeof(q));
+  q.rects = cu.rects.data(); q.n_rects = (int)cu.rects.size(); q.rect_samples = cu.rectSamples.data(); q.n_rect_samples = cu.rectSamples.size();
+  q.visit = &cu.visit; q.want_rmd = 1; q.result = &cu.res; q.detail = &cu.det;
+  q.rates = &s.rates; q.states = &s.states;
+  q.autos = autos.data(); q.n_autos = (int)autos.size(); q.max_auto = maxAuto; q.n_auto = &nAuto; q.auto_slot = slots.data(); q.auto_tmpl = tmpl.data();
+  q.auto_level = level.data(); q.auto_reco = reco.data(); q.auto_pred = pred.data(); q.auto_results = res.data();
+  const auto t0 = std::chrono::steady_clock::now();
+  gpuCheck(vvcb_cu_eval(g_gpu, &q, 1), "vvcb_cu_eval:");
+  g_st.engineNs += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+  cu.pushed = true; cu.rmdValid = true;
+  g_st.rmdRoundTrips++; g_st.visits++; g_st.jobsPrefetched += nAuto;
+  for (int i = 0; i < nAuto; i++) {
+    const Tm& t = tm[tmpl[i]];
+    TuEntry& e = cu.tus[tuKey(slots[i], t.lfnst, t.mts)];
+    e.job = autos[tmpl[i]].job;
+    e.job.offset = (uint32_t)i * bs;
+    e.job.intra_mode = t.lfnst ? (slots[i] >= VVCB_SLOT_MIP ? (uint8_t)PLANAR_IDX : (slots[i] < VVCB_SLOT_MRL1 ? slots[i] : cu.visit.mpm[1 + (slots[i] - VVCB_SLOT_MRL1) % 5])) : 0;
+    e.res = res[i]; e.slot = slots[i];
+    e.level.assign(level.begin() + (size_t)i * bs, level.begin() + (size_t)(i + 1) * bs);
+    e.reco.assign(reco.begin() + (size_t)i * bs, reco.begin() + (size_t)(i + 1) * bs);
+    e.rateHash = s.rateHash; e.stateHash = s.stateHash;
+    std::vector<int16_t>& p = cu.pred[slots[i]];
+    if (p.empty()) p.assign(pred.begin() + (size_t)i * bs, pred.begin() + (size_t)(i + 1) * bs);
+  }
+}
+
 bool cuMatches(const CompArea& a) { return g_cu.valid && a.compID == COMPONENT_Y && a.x == g_cu.x && a.y == g_cu.y && (int)a.width == g_cu.w && (int)a.height == g_cu.h; }
 
 bool tsAllowedFor(const CodingUnit& cu, int w, int h)
@@ -557,10 +608,15 @@ bool __wrap__ZN11IntraSearch18estIntraPredLumaQTER10CodingUnitR11Partitionerdbii
   rememberEntryCtx(cu, is->m_CABACEstimator->getCtx());
   const Snapshot& snap = g_entrySnap;
   const bool tsAllowed = tsAllowedFor(cu, w, h), mtsAllowed = mtsAllowedFor(cu, w, h);
-  if (rmdRuns && !g_cu.rmdValid) fetch(g_cu, true, std::vector<TuSpec>(), snap, tsAllowed, mtsAllowed, false);
+  static const bool noPrefetch = getenv("VVCB_SHIM_NO_PREFETCH") != nullptr;
+  static const bool noMega = getenv("VVCB_SHIM_NO_MEGA") != nullptr;           // candidates fetched per estIntraPredLumaQT call instead of per CU
+  static const bool twoTrips = getenv("VVCB_SHIM_TWO_TRIPS") != nullptr;       // lists first, candidates in a second round trip (the shim names them)
+  if (rmdRuns && !g_cu.rmdValid) {
+    if (!noPrefetch && !noMega && !twoTrips && cu.lfnstIdx == 0 && cu.mtsFlag == 0) fetchFirstPass(g_cu, snap, tsAllowed, mtsAllowed, mtsUsage == 1, allowLfnstWithMip(Size(w, h)));
+    else fetch(g_cu, true, std::vector<TuSpec>(), snap, tsAllowed, mtsAllowed, false);
+  }
 
   // ---- the candidates the full-RD loop of this pass can reach (:1158; transforms per xRecurIntraCodingLumaQT :3340-3501) ----
-  static const bool noPrefetch = getenv("VVCB_SHIM_NO_PREFETCH") != nullptr;
   if (!noPrefetch) {
     struct M { bool mip; int mrl; int mode; };
     std::vector<M> modes;
@@ -597,7 +653,6 @@ bool __wrap__ZN11IntraSearch18estIntraPredLumaQTER10CodingUnitR11Partitionerdbii
     // First pass of a CU: EncCu::xCheckRDCostIntra (EL/EncCu.cpp:2453-2776) goes on to call this function for (lfnst 0, MTS index 0),
     // (lfnst 1) and (lfnst 2) with lists that derive from this pass's (saved lists + MPMs); their candidates ride along so that those
     // calls find everything cached.  VVCB_SHIM_NO_MEGA=1 fetches per call instead.
-    static const bool noMega = getenv("VVCB_SHIM_NO_MEGA") != nullptr;
     if (rmdRuns && !noMega && cu.lfnstIdx == 0 && cu.mtsFlag == 0) {
       std::vector<M> later = modes;
       auto addLater = [&](bool mip, int mrl, int mode) {

@@ -30,6 +30,7 @@ static std::mutex g_oracleMutex;      // the oracle keeps static scratch (single
 
 #define VVCB_BROKER_IMPL_FAKE 1
 #include "../../vvc_intra_b200/csrc/vvcb_broker.inc"
+#include "../../vvc_intra_b200/csrc/vvcb_expand.inc"
 
 extern "C" {
 
@@ -360,7 +361,7 @@ int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
   }
   for (int i = 0; i < n; i++) {
     vvcb_cu_request& q = reqs[i];
-    if ((q.want_rmd || q.n_jobs) && !q.visit) FAIL(VVCB_ERR_ARG, "vvcb_cu_eval: request %d has no visit", i);
+    if ((q.want_rmd || q.n_jobs || q.n_autos) && !q.visit) FAIL(VVCB_ERR_ARG, "vvcb_cu_eval: request %d has no visit", i);
     if (q.want_rmd) {
       if (!q.result) FAIL(VVCB_ERR_ARG, "vvcb_cu_eval: request %d wants the lists but gives no result pointer", i);
       int rc = vvcb_rmd_eval(ctx, q.visit, 1, q.result, q.detail);
@@ -373,6 +374,20 @@ int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
       const size_t ns = (size_t)q.n_jobs << (q.visit->log2w + q.visit->log2h);
       int rc = tu_eval_pred_local(ctx, q.visit, 1, src.data(), q.jobs, q.n_jobs, ns, q.rates, q.states, 1, nullptr, q.level, q.reco, q.pred, q.tu_results);
       if (rc) return rc;
+    }
+    if (q.n_autos) {
+      if (!q.want_rmd || !q.autos || q.max_auto <= 0 || !q.n_auto || !q.auto_slot || !q.auto_tmpl || !q.auto_results) FAIL(VVCB_ERR_ARG, "vvcb_cu_eval: request %d is malformed (templates)", i);
+      for (int k = 0; k < q.n_autos; k++) if ((q.autos[k].modes & VVCB_AUTO_REGULAR) && !q.detail) FAIL(VVCB_ERR_ARG, "vvcb_cu_eval: request %d is malformed (templates)", i);
+      std::vector<vvcb_tu_job> jobs(q.max_auto);
+      const int cnt = vvcb_expand_autos(*q.visit, *q.result, q.detail, q.autos, q.n_autos, q.max_auto, jobs.data(), q.auto_slot, q.auto_tmpl);
+      *q.n_auto = cnt;
+      if (cnt) {
+        std::vector<vvcb_tu_src> src(cnt);
+        for (int k = 0; k < cnt; k++) { src[k].visit = 0; src[k].slot = q.auto_slot[k]; }
+        const size_t ns = (size_t)cnt << (q.visit->log2w + q.visit->log2h);
+        int rc = tu_eval_pred_local(ctx, q.visit, 1, src.data(), jobs.data(), cnt, ns, q.rates, q.states, 1, nullptr, q.auto_level, q.auto_reco, q.auto_pred, q.auto_results);
+        if (rc) return rc;
+      }
     }
   }
   return VVCB_OK;

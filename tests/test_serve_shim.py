@@ -69,11 +69,28 @@ def test_served_encoder_is_bit_identical_and_computes_nothing_itself(built, tmp_
     assert len(a) > 100 and a == b
     rep = json.loads((tmp_path / 'rep.json').read_text())
     assert rep['enabled'] == 1 and rep['visits'] > 1000 and rep['rmd_round_trips'] == rep['visits']
-    assert rep['tu_round_trips'] < 1.1 * rep['visits']                      # one TU round trip per CU (all passes ride with the first)
+    assert rep['tu_round_trips'] < 0.05 * rep['visits']                     # ONE round trip per CU: lists and every candidate of all passes (templates)
     assert rep['demand_round_trips'] == 0 and rep['stale_context'] == 0 and rep['tu_residual_bits_reference'] == 0
     assert rep['predictions_skipped'] > 40 * rep['visits'] and rep['distortions_served'] == 2 * rep['predictions_skipped']
     assert rep['tu_quantised'] > 10000 and rep['tu_rdoq_ts'] > 500 and rep['tu_lfnst'] > 2000 and rep['tu_sse'] == rep['tu_quantised']
     assert rep['tu_residual_bits'] > 5000 and rep['tu_preselections'] > 2000
+
+
+def test_two_round_trips_name_the_same_candidates(built, tmp_path):
+    """VVCB_SHIM_TWO_TRIPS: lists first, then the candidates named by the shim from those lists -- the same candidates the engine's template expansion
+    names in one round trip (vvcb_expand.inc), the same bitstream."""
+    w, h, bits, qp = 64, 64, 8, 27
+    write_input(tmp_path, w, h, bits)
+    run([os.path.join(REF, 'EncoderApp')] + encoder_args(w, h, bits, qp) + ['-b', 'plain.bin'], tmp_path)
+    reps = []
+    for k, extra in enumerate(({}, {'VVCB_SHIM_TWO_TRIPS': '1'})):
+        env = dict(os.environ, LD_LIBRARY_PATH=FAKE, VVCB_SHIM_REPORT=str(tmp_path / ('rep%d.json' % k)), **extra)
+        env.pop('VVCB_BROKER', None)
+        run([os.path.join(REF, 'EncoderAppServe')] + encoder_args(w, h, bits, qp) + ['-b', 'serve%d.bin' % k], tmp_path, env)
+        assert (tmp_path / 'plain.bin').read_bytes() == (tmp_path / ('serve%d.bin' % k)).read_bytes()
+        reps.append(json.loads((tmp_path / ('rep%d.json' % k)).read_text()))
+    assert reps[0]['jobs_prefetched'] == reps[1]['jobs_prefetched'] and reps[0]['demand_round_trips'] == reps[1]['demand_round_trips'] == 0
+    assert reps[1]['tu_round_trips'] >= reps[1]['visits'] > 10 * (reps[0]['tu_round_trips'] + 1)
 
 
 def test_prefetch_is_only_a_hint(built, tmp_path):

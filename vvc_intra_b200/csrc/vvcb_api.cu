@@ -1104,10 +1104,13 @@ extern "C" int vvcb_tu_eval_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visits, in
   return tu_eval_impl(ctx, jobs, n, nullptr, nullptr, n_samples, rates, states, n_rates, coeff, level, reco, results, visits, n_visits, src, pred_out);
 }
 
+#include "vvcb_expand.inc"
+
 // One round trip per CU of a host walk, for any number of independent CUs (several walkers behind the broker): the reconstruction
 // rectangles of all requests travel in one copy and one scatter launch, the rough mode decisions of all requests are one launch_rmd
-// batch, the TU candidates of all requests one tu_eval_impl batch (job offsets, visit indices and snapshot indices are re-based onto
-// the merged arrays); one stream synchronisation at the end.
+// batch, the TU candidates of all requests one tu_eval_impl batch (job offsets, visit and snapshot indices are re-based onto
+// the merged arrays).  Requests with templates (vvcb_cu_auto) are expanded on the host between the two stages, from the lists the
+// first stage has just produced.
 extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
 {
   if (!ctx) return VVCB_ERR_ARG;
@@ -1115,26 +1118,35 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
   if (n == 0) return VVCB_OK;
   if (ctx->remote) return vvcbc_cu_eval(ctx->remote, reqs, n, ctx->err, sizeof(ctx->err));
   if (!ctx->bOrig) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: no frame (vvcb_frame_begin / vvcb_frame_alloc)"); return VVCB_ERR_STATE; }
-  size_t nRects = 0, nRectSamples = 0, nJobs = 0, nSamples = 0;
-  int nRmd = 0, nTuReq = 0;
-  bool anyDetail = false;
+  size_t nRects = 0, nRectSamples = 0;
+  int nRmd = 0;
+  bool anyDetail = false, anyAuto = false;
   for (int i = 0; i < n; i++) {
     const vvcb_cu_request& q = reqs[i];
-    bool ok = q.n_rects >= 0 && q.n_jobs >= 0 && (!q.n_rects || (q.rects && q.rect_samples)) && (!(q.want_rmd || q.n_jobs) || q.visit) &&
+    bool ok = q.n_rects >= 0 && q.n_jobs >= 0 && q.n_autos >= 0 && (!q.n_rects || (q.rects && q.rect_samples)) && (!(q.want_rmd || q.n_jobs || q.n_autos) || q.visit) &&
               (!q.want_rmd || q.result) && (!q.n_jobs || (q.jobs && q.slots && q.tu_results));
     if (ok && q.n_rects && (!ctx->wReco || ctx->bReco != ctx->wReco)) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: rectangles need a writable frame"); return VVCB_ERR_STATE; }
     for (int k = 0; ok && k < q.n_rects; k++) ok = rect_ok(ctx, q.rects[k], q.n_rect_samples);
+    if (ok && (q.n_jobs || q.n_autos)) ok = q.visit->log2w >= 2 && q.visit->log2w <= 6 && q.visit->log2h >= 2 && q.visit->log2h <= 6;
     if (ok && q.n_jobs) {
-      ok = q.visit->log2w >= 2 && q.visit->log2w <= 6 && q.visit->log2h >= 2 && q.visit->log2h <= 6;
-      const size_t bs = ok ? (size_t)1 << (q.visit->log2w + q.visit->log2h) : 0;
+      const size_t bs = (size_t)1 << (q.visit->log2w + q.visit->log2h);
       for (int k = 0; ok && k < q.n_jobs; k++) {
         const vvcb_tu_job& j = q.jobs[k];
         ok = j.rate_idx == 0 && (size_t)j.offset + bs <= (size_t)q.n_jobs * bs &&
              (!(j.flags & (VVCB_TU_DEPQUANT | VVCB_TU_RDOQ_TS)) || q.rates) && (!(j.flags & VVCB_TU_RATE) || q.states);
       }
-      nJobs += (size_t)q.n_jobs; nSamples += (size_t)q.n_jobs * bs; nTuReq++;
     }
-    if (!ok) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: request %d is malformed (pointers, rectangle outside the picture, job offset / snapshot)", i); return VVCB_ERR_ARG; }
+    if (ok && q.n_autos) {
+      ok = q.want_rmd && q.autos && q.max_auto > 0 && q.n_auto && q.auto_slot && q.auto_tmpl && q.auto_results && q.n_autos <= 32;
+      for (int k = 0; ok && k < q.n_autos; k++) {
+        const vvcb_cu_auto& a = q.autos[k];
+        ok = a.job.x == q.visit->x && a.job.y == q.visit->y && a.job.log2w == q.visit->log2w && a.job.log2h == q.visit->log2h &&
+             (!(a.modes & VVCB_AUTO_REGULAR) || q.detail) &&
+             (!(a.job.flags & (VVCB_TU_DEPQUANT | VVCB_TU_RDOQ_TS)) || q.rates) && (!(a.job.flags & VVCB_TU_RATE) || q.states);
+      }
+      anyAuto = anyAuto || ok;
+    }
+    if (!ok) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: request %d is malformed (pointers, rectangle outside the picture, job offset / snapshot, templates)", i); return VVCB_ERR_ARG; }
     nRects += (size_t)q.n_rects; nRectSamples += q.n_rects ? q.n_rect_samples : 0;
     nRmd += q.want_rmd != 0; anyDetail = anyDetail || (q.want_rmd && q.detail);
   }
@@ -1174,55 +1186,80 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
     if ((rc = launch_rmd(ctx, ctx->dVisits, nRmd, ctx->dResults, anyDetail ? ctx->dDetails : nullptr, nullptr, hv))) return rc;
     CK(cudaMemcpyAsync(hRes, ctx->dResults, (size_t)nRmd * sizeof(vvcb_rmd_result), cudaMemcpyDeviceToHost, ctx->stream));
     if (anyDetail) CK(cudaMemcpyAsync(hDet, ctx->dDetails, (size_t)nRmd * sizeof(vvcb_rmd_detail), cudaMemcpyDeviceToHost, ctx->stream));
+    if (anyAuto) CK(ctx_sync(ctx));                    // the templates are expanded from these lists
   }
-  // ---- TU candidates ----
+  // ---- TU candidates: the explicit jobs of every request and the expanded templates, as groups of one visit each ----
+  struct Group { int req; bool autos; int n; const vvcb_tu_job* jobs; const uint8_t* slots; };
+  std::vector<Group> groups;
+  std::vector<std::vector<vvcb_tu_job>> autoJobs;
+  size_t nJobs = 0, nSamples = 0;
+  {
+    int vi = 0;
+    for (int i = 0; i < n; i++) {
+      vvcb_cu_request& q = reqs[i];
+      if (q.n_jobs) { groups.push_back(Group{ i, false, q.n_jobs, q.jobs, q.slots }); nJobs += (size_t)q.n_jobs; nSamples += (size_t)q.n_jobs << (q.visit->log2w + q.visit->log2h); }
+      if (q.n_autos) {
+        autoJobs.emplace_back((size_t)q.max_auto);
+        const int cnt = vvcb_expand_autos(*q.visit, hRes[vi], q.detail ? &hDet[vi] : nullptr, q.autos, q.n_autos, q.max_auto, autoJobs.back().data(), q.auto_slot, q.auto_tmpl);
+        *q.n_auto = cnt;
+        if (cnt) { groups.push_back(Group{ i, true, cnt, autoJobs.back().data(), q.auto_slot }); nJobs += (size_t)cnt; nSamples += (size_t)cnt << (q.visit->log2w + q.visit->log2h); }
+      }
+      vi += q.want_rmd != 0;
+    }
+  }
   int32_t* hLevel = nullptr; int16_t* hReco = nullptr; int16_t* hPred = nullptr;
   std::vector<vvcb_tu_result> tuRes;
   if (nJobs) {
     bool wantLevel = false, wantReco = false, wantPred = false;
-    for (int i = 0; i < n; i++) if (reqs[i].n_jobs) { wantLevel = wantLevel || reqs[i].level; wantReco = wantReco || reqs[i].reco; wantPred = wantPred || reqs[i].pred; }
+    for (const Group& g : groups) {
+      const vvcb_cu_request& q = reqs[g.req];
+      wantLevel = wantLevel || (g.autos ? q.auto_level : q.level); wantReco = wantReco || (g.autos ? q.auto_reco : q.reco); wantPred = wantPred || (g.autos ? q.auto_pred : q.pred);
+    }
     if (wantLevel) { if ((rc = pin_buf(ctx, 5, nSamples * sizeof(int32_t)))) return rc; hLevel = static_cast<int32_t*>(ctx->hPin[5]); }
     if (wantReco)  { if ((rc = pin_buf(ctx, 6, nSamples * sizeof(int16_t)))) return rc; hReco = static_cast<int16_t*>(ctx->hPin[6]); }
     if (wantPred)  { if ((rc = pin_buf(ctx, 7, nSamples * sizeof(int16_t)))) return rc; hPred = static_cast<int16_t*>(ctx->hPin[7]); }
-    std::vector<vvcb_rmd_visit> tv(nTuReq);
-    std::vector<vvcb_dq_rates> rates(nTuReq);
-    std::vector<vvcb_ctx_states> states(nTuReq);
+    const int nGroups = (int)groups.size();
+    if (nGroups > 65535) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: more than 65535 TU groups in one call"); return VVCB_ERR_ARG; }
+    std::vector<vvcb_rmd_visit> tv(nGroups);
+    std::vector<vvcb_dq_rates> rates(nGroups);
+    std::vector<vvcb_ctx_states> states(nGroups);
     std::vector<vvcb_tu_job> jobs(nJobs);
     std::vector<vvcb_tu_src> src(nJobs);
     tuRes.resize(nJobs);
-    size_t ji = 0, so = 0; int ti = 0;
-    for (int i = 0; i < n; i++) {
-      const vvcb_cu_request& q = reqs[i];
-      if (!q.n_jobs) continue;
-      tv[ti] = *q.visit;
-      if (q.rates) rates[ti] = *q.rates; else memset(&rates[ti], 0, sizeof(vvcb_dq_rates));
-      if (q.states) states[ti] = *q.states; else memset(&states[ti], 0, sizeof(vvcb_ctx_states));
-      for (int k = 0; k < q.n_jobs; k++, ji++) {
-        jobs[ji] = q.jobs[k]; jobs[ji].offset += (uint32_t)so; jobs[ji].rate_idx = (uint16_t)ti;
-        src[ji].visit = (uint32_t)ti; src[ji].slot = q.slots[k]; src[ji].pad[0] = src[ji].pad[1] = src[ji].pad[2] = 0;
+    size_t ji = 0, so = 0;
+    for (int gi = 0; gi < nGroups; gi++) {
+      const Group& g = groups[gi];
+      const vvcb_cu_request& q = reqs[g.req];
+      tv[gi] = *q.visit;
+      if (q.rates) rates[gi] = *q.rates; else memset(&rates[gi], 0, sizeof(vvcb_dq_rates));
+      if (q.states) states[gi] = *q.states; else memset(&states[gi], 0, sizeof(vvcb_ctx_states));
+      for (int k = 0; k < g.n; k++, ji++) {
+        jobs[ji] = g.jobs[k]; jobs[ji].offset += (uint32_t)so; jobs[ji].rate_idx = (uint16_t)gi;
+        src[ji].visit = (uint32_t)gi; src[ji].slot = g.slots[k]; src[ji].pad[0] = src[ji].pad[1] = src[ji].pad[2] = 0;
       }
-      so += (size_t)q.n_jobs << (q.visit->log2w + q.visit->log2h);
-      ti++;
+      so += (size_t)g.n << (q.visit->log2w + q.visit->log2h);
     }
-    if (nTuReq > 65535) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: more than 65535 requests with TU jobs in one call"); return VVCB_ERR_ARG; }
-    rc = tu_eval_impl(ctx, jobs.data(), (int)nJobs, nullptr, nullptr, nSamples, rates.data(), states.data(), nTuReq, nullptr, hLevel, hReco, tuRes.data(),
-                      tv.data(), nTuReq, src.data(), hPred);
+    rc = tu_eval_impl(ctx, jobs.data(), (int)nJobs, nullptr, nullptr, nSamples, rates.data(), states.data(), nGroups, nullptr, hLevel, hReco, tuRes.data(),
+                      tv.data(), nGroups, src.data(), hPred);
     if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
   } else CK(ctx_sync(ctx));
   // ---- hand the outputs back ----
   {
-    int vi = 0; size_t ji = 0, so = 0;
+    int vi = 0;
     for (int i = 0; i < n; i++) {
       vvcb_cu_request& q = reqs[i];
       if (q.want_rmd) { *q.result = hRes[vi]; if (q.detail) *q.detail = hDet[vi]; vi++; }
-      if (q.n_jobs) {
-        const size_t ns = (size_t)q.n_jobs << (q.visit->log2w + q.visit->log2h);
-        if (q.level) memcpy(q.level, hLevel + so, ns * sizeof(int32_t));
-        if (q.reco) memcpy(q.reco, hReco + so, ns * sizeof(int16_t));
-        if (q.pred) memcpy(q.pred, hPred + so, ns * sizeof(int16_t));
-        memcpy(q.tu_results, &tuRes[ji], (size_t)q.n_jobs * sizeof(vvcb_tu_result));
-        so += ns; ji += (size_t)q.n_jobs;
-      }
+    }
+    size_t ji = 0, so = 0;
+    for (const Group& g : groups) {
+      vvcb_cu_request& q = reqs[g.req];
+      const size_t ns = (size_t)g.n << (q.visit->log2w + q.visit->log2h);
+      int32_t* lv = g.autos ? q.auto_level : q.level; int16_t* rc16 = g.autos ? q.auto_reco : q.reco; int16_t* pr = g.autos ? q.auto_pred : q.pred;
+      if (lv) memcpy(lv, hLevel + so, ns * sizeof(int32_t));
+      if (rc16) memcpy(rc16, hReco + so, ns * sizeof(int16_t));
+      if (pr) memcpy(pr, hPred + so, ns * sizeof(int16_t));
+      memcpy(g.autos ? q.auto_results : q.tu_results, &tuRes[ji], (size_t)g.n * sizeof(vvcb_tu_result));
+      so += ns; ji += (size_t)g.n;
     }
   }
   return VVCB_OK;
