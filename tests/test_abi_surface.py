@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported(built):
 
 
 def test_struct_sizes_match_header(built):
-    src = '#include <stdio.h>\n#include "include/vvc_intra_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(vvcb_rmd_visit), sizeof(vvcb_rmd_result), sizeof(vvcb_rates));return 0;}'
+    src = '#include <stdio.h>\n#include "include/vvc_intra_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vvcb_rmd_visit), sizeof(vvcb_rmd_result), sizeof(vvcb_rates), sizeof(vvcb_cu_request), sizeof(vvcb_cu_auto), sizeof(vvcb_rmd_brief), sizeof(vvcb_rect));return 0;}'
     exe = os.path.join(ROOT, 'tests/host_emul/_sizes')
     subprocess.run(['gcc', '-x', 'c', '-', '-I', ROOT, '-o', exe], input=src.encode(), cwd=ROOT, check=True)
     out = subprocess.check_output([exe]).split()
@@ -37,6 +37,10 @@ def test_struct_sizes_match_header(built):
     assert int(out[0]) == built.VISIT_DTYPE.itemsize == 80
     assert int(out[1]) == built.RESULT_DTYPE.itemsize == 368
     assert int(out[2]) == 44
+    import ctypes
+    from vvc_intra_b200 import engine as E
+    assert int(out[3]) == ctypes.sizeof(E.CuRequest) and int(out[4]) == E.CU_AUTO_DTYPE.itemsize == 40
+    assert int(out[5]) == E.BRIEF_DTYPE.itemsize == 64 and int(out[6]) == E.RECT_DTYPE.itemsize == 12
 
 
 def test_no_cpu_fallback_without_device(built):

@@ -932,3 +932,54 @@ def test_training_set_dump_through_the_feature_kernel(eng10, tmp_path):
     data = np.fromfile(tmp_path / 'Data_Partition.dat', '<i4').reshape(-1, 26)
     assert np.array_equal(data, O.features_batch(Y, jobs)['f'][:, :26])
     assert np.array_equal(np.fromfile(tmp_path / 'Label_Partition.dat', '<i4'), labels)
+
+
+def test_cu_eval_templates_expand_over_the_lists(eng10):
+    """vvcb_cu_auto: templates combined by the engine with the modes of the lists the same call produced (final list; regular-only list for the
+    templates that ask for it; MIP modes dropped where told), in list order; every expanded candidate equals the same candidate submitted explicitly."""
+    rng = np.random.default_rng(151)
+    orig, reco, visits = G.random_case(rng, 10, 2, plane=(256, 512))
+    eng10.frame_begin(orig)
+    eng10.reco_update(reco)
+    rates, states = vb.default_dq_rates(), vb.default_ctx_states()
+    reqs = []
+    for v in visits[:24]:
+        au = np.zeros(3, vb.CU_AUTO_DTYPE)
+        for k, (mts, lf, modes, skip) in enumerate(((0, 0, vb.AUTO_FINAL, 0), (2 if max(int(v['log2w']), int(v['log2h'])) <= 5 else 0, 0, vb.AUTO_FINAL | vb.AUTO_REGULAR, 0), (0, 1, vb.AUTO_REGULAR, 1))):
+            j = au[k]['job']
+            j['x'], j['y'], j['log2w'], j['log2h'], j['mts_idx'], j['lfnst_idx'] = v['x'], v['y'], v['log2w'], v['log2h'], mts, lf
+            j['flags'] = vb.TU_QUANT | vb.TU_DEPQUANT | vb.TU_RATE
+            j['qp_per'], j['qp_rem'], j['lambda'], j['cbf_delta_bits'] = 6, 3, 45.0, -1200
+            au[k]['modes'], au[k]['skip_mip'] = modes, skip
+        reqs.append(dict(visit=np.array([v]), want_rmd=True, autos=au, max_auto=64, rates=rates, states=states))
+    outs = eng10.cu_eval(reqs)
+    total = 0
+    for q, o in zip(reqs, outs):
+        v, res, det, au = q['visit'][0], o['result'][0], o['detail'][0], q['autos']
+        n = int(o['n_auto'][0])
+        final = [(int(m['mip']), int(m['mrl']), int(m['mode'])) for m in res['final_mode'][:res['n_final']]]
+        reg = [(int(m['mip']), int(m['mrl']), int(m['mode'])) for m in det['reg_mode'][:det['n_reg']]]
+        exp = []
+        for (mip, mrl, mode), in_final in [(m, True) for m in final] + [(m, False) for m in reg if m not in final]:
+            slot = vb.SLOT_MIP + mode if mip else mode if mrl == 0 else (vb.SLOT_MRL1 if mrl == 1 else vb.SLOT_MRL3) + list(v['mpm'][1:]).index(mode)
+            for t in range(3):
+                if (int(au[t]['modes']) & (vb.AUTO_FINAL if in_final else vb.AUTO_REGULAR)) and not (mip and au[t]['skip_mip']):
+                    exp.append((slot, t))
+        assert [(int(a), int(b)) for a, b in zip(o['auto_slot'][:n], o['auto_tmpl'][:n])] == exp[:64]
+        # the same candidates submitted explicitly
+        bs = 1 << (int(v['log2w']) + int(v['log2h']))
+        jobs = np.zeros(n, vb.TU_JOB_DTYPE)
+        for k in range(n):
+            jobs[k] = au[int(o['auto_tmpl'][k])]['job']
+            slot = int(o['auto_slot'][k])
+            mode = 0 if slot >= vb.SLOT_MIP else slot if slot < vb.SLOT_MRL1 else int(v['mpm'][1 + (slot - vb.SLOT_MRL1) % 5])
+            jobs[k]['offset'], jobs[k]['intra_mode'] = k * bs, mode if jobs[k]['lfnst_idx'] else 0
+        o2 = eng10.cu_eval([dict(visit=q['visit'], jobs=jobs, slots=o['auto_slot'][:n].copy(), rates=rates, states=states)])[0]
+        assert np.array_equal(o2['level'], o['auto_level'][:n * bs]) and np.array_equal(o2['reco'], o['auto_reco'][:n * bs]) and np.array_equal(o2['pred'], o['auto_pred'][:n * bs])
+        assert o2['tu_results'].tobytes() == o['auto_results'][:n].tobytes()
+        total += n
+    assert total > 200
+    bad = dict(reqs[0])
+    bad['want_rmd'] = False
+    with pytest.raises(vb.EngineError, match='malformed'):
+        eng10.cu_eval([bad])

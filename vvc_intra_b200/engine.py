@@ -68,7 +68,14 @@ class CuRequest(C.Structure):
     _fields_ = [('rects', C.c_void_p), ('n_rects', C.c_int), ('rect_samples', C.c_void_p), ('n_rect_samples', C.c_size_t),
                 ('visit', C.c_void_p), ('want_rmd', C.c_int), ('jobs', C.c_void_p), ('slots', C.c_void_p), ('n_jobs', C.c_int),
                 ('rates', C.c_void_p), ('states', C.c_void_p), ('result', C.c_void_p), ('detail', C.c_void_p),
-                ('level', C.c_void_p), ('reco', C.c_void_p), ('pred', C.c_void_p), ('tu_results', C.c_void_p)]
+                ('level', C.c_void_p), ('reco', C.c_void_p), ('pred', C.c_void_p), ('tu_results', C.c_void_p),
+                ('autos', C.c_void_p), ('n_autos', C.c_int), ('max_auto', C.c_int), ('n_auto', C.c_void_p), ('auto_slot', C.c_void_p), ('auto_tmpl', C.c_void_p),
+                ('auto_level', C.c_void_p), ('auto_reco', C.c_void_p), ('auto_pred', C.c_void_p), ('auto_results', C.c_void_p)]
+
+
+CU_AUTO_DTYPE = np.dtype([('job', TU_JOB_DTYPE), ('modes', 'u1'), ('skip_mip', 'u1'), ('pad', 'u1', 6)])
+assert CU_AUTO_DTYPE.itemsize == 40
+AUTO_FINAL, AUTO_REGULAR = 1, 2
 
 
 class EngineError(RuntimeError):
@@ -212,8 +219,9 @@ class IntraCostEngine:
 
     def cu_eval(self, requests):
         """vvcb_cu_eval.  requests: list of dicts with optional keys rects (RECT_DTYPE) + rect_samples, visit (VISIT_DTYPE, 1 entry),
-        want_rmd, jobs (TU_JOB_DTYPE) + slots (uint8) [+ rates (DQ_RATES_DTYPE, 1), states (CTX_STATES_DTYPE, 1)].  Returns a list of
-        dicts: result / detail (want_rmd), level / reco / pred / tu_results (jobs)."""
+        want_rmd, jobs (TU_JOB_DTYPE) + slots (uint8) [+ rates (DQ_RATES_DTYPE, 1), states (CTX_STATES_DTYPE, 1)], autos (CU_AUTO_DTYPE templates,
+        with want_rmd) + max_auto.  Returns a list of dicts: result / detail (want_rmd), level / reco / pred / tu_results (jobs), n_auto / auto_slot /
+        auto_tmpl / auto_level / auto_reco / auto_pred / auto_results (templates)."""
         arr = (CuRequest * len(requests))()
         keep, outs = [], []
         for r, q in zip(arr, requests):
@@ -244,6 +252,21 @@ class IntraCostEngine:
                 o['level'], o['reco'], o['pred'] = np.zeros(len(jb) * bs, np.int32), np.zeros(len(jb) * bs, np.int16), np.zeros(len(jb) * bs, np.int16)
                 o['tu_results'] = np.zeros(len(jb), TU_RESULT_DTYPE)
                 r.level, r.reco, r.pred, r.tu_results = o['level'].ctypes.data, o['reco'].ctypes.data, o['pred'].ctypes.data, o['tu_results'].ctypes.data
+            if q.get('autos') is not None and len(q['autos']):
+                au = np.ascontiguousarray(q['autos'], CU_AUTO_DTYPE)
+                mx = int(q.get('max_auto', 96))
+                keep.append(au)
+                for key, dt in (('rates', DQ_RATES_DTYPE), ('states', CTX_STATES_DTYPE)):
+                    if q.get(key) is not None and not getattr(r, key):
+                        a = np.ascontiguousarray(q[key], dt).reshape(1)
+                        keep.append(a)
+                        setattr(r, key, a.ctypes.data)
+                o['n_auto'], o['auto_slot'], o['auto_tmpl'] = np.zeros(1, np.int32), np.zeros(mx, np.uint8), np.zeros(mx, np.uint8)
+                o['auto_level'], o['auto_reco'], o['auto_pred'] = np.zeros(mx * bs, np.int32), np.zeros(mx * bs, np.int16), np.zeros(mx * bs, np.int16)
+                o['auto_results'] = np.zeros(mx, TU_RESULT_DTYPE)
+                r.autos, r.n_autos, r.max_auto, r.n_auto = au.ctypes.data, len(au), mx, o['n_auto'].ctypes.data
+                r.auto_slot, r.auto_tmpl, r.auto_level, r.auto_reco = o['auto_slot'].ctypes.data, o['auto_tmpl'].ctypes.data, o['auto_level'].ctypes.data, o['auto_reco'].ctypes.data
+                r.auto_pred, r.auto_results = o['auto_pred'].ctypes.data, o['auto_results'].ctypes.data
             outs.append(o)
         self._ck(self._lib.vvcb_cu_eval(self._ctx, C.byref(arr), len(requests)))
         return outs
