@@ -562,6 +562,9 @@ def bitexact_leg(frames, device):
             'bitstreams_identical': same, 'bitstreams_compared': n_plain, 'seconds': {'served': served_s, 'plain': plain_s},
             'engine_busy_frac': stats['busy_ns'] / stats['wall_ns'] / workers if stats['wall_ns'] else None,
             'broker': {k: stats[k] for k in ('cycles', 'requests', 'visits', 'tu_jobs', 'max_batch', 'kernel_launches')},
+            # host wall time of the workers inside vvcb_cu_eval per batch, microseconds: pack + launch the rough mode decision, wait for its
+            # lists, expand the templates, launch the TU stage, wait for it, hand the outputs back
+            'batch_phase_us': [round(x / 1e3 / max(1, stats['cycles']), 1) for x in stats.get('phase_ns', [])],
             'mean_round_trips_merged_per_batch': stats['requests'] / max(1, stats['cycles']),
             'walker_wait_for_engine_s_mean': tot('engine_wait_s') / n,
             'served_calls': {k: tot(k) for k in ('visits', 'predictions_skipped', 'distortions_served', 'tu_quantised', 'tu_sse', 'tu_residual_bits', 'jobs_prefetched', 'demand_round_trips')},

@@ -402,6 +402,11 @@ int vvcb_tu_kernel_times(vvcb_ctx* ctx, float ms[4], int* calls);
 int vvcb_measure_int_peak(vvcb_ctx* ctx, double* gops_imad, double* gops_alu, double* gops_mixed);
 /* kernel launches issued by this context since creation (bench.py reports the delta).           */
 uint64_t vvcb_launch_count(const vvcb_ctx* ctx);
+/* Where the host time of vvcb_cu_eval goes, cumulative wall-clock nanoseconds since the context was created: ns[0] packing the
+ * rectangles and launching the rough mode decision, ns[1] waiting for its lists (calls with candidate templates only), ns[2] expanding
+ * the templates and assembling the TU batch, ns[3] launching the TU stage, ns[4] waiting for its results, ns[5] handing the outputs
+ * back.  A measuring aid for the latency-bound use (profiles/).                                                                  */
+int vvcb_cu_eval_phases(const vvcb_ctx* ctx, uint64_t ns[6], uint64_t* calls);
 
 #ifdef __cplusplus
 }

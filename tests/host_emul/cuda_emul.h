@@ -51,6 +51,26 @@ static inline int __shfl_xor_sync(unsigned, int v, int mask)
   pthread_barrier_wait(&w.bar);
   return r;
 }
+static inline unsigned __ballot_sync(unsigned, bool pred)
+{
+  EmuWarp& w = emu_warp();
+  w.xbuf[threadIdx.x & 31] = pred;
+  pthread_barrier_wait(&w.bar);
+  unsigned r = 0;
+  for (int i = 0; i < 32; i++) r |= (unsigned)(w.xbuf[i] != 0) << i;
+  pthread_barrier_wait(&w.bar);
+  return r;
+}
+static inline int __reduce_max_sync(unsigned, int v)
+{
+  EmuWarp& w = emu_warp();
+  w.xbuf[threadIdx.x & 31] = v;
+  pthread_barrier_wait(&w.bar);
+  int r = w.xbuf[0];
+  for (int i = 1; i < 32; i++) r = w.xbuf[i] > r ? w.xbuf[i] : r;
+  pthread_barrier_wait(&w.bar);
+  return r;
+}
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicMax(int* p, int v)

@@ -131,19 +131,23 @@ extern "C" int emul_tu_eval(const int16_t* orig, int stride, int bd, const vvcb_
     emu_launch(2, kDqThreads, [&] { dq_first_kernel(jobs, order.data(), nDq, dqCoeff.data(), &dqRom, bd, firstRaw.data()); });
     std::vector<int> binCount(kDqBins, 0);
     const int sortGrid = (nDq + kDqSortPerBlock - 1) / kDqSortPerBlock;
-    emu_launch(sortGrid, kDqSortThreads, [&] { dq_hist_kernel(firstRaw.data(), nDq, binCount.data()); });
-    emu_launch(1, 32, [&] { dq_scan_kernel(binCount.data()); });
-    emu_launch(sortGrid, kDqSortThreads, [&] { dq_scatter_kernel(order.data(), firstRaw.data(), nDq, binCount.data(), orderSorted.data(), firstSorted.data()); });
+    const bool sortJobs = nDq > 48;            // the product's rule (vvcb_api.cu: more than 2048 jobs) at the scale of the test sets: both paths run
+    if (sortJobs) {
+      emu_launch(sortGrid, kDqSortThreads, [&] { dq_hist_kernel(firstRaw.data(), nDq, binCount.data()); });
+      emu_launch(1, 32, [&] { dq_scan_kernel(binCount.data()); });
+      emu_launch(sortGrid, kDqSortThreads, [&] { dq_scatter_kernel(order.data(), firstRaw.data(), nDq, binCount.data(), orderSorted.data(), firstSorted.data()); });
+    }
     DqParams D;
-    D.jobs = jobs; D.order = orderSorted.data(); D.firstPos = firstSorted.data(); D.n = nDq; D.coeff = dqCoeff.data(); D.level = level; D.deq = dqDeq.data(); D.results = results;
-    D.rates = rates; D.tabs = tabs.data(); D.rom = &dqRom; D.scratch = scratch.data(); D.bd = bd;
+    D.jobs = jobs; D.order = sortJobs ? orderSorted.data() : order.data(); D.firstPos = sortJobs ? firstSorted.data() : firstRaw.data(); D.n = nDq;
+    D.coeff = dqCoeff.data(); D.level = level; D.deq = dqDeq.data(); D.results = results;
+    D.rates = rates; D.tabs = tabs.data(); D.rom = &dqRom; D.scratch = scratch.data(); D.bd = bd; D.sparse = !sortJobs;
     emu_launch(grid, kDqThreads, [&] { dq_kernel(D); });
   }
   if (!tsOrder.empty()) {
     RdoqParams R;
     R.jobs = jobs; R.order = tsOrder.data(); R.n = (int)tsOrder.size(); R.coeff = dqCoeff.data(); R.level = level; R.deq = dqDeq.data();
     R.results = results; R.rates = rates; R.rom = &dqRom; R.bd = bd;
-    emu_launch(1, 128, [&] { rdoq_ts_kernel(R); });
+    emu_launch(2, kTsThreads, [&] { rdoq_ts_kernel(R); });
   }
   if (nDq || !tsOrder.empty()) {
     P.phase = 1;

@@ -12,6 +12,7 @@
 #include "vvcb_dq.cuh"
 #include "vvcb_rate.cuh"
 #include <vector>
+#include <time.h>
 #include <thread>
 #include <atomic>
 #include "vvcb_romfill.h"
@@ -85,6 +86,7 @@ struct vvcb_ctx {
   void* hPin[8]; size_t capPin[8];  // page-locked staging of vvcb_cu_eval / vvcb_reco_update_rects
   void* dRect[2]; size_t capRect[2];
   uint64_t launches;
+  uint64_t cuNs[6], cuCalls, tuWaitFrom;    // vvcb_cu_eval_phases
   int timing; int timedLaunches; float kms[3]; cudaEvent_t kev[4];
   char err[512];
 };
@@ -101,6 +103,8 @@ static char g_createErr[512] = "";
   } while (0)
 
 // wait for the context's stream: polling (default) or, with VVCB_OPT_YIELD_SYNC, sleeping on a blocking event
+static inline uint64_t host_ns() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec; }
+
 static cudaError_t ctx_sync(vvcb_ctx* ctx)
 {
   if (!ctx->yieldSync) return cudaStreamSynchronize(ctx->stream);
@@ -943,7 +947,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     if (nTs && (rc = tu_buf(ctx, 16, (size_t)nTs * sizeof(int)))) return rc;
   }
   if (nDq) {
-    dqGrid = (nDq + kDqGroups - 1) / kDqGroups;
+    dqGrid = nDq <= 2048 ? (nDq + kDqThreads / 32 - 1) / (kDqThreads / 32) : (nDq + kDqGroups - 1) / kDqGroups;   // walk-sized batch: one TU per warp
     if (dqGrid > ctx->numSms * 4) dqGrid = ctx->numSms * 4;
     if ((rc = tu_buf(ctx, 9, (size_t)nDq * sizeof(int)))) return rc;
     if ((rc = tu_buf(ctx, 11, (size_t)n_rates * sizeof(DqRateTab)))) return rc;
@@ -1043,7 +1047,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     D.jobs = P.jobs; D.order = sortJobs ? orderSorted : static_cast<const int*>(ctx->dTu[9]); D.firstPos = sortJobs ? firstSorted : firstRaw; D.n = nDq;
     D.coeff = P.dqCoeff; D.level = P.level; D.deq = static_cast<int32_t*>(ctx->dTu[8]); D.results = P.results;
     D.rates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]); D.tabs = static_cast<const DqRateTab*>(ctx->dTu[11]);
-    D.rom = ctx->dDqRom; D.scratch = static_cast<uint8_t*>(ctx->dTu[12]); D.bd = ctx->bd;
+    D.rom = ctx->dDqRom; D.scratch = static_cast<uint8_t*>(ctx->dTu[12]); D.bd = ctx->bd; D.sparse = !sortJobs;
     dq_kernel<<<dqGrid, kDqThreads, 0, ctx->stream>>>(D);
     ctx->launches += 3;
   }
@@ -1052,7 +1056,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     R.jobs = P.jobs; R.order = static_cast<const int*>(ctx->dTu[16]); R.n = nTs; R.coeff = P.dqCoeff; R.level = P.level;
     R.deq = static_cast<int32_t*>(ctx->dTu[8]); R.results = P.results; R.rates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]);
     R.rom = ctx->dDqRom; R.bd = ctx->bd;
-    rdoq_ts_kernel<<<(nTs + 127) / 128, 128, 0, tsAside ? ctx->sKind[0] : ctx->stream>>>(R);
+    rdoq_ts_kernel<<<std::min((nTs + kTsWarps - 1) / kTsWarps, 16 * ctx->numSms), kTsThreads, 0, tsAside ? ctx->sKind[0] : ctx->stream>>>(R);
     ctx->launches++;
     if (tsAside) {
       CK(cudaEventRecord(ctx->evKind[0], ctx->sKind[0]));
@@ -1071,7 +1075,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     RateParams R;
     R.jobs = P.jobs; R.order = static_cast<const int*>(ctx->dTu[17]); R.n = nRate; R.level = P.level; R.results = P.results;
     R.states = static_cast<const vvcb_ctx_states*>(ctx->dTu[18]); R.rom = ctx->dDqRom; R.rate = ctx->dRateRom; R.depQuant = ctx->depQuant;
-    rate_kernel<<<(nRate + kRateThreads - 1) / kRateThreads, kRateThreads, 0, ctx->stream>>>(R);
+    rate_kernel<<<std::min((nRate + kRateWarps - 1) / kRateWarps, 16 * ctx->numSms), kRateThreads, 0, ctx->stream>>>(R);
     ctx->launches++;
   }
   if (tm) CK(cudaEventRecord(ctx->tev[4], ctx->stream));
@@ -1081,6 +1085,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
   if (reco) CK(cudaMemcpyAsync(reco, ctx->dTu[5], n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (pred_out) CK(cudaMemcpyAsync(pred_out, ctx->dTu[2], n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(results, ctx->dTu[6], (size_t)n * sizeof(vvcb_tu_result), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->tuWaitFrom = host_ns();
   CK(ctx_sync(ctx));
   if (tm) {
     for (int i = 0; i < 4; i++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->tev[i], ctx->tev[i + 1])); ctx->tuMs[i] += ms; }
@@ -1152,6 +1157,8 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
   }
   CK(cudaSetDevice(ctx->device));
   int rc;
+  uint64_t tPhase = host_ns();
+  auto phase = [&](int k) { const uint64_t now = host_ns(); ctx->cuNs[k] += now - tPhase; tPhase = now; };
   // ---- reconstruction rectangles ----
   if (nRects) {
     if ((rc = pin_buf(ctx, 0, nRects * sizeof(vvcb_rect)))) return rc;
@@ -1186,7 +1193,8 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
     if ((rc = launch_rmd(ctx, ctx->dVisits, nRmd, ctx->dResults, anyDetail ? ctx->dDetails : nullptr, nullptr, hv))) return rc;
     CK(cudaMemcpyAsync(hRes, ctx->dResults, (size_t)nRmd * sizeof(vvcb_rmd_result), cudaMemcpyDeviceToHost, ctx->stream));
     if (anyDetail) CK(cudaMemcpyAsync(hDet, ctx->dDetails, (size_t)nRmd * sizeof(vvcb_rmd_detail), cudaMemcpyDeviceToHost, ctx->stream));
-    if (anyAuto) CK(ctx_sync(ctx));                    // the templates are expanded from these lists
+    phase(0);
+    if (anyAuto) { CK(ctx_sync(ctx)); phase(1); }      // the templates are expanded from these lists
   }
   // ---- TU candidates: the explicit jobs of every request and the expanded templates, as groups of one visit each ----
   struct Group { int req; bool autos; int n; const vvcb_tu_job* jobs; const uint8_t* slots; };
@@ -1239,10 +1247,12 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
       }
       so += (size_t)g.n << (q.visit->log2w + q.visit->log2h);
     }
+    phase(2);
     rc = tu_eval_impl(ctx, jobs.data(), (int)nJobs, nullptr, nullptr, nSamples, rates.data(), states.data(), nGroups, nullptr, hLevel, hReco, tuRes.data(),
                       tv.data(), nGroups, src.data(), hPred);
     if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
-  } else CK(ctx_sync(ctx));
+    { const uint64_t now = host_ns(); ctx->cuNs[3] += ctx->tuWaitFrom - tPhase; ctx->cuNs[4] += now - ctx->tuWaitFrom; tPhase = now; }
+  } else { phase(2); CK(ctx_sync(ctx)); phase(4); }
   // ---- hand the outputs back ----
   {
     int vi = 0;
@@ -1262,6 +1272,16 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
       so += ns; ji += (size_t)g.n;
     }
   }
+  phase(5);
+  ctx->cuCalls++;
+  return VVCB_OK;
+}
+
+extern "C" int vvcb_cu_eval_phases(const vvcb_ctx* ctx, uint64_t ns[6], uint64_t* calls)
+{
+  if (!ctx || !ns) return VVCB_ERR_ARG;
+  for (int i = 0; i < 6; i++) ns[i] = ctx->cuNs[i];
+  if (calls) *calls = ctx->cuCalls;
   return VVCB_OK;
 }
 
@@ -1300,7 +1320,7 @@ extern "C" int vvcb_residual_bits(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n,
   R.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); R.order = static_cast<const int*>(ctx->dTu[17]); R.n = n;
   R.level = static_cast<const int32_t*>(ctx->dTu[4]); R.results = static_cast<vvcb_tu_result*>(ctx->dTu[6]);
   R.states = static_cast<const vvcb_ctx_states*>(ctx->dTu[18]); R.rom = ctx->dDqRom; R.rate = ctx->dRateRom; R.depQuant = ctx->depQuant;
-  rate_kernel<<<(n + kRateThreads - 1) / kRateThreads, kRateThreads, 0, ctx->stream>>>(R);
+  rate_kernel<<<std::min((n + kRateWarps - 1) / kRateWarps, 16 * ctx->numSms), kRateThreads, 0, ctx->stream>>>(R);
   ctx->launches++;
   CK(cudaGetLastError());
   std::vector<vvcb_tu_result> res(n);

@@ -85,6 +85,7 @@ struct DqParams {
   const DqRom* rom;
   uint8_t* scratch;          // kDqSlotBytes per group of the grid
   int bd;
+  int sparse;                // 1: one TU per warp (group 0 works, the other seven idle) -- the latency-bound batches of a host walk
 };
 
 __global__ void dq_rate_kernel(const vvcb_dq_rates* rates, int n, DqRateTab* tabs)
@@ -259,11 +260,12 @@ __global__ void __launch_bounds__(kDqThreads, VVCB_DQ_MIN_CTAS) dq_kernel(DqPara
   uint8_t* ctxMem = P.scratch + (size_t)slot * kDqSlotBytes;
   uint4* trellis = reinterpret_cast<uint4*>(ctxMem + kDqCtxBytes);
   const int groupsTotal = gridDim.x * kDqGroups;
-  const int rounds = (P.n + groupsTotal - 1) / groupsTotal;
+  const int perRound = P.sparse ? groupsTotal >> 3 : groupsTotal;
+  const int rounds = (P.n + perRound - 1) / perRound;
 
   for (int round = 0; round < rounds; round++) {
     // round-robin over the size-sorted job list: the 8 groups of a warp get neighbours in the sorted order
-    const int ji = round * groupsTotal + slot;
+    const int ji = P.sparse ? ((lane >> 2) == 0 ? round * (groupsTotal >> 3) + (slot >> 3) : P.n) : round * groupsTotal + slot;
     const bool have = ji < P.n;
     vvcb_tu_job job;
     if (have) job = P.jobs[P.order[ji]];
@@ -283,8 +285,13 @@ __global__ void __launch_bounds__(kDqThreads, VVCB_DQ_MIN_CTAS) dq_kernel(DqPara
     const int ctxStride = sbbPad + shp.numCoeff;                   // eight context sets stay 16-byte aligned (copied as uint4)
 
     const int firstTestPos = have ? P.firstPos[ji] : -1;           // dq_first_kernel, :1638-1662
-    int steps = firstTestPos + 1;
-    for (int o = 4; o < 32; o <<= 1) steps = vmax(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+    // The groups of a warp walk in lock-step from a COMMON start position, the warp's largest first test position rounded up to the end of
+    // its sub-block; a group is idle until the walk reaches its own first test position.  All groups then cross their sub-block boundaries
+    // -- the expensive step, State::updateStateEOS -- in the same iteration instead of one after the other.
+    int top = firstTestPos;
+    for (int o = 4; o < 32; o <<= 1) top = vmax(top, __shfl_xor_sync(0xffffffffu, top, o));
+    const int startPos = top | 15, steps = top < 0 ? 0 : startPos + 1;
+    const int lastFetch = vmax(firstTestPos, 0);
 
     // ---- init (:1665-1688)
     __syncwarp();
@@ -316,13 +323,13 @@ __global__ void __launch_bounds__(kDqThreads, VVCB_DQ_MIN_CTAS) dq_kernel(DqPara
     int currSet = 0, prevSet = 4;              // CommonCtx::m_currSbbCtx / m_prevSbbCtx
     const int32_t* sigTab = &tab.sig[vmax(k - 1, 0)][0][0];
 
-    DqScanPos sp = scan[vmax(firstTestPos, 0)];                    // this iteration's position; the next one is fetched a step ahead
+    DqScanPos sp = scan[lastFetch];                                // this iteration's position; the next one is fetched a step ahead
     int coeffCur = coeff[sp.idx];
     for (int it = 0; it < steps; it++) {
-      const int scanIdx = firstTestPos - it;
-      const DqScanPos nx = scan[vmax(scanIdx - 1, 0)];
+      const int scanIdx = startPos - it;
+      const DqScanPos nx = scan[vmin(vmax(scanIdx - 1, 0), lastFetch)];
       const int coeffNext = coeff[nx.idx];
-      const bool act = scanIdx >= 0;
+      const bool act = scanIdx <= firstTestPos;                    // scanIdx >= 0 inside the loop
       { const int t = prev; prev = curr; curr = t; }               // std::swap(m_prevStates, m_currStates)
       long long dCost = kDqHuge >> 2;
       int dLevel = -1, dPrev = -2;
@@ -586,9 +593,8 @@ __global__ void __launch_bounds__(kDqThreads, VVCB_DQ_MIN_CTAS) dq_kernel(DqPara
 // RDOQ of transform-skip blocks: QuantRDOQ::xRateDistOptQuantTS (CL/QuantRDOQ.cpp:1243-1485) with xGetCodedLevelTSPred
 // (:2000-2065), xGetICRateTS (:2067-2150), xGetErrScaleCoeff (:383-393) and the transform-skip contexts of
 // CoeffCodingContext (CL/ContextModelling.h:197-365).  The decision of a coefficient depends on the decided levels of its
-// left and upper neighbours and on the sub-block flags before it, so a block is one serial chain: one thread per block,
-// the host sorts the jobs by size so that the lanes of a warp run chains of equal length.  Costs are IEEE doubles combined
-// in the reference's order (no contraction).
+// left and upper neighbours and on the sub-block flags before it, so a block is one serial chain: one warp per block (32
+// lanes stage, one walks).  Costs are IEEE doubles combined in the reference's order (no contraction).
 // =====================================================================================================
 struct RdoqParams {
   const vvcb_tu_job* jobs;
@@ -603,16 +609,21 @@ struct RdoqParams {
   int bd;
 };
 
-__device__ __forceinline__ int rdoq_ic_rate_ts(int absLevel, const vvcb_dq_rates& r, const uint32_t* sign, const uint32_t* gt1, int sgn, int ricePar)
+// the transform-skip prices of one vvcb_dq_rates snapshot, as the kernel stages them in shared memory
+struct TsRates { uint32_t sig_sbb[3][2], sig[3][2], par[1][2], gtx[5][2], lrg1[4][2], sign[6][2]; };
+static_assert(sizeof(vvcb_dq_rates) - offsetof(vvcb_dq_rates, ts_sig_sbb) >= sizeof(TsRates) &&
+              offsetof(vvcb_dq_rates, ts_sign) - offsetof(vvcb_dq_rates, ts_sig_sbb) == offsetof(TsRates, sign), "TsRates mirrors the tail of vvcb_dq_rates");
+
+__device__ __forceinline__ int rdoq_ic_rate_ts(int absLevel, const TsRates& r, const uint32_t* sign, const uint32_t* gt1, int sgn, int ricePar)
 {
   int rate = (int)sign[sgn];
   if (absLevel > 1) {
     rate += (int)gt1[1];
-    rate += (int)r.ts_par[0][(absLevel - 2) & 1];
+    rate += (int)r.par[0][(absLevel - 2) & 1];
     int cutoff = 2;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      if (absLevel >= cutoff) rate += (int)r.ts_gtx[cutoff >> 1][absLevel >= cutoff + 2];
+      if (absLevel >= cutoff) rate += (int)r.gtx[cutoff >> 1][absLevel >= cutoff + 2];
       cutoff += 2;
     }
     if (absLevel >= cutoff) {
@@ -632,13 +643,22 @@ __device__ __forceinline__ int rdoq_ic_rate_ts(int absLevel, const vvcb_dq_rates
   return rate;
 }
 
-__global__ void __launch_bounds__(128) rdoq_ts_kernel(RdoqParams P)
+constexpr int kTsWarps = 4;                          // blocks per CTA
+constexpr int kTsThreads = 32 * kTsWarps;
+
+// One warp per block: the 32 lanes stage the scan, the scaled magnitudes and the prices in shared memory, lane 0 walks the chain there
+// (the decided levels of the left / upper neighbours are read back from a shared-memory raster), global memory sees only the results.
+__global__ void __launch_bounds__(kTsThreads) rdoq_ts_kernel(RdoqParams P)
 {
+  __shared__ TsRates sRates[kTsWarps];
+  __shared__ uint32_t sScan[kTsWarps][1024];         // raster index | x << 16 | y << 24, by scan position
+  __shared__ uint32_t sMag[kTsWarps][1024];          // levelDouble | (coefficient < 0) << 31, by scan position
+  __shared__ int16_t sLevel[kTsWarps][1024];         // decided levels, raster
   const DqRom& rom = *P.rom;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < P.n; t += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int t = blockIdx.x * kTsWarps + wib; t < P.n; t += gridDim.x * kTsWarps) {
     const int ji = P.order[t];
     const vvcb_tu_job job = P.jobs[ji];
-    const vvcb_dq_rates& R = P.rates[job.rate_idx];
     const int lw = job.log2w, lh = job.log2h, w = 1 << lw;
     const DqShape shp = rom.shape[lw - 2][lh - 2];
     const DqScanPos* scan = rom.pos + shp.first;
@@ -650,116 +670,134 @@ __global__ void __launch_bounds__(128) rdoq_ts_kernel(RdoqParams P)
     const int trShift = 15 - P.bd - ((lw + lh) >> 1);
     const int qBits = 14 + job.qp_per + trShift;
     const int quantCoeff = rom.quantScales[job.qp_rem];
-    // xGetErrScaleCoeff: 2^15 * 2^(-2 transformShift) / QStep / QStep
-    const double errorScale = __ddiv_rn(__ddiv_rn(ldexp(32768.0, -2 * trShift), (double)quantCoeff), (double)quantCoeff);
-    const int iScale = rom.invQuantScales[job.qp_rem];
-    const int rightShift = 6 - (trShift + job.qp_per);
-    const int tgt = vmin(16, 32 + rightShift - 7);
-    const int inMin = -(1 << (tgt - 1)), inMax = (1 << (tgt - 1)) - 1;
-    unsigned long long sigGroups = 0;                 // m_sigCoeffGroupFlag, by raster position of the sub-block
-    bool anySigCG = false;
-    int absSum = 0;
-    for (int sb = 0; sb < shp.numSbb; sb++) {
-      const int sbPos = sbbPosTab[sb];
-      const int sy = sbPos / shp.widthInSbb, sx = sbPos - sy * shp.widthInSbb;
-      const int sigLeft = sx > 0 ? (int)((sigGroups >> (sbPos - 1)) & 1) : 0;
-      const int sigAbove = sy > 0 ? (int)((sigGroups >> (sbPos - shp.widthInSbb)) & 1) : 0;
-      const uint32_t* bitsSigGroup = R.ts_sig_sbb[sigLeft + sigAbove];
-      int noCoeffCoded = 0;
-      bool sig = false;
-      double baseCost = 0.0, sigCostSum = 0.0, codedLevelAndDist = 0.0, uncodedDist = 0.0;
-      for (int i = 0; i < 16; i++) {
-        const DqScanPos sp = scan[sb * 16 + i];
-        const int blk = sp.idx;
-        const int c = coeff[blk];
+    const TsRates& R = sRates[wib];
+    uint32_t* scn = sScan[wib];
+    uint32_t* mag = sMag[wib];
+    int16_t* lvl = sLevel[wib];
+    {
+      const uint32_t* src = &P.rates[job.rate_idx].ts_sig_sbb[0][0];
+      for (int i = lane; i < (int)(sizeof(TsRates) / 4); i += 32) reinterpret_cast<uint32_t*>(&sRates[wib])[i] = src[i];
+      const long long cap = 0x7fffffffll - (1ll << (qBits - 1));
+      for (int pos = lane; pos < shp.numCoeff; pos += 32) {
+        const DqScanPos sp = scan[pos];
+        const int c = coeff[sp.idx];
         const long long tmpLevel = (long long)vabs(c) * quantCoeff;
-        const long long cap = 0x7fffffffll - (1ll << (qBits - 1));
-        const int levelDouble = (int)(tmpLevel < cap ? tmpLevel : cap);
-        const int roundAbs = vmin(32767, (int)(((long long)levelDouble + (1ll << (qBits - 1))) >> qBits));
-        const int minAbs = roundAbs > 1 ? roundAbs - 1 : 1;
-        const int upAbs = vmin(32767, vmin(32767, levelDouble >> qBits) + 1);
-        const int right = sp.x > 0 ? level[blk - 1] : 0;       // neighTS: left ...
-        const int below = sp.y > 0 ? level[blk - w] : 0;       // ... and upper neighbour
-        const int pred1 = vmax(vabs(below), vabs(right));
-        int tested[3], nTested = 0;
-        tested[nTested++] = roundAbs;
-        if (minAbs != roundAbs) tested[nTested++] = minAbs;
-        const int predPixel = upAbs == pred1 ? 1 : (upAbs < pred1 ? upAbs + 1 : upAbs);
-        if (upAbs != roundAbs && upAbs != minAbs && predPixel == 1) tested[nTested++] = upAbs;
-        const double dErr = (double)levelDouble;
-        const double cost0 = __dmul_rn(__dmul_rn(dErr, dErr), errorScale);
-        const int numPos = (right != 0) + (below != 0);
-        const uint32_t* bitsSig = R.ts_sig[numPos];
-        const int ricePar = rom.tsRicePars[vmin(vabs(right) + vabs(below), 31)];
-        int signCtx;
-        if ((right == 0 && below == 0) || ((long long)right * below < 0)) signCtx = 0;
-        else if (right >= 0 && below >= 0) signCtx = 1;
-        else signCtx = 2;
-        const uint32_t* bitsSign = R.ts_sign[signCtx];
-        const uint32_t* bitsGt1 = R.ts_lrg1[numPos];
-        const int sgn = c < 0;
-        const bool isLast = i == 15 && noCoeffCoded == 0;
-        // xGetCodedLevelTSPred
-        double cost, csig = 0.0, currCostSig = 0.0;
-        int best = 0;
-        bool done = false;
-        if (!isLast && tested[0] < 3) {
-          csig = __dmul_rn(lambda, (double)bitsSig[0]);
-          cost = __dadd_rn(cost0, csig);
-          done = tested[0] == 0;
-        } else cost = 1.7976931348623157e308;
-        if (!done) {
-          if (!isLast) currCostSig = __dmul_rn(lambda, (double)bitsSig[1]);
-          for (int k = 0; k < nTested; k++) {
-            const int absLevel = tested[k];
-            const double e = (double)(levelDouble - (int)((unsigned)absLevel << qBits));
-            const double err = __dmul_rn(__dmul_rn(e, e), errorScale);
-            const int mod = absLevel == pred1 ? 1 : (absLevel < pred1 ? absLevel + 1 : absLevel);
-            double cur = __dadd_rn(err, __dmul_rn(lambda, (double)rdoq_ic_rate_ts(mod, R, bitsSign, bitsGt1, sgn, ricePar)));
-            cur = __dadd_rn(cur, currCostSig);
-            if (cur < cost) { best = absLevel; cost = cur; csig = currCostSig; }
-          }
-        }
-        if (best > 0) noCoeffCoded++;
-        const int lv = (best != 0 && c < 0) ? -best : best;
-        level[blk] = lv;
-        baseCost = __dadd_rn(baseCost, cost);
-        sigCostSum = __dadd_rn(sigCostSum, csig);
-        if (lv) {
-          sig = true;
-          codedLevelAndDist = __dadd_rn(codedLevelAndDist, __dsub_rn(cost, csig));
-          uncodedDist = __dadd_rn(uncodedDist, cost0);
-        }
-      }
-      if (sig && (sb != shp.numSbb - 1 || anySigCG)) {
-        double costZeroSB = baseCost;
-        baseCost = __dadd_rn(baseCost, __dmul_rn(lambda, (double)bitsSigGroup[1]));
-        costZeroSB = __dadd_rn(costZeroSB, __dmul_rn(lambda, (double)bitsSigGroup[0]));
-        costZeroSB = __dadd_rn(costZeroSB, uncodedDist);
-        costZeroSB = __dsub_rn(costZeroSB, codedLevelAndDist);
-        costZeroSB = __dsub_rn(costZeroSB, sigCostSum);
-        if (costZeroSB < baseCost) {
-          sig = false;
-          for (int i = 0; i < 16; i++) level[scan[sb * 16 + i].idx] = 0;
-        } else anySigCG = true;
-      }
-      if (sig) {
-        sigGroups |= 1ull << sbPos;
-        for (int i = 0; i < 16; i++) {
-          const int blk = scan[sb * 16 + i].idx;
-          const int lv = level[blk];
-          if (lv) {
-            absSum += vabs(lv);
-            const int qc = vmin(vmax(lv, inMin), inMax);
-            int d;
-            if (rightShift > 0) d = (qc * iScale + (1 << (rightShift - 1))) >> rightShift;
-            else                d = (int)((unsigned)(qc * iScale) << (-rightShift));
-            deq[blk] = vmin(vmax(d, -32768), 32767);
-          }
-        }
+        scn[pos] = (uint32_t)sp.idx | ((uint32_t)sp.x << 16) | ((uint32_t)sp.y << 24);
+        mag[pos] = (uint32_t)(tmpLevel < cap ? tmpLevel : cap) | (c < 0 ? 0x80000000u : 0u);
+        lvl[pos] = 0;                                  // numCoeff == w * h for a transform-skip block
       }
     }
-    P.results[ji].abs_sum_level = absSum;
+    __syncwarp();
+    if (lane == 0) {
+      // xGetErrScaleCoeff: 2^15 * 2^(-2 transformShift) / QStep / QStep
+      const double errorScale = __ddiv_rn(__ddiv_rn(ldexp(32768.0, -2 * trShift), (double)quantCoeff), (double)quantCoeff);
+      const int iScale = rom.invQuantScales[job.qp_rem];
+      const int rightShift = 6 - (trShift + job.qp_per);
+      const int tgt = vmin(16, 32 + rightShift - 7);
+      const int inMin = -(1 << (tgt - 1)), inMax = (1 << (tgt - 1)) - 1;
+      unsigned long long sigGroups = 0;                 // m_sigCoeffGroupFlag, by raster position of the sub-block
+      bool anySigCG = false;
+      int absSum = 0;
+      for (int sb = 0; sb < shp.numSbb; sb++) {
+        const int sbPos = sbbPosTab[sb];
+        const int sy = sbPos / shp.widthInSbb, sx = sbPos - sy * shp.widthInSbb;
+        const int sigLeft = sx > 0 ? (int)((sigGroups >> (sbPos - 1)) & 1) : 0;
+        const int sigAbove = sy > 0 ? (int)((sigGroups >> (sbPos - shp.widthInSbb)) & 1) : 0;
+        const uint32_t* bitsSigGroup = R.sig_sbb[sigLeft + sigAbove];
+        int noCoeffCoded = 0;
+        bool sig = false;
+        double baseCost = 0.0, sigCostSum = 0.0, codedLevelAndDist = 0.0, uncodedDist = 0.0;
+        for (int i = 0; i < 16; i++) {
+          const uint32_t sc = scn[sb * 16 + i], mg = mag[sb * 16 + i];
+          const int blk = (int)(sc & 0xffffu), spx = (int)((sc >> 16) & 0xff), spy = (int)(sc >> 24);
+          const int levelDouble = (int)(mg & 0x7fffffffu), sgn = (int)(mg >> 31);
+          const int roundAbs = vmin(32767, (int)(((long long)levelDouble + (1ll << (qBits - 1))) >> qBits));
+          const int minAbs = roundAbs > 1 ? roundAbs - 1 : 1;
+          const int upAbs = vmin(32767, vmin(32767, levelDouble >> qBits) + 1);
+          const int right = spx > 0 ? (int)lvl[blk - 1] : 0;      // neighTS: left ...
+          const int below = spy > 0 ? (int)lvl[blk - w] : 0;      // ... and upper neighbour
+          const int pred1 = vmax(vabs(below), vabs(right));
+          int tested[3], nTested = 0;
+          tested[nTested++] = roundAbs;
+          if (minAbs != roundAbs) tested[nTested++] = minAbs;
+          const int predPixel = upAbs == pred1 ? 1 : (upAbs < pred1 ? upAbs + 1 : upAbs);
+          if (upAbs != roundAbs && upAbs != minAbs && predPixel == 1) tested[nTested++] = upAbs;
+          const double dErr = (double)levelDouble;
+          const double cost0 = __dmul_rn(__dmul_rn(dErr, dErr), errorScale);
+          const int numPos = (right != 0) + (below != 0);
+          const uint32_t* bitsSig = R.sig[numPos];
+          const int ricePar = rom.tsRicePars[vmin(vabs(right) + vabs(below), 31)];
+          int signCtx;
+          if ((right == 0 && below == 0) || ((long long)right * below < 0)) signCtx = 0;
+          else if (right >= 0 && below >= 0) signCtx = 1;
+          else signCtx = 2;
+          const uint32_t* bitsSign = R.sign[signCtx];
+          const uint32_t* bitsGt1 = R.lrg1[numPos];
+          const bool isLast = i == 15 && noCoeffCoded == 0;
+          // xGetCodedLevelTSPred
+          double cost, csig = 0.0, currCostSig = 0.0;
+          int best = 0;
+          bool done = false;
+          if (!isLast && tested[0] < 3) {
+            csig = __dmul_rn(lambda, (double)bitsSig[0]);
+            cost = __dadd_rn(cost0, csig);
+            done = tested[0] == 0;
+          } else cost = 1.7976931348623157e308;
+          if (!done) {
+            if (!isLast) currCostSig = __dmul_rn(lambda, (double)bitsSig[1]);
+            for (int k = 0; k < nTested; k++) {
+              const int absLevel = tested[k];
+              const double e = (double)(levelDouble - (int)((unsigned)absLevel << qBits));
+              const double err = __dmul_rn(__dmul_rn(e, e), errorScale);
+              const int mod = absLevel == pred1 ? 1 : (absLevel < pred1 ? absLevel + 1 : absLevel);
+              double cur = __dadd_rn(err, __dmul_rn(lambda, (double)rdoq_ic_rate_ts(mod, R, bitsSign, bitsGt1, sgn, ricePar)));
+              cur = __dadd_rn(cur, currCostSig);
+              if (cur < cost) { best = absLevel; cost = cur; csig = currCostSig; }
+            }
+          }
+          if (best > 0) noCoeffCoded++;
+          const int lv = (best != 0 && sgn) ? -best : best;
+          lvl[blk] = (int16_t)lv;
+          baseCost = __dadd_rn(baseCost, cost);
+          sigCostSum = __dadd_rn(sigCostSum, csig);
+          if (lv) {
+            sig = true;
+            codedLevelAndDist = __dadd_rn(codedLevelAndDist, __dsub_rn(cost, csig));
+            uncodedDist = __dadd_rn(uncodedDist, cost0);
+          }
+        }
+        if (sig && (sb != shp.numSbb - 1 || anySigCG)) {
+          double costZeroSB = baseCost;
+          baseCost = __dadd_rn(baseCost, __dmul_rn(lambda, (double)bitsSigGroup[1]));
+          costZeroSB = __dadd_rn(costZeroSB, __dmul_rn(lambda, (double)bitsSigGroup[0]));
+          costZeroSB = __dadd_rn(costZeroSB, uncodedDist);
+          costZeroSB = __dsub_rn(costZeroSB, codedLevelAndDist);
+          costZeroSB = __dsub_rn(costZeroSB, sigCostSum);
+          if (costZeroSB < baseCost) {
+            sig = false;
+            for (int i = 0; i < 16; i++) lvl[scn[sb * 16 + i] & 0xffffu] = 0;
+          } else anySigCG = true;
+        }
+        if (sig) {
+          sigGroups |= 1ull << sbPos;
+          for (int i = 0; i < 16; i++) {
+            const int blk = (int)(scn[sb * 16 + i] & 0xffffu);
+            const int lv = lvl[blk];
+            if (lv) {
+              absSum += vabs(lv);
+              level[blk] = lv;                         // the caller zero-filled the block
+              const int qc = vmin(vmax(lv, inMin), inMax);
+              int d;
+              if (rightShift > 0) d = (qc * iScale + (1 << (rightShift - 1))) >> rightShift;
+              else                d = (int)((unsigned)(qc * iScale) << (-rightShift));
+              deq[blk] = vmin(vmax(d, -32768), 32767);
+            }
+          }
+        }
+      }
+      P.results[ji].abs_sum_level = absSum;
+    }
+    __syncwarp();
   }
 }
 
