@@ -563,7 +563,7 @@ def bitexact_leg(frames, device):
             'engine_busy_frac': stats['busy_ns'] / stats['wall_ns'] / workers if stats['wall_ns'] else None,
             'broker': {k: stats[k] for k in ('cycles', 'requests', 'visits', 'tu_jobs', 'max_batch', 'kernel_launches')},
             # host wall time of the workers inside vvcb_cu_eval per batch, microseconds: pack + launch the rough mode decision, wait for its
-            # lists, expand the templates, launch the TU stage, wait for it, hand the outputs back
+            # lists, expand the templates, launch the TU stage, wait for it, hand the outputs back; then the device spans of the two stages
             'batch_phase_us': [round(x / 1e3 / max(1, stats['cycles']), 1) for x in stats.get('phase_ns', [])],
             'mean_round_trips_merged_per_batch': stats['requests'] / max(1, stats['cycles']),
             'walker_wait_for_engine_s_mean': tot('engine_wait_s') / n,

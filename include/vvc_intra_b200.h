@@ -125,7 +125,8 @@ int  vvcb_device_count(void);
  * configuration): residual_coding then picks its significance context set with the quantiser state machine (EL/CABACWriter.cpp:3866). */
 #define VVCB_OPT_DEP_QUANT 1
 /* VVCB_OPT_YIELD_SYNC (default 0): 1 = the calling thread sleeps while it waits for the device (blocking event) instead of polling; for
- * hosts whose cores are shared with the encoder's walkers (the broker's worker threads).                                            */
+ * hosts whose cores are shared with the encoder's walkers (the broker's worker threads).  N in 2..1000 = it looks every N microseconds
+ * and sleeps in between (timed sleep instead of the blocking event's interrupt path).                                               */
 #define VVCB_OPT_YIELD_SYNC 2
 int  vvcb_set_option(vvcb_ctx* ctx, int option, int value);
 
@@ -405,8 +406,9 @@ uint64_t vvcb_launch_count(const vvcb_ctx* ctx);
 /* Where the host time of vvcb_cu_eval goes, cumulative wall-clock nanoseconds since the context was created: ns[0] packing the
  * rectangles and launching the rough mode decision, ns[1] waiting for its lists (calls with candidate templates only), ns[2] expanding
  * the templates and assembling the TU batch, ns[3] launching the TU stage, ns[4] waiting for its results, ns[5] handing the outputs
- * back.  A measuring aid for the latency-bound use (profiles/).                                                                  */
-int vvcb_cu_eval_phases(const vvcb_ctx* ctx, uint64_t ns[6], uint64_t* calls);
+ * back; then two spans on the device (CUDA events on the context's stream): ns[6] rough mode decision, ns[7] TU stage.  A measuring
+ * aid for the latency-bound use (profiles/).                                                                                     */
+int vvcb_cu_eval_phases(const vvcb_ctx* ctx, uint64_t ns[8], uint64_t* calls);
 
 #ifdef __cplusplus
 }

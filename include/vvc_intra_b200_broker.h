@@ -28,7 +28,7 @@ typedef struct vvcb_broker_stats {
   uint64_t wall_ns;           /* wall time since the server started serving                                   */
   uint64_t clients_seen;      /* clients that ever connected                                                  */
   uint64_t kernel_launches;   /* vvcb_launch_count of the server's context                                    */
-  uint64_t phase_ns[6];       /* vvcb_cu_eval_phases summed over the workers' contexts                        */
+  uint64_t phase_ns[8];       /* vvcb_cu_eval_phases summed over the workers' contexts                        */
 } vvcb_broker_stats;
 
 /* Server: creates the broker file at `path`, `workers` engine contexts on `device` (one per worker thread, each with its own stream,

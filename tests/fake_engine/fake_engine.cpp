@@ -36,7 +36,7 @@ extern "C" {
 
 int vvcb_device_count(void) { return 1; }
 uint64_t vvcb_launch_count(const vvcb_ctx*) { return 0; }
-int vvcb_cu_eval_phases(const vvcb_ctx* ctx, uint64_t ns[6], uint64_t* calls) { if (!ctx || !ns) return VVCB_ERR_ARG; for (int i = 0; i < 6; i++) ns[i] = 0; if (calls) *calls = 0; return VVCB_OK; }
+int vvcb_cu_eval_phases(const vvcb_ctx* ctx, uint64_t ns[8], uint64_t* calls) { if (!ctx || !ns) return VVCB_ERR_ARG; for (int i = 0; i < 8; i++) ns[i] = 0; if (calls) *calls = 0; return VVCB_OK; }
 const char* vvcb_last_error(const vvcb_ctx* ctx) { return ctx ? ctx->err : g_createErr; }
 
 int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_size)

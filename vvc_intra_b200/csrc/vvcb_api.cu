@@ -54,7 +54,7 @@ struct vvcb_ctx {
   cudaEvent_t ev0, ev1;
   Rom* dRom;
   TrRom* dTrRom;
-  void* dTu[20]; size_t capTu[20];  // TU scratch: jobs, resi, pred, coeff, level, reco, results; DepQuant: coeff in, dequantised out,
+  void* dTu[24]; size_t capTu[24];  // TU scratch: jobs, resi, pred, coeff, level, reco, results; DepQuant: coeff in, dequantised out,
                                     // job order, context prices, derived rate tables, per-group context memory + trellis
   DqRom* dDqRom;
   RateRom* dRateRom;
@@ -83,10 +83,11 @@ struct vvcb_ctx {
   int16_t* wReco;                   // writable reconstruction plane: own (dReco) or another context's (vvcb_frame_share)
   int yieldSync; cudaEvent_t evYield;   // VVCB_OPT_YIELD_SYNC
   void* remote;                     // broker client proxy: VVCB_BROKER was set at vvcb_create (vvcb_broker.inc)
-  void* hPin[8]; size_t capPin[8];  // page-locked staging of vvcb_cu_eval / vvcb_reco_update_rects
+  void* hPin[10]; size_t capPin[10];  // page-locked staging of vvcb_cu_eval / vvcb_reco_update_rects
   void* dRect[2]; size_t capRect[2];
   uint64_t launches;
-  uint64_t cuNs[6], cuCalls, tuWaitFrom;    // vvcb_cu_eval_phases
+  uint64_t cuNs[8], cuCalls, tuWaitFrom;    // vvcb_cu_eval_phases
+  cudaEvent_t cev[4]; bool cuSpan;          // device spans of the two stages of vvcb_cu_eval
   int timing; int timedLaunches; float kms[3]; cudaEvent_t kev[4];
   char err[512];
 };
@@ -109,7 +110,13 @@ static cudaError_t ctx_sync(vvcb_ctx* ctx)
 {
   if (!ctx->yieldSync) return cudaStreamSynchronize(ctx->stream);
   cudaError_t e = cudaEventRecord(ctx->evYield, ctx->stream);
-  return e != cudaSuccess ? e : cudaEventSynchronize(ctx->evYield);
+  if (e != cudaSuccess) return e;
+  if (ctx->yieldSync == 1) return cudaEventSynchronize(ctx->evYield);
+  // value N >= 2: look every N microseconds and sleep in between (the blocking event's wake-up costs several hundred microseconds on some
+  // hosts, tools/sync_latency.cu; a timed sleep of a real-time thread does not)
+  timespec nap = { 0, (long)ctx->yieldSync * 1000 };
+  while ((e = cudaEventQuery(ctx->evYield)) == cudaErrorNotReady) nanosleep(&nap, nullptr);
+  return e;
 }
 
 #include "vvcb_broker.inc"
@@ -179,6 +186,7 @@ extern "C" int vvcb_create(vvcb_ctx** out, int device, int bit_depth, int ctu_si
   if ((e = cudaEventCreateWithFlags(&ctx->evYield, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
   for (int i = 0; i < 4; i++) if ((e = cudaEventCreate(&ctx->kev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
+  for (int i = 0; i < 4; i++) if ((e = cudaEventCreate(&ctx->cev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
   for (int i = 0; i < 5; i++) if ((e = cudaEventCreate(&ctx->tev[i])) != cudaSuccess) return fail("cudaEventCreate", e);
   Rom* h = new Rom();
   fill_rom(*h);
@@ -219,11 +227,11 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   if (ctx->remote) { vvcbc_disconnect(ctx->remote); delete ctx; return; }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (int i = 0; i < 8; i++) if (ctx->hPin[i]) cudaFreeHost(ctx->hPin[i]);
+  for (int i = 0; i < 10; i++) if (ctx->hPin[i]) cudaFreeHost(ctx->hPin[i]);
   cudaFree(ctx->dRect[0]); cudaFree(ctx->dRect[1]); cudaFree(ctx->dBrief);
   cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dSlotMajor);
   cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred); cudaFree(ctx->dTrRom);
-  for (int i = 0; i < 20; i++) cudaFree(ctx->dTu[i]);
+  for (int i = 0; i < 24; i++) cudaFree(ctx->dTu[i]);
   cudaFree(ctx->dRateRom);
   cudaFree(ctx->dDqRom);
   for (int i = 0; i < 2; i++) cudaFree(ctx->dFeat[i]);
@@ -234,6 +242,7 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   }
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evYield);
   for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->kev[i]);
+  for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->cev[i]);
   for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->tev[i]);
   for (int i = 0; i < kSideStreams; i++) { cudaStreamSynchronize(ctx->sKind[i]); cudaStreamDestroy(ctx->sKind[i]); cudaEventDestroy(ctx->evKind[i]); }
   cudaEventDestroy(ctx->evPlan);
@@ -248,7 +257,7 @@ extern "C" int vvcb_set_option(vvcb_ctx* ctx, int option, int value)
     ctx->depQuant = value;
     return ctx->remote ? vvcbc_set_option(ctx->remote, option, value, ctx->err, sizeof(ctx->err)) : VVCB_OK;
   }
-  if (option == VVCB_OPT_YIELD_SYNC && (value == 0 || value == 1)) { ctx->yieldSync = value; return VVCB_OK; }
+  if (option == VVCB_OPT_YIELD_SYNC && value >= 0 && value <= 1000) { ctx->yieldSync = value; return VVCB_OK; }
   if (option == VVCB_OPT_TRUSTED_VISITS && (value == 0 || value == 1)) { ctx->trusted = value; return VVCB_OK; }
   snprintf(ctx->err, sizeof(ctx->err), "vvcb_set_option: unknown option %d or bad value %d", option, value);
   return VVCB_ERR_ARG;
@@ -852,6 +861,30 @@ extern "C" int vvcb_rmd_pred(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int slo
 
 extern "C" int vvcb_rmd_pred_all(vvcb_ctx* ctx, const vvcb_rmd_visit* visit, int16_t* pred) { return rmd_pred_impl(ctx, visit, -1, pred); }
 
+// Walk mode of the TU stage (vvcb_cu_eval): every host input travels in ONE page-locked arena and every output comes back in one, both moved
+// by a copy KERNEL over the mapped host memory instead of by the copy engines.  The engines' queues are shared by all streams of the
+// process in issue order: the small copies of one broker worker waited there behind another worker's copy whose kernels were still
+// running (0.6-0.7 ms per wait, profiles/r2_summary.md).  A kernel launch is ordered by its own stream only.
+struct TuWalk {
+  bool wantLevel, wantReco, wantPred;
+  vvcb_tu_result* results; int32_t* level; int16_t* reco; int16_t* pred;      // out: where the results lie in the page-locked arena (valid until the next call)
+};
+
+__global__ void arena_copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+static cudaError_t arena_copy(vvcb_ctx* ctx, const void* src, void* dst, size_t bytes)
+{
+  const size_t n16 = (bytes + 15) / 16;
+  if (!n16) return cudaSuccess;
+  const int grid = (int)std::min<size_t>((n16 + 255) / 256, (size_t)ctx->numSms * 4);
+  arena_copy_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), n16);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
 static int tu_buf(vvcb_ctx* ctx, int i, size_t bytes)
 {
   if (bytes > ctx->capTu[i]) {
@@ -866,11 +899,11 @@ static int tu_buf(vvcb_ctx* ctx, int i, size_t bytes)
 // produced on the device by tu_pred_kernel from the frame planes).
 static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int16_t* resi, const int16_t* pred, size_t n_samples,
                         const vvcb_dq_rates* rates, const vvcb_ctx_states* states, int n_rates, int32_t* coeff, int32_t* level, int16_t* reco, vvcb_tu_result* results,
-                        const vvcb_rmd_visit* visits, int n_visits, const vvcb_tu_src* src, int16_t* pred_out)
+                        const vvcb_rmd_visit* visits, int n_visits, const vvcb_tu_src* src, int16_t* pred_out, TuWalk* walk = nullptr)
 {
   if (!ctx) return VVCB_ERR_ARG;
   REMOTE_UNAVAILABLE("vvcb_tu_eval");
-  if (n < 0 || n_rates < 0 || (n > 0 && (!jobs || !results || (!src && !resi) || (src && (!visits || n_visits <= 0))))) {
+  if (n < 0 || n_rates < 0 || (n > 0 && (!jobs || (!results && !walk) || (!src && !resi) || (src && (!visits || n_visits <= 0)))) || (walk && !src)) {
     snprintf(ctx->err, sizeof(ctx->err), "vvcb_tu_eval: bad argument"); return VVCB_ERR_ARG;
   }
   if (n == 0) return VVCB_OK;
@@ -930,59 +963,7 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
   const int nDq = (int)order.size();
   CK(cudaSetDevice(ctx->device));
   int rc;
-  if ((rc = tu_buf(ctx, 0, (size_t)n * sizeof(vvcb_tu_job)))) return rc;
-  if ((rc = tu_buf(ctx, 1, n_samples * sizeof(int16_t)))) return rc;
-  if ((rc = tu_buf(ctx, 2, n_samples * sizeof(int16_t)))) return rc;
-  if (coeff && (rc = tu_buf(ctx, 3, n_samples * sizeof(int32_t)))) return rc;
-  if ((level || nDq || nTs || nRate) && (rc = tu_buf(ctx, 4, n_samples * sizeof(int32_t)))) return rc;
-  if (nRate && (rc = tu_buf(ctx, 17, (size_t)nRate * sizeof(int)))) return rc;
-  if (nRate && (rc = tu_buf(ctx, 18, (size_t)n_rates * sizeof(vvcb_ctx_states)))) return rc;
-  if (reco && (rc = tu_buf(ctx, 5, n_samples * sizeof(int16_t)))) return rc;
-  if ((rc = tu_buf(ctx, 6, (size_t)n * sizeof(vvcb_tu_result)))) return rc;
-  int dqGrid = 0;
-  if (nDq || nTs) {
-    if ((rc = tu_buf(ctx, 7, n_samples * sizeof(int32_t)))) return rc;
-    if ((rc = tu_buf(ctx, 8, n_samples * sizeof(int32_t)))) return rc;
-    if ((rc = tu_buf(ctx, 10, (size_t)n_rates * sizeof(vvcb_dq_rates)))) return rc;
-    if (nTs && (rc = tu_buf(ctx, 16, (size_t)nTs * sizeof(int)))) return rc;
-  }
-  if (nDq) {
-    dqGrid = nDq <= 2048 ? (nDq + kDqThreads / 32 - 1) / (kDqThreads / 32) : (nDq + kDqGroups - 1) / kDqGroups;   // walk-sized batch: one TU per warp
-    if (dqGrid > ctx->numSms * 4) dqGrid = ctx->numSms * 4;
-    if ((rc = tu_buf(ctx, 9, (size_t)nDq * sizeof(int)))) return rc;
-    if ((rc = tu_buf(ctx, 11, (size_t)n_rates * sizeof(DqRateTab)))) return rc;
-    if ((rc = tu_buf(ctx, 12, (size_t)dqGrid * kDqGroups * kDqSlotBytes))) return rc;
-    if ((rc = tu_buf(ctx, 13, ((size_t)nDq * 3 + kDqBins) * sizeof(int)))) return rc;
-  }
-  CK(cudaMemcpyAsync(ctx->dTu[0], jobs, (size_t)n * sizeof(vvcb_tu_job), cudaMemcpyHostToDevice, ctx->stream));
-  const bool tm = ctx->timing != 0;
-  if (src) {
-    if ((rc = tu_buf(ctx, 14, (size_t)n_visits * sizeof(vvcb_rmd_visit)))) return rc;
-    if ((rc = tu_buf(ctx, 15, (size_t)n * sizeof(vvcb_tu_src)))) return rc;
-    CK(cudaMemcpyAsync(ctx->dTu[14], visits, (size_t)n_visits * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dTu[15], src, (size_t)n * sizeof(vvcb_tu_src), cudaMemcpyHostToDevice, ctx->stream));
-    if (tm) CK(cudaEventRecord(ctx->tev[0], ctx->stream));
-    TuPredParams Q;
-    Q.visits = static_cast<const vvcb_rmd_visit*>(ctx->dTu[14]); Q.src = static_cast<const vvcb_tu_src*>(ctx->dTu[15]);
-    Q.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); Q.n = n;
-    Q.pred = static_cast<int16_t*>(ctx->dTu[2]); Q.resi = static_cast<int16_t*>(ctx->dTu[1]);
-    Q.orig = ctx->bOrig; Q.reco = ctx->bReco; Q.stride = ctx->stride; Q.bd = ctx->bd; Q.ctu = ctx->ctu; Q.rom = ctx->dRom;
-    const int pg = (n + kTuPredWarps - 1) / kTuPredWarps < ctx->numSms * 8 ? (n + kTuPredWarps - 1) / kTuPredWarps : ctx->numSms * 8;
-    tu_pred_kernel<<<pg, kTuPredWarps * 32, 0, ctx->stream>>>(Q);
-    ctx->launches++;
-  } else {
-    CK(cudaMemcpyAsync(ctx->dTu[1], resi, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-    if (pred) CK(cudaMemcpyAsync(ctx->dTu[2], pred, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-  }
-  TuParams P;
-  P.jobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); P.list = nullptr; P.n = 0;
-  P.resi = static_cast<const int16_t*>(ctx->dTu[1]); P.pred = static_cast<const int16_t*>(ctx->dTu[2]);
-  P.coeff = coeff ? static_cast<int32_t*>(ctx->dTu[3]) : nullptr;
-  P.level = (level || nDq || nTs || nRate) ? static_cast<int32_t*>(ctx->dTu[4]) : nullptr;
-  P.reco = reco ? static_cast<int16_t*>(ctx->dTu[5]) : nullptr;
-  P.results = static_cast<vvcb_tu_result*>(ctx->dTu[6]);
-  P.orig = ctx->bOrig; P.stride = ctx->stride; P.bd = ctx->bd; P.rom = ctx->dTrRom;
-  P.dqCoeff = static_cast<int32_t*>(ctx->dTu[7]); P.dqDeq = static_cast<const int32_t*>(ctx->dTu[8]); P.phase = 0;
+  const bool wLevel = walk ? walk->wantLevel : level != nullptr, wReco = walk ? walk->wantReco : reco != nullptr, wPred = walk ? walk->wantPred : pred_out != nullptr;
   // job index lists of the two team sizes of tu_eval_kernel: blocks of up to 256 samples go to one warp each
   std::vector<int> teamList(n);
   int nSmall = 0;
@@ -992,29 +973,141 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     nSmall = lo;
   }
   const int nLarge = n - nSmall;
-  if ((rc = tu_buf(ctx, 19, (size_t)n * sizeof(int)))) return rc;
-  CK(cudaMemcpyAsync(ctx->dTu[19], teamList.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  int dqGrid = 0;
+  if (nDq) {
+    dqGrid = nDq <= 2048 ? (nDq + kDqThreads / 32 - 1) / (kDqThreads / 32) : (nDq + kDqGroups - 1) / kDqGroups;   // walk-sized batch: one TU per warp
+    if (dqGrid > ctx->numSms * 4) dqGrid = ctx->numSms * 4;
+    if ((rc = tu_buf(ctx, 11, (size_t)n_rates * sizeof(DqRateTab)))) return rc;
+    if ((rc = tu_buf(ctx, 12, (size_t)dqGrid * kDqGroups * kDqSlotBytes))) return rc;
+    if ((rc = tu_buf(ctx, 13, ((size_t)nDq * 3 + kDqBins) * sizeof(int)))) return rc;
+  }
+  if ((rc = tu_buf(ctx, 1, n_samples * sizeof(int16_t)))) return rc;
+  if (coeff && (rc = tu_buf(ctx, 3, n_samples * sizeof(int32_t)))) return rc;
+  if ((nDq || nTs) && (rc = tu_buf(ctx, 7, n_samples * sizeof(int32_t)))) return rc;
+  // device pointers of the host inputs and of the outputs: separate buffers, or (walk mode) offsets into the two arenas
+  const vvcb_tu_job* dJobs; const vvcb_rmd_visit* dVis = nullptr; const vvcb_tu_src* dSrc = nullptr; const int *dTeam, *dOrder = nullptr, *dTsOrder = nullptr, *dRateOrder = nullptr;
+  const vvcb_dq_rates* dRates = nullptr; const vvcb_ctx_states* dStates = nullptr;
+  vvcb_tu_result* dResults; int16_t *dPredBuf, *dRecoBuf = nullptr; int32_t *dLevel = nullptr, *dDeq = nullptr;
+  const bool needLevel = wLevel || nDq || nTs || nRate;
+  size_t outBytes = 0;                                              // walk mode: bytes of the output arena that travel back
+  if (walk) {
+    auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    size_t o = 0;
+    auto take = [&](size_t b) { const size_t at = o; o += up16(b); return at; };
+    const size_t iJobs = take((size_t)n * sizeof(vvcb_tu_job)), iVis = take((size_t)n_visits * sizeof(vvcb_rmd_visit)), iSrc = take((size_t)n * sizeof(vvcb_tu_src)),
+                 iTeam = take((size_t)n * sizeof(int)), iOrder = take((size_t)nDq * sizeof(int)), iTs = take((size_t)nTs * sizeof(int)),
+                 iRates = take((nDq || nTs) ? (size_t)n_rates * sizeof(vvcb_dq_rates) : 0), iRateOrder = take((size_t)nRate * sizeof(int)),
+                 iStates = take(nRate ? (size_t)n_rates * sizeof(vvcb_ctx_states) : 0);
+    const size_t inBytes = o;
+    if ((rc = pin_buf(ctx, 9, inBytes))) return rc;
+    if ((rc = tu_buf(ctx, 20, inBytes))) return rc;
+    uint8_t* hin = static_cast<uint8_t*>(ctx->hPin[9]);
+    memcpy(hin + iJobs, jobs, (size_t)n * sizeof(vvcb_tu_job));
+    memcpy(hin + iVis, visits, (size_t)n_visits * sizeof(vvcb_rmd_visit));
+    memcpy(hin + iSrc, src, (size_t)n * sizeof(vvcb_tu_src));
+    memcpy(hin + iTeam, teamList.data(), (size_t)n * sizeof(int));
+    if (nDq) memcpy(hin + iOrder, order.data(), (size_t)nDq * sizeof(int));
+    if (nTs) memcpy(hin + iTs, tsOrder.data(), (size_t)nTs * sizeof(int));
+    if (nDq || nTs) memcpy(hin + iRates, rates, (size_t)n_rates * sizeof(vvcb_dq_rates));
+    if (nRate) { memcpy(hin + iRateOrder, rateOrder.data(), (size_t)nRate * sizeof(int)); memcpy(hin + iStates, states, (size_t)n_rates * sizeof(vvcb_ctx_states)); }
+    uint8_t* din = static_cast<uint8_t*>(ctx->dTu[20]);
+    CK(arena_copy(ctx, hin, din, inBytes));
+    dJobs = reinterpret_cast<const vvcb_tu_job*>(din + iJobs); dVis = reinterpret_cast<const vvcb_rmd_visit*>(din + iVis); dSrc = reinterpret_cast<const vvcb_tu_src*>(din + iSrc);
+    dTeam = reinterpret_cast<const int*>(din + iTeam); dOrder = reinterpret_cast<const int*>(din + iOrder); dTsOrder = reinterpret_cast<const int*>(din + iTs);
+    dRates = reinterpret_cast<const vvcb_dq_rates*>(din + iRates); dRateOrder = reinterpret_cast<const int*>(din + iRateOrder); dStates = reinterpret_cast<const vvcb_ctx_states*>(din + iStates);
+    // output arena: results | prediction | reconstruction | levels, then (not travelling) the dequantised coefficients next to the levels
+    o = 0;
+    const size_t oRes = take((size_t)n * sizeof(vvcb_tu_result)), oPred = take(n_samples * sizeof(int16_t)), oReco = take(wReco ? n_samples * sizeof(int16_t) : 0),
+                 oLevel = take(needLevel ? n_samples * sizeof(int32_t) : 0);
+    outBytes = wLevel ? o : (wReco ? oLevel : (wPred ? oReco : oPred));
+    const size_t oDeq = take((nDq || nTs) ? n_samples * sizeof(int32_t) : 0);
+    if ((rc = tu_buf(ctx, 21, o))) return rc;
+    if ((rc = pin_buf(ctx, 8, outBytes))) return rc;
+    uint8_t* dout = static_cast<uint8_t*>(ctx->dTu[21]);
+    uint8_t* hout = static_cast<uint8_t*>(ctx->hPin[8]);
+    dResults = reinterpret_cast<vvcb_tu_result*>(dout + oRes); dPredBuf = reinterpret_cast<int16_t*>(dout + oPred); dRecoBuf = wReco ? reinterpret_cast<int16_t*>(dout + oReco) : nullptr;
+    dLevel = needLevel ? reinterpret_cast<int32_t*>(dout + oLevel) : nullptr; dDeq = (nDq || nTs) ? reinterpret_cast<int32_t*>(dout + oDeq) : nullptr;
+    walk->results = reinterpret_cast<vvcb_tu_result*>(hout + oRes); walk->pred = reinterpret_cast<int16_t*>(hout + oPred);
+    walk->reco = reinterpret_cast<int16_t*>(hout + oReco); walk->level = reinterpret_cast<int32_t*>(hout + oLevel);
+    if (nDq || nTs) CK(cudaMemsetAsync(dLevel, 0, up16(n_samples * sizeof(int32_t)) + n_samples * sizeof(int32_t), ctx->stream));   // levels and dequantised coefficients: adjacent
+  } else {
+    if ((rc = tu_buf(ctx, 0, (size_t)n * sizeof(vvcb_tu_job)))) return rc;
+    if ((rc = tu_buf(ctx, 2, n_samples * sizeof(int16_t)))) return rc;
+    if (needLevel && (rc = tu_buf(ctx, 4, n_samples * sizeof(int32_t)))) return rc;
+    if (nRate && (rc = tu_buf(ctx, 17, (size_t)nRate * sizeof(int)))) return rc;
+    if (nRate && (rc = tu_buf(ctx, 18, (size_t)n_rates * sizeof(vvcb_ctx_states)))) return rc;
+    if (wReco && (rc = tu_buf(ctx, 5, n_samples * sizeof(int16_t)))) return rc;
+    if ((rc = tu_buf(ctx, 6, (size_t)n * sizeof(vvcb_tu_result)))) return rc;
+    if (nDq || nTs) {
+      if ((rc = tu_buf(ctx, 8, n_samples * sizeof(int32_t)))) return rc;
+      if ((rc = tu_buf(ctx, 10, (size_t)n_rates * sizeof(vvcb_dq_rates)))) return rc;
+      if (nTs && (rc = tu_buf(ctx, 16, (size_t)nTs * sizeof(int)))) return rc;
+    }
+    if (nDq && (rc = tu_buf(ctx, 9, (size_t)nDq * sizeof(int)))) return rc;
+    if ((rc = tu_buf(ctx, 19, (size_t)n * sizeof(int)))) return rc;
+    CK(cudaMemcpyAsync(ctx->dTu[0], jobs, (size_t)n * sizeof(vvcb_tu_job), cudaMemcpyHostToDevice, ctx->stream));
+    if (src) {
+      if ((rc = tu_buf(ctx, 14, (size_t)n_visits * sizeof(vvcb_rmd_visit)))) return rc;
+      if ((rc = tu_buf(ctx, 15, (size_t)n * sizeof(vvcb_tu_src)))) return rc;
+      CK(cudaMemcpyAsync(ctx->dTu[14], visits, (size_t)n_visits * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->dTu[15], src, (size_t)n * sizeof(vvcb_tu_src), cudaMemcpyHostToDevice, ctx->stream));
+      dVis = static_cast<const vvcb_rmd_visit*>(ctx->dTu[14]); dSrc = static_cast<const vvcb_tu_src*>(ctx->dTu[15]);
+    }
+    CK(cudaMemcpyAsync(ctx->dTu[19], teamList.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (nDq || nTs) {
+      CK(cudaMemsetAsync(ctx->dTu[4], 0, n_samples * sizeof(int32_t), ctx->stream));     // levels / dequantised coefficients the
+      CK(cudaMemsetAsync(ctx->dTu[8], 0, n_samples * sizeof(int32_t), ctx->stream));     // quantiser kernels do not reach stay zero
+      if (nDq) CK(cudaMemcpyAsync(ctx->dTu[9], order.data(), (size_t)nDq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      if (nTs) CK(cudaMemcpyAsync(ctx->dTu[16], tsOrder.data(), (size_t)nTs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->dTu[10], rates, (size_t)n_rates * sizeof(vvcb_dq_rates), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (nRate) {
+      CK(cudaMemcpyAsync(ctx->dTu[17], rateOrder.data(), (size_t)nRate * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->dTu[18], states, (size_t)n_rates * sizeof(vvcb_ctx_states), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    dJobs = static_cast<const vvcb_tu_job*>(ctx->dTu[0]); dTeam = static_cast<const int*>(ctx->dTu[19]);
+    dOrder = static_cast<const int*>(ctx->dTu[9]); dTsOrder = static_cast<const int*>(ctx->dTu[16]); dRateOrder = static_cast<const int*>(ctx->dTu[17]);
+    dRates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]); dStates = static_cast<const vvcb_ctx_states*>(ctx->dTu[18]);
+    dResults = static_cast<vvcb_tu_result*>(ctx->dTu[6]); dPredBuf = static_cast<int16_t*>(ctx->dTu[2]); dRecoBuf = wReco ? static_cast<int16_t*>(ctx->dTu[5]) : nullptr;
+    dLevel = needLevel ? static_cast<int32_t*>(ctx->dTu[4]) : nullptr; dDeq = static_cast<int32_t*>(ctx->dTu[8]);
+  }
+  const bool tm = ctx->timing != 0;
+  if (src) {
+    if (tm) CK(cudaEventRecord(ctx->tev[0], ctx->stream));
+    TuPredParams Q;
+    Q.visits = dVis; Q.src = dSrc; Q.jobs = dJobs; Q.n = n;
+    Q.pred = dPredBuf; Q.resi = static_cast<int16_t*>(ctx->dTu[1]);
+    Q.orig = ctx->bOrig; Q.reco = ctx->bReco; Q.stride = ctx->stride; Q.bd = ctx->bd; Q.ctu = ctx->ctu; Q.rom = ctx->dRom;
+    const int pg = (n + kTuPredWarps - 1) / kTuPredWarps < ctx->numSms * 8 ? (n + kTuPredWarps - 1) / kTuPredWarps : ctx->numSms * 8;
+    tu_pred_kernel<<<pg, kTuPredWarps * 32, 0, ctx->stream>>>(Q);
+    ctx->launches++;
+  } else {
+    CK(cudaMemcpyAsync(ctx->dTu[1], resi, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (pred) CK(cudaMemcpyAsync(dPredBuf, pred, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  TuParams P;
+  P.jobs = dJobs; P.list = nullptr; P.n = 0;
+  P.resi = static_cast<const int16_t*>(ctx->dTu[1]); P.pred = dPredBuf;
+  P.coeff = coeff ? static_cast<int32_t*>(ctx->dTu[3]) : nullptr;
+  P.level = dLevel;
+  P.reco = dRecoBuf;
+  P.results = dResults;
+  P.orig = ctx->bOrig; P.stride = ctx->stride; P.bd = ctx->bd; P.rom = ctx->dTrRom;
+  P.dqCoeff = static_cast<int32_t*>(ctx->dTu[7]); P.dqDeq = dDeq; P.phase = 0;
   auto launch_tu = [&](TuParams Q) {
     if (nSmall) {
-      Q.list = static_cast<const int*>(ctx->dTu[19]); Q.n = nSmall;
+      Q.list = dTeam; Q.n = nSmall;
       const int g = (nSmall + 3) / 4 < ctx->numSms * 8 ? (nSmall + 3) / 4 : ctx->numSms * 8;
       tu_eval_kernel<32><<<g, kTuThreads, 0, ctx->stream>>>(Q);
       ctx->launches++;
     }
     if (nLarge) {
-      Q.list = static_cast<const int*>(ctx->dTu[19]) + nSmall; Q.n = nLarge;
+      Q.list = dTeam + nSmall; Q.n = nLarge;
       const int g = nLarge < ctx->numSms * 8 ? nLarge : ctx->numSms * 8;
       tu_eval_kernel<128><<<g, kTuThreads, 0, ctx->stream>>>(Q);
       ctx->launches++;
     }
   };
-  if (nDq || nTs) {
-    CK(cudaMemsetAsync(ctx->dTu[4], 0, n_samples * sizeof(int32_t), ctx->stream));     // levels / dequantised coefficients the
-    CK(cudaMemsetAsync(ctx->dTu[8], 0, n_samples * sizeof(int32_t), ctx->stream));     // quantiser kernels do not reach stay zero
-    if (nDq) CK(cudaMemcpyAsync(ctx->dTu[9], order.data(), (size_t)nDq * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    if (nTs) CK(cudaMemcpyAsync(ctx->dTu[16], tsOrder.data(), (size_t)nTs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dTu[10], rates, (size_t)n_rates * sizeof(vvcb_dq_rates), cudaMemcpyHostToDevice, ctx->stream));
-  }
   if (tm && !src) CK(cudaEventRecord(ctx->tev[0], ctx->stream));
   launch_tu(P);
   if (tm) CK(cudaEventRecord(ctx->tev[1], ctx->stream));
@@ -1025,13 +1118,13 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
     CK(cudaStreamWaitEvent(ctx->sKind[0], ctx->evPlan, 0));
   }
   if (nDq) {
-    dq_rate_kernel<<<n_rates, 32, 0, ctx->stream>>>(static_cast<const vvcb_dq_rates*>(ctx->dTu[10]), n_rates, static_cast<DqRateTab*>(ctx->dTu[11]));
+    dq_rate_kernel<<<n_rates, 32, 0, ctx->stream>>>(dRates, n_rates, static_cast<DqRateTab*>(ctx->dTu[11]));
     DqParams D;
     int* firstRaw = static_cast<int*>(ctx->dTu[13]);
     int* orderSorted = firstRaw + nDq;
     int* firstSorted = firstRaw + 2 * nDq;
     const int firstGrid = (nDq + kDqGroups - 1) / kDqGroups < ctx->numSms * 8 ? (nDq + kDqGroups - 1) / kDqGroups : ctx->numSms * 8;
-    dq_first_kernel<<<firstGrid, kDqThreads, 0, ctx->stream>>>(P.jobs, static_cast<const int*>(ctx->dTu[9]), nDq, P.dqCoeff, ctx->dDqRom, ctx->bd, firstRaw);
+    dq_first_kernel<<<firstGrid, kDqThreads, 0, ctx->stream>>>(P.jobs, dOrder, nDq, P.dqCoeff, ctx->dDqRom, ctx->bd, firstRaw);
     // The counting sort by first test position buys warp efficiency for sweeps (eight TUs per warp walk scans of equal length); a walk's batch
     // of a few dozen candidates is latency bound and skips its three launches.
     const bool sortJobs = nDq > 2048;
@@ -1041,20 +1134,20 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
       CK(cudaMemsetAsync(binCount, 0, kDqBins * sizeof(int), ctx->stream));
       dq_hist_kernel<<<sortGrid, kDqSortThreads, 0, ctx->stream>>>(firstRaw, nDq, binCount);
       dq_scan_kernel<<<1, 32, 0, ctx->stream>>>(binCount);
-      dq_scatter_kernel<<<sortGrid, kDqSortThreads, 0, ctx->stream>>>(static_cast<const int*>(ctx->dTu[9]), firstRaw, nDq, binCount, orderSorted, firstSorted);
+      dq_scatter_kernel<<<sortGrid, kDqSortThreads, 0, ctx->stream>>>(dOrder, firstRaw, nDq, binCount, orderSorted, firstSorted);
       ctx->launches += 3;
     }
-    D.jobs = P.jobs; D.order = sortJobs ? orderSorted : static_cast<const int*>(ctx->dTu[9]); D.firstPos = sortJobs ? firstSorted : firstRaw; D.n = nDq;
-    D.coeff = P.dqCoeff; D.level = P.level; D.deq = static_cast<int32_t*>(ctx->dTu[8]); D.results = P.results;
-    D.rates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]); D.tabs = static_cast<const DqRateTab*>(ctx->dTu[11]);
+    D.jobs = P.jobs; D.order = sortJobs ? orderSorted : dOrder; D.firstPos = sortJobs ? firstSorted : firstRaw; D.n = nDq;
+    D.coeff = P.dqCoeff; D.level = P.level; D.deq = dDeq; D.results = P.results;
+    D.rates = dRates; D.tabs = static_cast<const DqRateTab*>(ctx->dTu[11]);
     D.rom = ctx->dDqRom; D.scratch = static_cast<uint8_t*>(ctx->dTu[12]); D.bd = ctx->bd; D.sparse = !sortJobs;
     dq_kernel<<<dqGrid, kDqThreads, 0, ctx->stream>>>(D);
     ctx->launches += 3;
   }
   if (nTs) {
     RdoqParams R;
-    R.jobs = P.jobs; R.order = static_cast<const int*>(ctx->dTu[16]); R.n = nTs; R.coeff = P.dqCoeff; R.level = P.level;
-    R.deq = static_cast<int32_t*>(ctx->dTu[8]); R.results = P.results; R.rates = static_cast<const vvcb_dq_rates*>(ctx->dTu[10]);
+    R.jobs = P.jobs; R.order = dTsOrder; R.n = nTs; R.coeff = P.dqCoeff; R.level = P.level;
+    R.deq = dDeq; R.results = P.results; R.rates = dRates;
     R.rom = ctx->dDqRom; R.bd = ctx->bd;
     rdoq_ts_kernel<<<std::min((nTs + kTsWarps - 1) / kTsWarps, 16 * ctx->numSms), kTsThreads, 0, tsAside ? ctx->sKind[0] : ctx->stream>>>(R);
     ctx->launches++;
@@ -1070,21 +1163,23 @@ static int tu_eval_impl(vvcb_ctx* ctx, const vvcb_tu_job* jobs, int n, const int
   }
   if (tm) CK(cudaEventRecord(ctx->tev[3], ctx->stream));
   if (nRate) {                                                     // levels are final: price them (CABACWriter::residual_coding on the estimator)
-    CK(cudaMemcpyAsync(ctx->dTu[17], rateOrder.data(), (size_t)nRate * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dTu[18], states, (size_t)n_rates * sizeof(vvcb_ctx_states), cudaMemcpyHostToDevice, ctx->stream));
     RateParams R;
-    R.jobs = P.jobs; R.order = static_cast<const int*>(ctx->dTu[17]); R.n = nRate; R.level = P.level; R.results = P.results;
-    R.states = static_cast<const vvcb_ctx_states*>(ctx->dTu[18]); R.rom = ctx->dDqRom; R.rate = ctx->dRateRom; R.depQuant = ctx->depQuant;
+    R.jobs = P.jobs; R.order = dRateOrder; R.n = nRate; R.level = P.level; R.results = P.results;
+    R.states = dStates; R.rom = ctx->dDqRom; R.rate = ctx->dRateRom; R.depQuant = ctx->depQuant;
     rate_kernel<<<std::min((nRate + kRateWarps - 1) / kRateWarps, 16 * ctx->numSms), kRateThreads, 0, ctx->stream>>>(R);
     ctx->launches++;
   }
   if (tm) CK(cudaEventRecord(ctx->tev[4], ctx->stream));
   CK(cudaGetLastError());
   if (coeff) CK(cudaMemcpyAsync(coeff, ctx->dTu[3], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (level) CK(cudaMemcpyAsync(level, ctx->dTu[4], n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (reco) CK(cudaMemcpyAsync(reco, ctx->dTu[5], n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (pred_out) CK(cudaMemcpyAsync(pred_out, ctx->dTu[2], n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(results, ctx->dTu[6], (size_t)n * sizeof(vvcb_tu_result), cudaMemcpyDeviceToHost, ctx->stream));
+  if (walk) CK(arena_copy(ctx, ctx->dTu[21], ctx->hPin[8], outBytes));
+  else {
+    if (level) CK(cudaMemcpyAsync(level, dLevel, n_samples * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (reco) CK(cudaMemcpyAsync(reco, dRecoBuf, n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pred_out) CK(cudaMemcpyAsync(pred_out, dPredBuf, n_samples * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(results, dResults, (size_t)n * sizeof(vvcb_tu_result), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (ctx->cuSpan) CK(cudaEventRecord(ctx->cev[3], ctx->stream));
   ctx->tuWaitFrom = host_ns();
   CK(ctx_sync(ctx));
   if (tm) {
@@ -1159,40 +1254,55 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
   int rc;
   uint64_t tPhase = host_ns();
   auto phase = [&](int k) { const uint64_t now = host_ns(); ctx->cuNs[k] += now - tPhase; tPhase = now; };
-  // ---- reconstruction rectangles ----
-  if (nRects) {
-    if ((rc = pin_buf(ctx, 0, nRects * sizeof(vvcb_rect)))) return rc;
-    if ((rc = pin_buf(ctx, 1, nRectSamples * sizeof(int16_t)))) return rc;
-    vvcb_rect* hr = static_cast<vvcb_rect*>(ctx->hPin[0]);
-    int16_t* hs = static_cast<int16_t*>(ctx->hPin[1]);
+  ctx->cuSpan = true;
+  CK(cudaEventRecord(ctx->cev[0], ctx->stream));
+  // ---- inputs of the first stage: rectangles | their samples | visits, one page-locked arena, moved by a copy kernel (see TuWalk) ----
+  auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  const size_t iSmp = up16(nRects * sizeof(vvcb_rect)), iVis = iSmp + up16(nRectSamples * sizeof(int16_t)), inBytes = iVis + up16((size_t)nRmd * sizeof(vvcb_rmd_visit));
+  vvcb_rmd_result* hRes = nullptr; vvcb_rmd_detail* hDet = nullptr;
+  if (inBytes) {
+    if ((rc = pin_buf(ctx, 0, inBytes))) return rc;
+    if ((rc = tu_buf(ctx, 22, inBytes))) return rc;
+    uint8_t* hin = static_cast<uint8_t*>(ctx->hPin[0]);
+    uint8_t* din = static_cast<uint8_t*>(ctx->dTu[22]);
+    vvcb_rect* hr = reinterpret_cast<vvcb_rect*>(hin);
+    int16_t* hs = reinterpret_cast<int16_t*>(hin + iSmp);
+    vvcb_rmd_visit* hv = reinterpret_cast<vvcb_rmd_visit*>(hin + iVis);
     size_t ri = 0, so = 0;
+    int vi = 0;
     for (int i = 0; i < n; i++) {
       const vvcb_cu_request& q = reqs[i];
+      if (q.want_rmd) hv[vi++] = *q.visit;
       if (!q.n_rects) continue;
       for (int k = 0; k < q.n_rects; k++) { hr[ri] = q.rects[k]; hr[ri].offset += (uint32_t)so; ri++; }
       memcpy(hs + so, q.rect_samples, q.n_rect_samples * sizeof(int16_t));
       so += q.n_rect_samples;
     }
-    if ((rc = launch_reco_rects(ctx, hr, (int)nRects, hs, nRectSamples))) return rc;
+    if (nRmd && (rc = check_visits(ctx, hv, nRmd))) return rc;
+    CK(arena_copy(ctx, hin, din, inBytes));
+    // ---- reconstruction rectangles ----
+    if (nRects) {
+      reco_scatter_kernel<<<(int)nRects < ctx->numSms * 8 ? (int)nRects : ctx->numSms * 8, 128, 0, ctx->stream>>>(reinterpret_cast<const vvcb_rect*>(din), (int)nRects,
+                                                                                                          reinterpret_cast<const int16_t*>(din + iSmp), ctx->wReco, ctx->stride);
+      ctx->launches++;
+      CK(cudaGetLastError());
+    }
+    // ---- rough mode decision ----
+    if (nRmd) {
+      const size_t oDet = up16((size_t)nRmd * sizeof(vvcb_rmd_result)), outBytes = oDet + (anyDetail ? (size_t)nRmd * sizeof(vvcb_rmd_detail) : 0);
+      if ((rc = tu_buf(ctx, 23, outBytes))) return rc;
+      if ((rc = pin_buf(ctx, 3, outBytes))) return rc;
+      uint8_t* dout = static_cast<uint8_t*>(ctx->dTu[23]);
+      uint8_t* hout = static_cast<uint8_t*>(ctx->hPin[3]);
+      hRes = reinterpret_cast<vvcb_rmd_result*>(hout);
+      hDet = anyDetail ? reinterpret_cast<vvcb_rmd_detail*>(hout + oDet) : nullptr;
+      if ((rc = launch_rmd(ctx, reinterpret_cast<const vvcb_rmd_visit*>(din + iVis), nRmd, reinterpret_cast<vvcb_rmd_result*>(dout),
+                           anyDetail ? reinterpret_cast<vvcb_rmd_detail*>(dout + oDet) : nullptr, nullptr, hv))) return rc;
+      CK(arena_copy(ctx, dout, hout, outBytes));
+    }
   }
-  // ---- rough mode decision ----
-  vvcb_rmd_result* hRes = nullptr; vvcb_rmd_detail* hDet = nullptr;
   if (nRmd) {
-    if ((rc = pin_buf(ctx, 2, (size_t)nRmd * sizeof(vvcb_rmd_visit)))) return rc;
-    if ((rc = pin_buf(ctx, 3, (size_t)nRmd * sizeof(vvcb_rmd_result)))) return rc;
-    if (anyDetail && (rc = pin_buf(ctx, 4, (size_t)nRmd * sizeof(vvcb_rmd_detail)))) return rc;
-    vvcb_rmd_visit* hv = static_cast<vvcb_rmd_visit*>(ctx->hPin[2]);
-    hRes = static_cast<vvcb_rmd_result*>(ctx->hPin[3]);
-    hDet = anyDetail ? static_cast<vvcb_rmd_detail*>(ctx->hPin[4]) : nullptr;
-    int vi = 0;
-    for (int i = 0; i < n; i++) if (reqs[i].want_rmd) hv[vi++] = *reqs[i].visit;
-    if ((rc = check_visits(ctx, hv, nRmd))) return rc;
-    if ((rc = ensure_visit_buffers(ctx, nRmd))) return rc;
-    if (anyDetail && (rc = ensure_details(ctx, nRmd))) return rc;
-    CK(cudaMemcpyAsync(ctx->dVisits, hv, (size_t)nRmd * sizeof(vvcb_rmd_visit), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = launch_rmd(ctx, ctx->dVisits, nRmd, ctx->dResults, anyDetail ? ctx->dDetails : nullptr, nullptr, hv))) return rc;
-    CK(cudaMemcpyAsync(hRes, ctx->dResults, (size_t)nRmd * sizeof(vvcb_rmd_result), cudaMemcpyDeviceToHost, ctx->stream));
-    if (anyDetail) CK(cudaMemcpyAsync(hDet, ctx->dDetails, (size_t)nRmd * sizeof(vvcb_rmd_detail), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->cev[1], ctx->stream));
     phase(0);
     if (anyAuto) { CK(ctx_sync(ctx)); phase(1); }      // the templates are expanded from these lists
   }
@@ -1216,16 +1326,14 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
     }
   }
   int32_t* hLevel = nullptr; int16_t* hReco = nullptr; int16_t* hPred = nullptr;
-  std::vector<vvcb_tu_result> tuRes;
+  vvcb_tu_result* tuRes = nullptr;
   if (nJobs) {
-    bool wantLevel = false, wantReco = false, wantPred = false;
+    TuWalk walk = {};
     for (const Group& g : groups) {
       const vvcb_cu_request& q = reqs[g.req];
-      wantLevel = wantLevel || (g.autos ? q.auto_level : q.level); wantReco = wantReco || (g.autos ? q.auto_reco : q.reco); wantPred = wantPred || (g.autos ? q.auto_pred : q.pred);
+      walk.wantLevel = walk.wantLevel || (g.autos ? q.auto_level : q.level); walk.wantReco = walk.wantReco || (g.autos ? q.auto_reco : q.reco);
+      walk.wantPred = walk.wantPred || (g.autos ? q.auto_pred : q.pred);
     }
-    if (wantLevel) { if ((rc = pin_buf(ctx, 5, nSamples * sizeof(int32_t)))) return rc; hLevel = static_cast<int32_t*>(ctx->hPin[5]); }
-    if (wantReco)  { if ((rc = pin_buf(ctx, 6, nSamples * sizeof(int16_t)))) return rc; hReco = static_cast<int16_t*>(ctx->hPin[6]); }
-    if (wantPred)  { if ((rc = pin_buf(ctx, 7, nSamples * sizeof(int16_t)))) return rc; hPred = static_cast<int16_t*>(ctx->hPin[7]); }
     const int nGroups = (int)groups.size();
     if (nGroups > 65535) { snprintf(ctx->err, sizeof(ctx->err), "vvcb_cu_eval: more than 65535 TU groups in one call"); return VVCB_ERR_ARG; }
     std::vector<vvcb_rmd_visit> tv(nGroups);
@@ -1233,7 +1341,6 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
     std::vector<vvcb_ctx_states> states(nGroups);
     std::vector<vvcb_tu_job> jobs(nJobs);
     std::vector<vvcb_tu_src> src(nJobs);
-    tuRes.resize(nJobs);
     size_t ji = 0, so = 0;
     for (int gi = 0; gi < nGroups; gi++) {
       const Group& g = groups[gi];
@@ -1248,9 +1355,13 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
       so += (size_t)g.n << (q.visit->log2w + q.visit->log2h);
     }
     phase(2);
-    rc = tu_eval_impl(ctx, jobs.data(), (int)nJobs, nullptr, nullptr, nSamples, rates.data(), states.data(), nGroups, nullptr, hLevel, hReco, tuRes.data(),
-                      tv.data(), nGroups, src.data(), hPred);
+    CK(cudaEventRecord(ctx->cev[2], ctx->stream));
+    rc = tu_eval_impl(ctx, jobs.data(), (int)nJobs, nullptr, nullptr, nSamples, rates.data(), states.data(), nGroups, nullptr, nullptr, nullptr, nullptr,
+                      tv.data(), nGroups, src.data(), nullptr, &walk);
+    tuRes = walk.results; hLevel = walk.level; hReco = walk.reco; hPred = walk.pred;
+    ctx->cuSpan = false;
     if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+    { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->cev[2], ctx->cev[3]) == cudaSuccess) ctx->cuNs[7] += (uint64_t)(ms * 1e6f); }
     { const uint64_t now = host_ns(); ctx->cuNs[3] += ctx->tuWaitFrom - tPhase; ctx->cuNs[4] += now - ctx->tuWaitFrom; tPhase = now; }
   } else { phase(2); CK(ctx_sync(ctx)); phase(4); }
   // ---- hand the outputs back ----
@@ -1268,19 +1379,21 @@ extern "C" int vvcb_cu_eval(vvcb_ctx* ctx, vvcb_cu_request* reqs, int n)
       if (lv) memcpy(lv, hLevel + so, ns * sizeof(int32_t));
       if (rc16) memcpy(rc16, hReco + so, ns * sizeof(int16_t));
       if (pr) memcpy(pr, hPred + so, ns * sizeof(int16_t));
-      memcpy(g.autos ? q.auto_results : q.tu_results, &tuRes[ji], (size_t)g.n * sizeof(vvcb_tu_result));
+      memcpy(g.autos ? q.auto_results : q.tu_results, tuRes + ji, (size_t)g.n * sizeof(vvcb_tu_result));
       so += ns; ji += (size_t)g.n;
     }
   }
   phase(5);
+  ctx->cuSpan = false;
+  if (nRmd) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->cev[0], ctx->cev[1]) == cudaSuccess) ctx->cuNs[6] += (uint64_t)(ms * 1e6f); }
   ctx->cuCalls++;
   return VVCB_OK;
 }
 
-extern "C" int vvcb_cu_eval_phases(const vvcb_ctx* ctx, uint64_t ns[6], uint64_t* calls)
+extern "C" int vvcb_cu_eval_phases(const vvcb_ctx* ctx, uint64_t ns[8], uint64_t* calls)
 {
   if (!ctx || !ns) return VVCB_ERR_ARG;
-  for (int i = 0; i < 6; i++) ns[i] = ctx->cuNs[i];
+  for (int i = 0; i < 8; i++) ns[i] = ctx->cuNs[i];
   if (calls) *calls = ctx->cuCalls;
   return VVCB_OK;
 }

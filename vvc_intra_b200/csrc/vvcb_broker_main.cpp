@@ -18,10 +18,10 @@ int main(int argc, char** argv)
       vvcb_broker_stats s;
       if (vvcb_broker_read_stats(path, &s) != VVCB_OK) return 1;
       printf("{\"cycles\": %llu, \"requests\": %llu, \"cu_requests\": %llu, \"visits\": %llu, \"tu_jobs\": %llu, \"max_batch\": %llu, \"busy_ns\": %llu, \"wall_ns\": %llu, "
-             "\"clients_seen\": %llu, \"kernel_launches\": %llu, \"phase_ns\": [%llu, %llu, %llu, %llu, %llu, %llu]}\n",
+             "\"clients_seen\": %llu, \"kernel_launches\": %llu, \"phase_ns\": [%llu, %llu, %llu, %llu, %llu, %llu, %llu, %llu]}\n",
              (unsigned long long)s.cycles, (unsigned long long)s.requests, (unsigned long long)s.cu_requests, (unsigned long long)s.visits, (unsigned long long)s.tu_jobs,
              (unsigned long long)s.max_batch, (unsigned long long)s.busy_ns, (unsigned long long)s.wall_ns, (unsigned long long)s.clients_seen, (unsigned long long)s.kernel_launches,
-             (unsigned long long)s.phase_ns[0], (unsigned long long)s.phase_ns[1], (unsigned long long)s.phase_ns[2], (unsigned long long)s.phase_ns[3], (unsigned long long)s.phase_ns[4], (unsigned long long)s.phase_ns[5]);
+             (unsigned long long)s.phase_ns[0], (unsigned long long)s.phase_ns[1], (unsigned long long)s.phase_ns[2], (unsigned long long)s.phase_ns[3], (unsigned long long)s.phase_ns[4], (unsigned long long)s.phase_ns[5], (unsigned long long)s.phase_ns[6], (unsigned long long)s.phase_ns[7]);
       return 0;
     }
     if (i + 1 >= argc) { fprintf(stderr, "vvcb_broker: %s needs a value\n", argv[i]); return 2; }
