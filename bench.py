@@ -502,8 +502,10 @@ def bitexact_leg(frames, device):
     if not all(os.path.exists(p) for p in (plain, served, cfg, broker)):
         return {'unavailable': 'oracle/_ref/EncoderAppServe or vvc_intra_b200/vvcb_broker was not built (run __graft_entry__.build() in the container that has /root/reference)'}
     cores = max(1, min(os.cpu_count() or 1, 64))
-    over = max(1, int(os.environ.get('VVCB_BENCH_OVERSUBSCRIBE', '8')))
-    workers = max(1, int(os.environ.get('VVCB_BENCH_WORKERS', '8')))
+    # walkers per host core and broker worker threads: the setting that measured best (profiles/r2_bitexact_scaling.json) -- the walkers'
+    # own CPU time bounds the leg from 256 walkers on 16 cores on, and two workers keep the batches large (about 30 CUs each)
+    over = max(1, int(os.environ.get('VVCB_BENCH_OVERSUBSCRIBE', '16')))
+    workers = max(1, int(os.environ.get('VVCB_BENCH_WORKERS', '2')))
     n = cores * over
     # the plain encoder runs on a bounded share of the same crops (its rate does not depend on how many there are); those are the
     # bitstreams the served ones are compared with
