@@ -134,6 +134,10 @@ struct PendingTu { const TransformUnit* tu = nullptr; TuEntry* e = nullptr; cons
 struct Tm { long long ns = 0; };
 struct Scope { Tm& t; std::chrono::steady_clock::time_point t0; Scope(Tm& x) : t(x), t0(std::chrono::steady_clock::now()) {} ~Scope() { t.ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); } };
 Tm g_tEst, g_tPre, g_tWrap;
+// the served wrappers run a few million times per CTU: their own time is only clocked on request (two clock reads per call were 8 % of a walker's CPU time)
+const bool g_wrapTimed = getenv("VVCB_SHIM_TIMES") != nullptr;
+struct WrapScope { long long t0; WrapScope() : t0(g_wrapTimed ? std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() : 0) {}
+                   ~WrapScope() { if (g_wrapTimed) g_tWrap.ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0; } };
 Tm g_prof[8][3];      // VVCB_SHIM_PROFILE=1: time inside the REAL functions by [family][luma whole-CU, luma ISP, chroma]
 const bool g_profile = getenv("VVCB_SHIM_PROFILE") != nullptr;
 const char* kFamily[8] = { "ref_fetch", "predict", "dist_param", "tr_presel", "tr_quant", "inv_tr", "sse", "resid_bits" };
@@ -701,7 +705,7 @@ void __wrap__ZN15IntraPrediction12initIntraMipERK14PredictionUnit(IntraPredictio
 
 static void servePrediction(PelBuf& pred, const PredictionUnit& pu, bool mip)
 {
-  Scope sc(g_tWrap);
+  WrapScope sc;
   const int slot = slotOf(pu, mip);
   if (!slotEvaluated(g_cu, slot)) die("prediction asked for a mode that is not an evaluation slot of the visit");
   if (g_inRmd) { g_curSlot = slot; g_st.predSkipped++; return; }        // only its SAD / SATD are read (setDistParam wrapper)
@@ -755,7 +759,7 @@ void __wrap__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamP
     __real__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamPSt6vectorISt4pairIibESaISA_EEi(tq, tu, c, qp, modes, maxCand);
     return;
   }
-  Scope sc(g_tWrap);
+  WrapScope sc;
   const int k = (int)modes->size();
   std::vector<int32_t> sums(k);
   std::vector<uint8_t> sel(k);
@@ -777,7 +781,7 @@ void __wrap__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamR
     __real__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamRiRK3Ctxb(tq, tu, c, qp, absSum, ctx, loadTr);
     return;
   }
-  Scope sc(g_tWrap);
+  WrapScope sc;
   const bool ts = tu.mtsIdx == MTS_SKIP;
   TuEntry& e = entryFor(tu, ctx, tu.mtsIdx, false);
   if (e.job.qp_per != qp.per(ts) || e.job.qp_rem != qp.rem(ts) || e.job.lambda != tq->m_quant->getLambda()) die("QP / lambda of the TU differ from the ones its candidate was computed with");
@@ -797,7 +801,7 @@ void __wrap__ZN7TrQuant15invTransformNxNER13TransformUnitRK11ComponentIDR7AreaBu
     __real__ZN7TrQuant15invTransformNxNER13TransformUnitRK11ComponentIDR7AreaBufIsERK7QpParam(tq, tu, c, resi, qp);
     return;
   }
-  Scope sc(g_tWrap);
+  WrapScope sc;
   const std::vector<int16_t>& pred = g_cu.pred[g_pend.e->slot];
   for (int y = 0; y < g_cu.h; y++)
     for (int x = 0; x < g_cu.w; x++) resi.at(x, y) = g_pend.e->reco[(size_t)y * g_cu.w + x] - pred[(size_t)y * g_cu.w + x];   // PelBuf::reconstruct clips pred + resi back to reco
@@ -822,7 +826,7 @@ Distortion __wrap__ZN6RdCost11getDistPartERK7AreaBufIKsES4_i11ComponentID5DFuncP
 void __wrap__ZN11CABACWriter15residual_codingERK13TransformUnit11ComponentIDP5CUCtx(CABACWriter* cw, const TransformUnit& tu, ComponentID c, CUCtx* cuCtx)
 {
   if (g_inEst && c == COMPONENT_Y && g_pend.tu == &tu && g_pend.e && !cw->m_BinEncoder.isEncoding() && cw == g_is->m_CABACEstimator) {
-    Scope sc(g_tWrap);
+    WrapScope sc;
     uint64_t stateHash = g_entrySnap.stateHash;
     if (!sameAsEntryCtx(cw->getCtx())) { vvcb_ctx_states st; fillStates(st, cw->getCtx()); stateHash = mix(&st, sizeof(st)); }
     if (stateHash == g_pend.e->stateHash) {
