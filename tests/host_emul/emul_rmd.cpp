@@ -89,7 +89,7 @@ extern "C" int emul_rmd_brief(const vvcb_rmd_visit* visits, int n, int ctu, cons
 {
   std::vector<uint32_t> sm((size_t)2 * VVCB_NUM_SLOTS * n);
   for (int i = 0; i < n; i++)
-    for (int s = 0; s < VVCB_NUM_SLOTS; s++) { sm[(size_t)s * n + i] = details[i].sad[s]; sm[(size_t)(VVCB_NUM_SLOTS + s) * n + i] = details[i].satd[s]; }
+    for (int s = 0; s < VVCB_NUM_SLOTS; s++) { sm[scratch_at(s, (unsigned)i, n)] = details[i].sad[s]; sm[(size_t)VVCB_NUM_SLOTS * n + scratch_at(s, (unsigned)i, n)] = details[i].satd[s]; }
   emu_launch((n + kListThreads - 1) / kListThreads, kListThreads, [&] { rmd_lists_kernel(visits, n, ctu, nullptr, nullptr, sm.data(), sm.data() + (size_t)VVCB_NUM_SLOTS * n, brief); });
   return 0;
 }

@@ -75,7 +75,7 @@ struct vvcb_ctx {
   // scratch for the host-pointer API
   vvcb_rmd_visit* dVisits; vvcb_rmd_result* dResults; size_t capVisits;
   vvcb_rmd_detail* dDetails; size_t capDetails;
-  uint32_t* dSlotMajor; size_t capSlotMajor;   // [2][VVCB_NUM_SLOTS][n] SAD / SATD scratch
+  uint32_t* dScratch; size_t capScratch;   // SAD / SATD scratch: two planes of n * VVCB_NUM_SLOTS words, visit-major (scratch_at, vvcb_rmd.cuh)
   WorkItem* dItems; size_t capItems;
   PlanState* dPlan;
   int16_t* dPred; size_t capPred;
@@ -229,7 +229,7 @@ extern "C" void vvcb_destroy(vvcb_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 10; i++) if (ctx->hPin[i]) cudaFreeHost(ctx->hPin[i]);
   cudaFree(ctx->dRect[0]); cudaFree(ctx->dRect[1]); cudaFree(ctx->dBrief);
-  cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dSlotMajor);
+  cudaFree(ctx->dRom); cudaFree(ctx->dOrig); cudaFree(ctx->dReco); cudaFree(ctx->dVisits); cudaFree(ctx->dResults); cudaFree(ctx->dDetails); cudaFree(ctx->dScratch);
   cudaFree(ctx->dItems); cudaFree(ctx->dPlan); cudaFree(ctx->dPred); cudaFree(ctx->dTrRom);
   for (int i = 0; i < 24; i++) cudaFree(ctx->dTu[i]);
   cudaFree(ctx->dRateRom);
@@ -522,10 +522,10 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   if (n == 0) return VVCB_OK;
   int rc = ensure_items(ctx, n);
   if (rc) return rc;
-  if ((size_t)n > ctx->capSlotMajor) {
-    cudaFree(ctx->dSlotMajor); ctx->dSlotMajor = nullptr; ctx->capSlotMajor = 0;
-    CK(cudaMalloc(&ctx->dSlotMajor, (size_t)n * 2 * VVCB_NUM_SLOTS * sizeof(uint32_t)));
-    ctx->capSlotMajor = (size_t)n;
+  if ((size_t)n > ctx->capScratch) {
+    cudaFree(ctx->dScratch); ctx->dScratch = nullptr; ctx->capScratch = 0;
+    CK(cudaMalloc(&ctx->dScratch, (size_t)n * 2 * VVCB_NUM_SLOTS * sizeof(uint32_t)));
+    ctx->capScratch = (size_t)n;
   }
   CK(cudaMemsetAsync(ctx->dPlan, 0, sizeof(PlanState), ctx->stream));
   const bool tm = ctx->timing != 0;
@@ -549,7 +549,7 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   EvalParams P;
   P.visits = dVisits; P.items = ctx->dItems; P.plan = ctx->dPlan;
   // without detail tables the lists only need min(2 * SAD, SATD): one scratch plane instead of two
-  P.sadSM = ctx->dSlotMajor; P.satdSM = (dDetails || dPred) ? ctx->dSlotMajor + (size_t)VVCB_NUM_SLOTS * n : nullptr; P.nVisits = n;
+  P.sadSM = ctx->dScratch; P.satdSM = (dDetails || dPred) ? ctx->dScratch + (size_t)VVCB_NUM_SLOTS * n : nullptr; P.nVisits = n;
   P.orig = ctx->bOrig; P.reco = ctx->bReco; P.stride = ctx->stride; P.bd = ctx->bd; P.ctu = ctx->ctu; P.rom = ctx->dRom;
   P.predOut = dPred;
   const long long maxWarps = (long long)n * 8;          // no point in more warps than work items

@@ -75,11 +75,29 @@ struct PlanState {                        // device-resident, zeroed before ever
   unsigned cursor[kNumBucketsAll];        // ... and consume cursor (eval)
 };
 
+// Position of (slot, visit) in the SAD / SATD scratch planes the evaluation kernels hand to the list kernel.  Visit-major: the ~100 values
+// of a visit are written by one warp within a few microseconds into 448 contiguous bytes, so the partial-sector writes merge in L2 and most of the
+// plane is still there when the list kernel reads it.  The slot-major layout of round 1 (coalesced for the list kernel, one thread per visit)
+// scattered every store into a sector of its own: 2.10 GB of DRAM traffic per 1080p sweep against 0.68 GB now, list kernel 1.10 -> 1.02 ms
+// (tools/scratch_layout_ab.sh, profiles/r2_summary.md).  VVCB_SCRATCH_VISIT_MAJOR=0 keeps the old layout for A/B builds.
+#ifndef VVCB_SCRATCH_VISIT_MAJOR
+#define VVCB_SCRATCH_VISIT_MAJOR 1
+#endif
+__host__ __device__ __forceinline__ size_t scratch_at(int slot, unsigned visit, int nVisits)
+{
+#if VVCB_SCRATCH_VISIT_MAJOR
+  (void)nVisits;
+  return (size_t)visit * VVCB_NUM_SLOTS + (size_t)slot;
+#else
+  return (size_t)slot * (size_t)nVisits + visit;
+#endif
+}
+
 struct EvalParams {
   const vvcb_rmd_visit* visits;
   const WorkItem*       items;
   PlanState*            plan;
-  uint32_t*             sadSM;    // slot-major scratch: sadSM[slot * nVisits + visit] (coalesced for the list kernel)
+  uint32_t*             sadSM;    // scratch plane, indexed by scratch_at(slot, visit, nVisits)
   uint32_t*             satdSM;   // nullptr: only min(2 * SAD, SATD) is handed over, in sadSM (no detail tables were asked for: the lists need nothing else)
   int                   nVisits;
   const int16_t*        orig;
@@ -690,8 +708,7 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
       }
       const vvcb_rmd_visit& v = sVisit[warp][vi];
       const SM& sm = smem[warp][vi];
-      uint32_t* sadOut  = P.sadSM + sIndex[warp][vi];
-      uint32_t* satdOut = P.satdSM ? P.satdSM + sIndex[warp][vi] : nullptr;
+      const unsigned vIdx = sIndex[warp][vi];
       const int16_t* org = P.orig + (size_t)v.y * P.stride + v.x;
       const int u = tk & (lanes - 1);
       const int slot = kind_slot(rom, v, KIND, (PACK ? 0 : item.slot_begin) + (tk >> sh.lgLanes));
@@ -815,8 +832,9 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
           satd += __shfl_xor_sync(0xffffffffu, satd, o);
         }
         if (act && gl == 0) {
-          if (P.satdSM) { sadOut[(size_t)slot * P.nVisits] = (uint32_t)sad; satdOut[(size_t)slot * P.nVisits] = (uint32_t)satd; }
-          else sadOut[(size_t)slot * P.nVisits] = (uint32_t)vmin(2 * sad, satd);                     // EL/IntraSearch.cpp:515
+          const size_t at = scratch_at(slot, vIdx, P.nVisits);
+          if (P.satdSM) { P.sadSM[at] = (uint32_t)sad; P.satdSM[at] = (uint32_t)satd; }
+          else P.sadSM[at] = (uint32_t)vmin(2 * sad, satd);                                          // EL/IntraSearch.cpp:515
         }
       } else {
         // 64 lanes per slot: two consecutive warp iterations belong to the same slot
@@ -827,8 +845,9 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
             accSatd += __shfl_xor_sync(0xffffffffu, accSatd, o);
           }
           if (lane == 0) {
-            if (P.satdSM) { sadOut[(size_t)slot * P.nVisits] = (uint32_t)accSad; satdOut[(size_t)slot * P.nVisits] = (uint32_t)accSatd; }
-            else sadOut[(size_t)slot * P.nVisits] = (uint32_t)vmin(2 * accSad, accSatd);
+            const size_t at = scratch_at(slot, vIdx, P.nVisits);
+            if (P.satdSM) { P.sadSM[at] = (uint32_t)accSad; P.satdSM[at] = (uint32_t)accSatd; }
+            else P.sadSM[at] = (uint32_t)vmin(2 * accSad, accSatd);
           }
           accSad = 0; accSatd = 0;
         }
@@ -944,8 +963,8 @@ __constant__ uint8_t cFastModes[6][6] = {
 
 constexpr int kListThreads = 128;
 
-// Slot-major scratch -> per-visit detail tables (only when the caller asked for details): a shared-memory tile
-// transpose so that both the reads (fixed slot, consecutive visits) and the writes (one visit's row) are coalesced.
+// Scratch planes -> per-visit detail tables (only when the caller asked for details), through a shared-memory tile (written for the
+// slot-major layout, where it was a transpose; with the visit-major planes it is a staged copy that fills the slots never evaluated).
 __global__ void __launch_bounds__(256) rmd_detail_kernel(const vvcb_rmd_visit* visits, int n, int ctu, vvcb_rmd_detail* details,
                                                          const uint32_t* sadSM, const uint32_t* satdSM)
 {
@@ -959,8 +978,8 @@ __global__ void __launch_bounds__(256) rmd_detail_kernel(const vvcb_rmd_visit* v
     const int numMip = visit_num_mip(v);
     for (int s = wrp; s < VVCB_NUM_SLOTS; s += 8) {
       const bool evaluated = s < VVCB_SLOT_MRL1 || (s < VVCB_SLOT_MIP ? mrlAllowed : s - VVCB_SLOT_MIP < numMip);
-      tile[lane][s] = evaluated ? sadSM[(size_t)s * n + vi] : VVCB_SAT_NONE;
-      tile[lane][VVCB_NUM_SLOTS + s] = evaluated ? satdSM[(size_t)s * n + vi] : VVCB_SAT_NONE;
+      tile[lane][s] = evaluated ? sadSM[scratch_at(s, (unsigned)vi, n)] : VVCB_SAT_NONE;
+      tile[lane][VVCB_NUM_SLOTS + s] = evaluated ? satdSM[scratch_at(s, (unsigned)vi, n)] : VVCB_SAT_NONE;
     }
   }
   __syncthreads();
@@ -1069,13 +1088,14 @@ __global__ void __launch_bounds__(kListThreads, VVCB_LIST_MIN_CTAS) rmd_lists_ke
     const int numMip = visit_num_mip(v);
     const bool testMip = numMip > 0;
     const bool mrlAllowed = visit_mrl_allowed(v, ctu);
-    const uint32_t* mySad = sadSM + vi;
-    const uint32_t* mySatd = satdSM ? satdSM + vi : nullptr;        // nullptr: sadSM already holds min(2 * SAD, SATD)
+    const uint32_t* mySad = sadSM;
+    const uint32_t* mySatd = satdSM;                                // nullptr: sadSM already holds min(2 * SAD, SATD)
     vvcb_rmd_detail* D = details ? details + vi : nullptr;
 
     auto dist_of = [&](int slot) -> double {
-      if (!mySatd) return (double)mySad[(size_t)slot * n];
-      const uint64_t sad = mySad[(size_t)slot * n], satd = mySatd[(size_t)slot * n];
+      const size_t at = scratch_at(slot, (unsigned)vi, n);
+      if (!mySatd) return (double)mySad[at];
+      const uint64_t sad = mySad[at], satd = mySatd[at];
       return (double)(sad * 2 < satd ? sad * 2 : satd);                        // :515
     };
     auto cost_of = [&](double dist, bool isMip, int mrl, int mode) -> double {
