@@ -684,7 +684,16 @@ def test_cu_eval_merges_independent_requests(bd, seed, eng8, eng10):
                 reqs[-1]['jobs']['offset'] = np.arange(len(keep)) * w * h
             expect.append((res[vi], det[vi], [items[i] for i in keep]))
     order = rng.permutation(len(reqs))
+    ns0, calls0 = eng.cu_eval_phases()
     outs = eng.cu_eval([reqs[i] for i in order])
+    ns1, calls1 = eng.cu_eval_phases()
+    assert calls1 == calls0 + 1 and all(b >= a for a, b in zip(ns0, ns1)) and ns1[6] > ns0[6] and ns1[7] > ns0[7]      # both device spans were clocked
+    # the same batch with the timed-sleep wait (what the broker's workers use) and with the blocking event: identical bytes
+    for mode in (20, 1, 0):
+        eng.set_option(vb.OPT_YIELD_SYNC, mode)
+        again = eng.cu_eval([reqs[i] for i in order])
+        for a, b in zip(outs, again):
+            assert sorted(a.keys()) == sorted(b.keys()) and all(np.asarray(a[k]).tobytes() == np.asarray(b[k]).tobytes() for k in a)
     n_rmd = n_tu = 0
     for o, i in zip(outs, order):
         res, det, its = expect[i]

@@ -137,6 +137,7 @@ def load_library():
         L.vvcb_kernel_timing.argtypes = [C.c_void_p, C.c_int]
         L.vvcb_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.vvcb_tu_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.vvcb_cu_eval_phases.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.vvcb_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.vvcb_frame_alloc.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.vvcb_reco_from_orig.argtypes = [C.c_void_p]
@@ -187,6 +188,12 @@ class IntraCostEngine:
     def _ck(self, rc):
         if rc != 0:
             raise EngineError('%s (status %d)' % (self._lib.vvcb_last_error(self._ctx).decode(), rc))
+
+    def cu_eval_phases(self):
+        """vvcb_cu_eval_phases: (ns[8], calls) -- cumulative host nanoseconds of the six phases of vvcb_cu_eval and the device spans of its two stages."""
+        ns, calls = (C.c_uint64 * 8)(), C.c_uint64(0)
+        self._ck(self._lib.vvcb_cu_eval_phases(self._ctx, ns, C.byref(calls)))
+        return [int(x) for x in ns], int(calls.value)
 
     def set_option(self, option, value):
         self._ck(self._lib.vvcb_set_option(self._ctx, option, value))
