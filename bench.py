@@ -487,8 +487,9 @@ def write_crop(d, frames, k):
 
 
 def encoder_cmd(enc, cfg, qp, out):
+    # VVCB_BENCH_ENCODER_ARGS: extra reference-encoder options for side experiments (both arms get them), e.g. "--ALF=0"
     return [enc, '-c', cfg, '-i', 'in.yuv', '-wdt', str(CTU), '-hgt', str(CTU), '-q', str(qp), '-f', '1', '-fr', '30', '-b', out,
-            '--InputBitDepth=10', '--InternalBitDepth=10', '--OutputBitDepth=10']
+            '--InputBitDepth=10', '--InternalBitDepth=10', '--OutputBitDepth=10'] + os.environ.get('VVCB_BENCH_ENCODER_ARGS', '').split()
 
 
 def bitexact_leg(frames, device):
