@@ -91,8 +91,10 @@ namespace {
 struct TuEntry {
   vvcb_tu_job    job;
   vvcb_tu_result res;
-  std::vector<int32_t> level;
-  std::vector<int16_t> reco;
+  std::vector<int32_t> level;               // own storage (candidates fetched one by one); the first-pass prefetch leaves its blocks in
+  std::vector<int16_t> reco;                //   the shim's reusable arrays and only sets the pointers
+  const int32_t* lv = nullptr;              // the levels / the reconstruction of this candidate, w * h each
+  const int16_t* rc = nullptr;
   uint64_t rateHash = 0, stateHash = 0;     // context snapshot the levels / the bits were computed with
   int      slot = 0;
 };
@@ -385,6 +387,7 @@ void fetch(CuCache& cu, bool wantRmd, const std::vector<TuSpec>& specs, const Sn
     e.job = jobs[i]; e.res = res[i]; e.slot = need[i].slot;
     e.level.assign(level.begin() + (size_t)i * bs, level.begin() + (size_t)(i + 1) * bs);
     e.reco.assign(reco.begin() + (size_t)i * bs, reco.begin() + (size_t)(i + 1) * bs);
+    e.lv = e.level.data(); e.rc = e.reco.data();
     e.rateHash = s.rateHash; e.stateHash = s.stateHash;
     std::vector<int16_t>& p = cu.pred[need[i].slot];
     if (p.empty()) p.assign(pred.begin() + (size_t)i * bs, pred.begin() + (size_t)(i + 1) * bs);
@@ -410,8 +413,10 @@ void fetchFirstPass(CuCache& cu, const Snapshot& s, bool tsAllowed, bool mtsAllo
     autos[i].modes = tm[i].modes; autos[i].skip_mip = tm[i].skipMip;
   }
   const int maxAuto = 96, bs = cu.w * cu.h;
-  std::vector<int32_t> level((size_t)maxAuto * bs);
-  std::vector<int16_t> reco((size_t)maxAuto * bs), pred((size_t)maxAuto * bs);
+  // reused from CU to CU: fresh arrays of 96 blocks cost a walker ~0.5 GB of zero-filled, page-faulted memory per CTU
+  static std::vector<int32_t> level;
+  static std::vector<int16_t> reco, pred;
+  if (level.size() < (size_t)maxAuto * bs) { level.resize((size_t)maxAuto * bs); reco.resize((size_t)maxAuto * bs); pred.resize((size_t)maxAuto * bs); }
   std::vector<vvcb_tu_result> res(maxAuto);
   std::vector<uint8_t> slots(maxAuto), tmpl(maxAuto);
   int nAuto = 0;
@@ -434,8 +439,8 @@ void fetchFirstPass(CuCache& cu, const Snapshot& s, bool tsAllowed, bool mtsAllo
     e.job.offset = (uint32_t)i * bs;
     e.job.intra_mode = t.lfnst ? (slots[i] >= VVCB_SLOT_MIP ? (uint8_t)PLANAR_IDX : (slots[i] < VVCB_SLOT_MRL1 ? slots[i] : cu.visit.mpm[1 + (slots[i] - VVCB_SLOT_MRL1) % 5])) : 0;
     e.res = res[i]; e.slot = slots[i];
-    e.level.assign(level.begin() + (size_t)i * bs, level.begin() + (size_t)(i + 1) * bs);
-    e.reco.assign(reco.begin() + (size_t)i * bs, reco.begin() + (size_t)(i + 1) * bs);
+    e.level.clear(); e.reco.clear();
+    e.lv = level.data() + (size_t)i * bs; e.rc = reco.data() + (size_t)i * bs;    // valid until the next CU's prefetch, which starts a new cache
     e.rateHash = s.rateHash; e.stateHash = s.stateHash;
     std::vector<int16_t>& p = cu.pred[slots[i]];
     if (p.empty()) p.assign(pred.begin() + (size_t)i * bs, pred.begin() + (size_t)(i + 1) * bs);
@@ -786,7 +791,7 @@ void __wrap__ZN7TrQuant12transformNxNER13TransformUnitRK11ComponentIDRK7QpParamR
   TuEntry& e = entryFor(tu, ctx, tu.mtsIdx, false);
   if (e.job.qp_per != qp.per(ts) || e.job.qp_rem != qp.rem(ts) || e.job.lambda != tq->m_quant->getLambda()) die("QP / lambda of the TU differ from the ones its candidate was computed with");
   CoeffBuf lv = tu.getCoeffs(c);
-  for (int y = 0; y < g_cu.h; y++) memcpy(&lv.at(0, y), &e.level[(size_t)y * g_cu.w], g_cu.w * sizeof(TCoeff));
+  for (int y = 0; y < g_cu.h; y++) memcpy(&lv.at(0, y), &e.lv[(size_t)y * g_cu.w], g_cu.w * sizeof(TCoeff));
   absSum = e.res.abs_sum_level;
   TU::setCbfAtDepth(tu, c, tu.depth, absSum > 0);
   g_pend.tu = &tu; g_pend.e = &e; g_pend.recoBuf = tu.cs->getRecoBuf(tu.blocks[c]).buf;
@@ -804,7 +809,7 @@ void __wrap__ZN7TrQuant15invTransformNxNER13TransformUnitRK11ComponentIDR7AreaBu
   WrapScope sc;
   const std::vector<int16_t>& pred = g_cu.pred[g_pend.e->slot];
   for (int y = 0; y < g_cu.h; y++)
-    for (int x = 0; x < g_cu.w; x++) resi.at(x, y) = g_pend.e->reco[(size_t)y * g_cu.w + x] - pred[(size_t)y * g_cu.w + x];   // PelBuf::reconstruct clips pred + resi back to reco
+    for (int x = 0; x < g_cu.w; x++) resi.at(x, y) = g_pend.e->rc[(size_t)y * g_cu.w + x] - pred[(size_t)y * g_cu.w + x];   // PelBuf::reconstruct clips pred + resi back to reco
   g_st.invServed++;
 }
 
