@@ -72,6 +72,24 @@ extern "C" int emul_rmd_eval(const int16_t* orig, const int16_t* reco, int strid
   std::vector<uint32_t> sm((size_t)2 * VVCB_NUM_SLOTS * n);
   P.sadSM = sm.data(); P.satdSM = (details || predOut) ? sm.data() + (size_t)VVCB_NUM_SLOTS * n : nullptr; P.nVisits = n;   // as launch_rmd (vvcb_api.cu)
   P.orig = orig; P.reco = reco; P.stride = stride; P.bd = bd; P.ctu = ctu; P.rom = &rom; P.predOut = predOut;
+  if (!predOut && n <= 48) {
+    // walk-sized batch, as launch_rmd (vvcb_api.cu) runs it: one any-bucket launch for the packed items, one for the plain ones
+    for (int mode = 1; mode >= 0; mode--) {
+      EvalAny A;
+      A.n = 0;
+      int cta = 0;
+      for (int b = 0; b < kNumBuckets; b++) {
+        bool occupied = mode == 0 ? plan.count[b] != 0 : false;
+        if (mode == 1) for (int i = 0; i < pack_shape_count(b / kNumKinds); i++) occupied = occupied || plan.count[kNumBuckets + pack_shape(b / kNumKinds, i) * kNumKinds + b % kNumKinds];
+        if (!occupied) continue;
+        A.bucket[A.n] = (unsigned char)b; A.firstCta[A.n] = cta; cta += 1 + (b & 1); A.n++;          // one or two CTAs per bucket: both walk the bucket's cursor
+      }
+      A.firstCta[A.n] = cta;
+      if (!A.n) continue;
+      if (mode) emu_launch(cta, EvalCfg<true>::kThreads, [&] { rmd_eval_any_kernel<1>(P, A); });
+      else      emu_launch(cta, EvalCfg<false>::kThreads, [&] { rmd_eval_any_kernel<0>(P, A); });
+    }
+  } else
   for (int b = 0; b < kNumBuckets; b++) {
     bool packed = false;
     for (int i = 0; i < pack_shape_count(b / kNumKinds); i++) packed = packed || plan.count[kNumBuckets + pack_shape(b / kNumKinds, i) * kNumKinds + b % kNumKinds];

@@ -532,6 +532,7 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   if (tm) CK(cudaEventRecord(ctx->kev[0], ctx->stream));
   const int pack = dPred ? 0 : 1;     // the prediction-output kernels (parity / integration entry points) take plain items only
   bool needAll = !hostVisits || n > 4096, need[2][kNumBuckets] = {};
+  int inBucket[2][kNumBuckets] = {};                  // visits per (packed / plain, bucket)
   if (!needAll)
     for (int i = 0; i < n; i++) {
       const vvcb_rmd_visit& v = hostVisits[i];
@@ -539,7 +540,8 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
       const int packed = pack && small_shape_index(sh.lw, sh.lh) >= 0 ? 1 : 0;
       const bool mip = !(v.flags & VVCB_VISIT_NO_MIP) && mip_num_modes(sh.w, sh.h) > 0;
       need[packed][sh.tile * kNumKinds + KIND_ANG] = need[packed][sh.tile * kNumKinds + KIND_PDC] = true;
-      if (mip) need[packed][sh.tile * kNumKinds + KIND_MIP] = true;
+      inBucket[packed][sh.tile * kNumKinds + KIND_ANG]++; inBucket[packed][sh.tile * kNumKinds + KIND_PDC]++;
+      if (mip) { need[packed][sh.tile * kNumKinds + KIND_MIP] = true; inBucket[packed][sh.tile * kNumKinds + KIND_MIP]++; }
     }
   int evalLaunches = 0;
   rmd_plan_count<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan, pack);
@@ -557,12 +559,34 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   // several streams, longest first, the CTAs of the following kernels move in as soon as SM slots free up.  Measured (profiles/r1z_summary.md):
   // no effect on a whole resident sweep (persistent warps drain within one item of each other), 20.3 -> 17.7 ms for the chunked host-buffer
   // path, where every chunk pays the hand-over between its 33 launches.
+  static const int kindOrder[kNumKinds] = { KIND_ANG, KIND_MIP, KIND_PDC };
+  static const int tileOrder[kNumClasses] = { 3, 4, 5, 1, 2, 0 };
+  if (!needAll && !dPred) {
+    // walk-sized batch: ONE launch for the packed items and one for the plain ones, the CTAs dealt to the occupied buckets (rmd_eval_any_kernel)
+    for (int mode = 1; mode >= 0; mode--) {
+      EvalAny A;
+      A.n = 0;
+      int cta = 0;
+      const int warpsPerCta = mode ? EvalCfg<true>::kWarps : EvalCfg<false>::kWarps, minCtas = mode ? EvalCfg<true>::kMinCtas : EvalCfg<false>::kMinCtas;
+      for (int ki = 0; ki < kNumKinds; ki++)
+        for (int ti = 0; ti < kNumClasses; ti++) {
+          const int b = tileOrder[ti] * kNumKinds + kindOrder[ki];
+          if (!need[mode][b] || (mode == 0 && b < kNumKinds)) continue;            // (the 4x4 class has no plain shapes)
+          int ctas = (inBucket[mode][b] * 8 + warpsPerCta - 1) / warpsPerCta;     // no point in more warps than work items
+          if (ctas > ctx->numSms * minCtas) ctas = ctx->numSms * minCtas;
+          A.bucket[A.n] = (unsigned char)b; A.firstCta[A.n] = cta; cta += ctas; A.n++;
+        }
+      A.firstCta[A.n] = cta;
+      if (!A.n) continue;
+      if (mode) rmd_eval_any_kernel<1><<<cta, EvalCfg<true>::kThreads, 0, ctx->stream>>>(P, A);
+      else      rmd_eval_any_kernel<0><<<cta, EvalCfg<false>::kThreads, 0, ctx->stream>>>(P, A);
+      evalLaunches++;
+    }
+  } else {
   const int useStreams = needAll ? ctx->evalStreams : (ctx->evalStreams < 3 ? ctx->evalStreams : 3);   // a handful of launches: fewer hand-overs
   const int nSide = useStreams - 1;
   CK(cudaEventRecord(ctx->evPlan, ctx->stream));
   for (int i = 0; i < nSide; i++) CK(cudaStreamWaitEvent(ctx->sKind[i], ctx->evPlan, 0));
-  static const int kindOrder[kNumKinds] = { KIND_ANG, KIND_MIP, KIND_PDC };
-  static const int tileOrder[kNumClasses] = { 3, 4, 5, 1, 2, 0 };
   int dealt = 0;
   auto next_stream = [&]() { const int k = dealt++ % useStreams; return k == 0 ? ctx->stream : ctx->sKind[k - 1]; };
   for (int ki = 0; ki < kNumKinds; ki++)
@@ -574,6 +598,7 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
       if (b >= kNumKinds && (needAll || need[0][b])) { VVCB_FOR_BUCKET(b, 0, launch_eval_bucket, P, ctx->numSms, maxWarps, next_stream()); evalLaunches++; }
     }
   for (int i = 0; i < nSide; i++) { CK(cudaEventRecord(ctx->evKind[i], ctx->sKind[i])); CK(cudaStreamWaitEvent(ctx->stream, ctx->evKind[i], 0)); }
+  }
   if (tm) CK(cudaEventRecord(ctx->kev[2], ctx->stream));
   if (dDetails) { rmd_detail_kernel<<<(n + 31) / 32, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dDetails, P.sadSM, P.satdSM); ctx->launches++; }
   rmd_lists_kernel<<<(n + kListThreads - 1) / kListThreads, kListThreads, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dResults, dDetails, P.sadSM, P.satdSM, dBrief);

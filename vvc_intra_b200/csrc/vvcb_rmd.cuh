@@ -599,20 +599,32 @@ __host__ __device__ __forceinline__ int pack_shape(int tile, int i)
 
 // MODE 0: plain items; MODE 1: packed items; MODE 2: plain items + the prediction samples of visit 0 written to P.predOut (the parity /
 // integration entry points vvcb_rmd_pred*; kept out of the throughput kernels: 350 instructions in the middle of their hot loop)
+// The shared memory of one evaluation CTA, as one block: the per-bucket kernels declare it statically, the any-bucket kernels (below) hand
+// the same layout to whichever bucket their CTA serves.
+template <bool PACK> struct EvalShared {
+  using Cfg = EvalCfg<PACK>;
+  typename Cfg::Smem smem[Cfg::kWarps][Cfg::kVisits];
+  int16_t sScratch[Cfg::kWarps][kSlotLineWords];                  // per-slot scratch of the slots in flight
+  vvcb_rmd_visit sVisit[Cfg::kWarps][Cfg::kVisits];
+  int sSlots[Cfg::kWarps][Cfg::kVisits + 1];                      // packed items: number of slots of each visit
+  unsigned sIndex[Cfg::kWarps][Cfg::kVisits];                     // the visits' indices in the batch
+  uint32_t sFilt[64];
+};
+
 template <int TILE, int KIND, int MODE>
-__global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 1>::kMinCtas) rmd_eval_kernel(EvalParams P)
+__device__ __forceinline__ void rmd_eval_body(const EvalParams& P, EvalShared<MODE == 1>& shm)
 {
   constexpr bool PACK = MODE == 1, WITH_PRED = MODE == 2;
   using Cfg = EvalCfg<PACK>;
   using SM = typename Cfg::Smem;
   constexpr int S = TILE < 3 ? 4 : 8;
   constexpr int V = Cfg::kVisits;
-  __shared__ SM smem[Cfg::kWarps][V];
-  __shared__ int16_t sScratch[Cfg::kWarps][kSlotLineWords];       // per-slot scratch of the slots in flight
-  __shared__ vvcb_rmd_visit sVisit[Cfg::kWarps][V];
-  __shared__ int sSlots[Cfg::kWarps][V + 1];                      // packed items: number of slots of each visit
-  __shared__ unsigned sIndex[Cfg::kWarps][V];                     // the visits' indices in the batch
-  __shared__ uint32_t sFilt[64];
+  auto& smem = shm.smem;
+  auto& sScratch = shm.sScratch;
+  auto& sVisit = shm.sVisit;
+  auto& sSlots = shm.sSlots;
+  auto& sIndex = shm.sIndex;
+  auto& sFilt = shm.sFilt;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < 64) sFilt[threadIdx.x] = (&P.rom->filt[0][0])[threadIdx.x];
   __syncthreads();
@@ -854,6 +866,38 @@ __global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 
       }
     }
   }
+  }
+}
+
+template <int TILE, int KIND, int MODE>
+__global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 1>::kMinCtas) rmd_eval_kernel(EvalParams P)
+{
+  __shared__ EvalShared<MODE == 1> shm;
+  rmd_eval_body<TILE, KIND, MODE>(P, shm);
+}
+
+// One launch for every bucket a walk-sized batch occupies (vvcb_cu_eval: a few dozen visits of mixed shapes): the CTAs of the grid are dealt
+// to the (tile class, kind) buckets by a small table and each runs that bucket's body.  A batch of 40 CUs spent more device time between its
+// ~16 evaluation launches than inside them (profiles/r2_summary.md); the sweep keeps the per-bucket kernels (their own register allocation).
+struct EvalAny {
+  int n;                       // buckets in this launch
+  int firstCta[19];            // CTAs [firstCta[k], firstCta[k + 1]) serve bucket[k]
+  unsigned char bucket[20];    // tile class * kNumKinds + kind
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(EvalCfg<MODE == 1>::kThreads, EvalCfg<MODE == 1>::kMinCtas) rmd_eval_any_kernel(EvalParams P, EvalAny A)
+{
+  __shared__ EvalShared<MODE == 1> shm;
+  int k = 0;
+  while (k + 1 < A.n && (int)blockIdx.x >= A.firstCta[k + 1]) k++;
+  switch (A.bucket[k]) {
+    case 0:  rmd_eval_body<0, 0, MODE>(P, shm); break;  case 1:  rmd_eval_body<0, 1, MODE>(P, shm); break;  case 2:  rmd_eval_body<0, 2, MODE>(P, shm); break;
+    case 3:  rmd_eval_body<1, 0, MODE>(P, shm); break;  case 4:  rmd_eval_body<1, 1, MODE>(P, shm); break;  case 5:  rmd_eval_body<1, 2, MODE>(P, shm); break;
+    case 6:  rmd_eval_body<2, 0, MODE>(P, shm); break;  case 7:  rmd_eval_body<2, 1, MODE>(P, shm); break;  case 8:  rmd_eval_body<2, 2, MODE>(P, shm); break;
+    case 9:  rmd_eval_body<3, 0, MODE>(P, shm); break;  case 10: rmd_eval_body<3, 1, MODE>(P, shm); break;  case 11: rmd_eval_body<3, 2, MODE>(P, shm); break;
+    case 12: rmd_eval_body<4, 0, MODE>(P, shm); break;  case 13: rmd_eval_body<4, 1, MODE>(P, shm); break;  case 14: rmd_eval_body<4, 2, MODE>(P, shm); break;
+    case 15: rmd_eval_body<5, 0, MODE>(P, shm); break;  case 16: rmd_eval_body<5, 1, MODE>(P, shm); break;  case 17: rmd_eval_body<5, 2, MODE>(P, shm); break;
   }
 }
 
