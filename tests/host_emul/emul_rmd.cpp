@@ -64,15 +64,20 @@ extern "C" int emul_rmd_eval(const int16_t* orig, const int16_t* reco, int strid
   PlanState plan;
   memset(&plan, 0, sizeof(plan));
   const int pack = predOut ? 0 : 1;
-  emu_launch((n + 255) / 256, 256, [&] { rmd_plan_count(visits, n, ctu, &plan, pack); });
-  emu_launch(1, 32, [&] { rmd_plan_scan(&plan); });
-  emu_launch((n + 255) / 256, 256, [&] { rmd_plan_fill(visits, n, ctu, &plan, items.data(), pack); });
+  if (!predOut && n <= 96) {                  // walk-sized batch, as launch_rmd runs it (the plan state is written whole: start from garbage)
+    memset(&plan, 0xA5, sizeof(plan));
+    emu_launch(1, 256, [&] { rmd_plan_small(visits, n, ctu, &plan, items.data(), pack); });
+  } else {
+    emu_launch((n + 255) / 256, 256, [&] { rmd_plan_count(visits, n, ctu, &plan, pack); });
+    emu_launch(1, 32, [&] { rmd_plan_scan(&plan); });
+    emu_launch((n + 255) / 256, 256, [&] { rmd_plan_fill(visits, n, ctu, &plan, items.data(), pack); });
+  }
   EvalParams P;
   P.visits = visits; P.items = items.data(); P.plan = &plan;
   std::vector<uint32_t> sm((size_t)2 * VVCB_NUM_SLOTS * n);
   P.sadSM = sm.data(); P.satdSM = (details || predOut) ? sm.data() + (size_t)VVCB_NUM_SLOTS * n : nullptr; P.nVisits = n;   // as launch_rmd (vvcb_api.cu)
   P.orig = orig; P.reco = reco; P.stride = stride; P.bd = bd; P.ctu = ctu; P.rom = &rom; P.predOut = predOut;
-  if (!predOut && n <= 48) {
+  if (!predOut && n <= 96) {
     // walk-sized batch, as launch_rmd (vvcb_api.cu) runs it: one any-bucket launch for the packed items, one for the plain ones
     for (int mode = 1; mode >= 0; mode--) {
       EvalAny A;

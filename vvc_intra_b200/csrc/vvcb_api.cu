@@ -527,7 +527,8 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
     CK(cudaMalloc(&ctx->dScratch, (size_t)n * 2 * VVCB_NUM_SLOTS * sizeof(uint32_t)));
     ctx->capScratch = (size_t)n;
   }
-  CK(cudaMemsetAsync(ctx->dPlan, 0, sizeof(PlanState), ctx->stream));
+  const bool smallPlan = hostVisits && n <= 4096;         // walk-sized batch: one planning launch (rmd_plan_small), the plan state is written whole
+  if (!smallPlan) CK(cudaMemsetAsync(ctx->dPlan, 0, sizeof(PlanState), ctx->stream));
   const bool tm = ctx->timing != 0;
   if (tm) CK(cudaEventRecord(ctx->kev[0], ctx->stream));
   const int pack = dPred ? 0 : 1;     // the prediction-output kernels (parity / integration entry points) take plain items only
@@ -544,9 +545,12 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
       if (mip) { need[packed][sh.tile * kNumKinds + KIND_MIP] = true; inBucket[packed][sh.tile * kNumKinds + KIND_MIP]++; }
     }
   int evalLaunches = 0;
-  rmd_plan_count<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan, pack);
-  rmd_plan_scan<<<1, 32, 0, ctx->stream>>>(ctx->dPlan);
-  rmd_plan_fill<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan, ctx->dItems, pack);
+  if (smallPlan) rmd_plan_small<<<1, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan, ctx->dItems, pack);
+  else {
+    rmd_plan_count<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan, pack);
+    rmd_plan_scan<<<1, 32, 0, ctx->stream>>>(ctx->dPlan);
+    rmd_plan_fill<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, ctx->dPlan, ctx->dItems, pack);
+  }
   if (tm) CK(cudaEventRecord(ctx->kev[1], ctx->stream));
   EvalParams P;
   P.visits = dVisits; P.items = ctx->dItems; P.plan = ctx->dPlan;
@@ -602,7 +606,7 @@ static int launch_rmd(vvcb_ctx* ctx, const vvcb_rmd_visit* dVisits, int n, vvcb_
   if (tm) CK(cudaEventRecord(ctx->kev[2], ctx->stream));
   if (dDetails) { rmd_detail_kernel<<<(n + 31) / 32, 256, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dDetails, P.sadSM, P.satdSM); ctx->launches++; }
   rmd_lists_kernel<<<(n + kListThreads - 1) / kListThreads, kListThreads, 0, ctx->stream>>>(dVisits, n, ctx->ctu, dResults, dDetails, P.sadSM, P.satdSM, dBrief);
-  ctx->launches += 3 + evalLaunches + 1;
+  ctx->launches += (smallPlan ? 1 : 3) + evalLaunches + 1;
   CK(cudaGetLastError());
   if (tm) {
     CK(cudaEventRecord(ctx->kev[3], ctx->stream));

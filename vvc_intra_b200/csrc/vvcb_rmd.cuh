@@ -238,6 +238,55 @@ __global__ void rmd_plan_fill(const vvcb_rmd_visit* visits, int n, int ctu, Plan
     }
 }
 
+// The three planning passes in one launch of one CTA, for the walk-sized batches of vvcb_cu_eval (a few dozen visits; plan state need not be
+// zeroed beforehand).  The order of the items inside a bucket differs from the three-kernel plan; nothing depends on it.
+__global__ void __launch_bounds__(256) rmd_plan_small(const vvcb_rmd_visit* visits, int n, int ctu, PlanState* plan, WorkItem* items, int pack)
+{
+  __shared__ unsigned cnt[kNumBucketsAll], off[kNumBucketsAll], cur[kNumBucketsAll];
+  for (int b = threadIdx.x; b < kNumBucketsAll; b += blockDim.x) cnt[b] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const vvcb_rmd_visit v = visits[i];
+    const Shape sh = make_shape(v.log2w, v.log2h);
+    const bool packed = pack && small_shape_index(sh.lw, sh.lh) >= 0;
+    for (int kind = 0; kind < kNumKinds; kind++) {
+      int perItem;
+      const int nItems = items_of(kind_slot_count(v, kind, ctu), sh.lanes, perItem, packed);
+      if (nItems) atomicAdd(&cnt[bucket_of(sh, kind, packed)], (unsigned)nItems);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned acc = 0;
+    for (int b = 0; b < kNumBucketsAll; b++) {
+      off[b] = acc; cur[b] = 0;
+      plan->count[b] = cnt[b]; plan->offset[b] = acc; plan->fill[b] = cnt[b]; plan->cursor[b] = 0;
+      acc += cnt[b];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const vvcb_rmd_visit v = visits[i];
+    const Shape sh = make_shape(v.log2w, v.log2h);
+    const bool packed = pack && small_shape_index(sh.lw, sh.lh) >= 0;
+    for (int kind = 0; kind < kNumKinds; kind++) {
+      int perItem;
+      const int nSlots = kind_slot_count(v, kind, ctu);
+      const int nItems = items_of(nSlots, sh.lanes, perItem, packed);
+      if (!nItems) continue;
+      const int b = bucket_of(sh, kind, packed);
+      const unsigned at = off[b] + atomicAdd(&cur[b], (unsigned)nItems);
+      for (int k = 0; k < nItems; k++) {
+        WorkItem w;
+        w.visit = (uint32_t)i;
+        w.slot_begin = (uint16_t)(k * perItem);
+        w.slot_count = (uint16_t)vmin(perItem, nSlots - k * perItem);
+        items[at + k] = w;
+      }
+    }
+  }
+}
+
 // =====================================================================================================
 // reference lines of one visit into the warp's shared memory
 // =====================================================================================================
