@@ -507,7 +507,7 @@ def bitexact_leg(frames, device):
     # own CPU time bounds the leg from 256 walkers on 16 cores on, and two workers keep the batches large (about 30 CUs each)
     over = max(1, int(os.environ.get('VVCB_BENCH_OVERSUBSCRIBE', '16')))
     workers = max(1, int(os.environ.get('VVCB_BENCH_WORKERS', '2')))
-    n = cores * over
+    n = min(cores * over, 512)                       # bounded: a 6 MB broker slot and one encoder process per walker
     # the plain encoder runs on a bounded share of the same crops (its rate does not depend on how many there are); those are the
     # bitstreams the served ones are compared with
     n_plain = min(n, cores * max(1, int(os.environ.get('VVCB_BENCH_PLAIN_ROUNDS', '2'))))
