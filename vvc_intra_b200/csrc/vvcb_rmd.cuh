@@ -1153,8 +1153,8 @@ __device__ void store_list_detail(const SmList& L, int32_t* n, vvcb_mode* m, dou
 }
 
 // One thread per visit: EL/IntraSearch.cpp:489-802 minus the predictions (already reduced to SAD/SATD, read from
-// the slot-major scratch: coalesced across the visits of a warp whenever they look at the same slot).  The result
-// structs are written by the whole warp, one visit after the other, so that every store is a full line.
+// the visit's 448 contiguous bytes of the scratch plane, scratch_at: mostly L2 hits, the evaluation kernels have just written them).
+// The result structs are written by the whole warp, one visit after the other, so that every store is a full line.
 #ifndef VVCB_LIST_MIN_CTAS
 #define VVCB_LIST_MIN_CTAS 4
 #endif
