@@ -1,5 +1,7 @@
-"""Frame-parallel gather (vvc_intra_b200/assemble.py): pictures encoded by independent encoder processes, concatenated, decoded by the reference decoder.
-CPU test on the reference binaries built by oracle/Makefile.ref (skipped where they are absent)."""
+"""Frame-parallel gather (vvc_intra_b200/assemble.py, vvc_intra_b200/hls.py): pictures encoded by independent encoder processes and gathered into the
+sequential encoder's bitstream, byte for byte; the reference's own Parcat reproduced byte for byte.  The fixtures under tests/golden/assemble/ are
+outputs of the unmodified reference (tools/make_assemble_golden.py); the live tests run the reference binaries built by oracle/Makefile.ref and are
+skipped where those are absent."""
 import os
 import subprocess
 
@@ -7,6 +9,79 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, 'oracle/_ref')
+GOLD = os.path.join(ROOT, 'tests/golden/assemble')
+
+
+def test_bit_exact_gather_reproduces_the_sequential_encoder(tmp_path):
+    """Four 256x128 10-bit pictures encoded one process per picture; the gather must be the sequential encoder's stream.  The slice headers of
+    pictures 1.. grow by two bits (one byte after re-alignment for pictures 1-3), picture 3 carries an ALF APS whose id must not move."""
+    from vvc_intra_b200 import assemble, hls
+    paths = [os.path.join(GOLD, 'pic_256x128_10b_qp27_f%d.bin' % f) for f in range(4)]
+    stats = assemble.assemble_sequential(paths, str(tmp_path / 'all.bin'))
+    seq = open(os.path.join(GOLD, 'pic_256x128_10b_qp27_seq.bin'), 'rb').read()
+    assert (tmp_path / 'all.bin').read_bytes() == seq
+    assert [s['bytes_out'] - s['bytes_in'] for s in stats] == [0, 1, 1, 1]
+    types = [hls.NAL_NAMES[hls.nal_unit_type(u)] for _, u in hls.split_nal_units(seq)]
+    assert types.count('IDR_W_RADL') == 1 and types.count('CRA') == 3 and types.count('APS') == 1
+    # the plain concatenation differs from it in exactly the three re-numbered slice NAL units
+    assemble.concat_segments(paths, str(tmp_path / 'cat.bin'))
+    diff = assemble.diff_against_sequential((tmp_path / 'cat.bin').read_bytes(), seq)
+    assert [(d[1], d[2]) for d in diff] == [('IDR_W_RADL', 'CRA')] * 3
+    # ReWriteParamSets=0 flavour: parameter sets only ahead of the first picture
+    assemble.assemble_sequential(paths, str(tmp_path / 'lean.bin'), rewrite_param_sets=False)
+    lean = [hls.NAL_NAMES[hls.nal_unit_type(u)] for _, u in hls.split_nal_units((tmp_path / 'lean.bin').read_bytes())]
+    assert lean.count('SPS') == 1 and lean.count('PPS') == 1 and lean.count('CRA') == 3
+    # a segment that is not a one-picture IDR stream is refused
+    with pytest.raises(ValueError):
+        assemble.assemble_sequential([paths[0], os.path.join(GOLD, 'pic_256x128_10b_qp27_seq.bin')], str(tmp_path / 'x.bin'))
+
+
+def test_parcat_segments_matches_the_reference_tool(tmp_path):
+    from vvc_intra_b200 import assemble
+    segs = [os.path.join(GOLD, 'seg_64x64_8b_qp32_s%d.bin' % k) for k in range(3)]
+    assert assemble.parcat_segments(segs, str(tmp_path / 'out.bin')) == 6                  # six pictures re-numbered (POC 1..6)
+    assert (tmp_path / 'out.bin').read_bytes() == open(os.path.join(GOLD, 'seg_64x64_8b_qp32_parcat.bin'), 'rb').read()
+    assert assemble.parcat_segments(segs[:1], str(tmp_path / 'one.bin')) == 2              # a single segment passes through unchanged
+    assert (tmp_path / 'one.bin').read_bytes() == open(segs[0], 'rb').read()
+
+
+def test_syntax_reader_on_reference_streams():
+    """Every parameter set of the fixtures parses to its rbsp_trailing_bits, every slice header to its alignment bits; escaping is the encoder's."""
+    import random
+    from vvc_intra_b200 import hls
+    seen = set()
+    for name in sorted(os.listdir(GOLD)):
+        data = open(os.path.join(GOLD, name), 'rb').read()
+        sps, pps = {}, {}
+        for _, u in hls.split_nal_units(data):
+            t, rbsp = hls.nal_unit_type(u), hls.unescape(u[2:])
+            assert hls.escape(rbsp) == u[2:]
+            if t == hls.NAL_SPS:
+                s = hls.parse_sps(rbsp)
+                sps[s['sps_id']] = s
+                assert (s['width'], s['height'], s['poc_bits']) in ((256, 128, 8), (64, 64, 8)) and s['alf'] and s['sao'] and s['lmcs']
+            elif t == hls.NAL_PPS:
+                p = hls.parse_pps(rbsp, sps)
+                pps[p['pps_id']] = p
+            elif t in (hls.NAL_IDR_W_RADL, hls.NAL_CRA):
+                h = hls.parse_intra_slice_header(rbsp, t, sps[0], pps)
+                assert h['slice_type'] == hls.I_SLICE and (h['after_rpl'] - h['after_poc']) == (2 if t == hls.NAL_CRA else 0)
+                seen.add((t, h['poc_lsb']))
+    assert {(hls.NAL_CRA, n) for n in range(1, 7)} <= seen and (hls.NAL_IDR_W_RADL, 0) in seen
+    rng = random.Random(7)
+    for _ in range(200):                                             # emulation prevention round trip on zero-heavy payloads
+        rbsp = bytes(rng.choice((0, 0, 0, 1, 2, 3, 4, 255)) for _ in range(rng.randrange(1, 40)))
+        esc = hls.escape(rbsp)
+        assert b'\x00\x00\x00' not in esc and b'\x00\x00\x01' not in esc and b'\x00\x00\x02' not in esc and esc[-1] != 0
+        assert hls.unescape(esc) == rbsp or (rbsp[-1] == 0 and hls.unescape(esc) == rbsp + b'\x03')
+    with pytest.raises(ValueError):
+        hls.parse_sps(bytes(40))
+    w = hls.BitWriter()
+    for v in (0, 1, 2, 7, 8, 300):
+        w.ue(v)
+    w.align()
+    r = hls.BitReader(w.tobytes())
+    assert [r.ue() for _ in range(6)] == [0, 1, 2, 7, 8, 300] and r.at_trailing_bits()
 
 
 def test_frame_parallel_gather_decodes_to_the_sequential_reconstruction(tmp_path):
@@ -40,6 +115,9 @@ def test_frame_parallel_gather_decodes_to_the_sequential_reconstruction(tmp_path
     # what separates the gather from the sequential bitstream: only the slice NAL units of pictures 1.. (IDR / POC 0 against CRA / POC n), same sizes
     diff = assemble.diff_against_sequential((tmp_path / 'all.bin').read_bytes(), (tmp_path / 'seq.bin').read_bytes())
     assert len(diff) == n - 1 and all(d[1].startswith('IDR') and d[2] == 'CRA' and d[3] == d[4] for d in diff), diff
+    # the bit-exact gather closes that gap
+    assemble.assemble_sequential([str(tmp_path / ('f%d.bin' % f)) for f in range(n)], str(tmp_path / 'exact.bin'))
+    assert (tmp_path / 'exact.bin').read_bytes() == (tmp_path / 'seq.bin').read_bytes()
     with pytest.raises(ValueError):
         (tmp_path / 'bad.bin').write_bytes(b'\x00\x00\x01\x11\x02')
         assemble.concat_segments([str(tmp_path / 'bad.bin')], str(tmp_path / 'x.bin'))
