@@ -992,3 +992,54 @@ def test_cu_eval_templates_expand_over_the_lists(eng10):
     bad['want_rmd'] = False
     with pytest.raises(vb.EngineError, match='malformed'):
         eng10.cu_eval([bad])
+
+
+def test_frame_parallel_served_encode_gathers_to_the_sequential_bitstream(tmp_path):
+    """The whole frame-parallel route on the GPU: one served encoder process per picture of a three-picture 10-bit sequence,
+    all sharing one engine context through the broker; the gather (vvc_intra_b200/assemble.py) must reproduce the bitstream the plain sequential
+    encoder writes for the sequence, byte for byte."""
+    import json
+    import os
+    import subprocess
+    from make_golden import synth_yuv
+    from vvc_intra_b200 import assemble
+    root, (plain, served, cfg) = _ref_binaries('EncoderApp', 'EncoderAppServe')
+    broker = os.path.join(root, 'vvc_intra_b200/vvcb_broker')
+    w, h, bits, qp, n = 128, 64, 10, 32, 3
+    data = b''
+    for f in range(n):
+        Y, U, V = synth_yuv(w, h, bits, f)
+        data += Y.tobytes() + U.tobytes() + V.tobytes()
+    (tmp_path / 'in.yuv').write_bytes(data)
+    (tmp_path / 'Time_python.dat').write_bytes(b'')
+    args = _encoder_args(cfg, w, h, bits, qp)
+    args = args[:args.index('-f')] + args[args.index('-f') + 2:]
+    path = str(tmp_path / 'broker.shm')
+    env0 = dict(os.environ)
+    env0.pop('LD_LIBRARY_PATH', None)
+    env0.pop('VVCB_BROKER', None)
+    server = subprocess.Popen([broker, path, '--bit-depth', '10', '--clients', '4', '--frame', '128x64', '--workers', '2'], env=env0, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        seq = subprocess.Popen([plain] + args + ['-f', str(n), '-b', 'seq.bin'], cwd=tmp_path, env=env0, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        procs = [subprocess.Popen([served] + args + ['-f', '1', '--FrameSkip=%d' % f, '-b', 'f%d.bin' % f], cwd=tmp_path,
+                                  env=dict(env0, VVCB_BROKER=path, VVCB_SHIM_REPORT=str(tmp_path / ('rep%d.json' % f))), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                 for f in range(n)]
+        for p in procs:
+            out, _ = p.communicate(timeout=900)
+            assert p.returncode == 0, out[-2000:]
+        assert seq.wait(timeout=900) == 0
+        stats = json.loads(subprocess.check_output([broker, path, '--stats'], env=env0))
+        assert stats['clients_seen'] == n and stats['kernel_launches'] > 1000
+    finally:
+        subprocess.run([broker, path, '--stop'], env=env0)
+        try:
+            out, _ = server.communicate(timeout=60)
+        except subprocess.TimeoutExpired:
+            server.kill()
+            out = ''
+    assert server.returncode == 0, out[-2000:]
+    for f in range(n):
+        assert json.loads((tmp_path / ('rep%d.json' % f)).read_text())['visits'] > 100
+    stats = assemble.assemble_sequential([str(tmp_path / ('f%d.bin' % f)) for f in range(n)], str(tmp_path / 'all.bin'))
+    assert (tmp_path / 'all.bin').read_bytes() == (tmp_path / 'seq.bin').read_bytes()
+    print('frame-parallel gather', stats)

@@ -158,3 +158,45 @@ def test_broker_rejects_what_does_not_fit(built, tmp_path):
     finally:
         subprocess.run([os.path.join(FAKE, 'vvcb_broker'), path, '--stop'], env=env)
         server.wait(timeout=30)
+
+
+def test_frame_parallel_served_encode_gathers_to_the_sequential_bitstream(built, tmp_path):
+    """The whole frame-parallel route: one served encoder process per picture of a three-picture sequence, all sharing one
+    engine context through the broker; the gather (vvc_intra_b200/assemble.py) must reproduce the bitstream the plain sequential encoder writes
+    for the sequence, byte for byte."""
+    from make_golden import synth_yuv
+    from vvc_intra_b200 import assemble
+    w, h, bits, qp, n = 64, 64, 8, 32, 3
+    data = b''
+    for f in range(n):
+        Y, U, V = synth_yuv(w, h, bits, f)
+        data += Y.tobytes() + U.tobytes() + V.tobytes()
+    (tmp_path / 'in.yuv').write_bytes(data)
+    (tmp_path / 'Time_python.dat').write_bytes(b'')
+    args = [a for a in encoder_args(w, h, bits, qp)]
+    args = args[:args.index('-f')] + args[args.index('-f') + 2:]
+    path = str(tmp_path / 'broker.shm')
+    envb = dict(os.environ, LD_LIBRARY_PATH=FAKE)
+    server = subprocess.Popen([os.path.join(FAKE, 'vvcb_broker'), path, '--bit-depth', '8', '--clients', '4', '--frame', '64x64', '--workers', '2'],
+                              env=envb, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    try:
+        seq = subprocess.Popen([os.path.join(REF, 'EncoderApp')] + args + ['-f', str(n), '-b', 'seq.bin'], cwd=tmp_path, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        procs = [subprocess.Popen([os.path.join(REF, 'EncoderAppServe')] + args + ['-f', '1', '--FrameSkip=%d' % f, '-b', 'f%d.bin' % f], cwd=tmp_path,
+                                  env=dict(envb, VVCB_BROKER=path, VVCB_SHIM_REPORT=str(tmp_path / ('rep%d.json' % f))), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                 for f in range(n)]
+        for p in procs:
+            out, _ = p.communicate(timeout=600)
+            assert p.returncode == 0, out[-3000:]
+        assert seq.wait(timeout=600) == 0
+        stats = json.loads(subprocess.check_output([os.path.join(FAKE, 'vvcb_broker'), path, '--stats'], env=envb))
+        assert stats['clients_seen'] == n
+    finally:
+        subprocess.run([os.path.join(FAKE, 'vvcb_broker'), path, '--stop'], env=envb)
+        try:
+            server.wait(timeout=30)
+        except subprocess.TimeoutExpired:
+            server.kill()
+    for f in range(n):
+        assert json.loads((tmp_path / ('rep%d.json' % f)).read_text())['visits'] > 100
+    assemble.assemble_sequential([str(tmp_path / ('f%d.bin' % f)) for f in range(n)], str(tmp_path / 'all.bin'))
+    assert (tmp_path / 'all.bin').read_bytes() == (tmp_path / 'seq.bin').read_bytes()
