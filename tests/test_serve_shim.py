@@ -200,3 +200,31 @@ def test_frame_parallel_served_encode_gathers_to_the_sequential_bitstream(built,
         assert json.loads((tmp_path / ('rep%d.json' % f)).read_text())['visits'] > 100
     assemble.assemble_sequential([str(tmp_path / ('f%d.bin' % f)) for f in range(n)], str(tmp_path / 'all.bin'))
     assert (tmp_path / 'all.bin').read_bytes() == (tmp_path / 'seq.bin').read_bytes()
+
+
+def test_frame_parallel_driver_over_two_brokers(built, tmp_path):
+    """vvc_intra_b200/frame_parallel.py: four pictures dealt over two engine contexts (two brokers -- on the GPU box two devices), at most three
+    encoder processes alive at a time; bitstream and reconstruction equal the plain sequential encoder's."""
+    from make_golden import synth_yuv
+    from vvc_intra_b200 import frame_parallel
+    w, h, bits, qp, n = 64, 64, 8, 32, 4
+    data = b''
+    for f in range(n):
+        Y, U, V = synth_yuv(w, h, bits, f)
+        data += Y.tobytes() + U.tobytes() + V.tobytes()
+    (tmp_path / 'in.yuv').write_bytes(data)
+    (tmp_path / 'Time_python.dat').write_bytes(b'')
+    args = encoder_args(w, h, bits, qp)                                     # carries `-f 1`: the driver replaces it
+    seq = subprocess.Popen([os.path.join(REF, 'EncoderApp')] + args[:args.index('-f')] + args[args.index('-f') + 2:] + ['-f', str(n), '-b', 'seq.bin', '-o', 'seq.yuv'],
+                           cwd=tmp_path, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    st = frame_parallel.encode_sequence(os.path.join(REF, 'EncoderAppServe'), args, n, str(tmp_path / 'all.bin'), devices=(0, 0), bit_depth=bits, frame_size=(w, h),
+                                        workdir=str(tmp_path / 'work'), max_procs=3, broker_bin=os.path.join(FAKE, 'vvcb_broker'),
+                                        env=dict(os.environ, LD_LIBRARY_PATH=FAKE), recon_path=str(tmp_path / 'all.yuv'), cwd=str(tmp_path), timeout=600)
+    assert seq.wait(timeout=600) == 0
+    assert (tmp_path / 'all.bin').read_bytes() == (tmp_path / 'seq.bin').read_bytes()
+    assert (tmp_path / 'all.yuv').read_bytes() == (tmp_path / 'seq.yuv').read_bytes()
+    assert [p['picture'] for p in st['pictures']] == [0, 1, 2, 3] and [d['pictures'] for d in st['devices']] == [2, 2]
+    assert all(d['clients_seen'] == 2 and d['visits'] > 100 for d in st['devices']) and st['bytes'] == len((tmp_path / 'seq.bin').read_bytes())
+    with pytest.raises(frame_parallel.FrameParallelError):                  # a failing encoder surfaces with its output
+        frame_parallel.encode_sequence(os.path.join(REF, 'EncoderAppServe'), ['-c', 'missing.cfg'], 1, str(tmp_path / 'x.bin'), bit_depth=bits, frame_size=(w, h),
+                                       broker_bin=os.path.join(FAKE, 'vvcb_broker'), env=dict(os.environ, LD_LIBRARY_PATH=FAKE), cwd=str(tmp_path), timeout=60)
