@@ -121,3 +121,33 @@ def test_frame_parallel_gather_decodes_to_the_sequential_reconstruction(tmp_path
     with pytest.raises(ValueError):
         (tmp_path / 'bad.bin').write_bytes(b'\x00\x00\x01\x11\x02')
         assemble.concat_segments([str(tmp_path / 'bad.bin')], str(tmp_path / 'x.bin'))
+
+
+@pytest.mark.parametrize('w,h,bits,qp,extra', [
+    (64, 64, 10, 22, ['--SEIDecodedPictureHash=1']),                 # suffix SEI behind every picture
+    (64, 64, 8, 37, ['--ALF=0', '--SAO=0']),                         # shorter slice headers
+    (128, 64, 8, 27, ['--LMCSEnable=0', '--DepQuant=0']),            # sign_data_hiding_enabled_flag in the header
+    (64, 64, 8, 32, ['--LoopFilterDisable=1', '--JointCbCr=0']),     # deblocking control in the PPS
+    (72, 40, 8, 32, []),                                             # conformance window
+])
+def test_bit_exact_gather_across_encoder_options(w, h, bits, qp, extra, tmp_path):
+    """Live: the header reader must follow whatever the options do to the SPS / PPS / slice header."""
+    from make_golden import synth_yuv
+    from vvc_intra_b200 import assemble
+    enc, cfg = os.path.join(REF, 'EncoderApp'), os.path.join(REF, 'encoder_intra.cfg')
+    if not all(os.path.exists(p) for p in (enc, cfg)):
+        pytest.skip('oracle/_ref binaries are built only in the container that has /root/reference')
+    n = 2
+    data = b''
+    for f in range(n):
+        Y, U, V = synth_yuv(w, h, bits, f)
+        data += Y.tobytes() + U.tobytes() + V.tobytes()
+    (tmp_path / 'in.yuv').write_bytes(data)
+    (tmp_path / 'Time_python.dat').write_bytes(b'')
+    args = [enc, '-c', cfg, '-i', 'in.yuv', '-wdt', str(w), '-hgt', str(h), '-q', str(qp), '-fr', '30', '--InputBitDepth=%d' % bits,
+            '--InternalBitDepth=%d' % bits, '--OutputBitDepth=%d' % bits] + extra
+    procs = [subprocess.Popen(args + ['-f', '1', '--FrameSkip=%d' % f, '-b', 'f%d.bin' % f], cwd=tmp_path, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for f in range(n)]
+    procs.append(subprocess.Popen(args + ['-f', str(n), '-b', 'seq.bin'], cwd=tmp_path, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+    assert all(p.wait() == 0 for p in procs)
+    assemble.assemble_sequential([str(tmp_path / ('f%d.bin' % f)) for f in range(n)], str(tmp_path / 'all.bin'))
+    assert (tmp_path / 'all.bin').read_bytes() == (tmp_path / 'seq.bin').read_bytes()
