@@ -14,4 +14,4 @@ __all__ = ['IntraCostEngine', 'EngineError', 'VISIT_DTYPE', 'RESULT_DTYPE', 'DET
            'candidate_availability', 'build_sweep_visits']
 from . import shard
 from .tu_sweep import build_tu_sweep, build_tu_jobs_from_lists, slots_of_modes, default_dq_rates, default_ctx_states, lambda_for_qp
-from . import assemble, training_set
+from . import assemble, hls, training_set          # frame_parallel (a driver with a CLI) is imported on demand

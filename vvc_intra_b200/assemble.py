@@ -172,3 +172,31 @@ def parcat_segments(paths, out_path, bits_for_poc=8):
                     skip_next_sei = False
             poc_base += cnt
     return poc_base
+
+
+def main(argv=None):
+    """python -m vvc_intra_b200.assemble [--parcat | --concat] [--no-param-sets] seg0.bin seg1.bin ... out.bin
+    default: the bit-exact gather of one-picture segments; --parcat: the reference tool's behaviour (same argument order as `Parcat`)."""
+    import argparse
+    ap = argparse.ArgumentParser(description=main.__doc__)
+    ap.add_argument('--parcat', action='store_true', help='overlapping random-access segments, as APP/Parcat')
+    ap.add_argument('--concat', action='store_true', help='plain concatenation of self-contained segments')
+    ap.add_argument('--no-param-sets', action='store_true', help='bit-exact gather for ReWriteParamSets=0: parameter sets only ahead of the first picture')
+    ap.add_argument('files', nargs='+', help='segments in order, then the output file')
+    a = ap.parse_args(argv)
+    if len(a.files) < 2:
+        ap.error('need at least one segment and the output file')
+    segs, out = a.files[:-1], a.files[-1]
+    if a.parcat:
+        print('%d pictures re-numbered' % parcat_segments(segs, out))
+    elif a.concat:
+        print('%d segments, %d bytes' % (len(segs), sum(s['bytes'] for s in concat_segments(segs, out))))
+    else:
+        st = assemble_sequential(segs, out, rewrite_param_sets=not a.no_param_sets)
+        print('%d pictures, %d bytes' % (len(st), sum(s['bytes_out'] for s in st)))
+    return 0
+
+
+if __name__ == '__main__':
+    import sys
+    sys.exit(main())
