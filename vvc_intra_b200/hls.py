@@ -147,18 +147,13 @@ class BitWriter:
 
 
 def _ref_pic_list_struct(r, long_term, poc_bits, forbid_zero_delta):
-    """EL/VLCWriter.cpp:161-206.  Returns the number of entries (the gather only needs to step over the structure)."""
+    """EL/VLCWriter.cpp:161-206 for lists of short-term pictures.  Returns the number of entries (the gather only needs to step over the structure)."""
+    if long_term:
+        raise NotImplementedError('long-term reference pictures')
     n = r.ue()
-    lt_flags = []
     for _ in range(n):
-        st = r.flag() if long_term else 1          # st_ref_pic_flag is written only when the list holds long-term pictures; see the note below
-        lt_flags.append(not st)
-        if st:
-            a = r.ue() + (1 if forbid_zero_delta else 0)
-            if a > 0:
-                r.flag()
-        else:
-            r.u(poc_bits)
+        if r.ue() + (1 if forbid_zero_delta else 0) > 0:          # abs_delta_poc_st (minus 1 when a zero delta cannot occur: no weighted prediction)
+            r.flag()                                               # strp_entry_sign_flag
     return n
 
 
@@ -199,15 +194,13 @@ def parse_sps(rbsp):
     for forbid in (True, False):
         r.pos = start
         s['num_rpl0'] = r.ue()
-        if s['long_term_refs']:
-            raise NotImplementedError('long-term reference pictures')
         for _ in range(s['num_rpl0']):
-            _ref_pic_list_struct(r, False, s['poc_bits'], forbid)
+            _ref_pic_list_struct(r, s['long_term_refs'], s['poc_bits'], forbid)
         s['num_rpl1'] = s['num_rpl0']
         if not s['rpl1_copy']:
             s['num_rpl1'] = r.ue()
             for _ in range(s['num_rpl1']):
-                _ref_pic_list_struct(r, False, s['poc_bits'], forbid)
+                _ref_pic_list_struct(r, s['long_term_refs'], s['poc_bits'], forbid)
         try:
             _sps_after_lists(r, s)
         except ValueError:
