@@ -11,7 +11,9 @@ Three gathers, from the plainest to the bit-exact one:
   slice_pic_order_cnt_lsb = n, the reference-picture-list bits of a non-IDR picture, header re-aligned, emulation prevention redone -- so that the
   gathered stream is byte-identical to `EncoderApp -f <N>` (tests/test_assemble.py).  Nothing else differs: every CRA picture of an all-intra sequence
   has pending-RAS initialisation (EL/EncGOP.cpp:4213-4225), which resets the ALF APS ids (EL/EncAdaptiveLoopFilter.cpp:667-674) and the SAO state
-  exactly as an IDR does, and the parameter sets are re-sent with every IRAP picture (EL/EncGOP.cpp:2754-2759, ReWriteParamSets).
+  exactly as an IDR does, and the parameter sets are re-sent with every IRAP picture (EL/EncGOP.cpp:2754-2759, ReWriteParamSets).  The LMCS analysis
+  of an intra picture starts from that picture's own statistics with its state re-initialised (EL/EncReshape.cpp:564-789); the header reader steps over
+  slice_lmcs_aps_id, but no test stream has slice_lmcs_enabled_flag = 1 -- the reference switches LMCS off for all the synthetic content tried.
 * `parcat_segments`: what the reference's own APP/Parcat does with random-access segments that overlap by their IDR picture (parcat.cpp:247-384):
   parameter sets and the IDR picture of segments 2.. dropped, the POC of the other pictures advanced by the pictures gathered so far.  Checked byte for
   byte against the reference's Parcat binary.
