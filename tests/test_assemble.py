@@ -36,6 +36,19 @@ def test_bit_exact_gather_reproduces_the_sequential_encoder(tmp_path):
         assemble.assemble_sequential([paths[0], os.path.join(GOLD, 'pic_256x128_10b_qp27_seq.bin')], str(tmp_path / 'x.bin'))
 
 
+def test_bit_exact_gather_when_every_picture_carries_an_alf_aps(tmp_path):
+    """configs[0]'s picture size and QP (416x240 8-bit QP 32), two pictures, each with an ALF APS: the sequential encoder gives both id 7 -- the id counter
+    restarts with every CRA picture (pending-RAS initialisation, EL/EncGOP.cpp:4213-4225 -> EL/EncAdaptiveLoopFilter.cpp:667-674) -- so the per-picture
+    streams already carry the right ids and the gather is byte-identical."""
+    from vvc_intra_b200 import assemble, hls
+    paths = [os.path.join(GOLD, 'pic_416x240_8b_qp32_f%d.bin' % f) for f in range(2)]
+    assemble.assemble_sequential(paths, str(tmp_path / 'all.bin'))
+    seq = open(os.path.join(GOLD, 'pic_416x240_8b_qp32_seq.bin'), 'rb').read()
+    assert (tmp_path / 'all.bin').read_bytes() == seq
+    aps = [hls.BitReader(hls.unescape(u[2:])) for _, u in hls.split_nal_units(seq) if hls.nal_unit_type(u) == hls.NAL_APS]
+    assert [(r.u(5), r.u(3)) for r in aps] == [(7, 0), (7, 0)]            # adaptation_parameter_set_id, aps_params_type (ALF), EL/VLCWriter.cpp:493-513
+
+
 def test_parcat_segments_matches_the_reference_tool(tmp_path):
     from vvc_intra_b200 import assemble
     segs = [os.path.join(GOLD, 'seg_64x64_8b_qp32_s%d.bin' % k) for k in range(3)]
@@ -59,7 +72,7 @@ def test_syntax_reader_on_reference_streams():
             if t == hls.NAL_SPS:
                 s = hls.parse_sps(rbsp)
                 sps[s['sps_id']] = s
-                assert (s['width'], s['height'], s['poc_bits']) in ((256, 128, 8), (64, 64, 8)) and s['alf'] and s['sao'] and s['lmcs']
+                assert (s['width'], s['height'], s['poc_bits']) in ((256, 128, 8), (64, 64, 8), (416, 240, 8)) and s['alf'] and s['sao'] and s['lmcs']
             elif t == hls.NAL_PPS:
                 p = hls.parse_pps(rbsp, sps)
                 pps[p['pps_id']] = p

@@ -7,6 +7,8 @@ vvc_intra_b200/assemble.py.  Runs only in the build container (/root/reference p
 
   pic_256x128_10b_qp27_f<n>.bin   one encoder process per picture (-f 1 --FrameSkip=n), n = 0..3; picture 3 carries an ALF APS
   pic_256x128_10b_qp27_seq.bin    the sequential encoder over the same four pictures (-f 4): what assemble_sequential must reproduce
+  pic_416x240_8b_qp32_f<n>.bin    configs[0]'s picture size and QP, n = 0..1: BOTH pictures carry an ALF APS, with id 7 in the sequential stream too
+  pic_416x240_8b_qp32_seq.bin     (the APS id counter restarts with every CRA picture: pending-RAS initialisation)
   seg_64x64_8b_qp32_s<k>.bin      three-picture segments overlapping by one picture (-f 3 --FrameSkip=2k), k = 0..2
   seg_64x64_8b_qp32_parcat.bin    Parcat s0 s1 s2: what parcat_segments must reproduce (it also equals the sequential encoder's stream)"""
 import os
@@ -54,6 +56,13 @@ def main():
         for f in range(n):
             shutil.copy(os.path.join(tmp, 'f%d.bin' % f), os.path.join(OUT, 'pic_256x128_10b_qp27_f%d.bin' % f))
         shutil.copy(os.path.join(tmp, 'seq.bin'), os.path.join(OUT, 'pic_256x128_10b_qp27_seq.bin'))
+        w, h, bits, qp, n = 416, 240, 8, 32, 2
+        write_input(tmp, w, h, bits, n)
+        a = encoder_args(w, h, bits, qp)
+        run_all([a + ['-f', '1', '--FrameSkip=%d' % f, '-b', 'g%d.bin' % f] for f in range(n)] + [a + ['-f', str(n), '-b', 'gseq.bin']], tmp)
+        for f in range(n):
+            shutil.copy(os.path.join(tmp, 'g%d.bin' % f), os.path.join(OUT, 'pic_416x240_8b_qp32_f%d.bin' % f))
+        shutil.copy(os.path.join(tmp, 'gseq.bin'), os.path.join(OUT, 'pic_416x240_8b_qp32_seq.bin'))
         w, h, bits, qp, n = 64, 64, 8, 32, 7
         write_input(tmp, w, h, bits, n)
         a = encoder_args(w, h, bits, qp)
