@@ -49,6 +49,41 @@ def test_bit_exact_gather_when_every_picture_carries_an_alf_aps(tmp_path):
     assert [(r.u(5), r.u(3)) for r in aps] == [(7, 0), (7, 0)]            # adaptation_parameter_set_id, aps_params_type (ALF), EL/VLCWriter.cpp:493-513
 
 
+def test_library_gather_matches_the_reference_and_its_python_twin(tmp_path):
+    """include/vvc_intra_b200_gather.h: the C++ gather inside libvvc_intra_b200.so (host code; runs without a GPU) on the reference fixtures."""
+    import ctypes as C
+    import re
+    from vvc_intra_b200 import assemble, engine
+    lib = engine.load_library()
+    hdr = open(os.path.join(ROOT, 'include/vvc_intra_b200_gather.h')).read()
+    names = sorted(set(re.findall(r'\b(vvcb_gather_[a-z_]+)\s*\(', hdr)))
+    assert names == ['vvcb_gather_parcat', 'vvcb_gather_sequential'] and all(hasattr(lib, n) for n in names)
+    for stem, n in (('pic_256x128_10b_qp27', 4), ('pic_416x240_8b_qp32', 2)):
+        paths = [os.path.join(GOLD, '%s_f%d.bin' % (stem, f)) for f in range(n)]
+        seq = open(os.path.join(GOLD, stem + '_seq.bin'), 'rb').read()
+        assert assemble.gather_sequential(paths, str(tmp_path / 'lib.bin')) == len(seq)
+        assert (tmp_path / 'lib.bin').read_bytes() == seq
+        assemble.gather_sequential(paths, str(tmp_path / 'lib_lean.bin'), rewrite_param_sets=False)
+        assemble.assemble_sequential(paths, str(tmp_path / 'py_lean.bin'), rewrite_param_sets=False)
+        assert (tmp_path / 'lib_lean.bin').read_bytes() == (tmp_path / 'py_lean.bin').read_bytes()
+    segs = [os.path.join(GOLD, 'seg_64x64_8b_qp32_s%d.bin' % k) for k in range(3)]
+    assert assemble.gather_parcat(segs, str(tmp_path / 'pc.bin')) == 6
+    assert (tmp_path / 'pc.bin').read_bytes() == open(os.path.join(GOLD, 'seg_64x64_8b_qp32_parcat.bin'), 'rb').read()
+    # error behaviour: status codes and messages of the C ABI
+    with pytest.raises(ValueError, match='not a one-picture segment'):
+        assemble.gather_sequential([os.path.join(GOLD, 'pic_256x128_10b_qp27_seq.bin')], str(tmp_path / 'x.bin'))
+    with pytest.raises(ValueError, match='cannot open'):
+        assemble.gather_sequential([str(tmp_path / 'missing.bin')], str(tmp_path / 'x.bin'))
+    with pytest.raises(ValueError, match='cannot write'):
+        assemble.gather_parcat(segs, str(tmp_path / 'no_such_dir' / 'x.bin'))
+    (tmp_path / 'junk.bin').write_bytes(b'\x00\x00\x01\x91\x02' + bytes(20) + b'\x80')      # an SPS NAL unit of zeros
+    with pytest.raises(ValueError):
+        assemble.gather_parcat([str(tmp_path / 'junk.bin')], str(tmp_path / 'x.bin'))
+    err = C.create_string_buffer(64)
+    assert lib.vvcb_gather_sequential(None, 0, None, 1, None, err, 64) == -1 and b'bad argument' in err.value
+    assert lib.vvcb_gather_parcat(None, 0, None, None, None, 0) == -1                               # no message buffer: still a status
+
+
 def test_parcat_segments_matches_the_reference_tool(tmp_path):
     from vvc_intra_b200 import assemble
     segs = [os.path.join(GOLD, 'seg_64x64_8b_qp32_s%d.bin' % k) for k in range(3)]
@@ -164,3 +199,5 @@ def test_bit_exact_gather_across_encoder_options(w, h, bits, qp, extra, tmp_path
     assert all(p.wait() == 0 for p in procs)
     assemble.assemble_sequential([str(tmp_path / ('f%d.bin' % f)) for f in range(n)], str(tmp_path / 'all.bin'))
     assert (tmp_path / 'all.bin').read_bytes() == (tmp_path / 'seq.bin').read_bytes()
+    assemble.gather_sequential([str(tmp_path / ('f%d.bin' % f)) for f in range(n)], str(tmp_path / 'lib.bin'))      # the library's C++ gather
+    assert (tmp_path / 'lib.bin').read_bytes() == (tmp_path / 'seq.bin').read_bytes()

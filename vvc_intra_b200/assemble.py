@@ -39,6 +39,37 @@ def concat_segments(paths, out_path):
     return stats
 
 
+def _gather_call(name, paths, out_path, *extra):
+    """The library's gather entry points (include/vvc_intra_b200_gather.h): host code of libvvc_intra_b200.so, no CUDA device involved."""
+    import ctypes as C
+    from . import engine
+    lib = engine.load_library()
+    arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+    err = C.create_string_buffer(512)
+    rc = getattr(lib, name)(arr, len(paths), os.fsencode(out_path), *extra, err, len(err))
+    if rc == -3:
+        raise NotImplementedError(err.value.decode())
+    if rc != 0:
+        raise ValueError(err.value.decode())
+
+
+def gather_sequential(paths, out_path, rewrite_param_sets=True):
+    """vvcb_gather_sequential: the bit-exact gather done by the library (C++; `assemble_sequential` below is its Python twin, kept as the cross-check
+    of the tests and for the per-picture statistics).  Returns the number of bytes written."""
+    import ctypes as C
+    n = C.c_uint64(0)
+    _gather_call('vvcb_gather_sequential', list(paths), out_path, C.c_int(1 if rewrite_param_sets else 0), C.byref(n))
+    return n.value
+
+
+def gather_parcat(paths, out_path):
+    """vvcb_gather_parcat: the reference's Parcat done by the library (twin: `parcat_segments`).  Returns the number of pictures re-numbered."""
+    import ctypes as C
+    k = C.c_int(0)
+    _gather_call('vvcb_gather_parcat', list(paths), out_path, C.byref(k))
+    return k.value
+
+
 def diff_against_sequential(assembled, sequential):
     """NAL-by-NAL comparison of an assembled bitstream with the sequential encoder's: list of (index, type assembled, type sequential, bytes assembled,
     bytes sequential, number of differing bytes) for the units that differ."""
@@ -190,12 +221,11 @@ def main(argv=None):
         ap.error('need at least one segment and the output file')
     segs, out = a.files[:-1], a.files[-1]
     if a.parcat:
-        print('%d pictures re-numbered' % parcat_segments(segs, out))
+        print('%d pictures re-numbered' % gather_parcat(segs, out))
     elif a.concat:
         print('%d segments, %d bytes' % (len(segs), sum(s['bytes'] for s in concat_segments(segs, out))))
     else:
-        st = assemble_sequential(segs, out, rewrite_param_sets=not a.no_param_sets)
-        print('%d pictures, %d bytes' % (len(st), sum(s['bytes_out'] for s in st)))
+        print('%d pictures, %d bytes' % (len(segs), gather_sequential(segs, out, rewrite_param_sets=not a.no_param_sets)))
     return 0
 
 

@@ -1684,3 +1684,6 @@ extern "C" int vvcb_measure_int_peak(vvcb_ctx* ctx, double* gops_imad, double* g
   return VVCB_OK;
 }
 extern "C" uint64_t vvcb_launch_count(const vvcb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// the frame-parallel gather (include/vvc_intra_b200_gather.h): host code only
+#include "vvcb_gather.inc"

@@ -113,7 +113,7 @@ def encode_sequence(encoder, encoder_args, n_frames, out_path, devices=(0,), bit
                 stats['devices'].append(dict(json.loads(subprocess.check_output([broker_bin, path, '--stats'], env=env)), device=devices[r], pictures=len(per_device[r])))
             except (subprocess.CalledProcessError, ValueError):
                 stats['devices'].append({'device': devices[r], 'pictures': len(per_device[r])})
-        stats['gather'] = assemble.assemble_sequential([os.path.join(workdir, 'pic%06d.bin' % k) for k in units], out_path, rewrite_param_sets=rewrite_param_sets)
+        stats['gather_bytes'] = assemble.gather_sequential([os.path.join(workdir, 'pic%06d.bin' % k) for k in units], out_path, rewrite_param_sets=rewrite_param_sets)
         if recon_path:
             with open(recon_path, 'wb') as out:
                 for k in units:
