@@ -84,6 +84,21 @@ def test_library_gather_matches_the_reference_and_its_python_twin(tmp_path):
     assert lib.vvcb_gather_parcat(None, 0, None, None, None, 0) == -1                               # no message buffer: still a status
 
 
+def test_library_gather_survives_damaged_streams(tmp_path):
+    """Mutation fuzz of the C++ gather under AddressSanitizer + UBSan (tests/host_emul/gather_fuzz.cpp): bit flips, replaced bytes, truncations and
+    inserted bytes in reference streams must come back as status codes."""
+    exe = str(tmp_path / 'gather_fuzz')
+    r = subprocess.run(['g++', '-std=c++17', '-O1', '-g', '-fsanitize=address,undefined', '-fno-sanitize-recover=undefined', '-o', exe,
+                        os.path.join(ROOT, 'tests/host_emul/gather_fuzz.cpp')], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        pytest.skip('no sanitizer runtime for g++ here: ' + r.stdout[-300:])
+    streams = [os.path.join(GOLD, f) for f in ('pic_416x240_8b_qp32_f0.bin', 'pic_416x240_8b_qp32_f1.bin', 'seg_64x64_8b_qp32_s0.bin', 'seg_64x64_8b_qp32_s1.bin')]
+    r = subprocess.run([exe, '2500', str(tmp_path)] + streams, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    ok, refused, unsupported = (int(v) for v in r.stdout.split())
+    assert ok + refused + unsupported == 5000 and ok > 500 and refused > 500
+
+
 def test_parcat_segments_matches_the_reference_tool(tmp_path):
     from vvc_intra_b200 import assemble
     segs = [os.path.join(GOLD, 'seg_64x64_8b_qp32_s%d.bin' % k) for k in range(3)]

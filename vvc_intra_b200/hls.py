@@ -180,6 +180,8 @@ def parse_sps(rbsp):
     s['width'], s['height'] = r.ue(), r.ue()
     r.ue(); r.ue(); r.ue()                                           # bit depths, min_qp_prime_ts_minus4
     s['poc_bits'] = r.ue() + 4
+    if s['poc_bits'] > 16:
+        raise ValueError('log2_max_pic_order_cnt_lsb out of range')
     s['idr_rpl_present'] = r.flag()
     ordering = r.flag()
     for i in range(sub_layers):
