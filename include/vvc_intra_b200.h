@@ -351,6 +351,39 @@ void vvcb_mts_preselect(const int32_t* sums, int n, int width, int height, int m
  * (vvcb_tu_result::frac_bits + its own header bits).                                                                          */
 double vvcb_calc_rd_cost(double lambda, uint64_t frac_bits, uint64_t distortion);
 
+/* ---- intra sub-partitions (ISP): geometry of one luma CU (pure host logic; SURVEY 8 row f1, first slice) ----------------------------
+ * What the job builder of an ISP candidate needs before any kernel runs, as the reference derives it:
+ *   CU::canUseISP (CL/UnitTools.cpp:426)  -- log2w + log2h > 4 and neither side above max_tb_size;
+ *   CU::getISPSplitDim (:437) and PartitionerImpl::getTUIntraSubPartitions (CL/UnitPartitioner.cpp:978) -- 2 or 4 transform blocks,
+ *     each of at least 16 samples, stacked along the split direction;
+ *   CU::isPredRegDiffFromTB / isFirstTBInPredReg / adjustPredArea (CL/UnitTools.cpp:4334-4355) -- vertical split of a 4xN or 8xN (N > 4)
+ *     CU: the 1xN / 2xN transform blocks are predicted in regions 4 samples wide, at the first block of each region;
+ *   IntraPrediction::initIntraPatternChTypeISP (CL/IntraPrediction.cpp:1092-1203) -- reference-line lengths: the first region fetches
+ *     the lines of the whole CU once (fetch_*), every region then predicts with top = cu_w + pred_w, left = cu_h + pred_h samples;
+ *   TrQuant::getTrTypes (CL/TrQuant.cpp:752-783) -- ISP blocks take DST-VII in a direction of 4..16 samples, DCT-II otherwise
+ *     (DCT-II in both when the SPS switches MTS off: use_mts = sps.getUseMTS()).
+ * The evaluation kernels for these blocks (1xN / 2xN / Nx1 / Nx2 transforms, their scans and contexts) are NOT in the library yet:
+ * the served encoder hands ISP candidates to the reference code.                                                         */
+#define VVCB_ISP_NONE 0
+#define VVCB_ISP_HOR  1   /* HOR_INTRA_SUBPARTITIONS: blocks stacked top to bottom (TU_1D_HORZ_SPLIT) */
+#define VVCB_ISP_VER  2   /* VER_INTRA_SUBPARTITIONS: blocks side by side (TU_1D_VERT_SPLIT)          */
+#define VVCB_TR_DCT2  0   /* TransType (CL/TypeDef.h) */
+#define VVCB_TR_DCT8  1
+#define VVCB_TR_DST7  2
+#define VVCB_ISP_MAX_PARTS 4
+typedef struct vvcb_isp_part {
+  int16_t x, y, w, h;                      /* transform block, luma samples relative to the CU's top-left                          */
+  int16_t pred_x, pred_y, pred_w, pred_h;  /* prediction region the block lies in (== the block unless the 4-wide rule applies)     */
+  int16_t top_ref_len, left_ref_len;       /* m_topRefLength / m_leftRefLength while this region is predicted                       */
+  int16_t fetch_top_len, fetch_left_len;   /* first block only: lengths of the one xFillReferenceSamples over the CU; else 0        */
+  uint8_t predicts;                        /* 1: the region's prediction is made when this block is coded (isFirstTBInPredReg)      */
+  uint8_t tr_hor, tr_ver;                  /* VVCB_TR_*                                                                             */
+  uint8_t last;                            /* CU::isISPLast                                                                         */
+} vvcb_isp_part;                           /* 28 bytes */
+/* parts: room for VVCB_ISP_MAX_PARTS.  Returns the number of blocks (2 or 4), 0 when the CU may not use ISP (canUseISP false),
+ * VVCB_ERR_ARG for sizes that are not powers of two in 4..64, an isp_mode other than VVCB_ISP_HOR / VVCB_ISP_VER, or parts == NULL. */
+int vvcb_isp_plan(int cu_w, int cu_h, int isp_mode, int max_tb_size, int use_mts, vvcb_isp_part* parts);
+
 /* ---- texture features (orig-only, trivially parallel) ------------------------------------------------------------
  * vvcb_ctu_hads_islice: EncCu::updateCtuDataISlice (EL/EncCu.cpp:564-675) for every CTU of the frame, as
  * EncSlice::calCostSliceI calls it (EL/EncSlice.cpp:1276-1298): sum over the complete 8x8 blocks of the CTU's

@@ -1507,6 +1507,45 @@ extern "C" void vvcb_mts_preselect(const int32_t* sums, int n, int width, int he
   }
 }
 
+// host logic: geometry of an intra sub-partition CU (include/vvc_intra_b200.h; CL/UnitTools.cpp:426-460, :4334-4355,
+// CL/UnitPartitioner.cpp:978, CL/IntraPrediction.cpp:1092-1203, CL/TrQuant.cpp:752-783).  Everything follows from the two log2
+// sizes: a block keeps at least 16 samples, so along the split the CU is cut in four unless that would leave fewer (then in blocks
+// of 16 / other-side samples: two of them for 4x8 and 8x4).
+extern "C" int vvcb_isp_plan(int cu_w, int cu_h, int isp_mode, int max_tb_size, int use_mts, vvcb_isp_part* parts)
+{
+  auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) l++; return (1 << l) == v ? l : -1; };
+  const int lw = lg2(cu_w), lh = lg2(cu_h);
+  if (!parts || lw < 2 || lw > 6 || lh < 2 || lh > 6 || (isp_mode != VVCB_ISP_HOR && isp_mode != VVCB_ISP_VER)) return VVCB_ERR_ARG;
+  if (lw + lh <= 4 || cu_w > max_tb_size || cu_h > max_tb_size) return 0;
+  const bool hor = isp_mode == VVCB_ISP_HOR;
+  const int split = hor ? cu_h : cu_w, other = hor ? cu_w : cu_h;
+  const int floorSize = other < 16 ? 16 / other : 1;                 // smallest block extent that still holds 16 samples
+  const int size = (split >> 2) < floorSize ? floorSize : (split >> 2);
+  const int n = split / size;
+  // 4xN and 8xN (N > 4) cut vertically: blocks 1 or 2 samples wide, predicted four columns at a time
+  const bool wideRegions = !hor && (cu_w == 4 || (cu_w == 8 && cu_h > 4));
+  for (int i = 0; i < n; i++) {
+    vvcb_isp_part& p = parts[i];
+    p.x = int16_t(hor ? 0 : i * size); p.y = int16_t(hor ? i * size : 0);
+    p.w = int16_t(hor ? cu_w : size);  p.h = int16_t(hor ? size : cu_h);
+    p.pred_x = p.x; p.pred_y = p.y; p.pred_w = p.w; p.pred_h = p.h; p.predicts = 1;
+    if (wideRegions && size < 4) {
+      p.pred_x = int16_t(p.x & ~3); p.pred_w = 4;
+      p.predicts = (p.x & 3) == 0;
+    }
+    p.top_ref_len = int16_t(cu_w + p.pred_w); p.left_ref_len = int16_t(cu_h + p.pred_h);
+    p.fetch_top_len = p.fetch_left_len = 0;
+    if (i == 0) {
+      p.fetch_top_len  = int16_t(hor ? cu_w + p.pred_w : 2 * cu_w);
+      p.fetch_left_len = int16_t(hor ? 2 * cu_h : cu_h + p.pred_h);
+    }
+    p.tr_hor = uint8_t(use_mts && p.w >= 4 && p.w <= 16 ? VVCB_TR_DST7 : VVCB_TR_DCT2);
+    p.tr_ver = uint8_t(use_mts && p.h >= 4 && p.h <= 16 ? VVCB_TR_DST7 : VVCB_TR_DCT2);
+    p.last = i == n - 1;
+  }
+  return n;
+}
+
 static int feat_buf(vvcb_ctx* ctx, int i, size_t bytes)
 {
   if (bytes > ctx->capFeat[i]) {

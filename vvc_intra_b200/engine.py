@@ -74,6 +74,11 @@ class CuRequest(C.Structure):
 
 
 CU_AUTO_DTYPE = np.dtype([('job', TU_JOB_DTYPE), ('modes', 'u1'), ('skip_mip', 'u1'), ('pad', 'u1', 6)])
+# vvcb_isp_part (include/vvc_intra_b200.h): one transform block of an intra sub-partition CU
+ISP_PART_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('w', '<i2'), ('h', '<i2'), ('pred_x', '<i2'), ('pred_y', '<i2'), ('pred_w', '<i2'), ('pred_h', '<i2'),
+                           ('top_ref_len', '<i2'), ('left_ref_len', '<i2'), ('fetch_top_len', '<i2'), ('fetch_left_len', '<i2'),
+                           ('predicts', 'u1'), ('tr_hor', 'u1'), ('tr_ver', 'u1'), ('last', 'u1')])
+ISP_HOR, ISP_VER, TR_DCT2, TR_DCT8, TR_DST7 = 1, 2, 0, 1, 2
 assert CU_AUTO_DTYPE.itemsize == 40
 AUTO_FINAL, AUTO_REGULAR = 1, 2
 
@@ -131,6 +136,7 @@ def load_library():
         L.vvcb_mts_preselect.restype = None
         L.vvcb_calc_rd_cost.argtypes = [C.c_double, C.c_uint64, C.c_uint64]
         L.vvcb_calc_rd_cost.restype = C.c_double
+        L.vvcb_isp_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vvcb_ctu_hads_islice.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.vvcb_features_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.vvcb_frame_bind_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -407,6 +413,17 @@ class IntraCostEngine:
     def calc_rd_cost(lam, frac_bits, distortion):
         """vvcb_calc_rd_cost: RdCost::calcRdCost (pure host logic, no context needed)."""
         return float(load_library().vvcb_calc_rd_cost(float(lam), int(frac_bits), int(distortion)))
+
+    @staticmethod
+    def isp_plan(cu_w, cu_h, isp_mode, max_tb_size=64, use_mts=True):
+        """vvcb_isp_plan: transform blocks, prediction regions, reference-line lengths and transform types of an intra sub-partition
+        CU (CU::canUseISP / getISPSplitDim, getTUIntraSubPartitions, initIntraPatternChTypeISP, TrQuant::getTrTypes).  Pure host logic.
+        Returns an ISP_PART_DTYPE array, empty when the CU may not use ISP."""
+        parts = np.zeros(4, ISP_PART_DTYPE)
+        n = load_library().vvcb_isp_plan(int(cu_w), int(cu_h), int(isp_mode), int(max_tb_size), int(bool(use_mts)), _ptr(parts))
+        if n < 0:
+            raise EngineError('vvcb_isp_plan: bad argument (sizes are powers of two in 4..64, isp_mode 1 = horizontal or 2 = vertical)')
+        return parts[:n]
 
     def mts_preselect(self, sums, width, height, max_cand):
         sums = np.ascontiguousarray(sums, np.int32)
