@@ -98,3 +98,19 @@ def test_calc_rd_cost_is_the_reference_formula(built):
         scale = float(1 << 15) / lam
         assert built.IntraCostEngine.calc_rd_cost(lam, bits, dist) == scale * float(dist) + float(bits)
     assert built.IntraCostEngine.calc_rd_cost(57.0, 0, 0) == 0.0
+
+
+def test_calc_rd_cost_matches_the_reference_function(built):
+    """Bit patterns of RdCost::calcRdCost as the UNMODIFIED reference computes it (tests/golden/rd_cost.txt, written by
+    oracle/dump_rd_cost.cpp through oracle/_ref/libvtmref.a: setLambda + saveUnadjustedLambda + calcRdCost, CL/RdCost.cpp:63-88)."""
+    import struct
+    n = 0
+    for line in open(os.path.join(ROOT, 'tests/golden/rd_cost.txt')):
+        if line.startswith('#'):
+            continue
+        lam_bits, bits, dist, cost_bits = line.split()
+        lam = struct.unpack('<d', struct.pack('<Q', int(lam_bits, 16)))[0]
+        got = built.IntraCostEngine.calc_rd_cost(lam, int(bits), int(dist))
+        assert struct.unpack('<Q', struct.pack('<d', got))[0] == int(cost_bits, 16), line
+        n += 1
+    assert n == 600
