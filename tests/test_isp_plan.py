@@ -95,7 +95,7 @@ def test_plan_properties(eng):
 
 def test_bad_arguments_are_refused(eng):
     E = eng.IntraCostEngine
-    for args in ((12, 8, 1), (8, 128, 1), (2, 8, 2), (8, 8, 0), (8, 8, 3)):
+    for args in ((12, 8, 1), (8, 128, 1), (1 << 30, 8, 1), (8, 2147483647, 2), (-8, 8, 1), (2, 8, 2), (8, 8, 0), (8, 8, 3)):
         with pytest.raises(eng.EngineError):
             E.isp_plan(*args)
 

@@ -1513,7 +1513,7 @@ extern "C" void vvcb_mts_preselect(const int32_t* sums, int n, int width, int he
 // of 16 / other-side samples: two of them for 4x8 and 8x4).
 extern "C" int vvcb_isp_plan(int cu_w, int cu_h, int isp_mode, int max_tb_size, int use_mts, vvcb_isp_part* parts)
 {
-  auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) l++; return (1 << l) == v ? l : -1; };
+  auto lg2 = [](int v) { int l = 0; if (v > 64) return -1; while ((1 << l) < v) l++; return (1 << l) == v ? l : -1; };
   const int lw = lg2(cu_w), lh = lg2(cu_h);
   if (!parts || lw < 2 || lw > 6 || lh < 2 || lh > 6 || (isp_mode != VVCB_ISP_HOR && isp_mode != VVCB_ISP_VER)) return VVCB_ERR_ARG;
   if (lw + lh <= 4 || cu_w > max_tb_size || cu_h > max_tb_size) return 0;
