@@ -232,3 +232,10 @@ extern "C" int emul_residual_bits(const vvcb_tu_job* jobs, int n, const int32_t*
   emu_launch(2, kRateThreads, [&] { rate_kernel(R); });
   return 0;
 }
+
+// make_mode_param (vvcb_core.cuh): the per (shape, mode, reference line) prediction parameters the library's ROM is built from
+extern "C" void emul_mode_param(int w, int h, int mode, int mrl, int32_t* out)
+{
+  const ModeParam p = make_mode_param(w, h, mode, mrl);
+  out[0] = p.is_ver; out[1] = p.ref_filter; out[2] = p.interp; out[3] = p.pdpc; out[4] = p.angle; out[5] = p.inv_angle; out[6] = p.ang_scale;
+}

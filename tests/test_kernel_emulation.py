@@ -306,3 +306,30 @@ def test_emulated_rate_kernel_matches_reference(emul, name):
     got = run_emul_rate(emul, jobs, levels, states)
     bad = [(r['w'], r['h'], r['mts'], int(g), r['bits']) for g, r in zip(got, recs) if int(g) != r['bits']]
     assert not bad, (len(bad), bad[:5])
+
+
+def test_mode_params_match_the_reference_function(emul):
+    """make_mode_param (vvcb_core.cuh, the source the library's parameter ROM is built from) against the UNMODIFIED reference's compiled
+    IntraPrediction::initPredIntraParams (CL/IntraPrediction.cpp:487-618) for 17 shapes x 67 modes x reference lines 0 / 1 / 3:
+    tests/golden/intra_params.txt.gz, written by oracle/dump_intra_params.cpp through oracle/_ref/libvtmref.a."""
+    import gzip
+    emul.emul_mode_param.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    out = np.zeros(7, np.int32)
+    n = 0
+    shapes = set()
+    for line in gzip.open(os.path.join(ROOT, 'tests/golden/intra_params.txt.gz'), 'rt'):
+        if line.startswith('#'):
+            continue
+        head, _, tail = line.partition('|')
+        w, h, mode, mrl = (int(v) for v in head.split())
+        is_ver, ref_filter, interp, pdpc, angle, inv_angle, scale = (int(v) for v in tail.split())
+        emul.emul_mode_param(w, h, mode, mrl, out.ctypes.data_as(C.c_void_p))
+        key = (w, h, mode, mrl)
+        assert (out[0], out[1], out[2], out[3]) == (is_ver, ref_filter, interp, pdpc), key
+        if mode > 1:                              # the reference leaves the angle fields untouched for planar / DC
+            assert (out[4], out[5]) == (angle, inv_angle), key
+            if angle > 0 and pdpc:                # angularScale is only written for positive angles and only read with PDPC
+                assert out[6] == scale, key
+        n += 1
+        shapes.add((w, h))
+    assert len(shapes) == 17 and n == 17 * (67 + 66 + 66)
