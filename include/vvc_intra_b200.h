@@ -383,6 +383,18 @@ typedef struct vvcb_isp_part {
 /* parts: room for VVCB_ISP_MAX_PARTS.  Returns the number of blocks (2 or 4), 0 when the CU may not use ISP (canUseISP false),
  * VVCB_ERR_ARG for sizes that are not powers of two in 4..64, an isp_mode other than VVCB_ISP_HOR / VVCB_ISP_VER, or parts == NULL. */
 int vvcb_isp_plan(int cu_w, int cu_h, int isp_mode, int max_tb_size, int use_mts, vvcb_isp_part* parts);
+/* IntraPrediction::initPredIntraParams (CL/IntraPrediction.cpp:487-618) for a prediction region (vvcb_isp_part::pred_w x pred_h) of an ISP CU and
+ * one luma mode 0..66: the wide-angle remap takes the CU's shape, PDPC (regions of at least 4x4 only) and its scale the region's; the reference
+ * lines are never smoothed and the interpolation is the cubic one (refFilterFlag = interpolationFlag = false), reference line 0.               */
+typedef struct vvcb_isp_mode {
+  int16_t  angle;       /* intraPredAngle, 0 for planar / DC                       */
+  uint16_t inv_angle;   /* invAngle                                                */
+  uint8_t  is_ver;      /* isModeVer (after the wide-angle remap)                  */
+  uint8_t  pdpc;        /* applyPDPC                                               */
+  int8_t   ang_scale;   /* angularScale, meaningful for positive angles with pdpc  */
+  uint8_t  pad;
+} vvcb_isp_mode;        /* 8 bytes */
+int vvcb_isp_mode_param(int cu_w, int cu_h, int pred_w, int pred_h, int mode, vvcb_isp_mode* out);
 
 /* ---- texture features (orig-only, trivially parallel) ------------------------------------------------------------
  * vvcb_ctu_hads_islice: EncCu::updateCtuDataISlice (EL/EncCu.cpp:564-675) for every CTU of the frame, as

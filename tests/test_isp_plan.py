@@ -107,3 +107,38 @@ def test_struct_size_matches_header(eng):
     out = int(subprocess.check_output([exe]))
     os.remove(exe)
     assert out == eng.ISP_PART_DTYPE.itemsize == 28
+
+
+def test_isp_mode_params_match_the_reference_function(eng):
+    """vvcb_isp_mode_param against the UNMODIFIED reference's compiled IntraPrediction::initPredIntraParams with cu.ispMode set, for the
+    prediction regions of every ISP CU shape x both splits x 67 modes (the ISP part of tests/golden/intra_params.txt.gz, written by
+    oracle/dump_intra_params.cpp).  The region sizes of the table are the ones vvcb_isp_plan returns."""
+    import gzip
+    E = eng.IntraCostEngine
+    n = 0
+    regions = {}
+    for line in gzip.open(os.path.join(ROOT, 'tests/golden/intra_params.txt.gz'), 'rt'):
+        if not line.startswith('ISP'):
+            continue
+        head, _, tail = line[3:].partition('|')
+        w, h, split, pw, ph, mode = (int(v) for v in head.split())
+        is_ver, ref_filter, interp, pdpc, angle, inv_angle, scale = (int(v) for v in tail.split())
+        if (w, h, split) not in regions:
+            regions[(w, h, split)] = E.isp_plan(w, h, split)[0]
+        first = regions[(w, h, split)]
+        assert (first['pred_w'], first['pred_h']) == (pw, ph)
+        p = E.isp_mode_param(w, h, pw, ph, mode)
+        key = (w, h, split, pw, ph, mode)
+        assert (ref_filter, interp) == (0, 0), key          # never smoothed, cubic interpolation: what the header promises
+        assert (p['is_ver'], p['pdpc']) == (is_ver, pdpc), key
+        if mode > 1:
+            assert (p['angle'], p['inv_angle']) == (angle, inv_angle), key
+            if angle > 0 and pdpc:
+                assert p['ang_scale'] == scale, key
+        else:
+            assert p['angle'] == 0
+        n += 1
+    assert n == 48 * 67 and len(regions) == 48
+    for args in ((8, 8, 16, 2, 5), (8, 8, 8, 2, 67), (6, 8, 2, 8, 3), (128, 8, 8, 8, 3)):
+        with pytest.raises(eng.EngineError):
+            E.isp_mode_param(*args)

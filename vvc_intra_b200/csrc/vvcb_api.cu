@@ -1546,6 +1546,16 @@ extern "C" int vvcb_isp_plan(int cu_w, int cu_h, int isp_mode, int max_tb_size, 
   return n;
 }
 
+// host logic: prediction parameters of one mode for a prediction region of an ISP CU (include/vvc_intra_b200.h)
+extern "C" int vvcb_isp_mode_param(int cu_w, int cu_h, int pred_w, int pred_h, int mode, vvcb_isp_mode* out)
+{
+  auto pow2 = [](int v, int lo) { return v >= lo && v <= 64 && (v & (v - 1)) == 0; };
+  if (!out || !pow2(cu_w, 4) || !pow2(cu_h, 4) || !pow2(pred_w, 1) || !pow2(pred_h, 1) || pred_w > cu_w || pred_h > cu_h || mode < 0 || mode > 66) return VVCB_ERR_ARG;
+  const ModeParam p = make_mode_param_isp(cu_w, cu_h, pred_w, pred_h, mode);
+  out->angle = p.angle; out->inv_angle = p.inv_angle; out->is_ver = p.is_ver; out->pdpc = p.pdpc; out->ang_scale = p.ang_scale; out->pad = 0;
+  return VVCB_OK;
+}
+
 static int feat_buf(vvcb_ctx* ctx, int i, size_t bytes)
 {
   if (bytes > ctx->capFeat[i]) {

@@ -140,6 +140,23 @@ VHD ModeParam make_mode_param(int w, int h, int mode, int mrl)
   return p;
 }
 
+// initPredIntraParams for a prediction region (pw x ph) of an intra sub-partition CU (cuW x cuH): the wide-angle remap takes the CU's
+// shape, PDPC and its scale the region's; no reference smoothing, cubic interpolation only, reference line 0 (CL/IntraPrediction.cpp:
+// 492-511, :544-551, :558-574 with JVET_O0502_ISP_CLEANUP).  Host side of vvcb_isp_mode_param.
+VHD ModeParam make_mode_param_isp(int cuW, int cuH, int pw, int ph, int mode)
+{
+  ModeParam p = make_mode_param(cuW, cuH, mode, 1);      // reference line 1: angle fields only, no filters, no PDPC
+  p.pdpc = pw >= 4 && ph >= 4;
+  p.ang_scale = 0;
+  if (mode > 1 && p.angle < 0) p.pdpc = 0;
+  else if (mode > 1 && p.angle > 0) {
+    const int sc = vmin(2, vlog2(p.is_ver ? ph : pw) - (vlog2(3 * p.inv_angle - 2) - 8));
+    p.ang_scale = (int8_t)sc;
+    p.pdpc = p.pdpc && sc >= 0;
+  }
+  return p;
+}
+
 VHD int mip_num_modes(int w, int h)
 {
   if (w > 4 * h || h > 4 * w) return 0;

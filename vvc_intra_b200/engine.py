@@ -78,6 +78,7 @@ CU_AUTO_DTYPE = np.dtype([('job', TU_JOB_DTYPE), ('modes', 'u1'), ('skip_mip', '
 ISP_PART_DTYPE = np.dtype([('x', '<i2'), ('y', '<i2'), ('w', '<i2'), ('h', '<i2'), ('pred_x', '<i2'), ('pred_y', '<i2'), ('pred_w', '<i2'), ('pred_h', '<i2'),
                            ('top_ref_len', '<i2'), ('left_ref_len', '<i2'), ('fetch_top_len', '<i2'), ('fetch_left_len', '<i2'),
                            ('predicts', 'u1'), ('tr_hor', 'u1'), ('tr_ver', 'u1'), ('last', 'u1')])
+ISP_MODE_DTYPE = np.dtype([('angle', '<i2'), ('inv_angle', '<u2'), ('is_ver', 'u1'), ('pdpc', 'u1'), ('ang_scale', 'i1'), ('pad', 'u1')])
 ISP_HOR, ISP_VER, TR_DCT2, TR_DCT8, TR_DST7 = 1, 2, 0, 1, 2
 assert CU_AUTO_DTYPE.itemsize == 40
 AUTO_FINAL, AUTO_REGULAR = 1, 2
@@ -137,6 +138,7 @@ def load_library():
         L.vvcb_calc_rd_cost.argtypes = [C.c_double, C.c_uint64, C.c_uint64]
         L.vvcb_calc_rd_cost.restype = C.c_double
         L.vvcb_isp_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.vvcb_isp_mode_param.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.vvcb_ctu_hads_islice.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.vvcb_features_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.vvcb_frame_bind_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -424,6 +426,14 @@ class IntraCostEngine:
         if n < 0:
             raise EngineError('vvcb_isp_plan: bad argument (sizes are powers of two in 4..64, isp_mode 1 = horizontal or 2 = vertical)')
         return parts[:n]
+
+    @staticmethod
+    def isp_mode_param(cu_w, cu_h, pred_w, pred_h, mode):
+        """vvcb_isp_mode_param: initPredIntraParams for a prediction region of an ISP CU (pure host logic).  Returns an ISP_MODE_DTYPE record."""
+        out = np.zeros(1, ISP_MODE_DTYPE)
+        if load_library().vvcb_isp_mode_param(int(cu_w), int(cu_h), int(pred_w), int(pred_h), int(mode), _ptr(out)) != 0:
+            raise EngineError('vvcb_isp_mode_param: bad argument')
+        return out[0]
 
     def mts_preselect(self, sums, width, height, max_cand):
         sums = np.ascontiguousarray(sums, np.int32)
